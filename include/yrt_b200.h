@@ -1,0 +1,188 @@
+/*
+ * yrt_b200.h — C ABI of the B200-native render path (libyrt_b200.so).
+ *
+ * The reference (sebcossu/yocto_raytracing) has no plugin / FFI interface; its hot
+ * path is the C++ call pair in main():
+ *     build_bvh(scn, false);                                  src/raytrace.cpp:278  (decl src/scene.h:238)
+ *     auto hdr = raytrace(scn, {amb,amb,amb}, resolution, samples);   src/raytrace.cpp:282  (def :213)
+ * This header is what a maintainer binds instead of those two calls: the host keeps
+ * load_scene() (src/scene.cpp:113) and save_hdr_or_ldr() (src/image.cpp:81), flattens
+ * the loaded `scene` (src/scene.h:136-155) into the SoA `yrt_scene_desc` below and
+ * calls yrt_scene_create() + yrt_render().  See INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *  - plain C, plain pointers and sizes; no CUDA / torch types in any signature
+ *    (a CUDA stream crosses as `void*`, a device pointer as `void*`).
+ *  - all `const T*` inputs are HOST memory borrowed for the duration of the call.
+ *  - every function returning int returns YRT_OK (0) or a negative yrt_status;
+ *    yrt_last_error() gives the message (thread-local).  The reference's own error
+ *    convention is printf + exit(1) (src/scene.cpp:119-122); the host shim mirrors it.
+ *  - there is NO CPU fallback: without a usable CUDA device every compute entry point
+ *    fails with YRT_ERR_NO_DEVICE.
+ */
+#ifndef YRT_B200_H_
+#define YRT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YRT_ABI_VERSION 1
+
+typedef enum yrt_status {
+    YRT_OK = 0,
+    YRT_ERR_INVALID = -1,      /* bad argument / malformed scene description        */
+    YRT_ERR_NO_DEVICE = -2,    /* no CUDA device, or fewer than requested            */
+    YRT_ERR_CUDA = -3,         /* a CUDA runtime call or kernel failed               */
+    YRT_ERR_UNSUPPORTED = -4,  /* valid input the path does not cover (see message)  */
+    YRT_ERR_OOM = -5
+} yrt_status;
+
+/* element kind of a shape: the reference keeps three index vectors per shape
+ * (src/scene.h:36-38) and dispatches triangles > lines > points (src/scene.cpp:405-427);
+ * every shape the loader produces holds exactly one kind, which is what we require. */
+enum { YRT_TRIANGLES = 0, YRT_LINES = 1, YRT_POINTS = 2 };
+
+/*
+ * Flattened scene (replaces the pointer graph `scene`, src/scene.h:136-155).
+ * SoA, int32 ids, float32 data.  Vertex indices in elem_idx are LOCAL to the shape
+ * (0 .. shape_vert_cnt-1), exactly the values held in shape::triangles/lines/points.
+ */
+typedef struct yrt_scene_desc {
+    int32_t n_shapes, n_instances, n_materials, n_textures;
+    int32_t n_verts;      /* total vertices over all shapes                       */
+    int32_t n_elem_idx;   /* total ints in elem_idx (3 / 2 / 1 per element)        */
+
+    /* per shape [n_shapes]  (src/scene.h:26-50) */
+    const int32_t* shape_kind;      /* YRT_TRIANGLES / YRT_LINES / YRT_POINTS        */
+    const int32_t* shape_elem_off;  /* first int of this shape in elem_idx           */
+    const int32_t* shape_elem_cnt;  /* number of ELEMENTS                            */
+    const int32_t* shape_vert_off;  /* first vertex of this shape in pos/norm/…      */
+    const int32_t* shape_vert_cnt;
+    const int32_t* shape_has_uv;    /* 0: shape::texcoord empty -> uv := (0,0)       */
+    const int32_t* shape_has_radius;/* 0: shape::radius empty (triangles)            */
+
+    const int32_t* elem_idx;        /* [n_elem_idx]                                  */
+    const float* pos;               /* [3*n_verts]  shape::pos                       */
+    const float* norm;              /* [3*n_verts]  shape::norm (tangent for lines)  */
+    const float* uv;                /* [2*n_verts]  shape::texcoord, 0 where absent  */
+    const float* radius;            /* [n_verts]    shape::radius,   0 where absent  */
+
+    /* per instance [n_instances]  (src/scene.h:99-111), in scn->instances order */
+    const float* inst_frame;        /* 12 floats each: x, y, z, o (src/vmath.h:145)  */
+    const int32_t* inst_shape;      /* index into shapes                             */
+    const int32_t* inst_mat;        /* index into materials                          */
+
+    /* per material [n_materials]  (src/scene.h:62-87) */
+    const float* mat_ke;            /* 3 each */
+    const float* mat_kd;
+    const float* mat_ks;
+    const float* mat_kr;
+    const float* mat_rs;            /* 1 each; ns is derived on the host like src/raytrace.cpp:144 */
+    const int32_t* mat_kd_tex;      /* texture index or -1 */
+    const int32_t* mat_ks_tex;
+
+    /* per texture [n_textures]: texture::ldr (src/scene.h:54-58), RGBA8 row-major  */
+    const int32_t* tex_w;
+    const int32_t* tex_h;
+    const int64_t* tex_off;         /* byte offset of texel (0,0) in tex_rgba8       */
+    const uint8_t* tex_rgba8;
+    int64_t tex_bytes;
+} yrt_scene_desc;
+
+/* camera (src/scene.h:115-123); only cameras.front() is used (src/raytrace.cpp:215) */
+typedef struct yrt_camera {
+    float frame[12];   /* x, y, z, o */
+    float fovy, aspect, aperture, focus;
+} yrt_camera;
+
+/* per-frame counters and timings filled by the render entry points (optional) */
+typedef struct yrt_stats {
+    int64_t primary_rays;     /* intersect_first calls the reference would make from raytrace() */
+    int64_t reflection_rays;  /* intersect_first calls from recursive shade()                   */
+    int64_t shadow_rays;      /* intersect_any calls                                            */
+    int64_t launches;         /* kernels of this library launched for the frame                 */
+    float ms_total;           /* CUDA-event time of the whole call on the device(s), max        */
+    float ms_trace_closest;   /* sum over launches, device 0                                    */
+    float ms_trace_any;
+    float ms_shade;
+    float ms_other;
+    float ms_gather;          /* multi-GPU framebuffer gather                                   */
+    int32_t max_depth;        /* deepest reflection recursion reached                           */
+    int32_t n_gpus;
+} yrt_stats;
+
+typedef struct yrt_scene yrt_scene;   /* opaque: device-resident scene + LBVH on every initialised GPU */
+
+/* ---- library / device management ------------------------------------------------ */
+int yrt_abi_version(void);
+const char* yrt_last_error(void);
+/* number of CUDA devices visible (0 if none / no driver); never fails */
+int yrt_device_count(void);
+/* use devices 0..n_gpus-1 for the in-process path (yrt_render); n_gpus<=0 means 1.
+ * May be called again to change the set while no scene is alive. */
+int yrt_init(int n_gpus);
+/* use exactly this device (one process per GPU: torchrun ranks pass LOCAL_RANK) */
+int yrt_init_device(int device);
+
+/* ---- scene ----------------------------------------------------------------------- */
+/* replaces build_bvh(scn,false) (src/raytrace.cpp:278): validates, uploads to every
+ * initialised GPU and builds the two-level LBVH there (Morton + radix sort + Karras). */
+int yrt_scene_create(const yrt_scene_desc* desc, yrt_scene** out);
+void yrt_scene_destroy(yrt_scene* scn);
+/* build facts: out[0]=blas nodes, [1]=tlas nodes, [2]=blas max depth, [3]=tlas max depth,
+ * [4]=lights, [5]=prims, [6]=build microseconds (device 0), [7]=reflective materials */
+int yrt_scene_info(const yrt_scene* scn, int64_t out[8]);
+
+/* image width the reference derives from the camera: (int)std::round(aspect*resolution)
+ * (src/raytrace.cpp:216) */
+int yrt_image_width(const yrt_camera* cam, int resolution);
+
+/* ---- render ---------------------------------------------------------------------- */
+/* replaces raytrace(scn, amb, resolution, samples) (src/raytrace.cpp:213-254).
+ * `samples` is the per-axis count N (N*N samples per pixel, src/raytrace.cpp:232-234).
+ * rgba_out: HOST buffer, width*height*4 floats, row-major pixels[j*width+i] like image4f
+ * (src/image.h:15).  Uses every GPU given to yrt_init (interleaved row tiles, gathered
+ * on device 0, one device->host copy). */
+int yrt_render(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height,
+               int samples, float* rgba_out, yrt_stats* stats);
+
+/* Same frame, device-resident, for one-process-per-GPU drivers: renders only the rows
+ * owned by `rank` of `world` (row tile t of `tile_rows` rows belongs to rank t % world)
+ * into d_rgba (DEVICE pointer on the current yrt device) holding the rank's rows packed in
+ * increasing row order: yrt_rows_owned(height,tile_rows,rank,world)*width*4 floats.
+ * stream: cudaStream_t as void* (NULL = default stream).  Asynchronous w.r.t. the host
+ * unless stats != NULL. */
+int yrt_render_rows(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height,
+                    int samples, int tile_rows, int rank, int world, void* d_rgba, void* stream,
+                    yrt_stats* stats);
+int yrt_rows_owned(int height, int tile_rows, int rank, int world);
+/* scatter a rank's packed rows into the full row-major framebuffer (both DEVICE pointers) */
+int yrt_unpack_rows(const void* d_packed, void* d_full, int width, int height, int tile_rows,
+                    int rank, int world, void* stream);
+
+/* parity hook for the closest-hit metric: for every primary ray, in the order
+ * ((j*width+i)*samples+jj)*samples+ii, ids_out[3*r+0..2] = (instance index in
+ * scn->instances, shape index in scn->shapes, element index ei) or (-1,-1,-1) on a miss;
+ * dist_out[r] = hit distance (intersection3f::dist, src/scene.h:231) or 0.  HOST buffers;
+ * dist_out / uv_out (2 floats per ray: ew.y, ew.z for triangles, ew.y for lines) may be NULL. */
+int yrt_trace_primary(yrt_scene* scn, const yrt_camera* cam, int width, int height, int samples,
+                      int32_t* ids_out, float* dist_out, float* uv_out);
+
+/* generic ray queries (intersect_first / intersect_any, src/scene.cpp:483-494) on HOST arrays
+ * of n rays: rays = 8 floats each (o.xyz, d.xyz, tmin, tmax).  ids_out as above (closest) or
+ * occluded_out[n] bytes (any). */
+int yrt_intersect_first(yrt_scene* scn, const float* rays, int64_t n, int32_t* ids_out,
+                        float* dist_out, float* uv_out);
+int yrt_intersect_any(yrt_scene* scn, const float* rays, int64_t n, uint8_t* occluded_out);
+
+/* next-row: tonemap (src/image.cpp:55-78, exposure 0, no filmic, sRGB 1/2.2,
+ * truncating) of a HOST float image into HOST RGBA8, computed on the device. */
+int yrt_tonemap(const float* rgba_in, int width, int height, uint8_t* rgba8_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YRT_B200_H_ */

@@ -1,0 +1,67 @@
+"""ctypes binding of tests/host_emu/libyrt_hostemu.so (device code compiled for the CPU; tests only)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from yocto_raytracing_b200 import _lib
+
+_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu", "libyrt_hostemu.so")
+
+
+def available():
+    return os.path.exists(_PATH)
+
+
+_emu = None
+
+
+def lib():
+    global _emu
+    if _emu is None:
+        _emu = C.CDLL(_PATH)
+        _emu.emu_last_error.restype = C.c_char_p
+    return _emu
+
+
+class EmuScene:
+    def __init__(self, flat, leaf_blas=0, leaf_tlas=0):
+        self.flat = flat
+        self._desc = flat.desc()
+        self.h = C.c_void_p()
+        st = lib().emu_scene_create(C.byref(self._desc), leaf_blas, leaf_tlas, C.byref(self.h))
+        if st != 0:
+            raise RuntimeError(lib().emu_last_error().decode())
+
+    def info(self):
+        out = (C.c_int64 * 8)()
+        lib().emu_scene_info(self.h, out)
+        return list(out)
+
+    def trace_primary(self, width, height, samples):
+        n = width * height * samples * samples
+        ids = np.empty((n, 3), np.int32)
+        dist = np.empty(n, np.float32)
+        uv = np.empty((n, 2), np.float32)
+        ctr = (C.c_int64 * 4)()
+        cam = self.flat.camera_struct()
+        st = lib().emu_trace_primary(self.h, C.byref(cam), width, height, samples, C.c_void_p(ids.ctypes.data),
+                                     C.c_void_p(dist.ctypes.data), C.c_void_p(uv.ctypes.data), ctr)
+        assert st == 0
+        return ids, dist, uv, list(ctr)
+
+    def render(self, width, height, samples, amb=0.1, max_depth=16):
+        img = np.empty((height, width, 4), np.float32)
+        cam = self.flat.camera_struct()
+        a = (C.c_float * 3)(amb, amb, amb)
+        rc = (C.c_int64 * 3)()
+        st = lib().emu_render(self.h, C.byref(cam), a, width, height, samples, max_depth, C.c_void_p(img.ctypes.data), rc)
+        assert st == 0
+        return img, list(rc)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().emu_scene_destroy(self.h)
+        except Exception:
+            pass

@@ -1,0 +1,289 @@
+// host_emu.cu — TEST INFRASTRUCTURE, never part of the product path.
+//
+// Compiles the __host__ __device__ code of yocto_raytracing_b200/csrc (math, LBVH item functions,
+// traversal, shading) for the CPU and drives it with plain loops, so that the device logic can be
+// checked against the reference where there is no GPU: same Morton keys / Karras topology / refit
+// / node emit as the CUDA build (std::stable_sort stands in for the device radix sort), same
+// trace_ray / shade_hit code as the kernels.  libyrt_b200.so never links or calls this.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "yrt_internal.h"
+#include "yrt_shade.cuh"
+#include "yrt_trace.cuh"
+
+using namespace yrt;
+
+namespace {
+
+struct EmuLbvh {
+    std::vector<float4> nodes;
+    std::vector<int> order, seg_root, seg_depth, seg_box_lo, seg_box_hi;
+};
+
+void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi, const int* seg_of, const int* seg_first, int leaf_size,
+              EmuLbvh& out) {
+    size_t ni = n > 1 ? n - 1 : 1;
+    std::vector<int> cent_lo(3 * n_seg), cent_hi(3 * n_seg);
+    out.seg_box_lo.assign(3 * n_seg, 0);
+    out.seg_box_hi.assign(3 * n_seg, 0);
+    std::vector<unsigned long long> keys(std::max(n, 1));
+    out.order.assign(std::max(n, 1), 0);
+    std::vector<int> left(ni), right(ni), rfirst(ni), rlast(ni), pint(ni), pleaf(std::max(n, 1), -1), flags(ni);
+    std::vector<float4> nlo(ni), nhi(ni);
+    out.nodes.assign(4 * ni, mk4(0, 0, 0, 0));
+    out.seg_root.assign(n_seg, 0);
+    out.seg_depth.assign(n_seg, 0);
+    LbvhArrays a;
+    a.n = n; a.n_seg = n_seg; a.box_lo = lo.data(); a.box_hi = hi.data(); a.seg_of = seg_of; a.seg_first = seg_first;
+    a.seg_cent_lo = cent_lo.data(); a.seg_cent_hi = cent_hi.data(); a.seg_box_lo = out.seg_box_lo.data(); a.seg_box_hi = out.seg_box_hi.data();
+    a.keys = keys.data(); a.order = out.order.data(); a.left = left.data(); a.right = right.data();
+    a.range_first = rfirst.data(); a.range_last = rlast.data(); a.parent_int = pint.data(); a.parent_leaf = pleaf.data();
+    a.flags = flags.data(); a.node_lo = nlo.data(); a.node_hi = nhi.data(); a.nodes = out.nodes.data();
+    a.seg_root = out.seg_root.data(); a.seg_depth = out.seg_depth.data(); a.leaf_size = leaf_size;
+    for (int s = 0; s < n_seg; s++) seg_bounds_init_item(a, s);
+    for (int i = 0; i < n; i++) seg_bounds_item(a, i);
+    for (int i = 0; i < n; i++) morton_item(a, i);
+    {   // stands in for the stable LSD radix sort of (key, order) pairs
+        std::vector<int> idx(n);
+        std::iota(idx.begin(), idx.end(), 0);
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return keys[x] < keys[y]; });
+        std::vector<unsigned long long> k2(n);
+        std::vector<int> o2(n);
+        for (int k = 0; k < n; k++) { k2[k] = keys[idx[k]]; o2[k] = out.order[idx[k]]; }
+        std::copy(k2.begin(), k2.end(), keys.begin());
+        std::copy(o2.begin(), o2.end(), out.order.begin());
+    }
+    if (n > 1) {
+        for (int i = 0; i < n - 1; i++) karras_item(a, i);
+        for (int i = 0; i < n; i++) refit_item(a, i);
+        for (int i = 0; i < n - 1; i++) emit_item(a, i);
+    }
+    for (int s = 0; s < n_seg; s++) single_root_item(a, s);
+    if (n > 1) for (int i = 0; i < n; i++) depth_item(a, i);
+}
+
+struct EmuScene {
+    HostScene hs;
+    EmuLbvh blas, tlas;
+    std::vector<float4> prim_recs, prim_attrs, inst_recs;
+    std::vector<int> prim_rank, inst_rank;
+    SceneView view;
+    int blas_depth = 0, tlas_depth = 0;
+};
+
+int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tlas) {
+    YRT_TRY(host_scene_from_desc(d, es.hs));
+    HostScene& hs = es.hs;
+    GeomView g;
+    g.shape_kind = hs.shape_kind.data(); g.shape_elem_off = hs.shape_elem_off.data(); g.shape_elem_cnt = hs.shape_elem_cnt.data();
+    g.shape_vert_off = hs.shape_vert_off.data(); g.shape_prim_off = hs.shape_prim_off.data(); g.elem_idx = hs.elem_idx.data();
+    g.pos = hs.pos.data(); g.norm = hs.norm.data(); g.uv = hs.uv.data(); g.radius = hs.radius.data();
+    g.prim_shape = hs.prim_shape.data(); g.n_prims = hs.n_prims;
+    int np = hs.n_prims;
+    std::vector<float4> plo(std::max(np, 1)), phi(std::max(np, 1));
+    for (int i = 0; i < np; i++) {
+        Box b = prim_bounds(g, i);
+        plo[i] = mk4(b.lo.x, b.lo.y, b.lo.z, 0.f);
+        phi[i] = mk4(b.hi.x, b.hi.y, b.hi.z, 0.f);
+    }
+    int nseg = std::max(hs.n_shapes, 1);
+    emu_lbvh(np, nseg, plo, phi, g.prim_shape, g.shape_prim_off, leaf_blas, es.blas);
+    // prim + attribute records in BLAS leaf order (mirrors k_gather_prims)
+    es.prim_recs.assign(3 * (size_t)std::max(np, 1), mk4(0, 0, 0, 0));
+    es.prim_attrs.assign(4 * (size_t)std::max(np, 1), mk4(0, 0, 0, 0));
+    es.prim_rank.assign(std::max(np, 1), 0);
+    for (int k = 0; k < np; k++) {
+        int gp = es.blas.order[k];
+        es.prim_rank[k] = hs.prim_rank[gp];
+        int s = g.prim_shape[gp], e = gp - g.shape_prim_off[s], kind = g.shape_kind[s], vo = g.shape_vert_off[s];
+        int nv = kind == 0 ? 3 : (kind == 1 ? 2 : 1);
+        const int* t = g.elem_idx + g.shape_elem_off[s] + (size_t)nv * e;
+        int v[3] = {vo + t[0], vo + t[nv > 1 ? 1 : 0], vo + t[nv > 2 ? 2 : 0]};
+        vec3 p0 = ld3(g.pos, v[0]), p1 = ld3(g.pos, v[1]), p2 = ld3(g.pos, v[2]);
+        vec3 n0 = ld3(g.norm, v[0]), n1 = ld3(g.norm, v[1]), n2 = ld3(g.norm, v[2]);
+        bool huv = hs.shape_has_uv[s] != 0;
+        float u0 = huv ? g.uv[2 * v[0]] : 0.f, w0 = huv ? g.uv[2 * v[0] + 1] : 0.f;
+        float u1 = huv ? g.uv[2 * v[1]] : 0.f, w1 = huv ? g.uv[2 * v[1] + 1] : 0.f;
+        float u2 = huv ? g.uv[2 * v[2]] : 0.f, w2 = huv ? g.uv[2 * v[2] + 1] : 0.f;
+        float4* pr = &es.prim_recs[3 * (size_t)k];
+        float4* ar = &es.prim_attrs[4 * (size_t)k];
+        pr[0] = mk4(p0.x, p0.y, p0.z, int_as_float(e));
+        if (kind == 0) { pr[1] = mk4(p1.x, p1.y, p1.z, 0.f); pr[2] = mk4(p2.x, p2.y, p2.z, 0.f); }
+        else if (kind == 1) { pr[1] = mk4(p1.x, p1.y, p1.z, g.radius[v[0]]); pr[2] = mk4(g.radius[v[1]], 0.f, 0.f, 0.f); }
+        else { pr[1] = mk4(g.radius[v[0]], 0.f, 0.f, 0.f); pr[2] = mk4(0.f, 0.f, 0.f, 0.f); }
+        ar[0] = mk4(n0.x, n0.y, n0.z, u0); ar[1] = mk4(n1.x, n1.y, n1.z, w0); ar[2] = mk4(n2.x, n2.y, n2.z, u1); ar[3] = mk4(w1, u2, w2, 0.f);
+    }
+    // TLAS (mirrors k_inst_boxes / k_inst_recs)
+    int na = (int)hs.active_inst.size();
+    std::vector<float4> ilo(std::max(na, 1)), ihi(std::max(na, 1));
+    for (int a = 0; a < na; a++) {
+        int inst = hs.active_inst[a], s = hs.inst_shape[inst];
+        const float* fr = &hs.inst_frame[12 * (size_t)inst];
+        frame3 f;
+        f.x = mk3(fr[0], fr[1], fr[2]); f.y = mk3(fr[3], fr[4], fr[5]); f.z = mk3(fr[6], fr[7], fr[8]); f.o = mk3(fr[9], fr[10], fr[11]);
+        Box b;
+        b.lo = mk3(ordered_to_float(es.blas.seg_box_lo[3 * s]), ordered_to_float(es.blas.seg_box_lo[3 * s + 1]), ordered_to_float(es.blas.seg_box_lo[3 * s + 2]));
+        b.hi = mk3(ordered_to_float(es.blas.seg_box_hi[3 * s]), ordered_to_float(es.blas.seg_box_hi[3 * s + 1]), ordered_to_float(es.blas.seg_box_hi[3 * s + 2]));
+        Box w = instance_bounds(f, b);
+        ilo[a] = mk4(w.lo.x, w.lo.y, w.lo.z, 0.f);
+        ihi[a] = mk4(w.hi.x, w.hi.y, w.hi.z, 0.f);
+    }
+    std::vector<int> seg_of(std::max(na, 1), 0);
+    int sf[2] = {0, na};
+    emu_lbvh(na, 1, ilo, ihi, seg_of.data(), sf, leaf_tlas, es.tlas);
+    es.inst_recs.assign(4 * (size_t)std::max(na, 1), mk4(0, 0, 0, 0));
+    es.inst_rank.assign(std::max(na, 1), 0);
+    for (int k = 0; k < na; k++) {
+        int inst = hs.active_inst[es.tlas.order[k]], s = hs.inst_shape[inst];
+        es.inst_rank[k] = hs.inst_rank[inst];
+        const float* fr = &hs.inst_frame[12 * (size_t)inst];
+        float4* r = &es.inst_recs[4 * (size_t)k];
+        r[0] = mk4(fr[0], fr[1], fr[2], int_as_float(es.blas.seg_root[s]));
+        r[1] = mk4(fr[3], fr[4], fr[5], int_as_float(inst));
+        r[2] = mk4(fr[6], fr[7], fr[8], int_as_float(hs.inst_mat[inst]));
+        r[3] = mk4(fr[9], fr[10], fr[11], int_as_float((int)((unsigned)s | ((unsigned)hs.shape_kind[s] << 28))));
+    }
+    es.blas_depth = es.blas.seg_depth.empty() ? 0 : *std::max_element(es.blas.seg_depth.begin(), es.blas.seg_depth.end());
+    es.tlas_depth = es.tlas.seg_depth[0];
+    if (es.blas_depth + es.tlas_depth + 4 > YRT_STACK_CAP) { set_error("emu: tree too deep"); return YRT_ERR_UNSUPPORTED; }
+    SceneView& v = es.view;
+    v.tlas_nodes = es.tlas.nodes.data(); v.blas_nodes = es.blas.nodes.data(); v.inst_recs = es.inst_recs.data();
+    v.prim_recs = es.prim_recs.data(); v.prim_attrs = es.prim_attrs.data(); v.mat_recs = hs.mat_recs.data();
+    v.light_recs = hs.light_recs.data(); v.tex_rgba8 = hs.tex_rgba8.data(); v.tex_info = hs.tex_info.data();
+    v.inst_rank = es.inst_rank.data(); v.prim_rank = es.prim_rank.data();
+    v.srgb_lut = hs.srgb_lut; v.tlas_root = es.tlas.seg_root[0]; v.n_lights = (int)hs.light_inst.size(); v.n_active_instances = na;
+    return YRT_OK;
+}
+
+void hit_to_ids(const SceneView& sv, const HitRec& h, int* ids) {
+    if (h.si < 0) { ids[0] = ids[1] = ids[2] = -1; return; }
+    const float4* ir = sv.inst_recs + 4 * (size_t)h.si;
+    ids[0] = float_as_int(ir[1].w);
+    ids[1] = float_as_int(ir[3].w) & 0x0fffffff;
+    ids[2] = float_as_int(sv.prim_recs[3 * (size_t)h.prim].w);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* emu_last_error(void) { return get_error(); }
+
+int emu_scene_create(const yrt_scene_desc* d, int leaf_blas, int leaf_tlas, void** out) {
+    EmuScene* es = new EmuScene();
+    int st = emu_build(d, *es, leaf_blas > 0 ? leaf_blas : YRT_LEAF_SIZE_BLAS, leaf_tlas > 0 ? leaf_tlas : YRT_LEAF_SIZE_TLAS);
+    if (st != YRT_OK) { delete es; return st; }
+    *out = es;
+    return YRT_OK;
+}
+void emu_scene_destroy(void* p) { delete (EmuScene*)p; }
+int emu_scene_info(void* p, int64_t out[8]) {
+    EmuScene* es = (EmuScene*)p;
+    out[0] = es->hs.n_prims > 1 ? es->hs.n_prims - 1 : 0; out[1] = es->view.n_active_instances > 1 ? es->view.n_active_instances - 1 : 0;
+    out[2] = es->blas_depth; out[3] = es->tlas_depth; out[4] = es->view.n_lights; out[5] = es->hs.n_prims; out[6] = 0; out[7] = es->hs.n_reflective;
+    return YRT_OK;
+}
+
+// counters_out (optional, 4 int64): box tests, prim tests, instance entries, max stack
+int emu_trace_primary(void* p, const yrt_camera* cam, int width, int height, int samples, int32_t* ids, float* dist, float* uv,
+                      int64_t* counters_out) {
+    EmuScene* es = (EmuScene*)p;
+    camera_k ck;
+    {
+        const float* f = cam->frame;
+        ck.frame.x = mk3(f[0], f[1], f[2]); ck.frame.y = mk3(f[3], f[4], f[5]); ck.frame.z = mk3(f[6], f[7], f[8]); ck.frame.o = mk3(f[9], f[10], f[11]);
+        ck.h = 2.0f * cam->focus * tanf(cam->fovy / 2.0f); ck.w = ck.h * cam->aspect; ck.focus = cam->focus;
+    }
+    long long cb = 0, cp = 0, ci = 0; int cm = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : cb, cp, ci) reduction(max : cm)
+    for (int j = 0; j < height; j++) {
+        int stack[YRT_STACK_CAP];
+        for (int i = 0; i < width; i++)
+            for (int jj = 0; jj < samples; jj++)
+                for (int ii = 0; ii < samples; ii++) {
+                    size_t r = (((size_t)j * width + i) * samples + jj) * samples + ii;
+                    float u, v;
+                    sample_uv(i, j, ii, jj, samples, width, height, u, v);
+                    ray3 ray = eval_camera(ck, u, v);
+                    HitRec h;
+                    TraceCounters tc = {0, 0, 0, 0};
+                    trace_ray<false>(es->view, ray, h, stack, &tc);
+                    cb += tc.box_tests; cp += tc.prim_tests; ci += tc.inst_entries; cm = std::max(cm, tc.max_stack);
+                    hit_to_ids(es->view, h, ids + 3 * r);
+                    if (dist) dist[r] = h.dist;
+                    if (uv) { uv[2 * r] = h.w1; uv[2 * r + 1] = h.w2; }
+                }
+    }
+    if (counters_out) { counters_out[0] = cb; counters_out[1] = cp; counters_out[2] = ci; counters_out[3] = cm; }
+    return YRT_OK;
+}
+
+// the whole frame with the device functions: raygen -> closest -> shadow (any) -> shade -> reflection
+// loop with the same explicit {c, kr, la} stack as k_shade -> ordered per-pixel sum.
+// ray_counts (optional, 3 int64): primary, reflection, shadow
+int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, int height, int samples, int max_depth, float* rgba,
+               int64_t* ray_counts) {
+    EmuScene* es = (EmuScene*)p;
+    const SceneView& sv = es->view;
+    camera_k ck;
+    {
+        const float* f = cam->frame;
+        ck.frame.x = mk3(f[0], f[1], f[2]); ck.frame.y = mk3(f[3], f[4], f[5]); ck.frame.z = mk3(f[6], f[7], f[8]); ck.frame.o = mk3(f[9], f[10], f[11]);
+        ck.h = 2.0f * cam->focus * tanf(cam->fovy / 2.0f); ck.w = ck.h * cam->aspect; ck.focus = cam->focus;
+    }
+    vec3 ambv = mk3(amb[0], amb[1], amb[2]);
+    if (max_depth <= 0) max_depth = 16;
+    long long n_refl = 0, n_shadow = 0;
+#pragma omp parallel for schedule(dynamic, 2) reduction(+ : n_refl, n_shadow)
+    for (int j = 0; j < height; j++) {
+        int stack[YRT_STACK_CAP];
+        std::vector<vec3> sc(max_depth), skr(max_depth), sla(max_depth);
+        std::vector<uint8_t> vis(std::max(sv.n_lights, 1));
+        for (int i = 0; i < width; i++) {
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            for (int jj = 0; jj < samples; jj++)
+                for (int ii = 0; ii < samples; ii++) {
+                    float u, v;
+                    sample_uv(i, j, ii, jj, samples, width, height, u, v);
+                    ray3 ray = eval_camera(ck, u, v);
+                    vec3 value = mk3(0.f, 0.f, 0.f);
+                    int depth = 0;
+                    for (;;) {
+                        HitRec h;
+                        trace_ray<false>(sv, ray, h, stack, nullptr);
+                        if (depth > 0) n_refl++;
+                        if (h.si < 0) { value = mk3(0.f, 0.f, 0.f); break; }
+                        int kind;
+                        vec3 P = eval_hit_pos(sv, h.si, h.prim, h.w1, h.w2, kind);
+                        for (int k = 0; k < sv.n_lights; k++) {
+                            vec3 l, ke; float r;
+                            light_vector(sv, k, P, l, r, ke);
+                            ray3 sr = shadow_ray(P, l, r);
+                            HitRec hr;
+                            vis[k] = trace_ray<true>(sv, sr, hr, stack, nullptr) ? 0 : 1;
+                            n_shadow++;
+                        }
+                        vec3 c, kr, la; ray3 rr;
+                        bool spawn = shade_hit(sv, h.si, h.prim, h.w1, h.w2, ray.o, ambv, sv.srgb_lut, [&](int k) { return vis[k] != 0; },
+                                               depth + 1 < max_depth, value, c, kr, la, rr);
+                        if (!spawn) break;
+                        sc[depth] = c; skr[depth] = kr; sla[depth] = la;
+                        ray = rr;
+                        depth++;
+                    }
+                    for (int d = depth - 1; d >= 0; d--) value = combine_reflection(sc[d], value, skr[d], sla[d]);
+                    sx += value.x; sy += value.y; sz += value.z;
+                }
+            float dn = (float)(samples * samples);
+            float* o = rgba + 4 * ((size_t)j * width + i);
+            o[0] = sx / dn; o[1] = sy / dn; o[2] = sz / dn; o[3] = 1.0f;
+        }
+    }
+    if (ray_counts) { ray_counts[0] = (long long)width * height * samples * samples; ray_counts[1] = n_refl; ray_counts[2] = n_shadow; }
+    return YRT_OK;
+}
+
+}  // extern "C"

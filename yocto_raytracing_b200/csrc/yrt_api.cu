@@ -1,0 +1,293 @@
+// yrt_api.cu — the extern "C" boundary declared in include/yrt_b200.h.
+//
+// Multi-GPU inside one process (yrt_render with yrt_init(n>1)): the scene is replicated, GPU g
+// renders the interleaved row tiles t with t % n == g, its packed rows travel to GPU 0 with one
+// peer copy over NVLink, GPU 0 scatters them into the full framebuffer and does the single
+// device->host copy.  One process per GPU (torchrun): yrt_init_device + yrt_render_rows, the
+// gather is the caller's NCCL collective.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+#include "yrt_internal.h"
+
+using namespace yrt;
+
+namespace {
+std::mutex g_mu;
+std::vector<int> g_devices;   // empty until yrt_init*
+
+struct GatherState {          // device-0 side buffers of the in-process multi-GPU path
+    std::vector<DevBuf*> packed;   // per device, on that device
+    std::vector<DevBuf*> staged;   // per device, on device 0
+    DevBuf full;
+    std::vector<cudaEvent_t> done;
+    ~GatherState() {
+        for (auto p : packed) delete p;
+        for (auto p : staged) delete p;
+    }
+};
+GatherState* g_gather = nullptr;
+
+int ensure_init() {
+    if (!g_devices.empty()) return YRT_OK;
+    return yrt_init(1);
+}
+}  // namespace
+
+extern "C" {
+
+int yrt_abi_version(void) { return YRT_ABI_VERSION; }
+const char* yrt_last_error(void) { return get_error(); }
+
+int yrt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int yrt_init(int n_gpus) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (n_gpus <= 0) n_gpus = 1;
+    int have = yrt_device_count();
+    if (have < n_gpus) {
+        set_error("yrt_init: %d CUDA device(s) requested, %d visible — this library has no CPU path", n_gpus, have);
+        return YRT_ERR_NO_DEVICE;
+    }
+    g_devices.clear();
+    for (int i = 0; i < n_gpus; i++) g_devices.push_back(i);
+    for (int i = 1; i < n_gpus; i++) {   // NVLink peer access between GPU 0 and every other GPU (both ways)
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, 0, i) == cudaSuccess && can) { cudaSetDevice(0); cudaDeviceEnablePeerAccess(i, 0); }
+        if (cudaDeviceCanAccessPeer(&can, i, 0) == cudaSuccess && can) { cudaSetDevice(i); cudaDeviceEnablePeerAccess(0, 0); }
+        cudaGetLastError();
+    }
+    YRT_CUDA(cudaSetDevice(0));
+    delete g_gather;
+    g_gather = nullptr;
+    return YRT_OK;
+}
+
+int yrt_init_device(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int have = yrt_device_count();
+    if (device < 0 || device >= have) {
+        set_error("yrt_init_device: device %d not available (%d visible) — this library has no CPU path", device, have);
+        return YRT_ERR_NO_DEVICE;
+    }
+    g_devices.assign(1, device);
+    YRT_CUDA(cudaSetDevice(device));
+    delete g_gather;
+    g_gather = nullptr;
+    return YRT_OK;
+}
+
+int yrt_scene_create(const yrt_scene_desc* desc, yrt_scene** out) {
+    if (!out) { set_error("yrt_scene_create: out is null"); return YRT_ERR_INVALID; }
+    *out = nullptr;
+    yrt_scene* s = new yrt_scene();
+    int st = host_scene_from_desc(desc, s->host);
+    if (st != YRT_OK) { delete s; return st; }
+    st = ensure_init();
+    if (st != YRT_OK) { delete s; return st; }
+    for (int dev : g_devices) {
+        DevScene* ds = new DevScene();
+        s->dev.push_back(ds);
+        st = build_device_scene(s->host, dev, *ds);
+        if (st != YRT_OK) { yrt_scene_destroy(s); return st; }
+    }
+    *out = s;
+    return YRT_OK;
+}
+
+void yrt_scene_destroy(yrt_scene* scn) {
+    if (!scn) return;
+    for (DevScene* ds : scn->dev) {
+        destroy_device_scene(*ds);
+        delete ds;
+    }
+    delete scn;
+}
+
+int yrt_scene_info(const yrt_scene* scn, int64_t out[8]) {
+    if (!scn || scn->dev.empty() || !out) { set_error("yrt_scene_info: bad arguments"); return YRT_ERR_INVALID; }
+    const DevScene& d = *scn->dev[0];
+    out[0] = d.n_blas_nodes; out[1] = d.n_tlas_nodes; out[2] = d.blas_depth; out[3] = d.tlas_depth;
+    out[4] = d.view.n_lights; out[5] = d.n_prims; out[6] = (int64_t)d.build_us; out[7] = scn->host.n_reflective;
+    return YRT_OK;
+}
+
+int yrt_image_width(const yrt_camera* cam, int resolution) {
+    if (!cam) return 0;
+    return (int)roundf(cam->aspect * (float)resolution);   // (int)std::round(cam->aspect * resolution)
+}
+
+int yrt_rows_owned(int height, int tile_rows, int rank, int world) {
+    if (height <= 0 || tile_rows <= 0 || world <= 0 || rank < 0 || rank >= world) return 0;
+    return rows_owned(height, tile_rows, rank, world);
+}
+
+static int fill_params(const yrt_camera* cam, const float amb[3], int width, int height, int samples, RenderParams& rp) {
+    if (!cam) { set_error("camera is null"); return YRT_ERR_INVALID; }
+    rp.cam = make_camera_k(cam);
+    rp.amb = amb ? mk3(amb[0], amb[1], amb[2]) : mk3(0.f, 0.f, 0.f);
+    rp.width = width; rp.height = height; rp.samples = samples;
+    rp.tile_rows = 16; rp.rank = 0; rp.world = 1;
+    return YRT_OK;
+}
+
+int yrt_render_rows(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height, int samples, int tile_rows,
+                    int rank, int world, void* d_rgba, void* stream, yrt_stats* stats) {
+    if (!scn || scn->dev.empty() || !d_rgba) { set_error("yrt_render_rows: bad arguments"); return YRT_ERR_INVALID; }
+    RenderParams rp;
+    YRT_TRY(fill_params(cam, amb, width, height, samples, rp));
+    rp.tile_rows = tile_rows; rp.rank = rank; rp.world = world;
+    DevScene& ds = *scn->dev[0];
+    cudaStream_t st = stream ? (cudaStream_t)stream : ds.stream;
+    return render_rows_device(ds, rp, (float4*)d_rgba, st, stats, true);
+}
+
+int yrt_unpack_rows(const void* d_packed, void* d_full, int width, int height, int tile_rows, int rank, int world, void* stream) {
+    if (!d_packed || !d_full || width <= 0 || height <= 0 || tile_rows <= 0 || world <= 0 || rank < 0 || rank >= world) {
+        set_error("yrt_unpack_rows: bad arguments");
+        return YRT_ERR_INVALID;
+    }
+    return unpack_rows_device((const float4*)d_packed, (float4*)d_full, width, height, tile_rows, rank, world, (cudaStream_t)stream);
+}
+
+int yrt_render(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height, int samples, float* rgba_out,
+               yrt_stats* stats) {
+    if (!scn || scn->dev.empty() || !rgba_out) { set_error("yrt_render: bad arguments"); return YRT_ERR_INVALID; }
+    RenderParams rp0;
+    YRT_TRY(fill_params(cam, amb, width, height, samples, rp0));
+    const int G = (int)scn->dev.size();
+    const char* etr = getenv("YRT_TILE_ROWS");
+    int tile_rows = etr ? std::max(1, atoi(etr)) : 16;
+    if (G == 1) tile_rows = std::max(1, height);
+    if (!g_gather) g_gather = new GatherState();
+    GatherState& gs = *g_gather;
+    while ((int)gs.packed.size() < G) { gs.packed.push_back(new DevBuf()); gs.staged.push_back(new DevBuf()); gs.done.push_back(nullptr); }
+    DevScene& d0 = *scn->dev[0];
+    size_t full_bytes = sizeof(float4) * (size_t)width * height;
+    YRT_TRY(gs.full.alloc(full_bytes, d0.device));
+
+    std::vector<int> status(G, YRT_OK);
+    std::vector<std::string> errs(G);
+    std::vector<yrt_stats> dstats(G);
+    auto work = [&](int g) {
+        DevScene& ds = *scn->dev[g];
+        RenderParams rp = rp0;
+        rp.tile_rows = tile_rows; rp.rank = g; rp.world = G;
+        int own = rows_owned(height, tile_rows, g, G);
+        size_t bytes = sizeof(float4) * (size_t)own * width;
+        int s = YRT_OK;
+        float4* dst = nullptr;
+        if (G == 1) {
+            dst = gs.full.as<float4>();   // one GPU: packed order == row order
+        } else {
+            s = gs.packed[g]->alloc(bytes, ds.device);
+            dst = gs.packed[g]->as<float4>();
+        }
+        if (s == YRT_OK) s = render_rows_device(ds, rp, dst, ds.stream, stats ? &dstats[g] : nullptr, false);
+        if (s == YRT_OK && G > 1 && g > 0 && own > 0) {
+            s = gs.staged[g]->alloc(bytes, d0.device);
+            if (s == YRT_OK) {
+                cudaSetDevice(ds.device);
+                if (cudaMemcpyPeerAsync(gs.staged[g]->p, d0.device, gs.packed[g]->p, ds.device, bytes, ds.stream) != cudaSuccess) {
+                    set_error("peer copy of rank %d rows failed: %s", g, cudaGetErrorString(cudaGetLastError()));
+                    s = YRT_ERR_CUDA;
+                }
+            }
+        }
+        if (s == YRT_OK) {
+            cudaSetDevice(ds.device);
+            if (!gs.done[g]) cudaEventCreateWithFlags(&gs.done[g], cudaEventDisableTiming);
+            cudaEventRecord(gs.done[g], ds.stream);
+        }
+        status[g] = s;
+        if (s != YRT_OK) errs[g] = get_error();
+    };
+    if (G == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; g++) th.emplace_back(work, g);
+        for (auto& t : th) t.join();
+    }
+    for (int g = 0; g < G; g++)
+        if (status[g] != YRT_OK) { set_error("%s", errs[g].c_str()); return status[g]; }
+
+    // gather on GPU 0: wait for every rank's rows, scatter into the full framebuffer, one D2H copy
+    YRT_CUDA(cudaSetDevice(d0.device));
+    cudaStream_t s0 = d0.stream;
+    cudaEvent_t g0 = nullptr, g1 = nullptr;
+    if (stats) { cudaEventCreate(&g0); cudaEventCreate(&g1); }
+    if (G > 1) {
+        for (int g = 1; g < G; g++) YRT_CUDA(cudaStreamWaitEvent(s0, gs.done[g], 0));
+        if (stats) cudaEventRecord(g0, s0);
+        for (int g = 0; g < G; g++) {
+            const float4* src = g == 0 ? gs.packed[0]->as<float4>() : gs.staged[g]->as<float4>();
+            if (rows_owned(height, tile_rows, g, G) > 0)
+                YRT_TRY(unpack_rows_device(src, gs.full.as<float4>(), width, height, tile_rows, g, G, s0));
+        }
+        if (stats) cudaEventRecord(g1, s0);
+    }
+    YRT_CUDA(cudaMemcpyAsync(rgba_out, gs.full.p, full_bytes, cudaMemcpyDeviceToHost, s0));
+    YRT_CUDA(cudaStreamSynchronize(s0));
+    if (stats) {
+        // every device is idle now (GPU 0 waited for all of them): collect per-device stats
+        memset(stats, 0, sizeof(*stats));
+        for (int g = 0; g < G; g++) {
+            DevScene& ds = *scn->dev[g];
+            cudaSetDevice(ds.device);
+            cudaStreamSynchronize(ds.stream);
+            RenderParams rp = rp0;
+            rp.tile_rows = tile_rows; rp.rank = g; rp.world = G;
+            yrt_stats one;
+            YRT_TRY(collect_stats_device(ds, rp, &one));
+            stats->primary_rays += one.primary_rays;
+            stats->reflection_rays += one.reflection_rays;
+            stats->shadow_rays += one.shadow_rays;
+            stats->launches += one.launches;
+            stats->ms_total = std::max(stats->ms_total, one.ms_total);
+            stats->max_depth = std::max(stats->max_depth, one.max_depth);
+            if (g == 0) {
+                stats->ms_trace_closest = one.ms_trace_closest; stats->ms_trace_any = one.ms_trace_any;
+                stats->ms_shade = one.ms_shade; stats->ms_other = one.ms_other;
+            }
+        }
+        cudaSetDevice(d0.device);
+        if (G > 1) { float ms = 0.f; cudaEventElapsedTime(&ms, g0, g1); stats->ms_gather = ms; stats->launches += G; }
+        stats->n_gpus = G;
+        cudaEventDestroy(g0); cudaEventDestroy(g1);
+    }
+    return YRT_OK;
+}
+
+int yrt_trace_primary(yrt_scene* scn, const yrt_camera* cam, int width, int height, int samples, int32_t* ids_out, float* dist_out,
+                      float* uv_out) {
+    if (!scn || scn->dev.empty() || !ids_out) { set_error("yrt_trace_primary: bad arguments"); return YRT_ERR_INVALID; }
+    RenderParams rp;
+    float amb[3] = {0, 0, 0};
+    YRT_TRY(fill_params(cam, amb, width, height, samples, rp));
+    return trace_primary_device(*scn->dev[0], rp, ids_out, dist_out, uv_out);
+}
+
+int yrt_intersect_first(yrt_scene* scn, const float* rays, int64_t n, int32_t* ids_out, float* dist_out, float* uv_out) {
+    if (!scn || scn->dev.empty() || (n > 0 && !ids_out)) { set_error("yrt_intersect_first: bad arguments"); return YRT_ERR_INVALID; }
+    return intersect_rays_device(*scn->dev[0], rays, n, false, ids_out, dist_out, uv_out, nullptr);
+}
+
+int yrt_intersect_any(yrt_scene* scn, const float* rays, int64_t n, uint8_t* occluded_out) {
+    if (!scn || scn->dev.empty() || (n > 0 && !occluded_out)) { set_error("yrt_intersect_any: bad arguments"); return YRT_ERR_INVALID; }
+    return intersect_rays_device(*scn->dev[0], rays, n, true, nullptr, nullptr, nullptr, occluded_out);
+}
+
+int yrt_tonemap(const float* rgba_in, int width, int height, uint8_t* rgba8_out) {
+    if (!rgba_in || !rgba8_out || width <= 0 || height <= 0) { set_error("yrt_tonemap: bad arguments"); return YRT_ERR_INVALID; }
+    YRT_TRY(ensure_init());
+    return tonemap_device(g_devices[0], rgba_in, width, height, rgba8_out);
+}
+
+}  // extern "C"

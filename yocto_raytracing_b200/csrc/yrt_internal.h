@@ -1,0 +1,148 @@
+// yrt_internal.h — host-side plumbing shared by the translation units of libyrt_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/yrt_b200.h"
+#include "yrt_lbvh.cuh"
+#include "yrt_scene.cuh"
+
+namespace yrt {
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define YRT_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            ::yrt::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return (e_ == cudaErrorMemoryAllocation) ? YRT_ERR_OOM : YRT_ERR_CUDA;                  \
+        }                                                                                           \
+    } while (0)
+
+#define YRT_TRY(expr)              \
+    do {                           \
+        int s_ = (expr);           \
+        if (s_ != YRT_OK) return s_; \
+    } while (0)
+
+// device buffer owned by a DevScene / workspace (freed on the device it was allocated on)
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int device = -1;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    int alloc(size_t n, int dev);            // (re)allocates only when growing
+    int upload(const void* src, size_t n, int dev, cudaStream_t st);
+    void release();
+    template <class T> T* as() const { return (T*)p; }
+};
+
+// validated host copy of the scene description + everything derived on the host
+struct HostScene {
+    int n_shapes = 0, n_instances = 0, n_materials = 0, n_textures = 0, n_verts = 0, n_prims = 0;
+    std::vector<int> shape_kind, shape_elem_off, shape_elem_cnt, shape_vert_off, shape_vert_cnt, shape_prim_off;
+    std::vector<int> shape_has_uv;
+    std::vector<int> elem_idx, prim_shape;
+    std::vector<float> pos, norm, uv, radius;
+    std::vector<float> inst_frame;
+    std::vector<int> inst_shape, inst_mat;
+    std::vector<int> active_inst;            // instances whose shape has at least one element
+    std::vector<int> prim_rank;              // [n_prims] rank of each element in the reference's shape-BVH visit order
+    std::vector<int> inst_rank;              // [n_instances] rank of each instance in the reference's scene-BVH visit order
+    std::vector<float4> mat_recs;            // 4 per material (ns computed with the host libm)
+    std::vector<float4> light_recs;          // 5 per light, in instance order
+    std::vector<int> light_inst;
+    std::vector<int4> tex_info;
+    std::vector<uint8_t> tex_rgba8;
+    float srgb_lut[256];
+    int n_reflective = 0;
+};
+
+int host_scene_from_desc(const yrt_scene_desc* d, HostScene& hs);
+// visit ranks of the reference's top-down BVHs (make_node/split_prims, src/scene.cpp:572-639), for tie-breaking
+void reference_visit_ranks(HostScene& hs);
+
+struct PhaseTimer;
+
+// per-device render workspace (grown on demand, reused across frames)
+struct Workspace {
+    DevBuf hit, P, vis, rad, ray_o, ray_d, pstack, act0, act1, counters, stats, rows;
+    size_t cap_slots = 0;
+    int cap_lights = 0;
+    int cap_depth = 0;
+};
+
+struct DevScene {
+    int device = 0;
+    SceneView view;
+    // geometry inputs
+    DevBuf shape_kind, shape_elem_off, shape_elem_cnt, shape_vert_off, shape_prim_off, elem_idx, pos, norm, uv, radius, prim_shape;
+    DevBuf inst_frame, inst_shape, inst_mat, active_inst, prim_rank_in, inst_rank_in, prim_rank, inst_rank;
+    // build products
+    DevBuf blas_nodes, tlas_nodes, prim_recs, prim_attrs, inst_recs, mat_recs, light_recs, tex, tex_info, lut;
+    DevBuf blas_seg_root, blas_seg_depth, tlas_seg_root, tlas_seg_depth, shape_box_lo, shape_box_hi;
+    int n_prims = 0, n_active = 0, n_blas_nodes = 0, n_tlas_nodes = 0;
+    int blas_depth = 0, tlas_depth = 0;
+    float build_us = 0.f;
+    cudaStream_t stream = nullptr;   // owned
+    Workspace ws;
+    int sm_count = 148;
+    bool has_reflective = false;
+    int grid_closest_primary = 0, grid_closest_queue = 0, grid_any = 0;   // persistent grids (SMs x resident CTAs)
+    PhaseTimer* timer = nullptr;     // owned (yrt_render.cu)
+};
+
+int build_device_scene(const HostScene& hs, int device, DevScene& ds);
+void destroy_device_scene(DevScene& ds);
+
+struct RenderParams {
+    camera_k cam;
+    vec3 amb;
+    int width, height, samples;
+    int tile_rows, rank, world;   // interleaved row tiles
+};
+
+YRT_HD int rows_owned(int height, int tile_rows, int rank, int world) {
+    int n_tiles = (height + tile_rows - 1) / tile_rows;
+    int rows = 0;
+    for (int t = rank; t < n_tiles; t += world) {
+        int r0 = t * tile_rows, r1 = r0 + tile_rows;
+        if (r1 > height) r1 = height;
+        rows += r1 - r0;
+    }
+    return rows;
+}
+// global row of the rank's packed local row lr
+YRT_HD int global_row(int lr, int tile_rows, int rank, int world) {
+    int tl = lr / tile_rows;
+    return (tl * world + rank) * tile_rows + (lr - tl * tile_rows);
+}
+
+// renders the rank's rows into d_out (packed rows, float4 per pixel) on ds.device / `st`.
+// ids/dist/uvw (device, per primary ray) are filled instead of shading when ids != nullptr.
+int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cudaStream_t st, yrt_stats* stats,
+                       bool sync_for_stats);
+// waits for the frame issued by render_rows_device(…, stats != null, sync_for_stats = false) and fills stats
+int collect_stats_device(DevScene& ds, const RenderParams& rp, yrt_stats* stats);
+int trace_primary_device(DevScene& ds, const RenderParams& rp, int32_t* h_ids, float* h_dist, float* h_uv);
+int intersect_rays_device(DevScene& ds, const float* h_rays, int64_t n, bool any, int32_t* h_ids, float* h_dist,
+                          float* h_uv, uint8_t* h_occ);
+int unpack_rows_device(const float4* d_packed, float4* d_full, int width, int height, int tile_rows, int rank,
+                       int world, cudaStream_t st);
+int tonemap_device(int device, const float* h_rgba, int width, int height, uint8_t* h_out);
+
+camera_k make_camera_k(const yrt_camera* cam);
+
+}  // namespace yrt
+
+struct yrt_scene {
+    yrt::HostScene host;
+    std::vector<yrt::DevScene*> dev;   // one per initialised GPU
+};

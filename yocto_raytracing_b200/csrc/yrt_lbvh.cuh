@@ -1,0 +1,335 @@
+// yrt_lbvh.cuh — per-item functions of the GPU LBVH build (Morton keys -> radix sort -> Karras
+// topology -> bottom-up refit -> 64-byte two-child-box nodes with small-subtree leaves).
+//
+// Replaces build_bvh / make_node / split_prims (src/scene.cpp:508-658): the reference builds
+// top-down midpoint-split trees serially; topology is free for parity (SURVEY finding 4), the
+// primitive bounds are the reference's (scene.cpp:521-546, bbox_to_world src/vmath.h:312-326).
+// One build handles MANY trees at once: every item carries a segment id (its shape) in the top
+// 16 bits of the 64-bit key, so after the sort each segment is a contiguous range and — because no
+// other key shares its prefix — a subtree of the global radix tree; that subtree's root is the
+// segment's BLAS root.  The TLAS is the same build with a single segment.
+//
+// Item functions are __host__ __device__: the kernels in yrt_build.cu call them one thread per
+// item, tools/host_emu calls them in serial loops (tests only).
+#pragma once
+#include "yrt_scene.cuh"
+
+namespace yrt {
+
+#define YRT_LEAF_SIZE_BLAS 4   /* the reference also stops at <= 4 prims (scene.cpp:583) */
+#define YRT_LEAF_SIZE_TLAS 2
+
+// ---- order-preserving float <-> int for atomic min/max --------------------------------------
+YRT_HD int float_to_ordered(float f) { int i = float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+YRT_HD float ordered_to_float(int i) { return int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+#if defined(__CUDA_ARCH__)
+#define YRT_ATOMIC_MIN(p, v) atomicMin((p), (v))
+#define YRT_ATOMIC_MAX(p, v) atomicMax((p), (v))
+#define YRT_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define YRT_FENCE() __threadfence()
+#else
+template <class T> inline T yrt_host_min_(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <class T> inline T yrt_host_max_(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <class T> inline T yrt_host_add_(T* p, T v) { T o = *p; *p = o + v; return o; }
+#define YRT_ATOMIC_MIN(p, v) yrt_host_min_((p), (v))
+#define YRT_ATOMIC_MAX(p, v) yrt_host_max_((p), (v))
+#define YRT_ATOMIC_ADD(p, v) yrt_host_add_((p), (v))
+#define YRT_FENCE()
+#endif
+
+// ---- flattened geometry as uploaded (what the bounds / gather kernels read) -----------------
+struct GeomView {
+    const int* shape_kind;
+    const int* shape_elem_off;   // into elem_idx (ints)
+    const int* shape_elem_cnt;
+    const int* shape_vert_off;
+    const int* shape_prim_off;   // first global prim id of the shape (exclusive scan of elem_cnt)
+    const int* elem_idx;
+    const float* pos;            // 3 per vertex
+    const float* norm;
+    const float* uv;             // 2 per vertex (zeros where the shape has none)
+    const float* radius;         // 1 per vertex (zeros where the shape has none)
+    const int* prim_shape;       // [n_prims] shape of each global prim id
+    int n_prims;
+};
+
+YRT_HD vec3 ld3(const float* p, int i) { return mk3(p[3 * (size_t)i], p[3 * (size_t)i + 1], p[3 * (size_t)i + 2]); }
+
+struct Box { vec3 lo, hi; };
+YRT_HD Box box_invalid() { Box b; b.lo = mk3(FLT_MAX, FLT_MAX, FLT_MAX); b.hi = mk3(-FLT_MAX, -FLT_MAX, -FLT_MAX); return b; }
+YRT_HD void box_expand(Box& b, const vec3& lo, const vec3& hi) {   // vmath.h:292-296
+    b.lo = mk3(rmin(b.lo.x, lo.x), rmin(b.lo.y, lo.y), rmin(b.lo.z, lo.z));
+    b.hi = mk3(rmax(b.hi.x, hi.x), rmax(b.hi.y, hi.y), rmax(b.hi.z, hi.z));
+}
+// expand_bbox(bbox, p, r) of scene.cpp:521-523
+YRT_HD void box_expand_pr(Box& b, const vec3& p, float r) { box_expand(b, p - mk3(r, r, r), p + mk3(r, r, r)); }
+
+// bounds of global prim `g` in its shape's object space (scene.cpp:527-547)
+YRT_HD Box prim_bounds(const GeomView& g, int gp) {
+    int s = g.prim_shape[gp];
+    int e = gp - g.shape_prim_off[s];
+    int kind = g.shape_kind[s];
+    int vo = g.shape_vert_off[s];
+    Box b = box_invalid();
+    if (kind == 0) {
+        const int* t = g.elem_idx + g.shape_elem_off[s] + 3 * (size_t)e;
+        box_expand_pr(b, ld3(g.pos, vo + t[0]), 0.f);
+        box_expand_pr(b, ld3(g.pos, vo + t[1]), 0.f);
+        box_expand_pr(b, ld3(g.pos, vo + t[2]), 0.f);
+    } else if (kind == 1) {
+        const int* t = g.elem_idx + g.shape_elem_off[s] + 2 * (size_t)e;
+        box_expand_pr(b, ld3(g.pos, vo + t[0]), g.radius[vo + t[0]]);
+        box_expand_pr(b, ld3(g.pos, vo + t[1]), g.radius[vo + t[1]]);
+    } else {
+        const int* t = g.elem_idx + g.shape_elem_off[s] + (size_t)e;
+        box_expand_pr(b, ld3(g.pos, vo + t[0]), g.radius[vo + t[0]]);
+    }
+    return b;
+}
+
+// world bounds of an instance: bbox_to_world (vmath.h:312-326) of the shape's root box
+YRT_HD Box instance_bounds(const frame3& f, const Box& b) {
+    Box w = box_invalid();
+    for (int c = 0; c < 8; c++) {
+        vec3 p = mk3((c & 4) ? b.hi.x : b.lo.x, (c & 2) ? b.hi.y : b.lo.y, (c & 1) ? b.hi.z : b.lo.z);
+        vec3 q = transform_point(f, p);
+        box_expand(w, q, q);
+    }
+    return w;
+}
+
+// ---- build items ------------------------------------------------------------------------------
+struct LbvhArrays {
+    int n;                 // number of items (leaves)
+    int n_seg;
+    // inputs
+    float4* box_lo;        // [n] item bounds (xyz), .w unused
+    float4* box_hi;
+    const int* seg_of;     // [n] segment of item i (non-decreasing in i)
+    const int* seg_first;  // [n_seg+1] first item of each segment
+    // per segment reductions (ordered-int encoding): centroid bounds and full bounds
+    int* seg_cent_lo;      // [3*n_seg]
+    int* seg_cent_hi;
+    int* seg_box_lo;       // [3*n_seg]
+    int* seg_box_hi;
+    // sort
+    unsigned long long* keys;   // [n]
+    int* order;                 // [n] item id at sorted slot k
+    // topology over sorted slots: internal nodes 0..n-2, leaves 0..n-1
+    int* left;             // [n-1] child: >=0 internal, <0 => ~leaf slot
+    int* right;
+    int* range_first;      // [n-1]
+    int* range_last;
+    int* parent_int;       // [n-1] parent of an internal node (-1 root)
+    int* parent_leaf;      // [n]
+    int* flags;            // [n-1] refit arrival counters
+    float4* node_lo;       // [n-1] refit bounds of internal nodes
+    float4* node_hi;
+    // outputs
+    float4* nodes;         // [4*(n-1)]
+    int* seg_root;         // [n_seg] root ref per segment
+    int* seg_depth;        // [n_seg] max depth (levels of internal nodes) per segment
+    int leaf_size;
+};
+
+YRT_HD void seg_bounds_init_item(const LbvhArrays& a, int s) {
+    for (int c = 0; c < 3; c++) {
+        a.seg_cent_lo[3 * s + c] = float_to_ordered(FLT_MAX);
+        a.seg_cent_hi[3 * s + c] = float_to_ordered(-FLT_MAX);
+        a.seg_box_lo[3 * s + c] = float_to_ordered(FLT_MAX);
+        a.seg_box_hi[3 * s + c] = float_to_ordered(-FLT_MAX);
+    }
+    a.seg_root[s] = YRT_REF_SENTINEL;
+    a.seg_depth[s] = 0;
+}
+
+YRT_HD vec3 box_centroid(const float4& lo, const float4& hi) {   // (bbox.min + bbox.max) / 2, scene.cpp:531
+    return mk3((lo.x + hi.x) / 2.0f, (lo.y + hi.y) / 2.0f, (lo.z + hi.z) / 2.0f);
+}
+
+YRT_HD void seg_bounds_item(const LbvhArrays& a, int i) {
+    int s = a.seg_of[i];
+    float4 lo = a.box_lo[i], hi = a.box_hi[i];
+    vec3 c = box_centroid(lo, hi);
+    YRT_ATOMIC_MIN(&a.seg_cent_lo[3 * s + 0], float_to_ordered(c.x));
+    YRT_ATOMIC_MIN(&a.seg_cent_lo[3 * s + 1], float_to_ordered(c.y));
+    YRT_ATOMIC_MIN(&a.seg_cent_lo[3 * s + 2], float_to_ordered(c.z));
+    YRT_ATOMIC_MAX(&a.seg_cent_hi[3 * s + 0], float_to_ordered(c.x));
+    YRT_ATOMIC_MAX(&a.seg_cent_hi[3 * s + 1], float_to_ordered(c.y));
+    YRT_ATOMIC_MAX(&a.seg_cent_hi[3 * s + 2], float_to_ordered(c.z));
+    YRT_ATOMIC_MIN(&a.seg_box_lo[3 * s + 0], float_to_ordered(lo.x));
+    YRT_ATOMIC_MIN(&a.seg_box_lo[3 * s + 1], float_to_ordered(lo.y));
+    YRT_ATOMIC_MIN(&a.seg_box_lo[3 * s + 2], float_to_ordered(lo.z));
+    YRT_ATOMIC_MAX(&a.seg_box_hi[3 * s + 0], float_to_ordered(hi.x));
+    YRT_ATOMIC_MAX(&a.seg_box_hi[3 * s + 1], float_to_ordered(hi.y));
+    YRT_ATOMIC_MAX(&a.seg_box_hi[3 * s + 2], float_to_ordered(hi.z));
+}
+
+// spread the low 16 bits of v so that two zero bits separate consecutive bits
+YRT_HD unsigned long long spread16(unsigned int v) {
+    unsigned long long x = v & 0xffffull;
+    x = (x | (x << 16)) & 0x0000ff0000ffull;
+    x = (x | (x << 8)) & 0x00f00f00f00full;
+    x = (x | (x << 4)) & 0x0c30c30c30c3ull;
+    x = (x | (x << 2)) & 0x249249249249ull;
+    return x;
+}
+
+YRT_HD unsigned int quant16(float c, float lo, float hi) {
+    float ext = hi - lo;
+    if (!(ext > 0.f)) return 0u;
+    float t = (c - lo) / ext;
+    t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
+    unsigned int q = (unsigned int)(t * 65535.0f);
+    return q > 65535u ? 65535u : q;
+}
+
+// key = segment (16 bits) | 48-bit Morton code of the centroid inside the segment's centroid box
+YRT_HD void morton_item(const LbvhArrays& a, int i) {
+    int s = a.seg_of[i];
+    vec3 c = box_centroid(a.box_lo[i], a.box_hi[i]);
+    unsigned int qx = quant16(c.x, ordered_to_float(a.seg_cent_lo[3 * s + 0]), ordered_to_float(a.seg_cent_hi[3 * s + 0]));
+    unsigned int qy = quant16(c.y, ordered_to_float(a.seg_cent_lo[3 * s + 1]), ordered_to_float(a.seg_cent_hi[3 * s + 1]));
+    unsigned int qz = quant16(c.z, ordered_to_float(a.seg_cent_lo[3 * s + 2]), ordered_to_float(a.seg_cent_hi[3 * s + 2]));
+    unsigned long long m = (spread16(qx) << 2) | (spread16(qy) << 1) | spread16(qz);
+    a.keys[i] = ((unsigned long long)(unsigned)s << 48) | m;
+    a.order[i] = i;
+}
+
+YRT_HD int clz64_(unsigned long long x) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
+YRT_HD int clz32_(unsigned int x) {
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+
+// length of the common prefix of sorted keys i and j (index breaks ties); -1 outside [0,n)
+YRT_HD int delta_(const unsigned long long* keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    unsigned long long a = keys[i], b = keys[j];
+    if (a == b) return 64 + clz32_((unsigned)i ^ (unsigned)j);
+    return clz64_(a ^ b);
+}
+
+// Karras 2012, one internal node per call
+YRT_HD void karras_item(const LbvhArrays& a, int i) {
+    const unsigned long long* keys = a.keys;
+    int n = a.n;
+    int d = (delta_(keys, n, i, i + 1) - delta_(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta_(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta_(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta_(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta_(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta_(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + (d < 0 ? d : 0);
+    int first = i < j ? i : j, last = i < j ? j : i;
+    int lc, rc;
+    if (first == gamma) { lc = ~gamma; a.parent_leaf[gamma] = i; } else { lc = gamma; a.parent_int[gamma] = i; }
+    if (last == gamma + 1) { rc = ~(gamma + 1); a.parent_leaf[gamma + 1] = i; } else { rc = gamma + 1; a.parent_int[gamma + 1] = i; }
+    a.left[i] = lc;
+    a.right[i] = rc;
+    a.range_first[i] = first;
+    a.range_last[i] = last;
+    if (i == 0) a.parent_int[0] = -1;
+    a.flags[i] = 0;
+}
+
+YRT_HD void child_box_(const LbvhArrays& a, int c, float4& lo, float4& hi) {
+    if (c < 0) { int it = a.order[~c]; lo = a.box_lo[it]; hi = a.box_hi[it]; }
+    else { lo = a.node_lo[c]; hi = a.node_hi[c]; }
+}
+
+// bottom-up refit, one leaf per call; the second arrival at a node computes its bounds
+YRT_HD void refit_item(const LbvhArrays& a, int leaf) {
+    int p = a.parent_leaf[leaf];
+    while (p >= 0) {
+        YRT_FENCE();
+        int old = YRT_ATOMIC_ADD(&a.flags[p], 1);
+        if (old == 0) return;
+        YRT_FENCE();
+        float4 l0, h0, l1, h1;
+#if defined(__CUDA_ARCH__)
+        // children were written by other threads: read through L2, not the (incoherent) L1
+        {
+            int c0 = a.left[p], c1 = a.right[p];
+            if (c0 < 0) { int it = a.order[~c0]; l0 = a.box_lo[it]; h0 = a.box_hi[it]; }
+            else { l0 = __ldcg(&a.node_lo[c0]); h0 = __ldcg(&a.node_hi[c0]); }
+            if (c1 < 0) { int it = a.order[~c1]; l1 = a.box_lo[it]; h1 = a.box_hi[it]; }
+            else { l1 = __ldcg(&a.node_lo[c1]); h1 = __ldcg(&a.node_hi[c1]); }
+        }
+#else
+        child_box_(a, a.left[p], l0, h0);
+        child_box_(a, a.right[p], l1, h1);
+#endif
+        a.node_lo[p] = mk4(rmin(l0.x, l1.x), rmin(l0.y, l1.y), rmin(l0.z, l1.z), 0.f);
+        a.node_hi[p] = mk4(rmax(h0.x, h1.x), rmax(h0.y, h1.y), rmax(h0.z, h1.z), 0.f);
+        p = a.parent_int[p];
+    }
+}
+
+// reference of a child for traversal: subtrees of <= leaf_size items become one leaf
+YRT_HD int child_ref_(const LbvhArrays& a, int c) {
+    if (c < 0) return make_leaf_ref(~c, 1);
+    int cnt = a.range_last[c] - a.range_first[c] + 1;
+    if (cnt <= a.leaf_size) return make_leaf_ref(a.range_first[c], cnt);
+    return c;
+}
+
+// emit the 64-byte traversal node of internal node i and, if i is exactly a segment, its root ref
+YRT_HD void emit_item(const LbvhArrays& a, int i) {
+    int c0 = a.left[i], c1 = a.right[i];
+    float4 l0, h0, l1, h1;
+    child_box_(a, c0, l0, h0);
+    child_box_(a, c1, l1, h1);
+    float4* n = a.nodes + 4 * (size_t)i;
+    n[0] = mk4(l0.x, l0.y, l0.z, int_as_float(child_ref_(a, c0)));
+    n[1] = mk4(h0.x, h0.y, h0.z, int_as_float(child_ref_(a, c1)));
+    n[2] = mk4(l1.x, l1.y, l1.z, 0.f);
+    n[3] = mk4(h1.x, h1.y, h1.z, 0.f);
+    int first = a.range_first[i], last = a.range_last[i];
+    int s = a.seg_of[a.order[first]];
+    if (s == a.seg_of[a.order[last]] && first == a.seg_first[s] && last == a.seg_first[s + 1] - 1) {
+        a.seg_root[s] = child_ref_(a, i);
+    }
+}
+
+// segments of exactly one item have no internal node: their root is that leaf (one per segment)
+YRT_HD void single_root_item(const LbvhArrays& a, int s) {
+    int cnt = a.seg_first[s + 1] - a.seg_first[s];
+    if (cnt == 1) a.seg_root[s] = make_leaf_ref(a.seg_first[s], 1);
+}
+
+// depth of sorted leaf `leaf` below its segment root (counts internal nodes on the path)
+YRT_HD void depth_item(const LbvhArrays& a, int leaf) {
+    int s = a.seg_of[a.order[leaf]];
+    int sf = a.seg_first[s], sl = a.seg_first[s + 1] - 1;
+    if (sl == sf) return;
+    int d = 0;
+    int p = a.parent_leaf[leaf];
+    while (p >= 0) {
+        d++;
+        if (a.range_first[p] == sf && a.range_last[p] == sl) break;
+        p = a.parent_int[p];
+    }
+    YRT_ATOMIC_MAX(&a.seg_depth[s], d);
+}
+
+}  // namespace yrt

@@ -1,0 +1,633 @@
+// yrt_render.cu — the per-frame wavefront: persistent closest-hit / any-hit traversal kernels,
+// the shade kernel and the per-pixel resolve (sm_100a).
+//
+// Replaces raytrace() + shade() (src/raytrace.cpp:88-254) and the traversal they call
+// (src/scene.cpp:386-505).  One "slot" is one camera sample ((pixel, jj, ii), raytrace.cpp:232-241);
+// a batch is a run of image rows, all samples.  Per batch:
+//   k_trace_closest<primary>  rays generated in-kernel (eval_camera) -> hit + world position
+//   wave loop (depth = reflection recursion level):
+//     k_trace_any             one shadow ray per (hit, light), light-major so a warp shares a light
+//     k_shade                 Blinn-Phong / hair shading in light order; reflective hits push
+//                             {c, kr, la} on a per-slot stack and enqueue the mirror ray (compacted
+//                             queue); finished paths unwind the stack and write their radiance
+//     k_trace_closest<queue>  next wave's rays
+//   k_resolve                 ordered per-pixel sum over (jj,ii), divide by N*N, alpha = 1
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "yrt_internal.h"
+#include "yrt_shade.cuh"
+#include "yrt_trace.cuh"
+
+namespace yrt {
+
+#define TRACE_THREADS 128
+
+struct BatchParams {
+    camera_k cam;
+    vec3 amb;
+    int width, height, samples, spp;
+    int lr0;                      // first packed local row of the batch
+    int tile_rows, rank, world;
+    size_t cap_slots;             // stride of per-light / per-depth planes
+};
+
+// slot -> (i, j, ii, jj)
+__device__ __forceinline__ void slot_to_sample(const BatchParams& bp, unsigned slot, int& i, int& j, int& ii, int& jj) {
+    unsigned pix = slot / (unsigned)bp.spp;
+    unsigned s = slot - pix * (unsigned)bp.spp;
+    unsigned lr = pix / (unsigned)bp.width;
+    i = (int)(pix - lr * (unsigned)bp.width);
+    j = global_row(bp.lr0 + (int)lr, bp.tile_rows, bp.rank, bp.world);
+    jj = (int)(s / (unsigned)bp.samples);
+    ii = (int)(s - (unsigned)jj * (unsigned)bp.samples);
+}
+
+// warp-granular dynamic work fetch of a persistent kernel
+__device__ __forceinline__ unsigned warp_fetch(unsigned* counter, int lane) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(counter, 32u);
+    return __shfl_sync(0xffffffffu, base, 0);
+}
+
+// ---- closest hit --------------------------------------------------------------------------
+// PRIMARY: slot = work index, ray from the camera. Otherwise slot = act[idx] (or idx) and the ray
+// comes from ray_o/ray_d (o.xyz|tmin, d.xyz|tmax).
+template <bool PRIMARY>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(SceneView sv, BatchParams bp, const int* __restrict__ act,
+                                                                 const float4* __restrict__ ray_o,
+                                                                 const float4* __restrict__ ray_d, float4* __restrict__ hit_out,
+                                                                 float4* __restrict__ P_out, unsigned n, unsigned* counter) {
+    const int lane = threadIdx.x & 31;
+    int stack[YRT_STACK_CAP];
+    for (;;) {
+        unsigned base = warp_fetch(counter, lane);
+        if (base >= n) break;
+        unsigned idx = base + lane;
+        if (idx >= n) continue;
+        unsigned slot;
+        ray3 ray;
+        if (PRIMARY) {
+            slot = idx;
+            int i, j, ii, jj;
+            slot_to_sample(bp, slot, i, j, ii, jj);
+            float u, v;
+            sample_uv(i, j, ii, jj, bp.samples, bp.width, bp.height, u, v);
+            ray = eval_camera(bp.cam, u, v);
+        } else {
+            slot = act ? (unsigned)act[idx] : idx;
+            float4 o = ray_o[slot], d = ray_d[slot];
+            ray.o = xyz(o); ray.d = xyz(d); ray.tmin = o.w; ray.tmax = d.w;
+        }
+        HitRec h;
+        trace_ray<false>(sv, ray, h, stack, nullptr);
+        float4 P = mk4(0.f, 0.f, 0.f, h.dist);
+        if (h.si >= 0) {
+            int kind;
+            vec3 p = eval_hit_pos(sv, h.si, h.prim, h.w1, h.w2, kind);
+            P.x = p.x; P.y = p.y; P.z = p.z;
+        }
+        hit_out[slot] = mk4(int_as_float(h.si), int_as_float(h.prim), h.w1, h.w2);
+        P_out[slot] = P;
+    }
+}
+
+// ---- any hit: shadow rays, one per (hit, light) ------------------------------------------------
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_any_lights(SceneView sv, size_t cap_slots, const int* __restrict__ act,
+                                                                    const float4* __restrict__ hit, const float4* __restrict__ P,
+                                                                    uint8_t* __restrict__ vis, unsigned n_act, unsigned n_items,
+                                                                    unsigned* counter) {
+    const int lane = threadIdx.x & 31;
+    int stack[YRT_STACK_CAP];
+    for (;;) {
+        unsigned base = warp_fetch(counter, lane);
+        if (base >= n_items) break;
+        unsigned t = base + lane;
+        if (t >= n_items) continue;
+        unsigned k = t / n_act;
+        unsigned a = t - k * n_act;
+        unsigned slot = act ? (unsigned)act[a] : a;
+        float4 h = hit[slot];
+        if (float_as_int(h.x) < 0) continue;   // miss: shade() returns before the light loop
+        float4 Pq = P[slot];
+        vec3 p = xyz(Pq), l, ke;
+        float r;
+        light_vector(sv, (int)k, p, l, r, ke);
+        ray3 sr = shadow_ray(p, l, r);
+        HitRec hr;
+        bool occ = trace_ray<true>(sv, sr, hr, stack, nullptr);
+        vis[(size_t)k * cap_slots + slot] = occ ? 0 : 1;
+    }
+}
+
+// any hit on explicit rays (intersect_any, scene.cpp:489)
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_any_rays(SceneView sv, const float4* __restrict__ ray_o,
+                                                                  const float4* __restrict__ ray_d, uint8_t* __restrict__ occ_out,
+                                                                  unsigned n, unsigned* counter) {
+    const int lane = threadIdx.x & 31;
+    int stack[YRT_STACK_CAP];
+    for (;;) {
+        unsigned base = warp_fetch(counter, lane);
+        if (base >= n) break;
+        unsigned idx = base + lane;
+        if (idx >= n) continue;
+        float4 o = ray_o[idx], d = ray_d[idx];
+        ray3 ray;
+        ray.o = xyz(o); ray.d = xyz(d); ray.tmin = o.w; ray.tmax = d.w;
+        HitRec hr;
+        occ_out[idx] = trace_ray<true>(sv, ray, hr, stack, nullptr) ? 1 : 0;
+    }
+}
+
+// ---- shade ------------------------------------------------------------------------------------
+struct FrameCounters { unsigned long long hits, reflections, misses, pad; };
+
+__global__ void __launch_bounds__(256) k_shade(SceneView sv, BatchParams bp, int depth, int max_depth, const int* __restrict__ act,
+                                               unsigned n_act, const float4* __restrict__ hit, const float4* __restrict__ P,
+                                               const uint8_t* __restrict__ vis, float4* __restrict__ ray_o, float4* __restrict__ ray_d,
+                                               float4* __restrict__ pstack, float4* __restrict__ rad, int* __restrict__ next_act,
+                                               int* __restrict__ next_count, FrameCounters* __restrict__ fc) {
+    __shared__ float lut[256];
+    lut[threadIdx.x] = sv.srgb_lut[threadIdx.x];
+    __syncthreads();
+    unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = a < n_act;
+    bool is_hit = false, spawn = false;
+    unsigned slot = 0;
+    if (valid) {
+        slot = act ? (unsigned)act[a] : a;
+        float4 h = hit[slot];
+        int si = float_as_int(h.x);
+        vec3 value = mk3(0.f, 0.f, 0.f);          // miss: {0,0,0,1}, raytrace.cpp:93
+        if (si >= 0) {
+            is_hit = true;
+            vec3 ro = depth == 0 ? bp.cam.frame.o : xyz(ray_o[slot]);
+            vec3 c, kr, la;
+            ray3 rr;
+            const uint8_t* vrow = vis + slot;
+            size_t cap = bp.cap_slots;
+            spawn = shade_hit(sv, si, float_as_int(h.y), h.z, h.w, ro, bp.amb, lut,
+                              [&](int k) { return vrow[(size_t)k * cap] != 0; }, depth + 1 < max_depth, value, c, kr, la, rr);
+            if (spawn) {
+                float4* f = pstack + ((size_t)depth * cap + slot) * 3;
+                f[0] = mk4(c.x, c.y, c.z, 0.f);
+                f[1] = mk4(kr.x, kr.y, kr.z, 0.f);
+                f[2] = mk4(la.x, la.y, la.z, 0.f);
+                ray_o[slot] = mk4(rr.o.x, rr.o.y, rr.o.z, rr.tmin);
+                ray_d[slot] = mk4(rr.d.x, rr.d.y, rr.d.z, rr.tmax);
+            }
+        }
+        if (!spawn) {
+            // unwind the recursion: each level closes with c + col*kr, then + la (raytrace.cpp:203,206)
+            size_t cap = bp.cap_slots;
+            for (int d = depth - 1; d >= 0; d--) {
+                const float4* f = pstack + ((size_t)d * cap + slot) * 3;
+                value = combine_reflection(xyz(f[0]), value, xyz(f[1]), xyz(f[2]));
+            }
+            rad[slot] = mk4(value.x, value.y, value.z, 1.0f);
+        }
+    }
+    // compacted queue of the next wave + frame counters (warp-aggregated)
+    unsigned m_spawn = __ballot_sync(0xffffffffu, spawn);
+    unsigned m_hit = __ballot_sync(0xffffffffu, is_hit);
+    unsigned m_valid = __ballot_sync(0xffffffffu, valid);
+    int lane = threadIdx.x & 31;
+    if (m_spawn) {
+        int basei = 0;
+        if (lane == 0) basei = atomicAdd(next_count, __popc(m_spawn));
+        basei = __shfl_sync(0xffffffffu, basei, 0);
+        if (spawn) next_act[basei + __popc(m_spawn & ((1u << lane) - 1u))] = (int)slot;
+    }
+    if (lane == 0 && m_valid) {
+        if (m_hit) atomicAdd(&fc->hits, (unsigned long long)__popc(m_hit));
+        if (m_spawn) atomicAdd(&fc->reflections, (unsigned long long)__popc(m_spawn));
+        unsigned miss = m_valid & ~m_hit;
+        if (miss) atomicAdd(&fc->misses, (unsigned long long)__popc(miss));
+    }
+}
+
+// ---- resolve: raytrace.cpp:241-249 ------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resolve(const float4* __restrict__ rad, float4* __restrict__ out, int n_pix, int spp,
+                                                 size_t out_pix0) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pix) return;
+    const float4* r = rad + (size_t)p * spp;
+    float x = 0.f, y = 0.f, z = 0.f;
+    for (int s = 0; s < spp; s++) {   // (jj outer, ii inner) = slot order
+        float4 v = r[s];
+        x += v.x; y += v.y; z += v.z;
+    }
+    float d = (float)spp;             // float(samples * samples)
+    out[out_pix0 + p] = mk4(x / d, y / d, z / d, 1.0f);
+}
+
+// ---- parity hook: hit records -> (instance, shape, element) ids ----------------------------------
+__global__ void k_hit_ids(SceneView sv, const float4* __restrict__ hit, const float4* __restrict__ P, int n, int* __restrict__ ids,
+                          float* __restrict__ dist, float* __restrict__ uv) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    float4 h = hit[s];
+    int si = float_as_int(h.x);
+    int inst = -1, shape = -1, ei = -1;
+    float d = 0.f, a = 0.f, b = 0.f;
+    if (si >= 0) {
+        const float4* ir = sv.inst_recs + 4 * (size_t)si;
+        inst = float_as_int(ir[1].w);
+        shape = float_as_int(ir[3].w) & 0x0fffffff;
+        ei = float_as_int(sv.prim_recs[3 * (size_t)float_as_int(h.y)].w);
+        d = P[s].w; a = h.z; b = h.w;
+    }
+    ids[3 * (size_t)s] = inst; ids[3 * (size_t)s + 1] = shape; ids[3 * (size_t)s + 2] = ei;
+    if (dist) dist[s] = d;
+    if (uv) { uv[2 * (size_t)s] = a; uv[2 * (size_t)s + 1] = b; }
+}
+
+__global__ void k_unpack_rows(const float4* __restrict__ packed, float4* __restrict__ full, int width, int n_rows, int tile_rows,
+                              int rank, int world) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)n_rows * width;
+    if (t >= n) return;
+    int lr = (int)(t / width), i = (int)(t - (size_t)lr * width);
+    int j = global_row(lr, tile_rows, rank, world);
+    full[(size_t)j * width + i] = packed[t];
+}
+
+// tonemap(hdr, 0, false) of src/image.cpp:55-78: powf(2,0)=1 scale, powf(x,1/2.2f), clamp, truncate
+__global__ void k_tonemap(const float4* __restrict__ in, uchar4* __restrict__ out, size_t n) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float4 h = in[t];
+    const float e = 1.0f;   // powf(2, exposure) with exposure 0
+    float g = 1 / 2.2f;
+    float x = powf(h.x * e, g), y = powf(h.y * e, g), z = powf(h.z * e, g), w = h.w;
+    uchar4 o;
+    o.x = (unsigned char)(rclamp(x, 0.0f, 1.0f) * 255);
+    o.y = (unsigned char)(rclamp(y, 0.0f, 1.0f) * 255);
+    o.z = (unsigned char)(rclamp(z, 0.0f, 1.0f) * 255);
+    o.w = (unsigned char)(rclamp(w, 0.0f, 1.0f) * 255);
+    out[t] = o;
+}
+
+// ------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------
+camera_k make_camera_k(const yrt_camera* cam) {
+    camera_k c;
+    const float* f = cam->frame;
+    c.frame.x = mk3(f[0], f[1], f[2]); c.frame.y = mk3(f[3], f[4], f[5]); c.frame.z = mk3(f[6], f[7], f[8]); c.frame.o = mk3(f[9], f[10], f[11]);
+    // raytrace.cpp:21-22 on the host: tan() of a float argument resolves to tanf
+    c.h = 2.0f * cam->focus * tanf(cam->fovy / 2.0f);
+    c.w = c.h * cam->aspect;
+    c.focus = cam->focus;
+    return c;
+}
+
+static int env_int(const char* name, int def) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : def;
+}
+
+struct PhaseTimer {
+    struct Span { int cat; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    bool on = false;
+    cudaStream_t st = nullptr;
+    cudaEvent_t f0 = nullptr, f1 = nullptr;   // frame begin / end
+    int max_depth_seen = 0;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    void begin(int cat) { if (!on) return; Span s; s.cat = cat; s.a = get(); s.b = get(); cudaEventRecord(s.a, st); spans.push_back(s); }
+    void end() { if (!on) return; cudaEventRecord(spans.back().b, st); }
+    void collect(float out[5], int64_t& launches) {
+        for (int i = 0; i < 5; i++) out[i] = 0.f;
+        for (auto& s : spans) { float ms = 0.f; cudaEventElapsedTime(&ms, s.a, s.b); out[s.cat] += ms; pool.push_back(s.a); pool.push_back(s.b); }
+        launches = (int64_t)spans.size();
+        spans.clear();
+    }
+    ~PhaseTimer() { for (auto e : pool) cudaEventDestroy(e); for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); } }
+};
+enum { CAT_CLOSEST = 0, CAT_ANY = 1, CAT_SHADE = 2, CAT_OTHER = 3 };
+
+static int ensure_workspace(DevScene& ds, size_t slots, int n_lights, int depth_cap, bool reflective) {
+    Workspace& w = ds.ws;
+    int dev = ds.device;
+    if (slots > w.cap_slots || n_lights > w.cap_lights || (reflective ? depth_cap : 0) > w.cap_depth) {
+        size_t cs = std::max(slots, w.cap_slots);
+        int cl = std::max(n_lights, w.cap_lights);
+        int cd = std::max(reflective ? depth_cap : 0, w.cap_depth);
+        YRT_TRY(w.hit.alloc(sizeof(float4) * cs, dev));
+        YRT_TRY(w.P.alloc(sizeof(float4) * cs, dev));
+        YRT_TRY(w.rad.alloc(sizeof(float4) * cs, dev));
+        YRT_TRY(w.vis.alloc((size_t)std::max(cl, 1) * cs, dev));
+        if (cd > 0) {
+            YRT_TRY(w.ray_o.alloc(sizeof(float4) * cs, dev));
+            YRT_TRY(w.ray_d.alloc(sizeof(float4) * cs, dev));
+            YRT_TRY(w.pstack.alloc(sizeof(float4) * 3 * cs * (size_t)cd, dev));
+            YRT_TRY(w.act0.alloc(sizeof(int) * cs, dev));
+            YRT_TRY(w.act1.alloc(sizeof(int) * cs, dev));
+        }
+        w.cap_slots = cs; w.cap_lights = cl; w.cap_depth = cd;
+    }
+    YRT_TRY(w.counters.alloc(sizeof(unsigned) * 8192, dev));
+    YRT_TRY(w.stats.alloc(sizeof(FrameCounters) + 64, dev));
+    return YRT_OK;
+}
+
+static int persistent_grid(DevScene& ds, const void* kernel) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRACE_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    int cap = env_int("YRT_BLOCKS_PER_SM", 0);
+    if (cap > 0 && cap < per_sm) per_sm = cap;
+    return ds.sm_count * per_sm;
+}
+
+struct CounterRing {
+    unsigned* base; int next; int cap; cudaStream_t st;
+    int init(DevScene& ds, cudaStream_t s) {
+        base = ds.ws.counters.as<unsigned>(); next = 0; cap = 8192; st = s;
+        YRT_CUDA(cudaMemsetAsync(base, 0, sizeof(unsigned) * cap, st));
+        return YRT_OK;
+    }
+    int get(unsigned** out) {
+        if (next == cap) { YRT_CUDA(cudaMemsetAsync(base, 0, sizeof(unsigned) * cap, st)); next = 0; }
+        *out = base + next++;
+        return YRT_OK;
+    }
+};
+
+// batch of rows [lr0, lr0+nrows) of the rank's packed rows; primary hits only when ids_mode
+static int run_batch(DevScene& ds, const RenderParams& rp, int lr0, int nrows, size_t cap_slots, float4* d_out, cudaStream_t st,
+                     PhaseTimer& pt, CounterRing& ring, int depth_cap, bool reflective, bool primary_only, int& max_depth_seen) {
+    Workspace& w = ds.ws;
+    BatchParams bp;
+    bp.cam = rp.cam; bp.amb = rp.amb; bp.width = rp.width; bp.height = rp.height; bp.samples = rp.samples;
+    bp.spp = rp.samples * rp.samples; bp.lr0 = lr0; bp.tile_rows = rp.tile_rows; bp.rank = rp.rank; bp.world = rp.world;
+    bp.cap_slots = cap_slots;
+    unsigned n = (unsigned)((size_t)nrows * rp.width * bp.spp);
+    int nl = ds.view.n_lights;
+    if (!ds.grid_closest_primary) ds.grid_closest_primary = persistent_grid(ds, (const void*)k_trace_closest<true>);
+    if (!ds.grid_closest_queue) ds.grid_closest_queue = persistent_grid(ds, (const void*)k_trace_closest<false>);
+    if (!ds.grid_any) ds.grid_any = persistent_grid(ds, (const void*)k_trace_any_lights);
+    const int g_closest_p = ds.grid_closest_primary, g_closest_q = ds.grid_closest_queue, g_any = ds.grid_any;
+    auto grid_of = [](int g, unsigned items) { unsigned need = (items + TRACE_THREADS - 1) / TRACE_THREADS; return (int)std::max(1u, std::min((unsigned)g, need)); };
+
+    unsigned* ctr = nullptr;
+    YRT_TRY(ring.get(&ctr));
+    pt.begin(CAT_CLOSEST);
+    k_trace_closest<true><<<grid_of(g_closest_p, n), TRACE_THREADS, 0, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(),
+                                                                           w.P.as<float4>(), n, ctr);
+    pt.end();
+    if (primary_only) { YRT_CUDA(cudaGetLastError()); return YRT_OK; }
+
+    FrameCounters* fc = w.stats.as<FrameCounters>();
+    int* next_count = (int*)((char*)w.stats.p + sizeof(FrameCounters));
+    const int* act = nullptr;
+    int* act_bufs[2] = {w.act0.as<int>(), w.act1.as<int>()};
+    unsigned n_act = n;
+    for (int depth = 0;; depth++) {
+        if (depth + 1 > max_depth_seen) max_depth_seen = depth + 1;
+        if (nl > 0) {
+            unsigned long long items64 = (unsigned long long)n_act * (unsigned long long)nl;
+            if (items64 >= 0xfffffff0ull) { set_error("too many shadow rays in one batch (%llu): lower YRT_BATCH_SLOTS", items64); return YRT_ERR_UNSUPPORTED; }
+            unsigned items = (unsigned)items64;
+            YRT_TRY(ring.get(&ctr));
+            pt.begin(CAT_ANY);
+            k_trace_any_lights<<<grid_of(g_any, items), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
+                                                                               w.vis.as<uint8_t>(), n_act, items, ctr);
+            pt.end();
+        }
+        if (reflective) YRT_CUDA(cudaMemsetAsync(next_count, 0, sizeof(int), st));
+        int* next_act = reflective ? act_bufs[depth & 1] : nullptr;
+        pt.begin(CAT_SHADE);
+        k_shade<<<(n_act + 255) / 256, 256, 0, st>>>(ds.view, bp, depth, depth_cap, act, n_act, w.hit.as<float4>(), w.P.as<float4>(),
+                                                   w.vis.as<uint8_t>(), w.ray_o.as<float4>(), w.ray_d.as<float4>(), w.pstack.as<float4>(),
+                                                   w.rad.as<float4>(), next_act, next_count, fc);
+        pt.end();
+        if (!reflective || depth + 1 >= depth_cap) break;
+        int h_next = 0;
+        YRT_CUDA(cudaMemcpyAsync(&h_next, next_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        YRT_CUDA(cudaStreamSynchronize(st));
+        if (h_next <= 0) break;
+        n_act = (unsigned)h_next;
+        act = next_act;
+        YRT_TRY(ring.get(&ctr));
+        pt.begin(CAT_CLOSEST);
+        k_trace_closest<false><<<grid_of(g_closest_q, n_act), TRACE_THREADS, 0, st>>>(ds.view, bp, act, w.ray_o.as<float4>(), w.ray_d.as<float4>(),
+                                                                                    w.hit.as<float4>(), w.P.as<float4>(), n_act, ctr);
+        pt.end();
+    }
+    int n_pix = nrows * rp.width;
+    pt.begin(CAT_OTHER);
+    k_resolve<<<(n_pix + 255) / 256, 256, 0, st>>>(w.rad.as<float4>(), d_out, n_pix, bp.spp, (size_t)lr0 * rp.width);
+    pt.end();
+    YRT_CUDA(cudaGetLastError());
+    return YRT_OK;
+}
+
+static int check_params(const RenderParams& rp) {
+    if (rp.width <= 0 || rp.height <= 0 || rp.samples <= 0) { set_error("width, height and samples must be positive"); return YRT_ERR_INVALID; }
+    if (rp.tile_rows <= 0 || rp.world <= 0 || rp.rank < 0 || rp.rank >= rp.world) { set_error("bad row-tile partition (tile_rows %d rank %d world %d)", rp.tile_rows, rp.rank, rp.world); return YRT_ERR_INVALID; }
+    if ((long long)rp.samples * rp.samples > (1 << 20)) { set_error("samples too large"); return YRT_ERR_INVALID; }
+    return YRT_OK;
+}
+
+static int batch_rows_for(const RenderParams& rp, int n_lights, int own_rows) {
+    long long target = env_int("YRT_BATCH_SLOTS", 4 << 20);
+    long long per_row = (long long)rp.width * rp.samples * rp.samples;
+    long long lim = 0xfffffff0ll / std::max(1, n_lights);
+    if (target > lim) target = lim;
+    long long rows = std::max(1ll, target / per_row);
+    return (int)std::min<long long>(rows, std::max(own_rows, 1));
+}
+
+int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cudaStream_t st, yrt_stats* stats, bool sync_for_stats) {
+    YRT_TRY(check_params(rp));
+    YRT_CUDA(cudaSetDevice(ds.device));
+    int own = rows_owned(rp.height, rp.tile_rows, rp.rank, rp.world);
+    int spp = rp.samples * rp.samples;
+    int nl = ds.view.n_lights;
+    bool reflective = ds.has_reflective;
+    int depth_cap = std::max(1, env_int("YRT_MAX_DEPTH", 16));
+    int batch_rows = batch_rows_for(rp, nl, own);
+    size_t cap_slots = (size_t)batch_rows * rp.width * spp;
+    YRT_TRY(ensure_workspace(ds, cap_slots, nl, depth_cap, reflective));
+    cap_slots = ds.ws.cap_slots;
+
+    if (!ds.timer) ds.timer = new PhaseTimer();
+    PhaseTimer& pt = *ds.timer;
+    pt.on = stats != nullptr;
+    pt.st = st;
+    if (stats) {
+        if (!pt.f0) { pt.f0 = pt.get(); pt.f1 = pt.get(); }
+        cudaEventRecord(pt.f0, st);
+    }
+    CounterRing ring;
+    YRT_TRY(ring.init(ds, st));
+    YRT_CUDA(cudaMemsetAsync(ds.ws.stats.p, 0, sizeof(FrameCounters) + 64, st));
+    int max_depth_seen = 0;
+    for (int lr0 = 0; lr0 < own; lr0 += batch_rows) {
+        int nrows = std::min(batch_rows, own - lr0);
+        YRT_TRY(run_batch(ds, rp, lr0, nrows, cap_slots, d_out, st, pt, ring, depth_cap, reflective, false, max_depth_seen));
+    }
+    pt.max_depth_seen = max_depth_seen;
+    if (stats) {
+        cudaEventRecord(pt.f1, st);
+        if (sync_for_stats) YRT_TRY(collect_stats_device(ds, rp, stats));
+    }
+    return YRT_OK;
+}
+
+int collect_stats_device(DevScene& ds, const RenderParams& rp, yrt_stats* stats) {
+    if (!ds.timer || !ds.timer->f0) { set_error("collect_stats_device: no frame was rendered with stats"); return YRT_ERR_INVALID; }
+    PhaseTimer& pt = *ds.timer;
+    YRT_CUDA(cudaSetDevice(ds.device));
+    YRT_CUDA(cudaStreamSynchronize(pt.st));
+    FrameCounters fc;
+    YRT_CUDA(cudaMemcpy(&fc, ds.ws.stats.p, sizeof(fc), cudaMemcpyDeviceToHost));
+    float cat[5];
+    int64_t launches = 0;
+    pt.collect(cat, launches);
+    memset(stats, 0, sizeof(*stats));
+    int own = rows_owned(rp.height, rp.tile_rows, rp.rank, rp.world);
+    stats->primary_rays = (int64_t)own * rp.width * rp.samples * rp.samples;
+    stats->reflection_rays = (int64_t)fc.reflections;
+    stats->shadow_rays = (int64_t)fc.hits * ds.view.n_lights;
+    stats->launches = launches;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, pt.f0, pt.f1);
+    stats->ms_total = ms;
+    stats->ms_trace_closest = cat[CAT_CLOSEST];
+    stats->ms_trace_any = cat[CAT_ANY];
+    stats->ms_shade = cat[CAT_SHADE];
+    stats->ms_other = cat[CAT_OTHER];
+    stats->max_depth = pt.max_depth_seen;
+    stats->n_gpus = 1;
+    return YRT_OK;
+}
+
+int trace_primary_device(DevScene& ds, const RenderParams& rp_in, int32_t* h_ids, float* h_dist, float* h_uv) {
+    RenderParams rp = rp_in;
+    rp.tile_rows = std::max(rp.height, 1); rp.rank = 0; rp.world = 1;
+    YRT_TRY(check_params(rp));
+    YRT_CUDA(cudaSetDevice(ds.device));
+    cudaStream_t st = ds.stream;
+    int spp = rp.samples * rp.samples;
+    int batch_rows = batch_rows_for(rp, 1, rp.height);
+    size_t cap_slots = (size_t)batch_rows * rp.width * spp;
+    YRT_TRY(ensure_workspace(ds, cap_slots, ds.view.n_lights, 1, false));
+    DevBuf d_ids, d_dist, d_uv;
+    YRT_TRY(d_ids.alloc(sizeof(int) * 3 * cap_slots, ds.device));
+    YRT_TRY(d_dist.alloc(sizeof(float) * cap_slots, ds.device));
+    YRT_TRY(d_uv.alloc(sizeof(float) * 2 * cap_slots, ds.device));
+    PhaseTimer pt;
+    CounterRing ring;
+    YRT_TRY(ring.init(ds, st));
+    int mds = 0;
+    for (int lr0 = 0; lr0 < rp.height; lr0 += batch_rows) {
+        int nrows = std::min(batch_rows, rp.height - lr0);
+        size_t n = (size_t)nrows * rp.width * spp;
+        YRT_TRY(run_batch(ds, rp, lr0, nrows, ds.ws.cap_slots, nullptr, st, pt, ring, 1, false, true, mds));
+        k_hit_ids<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ds.view, ds.ws.hit.as<float4>(), ds.ws.P.as<float4>(), (int)n, d_ids.as<int>(),
+                                                             d_dist.as<float>(), d_uv.as<float>());
+        YRT_CUDA(cudaGetLastError());
+        size_t off = (size_t)lr0 * rp.width * spp;
+        YRT_CUDA(cudaMemcpyAsync(h_ids + 3 * off, d_ids.p, sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, st));
+        if (h_dist) YRT_CUDA(cudaMemcpyAsync(h_dist + off, d_dist.p, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+        if (h_uv) YRT_CUDA(cudaMemcpyAsync(h_uv + 2 * off, d_uv.p, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, st));
+        YRT_CUDA(cudaStreamSynchronize(st));
+    }
+    return YRT_OK;
+}
+
+int intersect_rays_device(DevScene& ds, const float* h_rays, int64_t n, bool any, int32_t* h_ids, float* h_dist, float* h_uv,
+                          uint8_t* h_occ) {
+    if (n < 0 || (n > 0 && !h_rays)) { set_error("bad ray array"); return YRT_ERR_INVALID; }
+    if (n == 0) return YRT_OK;
+    YRT_CUDA(cudaSetDevice(ds.device));
+    cudaStream_t st = ds.stream;
+    const int64_t chunk = 1 << 22;
+    DevBuf ro, rd, hit, P, ids, dist, uv, occ, ctr;
+    int64_t c = std::min(chunk, n);
+    YRT_TRY(ro.alloc(sizeof(float4) * c, ds.device));
+    YRT_TRY(rd.alloc(sizeof(float4) * c, ds.device));
+    YRT_TRY(hit.alloc(sizeof(float4) * c, ds.device));
+    YRT_TRY(P.alloc(sizeof(float4) * c, ds.device));
+    YRT_TRY(ids.alloc(sizeof(int) * 3 * c, ds.device));
+    YRT_TRY(dist.alloc(sizeof(float) * c, ds.device));
+    YRT_TRY(uv.alloc(sizeof(float) * 2 * c, ds.device));
+    YRT_TRY(occ.alloc((size_t)c, ds.device));
+    YRT_TRY(ctr.alloc(sizeof(unsigned), ds.device));
+    std::vector<float4> ho(c), hd(c);
+    int g_c = persistent_grid(ds, (const void*)k_trace_closest<false>);
+    int g_a = persistent_grid(ds, (const void*)k_trace_any_rays);
+    BatchParams bp;
+    memset(&bp, 0, sizeof(bp));
+    for (int64_t off = 0; off < n; off += chunk) {
+        int64_t m = std::min(chunk, n - off);
+        for (int64_t i = 0; i < m; i++) {
+            const float* r = h_rays + 8 * (off + i);
+            ho[i] = mk4(r[0], r[1], r[2], r[6]);
+            hd[i] = mk4(r[3], r[4], r[5], r[7]);
+        }
+        YRT_CUDA(cudaMemcpyAsync(ro.p, ho.data(), sizeof(float4) * m, cudaMemcpyHostToDevice, st));
+        YRT_CUDA(cudaMemcpyAsync(rd.p, hd.data(), sizeof(float4) * m, cudaMemcpyHostToDevice, st));
+        YRT_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(unsigned), st));
+        unsigned need = (unsigned)((m + TRACE_THREADS - 1) / TRACE_THREADS);
+        if (any) {
+            k_trace_any_rays<<<std::max(1u, std::min((unsigned)g_a, need)), TRACE_THREADS, 0, st>>>(ds.view, ro.as<float4>(), rd.as<float4>(),
+                                                                                                  occ.as<uint8_t>(), (unsigned)m, ctr.as<unsigned>());
+            YRT_CUDA(cudaGetLastError());
+            YRT_CUDA(cudaMemcpyAsync(h_occ + off, occ.p, (size_t)m, cudaMemcpyDeviceToHost, st));
+        } else {
+            k_trace_closest<false><<<std::max(1u, std::min((unsigned)g_c, need)), TRACE_THREADS, 0, st>>>(
+                ds.view, bp, nullptr, ro.as<float4>(), rd.as<float4>(), hit.as<float4>(), P.as<float4>(), (unsigned)m, ctr.as<unsigned>());
+            k_hit_ids<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(ds.view, hit.as<float4>(), P.as<float4>(), (int)m, ids.as<int>(),
+                                                                 dist.as<float>(), uv.as<float>());
+            YRT_CUDA(cudaGetLastError());
+            YRT_CUDA(cudaMemcpyAsync(h_ids + 3 * off, ids.p, sizeof(int) * 3 * m, cudaMemcpyDeviceToHost, st));
+            if (h_dist) YRT_CUDA(cudaMemcpyAsync(h_dist + off, dist.p, sizeof(float) * m, cudaMemcpyDeviceToHost, st));
+            if (h_uv) YRT_CUDA(cudaMemcpyAsync(h_uv + 2 * off, uv.p, sizeof(float) * 2 * m, cudaMemcpyDeviceToHost, st));
+        }
+        YRT_CUDA(cudaStreamSynchronize(st));
+    }
+    return YRT_OK;
+}
+
+void destroy_device_scene(DevScene& ds) {
+    cudaSetDevice(ds.device);
+    if (ds.stream) {
+        cudaStreamSynchronize(ds.stream);
+        cudaStreamDestroy(ds.stream);
+        ds.stream = nullptr;
+    }
+    delete ds.timer;
+    ds.timer = nullptr;
+}
+
+int unpack_rows_device(const float4* d_packed, float4* d_full, int width, int height, int tile_rows, int rank, int world, cudaStream_t st) {
+    int own = rows_owned(height, tile_rows, rank, world);
+    size_t n = (size_t)own * width;
+    if (n == 0) return YRT_OK;
+    k_unpack_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_packed, d_full, width, own, tile_rows, rank, world);
+    YRT_CUDA(cudaGetLastError());
+    return YRT_OK;
+}
+
+int tonemap_device(int device, const float* h_rgba, int width, int height, uint8_t* h_out) {
+    YRT_CUDA(cudaSetDevice(device));
+    size_t n = (size_t)width * height;
+    DevBuf in, out;
+    YRT_TRY(in.upload(h_rgba, sizeof(float4) * n, device, 0));
+    YRT_TRY(out.alloc(sizeof(uchar4) * n, device));
+    k_tonemap<<<(unsigned)((n + 255) / 256), 256>>>(in.as<float4>(), out.as<uchar4>(), n);
+    YRT_CUDA(cudaGetLastError());
+    YRT_CUDA(cudaMemcpy(h_out, out.p, sizeof(uchar4) * n, cudaMemcpyDeviceToHost));
+    return YRT_OK;
+}
+
+}  // namespace yrt

@@ -1,0 +1,98 @@
+// yrt_scene.cuh — device-resident scene layout (what lives in HBM) and node/leaf references.
+//
+// All records are multiples of 16 bytes and are fetched with 128-bit loads.
+//   BVH node (64 B, TLAS and BLAS alike; two-child-box layout):
+//     q0 = child0.lo.xyz | child0 ref      q1 = child0.hi.xyz | child1 ref
+//     q2 = child1.lo.xyz | -               q3 = child1.hi.xyz | -
+//   prim record (48 B, in BLAS leaf order, all shapes concatenated):
+//     triangle: q0 = v0.xyz | ei     q1 = v1.xyz | -      q2 = v2.xyz | -
+//     line:     q0 = v0.xyz | ei     q1 = v1.xyz | r0     q2 = r1, -, -, -
+//     point:    q0 = p.xyz  | ei     q1 = r, -, -, -
+//   prim attribute record (64 B, same order; pre-gathered shape::norm / shape::texcoord):
+//     q0 = n0.xyz | uv0.x   q1 = n1.xyz | uv0.y   q2 = n2.xyz | uv1.x   q3 = uv1.y, uv2.x, uv2.y, -
+//   instance record (64 B, in TLAS leaf order):
+//     q0 = frame.x | blas root ref   q1 = frame.y | instance index (scn->instances order)
+//     q2 = frame.z | material index  q3 = frame.o | shape index | kind << 28
+//   material record (64 B): kd.xyz|ns  ks.xyz|kd_tex  kr.xyz|ks_tex  ke.xyz|-
+//   light record (80 B): frame x,y,z,o (4 x float4, .w unused) + q4 = pos0.xyz | -,  then ke in q0..q2 .w
+#pragma once
+#include "yrt_math.cuh"
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#else
+#include <vector_types.h>
+#endif
+
+namespace yrt {
+
+// ---- references held in node child slots and on the traversal stack -----------------------
+//   ref >= 0         : internal node index
+//   ref <  0         : leaf; ~ref = (first << 3) | (count - 1), 1 <= count <= 8
+//   YRT_REF_SENTINEL : traversal stack marker "leave the current instance"
+#define YRT_REF_SENTINEL ((int)0x80000000)
+#define YRT_LEAF_MAX_COUNT 8
+#define YRT_MAX_LEAF_FIRST ((1 << 28) - 2)
+#define YRT_STACK_CAP 128   /* traversal stack entries (TLAS + BLAS levels simultaneously live); checked against the built depth */
+
+YRT_HD int make_leaf_ref(int first, int count) { return ~((first << 3) | (count - 1)); }
+YRT_HD int leaf_first(int ref) { return (~ref) >> 3; }
+YRT_HD int leaf_count(int ref) { return ((~ref) & 7) + 1; }
+
+YRT_HD float int_as_float(int i) {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(i);
+#else
+    union { int i; float f; } u; u.i = i; return u.f;
+#endif
+}
+YRT_HD int float_as_int(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(f);
+#else
+    union { int i; float f; } u; u.f = f; return u.i;
+#endif
+}
+
+YRT_HD float4 ld4(const float4* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+YRT_HD float4 mk4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+YRT_HD vec3 xyz(const float4& q) { return mk3(q.x, q.y, q.z); }
+
+// ---- what a kernel sees ------------------------------------------------------------------
+struct SceneView {
+    const float4* tlas_nodes;   // 4 per node
+    const float4* blas_nodes;   // 4 per node (all shapes in one array)
+    const float4* inst_recs;    // 4 per instance, TLAS leaf order
+    const float4* prim_recs;    // 3 per prim, BLAS leaf order
+    const float4* prim_attrs;   // 4 per prim
+    const float4* mat_recs;     // 4 per material
+    const float4* light_recs;   // 5 per light
+    const uint8_t* tex_rgba8;   // all textures
+    const int4* tex_info;       // per texture: w, h, byte offset lo, byte offset hi
+    const float* srgb_lut;      // 256 floats: fminf(1, powf(b/255, 2.2f)) computed with the HOST libm
+    // exact-distance ties: position of each instance / element in the reference's own (ray-independent)
+    // BVH visit sequence — the later-visited candidate wins a tie there (see yrt_host.cu); read on ties only
+    const int* inst_rank;       // per instance slot (TLAS leaf order)
+    const int* prim_rank;       // per prim slot (BLAS leaf order), rank inside its shape
+    int tlas_root;              // ref
+    int n_lights;
+    int n_active_instances;
+};
+
+// closest-hit result (16 B on the wire: si, prim, w1, w2; dist kept for the parity hook)
+struct HitRec {
+    int si;      // instance slot in TLAS leaf order (-1 = miss)
+    int prim;    // prim slot in BLAS leaf order
+    float w1;    // triangle: ew.y ; line: s (= ew.y) ; point: 0
+    float w2;    // triangle: ew.z
+    float dist;
+};
+
+}  // namespace yrt

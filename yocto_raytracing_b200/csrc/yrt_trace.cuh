@@ -1,0 +1,156 @@
+// yrt_trace.cuh — two-level BVH traversal (closest-hit and any-hit) for one ray.
+//
+// Replaces intersect_bvh(scene…) (src/scene.cpp:446-479) and intersect_bvh(shape…)
+// (src/scene.cpp:386-442).  What is kept bit-for-bit: the ray handed to the primitive tests
+// (transform_ray_inverse per instance, tmin/tmax copied, src/vmath.h:275-278), the primitive
+// tests themselves, the accept rule `t > tmax` rejects (so equal t is accepted and tmax shrinks
+// monotonically, scene.cpp:256,271,295) and the slab test's accept decision (scene.cpp:371-383).
+// What is free (SURVEY finding 4): tree topology and visit order — here an LBVH with near-child
+// first ordering.  Exact-distance ties (frequent in instance10000: overlapping instances with
+// coplanar faces) are resolved like the reference does, by its visit order, through rank tables.
+//
+// The same code runs on the device (kernels in yrt_render.cu) and on the host (tools/host_emu,
+// tests only).
+#pragma once
+#include "yrt_scene.cuh"
+
+namespace yrt {
+
+
+
+struct TraceCounters {   // optional per-ray work counters (roofline inputs), host_emu / debug kernels
+    int box_tests, prim_tests, inst_entries, max_stack;
+};
+
+// test the prims of one BLAS leaf; returns true if any was hit (tmax/hit updated)
+template <bool ANY>
+YRT_HD bool leaf_prims(const SceneView& sv, int kind, int first, int count, const ray3& lray_in, float& tmax,
+                       int si, HitRec& hit, TraceCounters* ctr) {
+    bool any_hit = false;
+    ray3 lray = lray_in;
+    for (int k = first; k < first + count; k++) {
+        lray.tmax = tmax;
+        const float4* pr = sv.prim_recs + 3 * (size_t)k;
+        float4 q0 = ld4(pr), q1 = ld4(pr + 1);
+        float t, a = 0.f, b = 0.f;
+        bool h;
+        if (ctr) ctr->prim_tests++;
+        if (kind == 0) {
+            float4 q2 = ld4(pr + 2);
+            h = intersect_triangle(lray, xyz(q0), xyz(q1), xyz(q2), t, a, b);
+        } else if (kind == 1) {
+            float4 q2 = ld4(pr + 2);
+            h = intersect_line(lray, xyz(q0), xyz(q1), q1.w, q2.x, t, a);
+        } else {
+            h = intersect_point(lray, xyz(q0), q1.x, t);
+        }
+        if (h && !ANY && hit.si >= 0 && t == tmax) {
+            // exact-distance tie with the current closest hit: the reference keeps whichever candidate
+            // its own traversal visits LAST (scene.cpp:256 accepts t == tmax and overwrites); reproduce
+            // that with the precomputed visit ranks instead of depending on our visit order
+            int ri_new = sv.inst_rank[si], ri_old = sv.inst_rank[hit.si];
+            h = ri_new > ri_old || (ri_new == ri_old && sv.prim_rank[k] > sv.prim_rank[hit.prim]);
+        }
+        if (h) {
+            tmax = t;
+            hit.si = si;
+            hit.prim = k;
+            hit.w1 = a;
+            hit.w2 = b;
+            hit.dist = t;
+            any_hit = true;
+            if (ANY) return true;
+        }
+    }
+    return any_hit;
+}
+
+YRT_HD vec3 inv3(const vec3& d) { return mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }   // scene.cpp:372
+
+// Closest hit (ANY=false): returns whether anything was hit, `hit` filled.
+// Any hit (ANY=true): returns at the first accepted primitive (scene.cpp:414,425,436,473).
+template <bool ANY>
+YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* stack, TraceCounters* ctr) {
+    hit.si = -1;
+    hit.prim = -1;
+    hit.w1 = hit.w2 = 0.f;
+    hit.dist = 0.f;
+    if (sv.n_active_instances <= 0) return false;
+
+    int sp = 0;
+    float tmax = wray.tmax;
+    const vec3 winvd = inv3(wray.d);
+    ray3 ray = wray;          // ray in the current space (world, or local to instance `si`)
+    vec3 invd = winvd;
+    bool top = true;
+    int si = -1, kind = 0;
+    int cur = sv.tlas_root;
+    bool found = false;
+
+    for (;;) {
+        bool pop = false;
+        if (cur >= 0) {
+            // internal node: test both child boxes against the current ray and current tmax
+            const float4* n = (top ? sv.tlas_nodes : sv.blas_nodes) + 4 * (size_t)cur;
+            float4 q0 = ld4(n), q1 = ld4(n + 1), q2 = ld4(n + 2), q3 = ld4(n + 3);
+            float e0, e1;
+            bool h0 = intersect_check_bbox(ray.o, invd, ray.tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, e0);
+            bool h1 = intersect_check_bbox(ray.o, invd, ray.tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, e1);
+            if (ctr) ctr->box_tests += 2;
+            int c0 = float_as_int(q0.w), c1 = float_as_int(q1.w);
+            if (h0 && h1) {
+                bool swap = e1 < e0;   // near child first
+                int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
+                stack[sp++] = farc;
+                if (ctr && sp > ctr->max_stack) ctr->max_stack = sp;
+                cur = nearc;
+            } else if (h0) {
+                cur = c0;
+            } else if (h1) {
+                cur = c1;
+            } else {
+                pop = true;
+            }
+        } else {
+            int first = leaf_first(cur), count = leaf_count(cur);
+            if (top) {
+                // TLAS leaf: enter its first instance, keep the rest for later
+                if (count > 1) {
+                    stack[sp++] = make_leaf_ref(first + 1, count - 1);
+                }
+                const float4* ir = sv.inst_recs + 4 * (size_t)first;
+                float4 q0 = ld4(ir), q1 = ld4(ir + 1), q2 = ld4(ir + 2), q3 = ld4(ir + 3);
+                frame3 f;
+                f.x = xyz(q0); f.y = xyz(q1); f.z = xyz(q2); f.o = xyz(q3);
+                ray3 w = wray;
+                w.tmax = tmax;
+                ray = transform_ray_inverse(f, w);   // scene.cpp:468
+                invd = inv3(ray.d);
+                si = first;
+                kind = ((unsigned)float_as_int(q3.w)) >> 28;
+                top = false;
+                stack[sp++] = YRT_REF_SENTINEL;
+                if (ctr) { ctr->inst_entries++; if (sp > ctr->max_stack) ctr->max_stack = sp; }
+                cur = float_as_int(q0.w);   // BLAS root ref of the instance's shape
+            } else {
+                if (leaf_prims<ANY>(sv, kind, first, count, ray, tmax, si, hit, ctr)) {
+                    found = true;
+                    if (ANY) return true;
+                }
+                pop = true;
+            }
+        }
+        if (pop) {
+            for (;;) {
+                if (sp == 0) return found;
+                cur = stack[--sp];
+                if (cur != YRT_REF_SENTINEL) break;
+                top = true;   // leave the instance: back to the world-space ray
+                ray = wray;
+                invd = winvd;
+            }
+        }
+    }
+}
+
+}  // namespace yrt

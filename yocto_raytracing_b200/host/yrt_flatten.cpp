@@ -1,0 +1,197 @@
+// yrt_flatten.cpp — see yrt_flatten.h.  Compiled with -I <reference>/src (scene.h, vmath.h, image.h).
+#include "yrt_flatten.h"
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+
+#include "scene.h"   // the reference's src/scene.h
+
+yrt_scene_desc yrt_flat_scene::desc() const {
+    yrt_scene_desc d;
+    memset(&d, 0, sizeof(d));
+    d.n_shapes = (int32_t)shape_kind.size();
+    d.n_instances = (int32_t)inst_shape.size();
+    d.n_materials = (int32_t)mat_rs.size();
+    d.n_textures = (int32_t)tex_w.size();
+    d.n_verts = (int32_t)(pos.size() / 3);
+    d.n_elem_idx = (int32_t)elem_idx.size();
+    d.shape_kind = shape_kind.data();
+    d.shape_elem_off = shape_elem_off.data();
+    d.shape_elem_cnt = shape_elem_cnt.data();
+    d.shape_vert_off = shape_vert_off.data();
+    d.shape_vert_cnt = shape_vert_cnt.data();
+    d.shape_has_uv = shape_has_uv.data();
+    d.shape_has_radius = shape_has_radius.data();
+    d.elem_idx = elem_idx.data();
+    d.pos = pos.data();
+    d.norm = norm.data();
+    d.uv = uv.data();
+    d.radius = radius.data();
+    d.inst_frame = inst_frame.data();
+    d.inst_shape = inst_shape.data();
+    d.inst_mat = inst_mat.data();
+    d.mat_ke = mat_ke.data();
+    d.mat_kd = mat_kd.data();
+    d.mat_ks = mat_ks.data();
+    d.mat_kr = mat_kr.data();
+    d.mat_rs = mat_rs.data();
+    d.mat_kd_tex = mat_kd_tex.data();
+    d.mat_ks_tex = mat_ks_tex.data();
+    d.tex_w = tex_w.data();
+    d.tex_h = tex_h.data();
+    d.tex_off = tex_off.data();
+    d.tex_rgba8 = tex_rgba8.data();
+    d.tex_bytes = (int64_t)tex_rgba8.size();
+    return d;
+}
+
+static void push3(std::vector<float>& v, const vec3f& a) { v.push_back(a.x); v.push_back(a.y); v.push_back(a.z); }
+
+yrt_camera yrt_flatten_camera(const camera* cam) {
+    yrt_camera c;
+    const frame3f& f = cam->frame;
+    const vec3f* ax[4] = {&f.x, &f.y, &f.z, &f.o};
+    for (int k = 0; k < 4; k++) { c.frame[3 * k] = ax[k]->x; c.frame[3 * k + 1] = ax[k]->y; c.frame[3 * k + 2] = ax[k]->z; }
+    c.fovy = cam->fovy; c.aspect = cam->aspect; c.aperture = cam->aperture; c.focus = cam->focus;
+    return c;
+}
+
+bool yrt_flatten(const scene* scn, yrt_flat_scene& out, std::string& err) {
+    out = yrt_flat_scene();
+    std::map<const shape*, int> shape_id;
+    std::map<const material*, int> mat_id;
+    std::map<const texture*, int> tex_id;
+    char msg[256];
+
+    for (auto txt : scn->textures) {
+        int id = (int)tex_id.size();
+        tex_id[txt] = id;
+        // eval_texture only ever reads texture::ldr (src/raytrace.cpp:43); an .hdr texture leaves it 0x0
+        out.tex_w.push_back(txt->ldr.width);
+        out.tex_h.push_back(txt->ldr.height);
+        out.tex_off.push_back((int64_t)out.tex_rgba8.size());
+        const unsigned char* px = (const unsigned char*)txt->ldr.pixels.data();
+        out.tex_rgba8.insert(out.tex_rgba8.end(), px, px + 4 * txt->ldr.pixels.size());
+    }
+    auto tex_of = [&](const texture* t) { return t ? tex_id.at(t) : -1; };
+
+    for (auto mat : scn->materials) {
+        mat_id[mat] = (int)mat_id.size();
+        push3(out.mat_ke, mat->ke); push3(out.mat_kd, mat->kd); push3(out.mat_ks, mat->ks); push3(out.mat_kr, mat->kr);
+        out.mat_rs.push_back(mat->rs);
+        out.mat_kd_tex.push_back(tex_of(mat->kd_txt));
+        out.mat_ks_tex.push_back(tex_of(mat->ks_txt));
+    }
+
+    for (auto shp : scn->shapes) {
+        int sid = (int)shape_id.size();
+        shape_id[shp] = sid;
+        int kinds = (!shp->triangles.empty()) + (!shp->lines.empty()) + (!shp->points.empty());
+        if (kinds > 1) {
+            // intersect_bvh dispatches triangles > lines > points (scene.cpp:405-427) but eval_* dispatches
+            // points > lines > triangles (scene.h:160-165): a mixed shape is inconsistent in the reference
+            snprintf(msg, sizeof(msg), "shape %d ('%s') mixes element kinds", sid, shp->name.c_str());
+            err = msg;
+            return false;
+        }
+        int kind = !shp->triangles.empty() ? YRT_TRIANGLES : (!shp->lines.empty() ? YRT_LINES : YRT_POINTS);
+        size_t nv = shp->pos.size();
+        if (shp->norm.size() != nv) { snprintf(msg, sizeof(msg), "shape %d: %zu normals for %zu positions", sid, shp->norm.size(), nv); err = msg; return false; }
+        bool has_uv = shp->texcoord.size() == nv && nv > 0;
+        bool has_r = shp->radius.size() == nv && nv > 0;
+        out.shape_kind.push_back(kind);
+        out.shape_elem_off.push_back((int32_t)out.elem_idx.size());
+        out.shape_vert_off.push_back((int32_t)(out.pos.size() / 3));
+        out.shape_vert_cnt.push_back((int32_t)nv);
+        out.shape_has_uv.push_back(has_uv);
+        out.shape_has_radius.push_back(has_r);
+        if (kind == YRT_TRIANGLES) {
+            out.shape_elem_cnt.push_back((int32_t)shp->triangles.size());
+            for (auto& t : shp->triangles) { out.elem_idx.push_back(t.x); out.elem_idx.push_back(t.y); out.elem_idx.push_back(t.z); }
+        } else if (kind == YRT_LINES) {
+            out.shape_elem_cnt.push_back((int32_t)shp->lines.size());
+            for (auto& l : shp->lines) { out.elem_idx.push_back(l.x); out.elem_idx.push_back(l.y); }
+        } else {
+            out.shape_elem_cnt.push_back((int32_t)shp->points.size());
+            for (auto p : shp->points) out.elem_idx.push_back(p);
+        }
+        for (size_t i = 0; i < nv; i++) {
+            push3(out.pos, shp->pos[i]);
+            push3(out.norm, shp->norm[i]);
+            out.uv.push_back(has_uv ? shp->texcoord[i].x : 0.f);
+            out.uv.push_back(has_uv ? shp->texcoord[i].y : 0.f);
+            out.radius.push_back(has_r ? shp->radius[i] : 0.f);
+        }
+    }
+
+    for (auto ist : scn->instances) {
+        if (!shape_id.count(ist->shp) || !mat_id.count(ist->mat)) { err = "instance refers to a shape/material outside the scene"; return false; }
+        const frame3f& f = ist->frame;
+        push3(out.inst_frame, f.x); push3(out.inst_frame, f.y); push3(out.inst_frame, f.z); push3(out.inst_frame, f.o);
+        out.inst_shape.push_back(shape_id[ist->shp]);
+        out.inst_mat.push_back(mat_id[ist->mat]);
+    }
+
+    if (!scn->cameras.empty()) {
+        out.cam = yrt_flatten_camera(scn->cameras.front());
+        out.has_camera = true;
+    }
+    return true;
+}
+
+namespace {
+struct Writer {
+    FILE* f;
+    int n = 0;
+    void arr(const char* name, int dtype, const void* data, int64_t count, size_t elem) {
+        char nm[24];
+        memset(nm, 0, sizeof(nm));
+        strncpy(nm, name, sizeof(nm) - 1);
+        fwrite(nm, 1, sizeof(nm), f);
+        int32_t dt = dtype;
+        fwrite(&dt, 4, 1, f);
+        fwrite(&count, 8, 1, f);
+        size_t bytes = (size_t)count * elem;
+        if (bytes) fwrite(data, 1, bytes, f);
+        static const char pad[8] = {0};
+        if (bytes % 8) fwrite(pad, 1, 8 - bytes % 8, f);
+        n++;
+    }
+    void i32(const char* name, const std::vector<int32_t>& v) { arr(name, 0, v.data(), (int64_t)v.size(), 4); }
+    void f32(const char* name, const std::vector<float>& v) { arr(name, 1, v.data(), (int64_t)v.size(), 4); }
+};
+}  // namespace
+
+bool yrt_flat_save(const yrt_flat_scene& fs, const std::string& path, std::string& err) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) { err = "cannot open " + path; return false; }
+    fwrite("YRTSCN01", 1, 8, f);
+    int32_t n_arrays = 26;
+    fwrite(&n_arrays, 4, 1, f);
+    int32_t zero = 0;
+    fwrite(&zero, 4, 1, f);
+    Writer w{f};
+    w.i32("shape_kind", fs.shape_kind); w.i32("shape_elem_off", fs.shape_elem_off); w.i32("shape_elem_cnt", fs.shape_elem_cnt);
+    w.i32("shape_vert_off", fs.shape_vert_off); w.i32("shape_vert_cnt", fs.shape_vert_cnt);
+    w.i32("shape_has_uv", fs.shape_has_uv); w.i32("shape_has_radius", fs.shape_has_radius);
+    w.i32("elem_idx", fs.elem_idx);
+    w.f32("pos", fs.pos); w.f32("norm", fs.norm); w.f32("uv", fs.uv); w.f32("radius", fs.radius);
+    w.f32("inst_frame", fs.inst_frame); w.i32("inst_shape", fs.inst_shape); w.i32("inst_mat", fs.inst_mat);
+    w.f32("mat_ke", fs.mat_ke); w.f32("mat_kd", fs.mat_kd); w.f32("mat_ks", fs.mat_ks); w.f32("mat_kr", fs.mat_kr); w.f32("mat_rs", fs.mat_rs);
+    w.i32("mat_kd_tex", fs.mat_kd_tex); w.i32("mat_ks_tex", fs.mat_ks_tex);
+    w.i32("tex_w", fs.tex_w); w.i32("tex_h", fs.tex_h);
+    w.arr("tex_off", 3, fs.tex_off.data(), (int64_t)fs.tex_off.size(), 8);
+    w.arr("tex_rgba8", 2, fs.tex_rgba8.data(), (int64_t)fs.tex_rgba8.size(), 1);
+    std::vector<float> cam(fs.cam.frame, fs.cam.frame + 12);
+    cam.push_back(fs.cam.fovy); cam.push_back(fs.cam.aspect); cam.push_back(fs.cam.aperture); cam.push_back(fs.cam.focus);
+    // camera rides as a 27th array; the count in the header is patched below
+    w.f32("camera", cam);
+    fseek(f, 8, SEEK_SET);
+    int32_t n = w.n;
+    fwrite(&n, 4, 1, f);
+    bool ok = !ferror(f);
+    fclose(f);
+    if (!ok) err = "write error on " + path;
+    return ok;
+}
