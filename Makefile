@@ -7,7 +7,8 @@
 REF      ?= /root/reference
 NVCC     ?= nvcc
 CXX      ?= g++
-CC       ?= gcc
+# plain system gcc for the C oracle (the /opt/gcc wrapper some shells export as $CC has no libgomp.spec)
+ORACLE_CC ?= $(shell command -v /usr/bin/gcc || echo gcc)
 ARCH     := -gencode arch=compute_100a,code=sm_100a
 # -fmad=false: the parity-critical arithmetic must not be contracted into FMA (SURVEY finding 4)
 NVFLAGS  := $(ARCH) -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC
@@ -33,7 +34,7 @@ $(LIB): build/yrt_host.o build/yrt_build.o build/yrt_render.o build/yrt_api.o
 
 oracle: oracle/liboracle.so
 oracle/liboracle.so: oracle/yrt_oracle.c oracle/yrt_oracle.h include/yrt_b200.h
-	$(CC) -std=c11 -O2 -fPIC -shared -ffp-contract=off -fopenmp -o $@ oracle/yrt_oracle.c -lm
+	$(ORACLE_CC) -std=c11 -O2 -fPIC -shared -ffp-contract=off -fopenmp -o $@ oracle/yrt_oracle.c -lm
 
 hostemu: tests/host_emu/libyrt_hostemu.so
 tests/host_emu/libyrt_hostemu.so: tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu $(HDRS)

@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s & ms/frame of the hot path on BASELINE.json's headline config:
+an instance10000_pointlight-shaped scene (10 004 instances of 14 shapes, 3 point lights) at 1920x1080,
+16 spp (-r 1080 -s 4), on 1/2/4/8 B200 of one node.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference's own CPU implementation on this box's host cores
+
+A step is one frame.  Rays are counted by reference semantics (intersect_first + intersect_any calls the
+reference would make: primary + reflection + shadow).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+# per-ray algorithmic work of the reference on this config (measured with counters in the
+# reference's BVH): 2.84 KB of node/primitive/instance bytes and 2.45 kflop per ray
+ALG_BYTES_PER_RAY = 2840.0
+ALG_FLOPS_PER_RAY = 2450.0
+FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--resolution", type=int, default=1080)
+    ap.add_argument("--samples", type=int, default=4)
+    ap.add_argument("--n-side", type=int, default=100, help="instances per grid side (100 -> 10 004 instances)")
+    ap.add_argument("--tile-rows", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-resolution", type=int, default=0, help="0 = sized for ~15 s of CPU work")
+    return ap.parse_args()
+
+
+def workload_name(args, flat):
+    w = flat.image_width(args.resolution)
+    return (f"instance10000_pointlight-shaped synthetic scene ({flat.n_instances} instances, {flat.n_shapes} shapes, "
+            f"{flat.n_elements} elements, {len(flat.light_instances())} point lights), {w}x{args.resolution}, {args.samples ** 2} spp")
+
+
+# ---- clocks during the timed region -----------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": float(max(pw))}
+
+
+# ---- the reference's CPU implementation, bounded sample ------------------------------------------------
+def cpu_reference_sample(synth_scene, flat, resolution, samples, ray_counter):
+    """Time the reference's raytrace() on this box's host cores for one bounded frame.  Prefers the UNMODIFIED
+    reference (oracle/_ref/ref_probe, compiled from /root/reference/src; single-threaded like the reference),
+    else the C port (oracle/yrt_oracle.c) on one thread.  ray_counter(resolution, samples) -> rays by
+    reference semantics."""
+    import ref_probe
+    w = flat.image_width(resolution)
+    cores_total = os.cpu_count() or 1
+    if ref_probe.available():
+        with tempfile.TemporaryDirectory() as td:
+            obj = synth_scene.write_obj(td)
+            _, info = ref_probe.image(obj, resolution, samples, 0.1)
+        secs, kind = float(info["raytrace_s"]), "reference"
+        rays = ray_counter(resolution, samples)
+    else:
+        from oracle import oracle
+        o = oracle.OracleScene(flat)
+        t0 = time.perf_counter()
+        _, cnt = o.render(w, resolution, samples, 0.1, threads=1)
+        secs, kind = time.perf_counter() - t0, "port"
+        rays = cnt["primary_rays"] + cnt["reflection_rays"] + cnt["shadow_rays"]
+    return {"value": rays / secs / 1e6, "unit": "Mrays/s", "cores": 1, "kind": kind, "host_cores_total": cores_total,
+            "sample": f"same scene, one frame at {w}x{resolution}, {samples * samples} spp = {rays} rays in {secs:.2f} s "
+                      f"(raytrace() phase only, single thread: the reference is single-threaded, src/raytrace.cpp:228-251)",
+            "seconds": secs, "rays": rays}
+
+
+def oracle_ray_count(flat, resolution, samples):
+    """Ray count by reference semantics without a GPU and without rendering: for this scene family every hit
+    casts n_lights shadow rays and nothing reflects; hits come from the C oracle's closest-hit pass."""
+    from oracle import oracle
+    o = oracle.OracleScene(flat)
+    w = flat.image_width(resolution)
+    ids, _, _ = o.trace_primary(w, resolution, samples)
+    hits = int((ids[:, 0] >= 0).sum())
+    return ids.shape[0] + hits * len(flat.light_instances())
+
+
+def sample_resolution_for(seconds, mrays_per_s=0.16, n_lights=3):
+    rays = seconds * mrays_per_s * 1e6
+    r = int((rays / ((1 + n_lights) * 16.0 / 9.0)) ** 0.5)
+    return max(36, min(1080, r - r % 2))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0      # one CPU arm per job: rank 0 alone runs it
+    from yocto_raytracing_b200 import synth
+    sc = synth.instance_grid_scene(args.n_side)
+    flat = sc.flat()
+    total = max(1, args.steps + args.warmup)
+    res = args.cpu_baseline_resolution or sample_resolution_for(min(20.0, 150.0 / total))
+    rays = oracle_ray_count(flat, res, 1)
+    times, last = [], None
+    for i in range(total):
+        last = cpu_reference_sample(sc, flat, res, 1, lambda r, s: rays)
+        if i >= args.warmup:
+            times.append(last["seconds"])
+    secs = float(np.mean(times))
+    value = rays / secs / 1e6
+    w = flat.image_width(args.resolution)
+    full_rays = None
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, flat), "step": f"bounded sample per step: one frame of the same scene at "
+                   f"{flat.image_width(res)}x{res}, 1 spp ({rays} rays); Mrays/s is resolution-independent for this path"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": 1, "kind": last["kind"], "host_cores_total": last["host_cores_total"],
+                         "sample": last["sample"]},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---- the B200 arm -----------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import yocto_raytracing_b200 as y
+    from yocto_raytracing_b200 import distributed as D
+    from yocto_raytracing_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    multi = world > 1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the render path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if multi:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    y.init_device(local)
+
+    sc = synth.instance_grid_scene(args.n_side)
+    flat = sc.flat()
+    W, H, S = flat.image_width(args.resolution), args.resolution, args.samples
+    scene = y.Scene(flat)
+    info = scene.info()
+    dev = torch.device("cuda", local)
+    tr = args.tile_rows if multi else H
+
+    def frame(want_stats=True):
+        return D.render_sharded(scene, W, H, S, 0.1, tr, None, want_stats)
+
+    def barrier():
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) ----
+    for _ in range(max(args.warmup, 3)):
+        frame()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stats_all = []
+    e0.record()
+    for _ in range(args.steps):
+        full, st = frame()
+        stats_all.append(st.as_dict())
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    rays_local = float(sum(s["primary_rays"] + s["reflection_rays"] + s["shadow_rays"] for s in stats_all))
+    tot = torch.tensor([rays_local, float(sum(s["launches"] for s in stats_all))], device=dev, dtype=torch.float64)
+    if multi:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = float(ms.item())
+    rays_total, launches = float(tot[0].item()), int(tot[1].item())
+    if multi:
+        launches += args.steps * (world + 1)      # NCCL gather + unpack kernels on rank 0
+    value = rays_total / (ms_total * 1e-3) / 1e6
+
+    # ---- end to end through the public API with HOST buffers (`e2e`) ----
+    pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+    host_np = pinned.numpy() if rank == 0 else None
+
+    def frame_e2e():
+        if not multi:
+            scene.render(W, H, S, 0.1, out=host_np, want_stats=False)      # yrt_render: camera in, host framebuffer out
+        else:
+            full, _ = frame(False)
+            if rank == 0:
+                pinned.copy_(full, non_blocking=True)
+            torch.cuda.synchronize()
+    for _ in range(2):
+        frame_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        frame_e2e()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if multi:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = rays_total / float(dt.item()) / 1e6
+
+    if rank != 0:
+        if multi:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (k_trace_any_lights: 75 % of the rays), rank 0 ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        hbm_peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    any_ms = float(np.mean([s["ms_trace_any"] for s in stats_all]))
+    any_n = max(1, int(np.mean([s["n_any"] for s in stats_all])))
+    closest_ms = float(np.mean([s["ms_trace_closest"] for s in stats_all]))
+    shade_ms = float(np.mean([s["ms_shade"] for s in stats_all]))
+    other_ms = float(np.mean([s["ms_other"] for s in stats_all]))
+    shadow_per_frame = float(np.mean([s["shadow_rays"] for s in stats_all]))
+    primary_per_frame = float(np.mean([s["primary_rays"] for s in stats_all]))
+    any_launch_ms = any_ms / any_n
+    rays_per_launch = shadow_per_frame / any_n
+    achieved = rays_per_launch * ALG_BYTES_PER_RAY / (any_launch_ms * 1e-3) / 1e9
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    fp32_peak_tflops = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    roofline = {
+        "kernel": "k_trace_any_lights", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        "traffic": None, "peak_source": peak_src, "launch_ms": any_launch_ms, "launches_per_frame": any_n, "rays_per_launch": rays_per_launch,
+        "algorithmic_bytes_per_ray": ALG_BYTES_PER_RAY,
+        "note": "2.84 KB/ray is cache-level (L1/L2) node+primitive traffic of the reference's traversal (SURVEY 8d); compulsory HBM traffic "
+                "is ~0.3 B/ray, so this path is latency/issue bound, not HBM bound — see fp32 and the ncu summary in profiles/",
+        "fp32": {"achieved_tflops": shadow_per_frame / (any_ms * 1e-3) * ALG_FLOPS_PER_RAY / 1e12, "peak_tflops": fp32_peak_tflops,
+                 "frac": shadow_per_frame / (any_ms * 1e-3) * ALG_FLOPS_PER_RAY / 1e12 / fp32_peak_tflops,
+                 "peak_def": "148 SMs x 128 lanes x 2 flop x SM clock under load"},
+        "kernel_share_of_step": any_ms / (ms_total / args.steps),
+    }
+
+    cpu_baseline = None
+    if not multi and not args.no_cpu_baseline:
+        res = args.cpu_baseline_resolution or sample_resolution_for(15.0)
+
+        def count(r, s):
+            _, st = scene.render(flat.image_width(r), r, s, 0.1)
+            return st.total_rays
+        cb = cpu_reference_sample(sc, flat, res, 1, count)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "host_cores_total", "sample")}
+
+    line = {
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args, flat), "rays_per_frame": rays_total / args.steps, "parallelism": f"row-tiles x{world}",
+                   "tile_rows": tr, "l2": "per-frame ray/hit queues (~1.7 GB streamed per frame) exceed the 126 MB L2; the 3 MB scene is "
+                   "cache-resident by design", "lbvh": info},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 64 + 12, "d2h_bytes_per_step": W * H * 16,
+                "ms_per_step": float(dt.item()) * 1e3 / args.steps,
+                "api": "Scene.render -> yrt_render (host framebuffer out)" if not multi else "distributed.render_sharded + NCCL gather + D2H on rank 0"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "breakdown_ms_per_frame_rank0": {"trace_closest": closest_ms, "trace_any": any_ms, "shade": shade_ms, "resolve": other_ms},
+        "mrays_s_by_kernel_rank0": {"closest": primary_per_frame / (closest_ms * 1e-3) / 1e6 if closest_ms else None,
+                                    "any": shadow_per_frame / (any_ms * 1e-3) / 1e6 if any_ms else None},
+    }
+    print(json.dumps(line), flush=True)
+    scene.close()
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_b200(a))

@@ -112,6 +112,7 @@ typedef struct yrt_stats {
     float ms_gather;          /* multi-GPU framebuffer gather                                   */
     int32_t max_depth;        /* deepest reflection recursion reached                           */
     int32_t n_gpus;
+    int32_t n_closest, n_any, n_shade, n_other;   /* launches per category (device 0)          */
 } yrt_stats;
 
 typedef struct yrt_scene yrt_scene;   /* opaque: device-resident scene + LBVH on every initialised GPU */

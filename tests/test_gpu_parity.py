@@ -1,0 +1,209 @@
+"""Parity of the CUDA path (through the C ABI) against the reference: golden outputs of the unmodified
+reference (tests/golden) and the C oracle on seeded synthetic scenes.  Run on the B200 box: pytest -m gpu.
+
+Bars (BASELINE.json north_star): closest-hit (instance, shape, element) equal on >= 99.99 % of primary rays;
+final RGBA8 after the reference tonemap within 1/255 per channel on >= 99.9 % of pixels.  Integer/index work
+(sort, partition, gather) is bit-exact.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, id_match, ldr_stats, load_golden
+from yocto_raytracing_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+ID_BAR = 0.9999
+PIXEL_BAR = 0.999
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_hit_ids_vs_reference(gpu, name):
+    flat, ref = load_golden(name)
+    w, h = int(ref["ids_width"]), int(ref["ids_height"])
+    with gpu.Scene(flat) as scn:
+        ids, dist, uv = scn.trace_primary(w, h, 1)
+    assert id_match(ids, ref["ids"]) >= ID_BAR
+    same = (ids == ref["ids"]).all(axis=1)
+    # same primitive => bit-identical distance and barycentrics (no FMA contraction on the device)
+    assert np.array_equal(dist[same].view(np.uint32), ref["dist"][same].view(np.uint32))
+    assert np.array_equal(uv[same].view(np.uint32), ref["uv"][same].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_image_vs_reference(gpu, oracle_mod, name):
+    flat, ref = load_golden(name)
+    h, w = ref["image"].shape[:2]
+    with gpu.Scene(flat) as scn:
+        img, st = scn.render(w, h, int(ref["image_samples"]), float(ref["ambient"]))
+    within1, ident, mx = ldr_stats(oracle_mod.tonemap(img), oracle_mod.tonemap(ref["image"]))
+    assert within1 >= PIXEL_BAR, (within1, ident, mx)
+    # float image: only the specular powf (CUDA vs glibc, a few ulp) may differ
+    close = np.isclose(img, ref["image"], rtol=2e-5, atol=1e-6).all(axis=2).mean()
+    assert close >= PIXEL_BAR, close
+    assert (img[..., 3] == 1.0).all()
+    assert st.primary_rays == w * h * int(ref["image_samples"]) ** 2
+
+
+def test_ray_counts_match_oracle(gpu, oracle_mod):
+    flat, _ = load_golden("refl")
+    with gpu.Scene(flat) as scn:
+        img, st = scn.render(96, 54, 2, 0.1)
+    _, cnt = oracle_mod.OracleScene(flat).render(96, 54, 2, 0.1, max_depth=16)
+    assert st.primary_rays == cnt["primary_rays"]
+    assert abs(st.reflection_rays - cnt["reflection_rays"]) <= 2 and abs(st.shadow_rays - cnt["shadow_rays"]) <= 4
+    assert st.max_depth == cnt["max_depth"]
+
+
+@pytest.mark.parametrize("maker,res,smp", [(lambda: synth.instance_grid_scene(24, seed=3), 120, 2), (lambda: synth.hair_scene(512, seed=5), 120, 2),
+                                           (lambda: synth.mixed_scene(11), 120, 3), (lambda: synth.mixed_scene(12, reflective_floor=False, textured=False), 64, 1)])
+def test_synthetic_scenes_vs_oracle(gpu, oracle_mod, maker, res, smp):
+    flat = maker().flat()
+    w = flat.image_width(res)
+    o = oracle_mod.OracleScene(flat)
+    ref_ids, ref_dist, _ = o.trace_primary(w, res, 1)
+    ref_img, cnt = o.render(w, res, smp, 0.1, max_depth=16, threads=8)
+    with gpu.Scene(flat) as scn:
+        ids, dist, _ = scn.trace_primary(w, res, 1)
+        img, st = scn.render(w, res, smp, 0.1)
+    assert id_match(ids, ref_ids) >= ID_BAR
+    within1, ident, mx = ldr_stats(oracle_mod.tonemap(img), oracle_mod.tonemap(ref_img))
+    assert within1 >= PIXEL_BAR, (within1, ident, mx)
+
+
+def test_generic_ray_queries_vs_oracle(gpu, oracle_mod):
+    flat = synth.mixed_scene(21).flat()
+    rng = np.random.RandomState(0)
+    n = 20000
+    o = rng.uniform(-6, 6, (n, 3)); o[:, 1] = rng.uniform(0.2, 6, n)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d, np.full((n, 1), 1e-4), rng.uniform(0.5, 30, (n, 1))], 1).astype(np.float32)
+    rays[:100, 3:6] = [0, -1, 0]          # axis-aligned directions: invd = +-inf paths of the slab test
+    rays[100:200, 3:6] = [1, 0, 0]
+    oc = oracle_mod.OracleScene(flat)
+    with gpu.Scene(flat) as scn:
+        ids, dist, uv = scn.intersect_first(rays)
+        occ = scn.intersect_any(rays)
+    rids, rdist, ruv = oc.intersect_first(rays)
+    rocc = oc.intersect_any(rays)
+    assert id_match(ids, rids) >= ID_BAR
+    same = (ids == rids).all(axis=1)
+    assert np.array_equal(dist[same], rdist[same])
+    assert (occ == rocc).mean() >= ID_BAR
+    assert np.array_equal(occ != 0, ids[:, 0] >= 0) or ((occ != 0) == (ids[:, 0] >= 0)).mean() >= ID_BAR   # any-hit <=> closest-hit exists
+
+
+def test_radix_sort_is_stable_and_exact(gpu):
+    lib = _lib.load()
+    rng = np.random.RandomState(1)
+    for n in (1, 2, 33, 1024, 1025, 100003):
+        keys = rng.randint(0, 2 ** 62, n, dtype=np.int64).astype(np.uint64)
+        keys[::3] = keys[0]               # many duplicates: stability matters
+        if n > 10:
+            keys[5:10] |= np.uint64(1) << np.uint64(63)
+        vals = np.arange(n, dtype=np.int32)
+        k2, v2 = keys.copy(), vals.copy()
+        assert lib.yrt_debug_sort_pairs(C.c_void_p(k2.ctypes.data), C.c_void_p(v2.ctypes.data), n) == 0
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(k2, keys[order]) and np.array_equal(v2, vals[order].astype(np.int32))
+
+
+def test_row_tiles_are_bit_identical_to_whole_frame(gpu):
+    """Multi-GPU partition emulated on one GPU: every (rank, world) renders its interleaved tiles; assembled
+    frames must equal the world=1 frame bit for bit (pixels are independent, per-pixel sum order is fixed)."""
+    import torch
+    from yocto_raytracing_b200 import distributed as D
+    flat, _ = load_golden("instance10000")
+    w, h, s = 160, 90, 2
+    with gpu.Scene(flat) as scn:
+        whole, _ = scn.render(w, h, s, 0.1)
+        for world, tr in ((2, 16), (3, 8), (8, 16)):
+            full = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+            for rank in range(world):
+                own = D.rows_owned(h, tr, rank, world)
+                if own == 0:
+                    continue
+                packed = torch.empty((own, w, 4), dtype=torch.float32, device="cuda")
+                scn.render_rows_into(packed.data_ptr(), w, h, s, 0.1, tr, rank, world, torch.cuda.current_stream().cuda_stream, True)
+                torch.cuda.synchronize()
+                D._unpack(packed, full, w, h, tr, rank, world)
+            torch.cuda.synchronize()
+            assert np.array_equal(full.cpu().numpy().view(np.uint32), whole.view(np.uint32)), (world, tr)
+
+
+def test_determinism_and_batching(gpu, monkeypatch):
+    flat = synth.mixed_scene(11).flat()
+    with gpu.Scene(flat) as scn:
+        a, _ = scn.render(128, 72, 2, 0.1)
+        b, _ = scn.render(128, 72, 2, 0.1)
+        monkeypatch.setenv("YRT_BATCH_SLOTS", "5000")      # many small batches instead of one
+        c, _ = scn.render(128, 72, 2, 0.1)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
+
+
+def test_edge_cases(gpu, oracle_mod):
+    # empty scene: no shapes, no instances -> black, alpha 1
+    sc = synth.SynthScene(name="empty")
+    sc.camera = synth.make_camera((0, 1, 5), (0, 0, 0), 0.5)
+    flat = sc.flat()
+    with gpu.Scene(flat) as scn:
+        img, st = scn.render(32, 18, 2, 0.1)
+        ids, _, _ = scn.trace_primary(32, 18, 1)
+    assert not img[..., :3].any() and (img[..., 3] == 1).all() and (ids == -1).all() and st.shadow_rays == 0
+    # one triangle, no lights: ambient only; single-element shapes have no internal BVH node
+    sc = synth.SynthScene(name="one")
+    sc.materials.append(synth.Material("m", kd=(0.5, 0.25, 1.0)))
+    sc.shapes.append(synth.Shape("t", 0, np.array([[-1, -1, 0], [1, -1, 0], [0, 1, 0]], np.float32), np.tile(np.array([0, 0, 1], np.float32), (3, 1)),
+                                 np.array([[0, 1, 2]], np.int32), "m", np.zeros((3, 2), np.float32)))
+    sc.instances.append(("t", 0, synth.translation_frame((0, 0, 0))))
+    sc.camera = synth.make_camera((0, 0, 5), (0, 0, 0), 0.5)
+    flat = sc.flat()
+    ref, _ = oracle_mod.OracleScene(flat).render(64, 36, 2, 0.2)
+    with gpu.Scene(flat) as scn:
+        img, st = scn.render(64, 36, 2, 0.2)
+    assert np.array_equal(img.view(np.uint32), ref.view(np.uint32)) and st.shadow_rays == 0
+    assert img[18, 32, 0] == np.float32(0.2) * np.float32(0.5)
+
+
+def test_device_tonemap_vs_reference_tonemap(gpu, oracle_mod):
+    _, ref = load_golden("simple")
+    a = gpu.tonemap(ref["image"])
+    b = oracle_mod.tonemap(ref["image"])
+    within1, ident, mx = ldr_stats(a, b)
+    assert within1 == 1.0 and ident >= 0.995      # CUDA powf vs glibc powf at a truncation boundary: <= 1 level
+
+
+def test_in_process_api_matches_reference_signature(gpu):
+    flat, ref = load_golden("basic")
+    with gpu.Scene(flat) as scn:
+        hdr = scn.raytrace(0.1, 90, 2)               # raytrace(scn, {amb,amb,amb}, resolution, samples)
+        info = scn.info()
+    assert hdr.shape == ref["image"].shape and info["lights"] == 2 and info["prims"] == flat.n_elements
+    assert info["blas_depth"] + info["tlas_depth"] + 4 <= 128
+
+
+def test_full_size_properties(gpu):
+    """BASELINE size (1920x1080, 16 spp, 10 004 instances): properties that need no CPU reference —
+    alpha = 1, finite, all primary rays counted, shadow rays = hits x lights, and the 1080p frame equals the
+    frame assembled from 8 ranks' tiles."""
+    import torch
+    from yocto_raytracing_b200 import distributed as D
+    flat = synth.instance_grid_scene(100).flat()
+    w, h, s = 1920, 1080, 4
+    with gpu.Scene(flat) as scn:
+        img, st = scn.render(w, h, s, 0.1)
+        assert st.primary_rays == w * h * 16 and st.shadow_rays % 3 == 0 and st.shadow_rays <= 3 * st.primary_rays
+        assert st.shadow_rays >= 0.99 * 3 * st.primary_rays      # the floor fills the view
+        assert np.isfinite(img).all() and (img[..., 3] == 1).all() and img[..., :3].min() >= 0
+        full = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+        for rank in range(8):
+            own = D.rows_owned(h, 16, rank, 8)
+            packed = torch.empty((own, w, 4), dtype=torch.float32, device="cuda")
+            scn.render_rows_into(packed.data_ptr(), w, h, s, 0.1, 16, rank, 8, torch.cuda.current_stream().cuda_stream, True)
+            torch.cuda.synchronize()
+            D._unpack(packed, full, w, h, 16, rank, 8)
+        torch.cuda.synchronize()
+        assert np.array_equal(full.cpu().numpy().view(np.uint32), img.view(np.uint32))

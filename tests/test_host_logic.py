@@ -1,0 +1,107 @@
+"""Host-side logic: scene container, synthetic generators, row-tile partition, and the world_size-2 gather
+(gloo, CPU) of the one-process-per-GPU path."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from yocto_raytracing_b200 import distributed as D
+from yocto_raytracing_b200 import synth
+from yocto_raytracing_b200.scene import FlatScene
+
+
+def test_flat_scene_npz_roundtrip(tmp_path):
+    flat = synth.mixed_scene(5).flat()
+    p = str(tmp_path / "s.npz")
+    flat.save_npz(p)
+    back = FlatScene.load(p)
+    for k, v in flat.arrays.items():
+        assert np.array_equal(v, back.arrays[k]), k
+    assert back.n_shapes == 9 and back.n_instances == flat.n_instances
+
+
+def test_lights_are_all_positive_ke_instances():
+    flat = synth.mixed_scene(5).flat()
+    lights = flat.light_instances()
+    # 'half_emitter' has ke = (5,0,5): AND of the three channels (raytrace.cpp:126) -> not a light
+    assert len(lights) == 2
+    flat2, _ = load_golden("instance10000")
+    assert len(flat2.light_instances()) == 3 and flat2.n_instances == 10004 and flat2.n_elements == 41987
+
+
+def test_instance_grid_has_named_shape():
+    sc = synth.instance_grid_scene(100)
+    flat = sc.flat()
+    assert flat.n_instances == 10004 and flat.n_shapes == 14
+    tri = flat.arrays["shape_elem_cnt"][:11]
+    assert tri[0] == 8192 and all(t in (3072, 4096) for t in tri[1:])
+    assert flat.image_width(1080) == 1920
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "bin", "yrt_flatten")), reason="needs the reference loader (built only where /root/reference exists)")
+def test_direct_flat_equals_reference_loader_on_written_obj(tmp_path):
+    """The OBJ our generator writes, loaded by the reference's own loader, gives the arrays we build directly."""
+    for sc in (synth.instance_grid_scene(6), synth.hair_scene(64), synth.mixed_scene(7)):
+        obj = sc.write_obj(str(tmp_path / sc.name))
+        y = obj[:-4] + ".yrts"
+        subprocess.run([os.path.join(ROOT, "bin", "yrt_flatten"), os.path.basename(obj), y], check=True, cwd=os.path.dirname(obj),
+                       stdout=subprocess.DEVNULL)
+        a, b = sc.flat(), FlatScene.load(y)
+        for k in a.arrays:
+            if k == "uv":   # the loader computes 1-(1-v): one rounding
+                assert np.allclose(a.arrays[k], b.arrays[k], atol=1e-6)
+            else:
+                assert np.array_equal(a.arrays[k], b.arrays[k]), (sc.name, k)
+
+
+@pytest.mark.parametrize("h,tr,world", [(1080, 16, 8), (720, 16, 3), (37, 8, 4), (5, 16, 8), (90, 16, 1)])
+def test_row_tile_partition_is_a_partition(h, tr, world):
+    seen = np.concatenate([D.global_rows(h, tr, r, world) for r in range(world)])
+    assert sorted(seen.tolist()) == list(range(h))
+    for r in range(world):
+        assert D.rows_owned(h, tr, r, world) == len(D.global_rows(h, tr, r, world))
+    assert max(D.rows_owned(h, tr, r, world) for r in range(world)) - min(D.rows_owned(h, tr, r, world) for r in range(world)) <= tr
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+from conftest import load_golden
+from oracle import oracle
+from yocto_raytracing_b200 import distributed as D
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+flat, _ = load_golden("basic")
+W, H, S, TR = 48, 27, 1, 4
+o = oracle.OracleScene(flat)
+full_ref, _ = o.render(W, H, S)                      # every rank can compute the expected frame
+rows = D.global_rows(H, TR, rank, world)
+packed = torch.from_numpy(np.ascontiguousarray(full_ref[rows]))   # "this rank's render": its own rows only
+out = D.gather_rows(packed, W, H, TR, rank, world)
+if rank == 0:
+    assert out is not None and np.array_equal(out.numpy(), full_ref), "gathered frame differs"
+    print("GATHER_OK")
+else:
+    assert out is None
+dist.destroy_process_group()
+'''
+
+
+def test_world2_gather_gloo():
+    """N>1 host path on CPU: 2 ranks (gloo), each holds only its interleaved row tiles; rank 0 must end up with
+    the full frame."""
+    with tempfile.TemporaryDirectory() as td:
+        script = os.path.join(td, "w.py")
+        open(script, "w").write(_WORKER)
+        procs = []
+        for r in range(2):
+            env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29531", OMP_NUM_THREADS="2")
+            procs.append(subprocess.Popen([sys.executable, script, ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+        outs = [p.communicate(timeout=300)[0].decode() for p in procs]
+        assert all(p.returncode == 0 for p in procs), outs
+        assert "GATHER_OK" in outs[0]

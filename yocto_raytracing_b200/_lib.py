@@ -50,6 +50,7 @@ class Stats(C.Structure):
         ("primary_rays", C.c_int64), ("reflection_rays", C.c_int64), ("shadow_rays", C.c_int64), ("launches", C.c_int64),
         ("ms_total", C.c_float), ("ms_trace_closest", C.c_float), ("ms_trace_any", C.c_float), ("ms_shade", C.c_float),
         ("ms_other", C.c_float), ("ms_gather", C.c_float), ("max_depth", C.c_int32), ("n_gpus", C.c_int32),
+        ("n_closest", C.c_int32), ("n_any", C.c_int32), ("n_shade", C.c_int32), ("n_other", C.c_int32),
     ]
 
     def as_dict(self):

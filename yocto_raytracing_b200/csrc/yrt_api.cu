@@ -255,6 +255,7 @@ int yrt_render(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int wi
             if (g == 0) {
                 stats->ms_trace_closest = one.ms_trace_closest; stats->ms_trace_any = one.ms_trace_any;
                 stats->ms_shade = one.ms_shade; stats->ms_other = one.ms_other;
+                stats->n_closest = one.n_closest; stats->n_any = one.n_any; stats->n_shade = one.n_shade; stats->n_other = one.n_other;
             }
         }
         cudaSetDevice(d0.device);

@@ -303,9 +303,9 @@ struct PhaseTimer {
     }
     void begin(int cat) { if (!on) return; Span s; s.cat = cat; s.a = get(); s.b = get(); cudaEventRecord(s.a, st); spans.push_back(s); }
     void end() { if (!on) return; cudaEventRecord(spans.back().b, st); }
-    void collect(float out[5], int64_t& launches) {
-        for (int i = 0; i < 5; i++) out[i] = 0.f;
-        for (auto& s : spans) { float ms = 0.f; cudaEventElapsedTime(&ms, s.a, s.b); out[s.cat] += ms; pool.push_back(s.a); pool.push_back(s.b); }
+    void collect(float out[5], int cnt[5], int64_t& launches) {
+        for (int i = 0; i < 5; i++) { out[i] = 0.f; cnt[i] = 0; }
+        for (auto& s : spans) { float ms = 0.f; cudaEventElapsedTime(&ms, s.a, s.b); out[s.cat] += ms; cnt[s.cat]++; pool.push_back(s.a); pool.push_back(s.b); }
         launches = (int64_t)spans.size();
         spans.clear();
     }
@@ -490,8 +490,9 @@ int collect_stats_device(DevScene& ds, const RenderParams& rp, yrt_stats* stats)
     FrameCounters fc;
     YRT_CUDA(cudaMemcpy(&fc, ds.ws.stats.p, sizeof(fc), cudaMemcpyDeviceToHost));
     float cat[5];
+    int cnt[5];
     int64_t launches = 0;
-    pt.collect(cat, launches);
+    pt.collect(cat, cnt, launches);
     memset(stats, 0, sizeof(*stats));
     int own = rows_owned(rp.height, rp.tile_rows, rp.rank, rp.world);
     stats->primary_rays = (int64_t)own * rp.width * rp.samples * rp.samples;
@@ -507,6 +508,7 @@ int collect_stats_device(DevScene& ds, const RenderParams& rp, yrt_stats* stats)
     stats->ms_other = cat[CAT_OTHER];
     stats->max_depth = pt.max_depth_seen;
     stats->n_gpus = 1;
+    stats->n_closest = cnt[CAT_CLOSEST]; stats->n_any = cnt[CAT_ANY]; stats->n_shade = cnt[CAT_SHADE]; stats->n_other = cnt[CAT_OTHER];
     return YRT_OK;
 }
 

@@ -1,0 +1,90 @@
+"""One process per GPU: interleaved row tiles over a replicated scene, framebuffer gathered to rank 0.
+
+Pixels are independent (src/raytrace.cpp:228-251), so the frame shards with no data-path exchange except
+the final gather: row tile t (tile_rows rows) belongs to rank t % world; every rank renders ALL samples of
+its pixels (the per-pixel (jj,ii) sum order is kept, so the image is bit-identical for any world size).
+torch.distributed is plumbing only: NCCL gather over NVLink on GPUs, gloo in the CPU tests of this logic.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check
+
+
+def n_tiles(height: int, tile_rows: int) -> int:
+    return (height + tile_rows - 1) // tile_rows
+
+
+def rows_owned(height: int, tile_rows: int, rank: int, world: int) -> int:
+    """Number of image rows rank renders (mirrors yrt_rows_owned)."""
+    rows = 0
+    for t in range(rank, n_tiles(height, tile_rows), world):
+        rows += min(height, (t + 1) * tile_rows) - t * tile_rows
+    return rows
+
+
+def global_rows(height: int, tile_rows: int, rank: int, world: int) -> np.ndarray:
+    """Global row index of each packed local row of `rank`, in packed order."""
+    out = []
+    for t in range(rank, n_tiles(height, tile_rows), world):
+        out.extend(range(t * tile_rows, min(height, (t + 1) * tile_rows)))
+    return np.asarray(out, np.int64)
+
+
+def gather_rows(packed: torch.Tensor, width: int, height: int, tile_rows: int, rank: int, world: int,
+                group=None) -> Optional[torch.Tensor]:
+    """Gather every rank's packed rows (rows_owned x width x 4 float32) on rank 0 and scatter them into the
+    (height, width, 4) framebuffer.  Returns the framebuffer on rank 0, None elsewhere."""
+    own = rows_owned(height, tile_rows, rank, world)
+    assert packed.shape == (own, width, 4) and packed.dtype == torch.float32
+    if world == 1:
+        full = torch.empty((height, width, 4), dtype=torch.float32, device=packed.device)
+        _unpack(packed, full, width, height, tile_rows, 0, 1)
+        return full
+    max_rows = max(rows_owned(height, tile_rows, r, world) for r in range(world))
+    send = packed
+    if own < max_rows:   # dist.gather needs equal shapes: pad the short ranks (at most one tile)
+        send = torch.zeros((max_rows, width, 4), dtype=torch.float32, device=packed.device)
+        send[:own] = packed
+    send = send.contiguous()
+    if rank == 0:
+        bufs = [torch.empty_like(send) for _ in range(world)]
+        dist.gather(send, gather_list=bufs, dst=0, group=group)
+        full = torch.empty((height, width, 4), dtype=torch.float32, device=packed.device)
+        for r in range(world):
+            n = rows_owned(height, tile_rows, r, world)
+            if n:
+                _unpack(bufs[r][:n], full, width, height, tile_rows, r, world)
+        return full
+    dist.gather(send, gather_list=None, dst=0, group=group)
+    return None
+
+
+def _unpack(packed: torch.Tensor, full: torch.Tensor, width, height, tile_rows, rank, world) -> None:
+    if packed.is_cuda:
+        st = torch.cuda.current_stream(packed.device).cuda_stream
+        check(_lib.load().yrt_unpack_rows(packed.contiguous().data_ptr(), full.data_ptr(), width, height, tile_rows, rank, world, st))
+    else:
+        idx = torch.from_numpy(global_rows(height, tile_rows, rank, world))
+        full[idx] = packed
+
+
+def render_sharded(scene, width: int, height: int, samples: int, amb=0.1, tile_rows: int = 16, group=None, want_stats=False):
+    """Render this rank's tiles with `scene` (a render.Scene bound to this process's GPU) and gather on rank 0.
+    Returns (framebuffer on rank 0 | None, Stats | None)."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    own = rows_owned(height, tile_rows, rank, world)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    packed = torch.empty((max(own, 1), width, 4), dtype=torch.float32, device=dev)[:own]
+    st = torch.cuda.current_stream(dev).cuda_stream
+    stats = scene.render_rows_into(packed.data_ptr() if own else torch.empty(4, device=dev).data_ptr(), width, height, samples, amb,
+                                   tile_rows, rank, world, st, want_stats)
+    full = gather_rows(packed, width, height, tile_rows, rank, world, group)
+    return full, stats
