@@ -43,7 +43,7 @@ class EmuScene:
         ids = np.empty((n, 3), np.int32)
         dist = np.empty(n, np.float32)
         uv = np.empty((n, 2), np.float32)
-        ctr = (C.c_int64 * 4)()
+        ctr = (C.c_int64 * 6)()
         cam = self.flat.camera_struct()
         st = lib().emu_trace_primary(self.h, C.byref(cam), width, height, samples, C.c_void_p(ids.ctypes.data),
                                      C.c_void_p(dist.ctypes.data), C.c_void_p(uv.ctypes.data), ctr)

@@ -24,7 +24,7 @@ struct EmuLbvh {
 };
 
 void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi, const int* seg_of, const int* seg_first, int leaf_size,
-              EmuLbvh& out) {
+              EmuLbvh& out, int ref_offset) {
     size_t ni = n > 1 ? n - 1 : 1;
     std::vector<int> cent_lo(3 * n_seg), cent_hi(3 * n_seg);
     out.seg_box_lo.assign(3 * n_seg, 0);
@@ -42,7 +42,7 @@ void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi
     a.keys = keys.data(); a.order = out.order.data(); a.left = left.data(); a.right = right.data();
     a.range_first = rfirst.data(); a.range_last = rlast.data(); a.parent_int = pint.data(); a.parent_leaf = pleaf.data();
     a.flags = flags.data(); a.node_lo = nlo.data(); a.node_hi = nhi.data(); a.nodes = out.nodes.data();
-    a.seg_root = out.seg_root.data(); a.seg_depth = out.seg_depth.data(); a.leaf_size = leaf_size;
+    a.seg_root = out.seg_root.data(); a.seg_depth = out.seg_depth.data(); a.leaf_size = leaf_size; a.ref_offset = ref_offset;
     for (int s = 0; s < n_seg; s++) seg_bounds_init_item(a, s);
     for (int i = 0; i < n; i++) seg_bounds_item(a, i);
     for (int i = 0; i < n; i++) morton_item(a, i);
@@ -70,6 +70,7 @@ struct EmuScene {
     EmuLbvh blas, tlas;
     std::vector<float4> prim_recs, prim_attrs, inst_recs;
     std::vector<int> prim_rank, inst_rank;
+    std::vector<float4> nodes;   // BLAS nodes then TLAS nodes, like the device array
     SceneView view;
     int blas_depth = 0, tlas_depth = 0;
 };
@@ -90,7 +91,7 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
         phi[i] = mk4(b.hi.x, b.hi.y, b.hi.z, 0.f);
     }
     int nseg = std::max(hs.n_shapes, 1);
-    emu_lbvh(np, nseg, plo, phi, g.prim_shape, g.shape_prim_off, leaf_blas, es.blas);
+    emu_lbvh(np, nseg, plo, phi, g.prim_shape, g.shape_prim_off, leaf_blas, es.blas, 0);
     // prim + attribute records in BLAS leaf order (mirrors k_gather_prims)
     es.prim_recs.assign(3 * (size_t)std::max(np, 1), mk4(0, 0, 0, 0));
     es.prim_attrs.assign(4 * (size_t)std::max(np, 1), mk4(0, 0, 0, 0));
@@ -133,7 +134,10 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
     }
     std::vector<int> seg_of(std::max(na, 1), 0);
     int sf[2] = {0, na};
-    emu_lbvh(na, 1, ilo, ihi, seg_of.data(), sf, leaf_tlas, es.tlas);
+    int nb_int = np > 1 ? np - 1 : 0;
+    emu_lbvh(na, 1, ilo, ihi, seg_of.data(), sf, leaf_tlas, es.tlas, nb_int);
+    es.nodes.assign(es.blas.nodes.begin(), es.blas.nodes.begin() + 4 * (size_t)nb_int);
+    es.nodes.insert(es.nodes.end(), es.tlas.nodes.begin(), es.tlas.nodes.end());
     es.inst_recs.assign(4 * (size_t)std::max(na, 1), mk4(0, 0, 0, 0));
     es.inst_rank.assign(std::max(na, 1), 0);
     for (int k = 0; k < na; k++) {
@@ -150,7 +154,7 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
     es.tlas_depth = es.tlas.seg_depth[0];
     if (es.blas_depth + es.tlas_depth + 4 > YRT_STACK_CAP) { set_error("emu: tree too deep"); return YRT_ERR_UNSUPPORTED; }
     SceneView& v = es.view;
-    v.tlas_nodes = es.tlas.nodes.data(); v.blas_nodes = es.blas.nodes.data(); v.inst_recs = es.inst_recs.data();
+    v.nodes = es.nodes.data(); v.inst_recs = es.inst_recs.data();
     v.prim_recs = es.prim_recs.data(); v.prim_attrs = es.prim_attrs.data(); v.mat_recs = hs.mat_recs.data();
     v.light_recs = hs.light_recs.data(); v.tex_rgba8 = hs.tex_rgba8.data(); v.tex_info = hs.tex_info.data();
     v.inst_rank = es.inst_rank.data(); v.prim_rank = es.prim_rank.data();
@@ -187,7 +191,7 @@ int emu_scene_info(void* p, int64_t out[8]) {
     return YRT_OK;
 }
 
-// counters_out (optional, 4 int64): box tests, prim tests, instance entries, max stack
+// counters_out (optional, 6 int64): box tests, prim tests, instance entries, max stack, fused-slab false rejects / extra accepts
 int emu_trace_primary(void* p, const yrt_camera* cam, int width, int height, int samples, int32_t* ids, float* dist, float* uv,
                       int64_t* counters_out) {
     EmuScene* es = (EmuScene*)p;
@@ -197,8 +201,8 @@ int emu_trace_primary(void* p, const yrt_camera* cam, int width, int height, int
         ck.frame.x = mk3(f[0], f[1], f[2]); ck.frame.y = mk3(f[3], f[4], f[5]); ck.frame.z = mk3(f[6], f[7], f[8]); ck.frame.o = mk3(f[9], f[10], f[11]);
         ck.h = 2.0f * cam->focus * tanf(cam->fovy / 2.0f); ck.w = ck.h * cam->aspect; ck.focus = cam->focus;
     }
-    long long cb = 0, cp = 0, ci = 0; int cm = 0;
-#pragma omp parallel for schedule(dynamic, 4) reduction(+ : cb, cp, ci) reduction(max : cm)
+    long long cb = 0, cp = 0, ci = 0, cfr = 0, cea = 0; int cm = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : cb, cp, ci, cfr, cea) reduction(max : cm)
     for (int j = 0; j < height; j++) {
         int stack[YRT_STACK_CAP];
         for (int i = 0; i < width; i++)
@@ -209,15 +213,16 @@ int emu_trace_primary(void* p, const yrt_camera* cam, int width, int height, int
                     sample_uv(i, j, ii, jj, samples, width, height, u, v);
                     ray3 ray = eval_camera(ck, u, v);
                     HitRec h;
-                    TraceCounters tc = {0, 0, 0, 0};
+                    TraceCounters tc = {0, 0, 0, 0, 0, 0};
                     trace_ray<false>(es->view, ray, h, stack, &tc);
                     cb += tc.box_tests; cp += tc.prim_tests; ci += tc.inst_entries; cm = std::max(cm, tc.max_stack);
+                    cfr += tc.slab_false_rejects; cea += tc.slab_extra_accepts;
                     hit_to_ids(es->view, h, ids + 3 * r);
                     if (dist) dist[r] = h.dist;
                     if (uv) { uv[2 * r] = h.w1; uv[2 * r + 1] = h.w2; }
                 }
     }
-    if (counters_out) { counters_out[0] = cb; counters_out[1] = cp; counters_out[2] = ci; counters_out[3] = cm; }
+    if (counters_out) { counters_out[0] = cb; counters_out[1] = cp; counters_out[2] = ci; counters_out[3] = cm; counters_out[4] = cfr; counters_out[5] = cea; }
     return YRT_OK;
 }
 

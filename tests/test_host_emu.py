@@ -18,6 +18,9 @@ def test_emulated_device_hit_ids(name):
     same = (ids == ref["ids"]).all(axis=1)
     assert np.array_equal(dist[same], ref["dist"][same]) and np.array_equal(uv[same], ref["uv"][same])
     assert ctr[3] < 64
+    # the fused (FFMA) slab test must accept a superset of the reference's slab test (scene.cpp:371-383)
+    assert ctr[4] == 0, f"{ctr[4]} boxes culled that the reference would enter"
+    assert ctr[5] <= 1e-3 * ctr[0]
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)

@@ -86,7 +86,7 @@ struct DevScene {
     DevBuf shape_kind, shape_elem_off, shape_elem_cnt, shape_vert_off, shape_prim_off, elem_idx, pos, norm, uv, radius, prim_shape;
     DevBuf inst_frame, inst_shape, inst_mat, active_inst, prim_rank_in, inst_rank_in, prim_rank, inst_rank;
     // build products
-    DevBuf blas_nodes, tlas_nodes, prim_recs, prim_attrs, inst_recs, mat_recs, light_recs, tex, tex_info, lut;
+    DevBuf nodes, prim_recs, prim_attrs, inst_recs, mat_recs, light_recs, tex, tex_info, lut;
     DevBuf blas_seg_root, blas_seg_depth, tlas_seg_root, tlas_seg_depth, shape_box_lo, shape_box_hi;
     int n_prims = 0, n_active = 0, n_blas_nodes = 0, n_tlas_nodes = 0;
     int blas_depth = 0, tlas_depth = 0;

@@ -17,7 +17,7 @@
 namespace yrt {
 
 #define YRT_LEAF_SIZE_BLAS 4   /* the reference also stops at <= 4 prims (scene.cpp:583) */
-#define YRT_LEAF_SIZE_TLAS 2
+#define YRT_LEAF_SIZE_TLAS 1   /* one instance per TLAS leaf: its world box is tested before the ray is transformed */
 
 // ---- order-preserving float <-> int for atomic min/max --------------------------------------
 YRT_HD int float_to_ordered(float f) { int i = float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
@@ -131,6 +131,7 @@ struct LbvhArrays {
     int* seg_root;         // [n_seg] root ref per segment
     int* seg_depth;        // [n_seg] max depth (levels of internal nodes) per segment
     int leaf_size;
+    int ref_offset;        // added to every internal-node reference (position of this tree set in the shared node array)
 };
 
 YRT_HD void seg_bounds_init_item(const LbvhArrays& a, int s) {
@@ -290,7 +291,7 @@ YRT_HD int child_ref_(const LbvhArrays& a, int c) {
     if (c < 0) return make_leaf_ref(~c, 1);
     int cnt = a.range_last[c] - a.range_first[c] + 1;
     if (cnt <= a.leaf_size) return make_leaf_ref(a.range_first[c], cnt);
-    return c;
+    return c + a.ref_offset;
 }
 
 // emit the 64-byte traversal node of internal node i and, if i is exactly a segment, its root ref

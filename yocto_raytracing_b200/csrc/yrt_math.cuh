@@ -149,22 +149,67 @@ YRT_HD bool intersect_line(const ray3& ray, const vec3& v0, const vec3& v1, floa
 }
 
 // ---- slab test: src/scene.cpp:371-383 ------------------------------------------------------
-// invd = 1/d is hoisted out (same three IEEE divides, done once per (ray, instance) instead of
-// once per call); the swap on invd<0 is a select of which bound feeds t0/t1. Returns the
-// reference's accept decision and the entry distance (for near/far ordering only).
-YRT_HD bool intersect_check_bbox(const vec3& o, const vec3& invd, float rtmin, float rtmax, float lox, float loy,
-                                 float loz, float hix, float hiy, float hiz, float& tenter) {
+// Same accept decision as the reference, restated for issue rate (the traversal is ALU-issue bound):
+//   * invd = 1/d and the three `invd < 0` swap predicates are hoisted out (computed once per
+//     (ray, space) instead of once per call; same IEEE divides);
+//   * the swap is a select of which product feeds t0/t1;
+//   * the ternary max/min chains become FMNMX: max(a, b) = (a > b) ? a : b returns b when a is NaN,
+//     exactly like fmaxf(a, b) with a non-NaN b — and in scene.cpp:378-379 only the FIRST operand
+//     (a slab distance, NaN when 0 * inf) can be NaN, the running value never is.  (+0 vs -0 may
+//     differ, which no comparison below can see.)
+// Returns the accept decision and the entry distance (for near/far ordering only).
+struct raysigns { bool x, y, z; };
+YRT_HD raysigns signs_of(const vec3& invd) { raysigns s; s.x = invd.x < 0; s.y = invd.y < 0; s.z = invd.z < 0; return s; }
+
+YRT_HD bool intersect_check_bbox(const vec3& o, const vec3& invd, const raysigns& sg, float rtmin, float rtmax, float lox,
+                                 float loy, float loz, float hix, float hiy, float hiz, float& tenter) {
     float ax = (lox - o.x) * invd.x, bx = (hix - o.x) * invd.x;
     float ay = (loy - o.y) * invd.y, by = (hiy - o.y) * invd.y;
     float az = (loz - o.z) * invd.z, bz = (hiz - o.z) * invd.z;
-    float t0x = (invd.x < 0) ? bx : ax, t1x = (invd.x < 0) ? ax : bx;
-    float t0y = (invd.y < 0) ? by : ay, t1y = (invd.y < 0) ? ay : by;
-    float t0z = (invd.z < 0) ? bz : az, t1z = (invd.z < 0) ? az : bz;
-    float tmin = rmax(t0z, rmax(t0y, rmax(t0x, rtmin)));
-    float tmax = rmin(t1z, rmin(t1y, rmin(t1x, rtmax)));
+    float t0x = sg.x ? bx : ax, t1x = sg.x ? ax : bx;
+    float t0y = sg.y ? by : ay, t1y = sg.y ? ay : by;
+    float t0z = sg.z ? bz : az, t1z = sg.z ? az : bz;
+    float tmin = fmaxf(t0z, fmaxf(t0y, fmaxf(t0x, rtmin)));
+    float tmax = fminf(t1z, fminf(t1y, fminf(t1x, rtmax)));
     tmax *= 1.00000024f;
     tenter = tmin;
     return tmin <= tmax;
+}
+
+// Fused slab test used by the traversal: t = p * invd - o * invd as ONE FFMA per plane instead of
+// FADD + FMUL (the kernels are issue bound and these 24 -> 12 instructions per node are the largest
+// single item, profiles/).  Its values differ from the reference's fl(fl(p - o) * invd) by at most
+// u |o invd| + 3u |t| (u = 2^-24), so the accept test is widened by exactly that: a relative slack
+// of 1 + 16u on tmax (the reference has 1 + 4u) plus an absolute pad of 8u max_i |o_i invd_i|, a
+// per-(ray, space) constant.  Hence it accepts a SUPERSET of what scene.cpp:371-383 accepts — a
+// box is never culled that the reference would enter — and what is found inside is decided by the
+// exact primitive tests, so hits are unchanged (tests/test_host_emu.py counts false rejects: 0).
+// NaN (0 * inf, inf - inf for direction components that are exactly 0) is dropped by FMNMX like in
+// the reference's ternaries, i.e. that axis does not constrain: again a superset.
+struct slabray { vec3 invd, noi; raysigns sg; float pad; };
+
+YRT_HD slabray make_slabray(const vec3& o, const vec3& invd) {
+    slabray r;
+    r.invd = invd;
+    r.noi = mk3(-(o.x * invd.x), -(o.y * invd.y), -(o.z * invd.z));
+    r.sg = signs_of(invd);
+    float m = fmaxf(fmaxf(fmaxf(fabsf(r.noi.x), fabsf(r.noi.y)), fabsf(r.noi.z)), 0.0f);
+    r.pad = m * 4.7683716e-7f;   // 8u
+    return r;
+}
+
+YRT_HD bool slab_test_fused(const slabray& r, float rtmin, float rtmax, float lox, float loy, float loz, float hix, float hiy,
+                            float hiz, float& tenter) {
+    float ax = fmaf(lox, r.invd.x, r.noi.x), bx = fmaf(hix, r.invd.x, r.noi.x);
+    float ay = fmaf(loy, r.invd.y, r.noi.y), by = fmaf(hiy, r.invd.y, r.noi.y);
+    float az = fmaf(loz, r.invd.z, r.noi.z), bz = fmaf(hiz, r.invd.z, r.noi.z);
+    float t0x = r.sg.x ? bx : ax, t1x = r.sg.x ? ax : bx;
+    float t0y = r.sg.y ? by : ay, t1y = r.sg.y ? ay : by;
+    float t0z = r.sg.z ? bz : az, t1z = r.sg.z ? az : bz;
+    float tmin = fmaxf(t0z, fmaxf(t0y, fmaxf(t0x, rtmin)));
+    float tmax = fminf(t1z, fminf(t1y, fminf(t1x, rtmax)));
+    tenter = tmin;
+    return tmin <= fmaf(tmax, 1.00000095f, r.pad);
 }
 
 // ---- camera: src/raytrace.cpp:6-37 ---------------------------------------------------------

@@ -436,8 +436,10 @@ static int check_params(const RenderParams& rp) {
     return YRT_OK;
 }
 
-static int batch_rows_for(const RenderParams& rp, int n_lights, int own_rows) {
-    long long target = env_int("YRT_BATCH_SLOTS", 4 << 20);
+static int batch_rows_for(const RenderParams& rp, int n_lights, int own_rows, bool reflective) {
+    // slots (camera samples) per batch: a whole 1080p/16spp frame (33.2 M slots, 51 B each) when nothing
+    // reflects — fewer launches and kernel tails; 4 M when the per-slot recursion stack must be allocated too
+    long long target = env_int("YRT_BATCH_SLOTS", reflective ? (4 << 20) : (48 << 20));
     long long per_row = (long long)rp.width * rp.samples * rp.samples;
     long long lim = 0xfffffff0ll / std::max(1, n_lights);
     if (target > lim) target = lim;
@@ -453,7 +455,7 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
     int nl = ds.view.n_lights;
     bool reflective = ds.has_reflective;
     int depth_cap = std::max(1, env_int("YRT_MAX_DEPTH", 16));
-    int batch_rows = batch_rows_for(rp, nl, own);
+    int batch_rows = batch_rows_for(rp, nl, own, reflective);
     size_t cap_slots = (size_t)batch_rows * rp.width * spp;
     YRT_TRY(ensure_workspace(ds, cap_slots, nl, depth_cap, reflective));
     cap_slots = ds.ws.cap_slots;
@@ -519,7 +521,7 @@ int trace_primary_device(DevScene& ds, const RenderParams& rp_in, int32_t* h_ids
     YRT_CUDA(cudaSetDevice(ds.device));
     cudaStream_t st = ds.stream;
     int spp = rp.samples * rp.samples;
-    int batch_rows = batch_rows_for(rp, 1, rp.height);
+    int batch_rows = batch_rows_for(rp, 1, rp.height, true);
     size_t cap_slots = (size_t)batch_rows * rp.width * spp;
     YRT_TRY(ensure_workspace(ds, cap_slots, ds.view.n_lights, 1, false));
     DevBuf d_ids, d_dist, d_uv;

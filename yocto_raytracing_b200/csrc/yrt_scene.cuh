@@ -31,6 +31,7 @@ namespace yrt {
 //   ref <  0         : leaf; ~ref = (first << 3) | (count - 1), 1 <= count <= 8
 //   YRT_REF_SENTINEL : traversal stack marker "leave the current instance"
 #define YRT_REF_SENTINEL ((int)0x80000000)
+#define YRT_REF_DONE ((int)0x80000001)      /* traversal finished (never a valid leaf: first <= YRT_MAX_LEAF_FIRST) */
 #define YRT_LEAF_MAX_COUNT 8
 #define YRT_MAX_LEAF_FIRST ((1 << 28) - 2)
 #define YRT_STACK_CAP 128   /* traversal stack entries (TLAS + BLAS levels simultaneously live); checked against the built depth */
@@ -67,8 +68,8 @@ YRT_HD vec3 xyz(const float4& q) { return mk3(q.x, q.y, q.z); }
 
 // ---- what a kernel sees ------------------------------------------------------------------
 struct SceneView {
-    const float4* tlas_nodes;   // 4 per node
-    const float4* blas_nodes;   // 4 per node (all shapes in one array)
+    const float4* nodes;        // 4 per node; BLAS nodes of all shapes first, TLAS nodes after them — one
+                                // array and one index space, so a node visit needs no level test
     const float4* inst_recs;    // 4 per instance, TLAS leaf order
     const float4* prim_recs;    // 3 per prim, BLAS leaf order
     const float4* prim_attrs;   // 4 per prim

@@ -20,6 +20,8 @@ namespace yrt {
 
 struct TraceCounters {   // optional per-ray work counters (roofline inputs), host_emu / debug kernels
     int box_tests, prim_tests, inst_entries, max_stack;
+    int slab_false_rejects;   // boxes the reference's slab test accepts but the fused one rejects (must stay 0)
+    int slab_extra_accepts;   // the other way round (harmless, costs a visit)
 };
 
 // test the prims of one BLAS leaf; returns true if any was hit (tmax/hit updated)
@@ -69,6 +71,12 @@ YRT_HD vec3 inv3(const vec3& d) { return mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z)
 
 // Closest hit (ANY=false): returns whether anything was hit, `hit` filled.
 // Any hit (ANY=true): returns at the first accepted primitive (scene.cpp:414,425,436,473).
+//
+// Loop shape ("while-while"): every lane first walks internal nodes — TLAS and BLAS nodes share the
+// same code, only the ray registers differ — until it holds a leaf; only then does the warp run the
+// leaf code (instance entry: transform the ray; element leaf: primitive tests).  With an if-if loop
+// the node path and the leaf paths would be issued in every iteration for partial warps; the
+// kernel is issue bound, so that matters (profiles/).
 template <bool ANY>
 YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* stack, TraceCounters* ctr) {
     hit.si = -1;
@@ -79,78 +87,86 @@ YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* s
 
     int sp = 0;
     float tmax = wray.tmax;
-    const vec3 winvd = inv3(wray.d);
-    ray3 ray = wray;          // ray in the current space (world, or local to instance `si`)
-    vec3 invd = winvd;
+    const float tmin = wray.tmin;            // copied unchanged into every instance space (vmath.h:277)
+    const slabray wsr = make_slabray(wray.o, inv3(wray.d));
+    vec3 o = wray.o, d = wray.d;                 // ray in the current space (world, or local to instance `si`)
+    slabray sr = wsr;
     bool top = true;
     int si = -1, kind = 0;
     int cur = sv.tlas_root;
     bool found = false;
 
+// pop the next reference; leaving an instance (sentinel) restores the world-space ray
+#define YRT_POP()                                   \
+    for (;;) {                                      \
+        if (sp == 0) { cur = YRT_REF_DONE; break; } \
+        cur = stack[--sp];                          \
+        if (cur != YRT_REF_SENTINEL) break;         \
+        top = true;                                 \
+        o = wray.o; d = wray.d; sr = wsr;           \
+    }
+
     for (;;) {
-        bool pop = false;
-        if (cur >= 0) {
-            // internal node: test both child boxes against the current ray and current tmax
-            const float4* n = (top ? sv.tlas_nodes : sv.blas_nodes) + 4 * (size_t)cur;
+        // ---- internal nodes: test both child boxes against the current ray and current tmax ----
+        while (cur >= 0) {
+            const float4* n = sv.nodes + 4 * (size_t)cur;
             float4 q0 = ld4(n), q1 = ld4(n + 1), q2 = ld4(n + 2), q3 = ld4(n + 3);
             float e0, e1;
-            bool h0 = intersect_check_bbox(ray.o, invd, ray.tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, e0);
-            bool h1 = intersect_check_bbox(ray.o, invd, ray.tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, e1);
-            if (ctr) ctr->box_tests += 2;
+            bool h0 = slab_test_fused(sr, tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, e0);
+            bool h1 = slab_test_fused(sr, tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, e1);
+            if (ctr) {   // host-side audit against the reference's own test
+                ctr->box_tests += 2;
+                float e;
+                bool r0 = intersect_check_bbox(o, sr.invd, sr.sg, tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, e);
+                bool r1 = intersect_check_bbox(o, sr.invd, sr.sg, tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, e);
+                ctr->slab_false_rejects += (r0 && !h0) + (r1 && !h1);
+                ctr->slab_extra_accepts += (!r0 && h0) + (!r1 && h1);
+            }
             int c0 = float_as_int(q0.w), c1 = float_as_int(q1.w);
             if (h0 && h1) {
                 bool swap = e1 < e0;   // near child first
-                int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
-                stack[sp++] = farc;
+                stack[sp++] = swap ? c0 : c1;
                 if (ctr && sp > ctr->max_stack) ctr->max_stack = sp;
-                cur = nearc;
+                cur = swap ? c1 : c0;
             } else if (h0) {
                 cur = c0;
             } else if (h1) {
                 cur = c1;
             } else {
-                pop = true;
-            }
-        } else {
-            int first = leaf_first(cur), count = leaf_count(cur);
-            if (top) {
-                // TLAS leaf: enter its first instance, keep the rest for later
-                if (count > 1) {
-                    stack[sp++] = make_leaf_ref(first + 1, count - 1);
-                }
-                const float4* ir = sv.inst_recs + 4 * (size_t)first;
-                float4 q0 = ld4(ir), q1 = ld4(ir + 1), q2 = ld4(ir + 2), q3 = ld4(ir + 3);
-                frame3 f;
-                f.x = xyz(q0); f.y = xyz(q1); f.z = xyz(q2); f.o = xyz(q3);
-                ray3 w = wray;
-                w.tmax = tmax;
-                ray = transform_ray_inverse(f, w);   // scene.cpp:468
-                invd = inv3(ray.d);
-                si = first;
-                kind = ((unsigned)float_as_int(q3.w)) >> 28;
-                top = false;
-                stack[sp++] = YRT_REF_SENTINEL;
-                if (ctr) { ctr->inst_entries++; if (sp > ctr->max_stack) ctr->max_stack = sp; }
-                cur = float_as_int(q0.w);   // BLAS root ref of the instance's shape
-            } else {
-                if (leaf_prims<ANY>(sv, kind, first, count, ray, tmax, si, hit, ctr)) {
-                    found = true;
-                    if (ANY) return true;
-                }
-                pop = true;
+                YRT_POP();
             }
         }
-        if (pop) {
-            for (;;) {
-                if (sp == 0) return found;
-                cur = stack[--sp];
-                if (cur != YRT_REF_SENTINEL) break;
-                top = true;   // leave the instance: back to the world-space ray
-                ray = wray;
-                invd = winvd;
+        if (cur == YRT_REF_DONE) break;
+        // ---- leaf ----
+        int first = leaf_first(cur), count = leaf_count(cur);
+        if (top) {
+            // TLAS leaf: enter its first instance, keep the rest for later
+            if (count > 1) stack[sp++] = make_leaf_ref(first + 1, count - 1);
+            const float4* ir = sv.inst_recs + 4 * (size_t)first;
+            float4 q0 = ld4(ir), q1 = ld4(ir + 1), q2 = ld4(ir + 2), q3 = ld4(ir + 3);
+            frame3 f;
+            f.x = xyz(q0); f.y = xyz(q1); f.z = xyz(q2); f.o = xyz(q3);
+            o = transform_point_inverse(f, wray.o);          // transform_ray_inverse, scene.cpp:468
+            d = transform_direction_inverse(f, wray.d);
+            sr = make_slabray(o, inv3(d));
+            si = first;
+            kind = ((unsigned)float_as_int(q3.w)) >> 28;
+            top = false;
+            stack[sp++] = YRT_REF_SENTINEL;
+            if (ctr) { ctr->inst_entries++; if (sp > ctr->max_stack) ctr->max_stack = sp; }
+            cur = float_as_int(q0.w);   // BLAS root ref of the instance's shape
+        } else {
+            ray3 lray;
+            lray.o = o; lray.d = d; lray.tmin = tmin; lray.tmax = tmax;
+            if (leaf_prims<ANY>(sv, kind, first, count, lray, tmax, si, hit, ctr)) {
+                found = true;
+                if (ANY) return true;
             }
+            YRT_POP();
         }
     }
+#undef YRT_POP
+    return found;
 }
 
 }  // namespace yrt
