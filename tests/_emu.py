@@ -43,7 +43,7 @@ class EmuScene:
         ids = np.empty((n, 3), np.int32)
         dist = np.empty(n, np.float32)
         uv = np.empty((n, 2), np.float32)
-        ctr = (C.c_int64 * 6)()
+        ctr = (C.c_int64 * 8)()
         cam = self.flat.camera_struct()
         st = lib().emu_trace_primary(self.h, C.byref(cam), width, height, samples, C.c_void_p(ids.ctypes.data),
                                      C.c_void_p(dist.ctypes.data), C.c_void_p(uv.ctypes.data), ctr)
@@ -54,7 +54,7 @@ class EmuScene:
         img = np.empty((height, width, 4), np.float32)
         cam = self.flat.camera_struct()
         a = (C.c_float * 3)(amb, amb, amb)
-        rc = (C.c_int64 * 3)()
+        rc = (C.c_int64 * 8)()
         st = lib().emu_render(self.h, C.byref(cam), a, width, height, samples, max_depth, C.c_void_p(img.ctypes.data), rc)
         assert st == 0
         return img, list(rc)

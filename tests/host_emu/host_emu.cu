@@ -6,6 +6,7 @@
 // / node emit as the CUDA build (std::stable_sort stands in for the device radix sort), same
 // trace_ray / shade_hit code as the kernels.  libyrt_b200.so never links or calls this.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -24,7 +25,7 @@ struct EmuLbvh {
 };
 
 void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi, const int* seg_of, const int* seg_first, int leaf_size,
-              EmuLbvh& out, int ref_offset) {
+              EmuLbvh& out, int ref_offset, int size_bits) {
     size_t ni = n > 1 ? n - 1 : 1;
     std::vector<int> cent_lo(3 * n_seg), cent_hi(3 * n_seg);
     out.seg_box_lo.assign(3 * n_seg, 0);
@@ -42,7 +43,7 @@ void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi
     a.keys = keys.data(); a.order = out.order.data(); a.left = left.data(); a.right = right.data();
     a.range_first = rfirst.data(); a.range_last = rlast.data(); a.parent_int = pint.data(); a.parent_leaf = pleaf.data();
     a.flags = flags.data(); a.node_lo = nlo.data(); a.node_hi = nhi.data(); a.nodes = out.nodes.data();
-    a.seg_root = out.seg_root.data(); a.seg_depth = out.seg_depth.data(); a.leaf_size = leaf_size; a.ref_offset = ref_offset;
+    a.seg_root = out.seg_root.data(); a.seg_depth = out.seg_depth.data(); a.leaf_size = leaf_size; a.ref_offset = ref_offset; a.size_bits = size_bits;
     for (int s = 0; s < n_seg; s++) seg_bounds_init_item(a, s);
     for (int i = 0; i < n; i++) seg_bounds_item(a, i);
     for (int i = 0; i < n; i++) morton_item(a, i);
@@ -91,7 +92,7 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
         phi[i] = mk4(b.hi.x, b.hi.y, b.hi.z, 0.f);
     }
     int nseg = std::max(hs.n_shapes, 1);
-    emu_lbvh(np, nseg, plo, phi, g.prim_shape, g.shape_prim_off, leaf_blas, es.blas, 0);
+    emu_lbvh(np, nseg, plo, phi, g.prim_shape, g.shape_prim_off, leaf_blas, es.blas, 0, getenv("YRT_SIZE_BITS_BLAS") ? atoi(getenv("YRT_SIZE_BITS_BLAS")) : YRT_SIZE_BITS_BLAS);
     // prim + attribute records in BLAS leaf order (mirrors k_gather_prims)
     es.prim_recs.assign(3 * (size_t)std::max(np, 1), mk4(0, 0, 0, 0));
     es.prim_attrs.assign(4 * (size_t)std::max(np, 1), mk4(0, 0, 0, 0));
@@ -135,7 +136,7 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
     std::vector<int> seg_of(std::max(na, 1), 0);
     int sf[2] = {0, na};
     int nb_int = np > 1 ? np - 1 : 0;
-    emu_lbvh(na, 1, ilo, ihi, seg_of.data(), sf, leaf_tlas, es.tlas, nb_int);
+    emu_lbvh(na, 1, ilo, ihi, seg_of.data(), sf, leaf_tlas, es.tlas, nb_int, getenv("YRT_SIZE_BITS_TLAS") ? atoi(getenv("YRT_SIZE_BITS_TLAS")) : YRT_SIZE_BITS_TLAS);
     es.nodes.assign(es.blas.nodes.begin(), es.blas.nodes.begin() + 4 * (size_t)nb_int);
     es.nodes.insert(es.nodes.end(), es.tlas.nodes.begin(), es.tlas.nodes.end());
     es.inst_recs.assign(4 * (size_t)std::max(na, 1), mk4(0, 0, 0, 0));
@@ -201,8 +202,8 @@ int emu_trace_primary(void* p, const yrt_camera* cam, int width, int height, int
         ck.frame.x = mk3(f[0], f[1], f[2]); ck.frame.y = mk3(f[3], f[4], f[5]); ck.frame.z = mk3(f[6], f[7], f[8]); ck.frame.o = mk3(f[9], f[10], f[11]);
         ck.h = 2.0f * cam->focus * tanf(cam->fovy / 2.0f); ck.w = ck.h * cam->aspect; ck.focus = cam->focus;
     }
-    long long cb = 0, cp = 0, ci = 0, cfr = 0, cea = 0; int cm = 0;
-#pragma omp parallel for schedule(dynamic, 4) reduction(+ : cb, cp, ci, cfr, cea) reduction(max : cm)
+    long long cb = 0, cp = 0, ci = 0, cfr = 0, cea = 0, ctb = 0; int cm = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : cb, cp, ci, cfr, cea, ctb) reduction(max : cm)
     for (int j = 0; j < height; j++) {
         int stack[YRT_STACK_CAP];
         for (int i = 0; i < width; i++)
@@ -213,22 +214,23 @@ int emu_trace_primary(void* p, const yrt_camera* cam, int width, int height, int
                     sample_uv(i, j, ii, jj, samples, width, height, u, v);
                     ray3 ray = eval_camera(ck, u, v);
                     HitRec h;
-                    TraceCounters tc = {0, 0, 0, 0, 0, 0};
+                    TraceCounters tc = {0, 0, 0, 0, 0, 0, 0};
                     trace_ray<false>(es->view, ray, h, stack, &tc);
                     cb += tc.box_tests; cp += tc.prim_tests; ci += tc.inst_entries; cm = std::max(cm, tc.max_stack);
-                    cfr += tc.slab_false_rejects; cea += tc.slab_extra_accepts;
+                    cfr += tc.slab_false_rejects; cea += tc.slab_extra_accepts; ctb += tc.tlas_box_tests;
                     hit_to_ids(es->view, h, ids + 3 * r);
                     if (dist) dist[r] = h.dist;
                     if (uv) { uv[2 * r] = h.w1; uv[2 * r + 1] = h.w2; }
                 }
     }
-    if (counters_out) { counters_out[0] = cb; counters_out[1] = cp; counters_out[2] = ci; counters_out[3] = cm; counters_out[4] = cfr; counters_out[5] = cea; }
+    if (counters_out) { counters_out[0] = cb; counters_out[1] = cp; counters_out[2] = ci; counters_out[3] = cm; counters_out[4] = cfr; counters_out[5] = cea; counters_out[6] = ctb; }
     return YRT_OK;
 }
 
 // the whole frame with the device functions: raygen -> closest -> shadow (any) -> shade -> reflection
 // loop with the same explicit {c, kr, la} stack as k_shade -> ordered per-pixel sum.
-// ray_counts (optional, 3 int64): primary, reflection, shadow
+// ray_counts (optional, 8 int64): primary, reflection, shadow, then for the shadow rays: box tests, tlas box tests,
+// prim tests, instance entries, occluded
 int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, int height, int samples, int max_depth, float* rgba,
                int64_t* ray_counts) {
     EmuScene* es = (EmuScene*)p;
@@ -241,8 +243,8 @@ int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, in
     }
     vec3 ambv = mk3(amb[0], amb[1], amb[2]);
     if (max_depth <= 0) max_depth = 16;
-    long long n_refl = 0, n_shadow = 0;
-#pragma omp parallel for schedule(dynamic, 2) reduction(+ : n_refl, n_shadow)
+    long long n_refl = 0, n_shadow = 0, sb = 0, stb = 0, sp_ = 0, si_ = 0, socc = 0;
+#pragma omp parallel for schedule(dynamic, 2) reduction(+ : n_refl, n_shadow, sb, stb, sp_, si_, socc)
     for (int j = 0; j < height; j++) {
         int stack[YRT_STACK_CAP];
         std::vector<vec3> sc(max_depth), skr(max_depth), sla(max_depth);
@@ -268,8 +270,10 @@ int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, in
                             light_vector(sv, k, P, l, r, ke);
                             ray3 sr = shadow_ray(P, l, r);
                             HitRec hr;
-                            vis[k] = trace_ray<true>(sv, sr, hr, stack, nullptr) ? 0 : 1;
+                            TraceCounters tc = {0, 0, 0, 0, 0, 0, 0};
+                            vis[k] = trace_ray<true>(sv, sr, hr, stack, &tc) ? 0 : 1;
                             n_shadow++;
+                            sb += tc.box_tests; stb += tc.tlas_box_tests; sp_ += tc.prim_tests; si_ += tc.inst_entries; socc += vis[k] ? 0 : 1;
                         }
                         vec3 c, kr, la; ray3 rr;
                         bool spawn = shade_hit(sv, h.si, h.prim, h.w1, h.w2, ray.o, ambv, sv.srgb_lut, [&](int k) { return vis[k] != 0; },
@@ -287,7 +291,8 @@ int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, in
             o[0] = sx / dn; o[1] = sy / dn; o[2] = sz / dn; o[3] = 1.0f;
         }
     }
-    if (ray_counts) { ray_counts[0] = (long long)width * height * samples * samples; ray_counts[1] = n_refl; ray_counts[2] = n_shadow; }
+    if (ray_counts) { ray_counts[0] = (long long)width * height * samples * samples; ray_counts[1] = n_refl; ray_counts[2] = n_shadow;
+        ray_counts[3] = sb; ray_counts[4] = stb; ray_counts[5] = sp_; ray_counts[6] = si_; ray_counts[7] = socc; }
     return YRT_OK;
 }
 

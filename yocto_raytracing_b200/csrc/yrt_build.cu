@@ -270,6 +270,7 @@ extern "C" int yrt_debug_sort_pairs(unsigned long long* h_keys, int* h_vals, int
 struct LbvhOut {
     float4* nodes;        // 4 float4 per internal node, preallocated by the caller
     int ref_offset;       // index of this tree set's node 0 in the shared node array
+    int size_bits;        // size-class bits in the sort key (see morton_item)
     DevBuf* seg_root;     // [n_seg]
     DevBuf* seg_depth;    // [n_seg]
     DevBuf* order;        // [n] item id at sorted slot
@@ -332,6 +333,7 @@ static int lbvh_build(int dev, cudaStream_t st, int n, int n_seg, float4* box_lo
     a.node_hi = nhi.as<float4>();
     a.nodes = out.nodes;
     a.ref_offset = out.ref_offset;
+    a.size_bits = out.size_bits;
     a.seg_root = out.seg_root->as<int>();
     a.seg_depth = out.seg_depth->as<int>();
     a.leaf_size = leaf_size;
@@ -410,6 +412,10 @@ int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
     const char* env_lt = getenv("YRT_LEAF_TLAS");
     int leaf_blas = env_lb ? atoi(env_lb) : YRT_LEAF_SIZE_BLAS;
     int leaf_tlas = env_lt ? atoi(env_lt) : YRT_LEAF_SIZE_TLAS;
+    const char* env_sb = getenv("YRT_SIZE_BITS_BLAS");
+    const char* env_st = getenv("YRT_SIZE_BITS_TLAS");
+    int size_bits_blas = std::min(std::max(env_sb ? atoi(env_sb) : YRT_SIZE_BITS_BLAS, 0), 3);
+    int size_bits_tlas = std::min(std::max(env_st ? atoi(env_st) : YRT_SIZE_BITS_TLAS, 0), 3);
     leaf_blas = std::min(std::max(leaf_blas, 1), YRT_LEAF_MAX_COUNT);
     leaf_tlas = std::min(std::max(leaf_tlas, 1), YRT_LEAF_MAX_COUNT);
 
@@ -438,7 +444,7 @@ int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
     int nb_int = hs.n_prims > 1 ? hs.n_prims - 1 : 0, nt_int = ds.n_active > 1 ? ds.n_active - 1 : 0;
     YRT_TRY(ds.nodes.alloc(sizeof(float4) * 4 * (size_t)(nb_int + nt_int + 2), device));
     LbvhOut bo;
-    bo.nodes = ds.nodes.as<float4>(); bo.ref_offset = 0; bo.seg_root = &ds.blas_seg_root; bo.seg_depth = &ds.blas_seg_depth; bo.order = &blas_order;
+    bo.nodes = ds.nodes.as<float4>(); bo.ref_offset = 0; bo.size_bits = size_bits_blas; bo.seg_root = &ds.blas_seg_root; bo.seg_depth = &ds.blas_seg_depth; bo.order = &blas_order;
     bo.seg_box_lo = &ds.shape_box_lo; bo.seg_box_hi = &ds.shape_box_hi;
     YRT_TRY(lbvh_build(device, st, hs.n_prims, std::max(hs.n_shapes, 1), plo.as<float4>(), phi.as<float4>(), g.prim_shape,
                        g.shape_prim_off, leaf_blas, bo));
@@ -463,7 +469,7 @@ int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
         k_inst_boxes<<<grid_for(na), 256, 0, st>>>(na, ds.active_inst.as<int>(), ds.inst_frame.as<float>(), ds.inst_shape.as<int>(),
                                                  ds.shape_box_lo.as<int>(), ds.shape_box_hi.as<int>(), ilo.as<float4>(), ihi.as<float4>());
     LbvhOut to;
-    to.nodes = ds.nodes.as<float4>() + 4 * (size_t)nb_int; to.ref_offset = nb_int; to.seg_root = &ds.tlas_seg_root; to.seg_depth = &ds.tlas_seg_depth; to.order = &tlas_order;
+    to.nodes = ds.nodes.as<float4>() + 4 * (size_t)nb_int; to.ref_offset = nb_int; to.size_bits = size_bits_tlas; to.seg_root = &ds.tlas_seg_root; to.seg_depth = &ds.tlas_seg_depth; to.order = &tlas_order;
     to.seg_box_lo = nullptr; to.seg_box_hi = nullptr;
     YRT_TRY(lbvh_build(device, st, na, 1, ilo.as<float4>(), ihi.as<float4>(), tl_seg_of.as<int>(), tl_seg_first.as<int>(), leaf_tlas, to));
     YRT_TRY(ds.inst_recs.alloc(sizeof(float4) * 4 * (size_t)std::max(na, 1), device));

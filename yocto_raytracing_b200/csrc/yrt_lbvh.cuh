@@ -17,6 +17,8 @@
 namespace yrt {
 
 #define YRT_LEAF_SIZE_BLAS 4   /* the reference also stops at <= 4 prims (scene.cpp:583) */
+#define YRT_SIZE_BITS_BLAS 0
+#define YRT_SIZE_BITS_TLAS 3
 #define YRT_LEAF_SIZE_TLAS 1   /* one instance per TLAS leaf: its world box is tested before the ray is transformed */
 
 // ---- order-preserving float <-> int for atomic min/max --------------------------------------
@@ -132,6 +134,7 @@ struct LbvhArrays {
     int* seg_depth;        // [n_seg] max depth (levels of internal nodes) per segment
     int leaf_size;
     int ref_offset;        // added to every internal-node reference (position of this tree set in the shared node array)
+    int size_bits;         // 0..3: top bits of the Morton part hold a size class (see morton_item)
 };
 
 YRT_HD void seg_bounds_init_item(const LbvhArrays& a, int s) {
@@ -186,14 +189,38 @@ YRT_HD unsigned int quant16(float c, float lo, float hi) {
     return q > 65535u ? 65535u : q;
 }
 
-// key = segment (16 bits) | 48-bit Morton code of the centroid inside the segment's centroid box
+// key = segment (16 bits) | [size class (size_bits)] | Morton code of the centroid inside the segment's
+// centroid box (16 bits per axis, 15 when a size class is present).
+// Size class: a plain LBVH buries an item that is much larger than its neighbours (the floor among
+// 10 000 unit-sized instances) deep in the tree, so every ancestor on that path inherits its huge box
+// and every ray has to walk that path.  Putting floor(log2(segment extent / item extent)) in the top
+// key bits makes items of very different size separate at the top levels of the radix tree instead
+// (cf. extended Morton codes, Vinkler et al. 2017); items of one class form an ordinary spatial LBVH.
 YRT_HD void morton_item(const LbvhArrays& a, int i) {
     int s = a.seg_of[i];
-    vec3 c = box_centroid(a.box_lo[i], a.box_hi[i]);
+    float4 lo = a.box_lo[i], hi = a.box_hi[i];
+    vec3 c = box_centroid(lo, hi);
     unsigned int qx = quant16(c.x, ordered_to_float(a.seg_cent_lo[3 * s + 0]), ordered_to_float(a.seg_cent_hi[3 * s + 0]));
     unsigned int qy = quant16(c.y, ordered_to_float(a.seg_cent_lo[3 * s + 1]), ordered_to_float(a.seg_cent_hi[3 * s + 1]));
     unsigned int qz = quant16(c.z, ordered_to_float(a.seg_cent_lo[3 * s + 2]), ordered_to_float(a.seg_cent_hi[3 * s + 2]));
-    unsigned long long m = (spread16(qx) << 2) | (spread16(qy) << 1) | spread16(qz);
+    unsigned long long m;
+    if (a.size_bits > 0) {
+        float E = fmaxf(fmaxf(ordered_to_float(a.seg_box_hi[3 * s + 0]) - ordered_to_float(a.seg_box_lo[3 * s + 0]),
+                              ordered_to_float(a.seg_box_hi[3 * s + 1]) - ordered_to_float(a.seg_box_lo[3 * s + 1])),
+                        ordered_to_float(a.seg_box_hi[3 * s + 2]) - ordered_to_float(a.seg_box_lo[3 * s + 2]));
+        float e = fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);
+        int maxc = (1 << a.size_bits) - 1;
+        int cls = maxc;
+        if (e > 0.f && E > 0.f) {
+            // exponent difference = floor(log2(E)) - floor(log2(e)), integer-only and deterministic
+            int de = ((float_as_int(E) >> 23) & 0xff) - ((float_as_int(e) >> 23) & 0xff);
+            cls = de < 0 ? 0 : (de > maxc ? maxc : de);
+        }
+        m = (spread16(qx >> 1) << 2) | (spread16(qy >> 1) << 1) | spread16(qz >> 1);   // 15 bits per axis
+        m |= (unsigned long long)cls << 45;
+    } else {
+        m = (spread16(qx) << 2) | (spread16(qy) << 1) | spread16(qz);
+    }
     a.keys[i] = ((unsigned long long)(unsigned)s << 48) | m;
     a.order[i] = i;
 }

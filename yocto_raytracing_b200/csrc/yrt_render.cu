@@ -45,7 +45,11 @@ __device__ __forceinline__ void slot_to_sample(const BatchParams& bp, unsigned s
     ii = (int)(s - (unsigned)jj * (unsigned)bp.samples);
 }
 
-// warp-granular dynamic work fetch of a persistent kernel
+// warp-granular dynamic work fetch of a persistent kernel: 32 consecutive items per warp.
+// (Measured alternative, profiles/r1_experiments.md: handing a finished lane a new ray while the rest of the
+// warp keeps traversing — per-warp item pool + warp vote — LOSES here, 19.4 -> 20.8..31.7 ms/frame as the refill
+// threshold goes from 32 to 1 idle lanes: the 32 rays of a warp are neighbouring samples that walk the tree
+// together, and refilled lanes are out of phase with them, so node and leaf code stop overlapping.)
 __device__ __forceinline__ unsigned warp_fetch(unsigned* counter, int lane) {
     unsigned base = 0;
     if (lane == 0) base = atomicAdd(counter, 32u);

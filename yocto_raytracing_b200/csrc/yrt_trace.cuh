@@ -22,6 +22,7 @@ struct TraceCounters {   // optional per-ray work counters (roofline inputs), ho
     int box_tests, prim_tests, inst_entries, max_stack;
     int slab_false_rejects;   // boxes the reference's slab test accepts but the fused one rejects (must stay 0)
     int slab_extra_accepts;   // the other way round (harmless, costs a visit)
+    int tlas_box_tests;       // part of box_tests spent in the instance tree
 };
 
 // test the prims of one BLAS leaf; returns true if any was hit (tmax/hit updated)
@@ -69,45 +70,52 @@ YRT_HD bool leaf_prims(const SceneView& sv, int kind, int first, int count, cons
 
 YRT_HD vec3 inv3(const vec3& d) { return mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }   // scene.cpp:372
 
-// Closest hit (ANY=false): returns whether anything was hit, `hit` filled.
-// Any hit (ANY=true): returns at the first accepted primitive (scene.cpp:414,425,436,473).
+// Resumable traversal state of one ray.  Closest hit (ANY=false) keeps shrinking tmax; any hit
+// (ANY=true) stops at the first accepted primitive (scene.cpp:414,425,436,473).
 //
-// Loop shape ("while-while"): every lane first walks internal nodes — TLAS and BLAS nodes share the
-// same code, only the ray registers differ — until it holds a leaf; only then does the warp run the
-// leaf code (instance entry: transform the ray; element leaf: primitive tests).  With an if-if loop
-// the node path and the leaf paths would be issued in every iteration for partial warps; the
-// kernel is issue bound, so that matters (profiles/).
+// Loop shape ("while-while"): nodes() walks internal nodes — TLAS and BLAS nodes share the same code
+// and one index space, only the ray registers differ — until the lane holds a leaf; leaf() then runs
+// the leaf code once (instance entry: transform the ray; element leaf: primitive tests).  With an
+// if-if loop the node path and the leaf paths would be issued in every iteration for partial warps;
+// the kernels are issue bound, so that matters (profiles/).  Being resumable lets the persistent
+// kernels hand a finished lane a new ray while the rest of the warp keeps going.
 template <bool ANY>
-YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* stack, TraceCounters* ctr) {
-    hit.si = -1;
-    hit.prim = -1;
-    hit.w1 = hit.w2 = 0.f;
-    hit.dist = 0.f;
-    if (sv.n_active_instances <= 0) return false;
+struct Tracer {
+    vec3 wo, wd;          // world-space ray
+    slabray wsr;
+    vec3 o, d;            // ray in the current space (world, or local to instance `si`)
+    slabray sr;
+    float tmin, tmax;     // tmin is copied unchanged into every instance space (vmath.h:277)
+    int cur, sp, si, kind;
+    bool top, found;
+    HitRec hit;
 
-    int sp = 0;
-    float tmax = wray.tmax;
-    const float tmin = wray.tmin;            // copied unchanged into every instance space (vmath.h:277)
-    const slabray wsr = make_slabray(wray.o, inv3(wray.d));
-    vec3 o = wray.o, d = wray.d;                 // ray in the current space (world, or local to instance `si`)
-    slabray sr = wsr;
-    bool top = true;
-    int si = -1, kind = 0;
-    int cur = sv.tlas_root;
-    bool found = false;
+    YRT_HD void idle() { cur = YRT_REF_DONE; sp = 0; found = false; }
+    YRT_HD bool done() const { return cur == YRT_REF_DONE; }
 
-// pop the next reference; leaving an instance (sentinel) restores the world-space ray
-#define YRT_POP()                                   \
-    for (;;) {                                      \
-        if (sp == 0) { cur = YRT_REF_DONE; break; } \
-        cur = stack[--sp];                          \
-        if (cur != YRT_REF_SENTINEL) break;         \
-        top = true;                                 \
-        o = wray.o; d = wray.d; sr = wsr;           \
+    YRT_HD void begin(const SceneView& sv, const ray3& wray) {
+        hit.si = -1; hit.prim = -1; hit.w1 = hit.w2 = 0.f; hit.dist = 0.f;
+        wo = wray.o; wd = wray.d;
+        wsr = make_slabray(wo, inv3(wd));
+        o = wo; d = wd; sr = wsr;
+        tmin = wray.tmin; tmax = wray.tmax;
+        sp = 0; si = -1; kind = 0; top = true; found = false;
+        cur = sv.n_active_instances > 0 ? sv.tlas_root : YRT_REF_DONE;
     }
 
-    for (;;) {
-        // ---- internal nodes: test both child boxes against the current ray and current tmax ----
+    // pop the next reference; leaving an instance (sentinel) restores the world-space ray
+    YRT_HD void pop(const int* stack) {
+        for (;;) {
+            if (sp == 0) { cur = YRT_REF_DONE; break; }
+            cur = stack[--sp];
+            if (cur != YRT_REF_SENTINEL) break;
+            top = true;
+            o = wo; d = wd; sr = wsr;
+        }
+    }
+
+    // internal nodes: test both child boxes against the current ray and current tmax, near child first
+    YRT_HD void nodes(const SceneView& sv, int* stack, TraceCounters* ctr) {
         while (cur >= 0) {
             const float4* n = sv.nodes + 4 * (size_t)cur;
             float4 q0 = ld4(n), q1 = ld4(n + 1), q2 = ld4(n + 2), q3 = ld4(n + 3);
@@ -116,6 +124,7 @@ YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* s
             bool h1 = slab_test_fused(sr, tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, e1);
             if (ctr) {   // host-side audit against the reference's own test
                 ctr->box_tests += 2;
+                if (top) ctr->tlas_box_tests += 2;
                 float e;
                 bool r0 = intersect_check_bbox(o, sr.invd, sr.sg, tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, e);
                 bool r1 = intersect_check_bbox(o, sr.invd, sr.sg, tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, e);
@@ -124,7 +133,7 @@ YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* s
             }
             int c0 = float_as_int(q0.w), c1 = float_as_int(q1.w);
             if (h0 && h1) {
-                bool swap = e1 < e0;   // near child first
+                bool swap = e1 < e0;
                 stack[sp++] = swap ? c0 : c1;
                 if (ctr && sp > ctr->max_stack) ctr->max_stack = sp;
                 cur = swap ? c1 : c0;
@@ -133,11 +142,13 @@ YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* s
             } else if (h1) {
                 cur = c1;
             } else {
-                YRT_POP();
+                pop(stack);
             }
         }
-        if (cur == YRT_REF_DONE) break;
-        // ---- leaf ----
+    }
+
+    // one leaf (cur < 0 and not done)
+    YRT_HD void leaf(const SceneView& sv, int* stack, TraceCounters* ctr) {
         int first = leaf_first(cur), count = leaf_count(cur);
         if (top) {
             // TLAS leaf: enter its first instance, keep the rest for later
@@ -146,8 +157,8 @@ YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* s
             float4 q0 = ld4(ir), q1 = ld4(ir + 1), q2 = ld4(ir + 2), q3 = ld4(ir + 3);
             frame3 f;
             f.x = xyz(q0); f.y = xyz(q1); f.z = xyz(q2); f.o = xyz(q3);
-            o = transform_point_inverse(f, wray.o);          // transform_ray_inverse, scene.cpp:468
-            d = transform_direction_inverse(f, wray.d);
+            o = transform_point_inverse(f, wo);              // transform_ray_inverse, scene.cpp:468
+            d = transform_direction_inverse(f, wd);
             sr = make_slabray(o, inv3(d));
             si = first;
             kind = ((unsigned)float_as_int(q3.w)) >> 28;
@@ -160,13 +171,24 @@ YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* s
             lray.o = o; lray.d = d; lray.tmin = tmin; lray.tmax = tmax;
             if (leaf_prims<ANY>(sv, kind, first, count, lray, tmax, si, hit, ctr)) {
                 found = true;
-                if (ANY) return true;
+                if (ANY) { cur = YRT_REF_DONE; return; }
             }
-            YRT_POP();
+            pop(stack);
         }
     }
-#undef YRT_POP
-    return found;
+};
+
+template <bool ANY>
+YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* stack, TraceCounters* ctr) {
+    Tracer<ANY> t;
+    t.begin(sv, wray);
+    for (;;) {
+        t.nodes(sv, stack, ctr);
+        if (t.done()) break;
+        t.leaf(sv, stack, ctr);
+    }
+    hit = t.hit;
+    return t.found;
 }
 
 }  // namespace yrt
