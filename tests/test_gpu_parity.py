@@ -208,3 +208,32 @@ def test_full_size_properties(gpu):
             D._unpack(packed, full, w, h, 16, rank, 8)
         torch.cuda.synchronize()
         assert np.array_equal(full.cpu().numpy().view(np.uint32), img.view(np.uint32))
+
+
+def test_drop_in_cli_matches_reference_cli(gpu, tmp_path):
+    """bin/raytrace (the reference's main() with build_bvh + raytrace swapped for the C ABI, same loader, same
+    PNG writer, same flags) against the unmodified reference binary on the same OBJ: PNG pixels within 1/255 on
+    >= 99.9 % of pixels.  Both binaries link the reference's loader, so they exist only where it was built."""
+    import os
+    import subprocess
+    from PIL import Image
+    from conftest import ROOT
+    ours, ref = os.path.join(ROOT, "bin", "raytrace"), os.path.join(ROOT, "oracle", "_ref", "raytrace_ref")
+    if not (os.path.exists(ours) and os.path.exists(ref)):
+        pytest.skip("bin/raytrace / oracle/_ref/raytrace_ref not built (need the reference sources at build time)")
+    for sc, res, smp in ((synth.instance_grid_scene(20, seed=9), 180, 2), (synth.mixed_scene(7), 120, 2), (synth.hair_scene(256), 120, 2)):
+        obj = sc.write_obj(str(tmp_path / sc.name))
+        cwd = os.path.dirname(obj)
+        a, b = os.path.join(cwd, "ours.png"), os.path.join(cwd, "ref.png")
+        args = ["-r", str(res), "-s", str(smp), "-a", "0.1"]
+        r1 = subprocess.run([ours] + args + ["-o", a, os.path.basename(obj)], cwd=cwd, capture_output=True, text=True)
+        assert r1.returncode == 0, r1.stdout + r1.stderr
+        # same four progress lines as the reference (src/raytrace.cpp:273-285)
+        assert [l.split()[0] for l in r1.stdout.strip().splitlines()[:4]] == ["loading", "creating", "tracing", "saving"]
+        subprocess.run([ref] + args + ["-o", b, os.path.basename(obj)], cwd=cwd, check=True, capture_output=True)
+        ia, ib = np.array(Image.open(a)), np.array(Image.open(b))
+        assert ia.shape == ib.shape
+        within1, ident, mx = ldr_stats(ia, ib)
+        assert within1 >= PIXEL_BAR, (sc.name, within1, ident, mx)
+    # unknown option: usage + non-zero exit like yu::cmdline (src/ext/yocto_utils.h:1157-1174)
+    assert subprocess.run([ours, "--bogus", "x.obj"], capture_output=True).returncode != 0

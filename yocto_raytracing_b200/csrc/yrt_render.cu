@@ -98,31 +98,33 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(SceneView sv, B
     }
 }
 
-// ---- any hit: shadow rays, one per (hit, light) ------------------------------------------------
+// ---- any hit: shadow rays ------------------------------------------------------------------------
+// One work item per hit; the lane walks the lights in order, so the 32 lanes of a warp (neighbouring
+// samples) trace towards the SAME light at the same time, and the hit record / position are read once
+// per hit instead of once per (hit, light).
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_any_lights(SceneView sv, size_t cap_slots, const int* __restrict__ act,
                                                                     const float4* __restrict__ hit, const float4* __restrict__ P,
-                                                                    uint8_t* __restrict__ vis, unsigned n_act, unsigned n_items,
-                                                                    unsigned* counter) {
+                                                                    uint8_t* __restrict__ vis, unsigned n_act, unsigned* counter) {
     const int lane = threadIdx.x & 31;
     int stack[YRT_STACK_CAP];
     for (;;) {
         unsigned base = warp_fetch(counter, lane);
-        if (base >= n_items) break;
-        unsigned t = base + lane;
-        if (t >= n_items) continue;
-        unsigned k = t / n_act;
-        unsigned a = t - k * n_act;
+        if (base >= n_act) break;
+        unsigned a = base + lane;
+        if (a >= n_act) continue;
         unsigned slot = act ? (unsigned)act[a] : a;
         float4 h = hit[slot];
-        if (float_as_int(h.x) < 0) continue;   // miss: shade() returns before the light loop
-        float4 Pq = P[slot];
-        vec3 p = xyz(Pq), l, ke;
-        float r;
-        light_vector(sv, (int)k, p, l, r, ke);
-        ray3 sr = shadow_ray(p, l, r);
-        HitRec hr;
-        bool occ = trace_ray<true>(sv, sr, hr, stack, nullptr);
-        vis[(size_t)k * cap_slots + slot] = occ ? 0 : 1;
+        if (float_as_int(h.x) < 0) continue;   // miss: shade() returns before the light loop (raytrace.cpp:93)
+        vec3 p = xyz(P[slot]);
+        for (int k = 0; k < sv.n_lights; k++) {
+            vec3 l, ke;
+            float r;
+            light_vector(sv, k, p, l, r, ke);
+            ray3 sr = shadow_ray(p, l, r);
+            HitRec hr;
+            bool occ = trace_ray<true>(sv, sr, hr, stack, nullptr);
+            vis[(size_t)k * cap_slots + slot] = occ ? 0 : 1;
+        }
     }
 }
 
@@ -396,13 +398,10 @@ static int run_batch(DevScene& ds, const RenderParams& rp, int lr0, int nrows, s
     for (int depth = 0;; depth++) {
         if (depth + 1 > max_depth_seen) max_depth_seen = depth + 1;
         if (nl > 0) {
-            unsigned long long items64 = (unsigned long long)n_act * (unsigned long long)nl;
-            if (items64 >= 0xfffffff0ull) { set_error("too many shadow rays in one batch (%llu): lower YRT_BATCH_SLOTS", items64); return YRT_ERR_UNSUPPORTED; }
-            unsigned items = (unsigned)items64;
             YRT_TRY(ring.get(&ctr));
             pt.begin(CAT_ANY);
-            k_trace_any_lights<<<grid_of(g_any, items), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
-                                                                               w.vis.as<uint8_t>(), n_act, items, ctr);
+            k_trace_any_lights<<<grid_of(g_any, n_act), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
+                                                                               w.vis.as<uint8_t>(), n_act, ctr);
             pt.end();
         }
         if (reflective) YRT_CUDA(cudaMemsetAsync(next_count, 0, sizeof(int), st));
@@ -445,8 +444,8 @@ static int batch_rows_for(const RenderParams& rp, int n_lights, int own_rows, bo
     // reflects — fewer launches and kernel tails; 4 M when the per-slot recursion stack must be allocated too
     long long target = env_int("YRT_BATCH_SLOTS", reflective ? (4 << 20) : (48 << 20));
     long long per_row = (long long)rp.width * rp.samples * rp.samples;
-    long long lim = 0xfffffff0ll / std::max(1, n_lights);
-    if (target > lim) target = lim;
+    if (target > 0x7fffff00ll) target = 0x7fffff00ll;
+    (void)n_lights;
     long long rows = std::max(1ll, target / per_row);
     return (int)std::min<long long>(rows, std::max(own_rows, 1));
 }
