@@ -215,13 +215,12 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput (`value`) ----
-    for _ in range(max(args.warmup, 3)):
-        frame()
-    barrier()
+    # the clock sampler starts BEFORE the warm-up so that no idle gap (clock ramp-down) precedes the timed region
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+    for _ in range(max(args.warmup, 3)):
+        frame()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stats_all = []
