@@ -50,6 +50,18 @@ class EmuScene:
         assert st == 0
         return ids, dist, uv, list(ctr)
 
+    def intersect(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        n = rays.shape[0]
+        ids = np.empty((n, 3), np.int32)
+        dist = np.empty(n, np.float32)
+        occ = np.empty(n, np.uint8)
+        fr = C.c_int64(0)
+        st = lib().emu_intersect(self.h, C.c_void_p(rays.ctypes.data), C.c_int64(n), C.c_void_p(ids.ctypes.data), C.c_void_p(dist.ctypes.data),
+                                 C.c_void_p(occ.ctypes.data), C.byref(fr))
+        assert st == 0
+        return ids, dist, occ, fr.value
+
     def render(self, width, height, samples, amb=0.1, max_depth=16):
         img = np.empty((height, width, 4), np.float32)
         cam = self.flat.camera_struct()

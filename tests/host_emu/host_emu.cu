@@ -227,6 +227,29 @@ int emu_trace_primary(void* p, const yrt_camera* cam, int width, int height, int
     return YRT_OK;
 }
 
+// generic rays (8 floats each: o, d, tmin, tmax): closest hit ids/dist + any-hit flags; false_rejects audits the slab test
+int emu_intersect(void* p, const float* rays, int64_t n, int32_t* ids, float* dist, uint8_t* occ, int64_t* false_rejects) {
+    EmuScene* es = (EmuScene*)p;
+    long long fr = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : fr)
+    for (int64_t r = 0; r < n; r++) {
+        int stack[YRT_STACK_CAP];
+        const float* q = rays + 8 * r;
+        ray3 ray;
+        ray.o = mk3(q[0], q[1], q[2]); ray.d = mk3(q[3], q[4], q[5]); ray.tmin = q[6]; ray.tmax = q[7];
+        HitRec h;
+        TraceCounters tc = {0, 0, 0, 0, 0, 0, 0};
+        trace_ray<false>(es->view, ray, h, stack, &tc);
+        hit_to_ids(es->view, h, ids + 3 * r);
+        dist[r] = h.dist;
+        HitRec h2;
+        occ[r] = trace_ray<true>(es->view, ray, h2, stack, &tc) ? 1 : 0;
+        fr += tc.slab_false_rejects;
+    }
+    if (false_rejects) *false_rejects = fr;
+    return YRT_OK;
+}
+
 // the whole frame with the device functions: raygen -> closest -> shadow (any) -> shade -> reflection
 // loop with the same explicit {c, kr, la} stack as k_shade -> ordered per-pixel sum.
 // ray_counts (optional, 8 int64): primary, reflection, shadow, then for the shadow rays: box tests, tlas box tests,

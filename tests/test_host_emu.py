@@ -41,3 +41,44 @@ def test_result_independent_of_tree_shape(leaf_blas, leaf_tlas):
     ids0, d0, _, _ = _emu.EmuScene(flat).trace_primary(96, 54, 1)
     ids1, d1, _, _ = _emu.EmuScene(flat, leaf_blas, leaf_tlas).trace_primary(96, 54, 1)
     assert np.array_equal(ids0, ids1) and np.array_equal(d0, d1)
+
+
+def test_axis_parallel_rays_slab_superset():
+    """Direction components that are exactly 0 (invd = +-inf): the slab test must still never cull a box the
+    reference would enter.  Uses a camera looking straight down the -z axis so that central rays are exact."""
+    from yocto_raytracing_b200 import synth
+    sc = synth.mixed_scene(7)
+    fr = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0.0, 1.0, 9.0], np.float32)      # identity rotation: d = (x, y, -focus)
+    sc.camera = np.concatenate([fr, np.array([0.6, 16 / 9, 0, 9.0], np.float32)])
+    flat = sc.flat()
+    from oracle import oracle
+    oracle.build()
+    # odd width/height with 1 sample put (u, v) = (0.5, 0.5) on a pixel centre: d = (0, 0, -1) exactly there,
+    # and whole rows / columns with one exactly-zero component
+    w, h = 97, 55
+    ids, dist, uv, ctr = _emu.EmuScene(flat).trace_primary(w, h, 1)
+    rids, rdist, _ = oracle.OracleScene(flat).trace_primary(w, h, 1)
+    assert ctr[4] == 0
+    assert id_match(ids, rids) >= 0.9995
+
+
+def test_generic_rays_incl_axis_aligned_vs_oracle(oracle_mod):
+    """Same rays as the GPU test: random rays plus exactly axis-aligned ones (invd = +-inf paths)."""
+    from yocto_raytracing_b200 import synth
+    flat = synth.mixed_scene(21).flat()
+    rng = np.random.RandomState(0)
+    n = 20000
+    o = rng.uniform(-6, 6, (n, 3)); o[:, 1] = rng.uniform(0.2, 6, n)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d, np.full((n, 1), 1e-4), rng.uniform(0.5, 30, (n, 1))], 1).astype(np.float32)
+    rays[:100, 3:6] = [0, -1, 0]
+    rays[100:200, 3:6] = [1, 0, 0]
+    rays[200:300, 3:6] = [0, 0, -1]
+    ids, dist, occ, false_rejects = _emu.EmuScene(flat).intersect(rays)
+    oc = oracle_mod.OracleScene(flat)
+    rids, rdist, _ = oc.intersect_first(rays)
+    rocc = oc.intersect_any(rays)
+    assert false_rejects == 0
+    assert id_match(ids, rids) >= 0.9999
+    assert id_match(ids[:300], rids[:300]) == 1.0
+    assert (occ == rocc).mean() >= 0.9999

@@ -273,6 +273,7 @@ void reference_visit_ranks(HostScene& hs) {
     hs.prim_rank.assign(std::max(hs.n_prims, 1), 0);
     hs.inst_rank.assign(std::max(hs.n_instances, 1), 0);
     std::vector<Box> shape_box(std::max(hs.n_shapes, 1), box_invalid());
+
     std::vector<RankItem> items;
     for (int s = 0; s < hs.n_shapes; s++) {
         int p0 = hs.shape_prim_off[s], p1 = hs.shape_prim_off[s + 1];

@@ -120,14 +120,15 @@ struct Tracer {
             const float4* n = sv.nodes + 4 * (size_t)cur;
             float4 q0 = ld4(n), q1 = ld4(n + 1), q2 = ld4(n + 2), q3 = ld4(n + 3);
             float e0, e1;
-            bool h0 = slab_test_fused(sr, tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, e0);
-            bool h1 = slab_test_fused(sr, tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, e1);
+            bool h0 = slab_test_ch(sr, tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.w, e0);
+            bool h1 = slab_test_ch(sr, tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, q3.w, e1);
             if (ctr) {   // host-side audit against the reference's own test
                 ctr->box_tests += 2;
                 if (top) ctr->tlas_box_tests += 2;
                 float e;
-                bool r0 = intersect_check_bbox(o, sr.invd, sr.sg, tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, e);
-                bool r1 = intersect_check_bbox(o, sr.invd, sr.sg, tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, e);
+                raysigns sgn = signs_of(sr.invd);   // the reference's test on the stored box [c-h, c+h] (a superset of the true box)
+                bool r0 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, q0.x - q1.x, q0.y - q1.y, q0.z - q1.z, q0.x + q1.x, q0.y + q1.y, q0.z + q1.z, e);
+                bool r1 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, q2.x - q3.x, q2.y - q3.y, q2.z - q3.z, q2.x + q3.x, q2.y + q3.y, q2.z + q3.z, e);
                 ctr->slab_false_rejects += (r0 && !h0) + (r1 && !h1);
                 ctr->slab_extra_accepts += (!r0 && h0) + (!r1 && h1);
             }
