@@ -11,7 +11,7 @@ CXX      ?= g++
 ORACLE_CC ?= $(shell command -v /usr/bin/gcc || echo gcc)
 ARCH     := -gencode arch=compute_100a,code=sm_100a
 # -fmad=false: the parity-critical arithmetic must not be contracted into FMA (SURVEY finding 4)
-NVFLAGS  := $(ARCH) -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC
+NVFLAGS  := $(ARCH) -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC $(EXTRA)
 CSRC     := yocto_raytracing_b200/csrc
 HOST     := yocto_raytracing_b200/host
 LIB      := yocto_raytracing_b200/libyrt_b200.so

@@ -24,6 +24,9 @@
 namespace yrt {
 
 #define TRACE_THREADS 128
+#ifndef TRACE_MIN_BLOCKS
+#define TRACE_MIN_BLOCKS 8   /* resident CTAs per SM the compiler must allow (64 registers per thread) */
+#endif
 
 struct BatchParams {
     camera_k cam;
@@ -60,7 +63,7 @@ __device__ __forceinline__ unsigned warp_fetch(unsigned* counter, int lane) {
 // PRIMARY: slot = work index, ray from the camera. Otherwise slot = act[idx] (or idx) and the ray
 // comes from ray_o/ray_d (o.xyz|tmin, d.xyz|tmax).
 template <bool PRIMARY>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(SceneView sv, BatchParams bp, const int* __restrict__ act,
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_closest(SceneView sv, BatchParams bp, const int* __restrict__ act,
                                                                  const float4* __restrict__ ray_o,
                                                                  const float4* __restrict__ ray_d, float4* __restrict__ hit_out,
                                                                  float4* __restrict__ P_out, unsigned n, unsigned* counter) {
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest(SceneView sv, B
 // One work item per hit; the lane walks the lights in order, so the 32 lanes of a warp (neighbouring
 // samples) trace towards the SAME light at the same time, and the hit record / position are read once
 // per hit instead of once per (hit, light).
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_any_lights(SceneView sv, size_t cap_slots, const int* __restrict__ act,
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_any_lights(SceneView sv, size_t cap_slots, const int* __restrict__ act,
                                                                     const float4* __restrict__ hit, const float4* __restrict__ P,
                                                                     uint8_t* __restrict__ vis, unsigned n_act, unsigned* counter) {
     const int lane = threadIdx.x & 31;

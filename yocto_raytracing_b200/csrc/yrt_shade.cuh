@@ -183,16 +183,21 @@ YRT_HD void shade_lights(const SceneView& sv, const HitAttr& a, const Material& 
         if (m.ks_tex >= 0) ks = ks * tks;
         vec3 ld = kd * (ke / (r * r));                       // raytrace.cpp:159-160
         vec3 ls = ks * (ke / (r * r));
+        // ks == (0,0,0) exactly (most materials of the instance scenes): ls = +0 * finite = +0 whatever the lobe
+        // is — the lobe base is in [0, 1+ulp] or NaN-free by construction only when it is finite, so the powf is
+        // skipped only if the base is finite and non-negative (then powf(base, ns > 0) is finite and ld + 0 == ld)
+        const bool no_spec = ks.x == 0.0f && ks.y == 0.0f && ks.z == 0.0f && m.ns > 0.0f && m.ns <= 1e6f;
         if (a.kind == 1) {                                   // shp->lines.size() > 0, raytrace.cpp:162-175
             float prodnl = dot(a.n, l), prodnh = dot(a.n, h);
             if (prodnl < 0.0f) prodnl = -prodnl;
             if (prodnh < 0.0f) prodnh = -prodnh;
             float sinnl = sqrtf(1.0f - prodnl), sinnh = sqrtf(1.0f - prodnh);
             ld = ld * sinnl;
-            ls = ls * powf(sinnh, m.ns);
+            if (!(no_spec && sinnh >= 0.0f && sinnh <= 1.0000005f)) ls = ls * powf(sinnh, m.ns);   // (1+5e-7)^1e6 < 2: finite
         } else {                                             // raytrace.cpp:176-180
             ld = ld * rmax(0.0f, dot(a.n, l));
-            ls = ls * powf(rmax(0.0f, dot(a.n, h)), m.ns);
+            float base = rmax(0.0f, dot(a.n, h));
+            if (!(no_spec && base >= 0.0f && base <= 1.0000005f)) ls = ls * powf(base, m.ns);
         }
         c = c + (ld + ls);                                   // raytrace.cpp:182
     }
