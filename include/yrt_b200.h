@@ -113,6 +113,8 @@ typedef struct yrt_stats {
     int32_t max_depth;        /* deepest reflection recursion reached                           */
     int32_t n_gpus;
     int32_t n_closest, n_any, n_shade, n_other;   /* launches per category (device 0)          */
+    int32_t frames;           /* frames the totals cover (1, or all frames between yrt_stats_begin/end) */
+    int32_t reserved;
 } yrt_stats;
 
 typedef struct yrt_scene yrt_scene;   /* opaque: device-resident scene + LBVH on every initialised GPU */
@@ -154,12 +156,18 @@ int yrt_render(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int wi
  * owned by `rank` of `world` (row tile t of `tile_rows` rows belongs to rank t % world)
  * into d_rgba (DEVICE pointer on the current yrt device) holding the rank's rows packed in
  * increasing row order: yrt_rows_owned(height,tile_rows,rank,world)*width*4 floats.
- * stream: cudaStream_t as void* (NULL = default stream).  Asynchronous w.r.t. the host
- * unless stats != NULL. */
+ * stream: cudaStream_t as void*; NULL = the legacy default stream (what PyTorch's default stream is), so the
+ * frame is ordered with the caller's other work on that stream.  Asynchronous w.r.t. the host unless
+ * stats != NULL (and no deferred statistics are open). */
 int yrt_render_rows(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height,
                     int samples, int tile_rows, int rank, int world, void* d_rgba, void* stream,
                     yrt_stats* stats);
 int yrt_rows_owned(int height, int tile_rows, int rank, int world);
+/* deferred statistics for yrt_render_rows: frames rendered between begin and end record per-launch CUDA events
+ * and ray counters WITHOUT any host synchronisation; yrt_stats_end waits for the device and returns the totals
+ * over those frames (stats->frames says how many). */
+int yrt_stats_begin(yrt_scene* scn);
+int yrt_stats_end(yrt_scene* scn, yrt_stats* totals);
 /* scatter a rank's packed rows into the full row-major framebuffer (both DEVICE pointers) */
 int yrt_unpack_rows(const void* d_packed, void* d_full, int width, int height, int tile_rows,
                     int rank, int world, void* stream);

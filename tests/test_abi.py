@@ -30,7 +30,7 @@ def test_header_symbols_all_exported_and_bound():
 def test_struct_layouts_match_header():
     # sizes implied by the header on LP64
     assert C.sizeof(_lib.Camera) == 16 * 4
-    assert C.sizeof(_lib.Stats) == 4 * 8 + 6 * 4 + 6 * 4
+    assert C.sizeof(_lib.Stats) == 4 * 8 + 6 * 4 + 8 * 4
     assert C.sizeof(_lib.SceneDesc) == 6 * 4 + 26 * 8 + 8
 
 

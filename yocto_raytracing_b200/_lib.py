@@ -51,6 +51,7 @@ class Stats(C.Structure):
         ("ms_total", C.c_float), ("ms_trace_closest", C.c_float), ("ms_trace_any", C.c_float), ("ms_shade", C.c_float),
         ("ms_other", C.c_float), ("ms_gather", C.c_float), ("max_depth", C.c_int32), ("n_gpus", C.c_int32),
         ("n_closest", C.c_int32), ("n_any", C.c_int32), ("n_shade", C.c_int32), ("n_other", C.c_int32),
+        ("frames", C.c_int32), ("reserved", C.c_int32),
     ]
 
     def as_dict(self):
@@ -77,6 +78,8 @@ SYMBOLS = {
     "yrt_render_rows": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
     "yrt_rows_owned": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "yrt_stats_begin": (C.c_int, [C.c_void_p]),
+    "yrt_stats_end": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "yrt_unpack_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "yrt_trace_primary": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),

@@ -133,7 +133,7 @@ static int fill_params(const yrt_camera* cam, const float amb[3], int width, int
     rp.cam = make_camera_k(cam);
     rp.amb = amb ? mk3(amb[0], amb[1], amb[2]) : mk3(0.f, 0.f, 0.f);
     rp.width = width; rp.height = height; rp.samples = samples;
-    rp.tile_rows = 16; rp.rank = 0; rp.world = 1;
+    rp.tile_rows = 1; rp.rank = 0; rp.world = 1;
     return YRT_OK;
 }
 
@@ -144,8 +144,18 @@ int yrt_render_rows(yrt_scene* scn, const yrt_camera* cam, const float amb[3], i
     YRT_TRY(fill_params(cam, amb, width, height, samples, rp));
     rp.tile_rows = tile_rows; rp.rank = rank; rp.world = world;
     DevScene& ds = *scn->dev[0];
-    cudaStream_t st = stream ? (cudaStream_t)stream : ds.stream;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = legacy default stream
     return render_rows_device(ds, rp, (float4*)d_rgba, st, stats, true);
+}
+
+int yrt_stats_begin(yrt_scene* scn) {
+    if (!scn || scn->dev.empty()) { set_error("yrt_stats_begin: bad arguments"); return YRT_ERR_INVALID; }
+    return stats_begin_device(*scn->dev[0]);
+}
+
+int yrt_stats_end(yrt_scene* scn, yrt_stats* totals) {
+    if (!scn || scn->dev.empty() || !totals) { set_error("yrt_stats_end: bad arguments"); return YRT_ERR_INVALID; }
+    return stats_end_device(*scn->dev[0], totals);
 }
 
 int yrt_unpack_rows(const void* d_packed, void* d_full, int width, int height, int tile_rows, int rank, int world, void* stream) {
@@ -163,7 +173,7 @@ int yrt_render(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int wi
     YRT_TRY(fill_params(cam, amb, width, height, samples, rp0));
     const int G = (int)scn->dev.size();
     const char* etr = getenv("YRT_TILE_ROWS");
-    int tile_rows = etr ? std::max(1, atoi(etr)) : 16;
+    int tile_rows = etr ? std::max(1, atoi(etr)) : 1;   // 1-row tiles: rows r, r+G, r+2G, ... balance best (cost varies smoothly down the image)
     if (G == 1) tile_rows = std::max(1, height);
     if (!g_gather) g_gather = new GatherState();
     GatherState& gs = *g_gather;

@@ -131,6 +131,8 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
                        bool sync_for_stats);
 // waits for the frame issued by render_rows_device(…, stats != null, sync_for_stats = false) and fills stats
 int collect_stats_device(DevScene& ds, const RenderParams& rp, yrt_stats* stats);
+int stats_begin_device(DevScene& ds);
+int stats_end_device(DevScene& ds, yrt_stats* stats);
 int trace_primary_device(DevScene& ds, const RenderParams& rp, int32_t* h_ids, float* h_dist, float* h_uv);
 int intersect_rays_device(DevScene& ds, const float* h_rays, int64_t n, bool any, int32_t* h_ids, float* h_dist,
                           float* h_uv, uint8_t* h_occ);

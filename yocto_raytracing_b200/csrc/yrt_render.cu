@@ -303,8 +303,10 @@ struct PhaseTimer {
     std::vector<Span> spans;
     std::vector<cudaEvent_t> pool;
     bool on = false;
+    bool deferred = false;        // between yrt_stats_begin and yrt_stats_end: record, never synchronise
+    int frames = 0;               // frames recorded since the last collect
+    int64_t primary = 0;          // primary rays of those frames
     cudaStream_t st = nullptr;
-    cudaEvent_t f0 = nullptr, f1 = nullptr;   // frame begin / end
     int max_depth_seen = 0;
     cudaEvent_t get() {
         if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
@@ -314,13 +316,19 @@ struct PhaseTimer {
     void end() { if (!on) return; cudaEventRecord(spans.back().b, st); }
     void collect(float out[5], int cnt[5], int64_t& launches) {
         for (int i = 0; i < 5; i++) { out[i] = 0.f; cnt[i] = 0; }
-        for (auto& s : spans) { float ms = 0.f; cudaEventElapsedTime(&ms, s.a, s.b); out[s.cat] += ms; cnt[s.cat]++; pool.push_back(s.a); pool.push_back(s.b); }
-        launches = (int64_t)spans.size();
+        launches = 0;
+        for (auto& s : spans) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, s.a, s.b);
+            out[s.cat] += ms; cnt[s.cat]++;
+            if (s.cat != 4) launches++;     // CAT_FRAME spans bracket a whole frame, they are not launches
+            pool.push_back(s.a); pool.push_back(s.b);
+        }
         spans.clear();
     }
     ~PhaseTimer() { for (auto e : pool) cudaEventDestroy(e); for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); } }
 };
-enum { CAT_CLOSEST = 0, CAT_ANY = 1, CAT_SHADE = 2, CAT_OTHER = 3 };
+enum { CAT_CLOSEST = 0, CAT_ANY = 1, CAT_SHADE = 2, CAT_OTHER = 3, CAT_FRAME = 4 };
 
 static int ensure_workspace(DevScene& ds, size_t slots, int n_lights, int depth_cap, bool reflective) {
     Workspace& w = ds.ws;
@@ -343,7 +351,7 @@ static int ensure_workspace(DevScene& ds, size_t slots, int n_lights, int depth_
         w.cap_slots = cs; w.cap_lights = cl; w.cap_depth = cd;
     }
     YRT_TRY(w.counters.alloc(sizeof(unsigned) * 8192, dev));
-    YRT_TRY(w.stats.alloc(sizeof(FrameCounters) + 64, dev));
+    YRT_TRY(w.stats.alloc(sizeof(FrameCounters) + 64, dev));   // counters + the next-wave count
     return YRT_OK;
 }
 
@@ -468,48 +476,52 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
 
     if (!ds.timer) ds.timer = new PhaseTimer();
     PhaseTimer& pt = *ds.timer;
-    pt.on = stats != nullptr;
+    pt.on = stats != nullptr || pt.deferred;
     pt.st = st;
-    if (stats) {
-        if (!pt.f0) { pt.f0 = pt.get(); pt.f1 = pt.get(); }
-        cudaEventRecord(pt.f0, st);
+    if (!pt.deferred) {   // a stand-alone frame starts from clean counters; deferred frames accumulate
+        for (auto& sp : pt.spans) { pt.pool.push_back(sp.a); pt.pool.push_back(sp.b); }
+        pt.spans.clear();
+        pt.frames = 0; pt.primary = 0;
+        YRT_CUDA(cudaMemsetAsync(ds.ws.stats.p, 0, sizeof(FrameCounters), st));
     }
+    pt.begin(CAT_FRAME);
+    const size_t frame_span = pt.spans.size();
     CounterRing ring;
     YRT_TRY(ring.init(ds, st));
-    YRT_CUDA(cudaMemsetAsync(ds.ws.stats.p, 0, sizeof(FrameCounters) + 64, st));
     int max_depth_seen = 0;
     for (int lr0 = 0; lr0 < own; lr0 += batch_rows) {
         int nrows = std::min(batch_rows, own - lr0);
         YRT_TRY(run_batch(ds, rp, lr0, nrows, cap_slots, d_out, st, pt, ring, depth_cap, reflective, false, max_depth_seen));
     }
-    pt.max_depth_seen = max_depth_seen;
-    if (stats) {
-        cudaEventRecord(pt.f1, st);
-        if (sync_for_stats) YRT_TRY(collect_stats_device(ds, rp, stats));
+    pt.max_depth_seen = pt.deferred ? std::max(pt.max_depth_seen, max_depth_seen) : max_depth_seen;
+    if (pt.on) {
+        cudaEventRecord(pt.spans[frame_span - 1].b, st);
+        pt.frames++;
+        pt.primary += (int64_t)own * rp.width * spp;
     }
+    if (stats && sync_for_stats && !pt.deferred) YRT_TRY(collect_stats_device(ds, rp, stats));
     return YRT_OK;
 }
 
 int collect_stats_device(DevScene& ds, const RenderParams& rp, yrt_stats* stats) {
-    if (!ds.timer || !ds.timer->f0) { set_error("collect_stats_device: no frame was rendered with stats"); return YRT_ERR_INVALID; }
+    (void)rp;
+    if (!ds.timer) { set_error("collect_stats_device: no frame was rendered with stats"); return YRT_ERR_INVALID; }
     PhaseTimer& pt = *ds.timer;
     YRT_CUDA(cudaSetDevice(ds.device));
     YRT_CUDA(cudaStreamSynchronize(pt.st));
     FrameCounters fc;
-    YRT_CUDA(cudaMemcpy(&fc, ds.ws.stats.p, sizeof(fc), cudaMemcpyDeviceToHost));
+    YRT_CUDA(cudaMemcpyAsync(&fc, ds.ws.stats.p, sizeof(fc), cudaMemcpyDeviceToHost, pt.st));
+    YRT_CUDA(cudaStreamSynchronize(pt.st));
     float cat[5];
     int cnt[5];
     int64_t launches = 0;
     pt.collect(cat, cnt, launches);
     memset(stats, 0, sizeof(*stats));
-    int own = rows_owned(rp.height, rp.tile_rows, rp.rank, rp.world);
-    stats->primary_rays = (int64_t)own * rp.width * rp.samples * rp.samples;
+    stats->primary_rays = pt.primary;
     stats->reflection_rays = (int64_t)fc.reflections;
     stats->shadow_rays = (int64_t)fc.hits * ds.view.n_lights;
     stats->launches = launches;
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, pt.f0, pt.f1);
-    stats->ms_total = ms;
+    stats->ms_total = cat[CAT_FRAME];
     stats->ms_trace_closest = cat[CAT_CLOSEST];
     stats->ms_trace_any = cat[CAT_ANY];
     stats->ms_shade = cat[CAT_SHADE];
@@ -517,7 +529,32 @@ int collect_stats_device(DevScene& ds, const RenderParams& rp, yrt_stats* stats)
     stats->max_depth = pt.max_depth_seen;
     stats->n_gpus = 1;
     stats->n_closest = cnt[CAT_CLOSEST]; stats->n_any = cnt[CAT_ANY]; stats->n_shade = cnt[CAT_SHADE]; stats->n_other = cnt[CAT_OTHER];
+    stats->frames = pt.frames;
+    pt.frames = 0; pt.primary = 0;
     return YRT_OK;
+}
+
+int stats_begin_device(DevScene& ds) {
+    if (!ds.timer) ds.timer = new PhaseTimer();
+    PhaseTimer& pt = *ds.timer;
+    YRT_CUDA(cudaSetDevice(ds.device));
+    YRT_TRY(ds.ws.stats.alloc(sizeof(FrameCounters) + 64, ds.device));
+    if (pt.st || ds.stream) YRT_CUDA(cudaStreamSynchronize(pt.st ? pt.st : ds.stream));
+    YRT_CUDA(cudaMemset(ds.ws.stats.p, 0, sizeof(FrameCounters)));
+    for (auto& sp : pt.spans) { pt.pool.push_back(sp.a); pt.pool.push_back(sp.b); }
+    pt.spans.clear();
+    pt.frames = 0; pt.primary = 0; pt.max_depth_seen = 0;
+    pt.deferred = true;
+    return YRT_OK;
+}
+
+int stats_end_device(DevScene& ds, yrt_stats* stats) {
+    if (!ds.timer || !ds.timer->deferred) { set_error("yrt_stats_end without yrt_stats_begin"); return YRT_ERR_INVALID; }
+    RenderParams dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    ds.timer->deferred = false;
+    if (!ds.timer->st) ds.timer->st = ds.stream;
+    return collect_stats_device(ds, dummy, stats);
 }
 
 int trace_primary_device(DevScene& ds, const RenderParams& rp_in, int32_t* h_ids, float* h_dist, float* h_uv) {

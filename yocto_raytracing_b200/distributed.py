@@ -75,7 +75,7 @@ def _unpack(packed: torch.Tensor, full: torch.Tensor, width, height, tile_rows, 
         full[idx] = packed
 
 
-def render_sharded(scene, width: int, height: int, samples: int, amb=0.1, tile_rows: int = 16, group=None, want_stats=False):
+def render_sharded(scene, width: int, height: int, samples: int, amb=0.1, tile_rows: int = 1, group=None, want_stats=False):
     """Render this rank's tiles with `scene` (a render.Scene bound to this process's GPU) and gather on rank 0.
     Returns (framebuffer on rank 0 | None, Stats | None)."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0

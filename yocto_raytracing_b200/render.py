@@ -104,6 +104,16 @@ class Scene:
                                           C.byref(st) if st is not None else None))
         return st
 
+    def stats_begin(self) -> None:
+        """Open deferred statistics: following render_rows_into frames record events/counters without host syncs."""
+        check(_lib.load().yrt_stats_begin(self._h))
+
+    def stats_end(self) -> Stats:
+        """Wait for the device and return the totals over the frames since stats_begin (Stats.frames of them)."""
+        st = Stats()
+        check(_lib.load().yrt_stats_end(self._h, C.byref(st)))
+        return st
+
     # ---- queries ------------------------------------------------------------------------------
     def trace_primary(self, width: int, height: int, samples: int):
         """(ids[n,3] = (instance, shape, element) or -1, dist[n], uv[n,2]) per primary ray, ray order
