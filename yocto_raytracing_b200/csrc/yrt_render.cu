@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_any_rays(SceneView sv, 
 // ---- shade ------------------------------------------------------------------------------------
 struct FrameCounters { unsigned long long hits, reflections, misses, pad; };
 
-__global__ void __launch_bounds__(256) k_shade(SceneView sv, BatchParams bp, int depth, int max_depth, const int* __restrict__ act,
+__global__ void __launch_bounds__(256, 4) k_shade(SceneView sv, BatchParams bp, int depth, int max_depth, const int* __restrict__ act,
                                                unsigned n_act, const float4* __restrict__ hit, const float4* __restrict__ P,
                                                const uint8_t* __restrict__ vis, float4* __restrict__ ray_o, float4* __restrict__ ray_d,
                                                float4* __restrict__ pstack, float4* __restrict__ rad, int* __restrict__ next_act,
