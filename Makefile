@@ -38,7 +38,7 @@ oracle/liboracle.so: oracle/yrt_oracle.c oracle/yrt_oracle.h include/yrt_b200.h
 
 hostemu: tests/host_emu/libyrt_hostemu.so
 tests/host_emu/libyrt_hostemu.so: tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu $(HDRS)
-	$(NVCC) -O2 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-ffp-contract=off,-fopenmp -shared -I$(CSRC) -o $@ tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu -lgomp
+	$(NVCC) -O2 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-ffp-contract=off,-fopenmp -shared $(EXTRA) -I$(CSRC) -o $@ tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu -lgomp
 
 ref: oracle/_ref/raytrace_ref oracle/_ref/ref_probe bin/raytrace bin/yrt_flatten
 oracle/_ref/%.o: $(REF)/src/%.cpp

@@ -14,6 +14,13 @@
 #pragma once
 #include "yrt_scene.cuh"
 
+#ifndef YRT_SPECULATE
+#define YRT_SPECULATE 0      /* measured: slower (profiles/r1_experiments.md) */
+#endif
+#ifndef YRT_ANY_UNORDERED
+#define YRT_ANY_UNORDERED 1  /* any-hit rays: skip the near/far ordering of the two children (the answer is order independent; -6 % kernel time) */
+#endif
+
 namespace yrt {
 
 
@@ -87,11 +94,12 @@ struct Tracer {
     slabray sr;
     float tmin, tmax;     // tmin is copied unchanged into every instance space (vmath.h:277)
     int cur, sp, si, kind;
+    int post;             // postponed leaf (speculative look-ahead), YRT_REF_NONE if none
     bool top, found;
     HitRec hit;
 
-    YRT_HD void idle() { cur = YRT_REF_DONE; sp = 0; found = false; }
-    YRT_HD bool done() const { return cur == YRT_REF_DONE; }
+    YRT_HD void idle() { cur = YRT_REF_DONE; post = YRT_REF_NONE; sp = 0; found = false; }
+    YRT_HD bool done() const { return cur == YRT_REF_DONE && post == YRT_REF_NONE; }
 
     YRT_HD void begin(const SceneView& sv, const ray3& wray) {
         hit.si = -1; hit.prim = -1; hit.w1 = hit.w2 = 0.f; hit.dist = 0.f;
@@ -99,57 +107,83 @@ struct Tracer {
         wsr = make_slabray(wo, inv3(wd));
         o = wo; d = wd; sr = wsr;
         tmin = wray.tmin; tmax = wray.tmax;
-        sp = 0; si = -1; kind = 0; top = true; found = false;
+        sp = 0; si = -1; kind = 0; top = true; found = false; post = YRT_REF_NONE;
         cur = sv.n_active_instances > 0 ? sv.tlas_root : YRT_REF_DONE;
     }
 
-    // pop the next reference; leaving an instance (sentinel) restores the world-space ray
+    // pop the next reference; leaving an instance (sentinel) restores the world-space ray — unless a leaf of
+    // this instance is still postponed: then the sentinel stays and the lane holds nothing (YRT_REF_NONE)
     YRT_HD void pop(const int* stack) {
         for (;;) {
             if (sp == 0) { cur = YRT_REF_DONE; break; }
-            cur = stack[--sp];
-            if (cur != YRT_REF_SENTINEL) break;
+            cur = stack[sp - 1];
+            if (cur != YRT_REF_SENTINEL) { --sp; break; }
+            if (post != YRT_REF_NONE) { cur = YRT_REF_NONE; break; }
+            --sp;
             top = true;
             o = wo; d = wd; sr = wsr;
         }
     }
 
-    // internal nodes: test both child boxes against the current ray and current tmax, near child first
-    YRT_HD void nodes(const SceneView& sv, int* stack, TraceCounters* ctr) {
-        while (cur >= 0) {
-            const float4* n = sv.nodes + 4 * (size_t)cur;
-            float4 q0 = ld4(n), q1 = ld4(n + 1), q2 = ld4(n + 2), q3 = ld4(n + 3);
-            float e0, e1;
-            bool h0 = slab_test_ch(sr, tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.w, e0);
-            bool h1 = slab_test_ch(sr, tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, q3.w, e1);
-            if (ctr) {   // host-side audit against the reference's own test
-                ctr->box_tests += 2;
-                if (top) ctr->tlas_box_tests += 2;
-                float e;
-                raysigns sgn = signs_of(sr.invd);   // the reference's test on the stored box [c-h, c+h] (a superset of the true box)
-                bool r0 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, q0.x - q1.x, q0.y - q1.y, q0.z - q1.z, q0.x + q1.x, q0.y + q1.y, q0.z + q1.z, e);
-                bool r1 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, q2.x - q3.x, q2.y - q3.y, q2.z - q3.z, q2.x + q3.x, q2.y + q3.y, q2.z + q3.z, e);
-                ctr->slab_false_rejects += (r0 && !h0) + (r1 && !h1);
-                ctr->slab_extra_accepts += (!r0 && h0) + (!r1 && h1);
-            }
-            int c0 = float_as_int(q0.w), c1 = float_as_int(q1.w);
-            if (h0 && h1) {
-                bool swap = e1 < e0;
-                stack[sp++] = swap ? c0 : c1;
-                if (ctr && sp > ctr->max_stack) ctr->max_stack = sp;
-                cur = swap ? c1 : c0;
-            } else if (h0) {
-                cur = c0;
-            } else if (h1) {
-                cur = c1;
-            } else {
-                pop(stack);
-            }
+    // one internal node: test both child boxes against the current ray and current tmax, near child first
+    YRT_HD void visit(const SceneView& sv, int* stack, TraceCounters* ctr) {
+        const float4* n = sv.nodes + 4 * (size_t)cur;
+        float4 q0 = ld4(n), q1 = ld4(n + 1), q2 = ld4(n + 2), q3 = ld4(n + 3);
+        float e0, e1;
+        bool h0 = slab_test_ch(sr, tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.w, e0);
+        bool h1 = slab_test_ch(sr, tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, q3.w, e1);
+        if (ctr) {   // host-side audit against the reference's own test
+            ctr->box_tests += 2;
+            if (top) ctr->tlas_box_tests += 2;
+            float e;
+            raysigns sgn = signs_of(sr.invd);   // the reference's test on the stored box [c-h, c+h] (a superset of the true box)
+            bool r0 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, q0.x - q1.x, q0.y - q1.y, q0.z - q1.z, q0.x + q1.x, q0.y + q1.y, q0.z + q1.z, e);
+            bool r1 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, q2.x - q3.x, q2.y - q3.y, q2.z - q3.z, q2.x + q3.x, q2.y + q3.y, q2.z + q3.z, e);
+            ctr->slab_false_rejects += (r0 && !h0) + (r1 && !h1);
+            ctr->slab_extra_accepts += (!r0 && h0) + (!r1 && h1);
+        }
+        int c0 = float_as_int(q0.w), c1 = float_as_int(q1.w);
+        if (h0 && h1) {
+            bool swap = (ANY && YRT_ANY_UNORDERED) ? false : (e1 < e0);   // near child first
+            stack[sp++] = swap ? c0 : c1;
+            if (ctr && sp > ctr->max_stack) ctr->max_stack = sp;
+            cur = swap ? c1 : c0;
+        } else if (h0) {
+            cur = c0;
+        } else if (h1) {
+            cur = c1;
+        } else {
+            pop(stack);
         }
     }
 
-    // one leaf (cur < 0 and not done)
+    // internal nodes until the lane holds a leaf.  With YRT_SPECULATE the first leaf found is postponed and the
+    // lane keeps walking nodes of the same space (the rest of the warp is still in this loop anyway) until it
+    // holds a second leaf; leaf() then handles the postponed one first.
+    YRT_HD void nodes(const SceneView& sv, int* stack, TraceCounters* ctr) {
+#if YRT_SPECULATE
+        for (;;) {
+            while (cur >= 0) visit(sv, stack, ctr);
+            if (cur == YRT_REF_DONE || cur == YRT_REF_NONE || post != YRT_REF_NONE) break;
+            if (sp == 0 || stack[sp - 1] == YRT_REF_SENTINEL) break;   // nothing to look ahead at in this space
+            post = cur;
+            cur = stack[--sp];
+            if (cur < 0) break;   // the next entry is a leaf too
+        }
+#else
+        while (cur >= 0) visit(sv, stack, ctr);
+#endif
+    }
+
+    // one leaf (cur < 0 and not done); a postponed leaf goes first and what is in hand returns to the stack
     YRT_HD void leaf(const SceneView& sv, int* stack, TraceCounters* ctr) {
+#if YRT_SPECULATE
+        if (post != YRT_REF_NONE) {
+            if (cur != YRT_REF_DONE && cur != YRT_REF_NONE) stack[sp++] = cur;
+            cur = post;
+            post = YRT_REF_NONE;
+        }
+#endif
         int first = leaf_first(cur), count = leaf_count(cur);
         if (top) {
             // TLAS leaf: enter its first instance, keep the rest for later
