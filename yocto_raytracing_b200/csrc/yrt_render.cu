@@ -20,6 +20,7 @@
 #include "yrt_internal.h"
 #include "yrt_shade.cuh"
 #include "yrt_trace.cuh"
+#include "yrt_packet.cuh"
 
 namespace yrt {
 
@@ -62,42 +63,55 @@ __device__ __forceinline__ unsigned warp_fetch(unsigned* counter, int lane) {
 // ---- closest hit --------------------------------------------------------------------------
 // PRIMARY: slot = work index, ray from the camera. Otherwise slot = act[idx] (or idx) and the ray
 // comes from ray_o/ray_d (o.xyz|tmin, d.xyz|tmax).
-template <bool PRIMARY>
+// PACKET: the warp's 32 rays walk one tree path (yrt_packet.cuh) — used for the camera rays and their shadow
+// rays, which are neighbouring samples; reflection waves and the generic query entry points trace per lane.
+template <bool PRIMARY, bool PACKET>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_closest(SceneView sv, BatchParams bp, const int* __restrict__ act,
                                                                  const float4* __restrict__ ray_o,
                                                                  const float4* __restrict__ ray_d, float4* __restrict__ hit_out,
                                                                  float4* __restrict__ P_out, unsigned n, unsigned* counter) {
     const int lane = threadIdx.x & 31;
-    int stack[YRT_STACK_CAP];
+    __shared__ int wstacks[PACKET ? TRACE_THREADS / 32 : 1][PACKET ? YRT_WSTACK : 1];
+    int stack[PACKET ? 1 : YRT_STACK_CAP];
     for (;;) {
         unsigned base = warp_fetch(counter, lane);
         if (base >= n) break;
         unsigned idx = base + lane;
-        if (idx >= n) continue;
-        unsigned slot;
+        const bool alive = idx < n;
+        unsigned slot = 0;
         ray3 ray;
-        if (PRIMARY) {
-            slot = idx;
-            int i, j, ii, jj;
-            slot_to_sample(bp, slot, i, j, ii, jj);
-            float u, v;
-            sample_uv(i, j, ii, jj, bp.samples, bp.width, bp.height, u, v);
-            ray = eval_camera(bp.cam, u, v);
-        } else {
-            slot = act ? (unsigned)act[idx] : idx;
-            float4 o = ray_o[slot], d = ray_d[slot];
-            ray.o = xyz(o); ray.d = xyz(d); ray.tmin = o.w; ray.tmax = d.w;
+        ray.o = mk3(0.f, 0.f, 0.f); ray.d = mk3(0.f, 0.f, 1.f); ray.tmin = 0.f; ray.tmax = 0.f;
+        if (alive) {
+            if (PRIMARY) {
+                slot = idx;
+                int i, j, ii, jj;
+                slot_to_sample(bp, slot, i, j, ii, jj);
+                float u, v;
+                sample_uv(i, j, ii, jj, bp.samples, bp.width, bp.height, u, v);
+                ray = eval_camera(bp.cam, u, v);
+            } else {
+                slot = act ? (unsigned)act[idx] : idx;
+                float4 o = ray_o[slot], d = ray_d[slot];
+                ray.o = xyz(o); ray.d = xyz(d); ray.tmin = o.w; ray.tmax = d.w;
+            }
         }
         HitRec h;
-        trace_ray<false>(sv, ray, h, stack, nullptr);
-        float4 P = mk4(0.f, 0.f, 0.f, h.dist);
-        if (h.si >= 0) {
-            int kind;
-            vec3 p = eval_hit_pos(sv, h.si, h.prim, h.w1, h.w2, kind);
-            P.x = p.x; P.y = p.y; P.z = p.z;
+        if (PACKET) {
+            bool found;
+            trace_packet<false>(sv, ray, alive, h, found, wstacks[threadIdx.x >> 5], lane);
+        } else if (alive) {
+            trace_ray<false>(sv, ray, h, stack, nullptr);
         }
-        hit_out[slot] = mk4(int_as_float(h.si), int_as_float(h.prim), h.w1, h.w2);
-        P_out[slot] = P;
+        if (alive) {
+            float4 P = mk4(0.f, 0.f, 0.f, h.dist);
+            if (h.si >= 0) {
+                int kind;
+                vec3 p = eval_hit_pos(sv, h.si, h.prim, h.w1, h.w2, kind);
+                P.x = p.x; P.y = p.y; P.z = p.z;
+            }
+            hit_out[slot] = mk4(int_as_float(h.si), int_as_float(h.prim), h.w1, h.w2);
+            P_out[slot] = P;
+        }
     }
 }
 
@@ -105,28 +119,38 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_close
 // One work item per hit; the lane walks the lights in order, so the 32 lanes of a warp (neighbouring
 // samples) trace towards the SAME light at the same time, and the hit record / position are read once
 // per hit instead of once per (hit, light).
+template <bool PACKET>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_any_lights(SceneView sv, size_t cap_slots, const int* __restrict__ act,
                                                                     const float4* __restrict__ hit, const float4* __restrict__ P,
                                                                     uint8_t* __restrict__ vis, unsigned n_act, unsigned* counter) {
     const int lane = threadIdx.x & 31;
-    int stack[YRT_STACK_CAP];
+    __shared__ int wstacks[PACKET ? TRACE_THREADS / 32 : 1][PACKET ? YRT_WSTACK : 1];
+    int stack[PACKET ? 1 : YRT_STACK_CAP];
     for (;;) {
         unsigned base = warp_fetch(counter, lane);
         if (base >= n_act) break;
         unsigned a = base + lane;
-        if (a >= n_act) continue;
-        unsigned slot = act ? (unsigned)act[a] : a;
-        float4 h = hit[slot];
-        if (float_as_int(h.x) < 0) continue;   // miss: shade() returns before the light loop (raytrace.cpp:93)
-        vec3 p = xyz(P[slot]);
+        bool alive = a < n_act;
+        unsigned slot = 0;
+        vec3 p = mk3(0.f, 0.f, 0.f);
+        if (alive) {
+            slot = act ? (unsigned)act[a] : a;
+            float4 h = hit[slot];
+            alive = float_as_int(h.x) >= 0;   // a miss casts no shadow rays: shade() returns before the light loop (raytrace.cpp:93)
+            if (alive) p = xyz(P[slot]);
+        }
+        if (!PACKET && !alive) continue;
+        if (PACKET && __ballot_sync(0xffffffffu, alive) == 0u) continue;
         for (int k = 0; k < sv.n_lights; k++) {
             vec3 l, ke;
             float r;
             light_vector(sv, k, p, l, r, ke);
             ray3 sr = shadow_ray(p, l, r);
             HitRec hr;
-            bool occ = trace_ray<true>(sv, sr, hr, stack, nullptr);
-            vis[(size_t)k * cap_slots + slot] = occ ? 0 : 1;
+            bool occ;
+            if (PACKET) trace_packet<true>(sv, sr, alive, hr, occ, wstacks[threadIdx.x >> 5], lane);
+            else occ = trace_ray<true>(sv, sr, hr, stack, nullptr);
+            if (alive) vis[(size_t)k * cap_slots + slot] = occ ? 0 : 1;
         }
     }
 }
@@ -387,17 +411,23 @@ static int run_batch(DevScene& ds, const RenderParams& rp, int lr0, int nrows, s
     bp.cap_slots = cap_slots;
     unsigned n = (unsigned)((size_t)nrows * rp.width * bp.spp);
     int nl = ds.view.n_lights;
-    if (!ds.grid_closest_primary) ds.grid_closest_primary = persistent_grid(ds, (const void*)k_trace_closest<true>);
-    if (!ds.grid_closest_queue) ds.grid_closest_queue = persistent_grid(ds, (const void*)k_trace_closest<false>);
-    if (!ds.grid_any) ds.grid_any = persistent_grid(ds, (const void*)k_trace_any_lights);
+    const bool packet = env_int("YRT_PACKET", 0) != 0;   // warp-cooperative packet traversal: measured slower here (profiles/r1_experiments.md)
+    if (ds.grid_packet != (int)packet) { ds.grid_closest_primary = ds.grid_any = 0; ds.grid_packet = (int)packet; }
+    if (!ds.grid_closest_primary) ds.grid_closest_primary = persistent_grid(ds, packet ? (const void*)k_trace_closest<true, true> : (const void*)k_trace_closest<true, false>);
+    if (!ds.grid_closest_queue) ds.grid_closest_queue = persistent_grid(ds, (const void*)k_trace_closest<false, false>);
+    if (!ds.grid_any) ds.grid_any = persistent_grid(ds, packet ? (const void*)k_trace_any_lights<true> : (const void*)k_trace_any_lights<false>);
     const int g_closest_p = ds.grid_closest_primary, g_closest_q = ds.grid_closest_queue, g_any = ds.grid_any;
     auto grid_of = [](int g, unsigned items) { unsigned need = (items + TRACE_THREADS - 1) / TRACE_THREADS; return (int)std::max(1u, std::min((unsigned)g, need)); };
 
     unsigned* ctr = nullptr;
     YRT_TRY(ring.get(&ctr));
     pt.begin(CAT_CLOSEST);
-    k_trace_closest<true><<<grid_of(g_closest_p, n), TRACE_THREADS, 0, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(),
-                                                                           w.P.as<float4>(), n, ctr);
+    if (packet)
+        k_trace_closest<true, true><<<grid_of(g_closest_p, n), TRACE_THREADS, 0, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(),
+                                                                                     w.P.as<float4>(), n, ctr);
+    else
+        k_trace_closest<true, false><<<grid_of(g_closest_p, n), TRACE_THREADS, 0, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(),
+                                                                                      w.P.as<float4>(), n, ctr);
     pt.end();
     if (primary_only) { YRT_CUDA(cudaGetLastError()); return YRT_OK; }
 
@@ -411,8 +441,13 @@ static int run_batch(DevScene& ds, const RenderParams& rp, int lr0, int nrows, s
         if (nl > 0) {
             YRT_TRY(ring.get(&ctr));
             pt.begin(CAT_ANY);
-            k_trace_any_lights<<<grid_of(g_any, n_act), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
-                                                                               w.vis.as<uint8_t>(), n_act, ctr);
+            // shadow rays of the camera hits are as coherent as the camera rays; those of reflection waves are not
+            if (packet && depth == 0)
+                k_trace_any_lights<true><<<grid_of(g_any, n_act), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
+                                                                                         w.vis.as<uint8_t>(), n_act, ctr);
+            else
+                k_trace_any_lights<false><<<grid_of(g_any, n_act), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
+                                                                                          w.vis.as<uint8_t>(), n_act, ctr);
             pt.end();
         }
         if (reflective) YRT_CUDA(cudaMemsetAsync(next_count, 0, sizeof(int), st));
@@ -431,7 +466,7 @@ static int run_batch(DevScene& ds, const RenderParams& rp, int lr0, int nrows, s
         act = next_act;
         YRT_TRY(ring.get(&ctr));
         pt.begin(CAT_CLOSEST);
-        k_trace_closest<false><<<grid_of(g_closest_q, n_act), TRACE_THREADS, 0, st>>>(ds.view, bp, act, w.ray_o.as<float4>(), w.ray_d.as<float4>(),
+        k_trace_closest<false, false><<<grid_of(g_closest_q, n_act), TRACE_THREADS, 0, st>>>(ds.view, bp, act, w.ray_o.as<float4>(), w.ray_d.as<float4>(),
                                                                                     w.hit.as<float4>(), w.P.as<float4>(), n_act, ctr);
         pt.end();
     }
@@ -610,7 +645,7 @@ int intersect_rays_device(DevScene& ds, const float* h_rays, int64_t n, bool any
     YRT_TRY(occ.alloc((size_t)c, ds.device));
     YRT_TRY(ctr.alloc(sizeof(unsigned), ds.device));
     std::vector<float4> ho(c), hd(c);
-    int g_c = persistent_grid(ds, (const void*)k_trace_closest<false>);
+    int g_c = persistent_grid(ds, (const void*)k_trace_closest<false, false>);
     int g_a = persistent_grid(ds, (const void*)k_trace_any_rays);
     BatchParams bp;
     memset(&bp, 0, sizeof(bp));
@@ -631,7 +666,7 @@ int intersect_rays_device(DevScene& ds, const float* h_rays, int64_t n, bool any
             YRT_CUDA(cudaGetLastError());
             YRT_CUDA(cudaMemcpyAsync(h_occ + off, occ.p, (size_t)m, cudaMemcpyDeviceToHost, st));
         } else {
-            k_trace_closest<false><<<std::max(1u, std::min((unsigned)g_c, need)), TRACE_THREADS, 0, st>>>(
+            k_trace_closest<false, false><<<std::max(1u, std::min((unsigned)g_c, need)), TRACE_THREADS, 0, st>>>(
                 ds.view, bp, nullptr, ro.as<float4>(), rd.as<float4>(), hit.as<float4>(), P.as<float4>(), (unsigned)m, ctr.as<unsigned>());
             k_hit_ids<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(ds.view, hit.as<float4>(), P.as<float4>(), (int)m, ids.as<int>(),
                                                                  dist.as<float>(), uv.as<float>());
