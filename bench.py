@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--samples", type=int, default=4)
     ap.add_argument("--n-side", type=int, default=100, help="instances per grid side (100 -> 10 004 instances)")
     ap.add_argument("--tile-rows", type=int, default=1, help="rows per interleaved tile (1: rows r, r+N, r+2N, ...)")
+    ap.add_argument("--gather", default="ipc", choices=["ipc", "nccl"],
+                    help="multi-GPU framebuffer exchange: ipc = every rank's resolve kernel stores its rows into rank 0's frame over "
+                         "NVLink peer memory + 1-element all-reduce; nccl = packed rows, NCCL gather, unpack on rank 0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-resolution", type=int, default=0, help="0 = sized for ~15 s of CPU work")
     return ap.parse_args()
@@ -206,7 +209,12 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     tr = args.tile_rows if multi else H
 
+    shared = D.SharedFrame(W, H) if args.gather == "ipc" else None
+
     def frame(want_stats=True):
+        if shared is not None:
+            st = shared.render(scene, S, 0.1, tr, want_stats)
+            return (shared.tensor() if rank == 0 else None), st
         return D.render_sharded(scene, W, H, S, 0.1, tr, None, want_stats)
 
     def barrier():
@@ -245,7 +253,7 @@ def run_b200(args):
     ms_total = float(ms.item())
     rays_total, launches = float(tot[0].item()), int(tot[1].item())
     if multi:
-        launches += args.steps * (world + 1)      # NCCL gather + unpack kernels on rank 0
+        launches += args.steps * (world if shared is not None else world + 1)      # + the exchange: all-reduce per rank / NCCL gather + unpack kernels
     value = rays_total / (ms_total * 1e-3) / 1e6
 
     # ---- end to end through the public API with HOST buffers (`e2e`) ----
@@ -329,13 +337,15 @@ def run_b200(args):
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(args, flat), "rays_per_frame": rays_total / args.steps, "parallelism": f"row-tiles x{world}",
+        "config": {"workload": workload_name(args, flat), "rays_per_frame": rays_total / args.steps, "parallelism": f"row-tiles x{world}", "exchange": args.gather if multi else "none",
                    "tile_rows": tr, "l2": "per-frame ray/hit queues (~1.7 GB streamed per frame) exceed the 126 MB L2; the 3 MB scene is "
                    "cache-resident by design", "lbvh": info},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 64 + 12, "d2h_bytes_per_step": W * H * 16,
                 "ms_per_step": float(dt.item()) * 1e3 / args.steps,
-                "api": "Scene.render -> yrt_render (host framebuffer out)" if not multi else "distributed.render_sharded + NCCL gather + D2H on rank 0"},
+                "api": "Scene.render -> yrt_render (host framebuffer out)" if not multi else
+                (f"distributed.SharedFrame.render (peer stores into rank 0's frame + all-reduce) + D2H on rank 0" if shared is not None
+                 else "distributed.render_sharded + NCCL gather + D2H on rank 0")},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,

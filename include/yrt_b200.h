@@ -163,6 +163,19 @@ int yrt_render_rows(yrt_scene* scn, const yrt_camera* cam, const float amb[3], i
                     int samples, int tile_rows, int rank, int world, void* d_rgba, void* stream,
                     yrt_stats* stats);
 int yrt_rows_owned(int height, int tile_rows, int rank, int world);
+/* Fused gather for one-process-per-GPU drivers: rank 0 allocates the full frame (yrt_frame_alloc) and exports a
+ * 64-byte CUDA IPC handle; the other ranks map it (yrt_frame_import: peer mapping over NVLink) and every rank's
+ * resolve kernel stores its rows at their final position in that ONE buffer (yrt_render_rows_into_frame) — no
+ * packed rows, no gather copy, no unpack; the caller only needs a completion barrier (e.g. a 1-element all-reduce
+ * on the same stream) before rank 0 reads the frame. */
+int yrt_render_rows_into_frame(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height,
+                               int samples, int tile_rows, int rank, int world, void* d_full, void* stream,
+                               yrt_stats* stats);
+int yrt_frame_alloc(int width, int height, void** d_full);
+int yrt_frame_free(void* d_full);
+int yrt_frame_export(void* d_full, unsigned char handle[64]);
+int yrt_frame_import(const unsigned char handle[64], void** d_full);
+int yrt_frame_release(void* d_full);
 /* deferred statistics for yrt_render_rows: frames rendered between begin and end record per-launch CUDA events
  * and ray counters WITHOUT any host synchronisation; yrt_stats_end waits for the device and returns the totals
  * over those frames (stats->frames says how many). */

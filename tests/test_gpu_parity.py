@@ -237,3 +237,27 @@ def test_drop_in_cli_matches_reference_cli(gpu, tmp_path):
         assert within1 >= PIXEL_BAR, (sc.name, within1, ident, mx)
     # unknown option: usage + non-zero exit like yu::cmdline (src/ext/yocto_utils.h:1157-1174)
     assert subprocess.run([ours, "--bogus", "x.obj"], capture_output=True).returncode != 0
+
+
+def test_fused_gather_into_one_frame(gpu):
+    """yrt_render_rows_into_frame: every rank's resolve stores its rows at their final position of ONE full frame
+    (what the ranks do over NVLink peer memory); emulated here by rendering all ranks of several partitions into
+    one buffer.  Must equal the whole-frame render bit for bit."""
+    import ctypes as C
+    import torch
+    lib = _lib.load()
+    flat, _ = load_golden("instance10000")
+    w, h, s = 160, 90, 2
+    with gpu.Scene(flat) as scn:
+        whole, _ = scn.render(w, h, s, 0.1)
+        for world, tr in ((2, 1), (8, 1), (3, 7)):
+            ptr = C.c_void_p()
+            assert lib.yrt_frame_alloc(w, h, C.byref(ptr)) == 0
+            for rank in range(world):
+                scn.render_rows_into_frame(ptr.value, w, h, s, 0.1, tr, rank, world, 0, rank == world - 1)
+            torch.cuda.synchronize()
+            iface = {"shape": (h, w, 4), "typestr": "<f4", "data": (ptr.value, False), "version": 3, "strides": None}
+            t = torch.as_tensor(type("F", (), {"__cuda_array_interface__": iface})(), device="cuda")
+            got = t.cpu().numpy()
+            assert lib.yrt_frame_free(ptr) == 0
+            assert np.array_equal(got.view(np.uint32), whole.view(np.uint32)), (world, tr)

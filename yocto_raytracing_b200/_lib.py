@@ -78,6 +78,13 @@ SYMBOLS = {
     "yrt_render_rows": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
     "yrt_rows_owned": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "yrt_render_rows_into_frame": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
+    "yrt_frame_alloc": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "yrt_frame_free": (C.c_int, [C.c_void_p]),
+    "yrt_frame_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "yrt_frame_import": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "yrt_frame_release": (C.c_int, [C.c_void_p]),
     "yrt_stats_begin": (C.c_int, [C.c_void_p]),
     "yrt_stats_end": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "yrt_unpack_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -148,6 +148,53 @@ int yrt_render_rows(yrt_scene* scn, const yrt_camera* cam, const float amb[3], i
     return render_rows_device(ds, rp, (float4*)d_rgba, st, stats, true);
 }
 
+int yrt_render_rows_into_frame(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height, int samples,
+                               int tile_rows, int rank, int world, void* d_full, void* stream, yrt_stats* stats) {
+    if (!scn || scn->dev.empty() || !d_full) { set_error("yrt_render_rows_into_frame: bad arguments"); return YRT_ERR_INVALID; }
+    RenderParams rp;
+    YRT_TRY(fill_params(cam, amb, width, height, samples, rp));
+    rp.tile_rows = tile_rows; rp.rank = rank; rp.world = world;
+    rp.scatter = true;
+    return render_rows_device(*scn->dev[0], rp, (float4*)d_full, (cudaStream_t)stream, stats, true);
+}
+
+int yrt_frame_alloc(int width, int height, void** d_full) {
+    if (!d_full || width <= 0 || height <= 0) { set_error("yrt_frame_alloc: bad arguments"); return YRT_ERR_INVALID; }
+    YRT_TRY(ensure_init());
+    YRT_CUDA(cudaSetDevice(g_devices[0]));
+    YRT_CUDA(cudaMalloc(d_full, sizeof(float4) * (size_t)width * height));
+    return YRT_OK;
+}
+
+int yrt_frame_free(void* d_full) {
+    if (d_full) YRT_CUDA(cudaFree(d_full));
+    return YRT_OK;
+}
+
+int yrt_frame_export(void* d_full, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!d_full || !handle) { set_error("yrt_frame_export: bad arguments"); return YRT_ERR_INVALID; }
+    cudaIpcMemHandle_t h;
+    YRT_CUDA(cudaIpcGetMemHandle(&h, d_full));
+    memcpy(handle, &h, 64);
+    return YRT_OK;
+}
+
+int yrt_frame_import(const unsigned char handle[64], void** d_full) {
+    if (!d_full || !handle) { set_error("yrt_frame_import: bad arguments"); return YRT_ERR_INVALID; }
+    YRT_TRY(ensure_init());
+    YRT_CUDA(cudaSetDevice(g_devices[0]));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    YRT_CUDA(cudaIpcOpenMemHandle(d_full, h, cudaIpcMemLazyEnablePeerAccess));
+    return YRT_OK;
+}
+
+int yrt_frame_release(void* d_full) {
+    if (d_full) YRT_CUDA(cudaIpcCloseMemHandle(d_full));
+    return YRT_OK;
+}
+
 int yrt_stats_begin(yrt_scene* scn) {
     if (!scn || scn->dev.empty()) { set_error("yrt_stats_begin: bad arguments"); return YRT_ERR_INVALID; }
     return stats_begin_device(*scn->dev[0]);

@@ -108,6 +108,7 @@ struct RenderParams {
     vec3 amb;
     int width, height, samples;
     int tile_rows, rank, world;   // interleaved row tiles
+    bool scatter = false;         // d_out is the full frame: rows go to their final position (fused gather)
 };
 
 YRT_HD int rows_owned(int height, int tile_rows, int rank, int world) {

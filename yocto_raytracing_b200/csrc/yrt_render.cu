@@ -242,8 +242,10 @@ __global__ void __launch_bounds__(256, 4) k_shade(SceneView sv, BatchParams bp, 
 }
 
 // ---- resolve: raytrace.cpp:241-249 ------------------------------------------------------------
+// scatter != 0: `out` is the FULL frame (possibly another GPU's memory mapped over NVLink) and every pixel goes to
+// its final position — the gather of the multi-GPU path fused into the resolve (no packed rows, no copy, no unpack)
 __global__ void __launch_bounds__(256) k_resolve(const float4* __restrict__ rad, float4* __restrict__ out, int n_pix, int spp,
-                                                 size_t out_pix0) {
+                                                 size_t out_pix0, int scatter, int width, int lr0, int tile_rows, int rank, int world) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pix) return;
     const float4* r = rad + (size_t)p * spp;
@@ -253,7 +255,12 @@ __global__ void __launch_bounds__(256) k_resolve(const float4* __restrict__ rad,
         x += v.x; y += v.y; z += v.z;
     }
     float d = (float)spp;             // float(samples * samples)
-    out[out_pix0 + p] = mk4(x / d, y / d, z / d, 1.0f);
+    size_t o = out_pix0 + p;
+    if (scatter) {
+        int lr = p / width, i = p - lr * width;
+        o = (size_t)global_row(lr0 + lr, tile_rows, rank, world) * width + i;
+    }
+    out[o] = mk4(x / d, y / d, z / d, 1.0f);
 }
 
 // ---- parity hook: hit records -> (instance, shape, element) ids ----------------------------------
@@ -472,7 +479,8 @@ static int run_batch(DevScene& ds, const RenderParams& rp, int lr0, int nrows, s
     }
     int n_pix = nrows * rp.width;
     pt.begin(CAT_OTHER);
-    k_resolve<<<(n_pix + 255) / 256, 256, 0, st>>>(w.rad.as<float4>(), d_out, n_pix, bp.spp, (size_t)lr0 * rp.width);
+    k_resolve<<<(n_pix + 255) / 256, 256, 0, st>>>(w.rad.as<float4>(), d_out, n_pix, bp.spp, (size_t)lr0 * rp.width, rp.scatter ? 1 : 0, rp.width, lr0,
+                                                  rp.tile_rows, rp.rank, rp.world);
     pt.end();
     YRT_CUDA(cudaGetLastError());
     return YRT_OK;

@@ -88,3 +88,58 @@ def render_sharded(scene, width: int, height: int, samples: int, amb=0.1, tile_r
                                    tile_rows, rank, world, st, want_stats)
     full = gather_rows(packed, width, height, tile_rows, rank, world, group)
     return full, stats
+
+
+class SharedFrame:
+    """The full framebuffer in rank 0's HBM, mapped into every other rank over NVLink (CUDA IPC).  Every rank's
+    resolve kernel stores its rows at their final position, so the per-frame exchange is the stores themselves plus
+    one 1-element all-reduce as completion barrier — no gather copy and no unpack."""
+
+    def __init__(self, width: int, height: int, group=None):
+        import ctypes as C
+        self.width, self.height, self.group = width, height, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        lib = _lib.load()
+        self._ptr = C.c_void_p()
+        self._owner = self.rank == 0
+        handle = C.create_string_buffer(64)
+        if self._owner:
+            check(lib.yrt_frame_alloc(width, height, C.byref(self._ptr)))
+            if self.world > 1:
+                check(lib.yrt_frame_export(self._ptr, handle))
+        if self.world > 1:
+            box = [handle.raw if self._owner else None]
+            dist.broadcast_object_list(box, src=0, group=group)
+            if not self._owner:
+                check(lib.yrt_frame_import(box[0], C.byref(self._ptr)))
+        self._token = torch.zeros(1, device=torch.device("cuda", torch.cuda.current_device()))
+
+    @property
+    def ptr(self) -> int:
+        return self._ptr.value
+
+    def tensor(self) -> torch.Tensor:
+        """Rank 0: the frame as a (height, width, 4) float32 CUDA tensor view (no copy)."""
+        assert self._owner
+        iface = {"shape": (self.height, self.width, 4), "typestr": "<f4", "data": (self.ptr, False), "version": 3, "strides": None}
+        holder = type("_Frame", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device=torch.device("cuda", torch.cuda.current_device()))
+
+    def render(self, scene, samples: int, amb=0.1, tile_rows: int = 1, want_stats: bool = False):
+        """Render this rank's rows into the shared frame and join the completion barrier (stream-ordered, no host sync)."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        st = torch.cuda.current_stream(dev).cuda_stream
+        stats = scene.render_rows_into_frame(self.ptr, self.width, self.height, samples, amb, tile_rows, self.rank, self.world, st, want_stats)
+        if self.world > 1:
+            dist.all_reduce(self._token, group=self.group)   # completes on rank 0 only after every rank's stores were issued
+        return stats
+
+    def close(self):
+        lib = _lib.load()
+        if self._ptr:
+            if self._owner:
+                lib.yrt_frame_free(self._ptr)
+            else:
+                lib.yrt_frame_release(self._ptr)
+            self._ptr = None

@@ -104,6 +104,17 @@ class Scene:
                                           C.byref(st) if st is not None else None))
         return st
 
+    def render_rows_into_frame(self, d_full: int, width: int, height: int, samples: int, amb=0.1, tile_rows: int = 1, rank: int = 0,
+                               world: int = 1, stream: int = 0, want_stats: bool = False):
+        """yrt_render_rows_into_frame: this rank's rows straight into the FULL frame at d_full (own or peer memory)."""
+        a = np.broadcast_to(np.asarray(amb, np.float32), (3,))
+        amb3 = (C.c_float * 3)(*[float(x) for x in a])
+        st = Stats() if want_stats else None
+        check(_lib.load().yrt_render_rows_into_frame(self._h, C.byref(self._cam), amb3, int(width), int(height), int(samples),
+                                                     int(tile_rows), int(rank), int(world), C.c_void_p(d_full), C.c_void_p(stream),
+                                                     C.byref(st) if st is not None else None))
+        return st
+
     def stats_begin(self) -> None:
         """Open deferred statistics: following render_rows_into frames record events/counters without host syncs."""
         check(_lib.load().yrt_stats_begin(self._h))
