@@ -96,6 +96,7 @@ struct DevScene {
     int sm_count = 148;
     bool has_reflective = false;
     int grid_closest_primary = 0, grid_closest_queue = 0, grid_any = 0;   // persistent grids (SMs x resident CTAs)
+    int grid_shadow_shade = 0;
     int grid_packet = -1;            // traversal mode the cached grids were computed for
     PhaseTimer* timer = nullptr;     // owned (yrt_render.cu)
 };

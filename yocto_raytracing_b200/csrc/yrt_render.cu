@@ -177,11 +177,71 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_any_rays(SceneView sv, 
 // ---- shade ------------------------------------------------------------------------------------
 struct FrameCounters { unsigned long long hits, reflections, misses, pad; };
 
-__global__ void __launch_bounds__(256, 4) k_shade(SceneView sv, BatchParams bp, int depth, int max_depth, const int* __restrict__ act,
-                                               unsigned n_act, const float4* __restrict__ hit, const float4* __restrict__ P,
-                                               const uint8_t* __restrict__ vis, float4* __restrict__ ray_o, float4* __restrict__ ray_d,
-                                               float4* __restrict__ pstack, float4* __restrict__ rad, int* __restrict__ next_act,
-                                               int* __restrict__ next_count, FrameCounters* __restrict__ fc) {
+struct ShadeBuffers {
+    const float4* hit;
+    float4 *ray_o, *ray_d, *pstack, *rad;
+    int* next_act;
+    int* next_count;
+    FrameCounters* fc;
+};
+
+// shade() of one sample whose shadow rays are known (vis(k) = light k unoccluded): writes the radiance of a finished
+// path, or pushes {c, kr, la} and the mirror ray of a path that goes on.  Returns spawn; is_hit says whether the ray hit.
+template <class VisFn>
+__device__ __forceinline__ bool shade_slot(const SceneView& sv, const BatchParams& bp, const ShadeBuffers& sb, int depth, int max_depth,
+                                           unsigned slot, const float4& h, const float* lut, VisFn vis, bool& is_hit) {
+    int si = float_as_int(h.x);
+    bool spawn = false;
+    vec3 value = mk3(0.f, 0.f, 0.f);          // miss: {0,0,0,1}, raytrace.cpp:93
+    const size_t cap = bp.cap_slots;
+    is_hit = si >= 0;
+    if (is_hit) {
+        vec3 ro = depth == 0 ? bp.cam.frame.o : xyz(sb.ray_o[slot]);
+        vec3 c, kr, la;
+        ray3 rr;
+        spawn = shade_hit(sv, si, float_as_int(h.y), h.z, h.w, ro, bp.amb, lut, vis, depth + 1 < max_depth, value, c, kr, la, rr);
+        if (spawn) {
+            float4* f = sb.pstack + ((size_t)depth * cap + slot) * 3;
+            f[0] = mk4(c.x, c.y, c.z, 0.f);
+            f[1] = mk4(kr.x, kr.y, kr.z, 0.f);
+            f[2] = mk4(la.x, la.y, la.z, 0.f);
+            sb.ray_o[slot] = mk4(rr.o.x, rr.o.y, rr.o.z, rr.tmin);
+            sb.ray_d[slot] = mk4(rr.d.x, rr.d.y, rr.d.z, rr.tmax);
+        }
+    }
+    if (!spawn) {
+        // unwind the recursion: each level closes with c + col*kr, then + la (raytrace.cpp:203,206)
+        for (int d = depth - 1; d >= 0; d--) {
+            const float4* f = sb.pstack + ((size_t)d * cap + slot) * 3;
+            value = combine_reflection(xyz(f[0]), value, xyz(f[1]), xyz(f[2]));
+        }
+        sb.rad[slot] = mk4(value.x, value.y, value.z, 1.0f);
+    }
+    return spawn;
+}
+
+// compacted queue of the next wave + frame counters (warp-aggregated; every lane of the warp must call it)
+__device__ __forceinline__ void shade_epilogue(const ShadeBuffers& sb, bool valid, bool is_hit, bool spawn, unsigned slot, int lane) {
+    unsigned m_spawn = __ballot_sync(0xffffffffu, spawn);
+    unsigned m_hit = __ballot_sync(0xffffffffu, is_hit);
+    unsigned m_valid = __ballot_sync(0xffffffffu, valid);
+    if (m_spawn) {
+        int basei = 0;
+        if (lane == 0) basei = atomicAdd(sb.next_count, __popc(m_spawn));
+        basei = __shfl_sync(0xffffffffu, basei, 0);
+        if (spawn) sb.next_act[basei + __popc(m_spawn & ((1u << lane) - 1u))] = (int)slot;
+    }
+    if (lane == 0 && m_valid) {
+        if (m_hit) atomicAdd(&sb.fc->hits, (unsigned long long)__popc(m_hit));
+        if (m_spawn) atomicAdd(&sb.fc->reflections, (unsigned long long)__popc(m_spawn));
+        unsigned miss = m_valid & ~m_hit;
+        if (miss) atomicAdd(&sb.fc->misses, (unsigned long long)__popc(miss));
+    }
+}
+
+// unfused shade: visibility bytes written by k_trace_any_lights (used when a scene has more than 32 lights)
+__global__ void __launch_bounds__(256, 4) k_shade(SceneView sv, BatchParams bp, ShadeBuffers sb, int depth, int max_depth,
+                                                  const int* __restrict__ act, unsigned n_act, const uint8_t* __restrict__ vis) {
     __shared__ float lut[256];
     lut[threadIdx.x] = sv.srgb_lut[threadIdx.x];
     __syncthreads();
@@ -191,57 +251,54 @@ __global__ void __launch_bounds__(256, 4) k_shade(SceneView sv, BatchParams bp, 
     unsigned slot = 0;
     if (valid) {
         slot = act ? (unsigned)act[a] : a;
-        float4 h = hit[slot];
-        int si = float_as_int(h.x);
-        vec3 value = mk3(0.f, 0.f, 0.f);          // miss: {0,0,0,1}, raytrace.cpp:93
-        if (si >= 0) {
-            is_hit = true;
-            vec3 ro = depth == 0 ? bp.cam.frame.o : xyz(ray_o[slot]);
-            vec3 c, kr, la;
-            ray3 rr;
-            const uint8_t* vrow = vis + slot;
-            size_t cap = bp.cap_slots;
-            spawn = shade_hit(sv, si, float_as_int(h.y), h.z, h.w, ro, bp.amb, lut,
-                              [&](int k) { return vrow[(size_t)k * cap] != 0; }, depth + 1 < max_depth, value, c, kr, la, rr);
-            if (spawn) {
-                float4* f = pstack + ((size_t)depth * cap + slot) * 3;
-                f[0] = mk4(c.x, c.y, c.z, 0.f);
-                f[1] = mk4(kr.x, kr.y, kr.z, 0.f);
-                f[2] = mk4(la.x, la.y, la.z, 0.f);
-                ray_o[slot] = mk4(rr.o.x, rr.o.y, rr.o.z, rr.tmin);
-                ray_d[slot] = mk4(rr.d.x, rr.d.y, rr.d.z, rr.tmax);
-            }
-        }
-        if (!spawn) {
-            // unwind the recursion: each level closes with c + col*kr, then + la (raytrace.cpp:203,206)
-            size_t cap = bp.cap_slots;
-            for (int d = depth - 1; d >= 0; d--) {
-                const float4* f = pstack + ((size_t)d * cap + slot) * 3;
-                value = combine_reflection(xyz(f[0]), value, xyz(f[1]), xyz(f[2]));
-            }
-            rad[slot] = mk4(value.x, value.y, value.z, 1.0f);
-        }
+        float4 h = sb.hit[slot];
+        const uint8_t* vrow = vis + slot;
+        size_t cap = bp.cap_slots;
+        spawn = shade_slot(sv, bp, sb, depth, max_depth, slot, h, lut, [&](int k) { return vrow[(size_t)k * cap] != 0; }, is_hit);
     }
-    // compacted queue of the next wave + frame counters (warp-aggregated)
-    unsigned m_spawn = __ballot_sync(0xffffffffu, spawn);
-    unsigned m_hit = __ballot_sync(0xffffffffu, is_hit);
-    unsigned m_valid = __ballot_sync(0xffffffffu, valid);
-    int lane = threadIdx.x & 31;
-    if (m_spawn) {
-        int basei = 0;
-        if (lane == 0) basei = atomicAdd(next_count, __popc(m_spawn));
-        basei = __shfl_sync(0xffffffffu, basei, 0);
-        if (spawn) next_act[basei + __popc(m_spawn & ((1u << lane) - 1u))] = (int)slot;
-    }
-    if (lane == 0 && m_valid) {
-        if (m_hit) atomicAdd(&fc->hits, (unsigned long long)__popc(m_hit));
-        if (m_spawn) atomicAdd(&fc->reflections, (unsigned long long)__popc(m_spawn));
-        unsigned miss = m_valid & ~m_hit;
-        if (miss) atomicAdd(&fc->misses, (unsigned long long)__popc(miss));
+    shade_epilogue(sb, valid, is_hit, spawn, slot, threadIdx.x & 31);
+}
+
+// fused shadow + shade (persistent): the lane that traces the shadow rays of a hit keeps their visibility in a
+// register mask and shades the hit right away — no visibility buffer, the hit record is read once, and one
+// launch (and one kernel tail) less per wave.  Up to 32 lights.
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow_shade(SceneView sv, BatchParams bp, ShadeBuffers sb, int depth,
+                                                                                 int max_depth, const int* __restrict__ act,
+                                                                                 unsigned n_act, const float4* __restrict__ P,
+                                                                                 unsigned* counter) {
+    __shared__ float lut[256];
+    for (int i = threadIdx.x; i < 256; i += TRACE_THREADS) lut[i] = sv.srgb_lut[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    int stack[YRT_STACK_CAP];
+    for (;;) {
+        unsigned base = warp_fetch(counter, lane);
+        if (base >= n_act) break;
+        unsigned a = base + lane;
+        const bool valid = a < n_act;
+        bool is_hit = false, spawn = false;
+        unsigned slot = 0;
+        if (valid) {
+            slot = act ? (unsigned)act[a] : a;
+            float4 h = sb.hit[slot];
+            unsigned vmask = 0u;
+            if (float_as_int(h.x) >= 0) {   // a miss casts no shadow rays: shade() returns before the light loop (raytrace.cpp:93)
+                vec3 p = xyz(P[slot]);
+                for (int k = 0; k < sv.n_lights; k++) {
+                    vec3 l, ke;
+                    float r;
+                    light_vector(sv, k, p, l, r, ke);
+                    ray3 sr = shadow_ray(p, l, r);
+                    HitRec hr;
+                    if (!trace_ray<true>(sv, sr, hr, stack, nullptr)) vmask |= 1u << k;
+                }
+            }
+            spawn = shade_slot(sv, bp, sb, depth, max_depth, slot, h, lut, [&](int k) { return ((vmask >> k) & 1u) != 0u; }, is_hit);
+        }
+        shade_epilogue(sb, valid, is_hit, spawn, slot, lane);
     }
 }
 
-// ---- resolve: raytrace.cpp:241-249 ------------------------------------------------------------
 // scatter != 0: `out` is the FULL frame (possibly another GPU's memory mapped over NVLink) and every pixel goes to
 // its final position — the gather of the multi-GPU path fused into the resolve (no packed rows, no copy, no unpack)
 __global__ void __launch_bounds__(256) k_resolve(const float4* __restrict__ rad, float4* __restrict__ out, int n_pix, int spp,
@@ -445,25 +502,37 @@ static int run_batch(DevScene& ds, const RenderParams& rp, int lr0, int nrows, s
     unsigned n_act = n;
     for (int depth = 0;; depth++) {
         if (depth + 1 > max_depth_seen) max_depth_seen = depth + 1;
-        if (nl > 0) {
-            YRT_TRY(ring.get(&ctr));
-            pt.begin(CAT_ANY);
-            // shadow rays of the camera hits are as coherent as the camera rays; those of reflection waves are not
-            if (packet && depth == 0)
-                k_trace_any_lights<true><<<grid_of(g_any, n_act), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
-                                                                                         w.vis.as<uint8_t>(), n_act, ctr);
-            else
-                k_trace_any_lights<false><<<grid_of(g_any, n_act), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
-                                                                                          w.vis.as<uint8_t>(), n_act, ctr);
-            pt.end();
-        }
         if (reflective) YRT_CUDA(cudaMemsetAsync(next_count, 0, sizeof(int), st));
         int* next_act = reflective ? act_bufs[depth & 1] : nullptr;
-        pt.begin(CAT_SHADE);
-        k_shade<<<(n_act + 255) / 256, 256, 0, st>>>(ds.view, bp, depth, depth_cap, act, n_act, w.hit.as<float4>(), w.P.as<float4>(),
-                                                   w.vis.as<uint8_t>(), w.ray_o.as<float4>(), w.ray_d.as<float4>(), w.pstack.as<float4>(),
-                                                   w.rad.as<float4>(), next_act, next_count, fc);
-        pt.end();
+        ShadeBuffers sb;
+        sb.hit = w.hit.as<float4>(); sb.ray_o = w.ray_o.as<float4>(); sb.ray_d = w.ray_d.as<float4>(); sb.pstack = w.pstack.as<float4>();
+        sb.rad = w.rad.as<float4>(); sb.next_act = next_act; sb.next_count = next_count; sb.fc = fc;
+        const bool fused = nl <= 32 && !packet && env_int("YRT_FUSE_SHADE", 0) != 0;   // measured: 16.76 vs 16.57 ms unfused at N=1 (spills at the 64-register cap); option only
+        if (fused) {
+            // shadow rays + shading in one persistent kernel (visibility stays in a register mask)
+            if (!ds.grid_shadow_shade) ds.grid_shadow_shade = persistent_grid(ds, (const void*)k_shadow_shade);
+            YRT_TRY(ring.get(&ctr));
+            pt.begin(CAT_ANY);
+            k_shadow_shade<<<grid_of(ds.grid_shadow_shade, n_act), TRACE_THREADS, 0, st>>>(ds.view, bp, sb, depth, depth_cap, act, n_act,
+                                                                                          w.P.as<float4>(), ctr);
+            pt.end();
+        } else {
+            if (nl > 0) {
+                YRT_TRY(ring.get(&ctr));
+                pt.begin(CAT_ANY);
+                // shadow rays of the camera hits are as coherent as the camera rays; those of reflection waves are not
+                if (packet && depth == 0)
+                    k_trace_any_lights<true><<<grid_of(g_any, n_act), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
+                                                                                             w.vis.as<uint8_t>(), n_act, ctr);
+                else
+                    k_trace_any_lights<false><<<grid_of(g_any, n_act), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
+                                                                                              w.vis.as<uint8_t>(), n_act, ctr);
+                pt.end();
+            }
+            pt.begin(CAT_SHADE);
+            k_shade<<<(n_act + 255) / 256, 256, 0, st>>>(ds.view, bp, sb, depth, depth_cap, act, n_act, w.vis.as<uint8_t>());
+            pt.end();
+        }
         if (!reflective || depth + 1 >= depth_cap) break;
         int h_next = 0;
         YRT_CUDA(cudaMemcpyAsync(&h_next, next_count, sizeof(int), cudaMemcpyDeviceToHost, st));
