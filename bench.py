@@ -249,6 +249,15 @@ def run_b200(args):
     if multi:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    # per-rank device time of the frames (render only, from the in-stream frame events) — shows rank imbalance
+    mine = torch.tensor([tot_stats.ms_total / args.steps, (tot_stats.ms_trace_closest + tot_stats.ms_trace_any + tot_stats.ms_shade + tot_stats.ms_other) / args.steps],
+                        device=dev, dtype=torch.float64)
+    per_rank = [torch.zeros_like(mine) for _ in range(world)]
+    if multi:
+        dist.all_gather(per_rank, mine)
+    else:
+        per_rank = [mine]
+    per_rank_ms = [[round(float(x[0]), 4), round(float(x[1]), 4)] for x in per_rank]
     clocks = sampler.stop() if rank == 0 else None
     ms_total = float(ms.item())
     rays_total, launches = float(tot[0].item()), int(tot[1].item())
@@ -349,6 +358,7 @@ def run_b200(args):
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "per_rank_render_ms_and_kernel_sum": per_rank_ms,
         "breakdown_ms_per_frame_rank0": {"trace_closest": closest_ms, "trace_any": any_ms, "shade": shade_ms, "resolve": other_ms},
         "mrays_s_by_kernel_rank0": {"closest": primary_per_frame / (closest_ms * 1e-3) / 1e6 if closest_ms else None,
                                     "any": shadow_per_frame / (any_ms * 1e-3) / 1e6 if any_ms else None},

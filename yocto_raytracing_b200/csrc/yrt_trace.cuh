@@ -86,7 +86,7 @@ YRT_HD vec3 inv3(const vec3& d) { return mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z)
 // if-if loop the node path and the leaf paths would be issued in every iteration for partial warps;
 // the kernels are issue bound, so that matters (profiles/).  Being resumable lets the persistent
 // kernels hand a finished lane a new ray while the rest of the warp keeps going.
-template <bool ANY>
+template <bool ANY, bool EXACT = false>
 struct Tracer {
     vec3 wo, wd;          // world-space ray
     slabray wsr;
@@ -130,8 +130,17 @@ struct Tracer {
         const float4* n = sv.nodes + 4 * (size_t)cur;
         float4 q0 = ld4(n), q1 = ld4(n + 1), q2 = ld4(n + 2), q3 = ld4(n + 3);
         float e0, e1;
-        bool h0 = slab_test_ch(sr, tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.w, e0);
-        bool h1 = slab_test_ch(sr, tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, q3.w, e1);
+        bool h0, h1;
+        if (EXACT) {
+            // rays (nearly) parallel to an axis plane: |invd| is huge there and so is the per-box pad of the fused
+            // test (it would accept half the scene); they take the reference's own formula on the stored box instead
+            raysigns sgn = signs_of(sr.invd);
+            h0 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, q0.x - q1.x, q0.y - q1.y, q0.z - q1.z, q0.x + q1.x, q0.y + q1.y, q0.z + q1.z, e0);
+            h1 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, q2.x - q3.x, q2.y - q3.y, q2.z - q3.z, q2.x + q3.x, q2.y + q3.y, q2.z + q3.z, e1);
+        } else {
+            h0 = slab_test_ch(sr, tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.w, e0);
+            h1 = slab_test_ch(sr, tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, q3.w, e1);
+        }
         if (ctr) {   // host-side audit against the reference's own test
             ctr->box_tests += 2;
             if (top) ctr->tlas_box_tests += 2;
@@ -213,9 +222,13 @@ struct Tracer {
     }
 };
 
-template <bool ANY>
-YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* stack, TraceCounters* ctr) {
-    Tracer<ANY> t;
+// |invd| above which a ray uses the reference's slab formula (Tracer<ANY, true>): below it the fused test's per-box pad
+// 8u max|invd| (hx+hy+hz) stays under 0.002 (hx+hy+hz)
+#define YRT_EXACT_SLAB_INVD 4096.0f
+
+template <bool ANY, bool EXACT>
+YRT_HD bool trace_ray_impl(const SceneView& sv, const ray3& wray, HitRec& hit, int* stack, TraceCounters* ctr) {
+    Tracer<ANY, EXACT> t;
     t.begin(sv, wray);
     for (;;) {
         t.nodes(sv, stack, ctr);
@@ -224,6 +237,15 @@ YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* s
     }
     hit = t.hit;
     return t.found;
+}
+
+template <bool ANY>
+YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* stack, TraceCounters* ctr) {
+    // decided on the world-space direction (instance frames of the configs are pure translations, so the local
+    // direction is the same; a rotated instance may still meet a large pad — slower, never wrong)
+    float m = fmaxf(fmaxf(fabsf(1.0f / wray.d.x), fabsf(1.0f / wray.d.y)), fabsf(1.0f / wray.d.z));
+    if (m > YRT_EXACT_SLAB_INVD) return trace_ray_impl<ANY, true>(sv, wray, hit, stack, ctr);
+    return trace_ray_impl<ANY, false>(sv, wray, hit, stack, ctr);
 }
 
 }  // namespace yrt
