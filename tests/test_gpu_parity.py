@@ -261,3 +261,35 @@ def test_fused_gather_into_one_frame(gpu):
             got = t.cpu().numpy()
             assert lib.yrt_frame_free(ptr) == 0
             assert np.array_equal(got.view(np.uint32), whole.view(np.uint32)), (world, tr)
+
+
+def test_large_scene_and_deep_trees(gpu, oracle_mod):
+    """90 000 instances (300 x 300 grid): the LBVH depth check, the radix sort at > 64 K keys and the tie ranks at scale."""
+    flat = synth.instance_grid_scene(300, seed=5).flat()
+    w, h = 160, 90
+    with gpu.Scene(flat) as scn:
+        info = scn.info()
+        ids, dist, _ = scn.trace_primary(w, h, 1)
+    assert info["tlas_nodes"] == flat.n_instances - 1 and info["blas_depth"] + info["tlas_depth"] + 4 <= 128
+    rids, rdist, _ = oracle_mod.OracleScene(flat).trace_primary(w, h, 1)
+    assert id_match(ids, rids) >= ID_BAR
+    same = (ids == rids).all(axis=1)
+    assert np.array_equal(dist[same], rdist[same])
+
+
+def test_in_process_multi_gpu_matches_single(gpu):
+    """yrt_init(n) + yrt_render: rows interleaved over the GPUs of this process, peer copies to GPU 0; bit-identical."""
+    n = gpu.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs in this process")
+    flat, _ = load_golden("instance10000")
+    with gpu.Scene(flat) as scn:
+        one, _ = scn.render(320, 180, 2, 0.1)
+    try:
+        gpu.init(min(n, 4))
+        with gpu.Scene(flat) as scn:
+            many, st = scn.render(320, 180, 2, 0.1)
+        assert st.n_gpus == min(n, 4)
+        assert np.array_equal(one.view(np.uint32), many.view(np.uint32))
+    finally:
+        gpu.init(1)
