@@ -242,6 +242,21 @@ def run_b200(args):
     tot_stats = scene.stats_end()
     assert tot_stats.frames == args.steps, (tot_stats.frames, args.steps)
     per_frame = {k: (v / args.steps if isinstance(v, (int, float)) else v) for k, v in tot_stats.as_dict().items()}
+    kernel_timing = "CUDA events around every launch inside the timed region"
+    if multi and os.environ.get("YRT_STREAMS", "2") != "1":
+        # a rank's share runs as two pipelines on two streams, so kernels of the two half shares overlap and an event
+        # span includes queueing behind the other pipeline: per-kernel durations come from a single-pipeline pass of
+        # 3 frames right after the timed region (same buffers, same kernels)
+        os.environ["YRT_STREAMS"] = "1"
+        scene.stats_begin()
+        for _ in range(3):
+            frame(False)
+        barrier()
+        k3 = scene.stats_end()
+        del os.environ["YRT_STREAMS"]
+        for key in ("ms_trace_closest", "ms_trace_any", "ms_shade", "ms_other", "n_closest", "n_any", "n_shade", "n_other"):
+            per_frame[key] = getattr(k3, key) / 3.0
+        kernel_timing = "single-pipeline pass of 3 frames right after the timed region (in the timed region two pipelines overlap kernels)"
     stats_all = [per_frame]
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     rays_local = float(tot_stats.primary_rays + tot_stats.reflection_rays + tot_stats.shadow_rays)
@@ -323,7 +338,7 @@ def run_b200(args):
         "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,
         "peak_source": f"148 SMs x 128 FP32 lanes x 2 flop x {sm_mhz:.0f} MHz (SM clock sampled during the timed region)",
         "traffic": NCU_DRAM_BYTES_PER_ANY_LAUNCH, "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/",
-        "launch_ms": any_launch_ms, "launches_per_frame": any_n, "rays_per_launch": rays_per_launch,
+        "launch_ms": any_launch_ms, "launch_timing": kernel_timing, "launches_per_frame": any_n, "rays_per_launch": rays_per_launch,
         "algorithmic_flops_per_ray": ALG_FLOPS_PER_RAY, "algorithmic_bytes_per_ray": ALG_BYTES_PER_RAY,
         "hbm": {"note": "literal bytes roofline: 2.84 KB/ray is CACHE-level (L1/L2) node+primitive traffic of the reference's traversal; "
                         "compulsory HBM traffic is ~11 B/ray (hit record + position + visibility), so frac > 1 here only says the "

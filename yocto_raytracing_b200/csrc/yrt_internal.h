@@ -93,6 +93,9 @@ struct DevScene {
     float build_us = 0.f;
     cudaStream_t stream = nullptr;   // owned
     Workspace ws;
+    Workspace ws_aux[3];             // further pipelines (part frames on several streams overlap kernel tails)
+    cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // owned
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     int sm_count = 148;
     bool has_reflective = false;
     int grid_closest_primary = 0, grid_closest_queue = 0, grid_any = 0;   // persistent grids (SMs x resident CTAs)
