@@ -204,8 +204,10 @@ def run_b200(args):
     sc = synth.instance_grid_scene(args.n_side)
     flat = sc.flat()
     W, H, S = flat.image_width(args.resolution), args.resolution, args.samples
-    scene = y.Scene(flat)
+    t_up = time.perf_counter()
+    scene = y.Scene(flat)           # validate + upload + GPU LBVH build (reported separately, not in the timed region)
     info = scene.info()
+    info["scene_create_ms_wall"] = round((time.perf_counter() - t_up) * 1e3, 3)
     dev = torch.device("cuda", local)
     tr = args.tile_rows if multi else H
 

@@ -152,6 +152,13 @@ int yrt_image_width(const yrt_camera* cam, int resolution);
 int yrt_render(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height,
                int samples, float* rgba_out, yrt_stats* stats);
 
+/* Next row: the same frame followed by tonemap(hdr, 0, false) (src/image.cpp:55-78) ON THE DEVICE, i.e. what
+ * save_hdr_or_ldr hands to the PNG writer: rgba8_out = width*height*4 bytes (HOST).  Only a quarter of the bytes cross to the
+ * host.  rgba_out (optional, HOST floats) additionally receives the float image.  The device powf differs from glibc's by a few
+ * ulp: at most one 8-bit level on ~0.3 % of pixels against the host tonemap. */
+int yrt_render_ldr(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height, int samples,
+                   uint8_t* rgba8_out, float* rgba_out, yrt_stats* stats);
+
 /* Same frame, device-resident, for one-process-per-GPU drivers: renders only the rows
  * owned by `rank` of `world` (row tile t of `tile_rows` rows belongs to rank t % world)
  * into d_rgba (DEVICE pointer on the current yrt device) holding the rank's rows packed in

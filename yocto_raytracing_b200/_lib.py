@@ -75,6 +75,8 @@ SYMBOLS = {
     "yrt_image_width": (C.c_int, [C.POINTER(Camera), C.c_int]),
     "yrt_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_void_p,
                              C.POINTER(Stats)]),
+    "yrt_render_ldr": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.POINTER(Stats)]),
     "yrt_render_rows": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
     "yrt_rows_owned": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),

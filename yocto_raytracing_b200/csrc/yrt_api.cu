@@ -17,12 +17,14 @@ using namespace yrt;
 namespace {
 std::mutex g_mu;
 std::vector<int> g_devices;   // empty until yrt_init*
+std::vector<int> g_peer_ok;   // per initialised device: can it store into device 0's memory (NVLink peer access)?
 
 struct GatherState {          // device-0 side buffers of the in-process multi-GPU path
     std::vector<DevBuf*> packed;   // per device, on that device
     std::vector<DevBuf*> staged;   // per device, on device 0
-    DevBuf full;
+    DevBuf full, ldr;
     std::vector<cudaEvent_t> done;
+    std::vector<int> direct;       // per device: stored straight into `full` (peer stores), nothing to unpack
     ~GatherState() {
         for (auto p : packed) delete p;
         for (auto p : staged) delete p;
@@ -56,11 +58,19 @@ int yrt_init(int n_gpus) {
         return YRT_ERR_NO_DEVICE;
     }
     g_devices.clear();
+    g_peer_ok.assign(n_gpus, 0);
+    g_peer_ok[0] = 1;
     for (int i = 0; i < n_gpus; i++) g_devices.push_back(i);
     for (int i = 1; i < n_gpus; i++) {   // NVLink peer access between GPU 0 and every other GPU (both ways)
         int can = 0;
         if (cudaDeviceCanAccessPeer(&can, 0, i) == cudaSuccess && can) { cudaSetDevice(0); cudaDeviceEnablePeerAccess(i, 0); }
-        if (cudaDeviceCanAccessPeer(&can, i, 0) == cudaSuccess && can) { cudaSetDevice(i); cudaDeviceEnablePeerAccess(0, 0); }
+        cudaGetLastError();
+        can = 0;
+        if (cudaDeviceCanAccessPeer(&can, i, 0) == cudaSuccess && can) {
+            cudaSetDevice(i);
+            cudaError_t e = cudaDeviceEnablePeerAccess(0, 0);
+            if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) g_peer_ok[i] = 1;
+        }
         cudaGetLastError();
     }
     YRT_CUDA(cudaSetDevice(0));
@@ -77,6 +87,7 @@ int yrt_init_device(int device) {
         return YRT_ERR_NO_DEVICE;
     }
     g_devices.assign(1, device);
+    g_peer_ok.assign(1, 1);
     YRT_CUDA(cudaSetDevice(device));
     delete g_gather;
     g_gather = nullptr;
@@ -213,9 +224,9 @@ int yrt_unpack_rows(const void* d_packed, void* d_full, int width, int height, i
     return unpack_rows_device((const float4*)d_packed, (float4*)d_full, width, height, tile_rows, rank, world, (cudaStream_t)stream);
 }
 
-int yrt_render(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height, int samples, float* rgba_out,
-               yrt_stats* stats) {
-    if (!scn || scn->dev.empty() || !rgba_out) { set_error("yrt_render: bad arguments"); return YRT_ERR_INVALID; }
+static int render_impl(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height, int samples, float* rgba_out,
+                       uint8_t* ldr_out, yrt_stats* stats) {
+    if (!scn || scn->dev.empty() || (!rgba_out && !ldr_out)) { set_error("yrt_render: bad arguments"); return YRT_ERR_INVALID; }
     RenderParams rp0;
     YRT_TRY(fill_params(cam, amb, width, height, samples, rp0));
     const int G = (int)scn->dev.size();
@@ -224,7 +235,7 @@ int yrt_render(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int wi
     if (G == 1) tile_rows = std::max(1, height);
     if (!g_gather) g_gather = new GatherState();
     GatherState& gs = *g_gather;
-    while ((int)gs.packed.size() < G) { gs.packed.push_back(new DevBuf()); gs.staged.push_back(new DevBuf()); gs.done.push_back(nullptr); }
+    while ((int)gs.packed.size() < G) { gs.packed.push_back(new DevBuf()); gs.staged.push_back(new DevBuf()); gs.done.push_back(nullptr); gs.direct.push_back(0); }
     DevScene& d0 = *scn->dev[0];
     size_t full_bytes = sizeof(float4) * (size_t)width * height;
     YRT_TRY(gs.full.alloc(full_bytes, d0.device));
@@ -240,14 +251,20 @@ int yrt_render(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int wi
         size_t bytes = sizeof(float4) * (size_t)own * width;
         int s = YRT_OK;
         float4* dst = nullptr;
+        const bool direct = G > 1 && g < (int)g_peer_ok.size() && g_peer_ok[g] && !getenv("YRT_NO_PEER_STORES");
         if (G == 1) {
             dst = gs.full.as<float4>();   // one GPU: packed order == row order
+        } else if (direct) {
+            // fused gather: this GPU's resolve kernel stores its rows straight into GPU 0's frame over NVLink
+            dst = gs.full.as<float4>();
+            rp.scatter = true;
         } else {
             s = gs.packed[g]->alloc(bytes, ds.device);
             dst = gs.packed[g]->as<float4>();
         }
         if (s == YRT_OK) s = render_rows_device(ds, rp, dst, ds.stream, stats ? &dstats[g] : nullptr, false);
-        if (s == YRT_OK && G > 1 && g > 0 && own > 0) {
+        gs.direct[g] = direct ? 1 : 0;
+        if (s == YRT_OK && G > 1 && g > 0 && own > 0 && !direct) {
             s = gs.staged[g]->alloc(bytes, d0.device);
             if (s == YRT_OK) {
                 cudaSetDevice(ds.device);
@@ -281,16 +298,23 @@ int yrt_render(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int wi
     cudaEvent_t g0 = nullptr, g1 = nullptr;
     if (stats) { cudaEventCreate(&g0); cudaEventCreate(&g1); }
     if (G > 1) {
-        for (int g = 1; g < G; g++) YRT_CUDA(cudaStreamWaitEvent(s0, gs.done[g], 0));
+        for (int g = 0; g < G; g++) YRT_CUDA(cudaStreamWaitEvent(s0, gs.done[g], 0));
         if (stats) cudaEventRecord(g0, s0);
         for (int g = 0; g < G; g++) {
+            if (gs.direct[g]) continue;   // rows already in place
             const float4* src = g == 0 ? gs.packed[0]->as<float4>() : gs.staged[g]->as<float4>();
             if (rows_owned(height, tile_rows, g, G) > 0)
                 YRT_TRY(unpack_rows_device(src, gs.full.as<float4>(), width, height, tile_rows, g, G, s0));
         }
         if (stats) cudaEventRecord(g1, s0);
     }
-    YRT_CUDA(cudaMemcpyAsync(rgba_out, gs.full.p, full_bytes, cudaMemcpyDeviceToHost, s0));
+    if (rgba_out) YRT_CUDA(cudaMemcpyAsync(rgba_out, gs.full.p, full_bytes, cudaMemcpyDeviceToHost, s0));
+    if (ldr_out) {   // tonemap on the device: a quarter of the bytes cross to the host
+        size_t npx = (size_t)width * height;
+        YRT_TRY(gs.ldr.alloc(4 * npx, d0.device));
+        YRT_TRY(tonemap_launch(gs.full.as<float4>(), gs.ldr.as<uint8_t>(), npx, s0));
+        YRT_CUDA(cudaMemcpyAsync(ldr_out, gs.ldr.p, 4 * npx, cudaMemcpyDeviceToHost, s0));
+    }
     YRT_CUDA(cudaStreamSynchronize(s0));
     if (stats) {
         // every device is idle now (GPU 0 waited for all of them): collect per-device stats
@@ -321,6 +345,18 @@ int yrt_render(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int wi
         cudaEventDestroy(g0); cudaEventDestroy(g1);
     }
     return YRT_OK;
+}
+
+int yrt_render(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height, int samples, float* rgba_out,
+               yrt_stats* stats) {
+    if (!rgba_out) { set_error("yrt_render: rgba_out is null"); return YRT_ERR_INVALID; }
+    return render_impl(scn, cam, amb, width, height, samples, rgba_out, nullptr, stats);
+}
+
+int yrt_render_ldr(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height, int samples, uint8_t* rgba8_out,
+                   float* rgba_out, yrt_stats* stats) {
+    if (!rgba8_out) { set_error("yrt_render_ldr: rgba8_out is null"); return YRT_ERR_INVALID; }
+    return render_impl(scn, cam, amb, width, height, samples, rgba_out, rgba8_out, stats);
 }
 
 int yrt_trace_primary(yrt_scene* scn, const yrt_camera* cam, int width, int height, int samples, int32_t* ids_out, float* dist_out,

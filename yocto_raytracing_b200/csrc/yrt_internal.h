@@ -144,6 +144,7 @@ int intersect_rays_device(DevScene& ds, const float* h_rays, int64_t n, bool any
                           float* h_uv, uint8_t* h_occ);
 int unpack_rows_device(const float4* d_packed, float4* d_full, int width, int height, int tile_rows, int rank,
                        int world, cudaStream_t st);
+int tonemap_launch(const float4* d_in, uint8_t* d_out, size_t n, cudaStream_t st);
 int tonemap_device(int device, const float* h_rgba, int width, int height, uint8_t* h_out);
 
 camera_k make_camera_k(const yrt_camera* cam);

@@ -810,6 +810,13 @@ int unpack_rows_device(const float4* d_packed, float4* d_full, int width, int he
     return YRT_OK;
 }
 
+int tonemap_launch(const float4* d_in, uint8_t* d_out, size_t n, cudaStream_t st) {
+    if (n == 0) return YRT_OK;
+    k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_in, (uchar4*)d_out, n);
+    YRT_CUDA(cudaGetLastError());
+    return YRT_OK;
+}
+
 int tonemap_device(int device, const float* h_rgba, int width, int height, uint8_t* h_out) {
     YRT_CUDA(cudaSetDevice(device));
     size_t n = (size_t)width * height;

@@ -87,6 +87,16 @@ class Scene:
                                      C.c_void_p(out.ctypes.data), C.byref(st) if st is not None else None))
         return out, st
 
+    def render_ldr(self, width: int, height: int, samples: int, amb=0.1, want_stats: bool = False):
+        """raytrace() + tonemap(hdr, 0, false) on the device -> uint8 (height, width, 4), what the reference saves as PNG."""
+        out = np.empty((height, width, 4), np.uint8)
+        a = np.broadcast_to(np.asarray(amb, np.float32), (3,))
+        amb3 = (C.c_float * 3)(*[float(x) for x in a])
+        st = Stats() if want_stats else None
+        check(_lib.load().yrt_render_ldr(self._h, C.byref(self._cam), amb3, int(width), int(height), int(samples),
+                                         C.c_void_p(out.ctypes.data), None, C.byref(st) if st is not None else None))
+        return out, st
+
     def raytrace(self, amb: float, resolution: int, samples: int) -> np.ndarray:
         """image4f raytrace(scn, {amb,amb,amb}, resolution, samples) — src/raytrace.cpp:213."""
         w, h = self.image_size(resolution)
