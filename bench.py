@@ -336,7 +336,7 @@ def run_b200(args):
     achieved_tflops = rays_per_launch * ALG_FLOPS_PER_RAY / (any_launch_ms * 1e-3) / 1e12
     cache_gbs = rays_per_launch * ALG_BYTES_PER_RAY / (any_launch_ms * 1e-3) / 1e9
     roofline = {
-        "kernel": "k_trace_any_lights", "bound": "fp32-issue (neither hbm nor tensor: SURVEY 8d)", "achieved": achieved_tflops,
+        "kernel": "k_trace_any_lights", "bound": "fp32", "bound_note": "FP32 instruction issue — neither hbm nor tensor (SURVEY 8d): the 3 MB scene is cache resident and nothing is a contraction", "achieved": achieved_tflops,
         "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,
         "peak_source": f"148 SMs x 128 FP32 lanes x 2 flop x {sm_mhz:.0f} MHz (SM clock sampled during the timed region)",
         "traffic": NCU_DRAM_BYTES_PER_ANY_LAUNCH, "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/",

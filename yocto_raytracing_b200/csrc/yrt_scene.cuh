@@ -64,6 +64,19 @@ YRT_HD float4 ld4(const float4* p) {
 #endif
 }
 
+// two adjacent 16-byte records, optionally with ONE 256-bit load (LDG.E.256, new on sm_100; p 32-byte aligned).
+// Measured (profiles/r1_experiments.md): 16.78 ms with LDG.256 vs 16.63 ms with 2 x LDG.128 per pair, so off by default.
+YRT_HD void ld8(const float4* p, float4& a, float4& b) {
+#if defined(__CUDA_ARCH__) && defined(YRT_LDG256)
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+#else
+    a = ld4(p);
+    b = ld4(p + 1);
+#endif
+}
+
 YRT_HD float4 mk4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 YRT_HD vec3 xyz(const float4& q) { return mk3(q.x, q.y, q.z); }
 

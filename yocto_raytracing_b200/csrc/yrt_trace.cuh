@@ -128,7 +128,9 @@ struct Tracer {
     // one internal node: test both child boxes against the current ray and current tmax, near child first
     YRT_HD void visit(const SceneView& sv, int* stack, TraceCounters* ctr) {
         const float4* n = sv.nodes + 4 * (size_t)cur;
-        float4 q0 = ld4(n), q1 = ld4(n + 1), q2 = ld4(n + 2), q3 = ld4(n + 3);
+        float4 q0, q1, q2, q3;
+        ld8(n, q0, q1);          // a 64-byte node = two 256-bit loads
+        ld8(n + 2, q2, q3);
         float e0, e1;
         bool h0, h1;
         if (EXACT) {
@@ -198,7 +200,9 @@ struct Tracer {
             // TLAS leaf: enter its first instance, keep the rest for later
             if (count > 1) stack[sp++] = make_leaf_ref(first + 1, count - 1);
             const float4* ir = sv.inst_recs + 4 * (size_t)first;
-            float4 q0 = ld4(ir), q1 = ld4(ir + 1), q2 = ld4(ir + 2), q3 = ld4(ir + 3);
+            float4 q0, q1, q2, q3;
+            ld8(ir, q0, q1);
+            ld8(ir + 2, q2, q3);
             frame3 f;
             f.x = xyz(q0); f.y = xyz(q1); f.z = xyz(q2); f.o = xyz(q3);
             o = transform_point_inverse(f, wo);              // transform_ray_inverse, scene.cpp:468
