@@ -235,6 +235,13 @@ def test_drop_in_cli_matches_reference_cli(gpu, tmp_path):
         assert ia.shape == ib.shape
         within1, ident, mx = ldr_stats(ia, ib)
         assert within1 >= PIXEL_BAR, (sc.name, within1, ident, mx)
+    # additive flag --gpus: same PNG from 2 GPUs (interleaved rows, peer stores into GPU 0's frame) as from 1
+    if gpu.device_count() >= 2:
+        c = os.path.join(cwd, "ours2.png")
+        r2 = subprocess.run([ours] + args + ["--gpus", "2", "--stats", "-o", c, os.path.basename(obj)], cwd=cwd, capture_output=True, text=True)
+        assert r2.returncode == 0, r2.stdout + r2.stderr
+        assert "on 2 GPU(s)" in r2.stdout
+        assert np.array_equal(np.array(Image.open(c)), ia)
     # unknown option: usage + non-zero exit like yu::cmdline (src/ext/yocto_utils.h:1157-1174)
     assert subprocess.run([ours, "--bogus", "x.obj"], capture_output=True).returncode != 0
 
