@@ -16,7 +16,7 @@
 
 namespace yrt {
 
-#define YRT_LEAF_SIZE_BLAS 4   /* the reference also stops at <= 4 prims (scene.cpp:583) */
+#define YRT_LEAF_SIZE_BLAS 3   /* subtrees of <= 3 elements become one leaf (measured 1..5: 17.89 / 16.59 / 16.41 / 16.62 / 16.64 ms; the reference stops at <= 4, scene.cpp:583) */
 #define YRT_SIZE_BITS_BLAS 0
 #define YRT_SIZE_BITS_TLAS 3
 #define YRT_LEAF_SIZE_TLAS 1   /* one instance per TLAS leaf: its world box is tested before the ray is transformed */
