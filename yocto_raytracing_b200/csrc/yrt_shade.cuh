@@ -176,28 +176,34 @@ YRT_HD void shade_lights(const SceneView& sv, const HitAttr& a, const Material& 
         vec3 l, ke;
         float r;
         light_vector(sv, k, a.p, l, r, ke);
-        vec3 v = normalize(ray_o - a.p);                     // raytrace.cpp:147
-        vec3 h = normalize(v + l);
         vec3 kd = m.kd, ks = m.ks;
         if (m.kd_tex >= 0) kd = kd * tkd;                    // raytrace.cpp:153-157
         if (m.ks_tex >= 0) ks = ks * tks;
         vec3 ld = kd * (ke / (r * r));                       // raytrace.cpp:159-160
         vec3 ls = ks * (ke / (r * r));
-        // ks == (0,0,0) exactly (most materials of the instance scenes): ls = +0 * finite = +0 whatever the lobe
-        // is — the lobe base is in [0, 1+ulp] or NaN-free by construction only when it is finite, so the powf is
-        // skipped only if the base is finite and non-negative (then powf(base, ns > 0) is finite and ld + 0 == ld)
+        // ks == (0,0,0) exactly (most materials of the instance scenes): ls = +0 * (finite lobe) = +0 and ld + 0 == ld,
+        // so the half vector and the powf are skipped.  The lobe is finite whenever ld is: its base n.h (or
+        // sqrt(1-|n.h|)) of finite unit vectors lies in [0, 1 + 3e-7] and ns <= 1e6; and if n, l or v is not finite,
+        // ld is NaN already and so is the sum, with or without the lobe.
         const bool no_spec = ks.x == 0.0f && ks.y == 0.0f && ks.z == 0.0f && m.ns > 0.0f && m.ns <= 1e6f;
         if (a.kind == 1) {                                   // shp->lines.size() > 0, raytrace.cpp:162-175
-            float prodnl = dot(a.n, l), prodnh = dot(a.n, h);
+            float prodnl = dot(a.n, l);
             if (prodnl < 0.0f) prodnl = -prodnl;
-            if (prodnh < 0.0f) prodnh = -prodnh;
-            float sinnl = sqrtf(1.0f - prodnl), sinnh = sqrtf(1.0f - prodnh);
-            ld = ld * sinnl;
-            if (!(no_spec && sinnh >= 0.0f && sinnh <= 1.0000005f)) ls = ls * powf(sinnh, m.ns);   // (1+5e-7)^1e6 < 2: finite
+            ld = ld * sqrtf(1.0f - prodnl);
+            if (!no_spec) {
+                vec3 v = normalize(ray_o - a.p);             // raytrace.cpp:147
+                vec3 h = normalize(v + l);
+                float prodnh = dot(a.n, h);
+                if (prodnh < 0.0f) prodnh = -prodnh;
+                ls = ls * powf(sqrtf(1.0f - prodnh), m.ns);
+            }
         } else {                                             // raytrace.cpp:176-180
             ld = ld * rmax(0.0f, dot(a.n, l));
-            float base = rmax(0.0f, dot(a.n, h));
-            if (!(no_spec && base >= 0.0f && base <= 1.0000005f)) ls = ls * powf(base, m.ns);
+            if (!no_spec) {
+                vec3 v = normalize(ray_o - a.p);             // raytrace.cpp:147
+                vec3 h = normalize(v + l);
+                ls = ls * powf(rmax(0.0f, dot(a.n, h)), m.ns);
+            }
         }
         c = c + (ld + ls);                                   // raytrace.cpp:182
     }
