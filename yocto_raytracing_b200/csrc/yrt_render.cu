@@ -6,12 +6,15 @@
 // a batch is a run of image rows, all samples.  Per batch:
 //   k_trace_closest<primary>  rays generated in-kernel (eval_camera) -> hit + world position
 //   wave loop (depth = reflection recursion level):
-//     k_trace_any             one shadow ray per (hit, light), light-major so a warp shares a light
+//     k_trace_any_lights      one hit per lane, lights walked in order (a warp traces towards one light at a time)
 //     k_shade                 Blinn-Phong / hair shading in light order; reflective hits push
 //                             {c, kr, la} on a per-slot stack and enqueue the mirror ray (compacted
 //                             queue); finished paths unwind the stack and write their radiance
 //     k_trace_closest<queue>  next wave's rays
-//   k_resolve                 ordered per-pixel sum over (jj,ii), divide by N*N, alpha = 1
+//   k_resolve                 ordered per-pixel sum over (jj,ii), divide by N*N, alpha = 1; in a multi-GPU frame it stores
+//                             straight into rank 0's frame (peer memory) — the gather is fused into it
+// A rank's share of a frame runs as two such pipelines on two streams (kernel tails overlap).  Measured alternatives
+// kept behind switches: YRT_PACKET (warp-cooperative traversal), YRT_FUSE_SHADE (k_shadow_shade), YRT_SPECULATE.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
