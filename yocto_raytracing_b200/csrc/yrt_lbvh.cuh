@@ -333,8 +333,8 @@ YRT_HD void emit_item(const LbvhArrays& a, int i) {
     box_center_half(l1.x, h1.x, ce1.x, ha1.x); box_center_half(l1.y, h1.y, ce1.y, ha1.y); box_center_half(l1.z, h1.z, ce1.z, ha1.z);
     n[0] = mk4(ce0.x, ce0.y, ce0.z, int_as_float(child_ref_(a, c0)));
     n[1] = mk4(ha0.x, ha0.y, ha0.z, int_as_float(child_ref_(a, c1)));
-    n[2] = mk4(ce1.x, ce1.y, ce1.z, half_sum(ha0.x, ha0.y, ha0.z));
-    n[3] = mk4(ha1.x, ha1.y, ha1.z, half_sum(ha1.x, ha1.y, ha1.z));
+    n[2] = mk4(ce1.x, ce1.y, ce1.z, 0.f);
+    n[3] = mk4(ha1.x, ha1.y, ha1.z, 0.f);
     int first = a.range_first[i], last = a.range_last[i];
     int s = a.seg_of[a.order[first]];
     if (s == a.seg_of[a.order[last]] && first == a.seg_first[s] && last == a.seg_first[s + 1] - 1) {

@@ -176,23 +176,24 @@ YRT_HD bool intersect_check_bbox(const vec3& o, const vec3& invd, const raysigns
     return tmin <= tmax;
 }
 
-// Slab test used by the traversal.  Nodes store each child box as centre c, half-extent h (rounded up, so
-// [c-h, c+h] contains the true box) and hs >= hx+hy+hz:  t0 = (c-o)*invd - h*|invd|,  t1 = (c-o)*invd + h*|invd|
-// needs NO per-axis near/far select and is 9 FFMA per box on the FMA pipe; only the two max3/min3 reductions
-// and the compare stay on the ALU pipe.  The first version (FADD+FMUL, FSETP+FSEL ternaries, 6 selects per
-// box) was ALU-pipe bound: ALU 70 %, FMA 27 % busy (profiles/).
-// Conservative by construction.  With u = 2^-24: tc = fl(c*invd - fl(o*invd)) is off by at most
-// u(|o invd| + |tc|) and |tc| <= |t| + h|invd|; the second FFMA adds u|t|.  So every computed t is within
-// u(M + S) + 2u|t| of the exact slab distance of the stored box, M = max_a |o_a invd_a| (per ray and space),
-// S = sum_a h_a |invd_a| <= hs * max_a |invd_a| (per box).  The reference accepts tmin <= tmax(1+4u) on values
-// carrying 2u relative error, i.e. exact T0 <= T1(1+9u); chaining the bounds,
-//       tmin <= tmax (1+16u) + 8u M + 8u max|invd| hs
-// accepts a SUPERSET of what scene.cpp:371-383 accepts for the true box: a box the reference would enter is
-// never culled, and what is found inside is decided by the exact primitive tests, so hits are unchanged
+// Slab test used by the traversal.  Nodes store each child box as centre c and half-extent h' (inflated at build
+// time, see box_center_half):  t0 = (c-o)*invd - h'*|invd|,  t1 = (c-o)*invd + h'*|invd|  needs NO per-axis near/far
+// select and is 9 FFMA per box on the FMA pipe; only the two max3/min3 reductions and the compare stay on the ALU
+// pipe.  The first version (FADD+FMUL, FSETP+FSEL ternaries, 6 selects per box) was ALU-pipe bound: ALU 70 %, FMA
+// 27 % busy (profiles/).
+// Conservative by construction.  With u = 2^-24: tc = fl(c*invd - fl(o*invd)) is off by at most u(|o invd| + |tc|) and
+// |tc| <= |t| + h'|invd|; the second FFMA adds u|t|.  h' = h(1+16u) exceeds the true half-extent h by more than the
+// 4u h it needs to (a) cover the rounding of c and h themselves and (b) absorb the u h'|invd| term: every computed near
+// (far) distance is at most u M + 2u|t| above (below) the exact slab distance of a box that still CONTAINS the true
+// box, M = max_a |o_a invd_a| per ray and space.  The reference accepts tmin <= tmax(1+4u) on values carrying 2u
+// relative error, i.e. exact T0 <= T1(1+9u); chaining the bounds,
+//       tmin <= tmax (1+16u) + 8u M
+// accepts a SUPERSET of what scene.cpp:371-383 accepts for the true box: a box the reference would enter is never
+// culled, and what is found inside is decided by the exact primitive tests, so hits are unchanged
 // (tests/test_host_emu.py audits every box test against the reference's formula: 0 false rejects).
-// NaN (inf-inf for direction components that are exactly 0) is dropped by FMNMX like in the reference's
-// ternaries: that axis does not constrain (|invd| = inf keeps h|invd| = inf or NaN, never a finite bound).
-struct slabray { vec3 invd, noi, ainv; float pad, kh; };
+// NaN (inf-inf for direction components that are exactly 0) is dropped by FMNMX like in the reference's ternaries:
+// that axis does not constrain (|invd| = inf keeps h'|invd| = inf or NaN, never a finite bound).
+struct slabray { vec3 invd, noi, ainv; float pad; };
 
 YRT_HD slabray make_slabray(const vec3& o, const vec3& invd) {
     slabray r;
@@ -201,12 +202,11 @@ YRT_HD slabray make_slabray(const vec3& o, const vec3& invd) {
     r.ainv = mk3(fabsf(invd.x), fabsf(invd.y), fabsf(invd.z));
     float m = fmaxf(fmaxf(fmaxf(fabsf(o.x) * r.ainv.x, fabsf(o.y) * r.ainv.y), fabsf(o.z) * r.ainv.z), 0.0f);
     r.pad = m * 4.7683716e-7f;                                              // 8u M
-    r.kh = fminf(fmaxf(fmaxf(r.ainv.x, r.ainv.y), r.ainv.z), 3e30f) * 4.7683716e-7f;   // 8u max|invd|, finite: 0 * kh stays 0
     return r;
 }
 
 YRT_HD bool slab_test_ch(const slabray& r, float rtmin, float rtmax, float cx, float cy, float cz, float hx, float hy,
-                         float hz, float hs, float& tenter) {
+                         float hz, float& tenter) {
     float tcx = fmaf(cx, r.invd.x, r.noi.x), tcy = fmaf(cy, r.invd.y, r.noi.y), tcz = fmaf(cz, r.invd.z, r.noi.z);
     float t0x = fmaf(hx, -r.ainv.x, tcx), t1x = fmaf(hx, r.ainv.x, tcx);
     float t0y = fmaf(hy, -r.ainv.y, tcy), t1y = fmaf(hy, r.ainv.y, tcy);
@@ -214,18 +214,17 @@ YRT_HD bool slab_test_ch(const slabray& r, float rtmin, float rtmax, float cx, f
     float tmin = fmaxf(t0z, fmaxf(t0y, fmaxf(t0x, rtmin)));
     float tmax = fminf(t1z, fminf(t1y, fminf(t1x, rtmax)));
     tenter = tmin;
-    return tmin <= fmaf(hs, r.kh, fmaf(tmax, 1.00000095f, r.pad));
+    return tmin <= fmaf(tmax, 1.00000095f, r.pad);
 }
 
-// centre / half-extent of a box, half-extent rounded up so that [c-h, c+h] contains [lo, hi]
+// centre / half-extent of a box; the half-extent is inflated by 1 + 16u: [c-h', c+h'] contains [lo, hi] with the
+// margin the slab test's error analysis needs (see slab_test_ch)
 YRT_HD void box_center_half(float lo, float hi, float& c, float& h) {
     c = (lo + hi) * 0.5f;
     float d = fmaxf(hi - c, c - lo);
-    h = d * 1.0000005f;   // d carries one rounding (<= u relative); 1 + 8u covers it
+    h = d * 1.00000095f;
     if (!(h >= 0.f)) h = 0.f;
 }
-// upper bound of hx + hy + hz
-YRT_HD float half_sum(float hx, float hy, float hz) { return (hx + hy + hz) * 1.0000005f; }
 
 // ---- camera: src/raytrace.cpp:6-37 ---------------------------------------------------------
 // h = 2*focus*tanf(fovy/2) and w = h*aspect are computed once on the host (raytrace.cpp:21-22).

@@ -3,7 +3,7 @@
 // All records are multiples of 16 bytes and are fetched with 128-bit loads.
 //   BVH node (64 B, TLAS and BLAS alike; two-child-box layout, boxes as centre / half-extent):
 //     q0 = child0.centre.xyz | child0 ref  q1 = child0.half.xyz | child1 ref
-//     q2 = child1.centre.xyz | hs0         q3 = child1.half.xyz | hs1      (hs >= hx+hy+hz, slab-test pad)
+//     q2 = child1.centre.xyz | -           q3 = child1.half.xyz | -        (half-extents inflated by 1 + 16u)
 //   prim record (48 B, in BLAS leaf order, all shapes concatenated):
 //     triangle: q0 = v0.xyz | ei     q1 = v1.xyz | -      q2 = v2.xyz | -
 //     line:     q0 = v0.xyz | ei     q1 = v1.xyz | r0     q2 = r1, -, -, -

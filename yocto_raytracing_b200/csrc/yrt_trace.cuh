@@ -140,8 +140,8 @@ struct Tracer {
             h0 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, q0.x - q1.x, q0.y - q1.y, q0.z - q1.z, q0.x + q1.x, q0.y + q1.y, q0.z + q1.z, e0);
             h1 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, q2.x - q3.x, q2.y - q3.y, q2.z - q3.z, q2.x + q3.x, q2.y + q3.y, q2.z + q3.z, e1);
         } else {
-            h0 = slab_test_ch(sr, tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.w, e0);
-            h1 = slab_test_ch(sr, tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, q3.w, e1);
+            h0 = slab_test_ch(sr, tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, e0);
+            h1 = slab_test_ch(sr, tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, e1);
         }
         if (ctr) {   // host-side audit against the reference's own test
             ctr->box_tests += 2;
