@@ -211,7 +211,20 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     tr = args.tile_rows if multi else H
 
-    shared = D.SharedFrame(W, H) if args.gather == "ipc" else None
+    shared = None
+    if args.gather == "ipc":
+        # CUDA IPC can be unavailable (container policy); every rank must take the same path
+        ok = torch.ones(1, device=dev)
+        try:
+            shared = D.SharedFrame(W, H)
+        except Exception as e:      # noqa: BLE001
+            ok.zero_()
+            print(f"[bench] rank {rank}: shared frame over CUDA IPC unavailable ({e}); falling back to the NCCL gather", file=sys.stderr)
+        if multi:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            shared = None
+            args.gather = "nccl"
 
     def frame(want_stats=True):
         if shared is not None:
