@@ -324,3 +324,21 @@ def test_many_samples_per_pixel(gpu, oracle_mod):
     assert st.primary_rays == w * h * 64
     within1, ident, mx = ldr_stats(oracle_mod.tonemap(img), oracle_mod.tonemap(ref))
     assert within1 >= PIXEL_BAR
+
+
+@pytest.mark.parametrize("name", ["simple", "basic", "refl", "instance10000"])
+def test_run_sh_configs_full_size(gpu, oracle_mod, name):
+    """The reference's own configs (run.sh: -r 720 -s 3 -> 1280x720, 9 spp) on the reference's scenes, at full size:
+    GPU image vs the C oracle (pinned bit-exactly to the reference) — pixels within 1/255 on >= 99.9 %, ray counts equal."""
+    import os
+    flat, _ = load_golden(name)
+    w, h, s = flat.image_width(720), 720, 3
+    assert w == 1280
+    ref, cnt = oracle_mod.OracleScene(flat).render(w, h, s, 0.1, max_depth=16, threads=os.cpu_count() or 4)
+    with gpu.Scene(flat) as scn:
+        img, st = scn.render(w, h, s, 0.1)
+    within1, ident, mx = ldr_stats(oracle_mod.tonemap(img), oracle_mod.tonemap(ref))
+    assert within1 >= PIXEL_BAR, (name, within1, ident, mx)
+    assert st.primary_rays == cnt["primary_rays"] == w * h * 9
+    assert abs(st.shadow_rays - cnt["shadow_rays"]) <= 1e-5 * cnt["shadow_rays"] + 4
+    assert abs(st.reflection_rays - cnt["reflection_rays"]) <= 1e-5 * cnt["reflection_rays"] + 4
