@@ -104,15 +104,24 @@ class SharedFrame:
         self._ptr = C.c_void_p()
         self._owner = self.rank == 0
         handle = C.create_string_buffer(64)
+        err = None
         if self._owner:
-            check(lib.yrt_frame_alloc(width, height, C.byref(self._ptr)))
-            if self.world > 1:
-                check(lib.yrt_frame_export(self._ptr, handle))
+            try:
+                check(lib.yrt_frame_alloc(width, height, C.byref(self._ptr)))
+                if self.world > 1:
+                    check(lib.yrt_frame_export(self._ptr, handle))
+            except Exception as e:          # the other ranks are waiting in the broadcast: tell them before raising
+                err = e
         if self.world > 1:
-            box = [handle.raw if self._owner else None]
+            box = [(handle.raw if err is None else None, None if err is None else str(err)) if self._owner else None]
             dist.broadcast_object_list(box, src=0, group=group)
+            raw, msg = box[0]
+            if raw is None:
+                raise err if err is not None else RuntimeError(f"rank 0 could not share the frame: {msg}")
             if not self._owner:
-                check(lib.yrt_frame_import(box[0], C.byref(self._ptr)))
+                check(lib.yrt_frame_import(raw, C.byref(self._ptr)))
+        elif err is not None:
+            raise err
         self._token = torch.zeros(1, device=torch.device("cuda", torch.cuda.current_device()))
 
     @property
