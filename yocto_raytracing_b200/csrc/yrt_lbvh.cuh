@@ -328,13 +328,10 @@ YRT_HD void emit_item(const LbvhArrays& a, int i) {
     child_box_(a, c0, l0, h0);
     child_box_(a, c1, l1, h1);
     float4* n = a.nodes + 4 * (size_t)i;
-    float4 ce0, ha0, ce1, ha1;
-    box_center_half(l0.x, h0.x, ce0.x, ha0.x); box_center_half(l0.y, h0.y, ce0.y, ha0.y); box_center_half(l0.z, h0.z, ce0.z, ha0.z);
-    box_center_half(l1.x, h1.x, ce1.x, ha1.x); box_center_half(l1.y, h1.y, ce1.y, ha1.y); box_center_half(l1.z, h1.z, ce1.z, ha1.z);
-    n[0] = mk4(ce0.x, ce0.y, ce0.z, int_as_float(child_ref_(a, c0)));
-    n[1] = mk4(ha0.x, ha0.y, ha0.z, int_as_float(child_ref_(a, c1)));
-    n[2] = mk4(ce1.x, ce1.y, ce1.z, 0.f);
-    n[3] = mk4(ha1.x, ha1.y, ha1.z, 0.f);
+    nodebox b0, b1;
+    box_center_half(l0.x, h0.x, b0.cx, b0.hx); box_center_half(l0.y, h0.y, b0.cy, b0.hy); box_center_half(l0.z, h0.z, b0.cz, b0.hz);
+    box_center_half(l1.x, h1.x, b1.cx, b1.hx); box_center_half(l1.y, h1.y, b1.cy, b1.hy); box_center_half(l1.z, h1.z, b1.cz, b1.hz);
+    node_pack(n, b0, b1, child_ref_(a, c0), child_ref_(a, c1));
     int first = a.range_first[i], last = a.range_last[i];
     int s = a.seg_of[a.order[first]];
     if (s == a.seg_of[a.order[last]] && first == a.seg_first[s] && last == a.seg_first[s + 1] - 1) {

@@ -56,10 +56,10 @@ __device__ __forceinline__ void trace_packet(const SceneView& sv, const ray3& wr
             const float4* n = sv.nodes + 4 * (size_t)cur;
             float4 q0 = ld4(n), q1 = ld4(n + 1), q2 = ld4(n + 2), q3 = ld4(n + 3);   // same address in every lane: one broadcast each
             float e0, e1;
-            bool h0 = slab_test_ch(sr, tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, e0);
-            bool h1 = slab_test_ch(sr, tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, e1);
+            bool h0, h1;
+            slab_test_node(sr, tmin, tmax, q0, q1, q2, h0, h1, e0, e1);
             unsigned m0 = __ballot_sync(FULL, h0), m1 = __ballot_sync(FULL, h1);
-            int c0 = float_as_int(q0.w), c1 = float_as_int(q1.w);
+            int c0 = float_as_int(q3.x), c1 = float_as_int(q3.y);
             if (m0 && m1) {
                 bool swap = false;
                 if (!ANY) {   // near child first, by majority of the lanes that enter both (else of all entering lanes)

@@ -78,6 +78,61 @@ YRT_HD void ld8(const float4* p, float4& a, float4& b) {
 }
 
 YRT_HD float4 mk4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+
+// ---- 64-byte traversal node ------------------------------------------------------------------
+//   q0 = (c0.x, c0.y, c1.x, c1.y)   q1 = (h0.x, h0.y, h1.x, h1.y)   q2 = (c0.z, c1.z, h0.z, h1.z)   q3 = (ref0, ref1, -, -)
+// The two child boxes are interleaved so that every FMA of the slab test has a partner with which it shares one packed
+// FFMA2 (sm_100: two fp32 FMAs per issue slot on an aligned register pair): x and y of one child pair up against the
+// ray's (invd.x, invd.y) / (noi.x, noi.y) / (ainv.x, ainv.y) pairs, and the z of child 0 pairs with the z of child 1
+// against a broadcast scalar.  20 FFMA per node become 10 FFMA2; the values are the same IEEE FMAs, so the accept
+// decisions are bit-identical to slab_test_ch on the same boxes (the host build below uses exactly that).
+struct nodebox { float cx, cy, cz, hx, hy, hz; };
+YRT_HD nodebox node_child(const float4& q0, const float4& q1, const float4& q2, int k) {
+    nodebox b;
+    if (k == 0) { b.cx = q0.x; b.cy = q0.y; b.cz = q2.x; b.hx = q1.x; b.hy = q1.y; b.hz = q2.z; }
+    else        { b.cx = q0.z; b.cy = q0.w; b.cz = q2.y; b.hx = q1.z; b.hy = q1.w; b.hz = q2.w; }
+    return b;
+}
+YRT_HD void node_pack(float4* n, const nodebox& b0, const nodebox& b1, int ref0, int ref1) {
+    n[0] = mk4(b0.cx, b0.cy, b1.cx, b1.cy);
+    n[1] = mk4(b0.hx, b0.hy, b1.hx, b1.hy);
+    n[2] = mk4(b0.cz, b1.cz, b0.hz, b1.hz);
+    n[3] = mk4(int_as_float(ref0), int_as_float(ref1), 0.f, 0.f);
+}
+
+#if defined(__CUDA_ARCH__)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+#endif
+
+// both children of one node against one ray; e0/e1 = entry distances (ordering only)
+YRT_HD void slab_test_node(const slabray& r, float rtmin, float rtmax, const float4& q0, const float4& q1, const float4& q2,
+                           bool& h0, bool& h1, float& e0, float& e1) {
+#if defined(__CUDA_ARCH__) && !defined(YRT_NO_FFMA2)
+    f32x2 ixy = pk2(r.invd.x, r.invd.y), nxy = pk2(r.noi.x, r.noi.y), axy = pk2(r.ainv.x, r.ainv.y), naxy = pk2(-r.ainv.x, -r.ainv.y);
+    f32x2 izz = pk2(r.invd.z, r.invd.z), nzz = pk2(r.noi.z, r.noi.z), azz = pk2(r.ainv.z, r.ainv.z), nazz = pk2(-r.ainv.z, -r.ainv.z);
+    f32x2 tc0 = fma2(pk2(q0.x, q0.y), ixy, nxy), tc1 = fma2(pk2(q0.z, q0.w), ixy, nxy), tcz = fma2(pk2(q2.x, q2.y), izz, nzz);
+    f32x2 hh0 = pk2(q1.x, q1.y), hh1 = pk2(q1.z, q1.w), hhz = pk2(q2.z, q2.w);
+    f32x2 lo0 = fma2(hh0, naxy, tc0), hi0 = fma2(hh0, axy, tc0);
+    f32x2 lo1 = fma2(hh1, naxy, tc1), hi1 = fma2(hh1, axy, tc1);
+    f32x2 loz = fma2(hhz, nazz, tcz), hiz = fma2(hhz, azz, tcz);
+    float t0x0, t0y0, t1x0, t1y0, t0x1, t0y1, t1x1, t1y1, t0z0, t0z1, t1z0, t1z1;
+    upk2(lo0, t0x0, t0y0); upk2(hi0, t1x0, t1y0); upk2(lo1, t0x1, t0y1); upk2(hi1, t1x1, t1y1);
+    upk2(loz, t0z0, t0z1); upk2(hiz, t1z0, t1z1);
+    float tmin0 = fmaxf(t0z0, fmaxf(t0y0, fmaxf(t0x0, rtmin))), tmax0 = fminf(t1z0, fminf(t1y0, fminf(t1x0, rtmax)));
+    float tmin1 = fmaxf(t0z1, fmaxf(t0y1, fmaxf(t0x1, rtmin))), tmax1 = fminf(t1z1, fminf(t1y1, fminf(t1x1, rtmax)));
+    float lim0, lim1;
+    upk2(fma2(pk2(tmax0, tmax1), pk2(1.00000095f, 1.00000095f), pk2(r.pad, r.pad)), lim0, lim1);
+    e0 = tmin0; e1 = tmin1;
+    h0 = tmin0 <= lim0; h1 = tmin1 <= lim1;
+#else
+    h0 = slab_test_ch(r, rtmin, rtmax, q0.x, q0.y, q2.x, q1.x, q1.y, q2.z, e0);
+    h1 = slab_test_ch(r, rtmin, rtmax, q0.z, q0.w, q2.y, q1.z, q1.w, q2.w, e1);
+#endif
+}
+
 YRT_HD vec3 xyz(const float4& q) { return mk3(q.x, q.y, q.z); }
 
 // ---- what a kernel sees ------------------------------------------------------------------

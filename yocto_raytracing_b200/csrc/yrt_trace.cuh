@@ -137,23 +137,24 @@ struct Tracer {
             // rays (nearly) parallel to an axis plane: |invd| is huge there and so is the per-box pad of the fused
             // test (it would accept half the scene); they take the reference's own formula on the stored box instead
             raysigns sgn = signs_of(sr.invd);
-            h0 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, q0.x - q1.x, q0.y - q1.y, q0.z - q1.z, q0.x + q1.x, q0.y + q1.y, q0.z + q1.z, e0);
-            h1 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, q2.x - q3.x, q2.y - q3.y, q2.z - q3.z, q2.x + q3.x, q2.y + q3.y, q2.z + q3.z, e1);
+            nodebox b0 = node_child(q0, q1, q2, 0), b1 = node_child(q0, q1, q2, 1);
+            h0 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, b0.cx - b0.hx, b0.cy - b0.hy, b0.cz - b0.hz, b0.cx + b0.hx, b0.cy + b0.hy, b0.cz + b0.hz, e0);
+            h1 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, b1.cx - b1.hx, b1.cy - b1.hy, b1.cz - b1.hz, b1.cx + b1.hx, b1.cy + b1.hy, b1.cz + b1.hz, e1);
         } else {
-            h0 = slab_test_ch(sr, tmin, tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, e0);
-            h1 = slab_test_ch(sr, tmin, tmax, q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, e1);
+            slab_test_node(sr, tmin, tmax, q0, q1, q2, h0, h1, e0, e1);
         }
         if (ctr) {   // host-side audit against the reference's own test
             ctr->box_tests += 2;
             if (top) ctr->tlas_box_tests += 2;
             float e;
             raysigns sgn = signs_of(sr.invd);   // the reference's test on the stored box [c-h, c+h] (a superset of the true box)
-            bool r0 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, q0.x - q1.x, q0.y - q1.y, q0.z - q1.z, q0.x + q1.x, q0.y + q1.y, q0.z + q1.z, e);
-            bool r1 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, q2.x - q3.x, q2.y - q3.y, q2.z - q3.z, q2.x + q3.x, q2.y + q3.y, q2.z + q3.z, e);
+            nodebox b0 = node_child(q0, q1, q2, 0), b1 = node_child(q0, q1, q2, 1);
+            bool r0 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, b0.cx - b0.hx, b0.cy - b0.hy, b0.cz - b0.hz, b0.cx + b0.hx, b0.cy + b0.hy, b0.cz + b0.hz, e);
+            bool r1 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, b1.cx - b1.hx, b1.cy - b1.hy, b1.cz - b1.hz, b1.cx + b1.hx, b1.cy + b1.hy, b1.cz + b1.hz, e);
             ctr->slab_false_rejects += (r0 && !h0) + (r1 && !h1);
             ctr->slab_extra_accepts += (!r0 && h0) + (!r1 && h1);
         }
-        int c0 = float_as_int(q0.w), c1 = float_as_int(q1.w);
+        int c0 = float_as_int(q3.x), c1 = float_as_int(q3.y);
         if (h0 && h1) {
             bool swap = (ANY && YRT_ANY_UNORDERED) ? false : (e1 < e0);   // near child first
             stack[sp++] = swap ? c0 : c1;
