@@ -14,7 +14,7 @@
 //   k_resolve                 ordered per-pixel sum over (jj,ii), divide by N*N, alpha = 1; in a multi-GPU frame it stores
 //                             straight into rank 0's frame (peer memory) — the gather is fused into it
 // A rank's share of a frame runs as two such pipelines on two streams (kernel tails overlap).  Measured alternatives
-// kept behind switches: YRT_PACKET (warp-cooperative traversal), YRT_FUSE_SHADE (k_shadow_shade), YRT_SPECULATE.
+// kept behind switches: YRT_PACKET (warp-cooperative traversal), YRT_FUSE_SHADE (k_shadow_shade).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>

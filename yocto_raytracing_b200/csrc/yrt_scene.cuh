@@ -32,7 +32,6 @@ namespace yrt {
 //   YRT_REF_SENTINEL : traversal stack marker "leave the current instance"
 #define YRT_REF_SENTINEL ((int)0x80000000)
 #define YRT_REF_DONE ((int)0x80000001)      /* traversal finished (never a valid leaf: first <= YRT_MAX_LEAF_FIRST) */
-#define YRT_REF_NONE ((int)0x80000002)      /* no reference in hand / no postponed leaf */
 #define YRT_LEAF_MAX_COUNT 8
 #define YRT_MAX_LEAF_FIRST ((1 << 28) - 2)
 #define YRT_STACK_CAP 128   /* traversal stack entries (TLAS + BLAS levels simultaneously live); checked against the built depth */

@@ -14,8 +14,8 @@
 #pragma once
 #include "yrt_scene.cuh"
 
-#ifndef YRT_SPECULATE
-#define YRT_SPECULATE 0      /* measured: slower (profiles/r1_experiments.md) */
+#ifndef YRT_VISIT_V2
+#define YRT_VISIT_V2 1
 #endif
 #ifndef YRT_ANY_UNORDERED
 #define YRT_ANY_UNORDERED 1  /* any-hit rays: skip the near/far ordering of the two children (the answer is order independent; -6 % kernel time) */
@@ -93,35 +93,33 @@ struct Tracer {
     vec3 o, d;            // ray in the current space (world, or local to instance `si`)
     slabray sr;
     float tmin, tmax;     // tmin is copied unchanged into every instance space (vmath.h:277)
-    int cur, sp, si, kind;
-    int post;             // postponed leaf (speculative look-ahead), YRT_REF_NONE if none
+    int cur, si, kind;
+    int* sp;              // next free stack slot; stack[0] holds a YRT_REF_DONE guard, so a pop needs no emptiness test
     bool top, found;
     HitRec hit;
 
-    YRT_HD void idle() { cur = YRT_REF_DONE; post = YRT_REF_NONE; sp = 0; found = false; }
-    YRT_HD bool done() const { return cur == YRT_REF_DONE && post == YRT_REF_NONE; }
+    YRT_HD bool done() const { return cur == YRT_REF_DONE; }
 
-    YRT_HD void begin(const SceneView& sv, const ray3& wray) {
+    YRT_HD void begin(const SceneView& sv, const ray3& wray, int* stack) {
         hit.si = -1; hit.prim = -1; hit.w1 = hit.w2 = 0.f; hit.dist = 0.f;
         wo = wray.o; wd = wray.d;
         wsr = make_slabray(wo, inv3(wd));
         o = wo; d = wd; sr = wsr;
         tmin = wray.tmin; tmax = wray.tmax;
-        sp = 0; si = -1; kind = 0; top = true; found = false; post = YRT_REF_NONE;
+        stack[0] = YRT_REF_DONE; sp = stack + 1;
+        si = -1; kind = 0; top = true; found = false;
         cur = sv.n_active_instances > 0 ? sv.tlas_root : YRT_REF_DONE;
     }
 
-    // pop the next reference; leaving an instance (sentinel) restores the world-space ray — unless a leaf of
-    // this instance is still postponed: then the sentinel stays and the lane holds nothing (YRT_REF_NONE)
-    YRT_HD void pop(const int* stack) {
-        for (;;) {
-            if (sp == 0) { cur = YRT_REF_DONE; break; }
-            cur = stack[sp - 1];
-            if (cur != YRT_REF_SENTINEL) { --sp; break; }
-            if (post != YRT_REF_NONE) { cur = YRT_REF_NONE; break; }
-            --sp;
+    // pop the next reference.  Leaving an instance (sentinel) restores the world-space ray and pops once more: only one
+    // sentinel is ever on the stack (instances are entered from the top level only), and the guard below everything
+    // (YRT_REF_DONE) ends the traversal without an emptiness test.
+    YRT_HD void pop() {
+        cur = *--sp;
+        if (cur == YRT_REF_SENTINEL) {
             top = true;
             o = wo; d = wd; sr = wsr;
+            cur = *--sp;
         }
     }
 
@@ -155,51 +153,47 @@ struct Tracer {
             ctr->slab_extra_accepts += (!r0 && h0) + (!r1 && h1);
         }
         int c0 = float_as_int(q3.x), c1 = float_as_int(q3.y);
+#if YRT_VISIT_V2
+        // one select for the next node, one predicated push when both children are entered, one branch for the pop
+        if (h0 || h1) {
+            int nxt = h0 ? c0 : c1;
+            if (h0 && h1) {
+                bool swap = (ANY && YRT_ANY_UNORDERED) ? false : (e1 < e0);   // near child first
+                *sp++ = swap ? c0 : c1;
+                if (ctr && (int)(sp - stack) > ctr->max_stack) ctr->max_stack = (int)(sp - stack);
+                if (swap) nxt = c1;
+            }
+            cur = nxt;
+        } else {
+            pop();
+        }
+#else
         if (h0 && h1) {
             bool swap = (ANY && YRT_ANY_UNORDERED) ? false : (e1 < e0);   // near child first
-            stack[sp++] = swap ? c0 : c1;
-            if (ctr && sp > ctr->max_stack) ctr->max_stack = sp;
+            *sp++ = swap ? c0 : c1;
+            if (ctr && (int)(sp - stack) > ctr->max_stack) ctr->max_stack = (int)(sp - stack);
             cur = swap ? c1 : c0;
         } else if (h0) {
             cur = c0;
         } else if (h1) {
             cur = c1;
         } else {
-            pop(stack);
+            pop();
         }
+#endif
     }
 
-    // internal nodes until the lane holds a leaf.  With YRT_SPECULATE the first leaf found is postponed and the
-    // lane keeps walking nodes of the same space (the rest of the warp is still in this loop anyway) until it
-    // holds a second leaf; leaf() then handles the postponed one first.
+    // internal nodes until the lane holds a leaf
     YRT_HD void nodes(const SceneView& sv, int* stack, TraceCounters* ctr) {
-#if YRT_SPECULATE
-        for (;;) {
-            while (cur >= 0) visit(sv, stack, ctr);
-            if (cur == YRT_REF_DONE || cur == YRT_REF_NONE || post != YRT_REF_NONE) break;
-            if (sp == 0 || stack[sp - 1] == YRT_REF_SENTINEL) break;   // nothing to look ahead at in this space
-            post = cur;
-            cur = stack[--sp];
-            if (cur < 0) break;   // the next entry is a leaf too
-        }
-#else
         while (cur >= 0) visit(sv, stack, ctr);
-#endif
     }
 
-    // one leaf (cur < 0 and not done); a postponed leaf goes first and what is in hand returns to the stack
+    // one leaf (cur < 0 and not done)
     YRT_HD void leaf(const SceneView& sv, int* stack, TraceCounters* ctr) {
-#if YRT_SPECULATE
-        if (post != YRT_REF_NONE) {
-            if (cur != YRT_REF_DONE && cur != YRT_REF_NONE) stack[sp++] = cur;
-            cur = post;
-            post = YRT_REF_NONE;
-        }
-#endif
         int first = leaf_first(cur), count = leaf_count(cur);
         if (top) {
             // TLAS leaf: enter its first instance, keep the rest for later
-            if (count > 1) stack[sp++] = make_leaf_ref(first + 1, count - 1);
+            if (count > 1) *sp++ = make_leaf_ref(first + 1, count - 1);
             const float4* ir = sv.inst_recs + 4 * (size_t)first;
             float4 q0, q1, q2, q3;
             ld8(ir, q0, q1);
@@ -212,8 +206,8 @@ struct Tracer {
             si = first;
             kind = ((unsigned)float_as_int(q3.w)) >> 28;
             top = false;
-            stack[sp++] = YRT_REF_SENTINEL;
-            if (ctr) { ctr->inst_entries++; if (sp > ctr->max_stack) ctr->max_stack = sp; }
+            *sp++ = YRT_REF_SENTINEL;
+            if (ctr) { ctr->inst_entries++; if ((int)(sp - stack) > ctr->max_stack) ctr->max_stack = (int)(sp - stack); }
             cur = float_as_int(q0.w);   // BLAS root ref of the instance's shape
         } else {
             ray3 lray;
@@ -222,7 +216,7 @@ struct Tracer {
                 found = true;
                 if (ANY) { cur = YRT_REF_DONE; return; }
             }
-            pop(stack);
+            pop();
         }
     }
 };
@@ -234,7 +228,7 @@ struct Tracer {
 template <bool ANY, bool EXACT>
 YRT_HD bool trace_ray_impl(const SceneView& sv, const ray3& wray, HitRec& hit, int* stack, TraceCounters* ctr) {
     Tracer<ANY, EXACT> t;
-    t.begin(sv, wray);
+    t.begin(sv, wray, stack);
     for (;;) {
         t.nodes(sv, stack, ctr);
         if (t.done()) break;
