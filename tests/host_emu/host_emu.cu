@@ -95,7 +95,7 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
     emu_lbvh(np, nseg, plo, phi, g.prim_shape, g.shape_prim_off, leaf_blas, es.blas, 0, getenv("YRT_SIZE_BITS_BLAS") ? atoi(getenv("YRT_SIZE_BITS_BLAS")) : YRT_SIZE_BITS_BLAS);
     // prim + attribute records in BLAS leaf order (mirrors k_gather_prims)
     es.prim_recs.assign(3 * (size_t)std::max(np, 1), mk4(0, 0, 0, 0));
-    es.prim_attrs.assign(4 * (size_t)std::max(np, 1), mk4(0, 0, 0, 0));
+    es.prim_attrs.assign(YRT_ATTR_STRIDE * (size_t)std::max(np, 1), mk4(0, 0, 0, 0));
     es.prim_rank.assign(std::max(np, 1), 0);
     for (int k = 0; k < np; k++) {
         int gp = es.blas.order[k];
@@ -111,11 +111,8 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
         float u1 = huv ? g.uv[2 * v[1]] : 0.f, w1 = huv ? g.uv[2 * v[1] + 1] : 0.f;
         float u2 = huv ? g.uv[2 * v[2]] : 0.f, w2 = huv ? g.uv[2 * v[2] + 1] : 0.f;
         float4* pr = &es.prim_recs[3 * (size_t)k];
-        float4* ar = &es.prim_attrs[4 * (size_t)k];
-        pr[0] = mk4(p0.x, p0.y, p0.z, int_as_float(e));
-        if (kind == 0) { pr[1] = mk4(p1.x, p1.y, p1.z, 0.f); pr[2] = mk4(p2.x, p2.y, p2.z, 0.f); }
-        else if (kind == 1) { pr[1] = mk4(p1.x, p1.y, p1.z, g.radius[v[0]]); pr[2] = mk4(g.radius[v[1]], 0.f, 0.f, 0.f); }
-        else { pr[1] = mk4(g.radius[v[0]], 0.f, 0.f, 0.f); pr[2] = mk4(0.f, 0.f, 0.f, 0.f); }
+        float4* ar = &es.prim_attrs[YRT_ATTR_STRIDE * (size_t)k];
+        pack_prim(kind, e, p0, p1, p2, kind == 0 ? 0.f : g.radius[v[0]], kind == 1 ? g.radius[v[1]] : 0.f, pr, ar);
         ar[0] = mk4(n0.x, n0.y, n0.z, u0); ar[1] = mk4(n1.x, n1.y, n1.z, w0); ar[2] = mk4(n2.x, n2.y, n2.z, u1); ar[3] = mk4(w1, u2, w2, 0.f);
     }
     // TLAS (mirrors k_inst_boxes / k_inst_recs)

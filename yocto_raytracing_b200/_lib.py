@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libyrt_b200.so")
+LIB_PATH = os.environ.get("YRT_B200_LIB") or os.path.join(_HERE, "libyrt_b200.so")   # override: A/B runs of build variants
 
 YRT_OK = 0
 

@@ -58,20 +58,8 @@ __global__ void k_gather_prims(GeomView g, const int* __restrict__ order, float4
     float u1 = huv ? g.uv[2 * (size_t)v[1]] : 0.f, w1 = huv ? g.uv[2 * (size_t)v[1] + 1] : 0.f;
     float u2 = huv ? g.uv[2 * (size_t)v[2]] : 0.f, w2 = huv ? g.uv[2 * (size_t)v[2] + 1] : 0.f;
     float4* pr = prim_recs + 3 * (size_t)k;
-    float4* ar = prim_attrs + 4 * (size_t)k;
-    if (kind == 0) {
-        pr[0] = mk4(p0.x, p0.y, p0.z, int_as_float(e));
-        pr[1] = mk4(p1.x, p1.y, p1.z, 0.f);
-        pr[2] = mk4(p2.x, p2.y, p2.z, 0.f);
-    } else if (kind == 1) {
-        pr[0] = mk4(p0.x, p0.y, p0.z, int_as_float(e));
-        pr[1] = mk4(p1.x, p1.y, p1.z, g.radius[v[0]]);
-        pr[2] = mk4(g.radius[v[1]], 0.f, 0.f, 0.f);
-    } else {
-        pr[0] = mk4(p0.x, p0.y, p0.z, int_as_float(e));
-        pr[1] = mk4(g.radius[v[0]], 0.f, 0.f, 0.f);
-        pr[2] = mk4(0.f, 0.f, 0.f, 0.f);
-    }
+    float4* ar = prim_attrs + YRT_ATTR_STRIDE * (size_t)k;
+    pack_prim(kind, e, p0, p1, p2, kind == 0 ? 0.f : g.radius[v[0]], kind == 1 ? g.radius[v[1]] : 0.f, pr, ar);
     ar[0] = mk4(n0.x, n0.y, n0.z, u0);
     ar[1] = mk4(n1.x, n1.y, n1.z, w0);
     ar[2] = mk4(n2.x, n2.y, n2.z, u1);
@@ -449,7 +437,7 @@ int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
     YRT_TRY(lbvh_build(device, st, hs.n_prims, std::max(hs.n_shapes, 1), plo.as<float4>(), phi.as<float4>(), g.prim_shape,
                        g.shape_prim_off, leaf_blas, bo));
     YRT_TRY(ds.prim_recs.alloc(sizeof(float4) * 3 * (size_t)std::max(hs.n_prims, 1), device));
-    YRT_TRY(ds.prim_attrs.alloc(sizeof(float4) * 4 * (size_t)std::max(hs.n_prims, 1), device));
+    YRT_TRY(ds.prim_attrs.alloc(sizeof(float4) * YRT_ATTR_STRIDE * (size_t)std::max(hs.n_prims, 1), device));
     YRT_TRY(ds.prim_rank.alloc(sizeof(int) * (size_t)std::max(hs.n_prims, 1), device));
     if (hs.n_prims > 0)
         k_gather_prims<<<grid_for(hs.n_prims), 256, 0, st>>>(g, blas_order.as<int>(), ds.prim_recs.as<float4>(),

@@ -91,10 +91,10 @@ YRT_HD ray3 transform_ray_inverse(const frame3& f, const ray3& r) {
 // ---- primitive tests: src/scene.cpp:229-307 ------------------------------------------------
 // Möller–Trumbore, two-sided, non-watertight (scene.cpp:229-263). On a hit writes t and the
 // two barycentrics (ew = {1-w1-w2, w1, w2, 0}).
-YRT_HD bool intersect_triangle(const ray3& ray, const vec3& v0, const vec3& v1, const vec3& v2, float& dist,
-                               float& ow1, float& ow2) {
-    vec3 e1 = v1 - v0;
-    vec3 e2 = v2 - v0;
+// The two edges e1 = v1 - v0, e2 = v2 - v0 (scene.cpp:236-237) do not depend on the ray: the build stores them (the same
+// two float subtractions, done once) and the traversal calls this form.
+YRT_HD bool intersect_triangle_edges(const ray3& ray, const vec3& v0, const vec3& e1, const vec3& e2, float& dist,
+                                     float& ow1, float& ow2) {
     vec3 r = cross(ray.d, e2);
     float den = dot(r, e1);
     if (den == 0) return false;
@@ -113,6 +113,11 @@ YRT_HD bool intersect_triangle(const ray3& ray, const vec3& v0, const vec3& v1, 
     ow1 = w1;
     ow2 = w2;
     return true;
+}
+
+YRT_HD bool intersect_triangle(const ray3& ray, const vec3& v0, const vec3& v1, const vec3& v2, float& dist,
+                               float& ow1, float& ow2) {
+    return intersect_triangle_edges(ray, v0, v1 - v0, v2 - v0, dist, ow1, ow2);
 }
 
 // scene.cpp:267-281; ew = {1,0,0,0}

@@ -34,6 +34,7 @@ namespace yrt {
 #define YRT_REF_DONE ((int)0x80000001)      /* traversal finished (never a valid leaf: first <= YRT_MAX_LEAF_FIRST) */
 #define YRT_LEAF_MAX_COUNT 8
 #define YRT_MAX_LEAF_FIRST ((1 << 28) - 2)
+#define YRT_ATTR_STRIDE 6
 #define YRT_STACK_CAP 128   /* traversal stack entries (TLAS + BLAS levels simultaneously live); checked against the built depth */
 
 YRT_HD int make_leaf_ref(int first, int count) { return ~((first << 3) | (count - 1)); }
@@ -140,7 +141,7 @@ struct SceneView {
                                 // array and one index space, so a node visit needs no level test
     const float4* inst_recs;    // 4 per instance, TLAS leaf order
     const float4* prim_recs;    // 3 per prim, BLAS leaf order
-    const float4* prim_attrs;   // 4 per prim
+    const float4* prim_attrs;   // YRT_ATTR_STRIDE per prim: normals + uv (4), triangles: v1, v2 (the trace record holds edges)
     const float4* mat_recs;     // 4 per material
     const float4* light_recs;   // 5 per light
     const uint8_t* tex_rgba8;   // all textures
@@ -154,6 +155,27 @@ struct SceneView {
     int n_lights;
     int n_active_instances;
 };
+
+// trace record (3 float4) + the vertex positions shading needs, for one element in BLAS leaf order.
+//   triangle: (v0 | element, e1 = v1 - v0, e2 = v2 - v0)  — the edges of scene.cpp:236-237, subtracted once here
+//   line:     (v0 | element, v1 | r0, r1)        point: (v0 | element, r0)
+// ar[4], ar[5] keep v1, v2 of a triangle for eval_hit (scene.h:166-168 interpolates the vertices, not the edges)
+YRT_HD void pack_prim(int kind, int e, const vec3& p0, const vec3& p1, const vec3& p2, float r0, float r1, float4* pr, float4* ar) {
+    pr[0] = mk4(p0.x, p0.y, p0.z, int_as_float(e));
+    if (kind == 0) {
+        vec3 e1 = p1 - p0, e2 = p2 - p0;
+        pr[1] = mk4(e1.x, e1.y, e1.z, 0.f);
+        pr[2] = mk4(e2.x, e2.y, e2.z, 0.f);
+    } else if (kind == 1) {
+        pr[1] = mk4(p1.x, p1.y, p1.z, r0);
+        pr[2] = mk4(r1, 0.f, 0.f, 0.f);
+    } else {
+        pr[1] = mk4(r0, 0.f, 0.f, 0.f);
+        pr[2] = mk4(0.f, 0.f, 0.f, 0.f);
+    }
+    ar[4] = mk4(p1.x, p1.y, p1.z, 0.f);
+    ar[5] = mk4(p2.x, p2.y, p2.z, 0.f);
+}
 
 // closest-hit result (16 B on the wire: si, prim, w1, w2; dist kept for the parity hook)
 struct HitRec {

@@ -39,7 +39,8 @@ YRT_HD vec3 eval_hit_pos(const SceneView& sv, int si, int prim, float w1, float 
         float ewx = 1 - w1;                             // scene.cpp:304
         lp = xyz(q0) * ewx + xyz(q1) * w1;              // scene.h:163-164
     } else {
-        float4 q1 = ld4(pr + 1), q2 = ld4(pr + 2);
+        const float4* ar = sv.prim_attrs + YRT_ATTR_STRIDE * (size_t)prim;
+        float4 q1 = ld4(ar + 4), q2 = ld4(ar + 5);      // v1, v2 (the trace record holds the edges)
         float ewx = 1 - w1 - w2;                        // scene.cpp:260
         lp = xyz(q0) * ewx + xyz(q1) * w1 + xyz(q2) * w2;   // scene.h:166-168
     }
@@ -57,7 +58,7 @@ YRT_HD void eval_hit(const SceneView& sv, int si, int prim, float w1, float w2, 
     a.inst = float_as_int(f1.w);
     a.mat = float_as_int(f2.w);
     const float4* pr = sv.prim_recs + 3 * (size_t)prim;
-    const float4* ar = sv.prim_attrs + 4 * (size_t)prim;
+    const float4* ar = sv.prim_attrs + YRT_ATTR_STRIDE * (size_t)prim;
     float4 q0 = ld4(pr), a0 = ld4(ar);
     a.ei = float_as_int(q0.w);
     vec3 lp, ln;
@@ -75,7 +76,7 @@ YRT_HD void eval_hit(const SceneView& sv, int si, int prim, float w1, float w2, 
         t0.x = a0.w; t0.y = a1.w; t1.x = a2.w; t1.y = a3.x;
         a.uv = t0 * ewx + t1 * w1;                      // scene.h:197-198
     } else {
-        float4 q1 = ld4(pr + 1), q2 = ld4(pr + 2), a1 = ld4(ar + 1), a2 = ld4(ar + 2), a3 = ld4(ar + 3);
+        float4 q1 = ld4(ar + 4), q2 = ld4(ar + 5), a1 = ld4(ar + 1), a2 = ld4(ar + 2), a3 = ld4(ar + 3);   // q1, q2 = v1, v2
         float ewx = 1 - w1 - w2;
         lp = xyz(q0) * ewx + xyz(q1) * w1 + xyz(q2) * w2;
         ln = normalize(xyz(a0) * ewx + xyz(a1) * w1 + xyz(a2) * w2);   // scene.h:183-185

@@ -47,7 +47,7 @@ YRT_HD bool leaf_prims(const SceneView& sv, int kind, int first, int count, cons
         if (ctr) ctr->prim_tests++;
         if (kind == 0) {
             float4 q2 = ld4(pr + 2);
-            h = intersect_triangle(lray, xyz(q0), xyz(q1), xyz(q2), t, a, b);
+            h = intersect_triangle_edges(lray, xyz(q0), xyz(q1), xyz(q2), t, a, b);   // record = (v0, e1, e2)
         } else if (kind == 1) {
             float4 q2 = ld4(pr + 2);
             h = intersect_line(lray, xyz(q0), xyz(q1), q1.w, q2.x, t, a);
