@@ -198,6 +198,17 @@ YRT_HD bool intersect_check_bbox(const vec3& o, const vec3& invd, const raysigns
 // (tests/test_host_emu.py audits every box test against the reference's formula: 0 false rejects).
 // NaN (inf-inf for direction components that are exactly 0) is dropped by FMNMX like in the reference's ternaries:
 // that axis does not constrain (|invd| = inf keeps h'|invd| = inf or NaN, never a finite bound).
+#ifndef YRT_APPROX_RCP
+#define YRT_APPROX_RCP 1   /* slab rays use MUFU.RCP (1 ulp) instead of the correctly rounded 1/d, see rcp_slab in yrt_trace.cuh */
+#endif
+// With YRT_APPROX_RCP each invd_a is off by a further 2u relative, i.e. every slab distance by 2u|t| more: the chain
+// above becomes T0 <= T1 (1+9u)(1+4u)/(1-4u) ~ T1 (1+17u), so the accept factor grows from 1+16u to 1+24u; the inflated
+// half-extents keep their margin ((1+16u)(1-2u) > 1+13u against the 4u they need).
+#if YRT_APPROX_RCP
+#define YRT_SLAB_ACCEPT 1.0000014305114746f   /* 1 + 24u */
+#else
+#define YRT_SLAB_ACCEPT 1.00000095f           /* 1 + 16u */
+#endif
 struct slabray { vec3 invd, noi, ainv; float pad; };
 
 YRT_HD slabray make_slabray(const vec3& o, const vec3& invd) {
@@ -219,7 +230,7 @@ YRT_HD bool slab_test_ch(const slabray& r, float rtmin, float rtmax, float cx, f
     float tmin = fmaxf(t0z, fmaxf(t0y, fmaxf(t0x, rtmin)));
     float tmax = fminf(t1z, fminf(t1y, fminf(t1x, rtmax)));
     tenter = tmin;
-    return tmin <= fmaf(tmax, 1.00000095f, r.pad);
+    return tmin <= fmaf(tmax, YRT_SLAB_ACCEPT, r.pad);
 }
 
 // centre / half-extent of a box; the half-extent is inflated by 1 + 16u: [c-h', c+h'] contains [lo, hi] with the

@@ -30,7 +30,7 @@ __device__ __forceinline__ void trace_packet(const SceneView& sv, const ray3& wr
 
     // per-lane ray state
     const vec3 wo = wray.o, wd = wray.d;
-    const slabray wsr = make_slabray(wo, inv3(wd));
+    const slabray wsr = make_slabray(wo, inv3_slab(wd));
     vec3 o = wo, d = wd;
     slabray sr = wsr;
     const float tmin = wray.tmin;
@@ -90,7 +90,7 @@ __device__ __forceinline__ void trace_packet(const SceneView& sv, const ray3& wr
             f.x = xyz(q0); f.y = xyz(q1); f.z = xyz(q2); f.o = xyz(q3);
             o = transform_point_inverse(f, wo);          // transform_ray_inverse, scene.cpp:468
             d = transform_direction_inverse(f, wd);
-            sr = make_slabray(o, inv3(d));
+            sr = make_slabray(o, inv3_slab(d));
             si = first;
             kind = ((unsigned)float_as_int(q3.w)) >> 28;
             top = false;

@@ -124,7 +124,7 @@ YRT_HD void slab_test_node(const slabray& r, float rtmin, float rtmax, const flo
     float tmin0 = fmaxf(t0z0, fmaxf(t0y0, fmaxf(t0x0, rtmin))), tmax0 = fminf(t1z0, fminf(t1y0, fminf(t1x0, rtmax)));
     float tmin1 = fmaxf(t0z1, fmaxf(t0y1, fmaxf(t0x1, rtmin))), tmax1 = fminf(t1z1, fminf(t1y1, fminf(t1x1, rtmax)));
     float lim0, lim1;
-    upk2(fma2(pk2(tmax0, tmax1), pk2(1.00000095f, 1.00000095f), pk2(r.pad, r.pad)), lim0, lim1);
+    upk2(fma2(pk2(tmax0, tmax1), pk2(YRT_SLAB_ACCEPT, YRT_SLAB_ACCEPT), pk2(r.pad, r.pad)), lim0, lim1);
     e0 = tmin0; e1 = tmin1;
     h0 = tmin0 <= lim0; h1 = tmin1 <= lim1;
 #else

@@ -77,6 +77,27 @@ YRT_HD bool leaf_prims(const SceneView& sv, int kind, int first, int count, cons
 
 YRT_HD vec3 inv3(const vec3& d) { return mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }   // scene.cpp:372
 
+// Reciprocal direction for the FUSED slab test only (never for Tracer<ANY, true>, which applies the reference's formula):
+// that test is a conservative cull, so 1/d may carry the 1 ulp (2u) error of MUFU.RCP instead of the correctly rounded
+// IEEE quotient (8 instructions per component) — the accept factor in slab_test_node budgets for it (yrt_math.cuh).
+// Host build (tests/host_emu): the correctly rounded quotient pushed one full ulp up or down, direction picked from
+// the operand's bits, so that the audit of every box test covers the worst case of the device's approximation.
+YRT_HD float rcp_slab(float x) {
+#if !YRT_APPROX_RCP
+    return 1.0f / x;
+#elif defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    float r = 1.0f / x;
+    if (!(fabsf(r) <= 3.0e38f) || r == 0.0f) return r;
+    int b = float_as_int(r);
+    return int_as_float((float_as_int(x) * 0x9E3779B1u) & 0x10000u ? b + 1 : b - 1);
+#endif
+}
+YRT_HD vec3 inv3_slab(const vec3& d) { return mk3(rcp_slab(d.x), rcp_slab(d.y), rcp_slab(d.z)); }
+
 // Resumable traversal state of one ray.  Closest hit (ANY=false) keeps shrinking tmax; any hit
 // (ANY=true) stops at the first accepted primitive (scene.cpp:414,425,436,473).
 //
@@ -103,7 +124,7 @@ struct Tracer {
     YRT_HD void begin(const SceneView& sv, const ray3& wray, int* stack) {
         hit.si = -1; hit.prim = -1; hit.w1 = hit.w2 = 0.f; hit.dist = 0.f;
         wo = wray.o; wd = wray.d;
-        wsr = make_slabray(wo, inv3(wd));
+        wsr = make_slabray(wo, EXACT ? inv3(wd) : inv3_slab(wd));
         o = wo; d = wd; sr = wsr;
         tmin = wray.tmin; tmax = wray.tmax;
         stack[0] = YRT_REF_DONE; sp = stack + 1;
@@ -202,7 +223,7 @@ struct Tracer {
             f.x = xyz(q0); f.y = xyz(q1); f.z = xyz(q2); f.o = xyz(q3);
             o = transform_point_inverse(f, wo);              // transform_ray_inverse, scene.cpp:468
             d = transform_direction_inverse(f, wd);
-            sr = make_slabray(o, inv3(d));
+            sr = make_slabray(o, EXACT ? inv3(d) : inv3_slab(d));
             si = first;
             kind = ((unsigned)float_as_int(q3.w)) >> 28;
             top = false;
@@ -241,9 +262,12 @@ YRT_HD bool trace_ray_impl(const SceneView& sv, const ray3& wray, HitRec& hit, i
 template <bool ANY>
 YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* stack, TraceCounters* ctr) {
     // decided on the world-space direction (instance frames of the configs are pure translations, so the local
-    // direction is the same; a rotated instance may still meet a large pad — slower, never wrong)
-    float m = fmaxf(fmaxf(fabsf(1.0f / wray.d.x), fabsf(1.0f / wray.d.y)), fabsf(1.0f / wray.d.z));
-    if (m > YRT_EXACT_SLAB_INVD) return trace_ray_impl<ANY, true>(sv, wray, hit, stack, ctr);
+    // direction is the same; a rotated instance may still meet a large pad — slower, never wrong).
+    // |1/d| > 4096  <=>  |d| < 2^-12 (the correctly rounded quotient is monotonic and exact at the power of two)
+    float ax = fabsf(wray.d.x), ay = fabsf(wray.d.y), az = fabsf(wray.d.z);
+    float m = fminf(fminf(ax, ay), az), big = fmaxf(fmaxf(ax, ay), az);
+    // (directions beyond 1e30 would underflow the flush-to-zero MUFU reciprocal: exact path as well; NaN goes there too)
+    if (!(m >= 1.0f / YRT_EXACT_SLAB_INVD && big <= 1.0e30f)) return trace_ray_impl<ANY, true>(sv, wray, hit, stack, ctr);
     return trace_ray_impl<ANY, false>(sv, wray, hit, stack, ctr);
 }
 
