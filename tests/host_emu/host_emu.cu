@@ -25,7 +25,7 @@ struct EmuLbvh {
 };
 
 void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi, const int* seg_of, const int* seg_first, int leaf_size,
-              EmuLbvh& out, int ref_offset, int size_bits) {
+              EmuLbvh& out, int ref_offset, int size_bits, int rotate_rounds) {
     size_t ni = n > 1 ? n - 1 : 1;
     std::vector<int> cent_lo(3 * n_seg), cent_hi(3 * n_seg);
     out.seg_box_lo.assign(3 * n_seg, 0);
@@ -34,6 +34,7 @@ void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi
     out.order.assign(std::max(n, 1), 0);
     std::vector<int> left(ni), right(ni), rfirst(ni), rlast(ni), pint(ni), pleaf(std::max(n, 1), -1), flags(ni);
     std::vector<float4> nlo(ni), nhi(ni);
+    std::vector<int> count(ni), new_slot(std::max(n, 1)), order_tmp(std::max(n, 1)), pleaf_tmp(std::max(n, 1));
     out.nodes.assign(4 * ni, mk4(0, 0, 0, 0));
     out.seg_root.assign(n_seg, 0);
     out.seg_depth.assign(n_seg, 0);
@@ -42,6 +43,7 @@ void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi
     a.seg_cent_lo = cent_lo.data(); a.seg_cent_hi = cent_hi.data(); a.seg_box_lo = out.seg_box_lo.data(); a.seg_box_hi = out.seg_box_hi.data();
     a.keys = keys.data(); a.order = out.order.data(); a.left = left.data(); a.right = right.data();
     a.range_first = rfirst.data(); a.range_last = rlast.data(); a.parent_int = pint.data(); a.parent_leaf = pleaf.data();
+    a.count = count.data(); a.new_slot = new_slot.data(); a.order_tmp = order_tmp.data(); a.parent_leaf_tmp = pleaf_tmp.data();
     a.flags = flags.data(); a.node_lo = nlo.data(); a.node_hi = nhi.data(); a.nodes = out.nodes.data();
     a.seg_root = out.seg_root.data(); a.seg_depth = out.seg_depth.data(); a.leaf_size = leaf_size; a.ref_offset = ref_offset; a.size_bits = size_bits;
     for (int s = 0; s < n_seg; s++) seg_bounds_init_item(a, s);
@@ -60,6 +62,16 @@ void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi
     if (n > 1) {
         for (int i = 0; i < n - 1; i++) karras_item(a, i);
         for (int i = 0; i < n; i++) refit_item(a, i);
+        for (int r = 0; r < rotate_rounds; r++) {
+            std::fill(flags.begin(), flags.end(), 0);
+            for (int i = 0; i < n; i++) rotate_refit_item(a, i);
+        }
+        if (rotate_rounds > 0) {
+            for (int i = 0; i < n; i++) relayout_slot_item(a, i);
+            for (int i = 0; i < n; i++) relayout_move_item(a, i);
+            for (int i = 0; i < n - 1; i++) relayout_refs_item(a, i);
+            for (int i = 0; i < n; i++) relayout_copy_item(a, i);
+        }
         for (int i = 0; i < n - 1; i++) emit_item(a, i);
     }
     for (int s = 0; s < n_seg; s++) single_root_item(a, s);
@@ -92,7 +104,8 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
         phi[i] = mk4(b.hi.x, b.hi.y, b.hi.z, 0.f);
     }
     int nseg = std::max(hs.n_shapes, 1);
-    emu_lbvh(np, nseg, plo, phi, g.prim_shape, g.shape_prim_off, leaf_blas, es.blas, 0, getenv("YRT_SIZE_BITS_BLAS") ? atoi(getenv("YRT_SIZE_BITS_BLAS")) : YRT_SIZE_BITS_BLAS);
+    emu_lbvh(np, nseg, plo, phi, g.prim_shape, g.shape_prim_off, leaf_blas, es.blas, 0, getenv("YRT_SIZE_BITS_BLAS") ? atoi(getenv("YRT_SIZE_BITS_BLAS")) : YRT_SIZE_BITS_BLAS,
+             getenv("YRT_ROTATE_BLAS") ? atoi(getenv("YRT_ROTATE_BLAS")) : YRT_ROTATE_ROUNDS_BLAS);
     // prim + attribute records in BLAS leaf order (mirrors k_gather_prims)
     es.prim_recs.assign(3 * (size_t)std::max(np, 1), mk4(0, 0, 0, 0));
     es.prim_attrs.assign(YRT_ATTR_STRIDE * (size_t)std::max(np, 1), mk4(0, 0, 0, 0));
@@ -133,7 +146,8 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
     std::vector<int> seg_of(std::max(na, 1), 0);
     int sf[2] = {0, na};
     int nb_int = np > 1 ? np - 1 : 0;
-    emu_lbvh(na, 1, ilo, ihi, seg_of.data(), sf, leaf_tlas, es.tlas, nb_int, getenv("YRT_SIZE_BITS_TLAS") ? atoi(getenv("YRT_SIZE_BITS_TLAS")) : YRT_SIZE_BITS_TLAS);
+    emu_lbvh(na, 1, ilo, ihi, seg_of.data(), sf, leaf_tlas, es.tlas, nb_int, getenv("YRT_SIZE_BITS_TLAS") ? atoi(getenv("YRT_SIZE_BITS_TLAS")) : YRT_SIZE_BITS_TLAS,
+             getenv("YRT_ROTATE_TLAS") ? atoi(getenv("YRT_ROTATE_TLAS")) : YRT_ROTATE_ROUNDS_TLAS);
     es.nodes.assign(es.blas.nodes.begin(), es.blas.nodes.begin() + 4 * (size_t)nb_int);
     es.nodes.insert(es.nodes.end(), es.tlas.nodes.begin(), es.tlas.nodes.end());
     es.inst_recs.assign(4 * (size_t)std::max(na, 1), mk4(0, 0, 0, 0));

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN_CASES, id_match, ldr_stats, load_golden
-from yocto_raytracing_b200 import _lib, synth
+from yocto_raytracing_b200 import FlatScene, _lib, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -244,6 +244,49 @@ def test_drop_in_cli_matches_reference_cli(gpu, tmp_path):
         assert np.array_equal(np.array(Image.open(c)), ia)
     # unknown option: usage + non-zero exit like yu::cmdline (src/ext/yocto_utils.h:1157-1174)
     assert subprocess.run([ours, "--bogus", "x.obj"], capture_output=True).returncode != 0
+
+
+def test_cli_scene_cache_and_device_ldr(gpu, tmp_path):
+    """SURVEY 8f.1 / 8f.2 through the CLI: --device-ldr (tonemap on the GPU, RGBA8 out) and --cache (flattened scene
+    <scene>.yrts written on the first run, read instead of the OBJ on the second).  The PNG of both runs must agree with
+    the unmodified reference binary's within 1/255 on >= 99.9 % of pixels, and the cached run must be identical to the
+    uncached one."""
+    import os
+    import subprocess
+    from PIL import Image
+    from conftest import ROOT
+    ours, ref = os.path.join(ROOT, "bin", "raytrace"), os.path.join(ROOT, "oracle", "_ref", "raytrace_ref")
+    if not (os.path.exists(ours) and os.path.exists(ref)):
+        pytest.skip("bin/raytrace / oracle/_ref/raytrace_ref not built (need the reference sources at build time)")
+    sc = synth.mixed_scene(7)
+    obj = sc.write_obj(str(tmp_path / sc.name))
+    cwd, name = os.path.dirname(obj), os.path.basename(obj)
+    args = ["-r", "120", "-s", "2", "-a", "0.1"]
+    outs = []
+    for i in range(2):
+        out = os.path.join(cwd, f"ours{i}.png")
+        r = subprocess.run([ours] + args + ["--cache", "--device-ldr", "--stats", "-o", out, name], cwd=cwd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert [l.split()[0] for l in r.stdout.strip().splitlines()[:4]] == ["loading", "creating", "tracing", "saving"]
+        assert ("(scene cache)" in r.stdout) == (i == 1), r.stdout
+        outs.append(np.array(Image.open(out)))
+    assert os.path.exists(obj + ".yrts")
+    assert np.array_equal(outs[0], outs[1])
+    # the cache file is what FlatScene.load reads: same scene through Python
+    flat = FlatScene.load(obj + ".yrts")
+    assert flat.arrays["inst_shape"].size == sc.flat().arrays["inst_shape"].size
+    b = os.path.join(cwd, "ref.png")
+    subprocess.run([ref] + args + ["-o", b, name], cwd=cwd, check=True, capture_output=True)
+    within1, ident, mx = ldr_stats(outs[0], np.array(Image.open(b)))
+    assert within1 >= PIXEL_BAR, (within1, ident, mx)
+    # a stale cache (older than the OBJ) is ignored and rewritten
+    os.utime(obj + ".yrts", (1, 1))
+    r = subprocess.run([ours] + args + ["--cache", "-o", os.path.join(cwd, "ours3.png"), name], cwd=cwd, capture_output=True, text=True)
+    assert r.returncode == 0 and "(scene cache)" not in r.stdout
+    assert os.stat(obj + ".yrts").st_mtime > 1
+    # .hdr output keeps the float path even with --device-ldr
+    r = subprocess.run([ours] + args + ["--device-ldr", "-o", os.path.join(cwd, "ours.hdr"), name], cwd=cwd, capture_output=True, text=True)
+    assert r.returncode == 0 and os.path.getsize(os.path.join(cwd, "ours.hdr")) > 0
 
 
 def test_fused_gather_into_one_frame(gpu):

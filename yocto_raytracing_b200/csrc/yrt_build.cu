@@ -33,6 +33,11 @@ __global__ void k_morton(LbvhArrays a) { int i = YRT_TID(); if (i < a.n) morton_
 __global__ void k_karras(LbvhArrays a) { int i = YRT_TID(); if (i < a.n - 1) karras_item(a, i); }
 __global__ void k_refit(LbvhArrays a) { int i = YRT_TID(); if (i < a.n) refit_item(a, i); }
 __global__ void k_emit(LbvhArrays a) { int i = YRT_TID(); if (i < a.n - 1) emit_item(a, i); }
+__global__ void k_rotate_refit(LbvhArrays a) { int i = YRT_TID(); if (i < a.n) rotate_refit_item(a, i); }
+__global__ void k_relayout_slot(LbvhArrays a) { int i = YRT_TID(); if (i < a.n) relayout_slot_item(a, i); }
+__global__ void k_relayout_move(LbvhArrays a) { int i = YRT_TID(); if (i < a.n) relayout_move_item(a, i); }
+__global__ void k_relayout_refs(LbvhArrays a) { int i = YRT_TID(); if (i < a.n - 1) relayout_refs_item(a, i); }
+__global__ void k_relayout_copy(LbvhArrays a) { int i = YRT_TID(); if (i < a.n) relayout_copy_item(a, i); }
 __global__ void k_single_root(LbvhArrays a) { int s = YRT_TID(); if (s < a.n_seg) single_root_item(a, s); }
 __global__ void k_depth(LbvhArrays a) { int i = YRT_TID(); if (i < a.n) depth_item(a, i); }
 
@@ -259,6 +264,7 @@ struct LbvhOut {
     float4* nodes;        // 4 float4 per internal node, preallocated by the caller
     int ref_offset;       // index of this tree set's node 0 in the shared node array
     int size_bits;        // size-class bits in the sort key (see morton_item)
+    int rotate_rounds;    // bottom-up tree-rotation passes after the refit (see rotate_refit_item)
     DevBuf* seg_root;     // [n_seg]
     DevBuf* seg_depth;    // [n_seg]
     DevBuf* order;        // [n] item id at sorted slot
@@ -271,7 +277,7 @@ static inline int grid_for(int n, int t = 256) { return n > 0 ? (n + t - 1) / t 
 static int lbvh_build(int dev, cudaStream_t st, int n, int n_seg, float4* box_lo, float4* box_hi, const int* d_seg_of,
                       const int* d_seg_first, int leaf_size, LbvhOut& out) {
     DevBuf cent_lo, cent_hi, sbox_lo_tmp, sbox_hi_tmp, keys, keys_alt, order_alt, left, right, rfirst, rlast, pint, pleaf,
-        flags, nlo, nhi, ghist;
+        flags, nlo, nhi, ghist, count, new_slot, order_tmp, pleaf_tmp;
     DevBuf* sbl = out.seg_box_lo ? out.seg_box_lo : &sbox_lo_tmp;
     DevBuf* sbh = out.seg_box_hi ? out.seg_box_hi : &sbox_hi_tmp;
     size_t ni = n > 1 ? (size_t)(n - 1) : 1;
@@ -292,6 +298,12 @@ static int lbvh_build(int dev, cudaStream_t st, int n, int n_seg, float4* box_lo
     YRT_TRY(flags.alloc(sizeof(int) * ni, dev));
     YRT_TRY(nlo.alloc(sizeof(float4) * ni, dev));
     YRT_TRY(nhi.alloc(sizeof(float4) * ni, dev));
+    if (out.rotate_rounds > 0) {
+        YRT_TRY(count.alloc(sizeof(int) * ni, dev));
+        YRT_TRY(new_slot.alloc(sizeof(int) * (size_t)std::max(n, 1), dev));
+        YRT_TRY(order_tmp.alloc(sizeof(int) * (size_t)std::max(n, 1), dev));
+        YRT_TRY(pleaf_tmp.alloc(sizeof(int) * (size_t)std::max(n, 1), dev));
+    }
     YRT_TRY(out.seg_root->alloc(sizeof(int) * (size_t)n_seg, dev));
     YRT_TRY(out.seg_depth->alloc(sizeof(int) * (size_t)n_seg, dev));
     YRT_CUDA(cudaMemsetAsync(pleaf.p, 0xff, sizeof(int) * (size_t)std::max(n, 1), st));   // -1: no parent
@@ -317,6 +329,10 @@ static int lbvh_build(int dev, cudaStream_t st, int n, int n_seg, float4* box_lo
     a.parent_int = pint.as<int>();
     a.parent_leaf = pleaf.as<int>();
     a.flags = flags.as<int>();
+    a.count = count.as<int>();
+    a.new_slot = new_slot.as<int>();
+    a.order_tmp = order_tmp.as<int>();
+    a.parent_leaf_tmp = pleaf_tmp.as<int>();
     a.node_lo = nlo.as<float4>();
     a.node_hi = nhi.as<float4>();
     a.nodes = out.nodes;
@@ -338,6 +354,16 @@ static int lbvh_build(int dev, cudaStream_t st, int n, int n_seg, float4* box_lo
         if (n > 1) {
             k_karras<<<grid_for(n - 1), 256, 0, st>>>(a);
             k_refit<<<grid_for(n), 256, 0, st>>>(a);
+            for (int r = 0; r < out.rotate_rounds; r++) {
+                YRT_CUDA(cudaMemsetAsync(a.flags, 0, sizeof(int) * ni, st));
+                k_rotate_refit<<<grid_for(n), 256, 0, st>>>(a);
+            }
+            if (out.rotate_rounds > 0) {   // leaf slots in tree order again (leaf references are (first, count) ranges)
+                k_relayout_slot<<<grid_for(n), 256, 0, st>>>(a);
+                k_relayout_move<<<grid_for(n), 256, 0, st>>>(a);
+                k_relayout_refs<<<grid_for(n - 1), 256, 0, st>>>(a);
+                k_relayout_copy<<<grid_for(n), 256, 0, st>>>(a);
+            }
             k_emit<<<grid_for(n - 1), 256, 0, st>>>(a);
         }
         k_single_root<<<grid_for(n_seg), 256, 0, st>>>(a);
@@ -404,6 +430,10 @@ int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
     const char* env_st = getenv("YRT_SIZE_BITS_TLAS");
     int size_bits_blas = std::min(std::max(env_sb ? atoi(env_sb) : YRT_SIZE_BITS_BLAS, 0), 3);
     int size_bits_tlas = std::min(std::max(env_st ? atoi(env_st) : YRT_SIZE_BITS_TLAS, 0), 3);
+    const char* env_rb = getenv("YRT_ROTATE_BLAS");
+    const char* env_rt = getenv("YRT_ROTATE_TLAS");
+    int rotate_blas = std::min(std::max(env_rb ? atoi(env_rb) : YRT_ROTATE_ROUNDS_BLAS, 0), 8);
+    int rotate_tlas = std::min(std::max(env_rt ? atoi(env_rt) : YRT_ROTATE_ROUNDS_TLAS, 0), 8);
     leaf_blas = std::min(std::max(leaf_blas, 1), YRT_LEAF_MAX_COUNT);
     leaf_tlas = std::min(std::max(leaf_tlas, 1), YRT_LEAF_MAX_COUNT);
 
@@ -432,7 +462,7 @@ int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
     int nb_int = hs.n_prims > 1 ? hs.n_prims - 1 : 0, nt_int = ds.n_active > 1 ? ds.n_active - 1 : 0;
     YRT_TRY(ds.nodes.alloc(sizeof(float4) * 4 * (size_t)(nb_int + nt_int + 2), device));
     LbvhOut bo;
-    bo.nodes = ds.nodes.as<float4>(); bo.ref_offset = 0; bo.size_bits = size_bits_blas; bo.seg_root = &ds.blas_seg_root; bo.seg_depth = &ds.blas_seg_depth; bo.order = &blas_order;
+    bo.nodes = ds.nodes.as<float4>(); bo.ref_offset = 0; bo.size_bits = size_bits_blas; bo.rotate_rounds = rotate_blas; bo.seg_root = &ds.blas_seg_root; bo.seg_depth = &ds.blas_seg_depth; bo.order = &blas_order;
     bo.seg_box_lo = &ds.shape_box_lo; bo.seg_box_hi = &ds.shape_box_hi;
     YRT_TRY(lbvh_build(device, st, hs.n_prims, std::max(hs.n_shapes, 1), plo.as<float4>(), phi.as<float4>(), g.prim_shape,
                        g.shape_prim_off, leaf_blas, bo));
@@ -457,7 +487,7 @@ int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
         k_inst_boxes<<<grid_for(na), 256, 0, st>>>(na, ds.active_inst.as<int>(), ds.inst_frame.as<float>(), ds.inst_shape.as<int>(),
                                                  ds.shape_box_lo.as<int>(), ds.shape_box_hi.as<int>(), ilo.as<float4>(), ihi.as<float4>());
     LbvhOut to;
-    to.nodes = ds.nodes.as<float4>() + 4 * (size_t)nb_int; to.ref_offset = nb_int; to.size_bits = size_bits_tlas; to.seg_root = &ds.tlas_seg_root; to.seg_depth = &ds.tlas_seg_depth; to.order = &tlas_order;
+    to.nodes = ds.nodes.as<float4>() + 4 * (size_t)nb_int; to.ref_offset = nb_int; to.size_bits = size_bits_tlas; to.rotate_rounds = rotate_tlas; to.seg_root = &ds.tlas_seg_root; to.seg_depth = &ds.tlas_seg_depth; to.order = &tlas_order;
     to.seg_box_lo = nullptr; to.seg_box_hi = nullptr;
     YRT_TRY(lbvh_build(device, st, na, 1, ilo.as<float4>(), ihi.as<float4>(), tl_seg_of.as<int>(), tl_seg_first.as<int>(), leaf_tlas, to));
     YRT_TRY(ds.inst_recs.alloc(sizeof(float4) * 4 * (size_t)std::max(na, 1), device));

@@ -19,6 +19,12 @@ namespace yrt {
 #define YRT_LEAF_SIZE_BLAS 3   /* subtrees of <= 3 elements become one leaf (measured 1..5: 17.89 / 16.59 / 16.41 / 16.62 / 16.64 ms; the reference stops at <= 4, scene.cpp:583) */
 #define YRT_SIZE_BITS_BLAS 0
 #define YRT_SIZE_BITS_TLAS 3
+#ifndef YRT_ROTATE_ROUNDS_BLAS
+#define YRT_ROTATE_ROUNDS_BLAS 0   /* bottom-up passes of tree rotations after the refit (see rotate_refit_item) */
+#endif
+#ifndef YRT_ROTATE_ROUNDS_TLAS
+#define YRT_ROTATE_ROUNDS_TLAS 0
+#endif
 #define YRT_LEAF_SIZE_TLAS 1   /* one instance per TLAS leaf: its world box is tested before the ray is transformed */
 
 // ---- order-preserving float <-> int for atomic min/max --------------------------------------
@@ -126,6 +132,10 @@ struct LbvhArrays {
     int* parent_int;       // [n-1] parent of an internal node (-1 root)
     int* parent_leaf;      // [n]
     int* flags;            // [n-1] refit arrival counters
+    int* count;            // [n-1] leaves below an internal node (tree rotations + re-layout)
+    int* new_slot;         // [n] sorted slot of each leaf after the re-layout
+    int* order_tmp;        // [n]
+    int* parent_leaf_tmp;  // [n]
     float4* node_lo;       // [n-1] refit bounds of internal nodes
     float4* node_hi;
     // outputs
@@ -311,6 +321,131 @@ YRT_HD void refit_item(const LbvhArrays& a, int leaf) {
         a.node_hi[p] = mk4(rmax(h0.x, h1.x), rmax(h0.y, h1.y), rmax(h0.z, h1.z), 0.f);
         p = a.parent_int[p];
     }
+}
+
+// ---- tree rotations (optional pass between refit and emit) ----------------------------------------
+// The radix tree splits every range at the spatial median of its Morton prefix, whatever the boxes look like.  One or
+// more bottom-up passes of tree rotations (Kensler 2008) repair the worst of it: at node p with children (L, R) and
+// R = (RL, RR), exchanging L with RL or RR leaves every subtree but R untouched, so the surface-area cost of the whole
+// tree changes by exactly area(R') - area(R); the best of the (up to) four exchanges is applied when it shrinks that
+// area.  Same arrival-counter walk as the refit (a node is handled by the second thread to reach it, when both subtrees
+// are final), so no two threads ever touch the same nodes.  Rotations never cross a segment (shape) boundary: the leaf
+// SET below p is unchanged, only its internal shape.  Afterwards the leaves below a node are no longer contiguous in
+// the sorted order, which the leaf references (first, count) need: relayout_* renumbers the leaf slots in tree order.
+#if defined(__CUDA_ARCH__)
+#define YRT_LDCG(p) __ldcg(p)
+#else
+#define YRT_LDCG(p) (*(p))
+#endif
+
+YRT_HD float half_area_(const float4& lo, const float4& hi) {
+    float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+YRT_HD void union_box_(const float4& l0, const float4& h0, const float4& l1, const float4& h1, float4& lo, float4& hi) {
+    lo = mk4(rmin(l0.x, l1.x), rmin(l0.y, l1.y), rmin(l0.z, l1.z), 0.f);
+    hi = mk4(rmax(h0.x, h1.x), rmax(h0.y, h1.y), rmax(h0.z, h1.z), 0.f);
+}
+// box / leaf count / parent link of a child reference whose subtree was finished by another thread
+YRT_HD void child_box_cg_(const LbvhArrays& a, int c, float4& lo, float4& hi) {
+    if (c < 0) { int it = a.order[~c]; lo = a.box_lo[it]; hi = a.box_hi[it]; }
+    else { lo = YRT_LDCG(&a.node_lo[c]); hi = YRT_LDCG(&a.node_hi[c]); }
+}
+YRT_HD int child_count_cg_(const LbvhArrays& a, int c) { return c < 0 ? 1 : YRT_LDCG(&a.count[c]); }
+YRT_HD void set_parent_(const LbvhArrays& a, int c, int p) {
+    if (c < 0) a.parent_leaf[~c] = p; else a.parent_int[c] = p;
+}
+
+YRT_HD void rotate_refit_item(const LbvhArrays& a, int leaf) {
+    int p = a.parent_leaf[leaf];
+    while (p >= 0) {
+        YRT_FENCE();
+        int old = YRT_ATOMIC_ADD(&a.flags[p], 1);
+        if (old == 0) return;
+        YRT_FENCE();
+        int c[2] = {YRT_LDCG(&a.left[p]), YRT_LDCG(&a.right[p])};
+        float4 lo[2], hi[2];
+        child_box_cg_(a, c[0], lo[0], hi[0]);
+        child_box_cg_(a, c[1], lo[1], hi[1]);
+        // the Karras range of p is still its leaf set (rotations below p only reshaped it)
+        bool one_segment = a.seg_of[a.order[a.range_first[p]]] == a.seg_of[a.order[a.range_last[p]]];
+        if (one_segment) {
+            float best = 0.f;
+            int best_side = -1, best_g = 0;
+            float4 best_lo = lo[0], best_hi = hi[0];
+            for (int side = 0; side < 2; side++) {          // `side` = the internal child that is reshaped
+                int r = c[side], l = c[1 - side];
+                if (r < 0) continue;
+                int g[2] = {YRT_LDCG(&a.left[r]), YRT_LDCG(&a.right[r])};
+                float ar = half_area_(lo[side], hi[side]);
+                for (int k = 0; k < 2; k++) {                 // grandchild g[k] moves up, l takes its place next to g[1-k]
+                    float4 gl, gh, nl, nh;
+                    child_box_cg_(a, g[1 - k], gl, gh);
+                    union_box_(lo[1 - side], hi[1 - side], gl, gh, nl, nh);
+                    float gain = ar - half_area_(nl, nh);
+                    if (gain > best) { best = gain; best_side = side; best_g = k; best_lo = nl; best_hi = nh; }
+                }
+                (void)l;
+            }
+            if (best_side >= 0) {
+                int r = c[best_side], l = c[1 - best_side];
+                int g[2] = {YRT_LDCG(&a.left[r]), YRT_LDCG(&a.right[r])};
+                int up = g[best_g], stay = g[1 - best_g];
+                // r keeps `stay` and adopts l; p keeps r and adopts `up`
+                if (best_g == 0) a.left[r] = l; else a.right[r] = l;
+                a.node_lo[r] = best_lo;
+                a.node_hi[r] = best_hi;
+                a.count[r] = child_count_cg_(a, l) + child_count_cg_(a, stay);
+                set_parent_(a, l, r);
+                if (best_side == 0) a.right[p] = up; else a.left[p] = up;
+                set_parent_(a, up, p);
+                // refresh p's view of its children
+                c[1 - best_side] = up;
+                child_box_cg_(a, up, lo[1 - best_side], hi[1 - best_side]);
+                lo[best_side] = best_lo; hi[best_side] = best_hi;
+            }
+        }
+        float4 nl, nh;
+        union_box_(lo[0], hi[0], lo[1], hi[1], nl, nh);
+        a.node_lo[p] = nl;
+        a.node_hi[p] = nh;
+        a.count[p] = child_count_cg_(a, c[0]) + child_count_cg_(a, c[1]);
+        p = YRT_LDCG(&a.parent_int[p]);
+    }
+}
+
+// new sorted slot of a leaf = number of leaves left of it in tree order; also the new [first, last] of every
+// internal node (written by its leftmost / rightmost leaf).  One leaf per call, two walks to the root.
+YRT_HD void relayout_slot_item(const LbvhArrays& a, int leaf) {
+    int pos = 0;
+    int child = ~leaf;
+    for (int p = a.parent_leaf[leaf]; p >= 0; p = a.parent_int[p]) {
+        if (a.right[p] == child) { int l = a.left[p]; pos += l < 0 ? 1 : a.count[l]; }
+        child = p;
+    }
+    a.new_slot[leaf] = pos;
+    bool leftmost = true, rightmost = true;
+    child = ~leaf;
+    for (int p = a.parent_leaf[leaf]; p >= 0 && (leftmost || rightmost); p = a.parent_int[p]) {
+        if (a.right[p] == child) leftmost = false; else rightmost = false;
+        if (leftmost) a.range_first[p] = pos;
+        if (rightmost) a.range_last[p] = pos;
+        child = p;
+    }
+}
+YRT_HD void relayout_move_item(const LbvhArrays& a, int leaf) {
+    int s = a.new_slot[leaf];
+    a.order_tmp[s] = a.order[leaf];
+    a.parent_leaf_tmp[s] = a.parent_leaf[leaf];
+}
+YRT_HD void relayout_copy_item(const LbvhArrays& a, int slot) {
+    a.order[slot] = a.order_tmp[slot];
+    a.parent_leaf[slot] = a.parent_leaf_tmp[slot];
+}
+YRT_HD void relayout_refs_item(const LbvhArrays& a, int i) {
+    int l = a.left[i], r = a.right[i];
+    if (l < 0) a.left[i] = ~a.new_slot[~l];
+    if (r < 0) a.right[i] = ~a.new_slot[~r];
 }
 
 // reference of a child for traversal: subtrees of <= leaf_size items become one leaf

@@ -1,8 +1,16 @@
 // raytrace_main.cpp — the drop-in `raytrace` CLI: the reference's main() (src/raytrace.cpp:256-287)
 // with build_bvh(scn,false) (:278) and raytrace(scn, amb, resolution, samples) (:282) replaced by the
 // C ABI of include/yrt_b200.h.  Everything else is the reference's own code, linked unchanged:
-// load_scene (src/scene.cpp:113), save_hdr_or_ldr (src/image.cpp:81), yu::cmdline
-// (src/ext/yocto_utils.h:1085+).  Same flags, same four progress lines; additive flags only.
+// load_scene (src/scene.cpp:113), save_hdr_or_ldr / save_image (src/image.cpp:81,:36), yu::cmdline
+// (src/ext/yocto_utils.h:1085+).  Same flags, same four progress lines; additive flags only:
+//   --gpus N       interleaved row tiles over N GPUs
+//   --cache        keep the flattened scene next to the OBJ (<scene>.yrts) and reuse it while it is not older than
+//                  the OBJ: skips load_scene (SURVEY 8f.2 — the OBJ parse costs more than a frame)
+//   --device-ldr   tonemap on the GPU (yrt_render_ldr): a quarter of the bytes cross to the host and
+//                  the host tonemap (src/image.cpp:55-78) is skipped; ignored for .hdr outputs
+//   --stats        ray counts and the time of every phase
+#include <sys/stat.h>
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -10,6 +18,17 @@
 #include "ext/yocto_utils.h"   // reference
 #include "scene.h"             // reference
 #include "yrt_flatten.h"
+
+namespace {
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// the cache is valid if it exists and is not older than the scene file
+bool cache_is_fresh(const std::string& scene_path, const std::string& cache_path) {
+    struct stat a, b;
+    if (stat(scene_path.c_str(), &a) != 0 || stat(cache_path.c_str(), &b) != 0) return false;
+    return b.st_mtime >= a.st_mtime;
+}
+}  // namespace
 
 int main(int argc, char** argv) {
     auto parser = yu::cmdline::make_parser(argc, argv, "raytrace", "raytrace scene");
@@ -20,23 +39,38 @@ int main(int argc, char** argv) {
     // additive (not in the reference)
     auto gpus = yu::cmdline::parse_opti(parser, "--gpus", "-g", "number of GPUs (interleaved row tiles)", 1);
     auto verbose = yu::cmdline::parse_flag(parser, "--stats", "", "print ray counts and timings", false);
+    auto use_cache = yu::cmdline::parse_flag(parser, "--cache", "", "reuse / write the flattened scene <scene>.yrts", false);
+    auto device_ldr = yu::cmdline::parse_flag(parser, "--device-ldr", "", "tonemap on the GPU (8-bit outputs)", false);
     auto scenein = yu::cmdline::parse_args(parser, "scenein", "input scene", "scene.obj", true);
     yu::cmdline::check_parser(parser);
 
+    double t_start = now_ms();
     printf("loading scene %s\n", scenein.c_str());
-    auto scn = load_scene(scenein);
-
-    printf("creating bvh\n");
     yrt_flat_scene flat;
     std::string err;
-    if (!yrt_flatten(scn, flat, err)) {
-        printf("could not flatten scene: %s\n", err.c_str());
-        exit(1);
+    std::string cache_path = scenein + ".yrts";
+    bool from_cache = false;
+    if (use_cache && cache_is_fresh(scenein, cache_path)) {
+        from_cache = yrt_flat_load(cache_path, flat, err);
+        if (!from_cache) printf("ignoring scene cache: %s\n", err.c_str());
+    }
+    double t_loaded = now_ms(), t_flat = t_loaded;
+    if (!from_cache) {
+        auto scn = load_scene(scenein);
+        t_loaded = now_ms();
+        if (!yrt_flatten(scn, flat, err)) {
+            printf("could not flatten scene: %s\n", err.c_str());
+            exit(1);
+        }
+        t_flat = now_ms();
+        if (use_cache && !yrt_flat_save(flat, cache_path, err)) printf("could not write scene cache: %s\n", err.c_str());
     }
     if (!flat.has_camera) {
         printf("scene has no camera\n");
         exit(1);
     }
+
+    printf("creating bvh\n");
     if (yrt_init(gpus) != YRT_OK) {
         printf("%s\n", yrt_last_error());
         exit(1);
@@ -47,27 +81,43 @@ int main(int argc, char** argv) {
         printf("%s\n", yrt_last_error());
         exit(1);
     }
+    double t_built = now_ms();
 
     printf("tracing scene\n");
-    auto cam = scn->cameras.front();
-    auto hdr = image4f((int)std::round(cam->aspect * resolution), resolution);   // src/raytrace.cpp:216
+    int width = yrt_image_width(&flat.cam, resolution);   // (int)std::round(cam->aspect * resolution), src/raytrace.cpp:216
+    bool want_hdr = imageout.length() >= 4 && imageout.substr(imageout.length() - 4) == ".hdr";   // src/image.cpp:82
+    bool ldr_on_device = device_ldr && !want_hdr;
+    auto hdr = image4f();
+    auto ldr = image4b();
     float ambient[3] = {amb, amb, amb};
     yrt_stats st;
-    auto t0 = std::chrono::steady_clock::now();
-    if (yrt_render(gscn, &flat.cam, ambient, hdr.width, hdr.height, samples, (float*)hdr.pixels.data(), &st) != YRT_OK) {
+    int rc;
+    if (ldr_on_device) {
+        ldr = image4b(width, resolution);
+        rc = yrt_render_ldr(gscn, &flat.cam, ambient, width, resolution, samples, (uint8_t*)ldr.pixels.data(), nullptr, &st);
+    } else {
+        hdr = image4f(width, resolution);
+        rc = yrt_render(gscn, &flat.cam, ambient, width, resolution, samples, (float*)hdr.pixels.data(), &st);
+    }
+    if (rc != YRT_OK) {
         printf("%s\n", yrt_last_error());
         exit(1);
     }
-    auto t1 = std::chrono::steady_clock::now();
-    if (verbose) {
-        double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
-        long long rays = (long long)(st.primary_rays + st.reflection_rays + st.shadow_rays);
-        printf("rays %lld (primary %lld, reflection %lld, shadow %lld) on %d GPU(s): %.3f ms device, %.3f ms call, %.1f Mrays/s\n", rays,
-               (long long)st.primary_rays, (long long)st.reflection_rays, (long long)st.shadow_rays, st.n_gpus, st.ms_total, ms,
-               rays / (ms * 1e3));
-    }
+    double t_traced = now_ms();
     yrt_scene_destroy(gscn);
 
     printf("saving image %s\n", imageout.c_str());
-    save_hdr_or_ldr(imageout, hdr);
+    if (ldr_on_device) save_image(imageout, ldr);   // what save_hdr_or_ldr does after its host tonemap (src/image.cpp:85-86)
+    else save_hdr_or_ldr(imageout, hdr);
+    double t_saved = now_ms();
+
+    if (verbose) {
+        long long rays = (long long)(st.primary_rays + st.reflection_rays + st.shadow_rays);
+        double ms = t_traced - t_built;
+        printf("rays %lld (primary %lld, reflection %lld, shadow %lld) on %d GPU(s): %.3f ms device, %.3f ms call, %.1f Mrays/s\n", rays,
+               (long long)st.primary_rays, (long long)st.reflection_rays, (long long)st.shadow_rays, st.n_gpus, st.ms_total, ms,
+               rays / (ms * 1e3));
+        printf("phases ms: load %.1f%s, flatten %.1f, init+upload+bvh %.1f, trace %.1f, tonemap+save %.1f, total %.1f\n", t_loaded - t_start,
+               from_cache ? " (scene cache)" : "", t_flat - t_loaded, t_built - t_flat, ms, t_saved - t_traced, t_saved - t_start);
+    }
 }

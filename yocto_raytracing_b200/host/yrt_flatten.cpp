@@ -195,3 +195,49 @@ bool yrt_flat_save(const yrt_flat_scene& fs, const std::string& path, std::strin
     if (!ok) err = "write error on " + path;
     return ok;
 }
+
+bool yrt_flat_load(const std::string& path, yrt_flat_scene& fs, std::string& err) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { err = "cannot open " + path; return false; }
+    char magic[8];
+    int32_t n_arrays = 0, reserved = 0;
+    bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "YRTSCN01", 8) == 0 && fread(&n_arrays, 4, 1, f) == 1 && fread(&reserved, 4, 1, f) == 1;
+    if (!ok) { fclose(f); err = path + ": not a YRTSCN01 file"; return false; }
+    fs = yrt_flat_scene();
+    std::vector<float> cam;
+    for (int a = 0; a < n_arrays && ok; a++) {
+        char nm[25] = {0};
+        int32_t dt = 0;
+        int64_t count = 0;
+        ok = fread(nm, 1, 24, f) == 24 && fread(&dt, 4, 1, f) == 1 && fread(&count, 8, 1, f) == 1 && count >= 0 && dt >= 0 && dt <= 3;
+        if (!ok) break;
+        static const size_t esz[4] = {4, 4, 1, 8};
+        size_t bytes = (size_t)count * esz[dt];
+        std::string name(nm);
+        void* dst = nullptr;
+        auto want = [&](const char* n, int t) { return name == n && dt == t; };
+#define YRT_I32(field) if (want(#field, 0)) { fs.field.resize((size_t)count); dst = fs.field.data(); }
+#define YRT_F32(field) if (want(#field, 1)) { fs.field.resize((size_t)count); dst = fs.field.data(); }
+        YRT_I32(shape_kind) YRT_I32(shape_elem_off) YRT_I32(shape_elem_cnt) YRT_I32(shape_vert_off) YRT_I32(shape_vert_cnt)
+        YRT_I32(shape_has_uv) YRT_I32(shape_has_radius) YRT_I32(elem_idx) YRT_I32(inst_shape) YRT_I32(inst_mat)
+        YRT_I32(mat_kd_tex) YRT_I32(mat_ks_tex) YRT_I32(tex_w) YRT_I32(tex_h)
+        YRT_F32(pos) YRT_F32(norm) YRT_F32(uv) YRT_F32(radius) YRT_F32(inst_frame)
+        YRT_F32(mat_ke) YRT_F32(mat_kd) YRT_F32(mat_ks) YRT_F32(mat_kr) YRT_F32(mat_rs)
+#undef YRT_I32
+#undef YRT_F32
+        if (want("tex_off", 3)) { fs.tex_off.resize((size_t)count); dst = fs.tex_off.data(); }
+        if (want("tex_rgba8", 2)) { fs.tex_rgba8.resize((size_t)count); dst = fs.tex_rgba8.data(); }
+        if (want("camera", 1)) { cam.resize((size_t)count); dst = cam.data(); }
+        if (dst) ok = bytes == 0 || fread(dst, 1, bytes, f) == bytes;
+        else ok = fseek(f, (long)bytes, SEEK_CUR) == 0;   // unknown array: skip
+        if (ok && bytes % 8) ok = fseek(f, (long)(8 - bytes % 8), SEEK_CUR) == 0;
+    }
+    fclose(f);
+    if (!ok) { err = path + ": truncated or malformed"; return false; }
+    if (cam.size() == 16) {
+        memcpy(fs.cam.frame, cam.data(), 12 * sizeof(float));
+        fs.cam.fovy = cam[12]; fs.cam.aspect = cam[13]; fs.cam.aperture = cam[14]; fs.cam.focus = cam[15];
+        fs.has_camera = true;
+    }
+    return true;
+}

@@ -39,5 +39,7 @@ yrt_camera yrt_flatten_camera(const camera* cam);
 
 // "YRTSCN01" container (named typed arrays) read by yocto_raytracing_b200/scene.py
 bool yrt_flat_save(const yrt_flat_scene& fs, const std::string& path, std::string& err);
+// ... and read back: the CLI's scene cache (parsing the 3.3 MB instance10000 OBJ costs more than a frame)
+bool yrt_flat_load(const std::string& path, yrt_flat_scene& fs, std::string& err);
 
 #endif
