@@ -25,7 +25,7 @@ struct EmuLbvh {
 };
 
 void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi, const int* seg_of, const int* seg_first, int leaf_size,
-              EmuLbvh& out, int ref_offset, int size_bits, int rotate_rounds) {
+              EmuLbvh& out, int ref_offset, int size_bits, int rotate_rounds, int rotate_pairs) {
     size_t ni = n > 1 ? n - 1 : 1;
     std::vector<int> cent_lo(3 * n_seg), cent_hi(3 * n_seg);
     out.seg_box_lo.assign(3 * n_seg, 0);
@@ -46,6 +46,7 @@ void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi
     a.count = count.data(); a.new_slot = new_slot.data(); a.order_tmp = order_tmp.data(); a.parent_leaf_tmp = pleaf_tmp.data();
     a.flags = flags.data(); a.node_lo = nlo.data(); a.node_hi = nhi.data(); a.nodes = out.nodes.data();
     a.seg_root = out.seg_root.data(); a.seg_depth = out.seg_depth.data(); a.leaf_size = leaf_size; a.ref_offset = ref_offset; a.size_bits = size_bits;
+    a.rotate_pairs = rotate_pairs;
     for (int s = 0; s < n_seg; s++) seg_bounds_init_item(a, s);
     for (int i = 0; i < n; i++) seg_bounds_item(a, i);
     for (int i = 0; i < n; i++) morton_item(a, i);
@@ -105,7 +106,8 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
     }
     int nseg = std::max(hs.n_shapes, 1);
     emu_lbvh(np, nseg, plo, phi, g.prim_shape, g.shape_prim_off, leaf_blas, es.blas, 0, getenv("YRT_SIZE_BITS_BLAS") ? atoi(getenv("YRT_SIZE_BITS_BLAS")) : YRT_SIZE_BITS_BLAS,
-             getenv("YRT_ROTATE_BLAS") ? atoi(getenv("YRT_ROTATE_BLAS")) : YRT_ROTATE_ROUNDS_BLAS);
+             getenv("YRT_ROTATE_BLAS") ? atoi(getenv("YRT_ROTATE_BLAS")) : YRT_ROTATE_ROUNDS_BLAS,
+             getenv("YRT_ROTATE_PAIRS_BLAS") ? atoi(getenv("YRT_ROTATE_PAIRS_BLAS")) : YRT_ROTATE_PAIRS_BLAS);
     // prim + attribute records in BLAS leaf order (mirrors k_gather_prims)
     es.prim_recs.assign(3 * (size_t)std::max(np, 1), mk4(0, 0, 0, 0));
     es.prim_attrs.assign(YRT_ATTR_STRIDE * (size_t)std::max(np, 1), mk4(0, 0, 0, 0));
@@ -147,7 +149,8 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
     int sf[2] = {0, na};
     int nb_int = np > 1 ? np - 1 : 0;
     emu_lbvh(na, 1, ilo, ihi, seg_of.data(), sf, leaf_tlas, es.tlas, nb_int, getenv("YRT_SIZE_BITS_TLAS") ? atoi(getenv("YRT_SIZE_BITS_TLAS")) : YRT_SIZE_BITS_TLAS,
-             getenv("YRT_ROTATE_TLAS") ? atoi(getenv("YRT_ROTATE_TLAS")) : YRT_ROTATE_ROUNDS_TLAS);
+             getenv("YRT_ROTATE_TLAS") ? atoi(getenv("YRT_ROTATE_TLAS")) : YRT_ROTATE_ROUNDS_TLAS,
+             getenv("YRT_ROTATE_PAIRS_TLAS") ? atoi(getenv("YRT_ROTATE_PAIRS_TLAS")) : YRT_ROTATE_PAIRS_TLAS);
     es.nodes.assign(es.blas.nodes.begin(), es.blas.nodes.begin() + 4 * (size_t)nb_int);
     es.nodes.insert(es.nodes.end(), es.tlas.nodes.begin(), es.tlas.nodes.end());
     es.inst_recs.assign(4 * (size_t)std::max(na, 1), mk4(0, 0, 0, 0));

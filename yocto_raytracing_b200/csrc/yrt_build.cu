@@ -265,6 +265,7 @@ struct LbvhOut {
     int ref_offset;       // index of this tree set's node 0 in the shared node array
     int size_bits;        // size-class bits in the sort key (see morton_item)
     int rotate_rounds;    // bottom-up tree-rotation passes after the refit (see rotate_refit_item)
+    int rotate_pairs;     // ... that also try grandchild pair exchanges
     DevBuf* seg_root;     // [n_seg]
     DevBuf* seg_depth;    // [n_seg]
     DevBuf* order;        // [n] item id at sorted slot
@@ -338,6 +339,7 @@ static int lbvh_build(int dev, cudaStream_t st, int n, int n_seg, float4* box_lo
     a.nodes = out.nodes;
     a.ref_offset = out.ref_offset;
     a.size_bits = out.size_bits;
+    a.rotate_pairs = out.rotate_pairs;
     a.seg_root = out.seg_root->as<int>();
     a.seg_depth = out.seg_depth->as<int>();
     a.leaf_size = leaf_size;
@@ -434,6 +436,8 @@ int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
     const char* env_rt = getenv("YRT_ROTATE_TLAS");
     int rotate_blas = std::min(std::max(env_rb ? atoi(env_rb) : YRT_ROTATE_ROUNDS_BLAS, 0), 8);
     int rotate_tlas = std::min(std::max(env_rt ? atoi(env_rt) : YRT_ROTATE_ROUNDS_TLAS, 0), 8);
+    int rotate_pairs_blas = getenv("YRT_ROTATE_PAIRS_BLAS") ? atoi(getenv("YRT_ROTATE_PAIRS_BLAS")) : YRT_ROTATE_PAIRS_BLAS;
+    int rotate_pairs_tlas = getenv("YRT_ROTATE_PAIRS_TLAS") ? atoi(getenv("YRT_ROTATE_PAIRS_TLAS")) : YRT_ROTATE_PAIRS_TLAS;
     leaf_blas = std::min(std::max(leaf_blas, 1), YRT_LEAF_MAX_COUNT);
     leaf_tlas = std::min(std::max(leaf_tlas, 1), YRT_LEAF_MAX_COUNT);
 
@@ -462,7 +466,7 @@ int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
     int nb_int = hs.n_prims > 1 ? hs.n_prims - 1 : 0, nt_int = ds.n_active > 1 ? ds.n_active - 1 : 0;
     YRT_TRY(ds.nodes.alloc(sizeof(float4) * 4 * (size_t)(nb_int + nt_int + 2), device));
     LbvhOut bo;
-    bo.nodes = ds.nodes.as<float4>(); bo.ref_offset = 0; bo.size_bits = size_bits_blas; bo.rotate_rounds = rotate_blas; bo.seg_root = &ds.blas_seg_root; bo.seg_depth = &ds.blas_seg_depth; bo.order = &blas_order;
+    bo.nodes = ds.nodes.as<float4>(); bo.ref_offset = 0; bo.size_bits = size_bits_blas; bo.rotate_rounds = rotate_blas; bo.rotate_pairs = rotate_pairs_blas; bo.seg_root = &ds.blas_seg_root; bo.seg_depth = &ds.blas_seg_depth; bo.order = &blas_order;
     bo.seg_box_lo = &ds.shape_box_lo; bo.seg_box_hi = &ds.shape_box_hi;
     YRT_TRY(lbvh_build(device, st, hs.n_prims, std::max(hs.n_shapes, 1), plo.as<float4>(), phi.as<float4>(), g.prim_shape,
                        g.shape_prim_off, leaf_blas, bo));
@@ -487,7 +491,7 @@ int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
         k_inst_boxes<<<grid_for(na), 256, 0, st>>>(na, ds.active_inst.as<int>(), ds.inst_frame.as<float>(), ds.inst_shape.as<int>(),
                                                  ds.shape_box_lo.as<int>(), ds.shape_box_hi.as<int>(), ilo.as<float4>(), ihi.as<float4>());
     LbvhOut to;
-    to.nodes = ds.nodes.as<float4>() + 4 * (size_t)nb_int; to.ref_offset = nb_int; to.size_bits = size_bits_tlas; to.rotate_rounds = rotate_tlas; to.seg_root = &ds.tlas_seg_root; to.seg_depth = &ds.tlas_seg_depth; to.order = &tlas_order;
+    to.nodes = ds.nodes.as<float4>() + 4 * (size_t)nb_int; to.ref_offset = nb_int; to.size_bits = size_bits_tlas; to.rotate_rounds = rotate_tlas; to.rotate_pairs = rotate_pairs_tlas; to.seg_root = &ds.tlas_seg_root; to.seg_depth = &ds.tlas_seg_depth; to.order = &tlas_order;
     to.seg_box_lo = nullptr; to.seg_box_hi = nullptr;
     YRT_TRY(lbvh_build(device, st, na, 1, ilo.as<float4>(), ihi.as<float4>(), tl_seg_of.as<int>(), tl_seg_first.as<int>(), leaf_tlas, to));
     YRT_TRY(ds.inst_recs.alloc(sizeof(float4) * 4 * (size_t)std::max(na, 1), device));

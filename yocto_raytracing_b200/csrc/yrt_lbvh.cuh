@@ -25,6 +25,8 @@ namespace yrt {
 #ifndef YRT_ROTATE_ROUNDS_TLAS
 #define YRT_ROTATE_ROUNDS_TLAS 2
 #endif
+#define YRT_ROTATE_PAIRS_BLAS 1     /* rotations also try the other two pairings of the four grandchildren ... */
+#define YRT_ROTATE_PAIRS_TLAS 0     /* ... which costs the instance tree more than it gains (host emulation, box tests per ray) */
 #define YRT_LEAF_SIZE_TLAS 1   /* one instance per TLAS leaf: its world box is tested before the ray is transformed */
 
 // ---- order-preserving float <-> int for atomic min/max --------------------------------------
@@ -145,6 +147,7 @@ struct LbvhArrays {
     int leaf_size;
     int ref_offset;        // added to every internal-node reference (position of this tree set in the shared node array)
     int size_bits;         // 0..3: top bits of the Morton part hold a size class (see morton_item)
+    int rotate_pairs;      // rotations also try the two other pairings of the four grandchildren (helps the BLAS, hurts the TLAS)
 };
 
 YRT_HD void seg_bounds_init_item(const LbvhArrays& a, int s) {
@@ -386,6 +389,37 @@ YRT_HD void rotate_refit_item(const LbvhArrays& a, int leaf) {
                     if (gain > best) { best = gain; best_side = side; best_g = k; best_lo = nl; best_hi = nh; }
                 }
                 (void)l;
+            }
+            // both children internal: the two other pairings of the four grandchildren (LL,LR | RL,RR) ->
+            // (LL,RL | LR,RR) and (LL,RR | LR,RL); cost change = area(L') + area(R') - area(L) - area(R)
+            int pair = -1;
+            float4 pl0, ph0, pl1, ph1;
+            if (a.rotate_pairs && c[0] >= 0 && c[1] >= 0) {
+                int gl[2] = {YRT_LDCG(&a.left[c[0]]), YRT_LDCG(&a.right[c[0]])};
+                int gr[2] = {YRT_LDCG(&a.left[c[1]]), YRT_LDCG(&a.right[c[1]])};
+                float4 bl[4], bh[4];
+                child_box_cg_(a, gl[0], bl[0], bh[0]); child_box_cg_(a, gl[1], bl[1], bh[1]);
+                child_box_cg_(a, gr[0], bl[2], bh[2]); child_box_cg_(a, gr[1], bl[3], bh[3]);
+                float cur = half_area_(lo[0], hi[0]) + half_area_(lo[1], hi[1]);
+                for (int k = 0; k < 2; k++) {   // LL pairs with RL (k = 0) or RR (k = 1)
+                    float4 l0_, h0_, l1_, h1_;
+                    union_box_(bl[0], bh[0], bl[2 + k], bh[2 + k], l0_, h0_);
+                    union_box_(bl[1], bh[1], bl[3 - k], bh[3 - k], l1_, h1_);
+                    float gain = cur - half_area_(l0_, h0_) - half_area_(l1_, h1_);
+                    if (gain > best) { best = gain; pair = k; best_side = -1; pl0 = l0_; ph0 = h0_; pl1 = l1_; ph1 = h1_; }
+                }
+                if (pair >= 0) {
+                    // L keeps LL and takes gr[pair]; R keeps gr[1 - pair] and takes LR
+                    int L = c[0], R = c[1], take = gr[pair], give = gl[1];
+                    a.right[L] = take; set_parent_(a, take, L);
+                    if (pair == 0) a.left[R] = give; else a.right[R] = give;
+                    set_parent_(a, give, R);
+                    a.node_lo[L] = pl0; a.node_hi[L] = ph0;
+                    a.node_lo[R] = pl1; a.node_hi[R] = ph1;
+                    a.count[L] = child_count_cg_(a, gl[0]) + child_count_cg_(a, take);
+                    a.count[R] = child_count_cg_(a, gr[1 - pair]) + child_count_cg_(a, give);
+                    lo[0] = pl0; hi[0] = ph0; lo[1] = pl1; hi[1] = ph1;
+                }
             }
             if (best_side >= 0) {
                 int r = c[best_side], l = c[1 - best_side];
