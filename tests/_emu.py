@@ -77,3 +77,15 @@ class EmuScene:
                 lib().emu_scene_destroy(self.h)
         except Exception:
             pass
+
+
+def workdist(mode, width=0, nrows=0, spp=1, tile_w=16, tile_h=8, chunk_items=2048, n_items=0, n_threads=16, n_sm=4):
+    """Runs the persistent kernels' work-distribution protocol (csrc/yrt_work.cuh) on host threads.
+    Returns (per-item hand-out counts, n_chunks, tasks handed out, max tasks of one thread)."""
+    n = width * nrows * spp if mode == 1 else n_items
+    count = np.zeros(max(n, 1), np.uint8)
+    tasks = C.c_longlong(0)
+    mx = C.c_longlong(0)
+    nc = lib().emu_workdist(mode, width, nrows, spp, tile_w, tile_h, C.c_uint(chunk_items), C.c_uint(n), n_threads, n_sm,
+                            C.c_void_p(count.ctypes.data), C.byref(tasks), C.byref(mx))
+    return count[:n], nc, tasks.value, mx.value

@@ -9,11 +9,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "yrt_internal.h"
 #include "yrt_shade.cuh"
 #include "yrt_trace.cuh"
+#include "yrt_work.cuh"
 
 using namespace yrt;
 
@@ -331,6 +333,46 @@ int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, in
     if (ray_counts) { ray_counts[0] = (long long)width * height * samples * samples; ray_counts[1] = n_refl; ray_counts[2] = n_shadow;
         ray_counts[3] = sb; ray_counts[4] = stb; ray_counts[5] = sp_; ray_counts[6] = si_; ray_counts[7] = socc; }
     return YRT_OK;
+}
+
+// The work-distribution protocol of the persistent kernels (yrt_work.cuh), run by host threads playing warps:
+// n_threads "warps" spread over n_sm state words fetch tasks until the input is exhausted and count, per item, how
+// often it was handed out (must be exactly once).  mode 1: tiles over nrows x width x spp; mode 2: runs over n_items.
+struct HostAtomics {
+    unsigned long long add64(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+    unsigned long long exch64(unsigned long long* p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+    unsigned long long load64(unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+    unsigned add32(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+    void pause() { std::this_thread::yield(); }
+};
+
+int emu_workdist(int mode, int width, int nrows, int spp, int tile_w, int tile_h, unsigned chunk_items, unsigned n_items, int n_threads,
+                 int n_sm, uint8_t* count, long long* tasks_out, long long* max_tasks_per_thread) {
+    std::vector<unsigned> rec(YRT_WORK_BLOCK_WORDS, 0u);
+    WorkDist wd = mode == 1 ? workdist_tiles(rec.data(), width, nrows, spp, tile_w, tile_h) : workdist_runs(rec.data(), n_items, chunk_items);
+    std::vector<long long> per_thread(n_threads, 0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++)
+        th.emplace_back([&, t]() {
+            HostAtomics at;
+            unsigned chunk, k;
+            while (fetch_task(at, wd, (unsigned)(t % n_sm), chunk, k)) {
+                per_thread[t]++;
+                for (int lane = 0; lane < 32; lane++) {
+                    unsigned item;
+                    if (task_item(wd, chunk, k, lane, item)) {
+                        if (item >= wd.n_items) { __atomic_fetch_add(&count[0], (uint8_t)100, __ATOMIC_RELAXED); continue; }
+                        __atomic_fetch_add(&count[item], (uint8_t)1, __ATOMIC_RELAXED);
+                    }
+                }
+            }
+        });
+    for (auto& x : th) x.join();
+    long long total = 0, mx = 0;
+    for (long long v : per_thread) { total += v; if (v > mx) mx = v; }
+    *tasks_out = total;
+    *max_tasks_per_thread = mx;
+    return (int)wd.n_chunks;
 }
 
 }  // extern "C"

@@ -145,6 +145,29 @@ def test_determinism_and_batching(gpu, monkeypatch):
     assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
 
 
+def test_work_distribution_modes_are_bit_identical(gpu, monkeypatch):
+    """SM-affine tiles (csrc/yrt_work.cuh) only change which warp traces which ray: the frame, the hit ids and the ray
+    counts must not depend on the scheme, the tile shape (ragged edges included) or the run length of the queues."""
+    flat = synth.mixed_scene(11).flat()          # reflective floor: exercises the queue launches too
+    w, h, s = 131, 73, 3
+    with gpu.Scene(flat) as scn:
+        monkeypatch.setenv("YRT_TILE", "0")
+        a, sa = scn.render(w, h, s, 0.1)
+        ia, da, _ = scn.trace_primary(w, h, s)
+        for env in ({}, {"YRT_TILE_W": "5", "YRT_TILE_H": "3", "YRT_TILES_PER_SM": "0"}, {"YRT_TILE_W": "64", "YRT_TILE_H": "64", "YRT_TILES_PER_SM": "0"},
+                    {"YRT_CHUNK_ITEMS": "33"}, {"YRT_BATCH_SLOTS": "7000"}):
+            env = dict(env, YRT_TILE="1")
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            b, sb = scn.render(w, h, s, 0.1)
+            ib, db, _ = scn.trace_primary(w, h, s)
+            for k in env:
+                monkeypatch.delenv(k)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), env
+            assert np.array_equal(ia, ib) and np.array_equal(da.view(np.uint32), db.view(np.uint32)), env
+            assert (sa.primary_rays, sa.shadow_rays, sa.reflection_rays) == (sb.primary_rays, sb.shadow_rays, sb.reflection_rays), env
+
+
 def test_edge_cases(gpu, oracle_mod):
     # empty scene: no shapes, no instances -> black, alpha 1
     sc = synth.SynthScene(name="empty")

@@ -24,11 +24,15 @@
 #include "yrt_shade.cuh"
 #include "yrt_trace.cuh"
 #include "yrt_packet.cuh"
+#include "yrt_work.cuh"
 
 namespace yrt {
 
 #ifndef YRT_DEFAULT_STREAMS
 #define YRT_DEFAULT_STREAMS 2   /* pipelines per frame (see render_rows_device) */
+#endif
+#ifndef YRT_TILE_DEFAULT
+#define YRT_TILE_DEFAULT 0   /* 1: SM-affine tiles (yrt_work.cuh), 0: every warp takes the next 32 slots; YRT_TILE overrides at run time */
 #endif
 #define TRACE_THREADS 128
 #ifndef TRACE_MIN_BLOCKS
@@ -69,6 +73,36 @@ __device__ __forceinline__ unsigned warp_fetch(unsigned* counter, int lane) {
     return __shfl_sync(0xffffffffu, base, 0);
 }
 
+__device__ __forceinline__ unsigned sm_id() {
+    unsigned r;
+    asm("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+
+// next 32 work items of the warp (yrt_work.cuh): false = the launch has no work left; `alive` = this lane has an item
+__device__ __forceinline__ bool warp_next(const WorkDist& wd, int lane, unsigned& item, bool& alive) {
+    if (wd.mode == 0) {
+        unsigned base = warp_fetch(wd.counter, lane);
+        if (base >= wd.n_items) return false;
+        item = base + lane;
+        alive = item < wd.n_items;
+        return true;
+    }
+    unsigned chunk = 0, k = 0;
+    int ok = 0;
+    if (lane == 0) {
+        DeviceAtomics at;
+        ok = fetch_task(at, wd, sm_id(), chunk, k) ? 1 : 0;
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (!ok) return false;
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    item = 0;
+    alive = task_item(wd, chunk, k, lane, item);
+    return true;
+}
+
 // ---- closest hit --------------------------------------------------------------------------
 // PRIMARY: slot = work index, ray from the camera. Otherwise slot = act[idx] (or idx) and the ray
 // comes from ray_o/ray_d (o.xyz|tmin, d.xyz|tmax).
@@ -78,15 +112,14 @@ template <bool PRIMARY, bool PACKET>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_closest(SceneView sv, BatchParams bp, const int* __restrict__ act,
                                                                  const float4* __restrict__ ray_o,
                                                                  const float4* __restrict__ ray_d, float4* __restrict__ hit_out,
-                                                                 float4* __restrict__ P_out, unsigned n, unsigned* counter) {
+                                                                 float4* __restrict__ P_out, WorkDist wd) {
     const int lane = threadIdx.x & 31;
     __shared__ int wstacks[PACKET ? TRACE_THREADS / 32 : 1][PACKET ? YRT_WSTACK : 1];
     int stack[PACKET ? 1 : YRT_STACK_CAP];
     for (;;) {
-        unsigned base = warp_fetch(counter, lane);
-        if (base >= n) break;
-        unsigned idx = base + lane;
-        const bool alive = idx < n;
+        unsigned idx = 0;
+        bool alive = false;
+        if (!warp_next(wd, lane, idx, alive)) break;
         unsigned slot = 0;
         ray3 ray;
         ray.o = mk3(0.f, 0.f, 0.f); ray.d = mk3(0.f, 0.f, 1.f); ray.tmin = 0.f; ray.tmax = 0.f;
@@ -131,15 +164,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_close
 template <bool PACKET>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS_ANY) k_trace_any_lights(SceneView sv, size_t cap_slots, const int* __restrict__ act,
                                                                     const float4* __restrict__ hit, const float4* __restrict__ P,
-                                                                    uint8_t* __restrict__ vis, unsigned n_act, unsigned* counter) {
+                                                                    uint8_t* __restrict__ vis, WorkDist wd) {
     const int lane = threadIdx.x & 31;
     __shared__ int wstacks[PACKET ? TRACE_THREADS / 32 : 1][PACKET ? YRT_WSTACK : 1];
     int stack[PACKET ? 1 : YRT_STACK_CAP];
     for (;;) {
-        unsigned base = warp_fetch(counter, lane);
-        if (base >= n_act) break;
-        unsigned a = base + lane;
-        bool alive = a < n_act;
+        unsigned a = 0;
+        bool alive = false;
+        if (!warp_next(wd, lane, a, alive)) break;
         unsigned slot = 0;
         vec3 p = mk3(0.f, 0.f, 0.f);
         if (alive) {
@@ -167,14 +199,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS_ANY) k_trace_a
 // any hit on explicit rays (intersect_any, scene.cpp:489)
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_any_rays(SceneView sv, const float4* __restrict__ ray_o,
                                                                   const float4* __restrict__ ray_d, uint8_t* __restrict__ occ_out,
-                                                                  unsigned n, unsigned* counter) {
+                                                                  WorkDist wd) {
     const int lane = threadIdx.x & 31;
     int stack[YRT_STACK_CAP];
     for (;;) {
-        unsigned base = warp_fetch(counter, lane);
-        if (base >= n) break;
-        unsigned idx = base + lane;
-        if (idx >= n) continue;
+        unsigned idx = 0;
+        bool alive = false;
+        if (!warp_next(wd, lane, idx, alive)) break;
+        if (!alive) continue;
         float4 o = ray_o[idx], d = ray_d[idx];
         ray3 ray;
         ray.o = xyz(o); ray.d = xyz(d); ray.tmin = o.w; ray.tmax = d.w;
@@ -273,18 +305,16 @@ __global__ void __launch_bounds__(256, 4) k_shade(SceneView sv, BatchParams bp, 
 // launch (and one kernel tail) less per wave.  Up to 32 lights.
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow_shade(SceneView sv, BatchParams bp, ShadeBuffers sb, int depth,
                                                                                  int max_depth, const int* __restrict__ act,
-                                                                                 unsigned n_act, const float4* __restrict__ P,
-                                                                                 unsigned* counter) {
+                                                                                 const float4* __restrict__ P, WorkDist wd) {
     __shared__ float lut[256];
     for (int i = threadIdx.x; i < 256; i += TRACE_THREADS) lut[i] = sv.srgb_lut[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     int stack[YRT_STACK_CAP];
     for (;;) {
-        unsigned base = warp_fetch(counter, lane);
-        if (base >= n_act) break;
-        unsigned a = base + lane;
-        const bool valid = a < n_act;
+        unsigned a = 0;
+        bool valid = false;
+        if (!warp_next(wd, lane, a, valid)) break;
         bool is_hit = false, spawn = false;
         unsigned slot = 0;
         if (valid) {
@@ -447,7 +477,7 @@ static int ensure_workspace(DevScene& ds, Workspace& w, size_t slots, int n_ligh
         }
         w.cap_slots = cs; w.cap_lights = cl; w.cap_depth = cd;
     }
-    YRT_TRY(w.counters.alloc(sizeof(unsigned) * 8192, dev));
+    YRT_TRY(w.counters.alloc(sizeof(unsigned) * YRT_WORK_BLOCK_WORDS * YRT_WORK_BLOCKS, dev));
     YRT_TRY(w.stats.alloc(sizeof(FrameCounters) + 64, dev));   // counters + the next-wave count
     return YRT_OK;
 }
@@ -460,19 +490,43 @@ static int persistent_grid(DevScene& ds, const void* kernel) {
     return ds.sm_count * per_sm;
 }
 
+// per-launch work records (chunk counter + per-SM state words, yrt_work.cuh), zeroed in one go and handed out in turn
 struct CounterRing {
     unsigned* base; int next; int cap; cudaStream_t st;
     int init(Workspace& w, cudaStream_t s) {
-        base = w.counters.as<unsigned>(); next = 0; cap = 8192; st = s;
-        YRT_CUDA(cudaMemsetAsync(base, 0, sizeof(unsigned) * cap, st));
+        base = w.counters.as<unsigned>(); next = 0; cap = YRT_WORK_BLOCKS; st = s;
+        YRT_CUDA(cudaMemsetAsync(base, 0, sizeof(unsigned) * YRT_WORK_BLOCK_WORDS * cap, st));
         return YRT_OK;
     }
     int get(unsigned** out) {
-        if (next == cap) { YRT_CUDA(cudaMemsetAsync(base, 0, sizeof(unsigned) * cap, st)); next = 0; }
-        *out = base + next++;
+        if (next == cap) { YRT_CUDA(cudaMemsetAsync(base, 0, sizeof(unsigned) * YRT_WORK_BLOCK_WORDS * cap, st)); next = 0; }
+        *out = base + (size_t)YRT_WORK_BLOCK_WORDS * next++;
         return YRT_OK;
     }
 };
+
+// Work distribution of one persistent launch over `n` items.  tiles: the items are the slots of a batch of nrows x width
+// pixels (camera rays and their shadow rays) -> SM-affine pixel tiles; otherwise SM-affine runs of queue entries.
+// YRT_TILE=0 restores the first scheme (every warp takes the next 32 items from one counter).
+// rec = a zeroed record of YRT_WORK_BLOCK_WORDS words (or at least one word when YRT_TILE=0 / legacy).
+static WorkDist make_workdist(unsigned* rec, unsigned n, bool tiles, int width, int nrows, int spp, int sm_count) {
+    if (env_int("YRT_TILE", YRT_TILE_DEFAULT) == 0) return workdist_linear(rec, n);
+    if (tiles) {
+        // Default tile 16 x 8 pixels (x 16 spp = 64 tasks of 32 rays: two per resident warp; sweep in profiles/r1_experiments.md).
+        // A launch with few tiles per SM (a rank's share of a multi-GPU frame) halves the tile until every SM gets enough of
+        // them to keep the end of the kernel balanced; a tile smaller than the SM's warp count just means the SM works on
+        // several neighbouring tiles at once.
+        int tw = env_int("YRT_TILE_W", 16), th = env_int("YRT_TILE_H", 8);
+        const long long want = (long long)env_int("YRT_TILES_PER_SM", 32) * sm_count;
+        while ((long long)((width + tw - 1) / tw) * ((nrows + th - 1) / th) < want && tw * th > 8) {
+            if (tw >= 2 * th) tw /= 2; else th = std::max(1, th / 2);
+        }
+        return workdist_tiles(rec, width, nrows, spp, tw, th);
+    }
+    unsigned ci = (unsigned)std::max(32, env_int("YRT_CHUNK_ITEMS", 1024));
+    while ((long long)((n + ci - 1) / ci) < 32ll * sm_count && ci > 128u) ci /= 2;
+    return workdist_runs(rec, n, ci);
+}
 
 // batch of rows [lr0, lr0+nrows) of the rank's packed rows; primary hits only when ids_mode
 static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0, int nrows, size_t cap_slots, float4* d_out, cudaStream_t st,
@@ -496,10 +550,10 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0
     pt.begin(CAT_CLOSEST);
     if (packet)
         k_trace_closest<true, true><<<grid_of(g_closest_p, n), TRACE_THREADS, 0, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(),
-                                                                                     w.P.as<float4>(), n, ctr);
+                                                                                     w.P.as<float4>(), make_workdist(ctr, n, true, rp.width, nrows, bp.spp, ds.sm_count));
     else
         k_trace_closest<true, false><<<grid_of(g_closest_p, n), TRACE_THREADS, 0, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(),
-                                                                                      w.P.as<float4>(), n, ctr);
+                                                                                      w.P.as<float4>(), make_workdist(ctr, n, true, rp.width, nrows, bp.spp, ds.sm_count));
     pt.end();
     if (primary_only) { YRT_CUDA(cudaGetLastError()); return YRT_OK; }
 
@@ -521,8 +575,8 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0
             if (!ds.grid_shadow_shade) ds.grid_shadow_shade = persistent_grid(ds, (const void*)k_shadow_shade);
             YRT_TRY(ring.get(&ctr));
             pt.begin(CAT_ANY);
-            k_shadow_shade<<<grid_of(ds.grid_shadow_shade, n_act), TRACE_THREADS, 0, st>>>(ds.view, bp, sb, depth, depth_cap, act, n_act,
-                                                                                          w.P.as<float4>(), ctr);
+            k_shadow_shade<<<grid_of(ds.grid_shadow_shade, n_act), TRACE_THREADS, 0, st>>>(ds.view, bp, sb, depth, depth_cap, act, w.P.as<float4>(),
+                                                                                          make_workdist(ctr, n_act, act == nullptr, rp.width, nrows, bp.spp, ds.sm_count));
             pt.end();
         } else {
             if (nl > 0) {
@@ -531,10 +585,10 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0
                 // shadow rays of the camera hits are as coherent as the camera rays; those of reflection waves are not
                 if (packet && depth == 0)
                     k_trace_any_lights<true><<<grid_of(g_any, n_act), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
-                                                                                             w.vis.as<uint8_t>(), n_act, ctr);
+                                                                                             w.vis.as<uint8_t>(), make_workdist(ctr, n_act, act == nullptr, rp.width, nrows, bp.spp, ds.sm_count));
                 else
                     k_trace_any_lights<false><<<grid_of(g_any, n_act), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
-                                                                                              w.vis.as<uint8_t>(), n_act, ctr);
+                                                                                              w.vis.as<uint8_t>(), make_workdist(ctr, n_act, act == nullptr, rp.width, nrows, bp.spp, ds.sm_count));
                 pt.end();
             }
             pt.begin(CAT_SHADE);
@@ -551,7 +605,8 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0
         YRT_TRY(ring.get(&ctr));
         pt.begin(CAT_CLOSEST);
         k_trace_closest<false, false><<<grid_of(g_closest_q, n_act), TRACE_THREADS, 0, st>>>(ds.view, bp, act, w.ray_o.as<float4>(), w.ray_d.as<float4>(),
-                                                                                    w.hit.as<float4>(), w.P.as<float4>(), n_act, ctr);
+                                                                                    w.hit.as<float4>(), w.P.as<float4>(),
+                                                                                    make_workdist(ctr, n_act, false, rp.width, nrows, bp.spp, ds.sm_count));
         pt.end();
     }
     int n_pix = nrows * rp.width;
@@ -754,7 +809,7 @@ int intersect_rays_device(DevScene& ds, const float* h_rays, int64_t n, bool any
     YRT_TRY(dist.alloc(sizeof(float) * c, ds.device));
     YRT_TRY(uv.alloc(sizeof(float) * 2 * c, ds.device));
     YRT_TRY(occ.alloc((size_t)c, ds.device));
-    YRT_TRY(ctr.alloc(sizeof(unsigned), ds.device));
+    YRT_TRY(ctr.alloc(sizeof(unsigned) * YRT_WORK_BLOCK_WORDS, ds.device));
     std::vector<float4> ho(c), hd(c);
     int g_c = persistent_grid(ds, (const void*)k_trace_closest<false, false>);
     int g_a = persistent_grid(ds, (const void*)k_trace_any_rays);
@@ -769,16 +824,18 @@ int intersect_rays_device(DevScene& ds, const float* h_rays, int64_t n, bool any
         }
         YRT_CUDA(cudaMemcpyAsync(ro.p, ho.data(), sizeof(float4) * m, cudaMemcpyHostToDevice, st));
         YRT_CUDA(cudaMemcpyAsync(rd.p, hd.data(), sizeof(float4) * m, cudaMemcpyHostToDevice, st));
-        YRT_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(unsigned), st));
+        YRT_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(unsigned) * YRT_WORK_BLOCK_WORDS, st));
         unsigned need = (unsigned)((m + TRACE_THREADS - 1) / TRACE_THREADS);
         if (any) {
             k_trace_any_rays<<<std::max(1u, std::min((unsigned)g_a, need)), TRACE_THREADS, 0, st>>>(ds.view, ro.as<float4>(), rd.as<float4>(),
-                                                                                                  occ.as<uint8_t>(), (unsigned)m, ctr.as<unsigned>());
+                                                                                                  occ.as<uint8_t>(),
+                                                                                                  make_workdist(ctr.as<unsigned>(), (unsigned)m, false, 0, 0, 1, ds.sm_count));
             YRT_CUDA(cudaGetLastError());
             YRT_CUDA(cudaMemcpyAsync(h_occ + off, occ.p, (size_t)m, cudaMemcpyDeviceToHost, st));
         } else {
             k_trace_closest<false, false><<<std::max(1u, std::min((unsigned)g_c, need)), TRACE_THREADS, 0, st>>>(
-                ds.view, bp, nullptr, ro.as<float4>(), rd.as<float4>(), hit.as<float4>(), P.as<float4>(), (unsigned)m, ctr.as<unsigned>());
+                ds.view, bp, nullptr, ro.as<float4>(), rd.as<float4>(), hit.as<float4>(), P.as<float4>(),
+                make_workdist(ctr.as<unsigned>(), (unsigned)m, false, 0, 0, 1, ds.sm_count));
             k_hit_ids<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(ds.view, hit.as<float4>(), P.as<float4>(), (int)m, ids.as<int>(),
                                                                  dist.as<float>(), uv.as<float>());
             YRT_CUDA(cudaGetLastError());
