@@ -139,6 +139,15 @@ void yrt_scene_destroy(yrt_scene* scn);
  * [4]=lights, [5]=prims, [6]=build microseconds (device 0), [7]=reflective materials */
 int yrt_scene_info(const yrt_scene* scn, int64_t out[8]);
 
+/* Number of instances whose frame is not rigid (x, y, z orthonormal within 1e-4).  The reference hands every instance
+ * the ray through transform_ray_inverse (src/vmath.h:275-278: dot products with the frame axes, direction re-normalised),
+ * which is the inverse only of a rigid frame, and then compares the LOCAL hit distances of different instances with each
+ * other and with the world-space boxes (src/scene.cpp:468-473): for scaled or sheared frames its result depends on the
+ * order in which its own BVH happens to visit the instances.  This library reproduces the reference for rigid frames
+ * (every scene of the reference; its OBJ `i` lines and glTF node transforms may carry others); for the rest it renders
+ * the same per-instance arithmetic in its own visit order, and the caller can warn.  Pure host function, needs no GPU. */
+int yrt_desc_nonrigid_instances(const yrt_scene_desc* desc);
+
 /* image width the reference derives from the camera: (int)std::round(aspect*resolution)
  * (src/raytrace.cpp:216) */
 int yrt_image_width(const yrt_camera* cam, int resolution);

@@ -133,3 +133,21 @@ def test_work_distribution_runs_cover_every_entry_once(n, chunk):
         assert (count == 1).all() and tasks >= -(-n // 32)
     else:
         assert tasks == 0
+
+
+def test_nonrigid_instance_frames_are_counted():
+    """Rigid frames (rotations + translations) are the domain where the reference is well defined; scaled / sheared ones
+    are only counted so that the host can warn (include/yrt_b200.h, yrt_desc_nonrigid_instances)."""
+    sc = synth.mixed_scene(31)
+    assert sc.flat().nonrigid_instances() == 0
+    inst = list(sc.instances)
+    name, si, fr = inst[3]
+    f = np.array(fr, np.float32).reshape(4, 3).copy()
+    f[0] *= 1.5
+    inst[3] = (name, si, f.reshape(-1))
+    name, si, fr = inst[5]
+    f = np.array(fr, np.float32).reshape(4, 3).copy()
+    f[0] += 0.3 * f[1]
+    inst[5] = (name, si, f.reshape(-1))
+    sc.instances = inst
+    assert sc.flat().nonrigid_instances() == 2

@@ -129,6 +129,20 @@ int yrt_scene_info(const yrt_scene* scn, int64_t out[8]) {
     return YRT_OK;
 }
 
+int yrt_desc_nonrigid_instances(const yrt_scene_desc* desc) {
+    if (!desc || (desc->n_instances > 0 && !desc->inst_frame)) return 0;
+    int n = 0;
+    for (int i = 0; i < desc->n_instances; i++) {
+        const float* f = desc->inst_frame + 12 * (size_t)i;
+        auto dot3 = [](const float* a, const float* b) { return (double)a[0] * b[0] + (double)a[1] * b[1] + (double)a[2] * b[2]; };
+        const double tol = 1e-4;
+        bool rigid = fabs(dot3(f, f) - 1.0) <= tol && fabs(dot3(f + 3, f + 3) - 1.0) <= tol && fabs(dot3(f + 6, f + 6) - 1.0) <= tol &&
+                     fabs(dot3(f, f + 3)) <= tol && fabs(dot3(f, f + 6)) <= tol && fabs(dot3(f + 3, f + 6)) <= tol;
+        if (!rigid) n++;
+    }
+    return n;
+}
+
 int yrt_image_width(const yrt_camera* cam, int resolution) {
     if (!cam) return 0;
     return (int)roundf(cam->aspect * (float)resolution);   // (int)std::round(cam->aspect * resolution)

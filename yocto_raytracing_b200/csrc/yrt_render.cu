@@ -34,7 +34,12 @@ namespace yrt {
 #ifndef YRT_TILE_DEFAULT
 #define YRT_TILE_DEFAULT 0   /* 1: SM-affine tiles (yrt_work.cuh), 0: every warp takes the next 32 slots; YRT_TILE overrides at run time */
 #endif
+#ifndef YRT_LIGHT_PIPE
+#define YRT_LIGHT_PIPE 0   /* shadow kernel: lanes move on to the next light without waiting for the warp (experiment, profiles/r1_experiments.md) */
+#endif
 #define TRACE_THREADS 128
+// dynamic shared memory of every kernel that runs a Tracer (yrt_trace.cuh: the world-space ray of each lane)
+#define TRACE_DSMEM (YRT_WORLD_SMEM ? YRT_WORLD_WORDS * TRACE_THREADS * sizeof(float) : 0)
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 8   /* resident CTAs per SM the compiler must allow (64 registers per thread) */
 #endif
@@ -182,6 +187,50 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS_ANY) k_trace_a
         }
         if (!PACKET && !alive) continue;
         if (PACKET && __ballot_sync(0xffffffffu, alive) == 0u) continue;
+#if YRT_LIGHT_PIPE
+        if (!PACKET) {
+            // experiment: a lane whose ray towards light k is finished starts on light k+1 at once instead of waiting for the
+            // rest of the warp (the warp then runs max-over-lanes of the SUM of the lights' visits, not the sum of the maxima)
+            int k = 0;
+            Tracer<true, false> t;
+            t.cur = YRT_REF_DONE;
+            bool need_ray = true;
+            for (;;) {
+                if (need_ray) {
+                    bool started = false;
+                    while (k < sv.n_lights) {
+                        vec3 l, ke;
+                        float r;
+                        light_vector(sv, k, p, l, r, ke);
+                        ray3 sr = shadow_ray(p, l, r);
+                        float ax = fabsf(sr.d.x), ay = fabsf(sr.d.y), az = fabsf(sr.d.z);
+                        float m = fminf(fminf(ax, ay), az), big = fmaxf(fmaxf(ax, ay), az);
+                        if (!(m >= 1.0f / YRT_EXACT_SLAB_INVD && big <= 1.0e30f)) {   // rare: the reference's slab formula, traced on the spot
+                            HitRec hr;
+                            bool occ = trace_ray_impl<true, true>(sv, sr, hr, stack, nullptr);
+                            vis[(size_t)k * cap_slots + slot] = occ ? 0 : 1;
+                            k++;
+                            continue;
+                        }
+                        t.begin(sv, sr, stack);
+                        started = true;
+                        break;
+                    }
+                    if (!started) break;
+                    need_ray = false;
+                }
+                t.nodes(sv, stack, nullptr);
+                if (t.done()) {
+                    vis[(size_t)k * cap_slots + slot] = t.found ? 0 : 1;
+                    k++;
+                    need_ray = true;
+                    continue;
+                }
+                t.leaf(sv, stack, nullptr);
+            }
+            continue;
+        }
+#endif
         for (int k = 0; k < sv.n_lights; k++) {
             vec3 l, ke;
             float r;
@@ -484,7 +533,7 @@ static int ensure_workspace(DevScene& ds, Workspace& w, size_t slots, int n_ligh
 
 static int persistent_grid(DevScene& ds, const void* kernel) {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRACE_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRACE_THREADS, TRACE_DSMEM) != cudaSuccess || per_sm < 1) per_sm = 4;
     int cap = env_int("YRT_BLOCKS_PER_SM", 0);
     if (cap > 0 && cap < per_sm) per_sm = cap;
     return ds.sm_count * per_sm;
@@ -549,10 +598,10 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0
     YRT_TRY(ring.get(&ctr));
     pt.begin(CAT_CLOSEST);
     if (packet)
-        k_trace_closest<true, true><<<grid_of(g_closest_p, n), TRACE_THREADS, 0, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(),
+        k_trace_closest<true, true><<<grid_of(g_closest_p, n), TRACE_THREADS, TRACE_DSMEM, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(),
                                                                                      w.P.as<float4>(), make_workdist(ctr, n, true, rp.width, nrows, bp.spp, ds.sm_count));
     else
-        k_trace_closest<true, false><<<grid_of(g_closest_p, n), TRACE_THREADS, 0, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(),
+        k_trace_closest<true, false><<<grid_of(g_closest_p, n), TRACE_THREADS, TRACE_DSMEM, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(),
                                                                                       w.P.as<float4>(), make_workdist(ctr, n, true, rp.width, nrows, bp.spp, ds.sm_count));
     pt.end();
     if (primary_only) { YRT_CUDA(cudaGetLastError()); return YRT_OK; }
@@ -575,7 +624,7 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0
             if (!ds.grid_shadow_shade) ds.grid_shadow_shade = persistent_grid(ds, (const void*)k_shadow_shade);
             YRT_TRY(ring.get(&ctr));
             pt.begin(CAT_ANY);
-            k_shadow_shade<<<grid_of(ds.grid_shadow_shade, n_act), TRACE_THREADS, 0, st>>>(ds.view, bp, sb, depth, depth_cap, act, w.P.as<float4>(),
+            k_shadow_shade<<<grid_of(ds.grid_shadow_shade, n_act), TRACE_THREADS, TRACE_DSMEM, st>>>(ds.view, bp, sb, depth, depth_cap, act, w.P.as<float4>(),
                                                                                           make_workdist(ctr, n_act, act == nullptr, rp.width, nrows, bp.spp, ds.sm_count));
             pt.end();
         } else {
@@ -584,10 +633,10 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0
                 pt.begin(CAT_ANY);
                 // shadow rays of the camera hits are as coherent as the camera rays; those of reflection waves are not
                 if (packet && depth == 0)
-                    k_trace_any_lights<true><<<grid_of(g_any, n_act), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
+                    k_trace_any_lights<true><<<grid_of(g_any, n_act), TRACE_THREADS, TRACE_DSMEM, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
                                                                                              w.vis.as<uint8_t>(), make_workdist(ctr, n_act, act == nullptr, rp.width, nrows, bp.spp, ds.sm_count));
                 else
-                    k_trace_any_lights<false><<<grid_of(g_any, n_act), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
+                    k_trace_any_lights<false><<<grid_of(g_any, n_act), TRACE_THREADS, TRACE_DSMEM, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
                                                                                               w.vis.as<uint8_t>(), make_workdist(ctr, n_act, act == nullptr, rp.width, nrows, bp.spp, ds.sm_count));
                 pt.end();
             }
@@ -604,7 +653,7 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0
         act = next_act;
         YRT_TRY(ring.get(&ctr));
         pt.begin(CAT_CLOSEST);
-        k_trace_closest<false, false><<<grid_of(g_closest_q, n_act), TRACE_THREADS, 0, st>>>(ds.view, bp, act, w.ray_o.as<float4>(), w.ray_d.as<float4>(),
+        k_trace_closest<false, false><<<grid_of(g_closest_q, n_act), TRACE_THREADS, TRACE_DSMEM, st>>>(ds.view, bp, act, w.ray_o.as<float4>(), w.ray_d.as<float4>(),
                                                                                     w.hit.as<float4>(), w.P.as<float4>(),
                                                                                     make_workdist(ctr, n_act, false, rp.width, nrows, bp.spp, ds.sm_count));
         pt.end();
@@ -827,13 +876,13 @@ int intersect_rays_device(DevScene& ds, const float* h_rays, int64_t n, bool any
         YRT_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(unsigned) * YRT_WORK_BLOCK_WORDS, st));
         unsigned need = (unsigned)((m + TRACE_THREADS - 1) / TRACE_THREADS);
         if (any) {
-            k_trace_any_rays<<<std::max(1u, std::min((unsigned)g_a, need)), TRACE_THREADS, 0, st>>>(ds.view, ro.as<float4>(), rd.as<float4>(),
+            k_trace_any_rays<<<std::max(1u, std::min((unsigned)g_a, need)), TRACE_THREADS, TRACE_DSMEM, st>>>(ds.view, ro.as<float4>(), rd.as<float4>(),
                                                                                                   occ.as<uint8_t>(),
                                                                                                   make_workdist(ctr.as<unsigned>(), (unsigned)m, false, 0, 0, 1, ds.sm_count));
             YRT_CUDA(cudaGetLastError());
             YRT_CUDA(cudaMemcpyAsync(h_occ + off, occ.p, (size_t)m, cudaMemcpyDeviceToHost, st));
         } else {
-            k_trace_closest<false, false><<<std::max(1u, std::min((unsigned)g_c, need)), TRACE_THREADS, 0, st>>>(
+            k_trace_closest<false, false><<<std::max(1u, std::min((unsigned)g_c, need)), TRACE_THREADS, TRACE_DSMEM, st>>>(
                 ds.view, bp, nullptr, ro.as<float4>(), rd.as<float4>(), hit.as<float4>(), P.as<float4>(),
                 make_workdist(ctr.as<unsigned>(), (unsigned)m, false, 0, 0, 1, ds.sm_count));
             k_hit_ids<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(ds.view, hit.as<float4>(), P.as<float4>(), (int)m, ids.as<int>(),

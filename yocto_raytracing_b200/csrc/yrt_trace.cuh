@@ -21,9 +21,17 @@
 #define YRT_ANY_UNORDERED 1  /* any-hit rays: skip the near/far ordering of the two children (the answer is order independent; -6 % kernel time) */
 #endif
 
+#ifndef YRT_WORLD_SMEM
+#define YRT_WORLD_SMEM 0   /* 1: the world-space ray waits in shared memory while the lane is inside an instance (13 registers less) */
+#endif
+#if YRT_WORLD_SMEM && defined(__CUDA_ARCH__)
+#define YRT_WORLD_IN_SMEM 1
+#else
+#define YRT_WORLD_IN_SMEM 0
+#endif
+#define YRT_WORLD_WORDS 13    /* o, d, 1/d, -o/d, pad */
+
 namespace yrt {
-
-
 
 struct TraceCounters {   // optional per-ray work counters (roofline inputs), host_emu / debug kernels
     int box_tests, prim_tests, inst_entries, max_stack;
@@ -109,8 +117,35 @@ YRT_HD vec3 inv3_slab(const vec3& d) { return mk3(rcp_slab(d.x), rcp_slab(d.y), 
 // kernels hand a finished lane a new ray while the rest of the warp keeps going.
 template <bool ANY, bool EXACT = false>
 struct Tracer {
+#if YRT_WORLD_IN_SMEM
+    // the world-space ray is needed again only when the lane leaves an instance: it waits in shared memory
+    // (word w of thread t at [w * blockDim.x + t]: conflict-free), kernels launch with YRT_WORLD_WORDS * 4 bytes per thread
+    __device__ __forceinline__ static float* wsave() {
+        extern __shared__ float yrt_world_save[];
+        return yrt_world_save + threadIdx.x;
+    }
+    __device__ __forceinline__ void save_world() {
+        float* w = wsave();
+        const unsigned T = blockDim.x;
+        w[0] = o.x; w[T] = o.y; w[2 * T] = o.z; w[3 * T] = d.x; w[4 * T] = d.y; w[5 * T] = d.z;
+        w[6 * T] = sr.invd.x; w[7 * T] = sr.invd.y; w[8 * T] = sr.invd.z;
+        w[9 * T] = sr.noi.x; w[10 * T] = sr.noi.y; w[11 * T] = sr.noi.z; w[12 * T] = sr.pad;
+    }
+    __device__ __forceinline__ void restore_world() {
+        const float* w = wsave();
+        const unsigned T = blockDim.x;
+        o = mk3(w[0], w[T], w[2 * T]); d = mk3(w[3 * T], w[4 * T], w[5 * T]);
+        sr.invd = mk3(w[6 * T], w[7 * T], w[8 * T]);
+        sr.noi = mk3(w[9 * T], w[10 * T], w[11 * T]);
+        sr.ainv = mk3(fabsf(sr.invd.x), fabsf(sr.invd.y), fabsf(sr.invd.z));
+        sr.pad = w[12 * T];
+    }
+#else
     vec3 wo, wd;          // world-space ray
     slabray wsr;
+    YRT_HD void save_world() { wo = o; wd = d; wsr = sr; }
+    YRT_HD void restore_world() { o = wo; d = wd; sr = wsr; }
+#endif
     vec3 o, d;            // ray in the current space (world, or local to instance `si`)
     slabray sr;
     float tmin, tmax;     // tmin is copied unchanged into every instance space (vmath.h:277)
@@ -123,9 +158,9 @@ struct Tracer {
 
     YRT_HD void begin(const SceneView& sv, const ray3& wray, int* stack) {
         hit.si = -1; hit.prim = -1; hit.w1 = hit.w2 = 0.f; hit.dist = 0.f;
-        wo = wray.o; wd = wray.d;
-        wsr = make_slabray(wo, EXACT ? inv3(wd) : inv3_slab(wd));
-        o = wo; d = wd; sr = wsr;
+        o = wray.o; d = wray.d;
+        sr = make_slabray(o, EXACT ? inv3(d) : inv3_slab(d));
+        save_world();
         tmin = wray.tmin; tmax = wray.tmax;
         stack[0] = YRT_REF_DONE; sp = stack + 1;
         si = -1; kind = 0; top = true; found = false;
@@ -139,7 +174,7 @@ struct Tracer {
         cur = *--sp;
         if (cur == YRT_REF_SENTINEL) {
             top = true;
-            o = wo; d = wd; sr = wsr;
+            restore_world();
             cur = *--sp;
         }
     }
@@ -221,8 +256,10 @@ struct Tracer {
             ld8(ir + 2, q2, q3);
             frame3 f;
             f.x = xyz(q0); f.y = xyz(q1); f.z = xyz(q2); f.o = xyz(q3);
-            o = transform_point_inverse(f, wo);              // transform_ray_inverse, scene.cpp:468
-            d = transform_direction_inverse(f, wd);
+            // top level: (o, d) is the world-space ray
+            vec3 lo = transform_point_inverse(f, o);         // transform_ray_inverse, scene.cpp:468
+            d = transform_direction_inverse(f, d);
+            o = lo;
             sr = make_slabray(o, EXACT ? inv3(d) : inv3_slab(d));
             si = first;
             kind = ((unsigned)float_as_int(q3.w)) >> 28;

@@ -76,6 +76,9 @@ int main(int argc, char** argv) {
         exit(1);
     }
     yrt_scene_desc desc = flat.desc();
+    if (int nonrigid = yrt_desc_nonrigid_instances(&desc))
+        fprintf(stderr, "warning: %d instance frame(s) are not rigid; the reference's own result for them depends on its BVH visit order "
+                        "(include/yrt_b200.h), the images may differ there\n", nonrigid);
     yrt_scene* gscn = nullptr;
     if (yrt_scene_create(&desc, &gscn) != YRT_OK) {
         printf("%s\n", yrt_last_error());

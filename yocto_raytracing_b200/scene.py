@@ -106,6 +106,12 @@ class FlatScene:
         v = np.float32(self.arrays["camera"][13]) * np.float32(resolution)
         return int(np.floor(np.float32(v) + np.float32(0.5))) if v >= 0 else int(np.ceil(v - np.float32(0.5)))
 
+    def nonrigid_instances(self) -> int:
+        """yrt_desc_nonrigid_instances: instances whose frame is not orthonormal (the reference's result for those depends
+        on its own BVH visit order, include/yrt_b200.h); host-only, needs no GPU."""
+        d = self.desc()
+        return int(_lib.load().yrt_desc_nonrigid_instances(C.byref(d)))
+
     def desc(self) -> _lib.SceneDesc:
         """ctypes view (borrows the numpy buffers: keep this FlatScene alive while it is used)."""
         a = self.arrays
