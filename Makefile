@@ -29,8 +29,8 @@ lib: $(LIB)
 build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
-$(LIB): build/yrt_host.o build/yrt_build.o build/yrt_render.o build/yrt_api.o
-	$(NVCC) $(ARCH) -shared -o $@ $^
+$(LIB): build/yrt_host.o build/yrt_build.o build/yrt_render.o build/yrt_api.o build/yrt_png.o
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lz
 
 oracle: oracle/liboracle.so
 oracle/liboracle.so: oracle/yrt_oracle.c oracle/yrt_oracle.h include/yrt_b200.h

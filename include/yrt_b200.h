@@ -148,6 +148,12 @@ int yrt_scene_info(const yrt_scene* scn, int64_t out[8]);
  * the same per-instance arithmetic in its own visit order, and the caller can warn.  Pure host function, needs no GPU. */
 int yrt_desc_nonrigid_instances(const yrt_scene_desc* desc);
 
+/* Optional replacement of save_image(filename, image4b) (src/image.cpp:41-44, stb_image_write's single-threaded PNG
+ * encoder: 0.63 s at 1920x1080): writes the same RGBA8 pixels (row-major, width*4 bytes per row, like
+ * image4b) as a PNG encoded on `threads` host threads (0 = all cores; level = zlib level 1..9, 0 = default 1).  PNG is
+ * lossless, so the decoded image is identical to the reference's file; the file bytes are not.  Host only, needs no GPU. */
+int yrt_write_png(const char* path, const uint8_t* rgba8, int width, int height, int threads, int level);
+
 /* image width the reference derives from the camera: (int)std::round(aspect*resolution)
  * (src/raytrace.cpp:216) */
 int yrt_image_width(const yrt_camera* cam, int resolution);

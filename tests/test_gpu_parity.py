@@ -310,6 +310,13 @@ def test_cli_scene_cache_and_device_ldr(gpu, tmp_path):
     # .hdr output keeps the float path even with --device-ldr
     r = subprocess.run([ours] + args + ["--device-ldr", "-o", os.path.join(cwd, "ours.hdr"), name], cwd=cwd, capture_output=True, text=True)
     assert r.returncode == 0 and os.path.getsize(os.path.join(cwd, "ours.hdr")) > 0
+    # --fast-png (parallel encoder instead of stb_image_write): the decoded pixels are those of the stb-written files,
+    # with the host tonemap (== ours3.png, same float frame) and with the device tonemap (== ours0.png)
+    for extra, same_as in (([], np.array(Image.open(os.path.join(cwd, "ours3.png")))), (["--device-ldr"], outs[0])):
+        out = os.path.join(cwd, "fast.png")
+        r = subprocess.run([ours] + args + ["--fast-png", "--stats"] + extra + ["-o", out, name], cwd=cwd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert np.array_equal(np.array(Image.open(out)), same_as), extra
 
 
 def test_fused_gather_into_one_frame(gpu):

@@ -151,3 +151,38 @@ def test_nonrigid_instance_frames_are_counted():
     inst[5] = (name, si, f.reshape(-1))
     sc.instances = inst
     assert sc.flat().nonrigid_instances() == 2
+
+
+@pytest.mark.parametrize("w,h,threads", [(1, 1, 0), (3, 2, 1), (257, 129, 3), (1920, 1080, 0), (1920, 1080, 1), (640, 2000, 8)])
+def test_parallel_png_decodes_to_the_same_pixels(tmp_path, w, h, threads):
+    """yrt_write_png (replaces stbi_write_png behind save_image, src/image.cpp:41-44): whatever the band
+    split, the file is a valid PNG that decodes to exactly the RGBA8 pixels handed in."""
+    from PIL import Image
+    import yocto_raytracing_b200 as y
+    rng = np.random.default_rng(w * 7 + h)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([xx * 255 // max(w - 1, 1), yy * 255 // max(h - 1, 1), (xx + yy) % 256, np.full_like(xx, 255)], -1).astype(np.uint8)
+    img[h // 4: h // 2, w // 4: w // 2] = rng.integers(0, 256, (h // 2 - h // 4, w // 2 - w // 4, 4))   # noise block, alpha included
+    p = str(tmp_path / "a.png")
+    y.write_png(p, img, threads=threads)
+    with Image.open(p) as im:
+        assert im.mode == "RGBA" and im.size == (w, h)
+        assert np.array_equal(np.array(im), img)
+
+
+def test_parallel_png_matches_reference_png_pixels(tmp_path):
+    """Re-encode a reference output (out/*.png fixtures are not shipped; use a golden float image through the oracle's
+    tonemap): decoded pixels equal the tonemapped frame."""
+    from PIL import Image
+    import yocto_raytracing_b200 as y
+    from oracle import oracle
+    _, ref = load_golden("simple")
+    ldr = oracle.tonemap(ref["image"])
+    p = str(tmp_path / "simple.png")
+    y.write_png(p, ldr)
+    with Image.open(p) as im:
+        assert np.array_equal(np.array(im), ldr)
+    with pytest.raises(y.YrtError):
+        y.write_png(str(tmp_path / "no_such_dir" / "x.png"), ldr)
+    with pytest.raises(ValueError):
+        y.write_png(p, ldr[..., :3])

@@ -5,7 +5,7 @@
         hdr = scn.raytrace(amb=0.1, resolution=720, samples=3)   # == reference raytrace()
 """
 from .scene import FlatScene, TRIANGLES, LINES, POINTS   # noqa: F401
-from .render import Scene, device_count, init, init_device, tonemap   # noqa: F401
+from .render import Scene, device_count, init, init_device, tonemap, write_png   # noqa: F401
 from ._lib import Stats, YrtError   # noqa: F401
 
-__all__ = ["FlatScene", "Scene", "Stats", "YrtError", "device_count", "init", "init_device", "tonemap", "TRIANGLES", "LINES", "POINTS"]
+__all__ = ["FlatScene", "Scene", "Stats", "YrtError", "device_count", "init", "init_device", "tonemap", "write_png", "TRIANGLES", "LINES", "POINTS"]

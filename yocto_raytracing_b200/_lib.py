@@ -74,6 +74,7 @@ SYMBOLS = {
     "yrt_scene_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "yrt_image_width": (C.c_int, [C.POINTER(Camera), C.c_int]),
     "yrt_desc_nonrigid_instances": (C.c_int, [C.POINTER(SceneDesc)]),
+    "yrt_write_png": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "yrt_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_void_p,
                              C.POINTER(Stats)]),
     "yrt_render_ldr": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -143,6 +143,10 @@ int yrt_desc_nonrigid_instances(const yrt_scene_desc* desc) {
     return n;
 }
 
+int yrt_write_png(const char* path, const uint8_t* rgba8, int width, int height, int threads, int level) {
+    return write_png_parallel(path, rgba8, width, height, threads, level <= 0 ? 1 : (level > 9 ? 9 : level));
+}
+
 int yrt_image_width(const yrt_camera* cam, int resolution) {
     if (!cam) return 0;
     return (int)roundf(cam->aspect * (float)resolution);   // (int)std::round(cam->aspect * resolution)

@@ -148,6 +148,7 @@ int tonemap_launch(const float4* d_in, uint8_t* d_out, size_t n, cudaStream_t st
 int tonemap_device(int device, const float* h_rgba, int width, int height, uint8_t* h_out);
 
 camera_k make_camera_k(const yrt_camera* cam);
+int write_png_parallel(const char* path, const uint8_t* rgba, int width, int height, int threads, int level);   // yrt_png.cu (host only)
 
 }  // namespace yrt
 

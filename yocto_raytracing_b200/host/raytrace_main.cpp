@@ -8,6 +8,8 @@
 //                  the OBJ: skips load_scene (SURVEY 8f.2 — the OBJ parse costs more than a frame)
 //   --device-ldr   tonemap on the GPU (yrt_render_ldr): a quarter of the bytes cross to the host and
 //                  the host tonemap (src/image.cpp:55-78) is skipped; ignored for .hdr outputs
+//   --fast-png     8-bit PNG outputs are written by yrt_write_png (parallel deflate) instead of stb_image_write: same pixels,
+//                  a fraction of the time (stbi_write_png costs 45 frames' worth of rendering at 1080p)
 //   --stats        ray counts and the time of every phase
 #include <sys/stat.h>
 
@@ -41,6 +43,7 @@ int main(int argc, char** argv) {
     auto verbose = yu::cmdline::parse_flag(parser, "--stats", "", "print ray counts and timings", false);
     auto use_cache = yu::cmdline::parse_flag(parser, "--cache", "", "reuse / write the flattened scene <scene>.yrts", false);
     auto device_ldr = yu::cmdline::parse_flag(parser, "--device-ldr", "", "tonemap on the GPU (8-bit outputs)", false);
+    auto fast_png = yu::cmdline::parse_flag(parser, "--fast-png", "", "write .png outputs with the parallel encoder", false);
     auto scenein = yu::cmdline::parse_args(parser, "scenein", "input scene", "scene.obj", true);
     yu::cmdline::check_parser(parser);
 
@@ -110,7 +113,14 @@ int main(int argc, char** argv) {
     yrt_scene_destroy(gscn);
 
     printf("saving image %s\n", imageout.c_str());
-    if (ldr_on_device) save_image(imageout, ldr);   // what save_hdr_or_ldr does after its host tonemap (src/image.cpp:85-86)
+    bool is_png = imageout.length() >= 4 && imageout.substr(imageout.length() - 4) == ".png";
+    if (fast_png && is_png && !want_hdr) {
+        if (!ldr_on_device) ldr = tonemap(hdr, 0, false);   // the reference's own host tonemap (src/image.cpp:55-78,:85)
+        if (yrt_write_png(imageout.c_str(), (const uint8_t*)ldr.pixels.data(), ldr.width, ldr.height, 0, 0) != YRT_OK) {
+            printf("%s\n", yrt_last_error());
+            exit(1);
+        }
+    } else if (ldr_on_device) save_image(imageout, ldr);   // what save_hdr_or_ldr does after its host tonemap (src/image.cpp:85-86)
     else save_hdr_or_ldr(imageout, hdr);
     double t_saved = now_ms();
 

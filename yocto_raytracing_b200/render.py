@@ -172,3 +172,12 @@ def tonemap(img: np.ndarray) -> np.ndarray:
     out = np.empty((h, w, 4), np.uint8)
     check(_lib.load().yrt_tonemap(C.c_void_p(img.ctypes.data), w, h, C.c_void_p(out.ctypes.data)))
     return out
+
+
+def write_png(path: str, rgba8: np.ndarray, threads: int = 0, level: int = 1) -> None:
+    """yrt_write_png: the RGBA8 frame (h,w,4) as a PNG encoded on `threads` host threads (0 = all); decodes to the same
+    pixels as the reference's save_image (src/image.cpp:41-44).  Host only."""
+    a = np.ascontiguousarray(rgba8, np.uint8)
+    if a.ndim != 3 or a.shape[2] != 4:
+        raise ValueError("write_png expects an (h, w, 4) uint8 array")
+    check(_lib.load().yrt_write_png(str(path).encode(), C.c_void_p(a.ctypes.data), int(a.shape[1]), int(a.shape[0]), int(threads), int(level)))
