@@ -178,7 +178,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -393,7 +393,7 @@ def run_b200(args):
         "mrays_s_by_kernel_rank0": {"closest": primary_per_frame / (closest_ms * 1e-3) / 1e6 if closest_ms else None,
                                     "any": shadow_per_frame / (any_ms * 1e-3) / 1e6 if any_ms else None},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     scene.close()
     if multi:
         dist.barrier()
@@ -401,6 +401,18 @@ def run_b200(args):
     return 0
 
 
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# Libraries underneath (NCCL with NCCL_DEBUG=VERSION/INFO, the CUDA runtime) write to file descriptor 1 behind Python's
+# back; the contract is one JSON line on stdout, so everything else that lands on fd 1 is sent to stderr.
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
     a = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     sys.exit(run_reference(a) if a.impl == "reference" else run_b200(a))

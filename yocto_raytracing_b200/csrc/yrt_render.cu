@@ -533,6 +533,10 @@ static int ensure_workspace(DevScene& ds, Workspace& w, size_t slots, int n_ligh
 
 static int persistent_grid(DevScene& ds, const void* kernel) {
     int per_sm = 0;
+    // experiment switch: shared-memory carve-out (percent of the 256 KB L1/shared array) forced for the traversal kernels, which
+    // use no shared memory themselves — what is carved out is taken from their L1 (profiles/r1_experiments.md)
+    int carve = env_int("YRT_CARVEOUT", -1);
+    if (carve >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(carve, 100));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRACE_THREADS, TRACE_DSMEM) != cudaSuccess || per_sm < 1) per_sm = 4;
     int cap = env_int("YRT_BLOCKS_PER_SM", 0);
     if (cap > 0 && cap < per_sm) per_sm = cap;

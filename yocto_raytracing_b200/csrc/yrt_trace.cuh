@@ -21,6 +21,9 @@
 #define YRT_ANY_UNORDERED 1  /* any-hit rays: skip the near/far ordering of the two children (the answer is order independent; -6 % kernel time) */
 #endif
 
+#ifndef YRT_RESTORE_OD
+#define YRT_RESTORE_OD 0   /* 1: an instance exit also restores the ray's origin and direction (the first version; dead values) */
+#endif
 #ifndef YRT_WORLD_SMEM
 #define YRT_WORLD_SMEM 0   /* 1: the world-space ray waits in shared memory while the lane is inside an instance (13 registers less) */
 #endif
@@ -140,11 +143,25 @@ struct Tracer {
         sr.ainv = mk3(fabsf(sr.invd.x), fabsf(sr.invd.y), fabsf(sr.invd.z));
         sr.pad = w[12 * T];
     }
+    __device__ __forceinline__ const vec3& world_o() const { return o; }
+    __device__ __forceinline__ const vec3& world_d() const { return d; }
 #else
     vec3 wo, wd;          // world-space ray
     slabray wsr;
     YRT_HD void save_world() { wo = o; wd = d; wsr = sr; }
-    YRT_HD void restore_world() { o = wo; d = wd; sr = wsr; }
+    // At the top level only the slab-test operands are read (the fused test needs neither o nor d, and the instance entry
+    // transforms wo / wd): (o, d) may keep the last instance's values there — six moves less per instance exit.  The
+    // reference's slab formula (EXACT) reads o.
+    YRT_HD void restore_world() {
+#if YRT_RESTORE_OD
+        o = wo; d = wd;
+#else
+        if (EXACT) o = wo;
+#endif
+        sr = wsr;
+    }
+    YRT_HD const vec3& world_o() const { return wo; }
+    YRT_HD const vec3& world_d() const { return wd; }
 #endif
     vec3 o, d;            // ray in the current space (world, or local to instance `si`)
     slabray sr;
@@ -203,8 +220,9 @@ struct Tracer {
             float e;
             raysigns sgn = signs_of(sr.invd);   // the reference's test on the stored box [c-h, c+h] (a superset of the true box)
             nodebox b0 = node_child(q0, q1, q2, 0), b1 = node_child(q0, q1, q2, 1);
-            bool r0 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, b0.cx - b0.hx, b0.cy - b0.hy, b0.cz - b0.hz, b0.cx + b0.hx, b0.cy + b0.hy, b0.cz + b0.hz, e);
-            bool r1 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, b1.cx - b1.hx, b1.cy - b1.hy, b1.cz - b1.hz, b1.cx + b1.hx, b1.cy + b1.hy, b1.cz + b1.hz, e);
+            const vec3 ao = top ? world_o() : o;   // (o is not restored at the top level)
+            bool r0 = intersect_check_bbox(ao, sr.invd, sgn, tmin, tmax, b0.cx - b0.hx, b0.cy - b0.hy, b0.cz - b0.hz, b0.cx + b0.hx, b0.cy + b0.hy, b0.cz + b0.hz, e);
+            bool r1 = intersect_check_bbox(ao, sr.invd, sgn, tmin, tmax, b1.cx - b1.hx, b1.cy - b1.hy, b1.cz - b1.hz, b1.cx + b1.hx, b1.cy + b1.hy, b1.cz + b1.hz, e);
             ctr->slab_false_rejects += (r0 && !h0) + (r1 && !h1);
             ctr->slab_extra_accepts += (!r0 && h0) + (!r1 && h1);
         }
@@ -256,9 +274,8 @@ struct Tracer {
             ld8(ir + 2, q2, q3);
             frame3 f;
             f.x = xyz(q0); f.y = xyz(q1); f.z = xyz(q2); f.o = xyz(q3);
-            // top level: (o, d) is the world-space ray
-            vec3 lo = transform_point_inverse(f, o);         // transform_ray_inverse, scene.cpp:468
-            d = transform_direction_inverse(f, d);
+            vec3 lo = transform_point_inverse(f, world_o());   // transform_ray_inverse, scene.cpp:468
+            d = transform_direction_inverse(f, world_d());
             o = lo;
             sr = make_slabray(o, EXACT ? inv3(d) : inv3_slab(d));
             si = first;
