@@ -8,6 +8,10 @@
 #pragma once
 #include "yrt_scene.cuh"
 
+#ifndef YRT_SHADE_ONE_DIVIDE
+#define YRT_SHADE_ONE_DIVIDE 1   /* 1: one divide instead of three for lights whose ke components are equal (exact) */
+#endif
+
 namespace yrt {
 
 struct HitAttr {
@@ -180,8 +184,19 @@ YRT_HD void shade_lights(const SceneView& sv, const HitAttr& a, const Material& 
         vec3 kd = m.kd, ks = m.ks;
         if (m.kd_tex >= 0) kd = kd * tkd;                    // raytrace.cpp:153-157
         if (m.ks_tex >= 0) ks = ks * tks;
+#if YRT_SHADE_ONE_DIVIDE
+        // ke / (r*r) is three IEEE divides by the same number (raytrace.cpp:159-160); a white light (ke.x, ke.y, ke.z the
+        // same bits) needs one of them — same quotient, bit for bit
+        const float rr = r * r;
+        vec3 kel;
+        if (float_as_int(ke.x) == float_as_int(ke.y) && float_as_int(ke.y) == float_as_int(ke.z)) { float q = ke.x / rr; kel = mk3(q, q, q); }
+        else kel = ke / rr;
+        vec3 ld = kd * kel;
+        vec3 ls = ks * kel;
+#else
         vec3 ld = kd * (ke / (r * r));                       // raytrace.cpp:159-160
         vec3 ls = ks * (ke / (r * r));
+#endif
         // ks == (0,0,0) exactly (most materials of the instance scenes): ls = +0 * (finite lobe) = +0 and ld + 0 == ld,
         // so the half vector and the powf are skipped.  The lobe is finite whenever ld is: its base n.h (or
         // sqrt(1-|n.h|)) of finite unit vectors lies in [0, 1 + 3e-7] and ns <= 1e6; and if n, l or v is not finite,

@@ -21,6 +21,12 @@
 #define YRT_ANY_UNORDERED 1  /* any-hit rays: skip the near/far ordering of the two children (the answer is order independent; -6 % kernel time) */
 #endif
 
+#ifndef YRT_STACK_TOP_REG
+#define YRT_STACK_TOP_REG 0   /* 1: the top of the traversal stack lives in a register (a pop hands out the next node without waiting for a load) */
+#endif
+#ifndef YRT_PREFETCH_PUSH
+#define YRT_PREFETCH_PUSH 0   /* 1: a postponed child node is prefetched into L1 when it is pushed */
+#endif
 #ifndef YRT_RESTORE_OD
 #define YRT_RESTORE_OD 0   /* 1: an instance exit also restores the ray's origin and direction (the first version; dead values) */
 #endif
@@ -168,6 +174,9 @@ struct Tracer {
     float tmin, tmax;     // tmin is copied unchanged into every instance space (vmath.h:277)
     int cur, si, kind;
     int* sp;              // next free stack slot; stack[0] holds a YRT_REF_DONE guard, so a pop needs no emptiness test
+#if YRT_STACK_TOP_REG
+    int tos;              // top of the stack (the entries below it are in memory)
+#endif
     bool top, found;
     HitRec hit;
 
@@ -180,6 +189,9 @@ struct Tracer {
         save_world();
         tmin = wray.tmin; tmax = wray.tmax;
         stack[0] = YRT_REF_DONE; sp = stack + 1;
+#if YRT_STACK_TOP_REG
+        tos = YRT_REF_DONE;   // logical stack = [guard in memory, DONE in the register]: the last pop reads the guard, never below it
+#endif
         si = -1; kind = 0; top = true; found = false;
         cur = sv.n_active_instances > 0 ? sv.tlas_root : YRT_REF_DONE;
     }
@@ -187,13 +199,38 @@ struct Tracer {
     // pop the next reference.  Leaving an instance (sentinel) restores the world-space ray and pops once more: only one
     // sentinel is ever on the stack (instances are entered from the top level only), and the guard below everything
     // (YRT_REF_DONE) ends the traversal without an emptiness test.
+    YRT_HD int take() {
+#if YRT_STACK_TOP_REG
+        int r = tos;
+        tos = *--sp;
+        return r;
+#else
+        return *--sp;
+#endif
+    }
+    YRT_HD void push(int ref) {
+#if YRT_STACK_TOP_REG
+        *sp++ = tos;
+        tos = ref;
+#else
+        *sp++ = ref;
+#endif
+    }
     YRT_HD void pop() {
-        cur = *--sp;
+        cur = take();
         if (cur == YRT_REF_SENTINEL) {
             top = true;
             restore_world();
-            cur = *--sp;
+            cur = take();
         }
+    }
+    // a node whose visit is postponed: start pulling its record towards the SM
+    YRT_HD void prefetch_node(const SceneView& sv, int ref) {
+#if YRT_PREFETCH_PUSH && defined(__CUDA_ARCH__)
+        if (ref >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(sv.nodes + 4 * (size_t)ref));
+#else
+        (void)sv; (void)ref;
+#endif
     }
 
     // one internal node: test both child boxes against the current ray and current tmax, near child first
@@ -233,7 +270,9 @@ struct Tracer {
             int nxt = h0 ? c0 : c1;
             if (h0 && h1) {
                 bool swap = (ANY && YRT_ANY_UNORDERED) ? false : (e1 < e0);   // near child first
-                *sp++ = swap ? c0 : c1;
+                const int later = swap ? c0 : c1;
+                push(later);
+                prefetch_node(sv, later);
                 if (ctr && (int)(sp - stack) > ctr->max_stack) ctr->max_stack = (int)(sp - stack);
                 if (swap) nxt = c1;
             }
@@ -244,7 +283,7 @@ struct Tracer {
 #else
         if (h0 && h1) {
             bool swap = (ANY && YRT_ANY_UNORDERED) ? false : (e1 < e0);   // near child first
-            *sp++ = swap ? c0 : c1;
+            push(swap ? c0 : c1);
             if (ctr && (int)(sp - stack) > ctr->max_stack) ctr->max_stack = (int)(sp - stack);
             cur = swap ? c1 : c0;
         } else if (h0) {
@@ -267,7 +306,7 @@ struct Tracer {
         int first = leaf_first(cur), count = leaf_count(cur);
         if (top) {
             // TLAS leaf: enter its first instance, keep the rest for later
-            if (count > 1) *sp++ = make_leaf_ref(first + 1, count - 1);
+            if (count > 1) push(make_leaf_ref(first + 1, count - 1));
             const float4* ir = sv.inst_recs + 4 * (size_t)first;
             float4 q0, q1, q2, q3;
             ld8(ir, q0, q1);
@@ -281,7 +320,7 @@ struct Tracer {
             si = first;
             kind = ((unsigned)float_as_int(q3.w)) >> 28;
             top = false;
-            *sp++ = YRT_REF_SENTINEL;
+            push(YRT_REF_SENTINEL);
             if (ctr) { ctr->inst_entries++; if ((int)(sp - stack) > ctr->max_stack) ctr->max_stack = (int)(sp - stack); }
             cur = float_as_int(q0.w);   // BLAS root ref of the instance's shape
         } else {
