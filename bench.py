@@ -31,7 +31,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 ALG_BYTES_PER_RAY = 2840.0
 ALG_FLOPS_PER_RAY = 2450.0
 # dram bytes of one k_trace_any_lights launch (whole 1080p/16spp frame) from the ncu --set full capture in profiles/
-NCU_DRAM_BYTES_PER_ANY_LAUNCH = 1.1833e9   # profiles/r1i_final_ncu_summary.txt: 1.0768 GB read + 0.1065 GB write (algorithmic: 33.2 M hits x 35 B)
+NCU_DRAM_BYTES_PER_ANY_LAUNCH = 1.1833e9   # profiles/r1j_final_ncu_summary.txt: 1.0755 GB read + 0.1078 GB write (algorithmic: 33.2 M hits x 35 B)
 FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
