@@ -338,12 +338,21 @@ int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, in
 // The work-distribution protocol of the persistent kernels (yrt_work.cuh), run by host threads playing warps:
 // n_threads "warps" spread over n_sm state words fetch tasks until the input is exhausted and count, per item, how
 // often it was handed out (must be exactly once).  mode 1: tiles over nrows x width x spp; mode 2: runs over n_items.
+// (the methods are only ever called on the host; the __device__ halves exist because fetch_task is a __host__ __device__ template)
 struct HostAtomics {
-    unsigned long long add64(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-    unsigned long long exch64(unsigned long long* p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
-    unsigned long long load64(unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
-    unsigned add32(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-    void pause() { std::this_thread::yield(); }
+#ifndef __CUDA_ARCH__
+    __host__ __device__ unsigned long long add64(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+    __host__ __device__ unsigned long long exch64(unsigned long long* p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+    __host__ __device__ unsigned long long load64(unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+    __host__ __device__ unsigned add32(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+    __host__ __device__ void pause() { std::this_thread::yield(); }
+#else
+    __host__ __device__ unsigned long long add64(unsigned long long*, unsigned long long) { return 0; }
+    __host__ __device__ unsigned long long exch64(unsigned long long*, unsigned long long) { return 0; }
+    __host__ __device__ unsigned long long load64(unsigned long long*) { return 0; }
+    __host__ __device__ unsigned add32(unsigned*, unsigned) { return 0; }
+    __host__ __device__ void pause() {}
+#endif
 };
 
 int emu_workdist(int mode, int width, int nrows, int spp, int tile_w, int tile_h, unsigned chunk_items, unsigned n_items, int n_threads,

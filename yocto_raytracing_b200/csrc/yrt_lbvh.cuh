@@ -377,7 +377,7 @@ YRT_HD void rotate_refit_item(const LbvhArrays& a, int leaf) {
             int best_side = -1, best_g = 0;
             float4 best_lo = lo[0], best_hi = hi[0];
             for (int side = 0; side < 2; side++) {          // `side` = the internal child that is reshaped
-                int r = c[side], l = c[1 - side];
+                int r = c[side];                              // (the other child, c[1 - side], is "l" in the comments below)
                 if (r < 0) continue;
                 int g[2] = {YRT_LDCG(&a.left[r]), YRT_LDCG(&a.right[r])};
                 float ar = half_area_(lo[side], hi[side]);
@@ -388,7 +388,6 @@ YRT_HD void rotate_refit_item(const LbvhArrays& a, int leaf) {
                     float gain = ar - half_area_(nl, nh);
                     if (gain > best) { best = gain; best_side = side; best_g = k; best_lo = nl; best_hi = nh; }
                 }
-                (void)l;
             }
             // both children internal: the two other pairings of the four grandchildren (LL,LR | RL,RR) ->
             // (LL,RL | LR,RR) and (LL,RR | LR,RL); cost change = area(L') + area(R') - area(L) - area(R)
