@@ -10,7 +10,7 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
         sys.path.insert(0, p)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["simple", "basic", "refl", "instance10000", "lines_synth", "mixed7"]
+GOLDEN_CASES = ["simple", "basic", "refl", "instance10000", "lines_synth", "mixed7", "gltf7"]
 
 
 def pytest_configure(config):

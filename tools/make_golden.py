@@ -1,7 +1,7 @@
 """Generate tests/golden/ from the UNMODIFIED reference compiled here (oracle/_ref, see Makefile `ref`).
 
 Run in a container that has /root/reference:   python tools/make_golden.py
-Writes, per reference scene (in/*_pointlight/*.obj) and per synthetic scene:
+Writes, per reference scene (in/*_pointlight/*.obj) and per synthetic scene (OBJ dialect, and one glTF written by tools/make_gltf.py):
   tests/golden/<name>.scene.npz   flattened scene as the reference's loader produced it (bin/yrt_flatten)
   tests/golden/<name>.ref.npz     outputs of the reference itself (oracle/_ref/ref_probe):
                                   image   float32 H x W x 4  raytrace() before tonemap (-r R -s S -a 0.1)
@@ -60,6 +60,10 @@ def main():
         for sc, res, smp, ids_res in ((synth.hair_scene(1024), 90, 2, 180), (synth.mixed_scene(7), 90, 2, 180)):
             obj = sc.write_obj(os.path.join(td, sc.name))
             one(sc.name, obj, res, smp, ids_res)
+        # glTF input: node hierarchy with translation + rotation quaternions, KHR_materials_pbrSpecularGlossiness
+        # materials, POINTS primitives as lights, a camera node — loaded by the reference's own glTF loader
+        import make_gltf
+        one("gltf7", make_gltf.gltf_scene(os.path.join(td, "gltf7")), 90, 2, 180)
 
 
 if __name__ == "__main__":
