@@ -186,3 +186,24 @@ def test_parallel_png_matches_reference_png_pixels(tmp_path):
         y.write_png(str(tmp_path / "no_such_dir" / "x.png"), ldr)
     with pytest.raises(ValueError):
         y.write_png(p, ldr[..., :3])
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py --impl reference (the reference's own CPU implementation, oracle/_ref, or the C port where it is absent) on a
+    tiny bounded sample: stdout carries the one JSON line of the contract and nothing else; no GPU involved."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-baseline-resolution", "24", "--n-side", "8"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "Mrays/s" and d["unit"] == "Mrays/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["higher_is_better"] is True and "workload" in d["config"]
+    # without a GPU the product arm refuses to run: there is no CPU fallback
+    import torch
+    if not torch.cuda.is_available():
+        r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
+        assert r2.returncode != 0 and r2.stdout.strip() == ""
