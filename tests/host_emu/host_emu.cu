@@ -132,18 +132,44 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
         pack_prim(kind, e, p0, p1, p2, kind == 0 ? 0.f : g.radius[v[0]], kind == 1 ? g.radius[v[1]] : 0.f, pr, ar);
         ar[0] = mk4(n0.x, n0.y, n0.z, u0); ar[1] = mk4(n1.x, n1.y, n1.z, w0); ar[2] = mk4(n2.x, n2.y, n2.z, u1); ar[3] = mk4(w1, u2, w2, 0.f);
     }
-    // TLAS (mirrors k_inst_boxes / k_inst_recs)
-    int na = (int)hs.active_inst.size();
-    std::vector<float4> ilo(std::max(na, 1)), ihi(std::max(na, 1));
-    for (int a = 0; a < na; a++) {
+    // TLAS (mirrors k_inst_boxes / k_inst_recs).  Prototype switch YRT_EMU_OPEN=d (host emulation only, profiles/r1_experiments.md):
+    // "opening" an instance replaces it in the TLAS by the 2^d subtrees d levels below its BLAS root, each item carrying the
+    // instance's frame and its own subtree root — the top of the instance's BLAS is re-built together with its neighbours.
+    const int open_depth = getenv("YRT_EMU_OPEN") ? atoi(getenv("YRT_EMU_OPEN")) : 0;
+    int na0 = (int)hs.active_inst.size();
+    struct Item { int active; int root; Box box; };
+    std::vector<Item> items;
+    for (int a = 0; a < na0; a++) {
         int inst = hs.active_inst[a], s = hs.inst_shape[inst];
-        const float* fr = &hs.inst_frame[12 * (size_t)inst];
-        frame3 f;
-        f.x = mk3(fr[0], fr[1], fr[2]); f.y = mk3(fr[3], fr[4], fr[5]); f.z = mk3(fr[6], fr[7], fr[8]); f.o = mk3(fr[9], fr[10], fr[11]);
         Box b;
         b.lo = mk3(ordered_to_float(es.blas.seg_box_lo[3 * s]), ordered_to_float(es.blas.seg_box_lo[3 * s + 1]), ordered_to_float(es.blas.seg_box_lo[3 * s + 2]));
         b.hi = mk3(ordered_to_float(es.blas.seg_box_hi[3 * s]), ordered_to_float(es.blas.seg_box_hi[3 * s + 1]), ordered_to_float(es.blas.seg_box_hi[3 * s + 2]));
-        Box w = instance_bounds(f, b);
+        std::vector<Item> cur = {{a, es.blas.seg_root[s], b}};
+        for (int lvl = 0; lvl < open_depth; lvl++) {
+            std::vector<Item> nxt;
+            for (const Item& it : cur) {
+                if (it.root < 0) { nxt.push_back(it); continue; }       // a leaf cannot be opened
+                const float4* n = &es.blas.nodes[4 * (size_t)it.root];
+                for (int k = 0; k < 2; k++) {
+                    nodebox cb = node_child(n[0], n[1], n[2], k);
+                    Box c;
+                    c.lo = mk3(cb.cx - cb.hx, cb.cy - cb.hy, cb.cz - cb.hz);
+                    c.hi = mk3(cb.cx + cb.hx, cb.cy + cb.hy, cb.cz + cb.hz);
+                    nxt.push_back({a, float_as_int(k == 0 ? n[3].x : n[3].y), c});
+                }
+            }
+            cur.swap(nxt);
+        }
+        items.insert(items.end(), cur.begin(), cur.end());
+    }
+    int na = (int)items.size();
+    std::vector<float4> ilo(std::max(na, 1)), ihi(std::max(na, 1));
+    for (int a = 0; a < na; a++) {
+        int inst = hs.active_inst[items[a].active];
+        const float* fr = &hs.inst_frame[12 * (size_t)inst];
+        frame3 f;
+        f.x = mk3(fr[0], fr[1], fr[2]); f.y = mk3(fr[3], fr[4], fr[5]); f.z = mk3(fr[6], fr[7], fr[8]); f.o = mk3(fr[9], fr[10], fr[11]);
+        Box w = instance_bounds(f, items[a].box);
         ilo[a] = mk4(w.lo.x, w.lo.y, w.lo.z, 0.f);
         ihi[a] = mk4(w.hi.x, w.hi.y, w.hi.z, 0.f);
     }
@@ -158,11 +184,12 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
     es.inst_recs.assign(4 * (size_t)std::max(na, 1), mk4(0, 0, 0, 0));
     es.inst_rank.assign(std::max(na, 1), 0);
     for (int k = 0; k < na; k++) {
-        int inst = hs.active_inst[es.tlas.order[k]], s = hs.inst_shape[inst];
+        const Item& it = items[es.tlas.order[k]];
+        int inst = hs.active_inst[it.active], s = hs.inst_shape[inst];
         es.inst_rank[k] = hs.inst_rank[inst];
         const float* fr = &hs.inst_frame[12 * (size_t)inst];
         float4* r = &es.inst_recs[4 * (size_t)k];
-        r[0] = mk4(fr[0], fr[1], fr[2], int_as_float(es.blas.seg_root[s]));
+        r[0] = mk4(fr[0], fr[1], fr[2], int_as_float(it.root));
         r[1] = mk4(fr[3], fr[4], fr[5], int_as_float(inst));
         r[2] = mk4(fr[6], fr[7], fr[8], int_as_float(hs.inst_mat[inst]));
         r[3] = mk4(fr[9], fr[10], fr[11], int_as_float((int)((unsigned)s | ((unsigned)hs.shape_kind[s] << 28))));
