@@ -36,7 +36,11 @@ oracle: oracle/liboracle.so
 oracle/liboracle.so: oracle/yrt_oracle.c oracle/yrt_oracle.h include/yrt_b200.h
 	$(ORACLE_CC) -std=c11 -O2 -fPIC -shared -ffp-contract=off -fopenmp -o $@ oracle/yrt_oracle.c -lm
 
-hostemu: tests/host_emu/libyrt_hostemu.so
+hostemu: tests/host_emu/libyrt_hostemu.so tests/host_emu/libyrt_hostemu_node48.so
+# the same emulation with the 48-byte node layout (-DYRT_NODE48=1, a build option of the library that is off by default):
+# keeps that layout's packing / unpacking and its conservative half-extents under test without a GPU
+tests/host_emu/libyrt_hostemu_node48.so: tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu $(HDRS)
+	$(NVCC) -O2 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-ffp-contract=off,-fopenmp -shared -DYRT_NODE48=1 -I$(CSRC) -o $@ tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu -lgomp
 tests/host_emu/libyrt_hostemu.so: tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu $(HDRS)
 	$(NVCC) -O2 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-ffp-contract=off,-fopenmp -shared $(EXTRA) -I$(CSRC) -o $@ tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu -lgomp
 
@@ -60,4 +64,4 @@ bin/yrt_flatten: $(HOST)/yrt_flatten_tool.cpp $(HOST)/yrt_flatten.cpp $(HOST)/yr
 	$(CXX) $(REFFLAGS) -I$(REF)/src -I$(HOST) -o $@ $(HOST)/yrt_flatten_tool.cpp $(HOST)/yrt_flatten.cpp $(REFOBJ)
 
 clean:
-	rm -rf build bin oracle/_ref oracle/liboracle.so tests/host_emu/libyrt_hostemu.so $(LIB)
+	rm -rf build bin oracle/_ref oracle/liboracle.so tests/host_emu/libyrt_hostemu.so tests/host_emu/libyrt_hostemu_node48.so $(LIB)

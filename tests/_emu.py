@@ -6,36 +6,43 @@ import numpy as np
 
 from yocto_raytracing_b200 import _lib
 
-_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu", "libyrt_hostemu.so")
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu")
+_PATH = os.path.join(_DIR, "libyrt_hostemu.so")
 
 
-def available():
-    return os.path.exists(_PATH)
+def _path(variant=""):
+    return os.path.join(_DIR, f"libyrt_hostemu_{variant}.so") if variant else _PATH
 
 
-_emu = None
+def available(variant=""):
+    return os.path.exists(_path(variant))
 
 
-def lib():
-    global _emu
-    if _emu is None:
-        _emu = C.CDLL(_PATH)
-        _emu.emu_last_error.restype = C.c_char_p
-    return _emu
+_libs = {}
+
+
+def lib(variant=""):
+    """The emulation library; variant "node48" = built with -DYRT_NODE48=1 (48-byte traversal nodes)."""
+    if variant not in _libs:
+        l = C.CDLL(_path(variant))
+        l.emu_last_error.restype = C.c_char_p
+        _libs[variant] = l
+    return _libs[variant]
 
 
 class EmuScene:
-    def __init__(self, flat, leaf_blas=0, leaf_tlas=0):
+    def __init__(self, flat, leaf_blas=0, leaf_tlas=0, variant=""):
         self.flat = flat
+        self._lib = lib(variant)
         self._desc = flat.desc()
         self.h = C.c_void_p()
-        st = lib().emu_scene_create(C.byref(self._desc), leaf_blas, leaf_tlas, C.byref(self.h))
+        st = self._lib.emu_scene_create(C.byref(self._desc), leaf_blas, leaf_tlas, C.byref(self.h))
         if st != 0:
-            raise RuntimeError(lib().emu_last_error().decode())
+            raise RuntimeError(self._lib.emu_last_error().decode())
 
     def info(self):
         out = (C.c_int64 * 8)()
-        lib().emu_scene_info(self.h, out)
+        self._lib.emu_scene_info(self.h, out)
         return list(out)
 
     def trace_primary(self, width, height, samples):
@@ -45,7 +52,7 @@ class EmuScene:
         uv = np.empty((n, 2), np.float32)
         ctr = (C.c_int64 * 8)()
         cam = self.flat.camera_struct()
-        st = lib().emu_trace_primary(self.h, C.byref(cam), width, height, samples, C.c_void_p(ids.ctypes.data),
+        st = self._lib.emu_trace_primary(self.h, C.byref(cam), width, height, samples, C.c_void_p(ids.ctypes.data),
                                      C.c_void_p(dist.ctypes.data), C.c_void_p(uv.ctypes.data), ctr)
         assert st == 0
         return ids, dist, uv, list(ctr)
@@ -57,7 +64,7 @@ class EmuScene:
         dist = np.empty(n, np.float32)
         occ = np.empty(n, np.uint8)
         fr = C.c_int64(0)
-        st = lib().emu_intersect(self.h, C.c_void_p(rays.ctypes.data), C.c_int64(n), C.c_void_p(ids.ctypes.data), C.c_void_p(dist.ctypes.data),
+        st = self._lib.emu_intersect(self.h, C.c_void_p(rays.ctypes.data), C.c_int64(n), C.c_void_p(ids.ctypes.data), C.c_void_p(dist.ctypes.data),
                                  C.c_void_p(occ.ctypes.data), C.byref(fr))
         assert st == 0
         return ids, dist, occ, fr.value
@@ -67,14 +74,14 @@ class EmuScene:
         cam = self.flat.camera_struct()
         a = (C.c_float * 3)(amb, amb, amb)
         rc = (C.c_int64 * 8)()
-        st = lib().emu_render(self.h, C.byref(cam), a, width, height, samples, max_depth, C.c_void_p(img.ctypes.data), rc)
+        st = self._lib.emu_render(self.h, C.byref(cam), a, width, height, samples, max_depth, C.c_void_p(img.ctypes.data), rc)
         assert st == 0
         return img, list(rc)
 
     def __del__(self):
         try:
             if self.h:
-                lib().emu_scene_destroy(self.h)
+                self._lib.emu_scene_destroy(self.h)
         except Exception:
             pass
 

@@ -37,7 +37,7 @@ void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi
     std::vector<int> left(ni), right(ni), rfirst(ni), rlast(ni), pint(ni), pleaf(std::max(n, 1), -1), flags(ni);
     std::vector<float4> nlo(ni), nhi(ni);
     std::vector<int> count(ni), new_slot(std::max(n, 1)), order_tmp(std::max(n, 1)), pleaf_tmp(std::max(n, 1));
-    out.nodes.assign(4 * ni, mk4(0, 0, 0, 0));
+    out.nodes.assign(YRT_NODE_STRIDE * ni, mk4(0, 0, 0, 0));
     out.seg_root.assign(n_seg, 0);
     out.seg_depth.assign(n_seg, 0);
     LbvhArrays a;
@@ -149,13 +149,15 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
             std::vector<Item> nxt;
             for (const Item& it : cur) {
                 if (it.root < 0) { nxt.push_back(it); continue; }       // a leaf cannot be opened
-                const float4* n = &es.blas.nodes[4 * (size_t)it.root];
+                const float4* n = &es.blas.nodes[YRT_NODE_STRIDE * (size_t)it.root];
+                int cref[2];
+                node_refs(n[1], n[YRT_NODE_STRIDE - 1], cref[0], cref[1]);
                 for (int k = 0; k < 2; k++) {
                     nodebox cb = node_child(n[0], n[1], n[2], k);
                     Box c;
                     c.lo = mk3(cb.cx - cb.hx, cb.cy - cb.hy, cb.cz - cb.hz);
                     c.hi = mk3(cb.cx + cb.hx, cb.cy + cb.hy, cb.cz + cb.hz);
-                    nxt.push_back({a, float_as_int(k == 0 ? n[3].x : n[3].y), c});
+                    nxt.push_back({a, cref[k], c});
                 }
             }
             cur.swap(nxt);
@@ -179,7 +181,7 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
     emu_lbvh(na, 1, ilo, ihi, seg_of.data(), sf, leaf_tlas, es.tlas, nb_int, getenv("YRT_SIZE_BITS_TLAS") ? atoi(getenv("YRT_SIZE_BITS_TLAS")) : YRT_SIZE_BITS_TLAS,
              getenv("YRT_ROTATE_TLAS") ? atoi(getenv("YRT_ROTATE_TLAS")) : YRT_ROTATE_ROUNDS_TLAS,
              getenv("YRT_ROTATE_PAIRS_TLAS") ? atoi(getenv("YRT_ROTATE_PAIRS_TLAS")) : YRT_ROTATE_PAIRS_TLAS);
-    es.nodes.assign(es.blas.nodes.begin(), es.blas.nodes.begin() + 4 * (size_t)nb_int);
+    es.nodes.assign(es.blas.nodes.begin(), es.blas.nodes.begin() + YRT_NODE_STRIDE * (size_t)nb_int);
     es.nodes.insert(es.nodes.end(), es.tlas.nodes.begin(), es.tlas.nodes.end());
     es.inst_recs.assign(4 * (size_t)std::max(na, 1), mk4(0, 0, 0, 0));
     es.inst_rank.assign(std::max(na, 1), 0);

@@ -261,7 +261,7 @@ extern "C" int yrt_debug_sort_pairs(unsigned long long* h_keys, int* h_vals, int
 // one LBVH build (many segments)
 // ------------------------------------------------------------------------------------------
 struct LbvhOut {
-    float4* nodes;        // 4 float4 per internal node, preallocated by the caller
+    float4* nodes;        // YRT_NODE_STRIDE float4 per internal node, preallocated by the caller
     int ref_offset;       // index of this tree set's node 0 in the shared node array
     int size_bits;        // size-class bits in the sort key (see morton_item)
     int rotate_rounds;    // bottom-up tree-rotation passes after the refit (see rotate_refit_item)
@@ -308,7 +308,7 @@ static int lbvh_build(int dev, cudaStream_t st, int n, int n_seg, float4* box_lo
     YRT_TRY(out.seg_root->alloc(sizeof(int) * (size_t)n_seg, dev));
     YRT_TRY(out.seg_depth->alloc(sizeof(int) * (size_t)n_seg, dev));
     YRT_CUDA(cudaMemsetAsync(pleaf.p, 0xff, sizeof(int) * (size_t)std::max(n, 1), st));   // -1: no parent
-    YRT_CUDA(cudaMemsetAsync(out.nodes, 0, sizeof(float4) * 4 * ni, st));
+    YRT_CUDA(cudaMemsetAsync(out.nodes, 0, sizeof(float4) * YRT_NODE_STRIDE * ni, st));
 
     LbvhArrays a;
     a.n = n;
@@ -464,7 +464,7 @@ int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
     YRT_TRY(phi.alloc(sizeof(float4) * (size_t)std::max(hs.n_prims, 1), device));
     if (hs.n_prims > 0) k_prim_boxes<<<grid_for(hs.n_prims), 256, 0, st>>>(g, plo.as<float4>(), phi.as<float4>());
     int nb_int = hs.n_prims > 1 ? hs.n_prims - 1 : 0, nt_int = ds.n_active > 1 ? ds.n_active - 1 : 0;
-    YRT_TRY(ds.nodes.alloc(sizeof(float4) * 4 * (size_t)(nb_int + nt_int + 2), device));
+    YRT_TRY(ds.nodes.alloc(sizeof(float4) * YRT_NODE_STRIDE * (size_t)(nb_int + nt_int + 2), device));
     LbvhOut bo;
     bo.nodes = ds.nodes.as<float4>(); bo.ref_offset = 0; bo.size_bits = size_bits_blas; bo.rotate_rounds = rotate_blas; bo.rotate_pairs = rotate_pairs_blas; bo.seg_root = &ds.blas_seg_root; bo.seg_depth = &ds.blas_seg_depth; bo.order = &blas_order;
     bo.seg_box_lo = &ds.shape_box_lo; bo.seg_box_hi = &ds.shape_box_hi;
@@ -491,7 +491,7 @@ int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
         k_inst_boxes<<<grid_for(na), 256, 0, st>>>(na, ds.active_inst.as<int>(), ds.inst_frame.as<float>(), ds.inst_shape.as<int>(),
                                                  ds.shape_box_lo.as<int>(), ds.shape_box_hi.as<int>(), ilo.as<float4>(), ihi.as<float4>());
     LbvhOut to;
-    to.nodes = ds.nodes.as<float4>() + 4 * (size_t)nb_int; to.ref_offset = nb_int; to.size_bits = size_bits_tlas; to.rotate_rounds = rotate_tlas; to.rotate_pairs = rotate_pairs_tlas; to.seg_root = &ds.tlas_seg_root; to.seg_depth = &ds.tlas_seg_depth; to.order = &tlas_order;
+    to.nodes = ds.nodes.as<float4>() + YRT_NODE_STRIDE * (size_t)nb_int; to.ref_offset = nb_int; to.size_bits = size_bits_tlas; to.rotate_rounds = rotate_tlas; to.rotate_pairs = rotate_pairs_tlas; to.seg_root = &ds.tlas_seg_root; to.seg_depth = &ds.tlas_seg_depth; to.order = &tlas_order;
     to.seg_box_lo = nullptr; to.seg_box_hi = nullptr;
     YRT_TRY(lbvh_build(device, st, na, 1, ilo.as<float4>(), ihi.as<float4>(), tl_seg_of.as<int>(), tl_seg_first.as<int>(), leaf_tlas, to));
     YRT_TRY(ds.inst_recs.alloc(sizeof(float4) * 4 * (size_t)std::max(na, 1), device));

@@ -141,7 +141,7 @@ struct LbvhArrays {
     float4* node_lo;       // [n-1] refit bounds of internal nodes
     float4* node_hi;
     // outputs
-    float4* nodes;         // [4*(n-1)]
+    float4* nodes;         // [YRT_NODE_STRIDE*(n-1)]
     int* seg_root;         // [n_seg] root ref per segment
     int* seg_depth;        // [n_seg] max depth (levels of internal nodes) per segment
     int leaf_size;
@@ -495,7 +495,7 @@ YRT_HD void emit_item(const LbvhArrays& a, int i) {
     float4 l0, h0, l1, h1;
     child_box_(a, c0, l0, h0);
     child_box_(a, c1, l1, h1);
-    float4* n = a.nodes + 4 * (size_t)i;
+    float4* n = a.nodes + YRT_NODE_STRIDE * (size_t)i;
     nodebox b0, b1;
     box_center_half(l0.x, h0.x, b0.cx, b0.hx); box_center_half(l0.y, h0.y, b0.cy, b0.hy); box_center_half(l0.z, h0.z, b0.cz, b0.hz);
     box_center_half(l1.x, h1.x, b1.cx, b1.hx); box_center_half(l1.y, h1.y, b1.cy, b1.hy); box_center_half(l1.z, h1.z, b1.cz, b1.hz);

@@ -53,13 +53,14 @@ __device__ __forceinline__ void trace_packet(const SceneView& sv, const ray3& wr
     for (;;) {
         // ---- internal nodes ----
         while (cur >= 0) {
-            const float4* n = sv.nodes + 4 * (size_t)cur;
-            float4 q0 = ld4(n), q1 = ld4(n + 1), q2 = ld4(n + 2), q3 = ld4(n + 3);   // same address in every lane: one broadcast each
+            float4 q0, q1, q2, q3;
+            node_load(sv.nodes, cur, q0, q1, q2, q3);   // same address in every lane: one broadcast each
             float e0, e1;
             bool h0, h1;
             slab_test_node(sr, tmin, tmax, q0, q1, q2, h0, h1, e0, e1);
             unsigned m0 = __ballot_sync(FULL, h0), m1 = __ballot_sync(FULL, h1);
-            int c0 = float_as_int(q3.x), c1 = float_as_int(q3.y);
+            int c0, c1;
+            node_refs(q1, q3, c0, c1);
             if (m0 && m1) {
                 bool swap = false;
                 if (!ANY) {   // near child first, by majority of the lanes that enter both (else of all entering lanes)

@@ -93,11 +93,59 @@ YRT_HD nodebox node_child(const float4& q0, const float4& q1, const float4& q2, 
     else        { b.cx = q0.z; b.cy = q0.w; b.cz = q2.y; b.hx = q1.z; b.hy = q1.w; b.hz = q2.w; }
     return b;
 }
+// YRT_NODE48 (build option, off): a 48-byte node.  The two child references ride in the low 16 bits of the four x / y
+// half-extents, whose upper 16 bits hold the half-extent rounded UP to bfloat16 — so the stored value (reference bits
+// included) is never below the inflated half-extent the slab test's error analysis asks for, at most 2^-7 above it.  A
+// node visit then returns 48 instead of 56 bytes per lane over the L1 data path (12 instead of 14 cycles per warp,
+// DESIGN.md 3.2) for two byte permutes.
+#ifndef YRT_NODE48
+#define YRT_NODE48 0
+#endif
+#define YRT_NODE_STRIDE (YRT_NODE48 ? 3 : 4)   /* float4 per node */
+YRT_HD float half_with_payload_(float h, unsigned payload16) {
+    unsigned b = (unsigned)float_as_int(h);
+    b = (b + 0xffffu) & 0xffff0000u;            // round up to a bfloat16 (h >= 0, finite)
+    if (b >= 0x7f800000u) b = 0x7f7f0000u;      // (never for real scenes: stay finite)
+    return int_as_float((int)(b | (payload16 & 0xffffu)));
+}
 YRT_HD void node_pack(float4* n, const nodebox& b0, const nodebox& b1, int ref0, int ref1) {
     n[0] = mk4(b0.cx, b0.cy, b1.cx, b1.cy);
+#if YRT_NODE48
+    n[1] = mk4(half_with_payload_(b0.hx, (unsigned)ref0), half_with_payload_(b0.hy, (unsigned)ref0 >> 16),
+               half_with_payload_(b1.hx, (unsigned)ref1), half_with_payload_(b1.hy, (unsigned)ref1 >> 16));
+    n[2] = mk4(b0.cz, b1.cz, b0.hz, b1.hz);
+#else
     n[1] = mk4(b0.hx, b0.hy, b1.hx, b1.hy);
     n[2] = mk4(b0.cz, b1.cz, b0.hz, b1.hz);
     n[3] = mk4(int_as_float(ref0), int_as_float(ref1), 0.f, 0.f);
+#endif
+}
+// the two child references of a node record (q1 = second float4; q3 = fourth float4 of the 64-byte layout)
+YRT_HD void node_refs(const float4& q1, const float4& q3, int& ref0, int& ref1) {
+#if YRT_NODE48
+    (void)q3;
+#if defined(__CUDA_ARCH__)
+    ref0 = (int)__byte_perm((unsigned)float_as_int(q1.x), (unsigned)float_as_int(q1.y), 0x5410);
+    ref1 = (int)__byte_perm((unsigned)float_as_int(q1.z), (unsigned)float_as_int(q1.w), 0x5410);
+#else
+    ref0 = (int)(((unsigned)float_as_int(q1.x) & 0xffffu) | ((unsigned)float_as_int(q1.y) << 16));
+    ref1 = (int)(((unsigned)float_as_int(q1.z) & 0xffffu) | ((unsigned)float_as_int(q1.w) << 16));
+#endif
+#else
+    (void)q1;
+    ref0 = float_as_int(q3.x); ref1 = float_as_int(q3.y);
+#endif
+}
+// loads one node record
+YRT_HD void node_load(const float4* nodes, int node, float4& q0, float4& q1, float4& q2, float4& q3) {
+    const float4* n = nodes + YRT_NODE_STRIDE * (size_t)node;
+    ld8(n, q0, q1);
+#if YRT_NODE48
+    q2 = ld4(n + 2);
+    q3 = q2;
+#else
+    ld8(n + 2, q2, q3);
+#endif
 }
 
 #if defined(__CUDA_ARCH__)

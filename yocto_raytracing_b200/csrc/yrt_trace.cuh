@@ -227,7 +227,7 @@ struct Tracer {
     // a node whose visit is postponed: start pulling its record towards the SM
     YRT_HD void prefetch_node(const SceneView& sv, int ref) {
 #if YRT_PREFETCH_PUSH && defined(__CUDA_ARCH__)
-        if (ref >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(sv.nodes + 4 * (size_t)ref));
+        if (ref >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(sv.nodes + YRT_NODE_STRIDE * (size_t)ref));
 #else
         (void)sv; (void)ref;
 #endif
@@ -235,10 +235,8 @@ struct Tracer {
 
     // one internal node: test both child boxes against the current ray and current tmax, near child first
     YRT_HD void visit(const SceneView& sv, int* stack, TraceCounters* ctr) {
-        const float4* n = sv.nodes + 4 * (size_t)cur;
         float4 q0, q1, q2, q3;
-        ld8(n, q0, q1);          // a 64-byte node = two 256-bit loads
-        ld8(n + 2, q2, q3);
+        node_load(sv.nodes, cur, q0, q1, q2, q3);
         float e0, e1;
         bool h0, h1;
         if (EXACT) {
@@ -263,7 +261,8 @@ struct Tracer {
             ctr->slab_false_rejects += (r0 && !h0) + (r1 && !h1);
             ctr->slab_extra_accepts += (!r0 && h0) + (!r1 && h1);
         }
-        int c0 = float_as_int(q3.x), c1 = float_as_int(q3.y);
+        int c0, c1;
+        node_refs(q1, q3, c0, c1);
 #if YRT_VISIT_V2
         // one select for the next node, one predicated push when both children are entered, one branch for the pop
         if (h0 || h1) {
