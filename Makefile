@@ -36,13 +36,16 @@ oracle: oracle/liboracle.so
 oracle/liboracle.so: oracle/yrt_oracle.c oracle/yrt_oracle.h include/yrt_b200.h
 	$(ORACLE_CC) -std=c11 -O2 -fPIC -shared -ffp-contract=off -fopenmp -o $@ oracle/yrt_oracle.c -lm
 
-hostemu: tests/host_emu/libyrt_hostemu.so tests/host_emu/libyrt_hostemu_node48.so
-# the same emulation with the 48-byte node layout (-DYRT_NODE48=1, a build option of the library that is off by default):
-# keeps that layout's packing / unpacking and its conservative half-extents under test without a GPU
-tests/host_emu/libyrt_hostemu_node48.so: tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu $(HDRS)
-	$(NVCC) -O2 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-ffp-contract=off,-fopenmp -shared -DYRT_NODE48=1 -I$(CSRC) -o $@ tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu -lgomp
+hostemu: tests/host_emu/libyrt_hostemu.so tests/host_emu/libyrt_hostemu_bin.so tests/host_emu/libyrt_hostemu_pack.so
+# the same emulation with the library's other node layouts (build options, see yrt_scene.cuh): binary nodes (-DYRT_WIDE=2) and
+# child references packed into the half-extents (-DYRT_PACK_REFS=1) — keeps them under test without a GPU
+EMUFLAGS := -O2 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-ffp-contract=off,-fopenmp -shared
+tests/host_emu/libyrt_hostemu_bin.so: tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu $(HDRS)
+	$(NVCC) $(EMUFLAGS) -DYRT_WIDE=2 -I$(CSRC) -o $@ tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu -lgomp
+tests/host_emu/libyrt_hostemu_pack.so: tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu $(HDRS)
+	$(NVCC) $(EMUFLAGS) -DYRT_PACK_REFS=1 -I$(CSRC) -o $@ tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu -lgomp
 tests/host_emu/libyrt_hostemu.so: tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu $(HDRS)
-	$(NVCC) -O2 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-ffp-contract=off,-fopenmp -shared $(EXTRA) -I$(CSRC) -o $@ tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu -lgomp
+	$(NVCC) $(EMUFLAGS) $(EXTRA) -I$(CSRC) -o $@ tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu -lgomp
 
 ref: oracle/_ref/raytrace_ref oracle/_ref/ref_probe bin/raytrace bin/yrt_flatten
 oracle/_ref/%.o: $(REF)/src/%.cpp
@@ -64,4 +67,4 @@ bin/yrt_flatten: $(HOST)/yrt_flatten_tool.cpp $(HOST)/yrt_flatten.cpp $(HOST)/yr
 	$(CXX) $(REFFLAGS) -I$(REF)/src -I$(HOST) -o $@ $(HOST)/yrt_flatten_tool.cpp $(HOST)/yrt_flatten.cpp $(REFOBJ)
 
 clean:
-	rm -rf build bin oracle/_ref oracle/liboracle.so tests/host_emu/libyrt_hostemu.so tests/host_emu/libyrt_hostemu_node48.so $(LIB)
+	rm -rf build bin oracle/_ref oracle/liboracle.so tests/host_emu/libyrt_hostemu*.so $(LIB)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define YRT_ABI_VERSION 1
+#define YRT_ABI_VERSION 2
 
 typedef enum yrt_status {
     YRT_OK = 0,
@@ -115,6 +115,9 @@ typedef struct yrt_stats {
     int32_t n_closest, n_any, n_shade, n_other;   /* launches per category (device 0)          */
     int32_t frames;           /* frames the totals cover (1, or all frames between yrt_stats_begin/end) */
     int32_t reserved;
+    int64_t truncated_paths;  /* mirror bounces dropped at the recursion cap (YRT_MAX_DEPTH, default 16); the
+                                 reference recurses without a bound (src/raytrace.cpp:190-204) — 0 means the
+                                 frame is what unbounded recursion gives                                      */
 } yrt_stats;
 
 typedef struct yrt_scene yrt_scene;   /* opaque: device-resident scene + LBVH on every initialised GPU */
@@ -139,14 +142,22 @@ void yrt_scene_destroy(yrt_scene* scn);
  * [4]=lights, [5]=prims, [6]=build microseconds (device 0), [7]=reflective materials */
 int yrt_scene_info(const yrt_scene* scn, int64_t out[8]);
 
+/* Allocates the render workspace of a (width x height, samples per axis) frame now, so that the first yrt_render of that
+ * size does not pay for it (1.7 GB for 1920x1080, 16 spp).  Optional. */
+int yrt_scene_prepare(yrt_scene* scn, int width, int height, int samples);
+
 /* Number of instances whose frame is not rigid (x, y, z orthonormal within 1e-4).  The reference hands every instance
  * the ray through transform_ray_inverse (src/vmath.h:275-278: dot products with the frame axes, direction re-normalised),
  * which is the inverse only of a rigid frame, and then compares the LOCAL hit distances of different instances with each
  * other and with the world-space boxes (src/scene.cpp:468-473): for scaled or sheared frames its result depends on the
- * order in which its own BVH happens to visit the instances.  This library reproduces the reference for rigid frames
- * (every scene of the reference; its OBJ `i` lines and glTF node transforms may carry others); for the rest it renders
- * the same per-instance arithmetic in its own visit order, and the caller can warn.  Pure host function, needs no GPU. */
+ * order in which its own BVH happens to visit the instances, which no other tree can reproduce.  This library reproduces
+ * the reference for rigid frames (every scene of the reference; its OBJ `i` lines and glTF node transforms may carry
+ * others) and REJECTS scenes with non-rigid frames: yrt_scene_create returns YRT_ERR_UNSUPPORTED, unless the caller has
+ * opted in with yrt_set_option("allow_nonrigid", 1) — then the same per-instance arithmetic runs in this library's visit
+ * order and the image may differ from the reference's where such instances overlap.  Pure host function, needs no GPU. */
 int yrt_desc_nonrigid_instances(const yrt_scene_desc* desc);
+/* process-wide options; unknown names return YRT_ERR_INVALID.  "allow_nonrigid" (0/1, default 0): see above. */
+int yrt_set_option(const char* name, int value);
 
 /* Optional replacement of save_image(filename, image4b) (src/image.cpp:41-44, stb_image_write's single-threaded PNG
  * encoder: 0.63 s at 1920x1080): writes the same RGBA8 pixels (row-major, width*4 bytes per row, like
@@ -221,6 +232,16 @@ int yrt_trace_primary(yrt_scene* scn, const yrt_camera* cam, int width, int heig
 int yrt_intersect_first(yrt_scene* scn, const float* rays, int64_t n, int32_t* ids_out,
                         float* dist_out, float* uv_out);
 int yrt_intersect_any(yrt_scene* scn, const float* rays, int64_t n, uint8_t* occluded_out);
+
+/* Per-ray work counters of the traversal kernels, for the roofline record ("the builder must also report its
+ * own per-ray counters"; the reference's sit at src/scene.cpp:371,229,468).  Only a library built with -DYRT_COUNTERS=1
+ * counts (tools/build_variants.sh; never the timed build): the regular build returns YRT_ERR_UNSUPPORTED.  out = 3 kernel
+ * classes (camera rays, mirror rays, shadow rays) x 8 words: rays, node visits, box tests, box tests in the instance tree,
+ * element tests, instance entries, 0, 0 — totals since the last call (reading resets them). */
+int yrt_counters_read(yrt_scene* scn, uint64_t out[24]);
+
+/* test hook: sorts n (key, value) pairs held in HOST arrays with the device radix sort of the LBVH build */
+int yrt_debug_sort_pairs(unsigned long long* h_keys, int* h_vals, int n);
 
 /* next-row: tonemap (src/image.cpp:55-78, exposure 0, no filmic, sRGB 1/2.2,
  * truncating) of a HOST float image into HOST RGBA8, computed on the device. */

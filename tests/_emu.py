@@ -22,7 +22,7 @@ _libs = {}
 
 
 def lib(variant=""):
-    """The emulation library; variant "node48" = built with -DYRT_NODE48=1 (48-byte traversal nodes)."""
+    """The emulation library; variants: "bin" = -DYRT_WIDE=2 (binary traversal nodes), "pack" = -DYRT_PACK_REFS=1."""
     if variant not in _libs:
         l = C.CDLL(_path(variant))
         l.emu_last_error.restype = C.c_char_p
@@ -73,7 +73,7 @@ class EmuScene:
         img = np.empty((height, width, 4), np.float32)
         cam = self.flat.camera_struct()
         a = (C.c_float * 3)(amb, amb, amb)
-        rc = (C.c_int64 * 8)()
+        rc = (C.c_int64 * 9)()
         st = self._lib.emu_render(self.h, C.byref(cam), a, width, height, samples, max_depth, C.c_void_p(img.ctypes.data), rc)
         assert st == 0
         return img, list(rc)
@@ -84,15 +84,3 @@ class EmuScene:
                 self._lib.emu_scene_destroy(self.h)
         except Exception:
             pass
-
-
-def workdist(mode, width=0, nrows=0, spp=1, tile_w=16, tile_h=8, chunk_items=2048, n_items=0, n_threads=16, n_sm=4):
-    """Runs the persistent kernels' work-distribution protocol (csrc/yrt_work.cuh) on host threads.
-    Returns (per-item hand-out counts, n_chunks, tasks handed out, max tasks of one thread)."""
-    n = width * nrows * spp if mode == 1 else n_items
-    count = np.zeros(max(n, 1), np.uint8)
-    tasks = C.c_longlong(0)
-    mx = C.c_longlong(0)
-    nc = lib().emu_workdist(mode, width, nrows, spp, tile_w, tile_h, C.c_uint(chunk_items), C.c_uint(n), n_threads, n_sm,
-                            C.c_void_p(count.ctypes.data), C.byref(tasks), C.byref(mx))
-    return count[:n], nc, tasks.value, mx.value

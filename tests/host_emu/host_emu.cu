@@ -15,7 +15,6 @@
 #include "yrt_internal.h"
 #include "yrt_shade.cuh"
 #include "yrt_trace.cuh"
-#include "yrt_work.cuh"
 
 using namespace yrt;
 
@@ -23,7 +22,7 @@ namespace {
 
 struct EmuLbvh {
     std::vector<float4> nodes;
-    std::vector<int> order, seg_root, seg_depth, seg_box_lo, seg_box_hi;
+    std::vector<int> order, seg_root, seg_depth, seg_need, seg_box_lo, seg_box_hi;
 };
 
 void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi, const int* seg_of, const int* seg_first, int leaf_size,
@@ -40,6 +39,8 @@ void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi
     out.nodes.assign(YRT_NODE_STRIDE * ni, mk4(0, 0, 0, 0));
     out.seg_root.assign(n_seg, 0);
     out.seg_depth.assign(n_seg, 0);
+    out.seg_need.assign(n_seg, 0);
+    std::vector<int> need(ni, 0);
     LbvhArrays a;
     a.n = n; a.n_seg = n_seg; a.box_lo = lo.data(); a.box_hi = hi.data(); a.seg_of = seg_of; a.seg_first = seg_first;
     a.seg_cent_lo = cent_lo.data(); a.seg_cent_hi = cent_hi.data(); a.seg_box_lo = out.seg_box_lo.data(); a.seg_box_hi = out.seg_box_hi.data();
@@ -47,7 +48,7 @@ void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi
     a.range_first = rfirst.data(); a.range_last = rlast.data(); a.parent_int = pint.data(); a.parent_leaf = pleaf.data();
     a.count = count.data(); a.new_slot = new_slot.data(); a.order_tmp = order_tmp.data(); a.parent_leaf_tmp = pleaf_tmp.data();
     a.flags = flags.data(); a.node_lo = nlo.data(); a.node_hi = nhi.data(); a.nodes = out.nodes.data();
-    a.seg_root = out.seg_root.data(); a.seg_depth = out.seg_depth.data(); a.leaf_size = leaf_size; a.ref_offset = ref_offset; a.size_bits = size_bits;
+    a.seg_root = out.seg_root.data(); a.seg_depth = out.seg_depth.data(); a.seg_need = out.seg_need.data(); a.need = need.data(); a.leaf_size = leaf_size; a.ref_offset = ref_offset; a.size_bits = size_bits;
     a.rotate_pairs = rotate_pairs;
     for (int s = 0; s < n_seg; s++) seg_bounds_init_item(a, s);
     for (int i = 0; i < n; i++) seg_bounds_item(a, i);
@@ -78,7 +79,11 @@ void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi
         for (int i = 0; i < n - 1; i++) emit_item(a, i);
     }
     for (int s = 0; s < n_seg; s++) single_root_item(a, s);
-    if (n > 1) for (int i = 0; i < n; i++) depth_item(a, i);
+    if (n > 1) {
+        for (int i = 0; i < n; i++) depth_item(a, i);
+        std::fill(flags.begin(), flags.end(), 0);
+        for (int i = 0; i < n; i++) stackneed_item(a, i);
+    }
 }
 
 struct EmuScene {
@@ -88,7 +93,7 @@ struct EmuScene {
     std::vector<int> prim_rank, inst_rank;
     std::vector<float4> nodes;   // BLAS nodes then TLAS nodes, like the device array
     SceneView view;
-    int blas_depth = 0, tlas_depth = 0;
+    int blas_depth = 0, tlas_depth = 0, stack_need = 0;
 };
 
 int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tlas) {
@@ -132,10 +137,7 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
         pack_prim(kind, e, p0, p1, p2, kind == 0 ? 0.f : g.radius[v[0]], kind == 1 ? g.radius[v[1]] : 0.f, pr, ar);
         ar[0] = mk4(n0.x, n0.y, n0.z, u0); ar[1] = mk4(n1.x, n1.y, n1.z, w0); ar[2] = mk4(n2.x, n2.y, n2.z, u1); ar[3] = mk4(w1, u2, w2, 0.f);
     }
-    // TLAS (mirrors k_inst_boxes / k_inst_recs).  Prototype switch YRT_EMU_OPEN=d (host emulation only, profiles/r1_experiments.md):
-    // "opening" an instance replaces it in the TLAS by the 2^d subtrees d levels below its BLAS root, each item carrying the
-    // instance's frame and its own subtree root — the top of the instance's BLAS is re-built together with its neighbours.
-    const int open_depth = getenv("YRT_EMU_OPEN") ? atoi(getenv("YRT_EMU_OPEN")) : 0;
+    // TLAS (mirrors k_inst_boxes / k_inst_recs)
     int na0 = (int)hs.active_inst.size();
     struct Item { int active; int root; Box box; };
     std::vector<Item> items;
@@ -144,25 +146,7 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
         Box b;
         b.lo = mk3(ordered_to_float(es.blas.seg_box_lo[3 * s]), ordered_to_float(es.blas.seg_box_lo[3 * s + 1]), ordered_to_float(es.blas.seg_box_lo[3 * s + 2]));
         b.hi = mk3(ordered_to_float(es.blas.seg_box_hi[3 * s]), ordered_to_float(es.blas.seg_box_hi[3 * s + 1]), ordered_to_float(es.blas.seg_box_hi[3 * s + 2]));
-        std::vector<Item> cur = {{a, es.blas.seg_root[s], b}};
-        for (int lvl = 0; lvl < open_depth; lvl++) {
-            std::vector<Item> nxt;
-            for (const Item& it : cur) {
-                if (it.root < 0) { nxt.push_back(it); continue; }       // a leaf cannot be opened
-                const float4* n = &es.blas.nodes[YRT_NODE_STRIDE * (size_t)it.root];
-                int cref[2];
-                node_refs(n[1], n[YRT_NODE_STRIDE - 1], cref[0], cref[1]);
-                for (int k = 0; k < 2; k++) {
-                    nodebox cb = node_child(n[0], n[1], n[2], k);
-                    Box c;
-                    c.lo = mk3(cb.cx - cb.hx, cb.cy - cb.hy, cb.cz - cb.hz);
-                    c.hi = mk3(cb.cx + cb.hx, cb.cy + cb.hy, cb.cz + cb.hz);
-                    nxt.push_back({a, cref[k], c});
-                }
-            }
-            cur.swap(nxt);
-        }
-        items.insert(items.end(), cur.begin(), cur.end());
+        items.push_back({a, es.blas.seg_root[s], b});
     }
     int na = (int)items.size();
     std::vector<float4> ilo(std::max(na, 1)), ihi(std::max(na, 1));
@@ -198,7 +182,8 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
     }
     es.blas_depth = es.blas.seg_depth.empty() ? 0 : *std::max_element(es.blas.seg_depth.begin(), es.blas.seg_depth.end());
     es.tlas_depth = es.tlas.seg_depth[0];
-    if (es.blas_depth + es.tlas_depth + 4 > YRT_STACK_CAP) { set_error("emu: tree too deep"); return YRT_ERR_UNSUPPORTED; }
+    es.stack_need = es.tlas.seg_need[0] + (es.blas.seg_need.empty() ? 0 : *std::max_element(es.blas.seg_need.begin(), es.blas.seg_need.end())) + 3;
+    if (es.stack_need > YRT_STACK_CAP) { set_error("emu: tree too deep"); return YRT_ERR_UNSUPPORTED; }
     SceneView& v = es.view;
     v.nodes = es.nodes.data(); v.inst_recs = es.inst_recs.data();
     v.prim_recs = es.prim_recs.data(); v.prim_attrs = es.prim_attrs.data(); v.mat_recs = hs.mat_recs.data();
@@ -233,11 +218,12 @@ void emu_scene_destroy(void* p) { delete (EmuScene*)p; }
 int emu_scene_info(void* p, int64_t out[8]) {
     EmuScene* es = (EmuScene*)p;
     out[0] = es->hs.n_prims > 1 ? es->hs.n_prims - 1 : 0; out[1] = es->view.n_active_instances > 1 ? es->view.n_active_instances - 1 : 0;
-    out[2] = es->blas_depth; out[3] = es->tlas_depth; out[4] = es->view.n_lights; out[5] = es->hs.n_prims; out[6] = 0; out[7] = es->hs.n_reflective;
+    out[2] = es->blas_depth; out[3] = es->tlas_depth; out[4] = es->view.n_lights; out[5] = es->hs.n_prims; out[6] = es->stack_need; out[7] = es->hs.n_reflective;
     return YRT_OK;
 }
 
-// counters_out (optional, 6 int64): box tests, prim tests, instance entries, max stack, fused-slab false rejects / extra accepts
+// counters_out (optional, 8 int64): box tests, prim tests, instance entries, max stack, fused-slab false rejects / extra accepts,
+// box tests in the instance tree, node visits
 int emu_trace_primary(void* p, const yrt_camera* cam, int width, int height, int samples, int32_t* ids, float* dist, float* uv,
                       int64_t* counters_out) {
     EmuScene* es = (EmuScene*)p;
@@ -247,10 +233,10 @@ int emu_trace_primary(void* p, const yrt_camera* cam, int width, int height, int
         ck.frame.x = mk3(f[0], f[1], f[2]); ck.frame.y = mk3(f[3], f[4], f[5]); ck.frame.z = mk3(f[6], f[7], f[8]); ck.frame.o = mk3(f[9], f[10], f[11]);
         ck.h = 2.0f * cam->focus * tanf(cam->fovy / 2.0f); ck.w = ck.h * cam->aspect; ck.focus = cam->focus;
     }
-    long long cb = 0, cp = 0, ci = 0, cfr = 0, cea = 0, ctb = 0; int cm = 0;
-#pragma omp parallel for schedule(dynamic, 4) reduction(+ : cb, cp, ci, cfr, cea, ctb) reduction(max : cm)
+    long long cb = 0, cp = 0, ci = 0, cfr = 0, cea = 0, ctb = 0, cnv = 0; int cm = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : cb, cp, ci, cfr, cea, ctb, cnv) reduction(max : cm)
     for (int j = 0; j < height; j++) {
-        int stack[YRT_STACK_CAP];
+        int stack[2 * YRT_STACK_CAP];
         for (int i = 0; i < width; i++)
             for (int jj = 0; jj < samples; jj++)
                 for (int ii = 0; ii < samples; ii++) {
@@ -259,16 +245,16 @@ int emu_trace_primary(void* p, const yrt_camera* cam, int width, int height, int
                     sample_uv(i, j, ii, jj, samples, width, height, u, v);
                     ray3 ray = eval_camera(ck, u, v);
                     HitRec h;
-                    TraceCounters tc = {0, 0, 0, 0, 0, 0, 0};
+                    TraceCounters tc = {0, 0, 0, 0, 0, 0, 0, 0};
                     trace_ray<false>(es->view, ray, h, stack, &tc);
                     cb += tc.box_tests; cp += tc.prim_tests; ci += tc.inst_entries; cm = std::max(cm, tc.max_stack);
-                    cfr += tc.slab_false_rejects; cea += tc.slab_extra_accepts; ctb += tc.tlas_box_tests;
+                    cfr += tc.slab_false_rejects; cea += tc.slab_extra_accepts; ctb += tc.tlas_box_tests; cnv += tc.node_visits;
                     hit_to_ids(es->view, h, ids + 3 * r);
                     if (dist) dist[r] = h.dist;
                     if (uv) { uv[2 * r] = h.w1; uv[2 * r + 1] = h.w2; }
                 }
     }
-    if (counters_out) { counters_out[0] = cb; counters_out[1] = cp; counters_out[2] = ci; counters_out[3] = cm; counters_out[4] = cfr; counters_out[5] = cea; counters_out[6] = ctb; }
+    if (counters_out) { counters_out[0] = cb; counters_out[1] = cp; counters_out[2] = ci; counters_out[3] = cm; counters_out[4] = cfr; counters_out[5] = cea; counters_out[6] = ctb; counters_out[7] = cnv; }
     return YRT_OK;
 }
 
@@ -278,12 +264,12 @@ int emu_intersect(void* p, const float* rays, int64_t n, int32_t* ids, float* di
     long long fr = 0;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : fr)
     for (int64_t r = 0; r < n; r++) {
-        int stack[YRT_STACK_CAP];
+        int stack[2 * YRT_STACK_CAP];
         const float* q = rays + 8 * r;
         ray3 ray;
         ray.o = mk3(q[0], q[1], q[2]); ray.d = mk3(q[3], q[4], q[5]); ray.tmin = q[6]; ray.tmax = q[7];
         HitRec h;
-        TraceCounters tc = {0, 0, 0, 0, 0, 0, 0};
+        TraceCounters tc = {0, 0, 0, 0, 0, 0, 0, 0};
         trace_ray<false>(es->view, ray, h, stack, &tc);
         hit_to_ids(es->view, h, ids + 3 * r);
         dist[r] = h.dist;
@@ -297,8 +283,8 @@ int emu_intersect(void* p, const float* rays, int64_t n, int32_t* ids, float* di
 
 // the whole frame with the device functions: raygen -> closest -> shadow (any) -> shade -> reflection
 // loop with the same explicit {c, kr, la} stack as k_shade -> ordered per-pixel sum.
-// ray_counts (optional, 8 int64): primary, reflection, shadow, then for the shadow rays: box tests, tlas box tests,
-// prim tests, instance entries, occluded
+// ray_counts (optional, 9 int64): primary, reflection, shadow, then for the shadow rays: box tests, tlas box tests,
+// prim tests, instance entries, occluded, node visits
 int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, int height, int samples, int max_depth, float* rgba,
                int64_t* ray_counts) {
     EmuScene* es = (EmuScene*)p;
@@ -311,10 +297,10 @@ int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, in
     }
     vec3 ambv = mk3(amb[0], amb[1], amb[2]);
     if (max_depth <= 0) max_depth = 16;
-    long long n_refl = 0, n_shadow = 0, sb = 0, stb = 0, sp_ = 0, si_ = 0, socc = 0;
-#pragma omp parallel for schedule(dynamic, 2) reduction(+ : n_refl, n_shadow, sb, stb, sp_, si_, socc)
+    long long n_refl = 0, n_shadow = 0, sb = 0, stb = 0, sp_ = 0, si_ = 0, socc = 0, snv = 0;
+#pragma omp parallel for schedule(dynamic, 2) reduction(+ : n_refl, n_shadow, sb, stb, sp_, si_, socc, snv)
     for (int j = 0; j < height; j++) {
-        int stack[YRT_STACK_CAP];
+        int stack[2 * YRT_STACK_CAP];
         std::vector<vec3> sc(max_depth), skr(max_depth), sla(max_depth);
         std::vector<uint8_t> vis(std::max(sv.n_lights, 1));
         for (int i = 0; i < width; i++) {
@@ -338,10 +324,10 @@ int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, in
                             light_vector(sv, k, P, l, r, ke);
                             ray3 sr = shadow_ray(P, l, r);
                             HitRec hr;
-                            TraceCounters tc = {0, 0, 0, 0, 0, 0, 0};
+                            TraceCounters tc = {0, 0, 0, 0, 0, 0, 0, 0};
                             vis[k] = trace_ray<true>(sv, sr, hr, stack, &tc) ? 0 : 1;
                             n_shadow++;
-                            sb += tc.box_tests; stb += tc.tlas_box_tests; sp_ += tc.prim_tests; si_ += tc.inst_entries; socc += vis[k] ? 0 : 1;
+                            sb += tc.box_tests; stb += tc.tlas_box_tests; sp_ += tc.prim_tests; si_ += tc.inst_entries; socc += vis[k] ? 0 : 1; snv += tc.node_visits;
                         }
                         vec3 c, kr, la; ray3 rr;
                         bool spawn = shade_hit(sv, h.si, h.prim, h.w1, h.w2, ray.o, ambv, sv.srgb_lut, [&](int k) { return vis[k] != 0; },
@@ -360,57 +346,8 @@ int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, in
         }
     }
     if (ray_counts) { ray_counts[0] = (long long)width * height * samples * samples; ray_counts[1] = n_refl; ray_counts[2] = n_shadow;
-        ray_counts[3] = sb; ray_counts[4] = stb; ray_counts[5] = sp_; ray_counts[6] = si_; ray_counts[7] = socc; }
+        ray_counts[3] = sb; ray_counts[4] = stb; ray_counts[5] = sp_; ray_counts[6] = si_; ray_counts[7] = socc; ray_counts[8] = snv; }
     return YRT_OK;
-}
-
-// The work-distribution protocol of the persistent kernels (yrt_work.cuh), run by host threads playing warps:
-// n_threads "warps" spread over n_sm state words fetch tasks until the input is exhausted and count, per item, how
-// often it was handed out (must be exactly once).  mode 1: tiles over nrows x width x spp; mode 2: runs over n_items.
-// (the methods are only ever called on the host; the __device__ halves exist because fetch_task is a __host__ __device__ template)
-struct HostAtomics {
-#ifndef __CUDA_ARCH__
-    __host__ __device__ unsigned long long add64(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-    __host__ __device__ unsigned long long exch64(unsigned long long* p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
-    __host__ __device__ unsigned long long load64(unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
-    __host__ __device__ unsigned add32(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-    __host__ __device__ void pause() { std::this_thread::yield(); }
-#else
-    __host__ __device__ unsigned long long add64(unsigned long long*, unsigned long long) { return 0; }
-    __host__ __device__ unsigned long long exch64(unsigned long long*, unsigned long long) { return 0; }
-    __host__ __device__ unsigned long long load64(unsigned long long*) { return 0; }
-    __host__ __device__ unsigned add32(unsigned*, unsigned) { return 0; }
-    __host__ __device__ void pause() {}
-#endif
-};
-
-int emu_workdist(int mode, int width, int nrows, int spp, int tile_w, int tile_h, unsigned chunk_items, unsigned n_items, int n_threads,
-                 int n_sm, uint8_t* count, long long* tasks_out, long long* max_tasks_per_thread) {
-    std::vector<unsigned> rec(YRT_WORK_BLOCK_WORDS, 0u);
-    WorkDist wd = mode == 1 ? workdist_tiles(rec.data(), width, nrows, spp, tile_w, tile_h) : workdist_runs(rec.data(), n_items, chunk_items);
-    std::vector<long long> per_thread(n_threads, 0);
-    std::vector<std::thread> th;
-    for (int t = 0; t < n_threads; t++)
-        th.emplace_back([&, t]() {
-            HostAtomics at;
-            unsigned chunk, k;
-            while (fetch_task(at, wd, (unsigned)(t % n_sm), chunk, k)) {
-                per_thread[t]++;
-                for (int lane = 0; lane < 32; lane++) {
-                    unsigned item;
-                    if (task_item(wd, chunk, k, lane, item)) {
-                        if (item >= wd.n_items) { __atomic_fetch_add(&count[0], (uint8_t)100, __ATOMIC_RELAXED); continue; }
-                        __atomic_fetch_add(&count[item], (uint8_t)1, __ATOMIC_RELAXED);
-                    }
-                }
-            }
-        });
-    for (auto& x : th) x.join();
-    long long total = 0, mx = 0;
-    for (long long v : per_thread) { total += v; if (v > mx) mx = v; }
-    *tasks_out = total;
-    *max_tasks_per_thread = mx;
-    return (int)wd.n_chunks;
 }
 
 }  // extern "C"

@@ -24,13 +24,13 @@ def test_header_symbols_all_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/yrt_b200.h but not exported"
         assert n in _lib.SYMBOLS, f"{n} has no ctypes prototype"
-    assert lib.yrt_abi_version() == 1
+    assert lib.yrt_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     # sizes implied by the header on LP64
     assert C.sizeof(_lib.Camera) == 16 * 4
-    assert C.sizeof(_lib.Stats) == 4 * 8 + 6 * 4 + 8 * 4
+    assert C.sizeof(_lib.Stats) == 4 * 8 + 6 * 4 + 8 * 4 + 8
     assert C.sizeof(_lib.SceneDesc) == 6 * 4 + 26 * 8 + 8
 
 

@@ -145,18 +145,15 @@ def test_determinism_and_batching(gpu, monkeypatch):
     assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
 
 
-def test_work_distribution_modes_are_bit_identical(gpu, monkeypatch):
-    """SM-affine tiles (csrc/yrt_work.cuh) only change which warp traces which ray: the frame, the hit ids and the ray
-    counts must not depend on the scheme, the tile shape (ragged edges included) or the run length of the queues."""
-    flat = synth.mixed_scene(11).flat()          # reflective floor: exercises the queue launches too
+def test_batch_size_and_grid_do_not_change_the_frame(gpu, monkeypatch):
+    """Which warp traces which ray (batch size, resident CTAs per SM) must not change the frame, the hit ids or the ray
+    counts; a reflective scene exercises the queue launches whose item counts live in device memory."""
+    flat = synth.mixed_scene(11).flat()
     w, h, s = 131, 73, 3
     with gpu.Scene(flat) as scn:
-        monkeypatch.setenv("YRT_TILE", "0")
         a, sa = scn.render(w, h, s, 0.1)
         ia, da, _ = scn.trace_primary(w, h, s)
-        for env in ({}, {"YRT_TILE_W": "5", "YRT_TILE_H": "3", "YRT_TILES_PER_SM": "0"}, {"YRT_TILE_W": "64", "YRT_TILE_H": "64", "YRT_TILES_PER_SM": "0"},
-                    {"YRT_CHUNK_ITEMS": "33"}, {"YRT_BATCH_SLOTS": "7000"}):
-            env = dict(env, YRT_TILE="1")
+        for env in ({"YRT_BATCH_SLOTS": "7000"}, {"YRT_BLOCKS_PER_SM": "1"}, {"YRT_BATCH_SLOTS": "333", "YRT_BLOCKS_PER_SM": "3"}):
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             b, sb = scn.render(w, h, s, 0.1)
@@ -165,7 +162,7 @@ def test_work_distribution_modes_are_bit_identical(gpu, monkeypatch):
                 monkeypatch.delenv(k)
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), env
             assert np.array_equal(ia, ib) and np.array_equal(da.view(np.uint32), db.view(np.uint32)), env
-            assert (sa.primary_rays, sa.shadow_rays, sa.reflection_rays) == (sb.primary_rays, sb.shadow_rays, sb.reflection_rays), env
+            assert (sa.primary_rays, sa.shadow_rays, sa.reflection_rays, sa.max_depth) == (sb.primary_rays, sb.shadow_rays, sb.reflection_rays, sb.max_depth), env
 
 
 def test_edge_cases(gpu, oracle_mod):

@@ -85,17 +85,35 @@ def test_generic_rays_incl_axis_aligned_vs_oracle(oracle_mod):
 
 
 @pytest.mark.parametrize("name", ["instance10000", "mixed7", "lines_synth"])
-def test_node48_layout_is_conservative_and_exact(name):
-    """-DYRT_NODE48=1 (48-byte traversal nodes: child references in the low 16 bits of four half-extents that are rounded
-    UP to bfloat16; a build option of the library, off by default): same hits as the reference, no box the reference
-    would enter is culled, and the looser boxes cost < 2 % more box tests than the 64-byte layout."""
-    if not (_emu.available() and _emu.available("node48")):
-        pytest.skip("host emulation (node48 variant) not built")
+@pytest.mark.parametrize("variant", ["bin", "pack"])
+def test_other_node_layouts_give_the_same_hits(name, variant):
+    """The library's other node layouts (build options): binary nodes (-DYRT_WIDE=2, round 1's tree) and child references
+    packed into the low 16 bits of half-extents that are rounded UP to bfloat16 (-DYRT_PACK_REFS=1): same hits as the
+    reference and as the default 4-wide nodes, no box the reference would enter is culled, and the packed layout's looser
+    boxes cost < 3 % more box tests."""
+    if not (_emu.available() and _emu.available(variant)):
+        pytest.skip(f"host emulation ({variant} variant) not built")
     flat, ref = load_golden(name)
     w, h = int(ref["ids_width"]), int(ref["ids_height"])
-    ids, dist, uv, ctr = _emu.EmuScene(flat, variant="node48").trace_primary(w, h, 1)
+    ids, dist, uv, ctr = _emu.EmuScene(flat, variant=variant).trace_primary(w, h, 1)
     ids0, dist0, uv0, ctr0 = _emu.EmuScene(flat).trace_primary(w, h, 1)
     assert id_match(ids, ref["ids"]) >= 0.9999
     assert np.array_equal(ids, ids0) and np.array_equal(dist.view(np.uint32), dist0.view(np.uint32))
-    assert ctr[4] == 0
-    assert ctr0[0] <= ctr[0] <= 1.02 * ctr0[0], (ctr[0], ctr0[0])
+    assert ctr[4] == 0 and ctr0[4] == 0
+    if variant == "pack":
+        assert ctr0[0] <= ctr[0] <= 1.03 * ctr0[0], (ctr[0], ctr0[0])
+    else:
+        # the 4-wide tree fetches about half as many node records as the binary one
+        assert ctr0[7] < 0.65 * ctr[7], (ctr0[7], ctr[7])
+
+
+def test_stack_need_bounds_the_stack_actually_used():
+    """stackneed_item (csrc/yrt_lbvh.cuh): the bound the build checks against YRT_STACK_CAP is never exceeded by a ray."""
+    from yocto_raytracing_b200 import synth
+    for flat in (load_golden("instance10000")[0], synth.hair_scene(2048, seed=3).flat(), synth.mixed_scene(5).flat()):
+        for variant in ("", "bin"):
+            if not _emu.available(variant):
+                continue
+            es = _emu.EmuScene(flat, variant=variant)
+            ids, dist, uv, ctr = es.trace_primary(128, 72, 1)
+            assert ctr[3] <= es.info()[6] <= 128, (ctr[3], es.info())

@@ -107,34 +107,6 @@ def test_world2_gather_gloo():
         assert "GATHER_OK" in outs[0]
 
 
-@pytest.mark.parametrize("w,h,spp,tw,th", [(1920, 135, 16, 16, 8), (161, 91, 9, 16, 8), (7, 3, 1, 16, 8), (1, 1, 1, 4, 4), (33, 17, 25, 8, 8),
-                                            (1280, 45, 9, 32, 4), (64, 64, 4, 1, 1)])
-def test_work_distribution_tiles_cover_every_slot_once(w, h, spp, tw, th):
-    """csrc/yrt_work.cuh run by host threads playing warps (same protocol code as the device): SM-affine pixel tiles
-    hand every slot of the batch out exactly once, whatever the tile shape and the ragged edges."""
-    import _emu
-    if not _emu.available():
-        pytest.skip("host emulation not built")
-    for n_threads, n_sm in ((24, 5), (7, 7), (32, 1)):
-        count, n_chunks, tasks, _ = _emu.workdist(1, w, h, spp, tw, th, n_threads=n_threads, n_sm=n_sm)
-        assert (count == 1).all()
-        assert n_chunks == -(-w // min(tw, w)) * -(-h // min(th, h))
-        assert tasks >= -(-w * h * spp // 32)
-
-
-@pytest.mark.parametrize("n,chunk", [(0, 2048), (1, 2048), (31, 32), (2049, 2048), (1000003, 1024), (5000, 64)])
-def test_work_distribution_runs_cover_every_entry_once(n, chunk):
-    import _emu
-    if not _emu.available():
-        pytest.skip("host emulation not built")
-    count, n_chunks, tasks, _ = _emu.workdist(2, n_items=n, chunk_items=chunk, n_threads=24, n_sm=5)
-    assert n_chunks == -(-n // chunk)
-    if n:
-        assert (count == 1).all() and tasks >= -(-n // 32)
-    else:
-        assert tasks == 0
-
-
 def test_nonrigid_instance_frames_are_counted():
     """Rigid frames (rotations + translations) are the domain where the reference is well defined; scaled / sheared ones
     are only counted so that the host can warn (include/yrt_b200.h, yrt_desc_nonrigid_instances)."""

@@ -51,7 +51,7 @@ class Stats(C.Structure):
         ("ms_total", C.c_float), ("ms_trace_closest", C.c_float), ("ms_trace_any", C.c_float), ("ms_shade", C.c_float),
         ("ms_other", C.c_float), ("ms_gather", C.c_float), ("max_depth", C.c_int32), ("n_gpus", C.c_int32),
         ("n_closest", C.c_int32), ("n_any", C.c_int32), ("n_shade", C.c_int32), ("n_other", C.c_int32),
-        ("frames", C.c_int32), ("reserved", C.c_int32),
+        ("frames", C.c_int32), ("reserved", C.c_int32), ("truncated_paths", C.c_int64),
     ]
 
     def as_dict(self):
@@ -97,6 +97,10 @@ SYMBOLS = {
     "yrt_intersect_first": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "yrt_intersect_any": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "yrt_tonemap": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "yrt_scene_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "yrt_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "yrt_counters_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "yrt_debug_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
 }
 
 _lib = None
@@ -116,7 +120,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.yrt_abi_version() != 1:
+    if lib.yrt_abi_version() != 2:
         raise RuntimeError("libyrt_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -31,6 +31,7 @@ struct GatherState {          // device-0 side buffers of the in-process multi-G
     }
 };
 GatherState* g_gather = nullptr;
+int g_allow_nonrigid = 0;    // yrt_set_option("allow_nonrigid")
 
 int ensure_init() {
     if (!g_devices.empty()) return YRT_OK;
@@ -100,6 +101,15 @@ int yrt_scene_create(const yrt_scene_desc* desc, yrt_scene** out) {
     yrt_scene* s = new yrt_scene();
     int st = host_scene_from_desc(desc, s->host);
     if (st != YRT_OK) { delete s; return st; }
+    if (!g_allow_nonrigid && !getenv("YRT_ALLOW_NONRIGID")) {
+        int nr = yrt_desc_nonrigid_instances(desc);
+        if (nr > 0) {
+            set_error("%d instance frame(s) are not rigid: the reference's result for them depends on the visit order of its own BVH "
+                      "(src/scene.cpp:468-473) and cannot be reproduced; opt in with yrt_set_option(\"allow_nonrigid\", 1)", nr);
+            delete s;
+            return YRT_ERR_UNSUPPORTED;
+        }
+    }
     st = ensure_init();
     if (st != YRT_OK) { delete s; return st; }
     for (int dev : g_devices) {
@@ -141,6 +151,24 @@ int yrt_desc_nonrigid_instances(const yrt_scene_desc* desc) {
         if (!rigid) n++;
     }
     return n;
+}
+
+int yrt_set_option(const char* name, int value) {
+    if (name && !strcmp(name, "allow_nonrigid")) { g_allow_nonrigid = value != 0; return YRT_OK; }
+    set_error("yrt_set_option: unknown option '%s'", name ? name : "(null)");
+    return YRT_ERR_INVALID;
+}
+
+int yrt_scene_prepare(yrt_scene* scn, int width, int height, int samples) {
+    if (!scn || scn->dev.empty() || width <= 0 || height <= 0 || samples <= 0) { set_error("yrt_scene_prepare: bad arguments"); return YRT_ERR_INVALID; }
+    const int G = (int)scn->dev.size();
+    for (DevScene* ds : scn->dev) YRT_TRY(presize_workspace_device(*ds, width, (height + G - 1) / G, samples));
+    return YRT_OK;
+}
+
+int yrt_counters_read(yrt_scene* scn, uint64_t out[24]) {
+    if (!scn || scn->dev.empty() || !out) { set_error("yrt_counters_read: bad arguments"); return YRT_ERR_INVALID; }
+    return read_counters_device(*scn->dev[0], out);
 }
 
 int yrt_write_png(const char* path, const uint8_t* rgba8, int width, int height, int threads, int level) {

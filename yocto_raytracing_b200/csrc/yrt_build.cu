@@ -40,6 +40,7 @@ __global__ void k_relayout_refs(LbvhArrays a) { int i = YRT_TID(); if (i < a.n -
 __global__ void k_relayout_copy(LbvhArrays a) { int i = YRT_TID(); if (i < a.n) relayout_copy_item(a, i); }
 __global__ void k_single_root(LbvhArrays a) { int s = YRT_TID(); if (s < a.n_seg) single_root_item(a, s); }
 __global__ void k_depth(LbvhArrays a) { int i = YRT_TID(); if (i < a.n) depth_item(a, i); }
+__global__ void k_stackneed(LbvhArrays a) { int i = YRT_TID(); if (i < a.n) stackneed_item(a, i); }
 
 // prim + attribute records in BLAS leaf order
 __global__ void k_gather_prims(GeomView g, const int* __restrict__ order, float4* __restrict__ prim_recs,
@@ -268,6 +269,7 @@ struct LbvhOut {
     int rotate_pairs;     // ... that also try grandchild pair exchanges
     DevBuf* seg_root;     // [n_seg]
     DevBuf* seg_depth;    // [n_seg]
+    DevBuf* seg_need;     // [n_seg] traversal stack entries needed below the segment root
     DevBuf* order;        // [n] item id at sorted slot
     DevBuf* seg_box_lo;   // [3*n_seg] ordered ints (may be null)
     DevBuf* seg_box_hi;
@@ -278,7 +280,7 @@ static inline int grid_for(int n, int t = 256) { return n > 0 ? (n + t - 1) / t 
 static int lbvh_build(int dev, cudaStream_t st, int n, int n_seg, float4* box_lo, float4* box_hi, const int* d_seg_of,
                       const int* d_seg_first, int leaf_size, LbvhOut& out) {
     DevBuf cent_lo, cent_hi, sbox_lo_tmp, sbox_hi_tmp, keys, keys_alt, order_alt, left, right, rfirst, rlast, pint, pleaf,
-        flags, nlo, nhi, ghist, count, new_slot, order_tmp, pleaf_tmp;
+        flags, nlo, nhi, ghist, count, new_slot, order_tmp, pleaf_tmp, need;
     DevBuf* sbl = out.seg_box_lo ? out.seg_box_lo : &sbox_lo_tmp;
     DevBuf* sbh = out.seg_box_hi ? out.seg_box_hi : &sbox_hi_tmp;
     size_t ni = n > 1 ? (size_t)(n - 1) : 1;
@@ -307,6 +309,8 @@ static int lbvh_build(int dev, cudaStream_t st, int n, int n_seg, float4* box_lo
     }
     YRT_TRY(out.seg_root->alloc(sizeof(int) * (size_t)n_seg, dev));
     YRT_TRY(out.seg_depth->alloc(sizeof(int) * (size_t)n_seg, dev));
+    YRT_TRY(out.seg_need->alloc(sizeof(int) * (size_t)n_seg, dev));
+    YRT_TRY(need.alloc(sizeof(int) * ni, dev));
     YRT_CUDA(cudaMemsetAsync(pleaf.p, 0xff, sizeof(int) * (size_t)std::max(n, 1), st));   // -1: no parent
     YRT_CUDA(cudaMemsetAsync(out.nodes, 0, sizeof(float4) * YRT_NODE_STRIDE * ni, st));
 
@@ -342,6 +346,8 @@ static int lbvh_build(int dev, cudaStream_t st, int n, int n_seg, float4* box_lo
     a.rotate_pairs = out.rotate_pairs;
     a.seg_root = out.seg_root->as<int>();
     a.seg_depth = out.seg_depth->as<int>();
+    a.seg_need = out.seg_need->as<int>();
+    a.need = need.as<int>();
     a.leaf_size = leaf_size;
 
     k_seg_init<<<grid_for(n_seg), 256, 0, st>>>(a);
@@ -369,7 +375,11 @@ static int lbvh_build(int dev, cudaStream_t st, int n, int n_seg, float4* box_lo
             k_emit<<<grid_for(n - 1), 256, 0, st>>>(a);
         }
         k_single_root<<<grid_for(n_seg), 256, 0, st>>>(a);
-        if (n > 1) k_depth<<<grid_for(n), 256, 0, st>>>(a);
+        if (n > 1) {
+            k_depth<<<grid_for(n), 256, 0, st>>>(a);
+            YRT_CUDA(cudaMemsetAsync(a.flags, 0, sizeof(int) * ni, st));
+            k_stackneed<<<grid_for(n), 256, 0, st>>>(a);
+        }
     }
     YRT_CUDA(cudaGetLastError());
     // temporaries are freed when this returns: wait for the work that uses them
@@ -466,7 +476,7 @@ int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
     int nb_int = hs.n_prims > 1 ? hs.n_prims - 1 : 0, nt_int = ds.n_active > 1 ? ds.n_active - 1 : 0;
     YRT_TRY(ds.nodes.alloc(sizeof(float4) * YRT_NODE_STRIDE * (size_t)(nb_int + nt_int + 2), device));
     LbvhOut bo;
-    bo.nodes = ds.nodes.as<float4>(); bo.ref_offset = 0; bo.size_bits = size_bits_blas; bo.rotate_rounds = rotate_blas; bo.rotate_pairs = rotate_pairs_blas; bo.seg_root = &ds.blas_seg_root; bo.seg_depth = &ds.blas_seg_depth; bo.order = &blas_order;
+    bo.nodes = ds.nodes.as<float4>(); bo.ref_offset = 0; bo.size_bits = size_bits_blas; bo.rotate_rounds = rotate_blas; bo.rotate_pairs = rotate_pairs_blas; bo.seg_root = &ds.blas_seg_root; bo.seg_depth = &ds.blas_seg_depth; bo.seg_need = &ds.blas_seg_need; bo.order = &blas_order;
     bo.seg_box_lo = &ds.shape_box_lo; bo.seg_box_hi = &ds.shape_box_hi;
     YRT_TRY(lbvh_build(device, st, hs.n_prims, std::max(hs.n_shapes, 1), plo.as<float4>(), phi.as<float4>(), g.prim_shape,
                        g.shape_prim_off, leaf_blas, bo));
@@ -491,7 +501,7 @@ int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
         k_inst_boxes<<<grid_for(na), 256, 0, st>>>(na, ds.active_inst.as<int>(), ds.inst_frame.as<float>(), ds.inst_shape.as<int>(),
                                                  ds.shape_box_lo.as<int>(), ds.shape_box_hi.as<int>(), ilo.as<float4>(), ihi.as<float4>());
     LbvhOut to;
-    to.nodes = ds.nodes.as<float4>() + YRT_NODE_STRIDE * (size_t)nb_int; to.ref_offset = nb_int; to.size_bits = size_bits_tlas; to.rotate_rounds = rotate_tlas; to.rotate_pairs = rotate_pairs_tlas; to.seg_root = &ds.tlas_seg_root; to.seg_depth = &ds.tlas_seg_depth; to.order = &tlas_order;
+    to.nodes = ds.nodes.as<float4>() + YRT_NODE_STRIDE * (size_t)nb_int; to.ref_offset = nb_int; to.size_bits = size_bits_tlas; to.rotate_rounds = rotate_tlas; to.rotate_pairs = rotate_pairs_tlas; to.seg_root = &ds.tlas_seg_root; to.seg_depth = &ds.tlas_seg_depth; to.seg_need = &ds.tlas_seg_need; to.order = &tlas_order;
     to.seg_box_lo = nullptr; to.seg_box_hi = nullptr;
     YRT_TRY(lbvh_build(device, st, na, 1, ilo.as<float4>(), ihi.as<float4>(), tl_seg_of.as<int>(), tl_seg_first.as<int>(), leaf_tlas, to));
     YRT_TRY(ds.inst_recs.alloc(sizeof(float4) * 4 * (size_t)std::max(na, 1), device));
@@ -511,19 +521,22 @@ int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
     cudaEventDestroy(e1);
 
     // depths / root back to the host
-    std::vector<int> bdepth(std::max(hs.n_shapes, 1), 0);
-    int tdepth = 0, troot = YRT_REF_SENTINEL;
+    std::vector<int> bdepth(std::max(hs.n_shapes, 1), 0), bneed(std::max(hs.n_shapes, 1), 0);
+    int tdepth = 0, tneed = 0, troot = YRT_REF_SENTINEL;
     YRT_CUDA(cudaMemcpy(bdepth.data(), ds.blas_seg_depth.p, sizeof(int) * bdepth.size(), cudaMemcpyDeviceToHost));
+    YRT_CUDA(cudaMemcpy(bneed.data(), ds.blas_seg_need.p, sizeof(int) * bneed.size(), cudaMemcpyDeviceToHost));
     YRT_CUDA(cudaMemcpy(&tdepth, ds.tlas_seg_depth.p, sizeof(int), cudaMemcpyDeviceToHost));
+    YRT_CUDA(cudaMemcpy(&tneed, ds.tlas_seg_need.p, sizeof(int), cudaMemcpyDeviceToHost));
     YRT_CUDA(cudaMemcpy(&troot, ds.tlas_seg_root.p, sizeof(int), cudaMemcpyDeviceToHost));
     ds.blas_depth = *std::max_element(bdepth.begin(), bdepth.end());
     ds.tlas_depth = tdepth;
     ds.n_blas_nodes = hs.n_prims > 1 ? hs.n_prims - 1 : 0;
     ds.n_tlas_nodes = na > 1 ? na - 1 : 0;
     if (na > 0 && troot == YRT_REF_SENTINEL) { set_error("internal: TLAS root not found"); return YRT_ERR_CUDA; }
-    // one stack entry per level + sentinel + the "rest of a TLAS leaf" entry
-    if (ds.blas_depth + ds.tlas_depth + 4 > YRT_STACK_CAP) {
-        set_error("LBVH too deep for the traversal stack (tlas %d + blas %d levels, capacity %d)", ds.tlas_depth, ds.blas_depth, YRT_STACK_CAP);
+    // entries below the TLAS root + entries below the deepest BLAS root + guard + sentinel + the "rest of a TLAS leaf" entry
+    ds.stack_need = tneed + *std::max_element(bneed.begin(), bneed.end()) + 3;
+    if (ds.stack_need > YRT_STACK_CAP) {
+        set_error("traversal tree too deep for the stack (%d entries needed: tlas %d + blas %d levels, capacity %d)", ds.stack_need, ds.tlas_depth, ds.blas_depth, YRT_STACK_CAP);
         return YRT_ERR_UNSUPPORTED;
     }
 

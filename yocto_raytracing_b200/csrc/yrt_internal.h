@@ -77,6 +77,11 @@ struct Workspace {
     size_t cap_slots = 0;
     int cap_lights = 0;
     int cap_depth = 0;
+    unsigned* h_counts = nullptr;        // pinned: per-wave active-sample counts as they arrive (reflective scenes)
+    cudaEvent_t ev_counts[66] = {};      // one per wave (YRT_MAX_WAVES + 2)
+    ~Workspace() {
+        if (h_counts) { cudaFreeHost(h_counts); for (auto e : ev_counts) if (e) cudaEventDestroy(e); }
+    }
 };
 
 struct DevScene {
@@ -87,9 +92,9 @@ struct DevScene {
     DevBuf inst_frame, inst_shape, inst_mat, active_inst, prim_rank_in, inst_rank_in, prim_rank, inst_rank;
     // build products
     DevBuf nodes, prim_recs, prim_attrs, inst_recs, mat_recs, light_recs, tex, tex_info, lut;
-    DevBuf blas_seg_root, blas_seg_depth, tlas_seg_root, tlas_seg_depth, shape_box_lo, shape_box_hi;
+    DevBuf blas_seg_root, blas_seg_depth, blas_seg_need, tlas_seg_root, tlas_seg_depth, tlas_seg_need, shape_box_lo, shape_box_hi;
     int n_prims = 0, n_active = 0, n_blas_nodes = 0, n_tlas_nodes = 0;
-    int blas_depth = 0, tlas_depth = 0;
+    int blas_depth = 0, tlas_depth = 0, stack_need = 0;
     float build_us = 0.f;
     cudaStream_t stream = nullptr;   // owned
     Workspace ws;
@@ -99,8 +104,7 @@ struct DevScene {
     int sm_count = 148;
     bool has_reflective = false;
     int grid_closest_primary = 0, grid_closest_queue = 0, grid_any = 0;   // persistent grids (SMs x resident CTAs)
-    int grid_shadow_shade = 0;
-    int grid_packet = -1;            // traversal mode the cached grids were computed for
+    DevBuf dctr;                     // per-ray work counters of the traversal kernels (-DYRT_COUNTERS=1 builds)
     PhaseTimer* timer = nullptr;     // owned (yrt_render.cu)
 };
 
@@ -137,6 +141,10 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
                        bool sync_for_stats);
 // waits for the frame issued by render_rows_device(…, stats != null, sync_for_stats = false) and fills stats
 int collect_stats_device(DevScene& ds, const RenderParams& rp, yrt_stats* stats);
+// allocates the render workspace of a (width x height, samples) frame now instead of inside the first render call
+int presize_workspace_device(DevScene& ds, int width, int height, int samples);
+// per-ray work counters (-DYRT_COUNTERS=1 builds): 3 kernel classes x 8 words, read and reset
+int read_counters_device(DevScene& ds, uint64_t out[24]);
 int stats_begin_device(DevScene& ds);
 int stats_end_device(DevScene& ds, yrt_stats* stats);
 int trace_primary_device(DevScene& ds, const RenderParams& rp, int32_t* h_ids, float* h_dist, float* h_uv);

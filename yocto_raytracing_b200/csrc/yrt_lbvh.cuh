@@ -1,5 +1,5 @@
 // yrt_lbvh.cuh — per-item functions of the GPU LBVH build (Morton keys -> radix sort -> Karras
-// topology -> bottom-up refit -> 64-byte two-child-box nodes with small-subtree leaves).
+// topology -> bottom-up refit -> rotations -> traversal nodes (binary or collapsed 4-wide) with small-subtree leaves).
 //
 // Replaces build_bvh / make_node / split_prims (src/scene.cpp:508-658): the reference builds
 // top-down midpoint-split trees serially; topology is free for parity (SURVEY finding 4), the
@@ -144,6 +144,8 @@ struct LbvhArrays {
     float4* nodes;         // [YRT_NODE_STRIDE*(n-1)]
     int* seg_root;         // [n_seg] root ref per segment
     int* seg_depth;        // [n_seg] max depth (levels of internal nodes) per segment
+    int* need;             // [n-1] traversal stack entries the subtree below a node can occupy (stackneed_item)
+    int* seg_need;         // [n_seg] ... below the segment's root
     int leaf_size;
     int ref_offset;        // added to every internal-node reference (position of this tree set in the shared node array)
     int size_bits;         // 0..3: top bits of the Morton part hold a size class (see morton_item)
@@ -159,6 +161,7 @@ YRT_HD void seg_bounds_init_item(const LbvhArrays& a, int s) {
     }
     a.seg_root[s] = YRT_REF_SENTINEL;
     a.seg_depth[s] = 0;
+    a.seg_need[s] = 0;
 }
 
 YRT_HD vec3 box_centroid(const float4& lo, const float4& hi) {   // (bbox.min + bbox.max) / 2, scene.cpp:531
@@ -489,17 +492,53 @@ YRT_HD int child_ref_(const LbvhArrays& a, int c) {
     return c + a.ref_offset;
 }
 
-// emit the 64-byte traversal node of internal node i and, if i is exactly a segment, its root ref
+// true if binary child reference c becomes a leaf of the traversal tree (a single item or a subtree of <= leaf_size items)
+YRT_HD bool is_leaf_child_(const LbvhArrays& a, int c) {
+    return c < 0 || a.range_last[c] - a.range_first[c] + 1 <= a.leaf_size;
+}
+
+// Emit the traversal node of binary internal node i and, if i is exactly a segment, its root ref.
+// YRT_WIDE == 4: the node's slots start as the two binary children; while a slot is free, the internal (non-leaf) slot
+// with the largest surface area is replaced by its own two children (the usual greedy binary -> wide collapse: the box
+// most likely to be entered is the one opened).  Every binary internal node gets a record at its own index, so segment
+// roots and child references need no renumbering; only the records reachable from a root through these wide links are
+// ever read (about one in three), and each is exactly one 128-byte line.
 YRT_HD void emit_item(const LbvhArrays& a, int i) {
-    int c0 = a.left[i], c1 = a.right[i];
-    float4 l0, h0, l1, h1;
-    child_box_(a, c0, l0, h0);
-    child_box_(a, c1, l1, h1);
-    float4* n = a.nodes + YRT_NODE_STRIDE * (size_t)i;
-    nodebox b0, b1;
-    box_center_half(l0.x, h0.x, b0.cx, b0.hx); box_center_half(l0.y, h0.y, b0.cy, b0.hy); box_center_half(l0.z, h0.z, b0.cz, b0.hz);
-    box_center_half(l1.x, h1.x, b1.cx, b1.hx); box_center_half(l1.y, h1.y, b1.cy, b1.hy); box_center_half(l1.z, h1.z, b1.cz, b1.hz);
-    node_pack(n, b0, b1, child_ref_(a, c0), child_ref_(a, c1));
+    int c[YRT_WIDE];
+    float4 lo[YRT_WIDE], hi[YRT_WIDE];
+    int nb = 2;
+    c[0] = a.left[i]; c[1] = a.right[i];
+    child_box_(a, c[0], lo[0], hi[0]);
+    child_box_(a, c[1], lo[1], hi[1]);
+#if YRT_WIDE == 4
+    while (nb < YRT_WIDE) {
+        int best = -1;
+        float best_area = -1.f;
+        for (int k = 0; k < nb; k++) {
+            if (is_leaf_child_(a, c[k])) continue;
+            float ar = half_area_(lo[k], hi[k]);
+            if (ar > best_area) { best_area = ar; best = k; }
+        }
+        if (best < 0) break;
+        // the opened slot keeps its position for its left child; the right child goes right behind it (siblings stay
+        // neighbours, so that pairs (0,1) / (2,3) of a fully opened node are the two binary subtrees)
+        int l = a.left[c[best]], r = a.right[c[best]];
+        for (int k = nb; k > best + 1; k--) { c[k] = c[k - 1]; lo[k] = lo[k - 1]; hi[k] = hi[k - 1]; }
+        c[best] = l; c[best + 1] = r;
+        child_box_(a, l, lo[best], hi[best]);
+        child_box_(a, r, lo[best + 1], hi[best + 1]);
+        nb++;
+    }
+#endif
+    nodebox bx[YRT_WIDE];
+    int ref[YRT_WIDE];
+    for (int k = 0; k < nb; k++) {
+        box_center_half(lo[k].x, hi[k].x, bx[k].cx, bx[k].hx);
+        box_center_half(lo[k].y, hi[k].y, bx[k].cy, bx[k].hy);
+        box_center_half(lo[k].z, hi[k].z, bx[k].cz, bx[k].hz);
+        ref[k] = child_ref_(a, c[k]);
+    }
+    node_pack(a.nodes + YRT_NODE_STRIDE * (size_t)i, bx, ref, nb);
     int first = a.range_first[i], last = a.range_last[i];
     int s = a.seg_of[a.order[first]];
     if (s == a.seg_of[a.order[last]] && first == a.seg_first[s] && last == a.seg_first[s + 1] - 1) {
@@ -526,6 +565,36 @@ YRT_HD void depth_item(const LbvhArrays& a, int leaf) {
         p = a.parent_int[p];
     }
     YRT_ATOMIC_MAX(&a.seg_depth[s], d);
+}
+
+// Traversal-stack entries the subtree below node record i can occupy at once: a visit leaves at most (children - 1)
+// siblings on the stack while it descends into one child, so need(i) = children(i) - 1 + max over internal children.
+// Bottom-up with the arrival counters of the refit (flags zeroed before): a node is handled by the second thread to
+// reach it, when every record below it has its value.  Runs after emit; reads the emitted records.
+YRT_HD void stackneed_item(const LbvhArrays& a, int leaf) {
+    int p = a.parent_leaf[leaf];
+    while (p >= 0) {
+        YRT_FENCE();
+        int old = YRT_ATOMIC_ADD(&a.flags[p], 1);
+        if (old == 0) return;
+        YRT_FENCE();
+        const float4* n = a.nodes + YRT_NODE_STRIDE * (size_t)p;
+        int nb = 0, deepest = 0;
+        for (int k = 0; k < YRT_WIDE; k++) {
+            nodebox b;
+            int ref;
+            node_child(n, k, b, ref);
+            if (!(b.hx >= 0.f)) continue;    // empty slot
+            nb++;
+            if (ref >= 0) { int c = YRT_LDCG(&a.need[ref - a.ref_offset]); if (c > deepest) deepest = c; }
+        }
+        int need = nb - 1 + deepest;
+        a.need[p] = need;
+        int first = a.range_first[p], last = a.range_last[p];
+        int s = a.seg_of[a.order[first]];
+        if (s == a.seg_of[a.order[last]] && first == a.seg_first[s] && last == a.seg_first[s + 1] - 1) a.seg_need[s] = need;
+        p = YRT_LDCG(&a.parent_int[p]);
+    }
 }
 
 }  // namespace yrt

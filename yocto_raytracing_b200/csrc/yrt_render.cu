@@ -10,11 +10,10 @@
 //     k_shade                 Blinn-Phong / hair shading in light order; reflective hits push
 //                             {c, kr, la} on a per-slot stack and enqueue the mirror ray (compacted
 //                             queue); finished paths unwind the stack and write their radiance
-//     k_trace_closest<queue>  next wave's rays
+//     k_trace_closest<queue>  next wave's rays; the wave's ray count stays in device memory (the host never waits for it)
 //   k_resolve                 ordered per-pixel sum over (jj,ii), divide by N*N, alpha = 1; in a multi-GPU frame it stores
 //                             straight into rank 0's frame (peer memory) — the gather is fused into it
-// A rank's share of a frame runs as two such pipelines on two streams (kernel tails overlap).  Measured alternatives
-// kept behind switches: YRT_PACKET (warp-cooperative traversal), YRT_FUSE_SHADE (k_shadow_shade).
+// A rank's share of a frame runs as two such pipelines on two streams (kernel tails overlap).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -23,7 +22,6 @@
 #include "yrt_internal.h"
 #include "yrt_shade.cuh"
 #include "yrt_trace.cuh"
-#include "yrt_packet.cuh"
 #include "yrt_work.cuh"
 
 namespace yrt {
@@ -31,21 +29,18 @@ namespace yrt {
 #ifndef YRT_DEFAULT_STREAMS
 #define YRT_DEFAULT_STREAMS 2   /* pipelines per frame (see render_rows_device) */
 #endif
-#ifndef YRT_TILE_DEFAULT
-#define YRT_TILE_DEFAULT 0   /* 1: SM-affine tiles (yrt_work.cuh), 0: every warp takes the next 32 slots; YRT_TILE overrides at run time */
-#endif
-#ifndef YRT_LIGHT_PIPE
-#define YRT_LIGHT_PIPE 0   /* shadow kernel: lanes move on to the next light without waiting for the warp (experiment, profiles/r1_experiments.md) */
+#ifndef YRT_COUNTERS
+#define YRT_COUNTERS 0          /* 1: the traversal kernels count their own per-ray work (node visits, box / element tests, instance entries) — a separate build of the library, never the timed one */
 #endif
 #define TRACE_THREADS 128
-// dynamic shared memory of every kernel that runs a Tracer (yrt_trace.cuh: the world-space ray of each lane)
-#define TRACE_DSMEM (YRT_WORLD_SMEM ? YRT_WORLD_WORDS * TRACE_THREADS * sizeof(float) : 0)
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 8   /* resident CTAs per SM the compiler must allow (64 registers per thread) */
 #endif
 #ifndef TRACE_MIN_BLOCKS_ANY
-#define TRACE_MIN_BLOCKS_ANY 9   /* the shadow kernel carries no hit record: 56 registers, 9 CTAs/SM measured 1.4 % faster than 8 */
+#define TRACE_MIN_BLOCKS_ANY 8
 #endif
+#define STACK_INTS_CLOSEST (YRT_STACK_CAP * (YRT_POP_CULL ? 2 : 1))
+#define STACK_INTS_ANY YRT_STACK_CAP
 
 struct BatchParams {
     camera_k cam;
@@ -67,182 +62,129 @@ __device__ __forceinline__ void slot_to_sample(const BatchParams& bp, unsigned s
     ii = (int)(s - (unsigned)jj * (unsigned)bp.samples);
 }
 
-// warp-granular dynamic work fetch of a persistent kernel: 32 consecutive items per warp.
-// (Measured alternative, profiles/r1_experiments.md: handing a finished lane a new ray while the rest of the
-// warp keeps traversing — per-warp item pool + warp vote — LOSES here, 19.4 -> 20.8..31.7 ms/frame as the refill
-// threshold goes from 32 to 1 idle lanes: the 32 rays of a warp are neighbouring samples that walk the tree
-// together, and refilled lanes are out of phase with them, so node and leaf code stop overlapping.)
-__device__ __forceinline__ unsigned warp_fetch(unsigned* counter, int lane) {
+// next 32 work items of the warp: false = the launch has no work left; `alive` = this lane has an item
+__device__ __forceinline__ bool warp_next(const WorkDist& wd, unsigned n_items, int lane, unsigned& item, bool& alive) {
     unsigned base = 0;
-    if (lane == 0) base = atomicAdd(counter, 32u);
-    return __shfl_sync(0xffffffffu, base, 0);
-}
-
-__device__ __forceinline__ unsigned sm_id() {
-    unsigned r;
-    asm("mov.u32 %0, %%smid;" : "=r"(r));
-    return r;
-}
-
-// next 32 work items of the warp (yrt_work.cuh): false = the launch has no work left; `alive` = this lane has an item
-__device__ __forceinline__ bool warp_next(const WorkDist& wd, int lane, unsigned& item, bool& alive) {
-    if (wd.mode == 0) {
-        unsigned base = warp_fetch(wd.counter, lane);
-        if (base >= wd.n_items) return false;
-        item = base + lane;
-        alive = item < wd.n_items;
-        return true;
-    }
-    unsigned chunk = 0, k = 0;
-    int ok = 0;
-    if (lane == 0) {
-        DeviceAtomics at;
-        ok = fetch_task(at, wd, sm_id(), chunk, k) ? 1 : 0;
-    }
-    ok = __shfl_sync(0xffffffffu, ok, 0);
-    if (!ok) return false;
-    chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    k = __shfl_sync(0xffffffffu, k, 0);
-    item = 0;
-    alive = task_item(wd, chunk, k, lane, item);
+    if (lane == 0) base = atomicAdd(wd.counter, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n_items) return false;
+    item = base + lane;
+    alive = item < n_items;
     return true;
 }
+__device__ __forceinline__ unsigned item_count(const WorkDist& wd) { return wd.n_items_dev ? min(*wd.n_items_dev, wd.n_items) : wd.n_items; }
+
+// ---- per-ray work counters of the traversal kernels (-DYRT_COUNTERS=1 builds only) --------------------------------
+// dctr = YRT_DCTR_WORDS words per kernel class (0 primary closest, 1 queue closest, 2 any): rays, node visits, box tests,
+// box tests in the instance tree, element tests, instance entries, warp-level node-loop trips x 32
+#define YRT_DCTR_WORDS 8
+#if YRT_COUNTERS
+#define YRT_CTR_DECL TraceCounters tc_ = {0, 0, 0, 0, 0, 0, 0, 0}; unsigned long long rays_ = 0
+#define YRT_CTR_PTR (&tc_)
+__device__ __forceinline__ void flush_counters(unsigned long long* dctr, const TraceCounters& tc, unsigned long long rays) {
+    unsigned long long v[6] = {rays, (unsigned long long)tc.node_visits, (unsigned long long)tc.box_tests, (unsigned long long)tc.tlas_box_tests,
+                               (unsigned long long)tc.prim_tests, (unsigned long long)tc.inst_entries};
+    for (int k = 0; k < 6; k++) {
+        unsigned long long x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(dctr + k, x);
+    }
+}
+#else
+#define YRT_CTR_DECL
+#define YRT_CTR_PTR ((TraceCounters*)nullptr)
+#endif
 
 // ---- closest hit --------------------------------------------------------------------------
 // PRIMARY: slot = work index, ray from the camera. Otherwise slot = act[idx] (or idx) and the ray
 // comes from ray_o/ray_d (o.xyz|tmin, d.xyz|tmax).
-// PACKET: the warp's 32 rays walk one tree path (yrt_packet.cuh) — used for the camera rays and their shadow
-// rays, which are neighbouring samples; reflection waves and the generic query entry points trace per lane.
-template <bool PRIMARY, bool PACKET>
+template <bool PRIMARY>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_closest(SceneView sv, BatchParams bp, const int* __restrict__ act,
                                                                  const float4* __restrict__ ray_o,
                                                                  const float4* __restrict__ ray_d, float4* __restrict__ hit_out,
-                                                                 float4* __restrict__ P_out, WorkDist wd) {
+                                                                 float4* __restrict__ P_out, WorkDist wd, unsigned long long* dctr) {
     const int lane = threadIdx.x & 31;
-    __shared__ int wstacks[PACKET ? TRACE_THREADS / 32 : 1][PACKET ? YRT_WSTACK : 1];
-    int stack[PACKET ? 1 : YRT_STACK_CAP];
+    const unsigned n_items = item_count(wd);
+    int stack[STACK_INTS_CLOSEST];
+    YRT_CTR_DECL;
     for (;;) {
         unsigned idx = 0;
         bool alive = false;
-        if (!warp_next(wd, lane, idx, alive)) break;
-        unsigned slot = 0;
+        if (!warp_next(wd, n_items, lane, idx, alive)) break;
+        if (!alive) continue;
+        unsigned slot;
         ray3 ray;
-        ray.o = mk3(0.f, 0.f, 0.f); ray.d = mk3(0.f, 0.f, 1.f); ray.tmin = 0.f; ray.tmax = 0.f;
-        if (alive) {
-            if (PRIMARY) {
-                slot = idx;
-                int i, j, ii, jj;
-                slot_to_sample(bp, slot, i, j, ii, jj);
-                float u, v;
-                sample_uv(i, j, ii, jj, bp.samples, bp.width, bp.height, u, v);
-                ray = eval_camera(bp.cam, u, v);
-            } else {
-                slot = act ? (unsigned)act[idx] : idx;
-                float4 o = ray_o[slot], d = ray_d[slot];
-                ray.o = xyz(o); ray.d = xyz(d); ray.tmin = o.w; ray.tmax = d.w;
-            }
+        if (PRIMARY) {
+            slot = idx;
+            int i, j, ii, jj;
+            slot_to_sample(bp, slot, i, j, ii, jj);
+            float u, v;
+            sample_uv(i, j, ii, jj, bp.samples, bp.width, bp.height, u, v);
+            ray = eval_camera(bp.cam, u, v);
+        } else {
+            slot = act ? (unsigned)act[idx] : idx;
+            float4 o = ray_o[slot], d = ray_d[slot];
+            ray.o = xyz(o); ray.d = xyz(d); ray.tmin = o.w; ray.tmax = d.w;
         }
         HitRec h;
-        if (PACKET) {
-            bool found;
-            trace_packet<false>(sv, ray, alive, h, found, wstacks[threadIdx.x >> 5], lane);
-        } else if (alive) {
-            trace_ray<false>(sv, ray, h, stack, nullptr);
+        trace_ray<false>(sv, ray, h, stack, YRT_CTR_PTR);
+#if YRT_COUNTERS
+        rays_++;
+#endif
+        float4 P = mk4(0.f, 0.f, 0.f, h.dist);
+        if (h.si >= 0) {
+            int kind;
+            vec3 p = eval_hit_pos(sv, h.si, h.prim, h.w1, h.w2, kind);
+            P.x = p.x; P.y = p.y; P.z = p.z;
         }
-        if (alive) {
-            float4 P = mk4(0.f, 0.f, 0.f, h.dist);
-            if (h.si >= 0) {
-                int kind;
-                vec3 p = eval_hit_pos(sv, h.si, h.prim, h.w1, h.w2, kind);
-                P.x = p.x; P.y = p.y; P.z = p.z;
-            }
-            hit_out[slot] = mk4(int_as_float(h.si), int_as_float(h.prim), h.w1, h.w2);
-            P_out[slot] = P;
-        }
+        hit_out[slot] = mk4(int_as_float(h.si), int_as_float(h.prim), h.w1, h.w2);
+        P_out[slot] = P;
     }
+#if YRT_COUNTERS
+    if (dctr) flush_counters(dctr, tc_, rays_);
+#else
+    (void)dctr;
+#endif
 }
 
 // ---- any hit: shadow rays ------------------------------------------------------------------------
 // One work item per hit; the lane walks the lights in order, so the 32 lanes of a warp (neighbouring
 // samples) trace towards the SAME light at the same time, and the hit record / position are read once
 // per hit instead of once per (hit, light).
-template <bool PACKET>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS_ANY) k_trace_any_lights(SceneView sv, size_t cap_slots, const int* __restrict__ act,
                                                                     const float4* __restrict__ hit, const float4* __restrict__ P,
-                                                                    uint8_t* __restrict__ vis, WorkDist wd) {
+                                                                    uint8_t* __restrict__ vis, WorkDist wd, unsigned long long* dctr) {
     const int lane = threadIdx.x & 31;
-    __shared__ int wstacks[PACKET ? TRACE_THREADS / 32 : 1][PACKET ? YRT_WSTACK : 1];
-    int stack[PACKET ? 1 : YRT_STACK_CAP];
+    const unsigned n_items = item_count(wd);
+    int stack[STACK_INTS_ANY];
+    YRT_CTR_DECL;
     for (;;) {
         unsigned a = 0;
         bool alive = false;
-        if (!warp_next(wd, lane, a, alive)) break;
-        unsigned slot = 0;
-        vec3 p = mk3(0.f, 0.f, 0.f);
-        if (alive) {
-            slot = act ? (unsigned)act[a] : a;
-            float4 h = hit[slot];
-            alive = float_as_int(h.x) >= 0;   // a miss casts no shadow rays: shade() returns before the light loop (raytrace.cpp:93)
-            if (alive) p = xyz(P[slot]);
-        }
-        if (!PACKET && !alive) continue;
-        if (PACKET && __ballot_sync(0xffffffffu, alive) == 0u) continue;
-#if YRT_LIGHT_PIPE
-        if (!PACKET) {
-            // experiment: a lane whose ray towards light k is finished starts on light k+1 at once instead of waiting for the
-            // rest of the warp (the warp then runs max-over-lanes of the SUM of the lights' visits, not the sum of the maxima)
-            int k = 0;
-            Tracer<true, false> t;
-            t.cur = YRT_REF_DONE;
-            bool need_ray = true;
-            for (;;) {
-                if (need_ray) {
-                    bool started = false;
-                    while (k < sv.n_lights) {
-                        vec3 l, ke;
-                        float r;
-                        light_vector(sv, k, p, l, r, ke);
-                        ray3 sr = shadow_ray(p, l, r);
-                        float ax = fabsf(sr.d.x), ay = fabsf(sr.d.y), az = fabsf(sr.d.z);
-                        float m = fminf(fminf(ax, ay), az), big = fmaxf(fmaxf(ax, ay), az);
-                        if (!(m >= 1.0f / YRT_EXACT_SLAB_INVD && big <= 1.0e30f)) {   // rare: the reference's slab formula, traced on the spot
-                            HitRec hr;
-                            bool occ = trace_ray_impl<true, true>(sv, sr, hr, stack, nullptr);
-                            vis[(size_t)k * cap_slots + slot] = occ ? 0 : 1;
-                            k++;
-                            continue;
-                        }
-                        t.begin(sv, sr, stack);
-                        started = true;
-                        break;
-                    }
-                    if (!started) break;
-                    need_ray = false;
-                }
-                t.nodes(sv, stack, nullptr);
-                if (t.done()) {
-                    vis[(size_t)k * cap_slots + slot] = t.found ? 0 : 1;
-                    k++;
-                    need_ray = true;
-                    continue;
-                }
-                t.leaf(sv, stack, nullptr);
-            }
-            continue;
-        }
-#endif
+        if (!warp_next(wd, n_items, lane, a, alive)) break;
+        if (!alive) continue;
+        unsigned slot = act ? (unsigned)act[a] : a;
+        float4 h = hit[slot];
+        if (float_as_int(h.x) < 0) continue;   // a miss casts no shadow rays: shade() returns before the light loop (raytrace.cpp:93)
+        vec3 p = xyz(P[slot]);
         for (int k = 0; k < sv.n_lights; k++) {
             vec3 l, ke;
             float r;
             light_vector(sv, k, p, l, r, ke);
             ray3 sr = shadow_ray(p, l, r);
             HitRec hr;
-            bool occ;
-            if (PACKET) trace_packet<true>(sv, sr, alive, hr, occ, wstacks[threadIdx.x >> 5], lane);
-            else occ = trace_ray<true>(sv, sr, hr, stack, nullptr);
-            if (alive) vis[(size_t)k * cap_slots + slot] = occ ? 0 : 1;
+            bool occ = trace_ray<true>(sv, sr, hr, stack, YRT_CTR_PTR);
+#if YRT_COUNTERS
+            rays_++;
+#endif
+            vis[(size_t)k * cap_slots + slot] = occ ? 0 : 1;
         }
     }
+#if YRT_COUNTERS
+    if (dctr) flush_counters(dctr, tc_, rays_);
+#else
+    (void)dctr;
+#endif
 }
 
 // any hit on explicit rays (intersect_any, scene.cpp:489)
@@ -250,11 +192,12 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_any_rays(SceneView sv, 
                                                                   const float4* __restrict__ ray_d, uint8_t* __restrict__ occ_out,
                                                                   WorkDist wd) {
     const int lane = threadIdx.x & 31;
-    int stack[YRT_STACK_CAP];
+    const unsigned n_items = item_count(wd);
+    int stack[STACK_INTS_ANY];
     for (;;) {
         unsigned idx = 0;
         bool alive = false;
-        if (!warp_next(wd, lane, idx, alive)) break;
+        if (!warp_next(wd, n_items, lane, idx, alive)) break;
         if (!alive) continue;
         float4 o = ray_o[idx], d = ray_d[idx];
         ray3 ray;
@@ -265,7 +208,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_any_rays(SceneView sv, 
 }
 
 // ---- shade ------------------------------------------------------------------------------------
-struct FrameCounters { unsigned long long hits, reflections, misses, pad; };
+struct FrameCounters { unsigned long long hits, reflections, misses, truncated, max_depth; };   // truncated: mirror bounces dropped at the depth cap
 
 struct ShadeBuffers {
     const float4* hit;
@@ -279,7 +222,7 @@ struct ShadeBuffers {
 // path, or pushes {c, kr, la} and the mirror ray of a path that goes on.  Returns spawn; is_hit says whether the ray hit.
 template <class VisFn>
 __device__ __forceinline__ bool shade_slot(const SceneView& sv, const BatchParams& bp, const ShadeBuffers& sb, int depth, int max_depth,
-                                           unsigned slot, const float4& h, const float* lut, VisFn vis, bool& is_hit) {
+                                           unsigned slot, const float4& h, const float* lut, VisFn vis, bool& is_hit, bool& truncated) {
     int si = float_as_int(h.x);
     bool spawn = false;
     vec3 value = mk3(0.f, 0.f, 0.f);          // miss: {0,0,0,1}, raytrace.cpp:93
@@ -289,7 +232,14 @@ __device__ __forceinline__ bool shade_slot(const SceneView& sv, const BatchParam
         vec3 ro = depth == 0 ? bp.cam.frame.o : xyz(sb.ray_o[slot]);
         vec3 c, kr, la;
         ray3 rr;
-        spawn = shade_hit(sv, si, float_as_int(h.y), h.z, h.w, ro, bp.amb, lut, vis, depth + 1 < max_depth, value, c, kr, la, rr);
+        spawn = shade_hit(sv, si, float_as_int(h.y), h.z, h.w, ro, bp.amb, lut, vis, true, value, c, kr, la, rr);
+        if (spawn && depth + 1 >= max_depth) {
+            // depth cap (the reference recurses without a bound, raytrace.cpp:190-204): the mirror term is dropped, the path
+            // closes with c + la, and the frame statistics say how often that happened
+            spawn = false;
+            truncated = true;
+            value = c + la;
+        }
         if (spawn) {
             float4* f = sb.pstack + ((size_t)depth * cap + slot) * 3;
             f[0] = mk4(c.x, c.y, c.z, 0.f);
@@ -311,8 +261,9 @@ __device__ __forceinline__ bool shade_slot(const SceneView& sv, const BatchParam
 }
 
 // compacted queue of the next wave + frame counters (warp-aggregated; every lane of the warp must call it)
-__device__ __forceinline__ void shade_epilogue(const ShadeBuffers& sb, bool valid, bool is_hit, bool spawn, unsigned slot, int lane) {
+__device__ __forceinline__ void shade_epilogue(const ShadeBuffers& sb, int depth, bool valid, bool is_hit, bool spawn, bool truncated, unsigned slot, int lane) {
     unsigned m_spawn = __ballot_sync(0xffffffffu, spawn);
+    unsigned m_trunc = __ballot_sync(0xffffffffu, truncated);
     unsigned m_hit = __ballot_sync(0xffffffffu, is_hit);
     unsigned m_valid = __ballot_sync(0xffffffffu, valid);
     if (m_spawn) {
@@ -326,65 +277,34 @@ __device__ __forceinline__ void shade_epilogue(const ShadeBuffers& sb, bool vali
         if (m_spawn) atomicAdd(&sb.fc->reflections, (unsigned long long)__popc(m_spawn));
         unsigned miss = m_valid & ~m_hit;
         if (miss) atomicAdd(&sb.fc->misses, (unsigned long long)__popc(miss));
+        if (m_trunc) atomicAdd(&sb.fc->truncated, (unsigned long long)__popc(m_trunc));
+        if (depth > 0) atomicMax(&sb.fc->max_depth, (unsigned long long)(depth + 1));
     }
 }
 
-// unfused shade: visibility bytes written by k_trace_any_lights (used when a scene has more than 32 lights)
+// one thread per active sample; n_act_dev (if not null) holds the number of active samples of this wave
 __global__ void __launch_bounds__(256, 4) k_shade(SceneView sv, BatchParams bp, ShadeBuffers sb, int depth, int max_depth,
-                                                  const int* __restrict__ act, unsigned n_act, const uint8_t* __restrict__ vis) {
+                                                  const int* __restrict__ act, unsigned n_act, const unsigned* __restrict__ n_act_dev,
+                                                  const uint8_t* __restrict__ vis) {
+    if (n_act_dev) {
+        n_act = min(n_act, *n_act_dev);
+        if (blockIdx.x * blockDim.x >= n_act) return;
+    }
     __shared__ float lut[256];
     lut[threadIdx.x] = sv.srgb_lut[threadIdx.x];
     __syncthreads();
     unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = a < n_act;
-    bool is_hit = false, spawn = false;
+    bool is_hit = false, spawn = false, truncated = false;
     unsigned slot = 0;
     if (valid) {
         slot = act ? (unsigned)act[a] : a;
         float4 h = sb.hit[slot];
         const uint8_t* vrow = vis + slot;
         size_t cap = bp.cap_slots;
-        spawn = shade_slot(sv, bp, sb, depth, max_depth, slot, h, lut, [&](int k) { return vrow[(size_t)k * cap] != 0; }, is_hit);
+        spawn = shade_slot(sv, bp, sb, depth, max_depth, slot, h, lut, [&](int k) { return vrow[(size_t)k * cap] != 0; }, is_hit, truncated);
     }
-    shade_epilogue(sb, valid, is_hit, spawn, slot, threadIdx.x & 31);
-}
-
-// fused shadow + shade (persistent): the lane that traces the shadow rays of a hit keeps their visibility in a
-// register mask and shades the hit right away — no visibility buffer, the hit record is read once, and one
-// launch (and one kernel tail) less per wave.  Up to 32 lights.
-__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_shadow_shade(SceneView sv, BatchParams bp, ShadeBuffers sb, int depth,
-                                                                                 int max_depth, const int* __restrict__ act,
-                                                                                 const float4* __restrict__ P, WorkDist wd) {
-    __shared__ float lut[256];
-    for (int i = threadIdx.x; i < 256; i += TRACE_THREADS) lut[i] = sv.srgb_lut[i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    int stack[YRT_STACK_CAP];
-    for (;;) {
-        unsigned a = 0;
-        bool valid = false;
-        if (!warp_next(wd, lane, a, valid)) break;
-        bool is_hit = false, spawn = false;
-        unsigned slot = 0;
-        if (valid) {
-            slot = act ? (unsigned)act[a] : a;
-            float4 h = sb.hit[slot];
-            unsigned vmask = 0u;
-            if (float_as_int(h.x) >= 0) {   // a miss casts no shadow rays: shade() returns before the light loop (raytrace.cpp:93)
-                vec3 p = xyz(P[slot]);
-                for (int k = 0; k < sv.n_lights; k++) {
-                    vec3 l, ke;
-                    float r;
-                    light_vector(sv, k, p, l, r, ke);
-                    ray3 sr = shadow_ray(p, l, r);
-                    HitRec hr;
-                    if (!trace_ray<true>(sv, sr, hr, stack, nullptr)) vmask |= 1u << k;
-                }
-            }
-            spawn = shade_slot(sv, bp, sb, depth, max_depth, slot, h, lut, [&](int k) { return ((vmask >> k) & 1u) != 0u; }, is_hit);
-        }
-        shade_epilogue(sb, valid, is_hit, spawn, slot, lane);
-    }
+    shade_epilogue(sb, depth, valid, is_hit, spawn, truncated, slot, threadIdx.x & 31);
 }
 
 // scatter != 0: `out` is the FULL frame (possibly another GPU's memory mapped over NVLink) and every pixel goes to
@@ -484,7 +404,6 @@ struct PhaseTimer {
     int64_t primary = 0;          // primary rays of those frames
     cudaStream_t st = nullptr;      // stream the next span is recorded on
     cudaStream_t main = nullptr;    // the frame's stream (what collect waits for)
-    int max_depth_seen = 0;
     cudaEvent_t get() {
         if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
         cudaEvent_t e; cudaEventCreate(&e); return e;
@@ -507,6 +426,11 @@ struct PhaseTimer {
 };
 enum { CAT_CLOSEST = 0, CAT_ANY = 1, CAT_SHADE = 2, CAT_OTHER = 3, CAT_FRAME = 4 };
 
+static int batch_rows_for(const RenderParams& rp, int n_lights, int own_rows, bool reflective);
+#define YRT_MAX_WAVES 64                                   /* upper limit of the reflection depth cap (YRT_MAX_DEPTH) */
+#define STATS_WAVE_COUNTS_OFFSET 64                          /* bytes: FrameCounters, then one active-sample count per wave */
+#define STATS_BYTES (STATS_WAVE_COUNTS_OFFSET + sizeof(unsigned) * (YRT_MAX_WAVES + 2))
+
 static int ensure_workspace(DevScene& ds, Workspace& w, size_t slots, int n_lights, int depth_cap, bool reflective) {
     int dev = ds.device;
     if (slots > w.cap_slots || n_lights > w.cap_lights || (reflective ? depth_cap : 0) > w.cap_depth) {
@@ -526,141 +450,117 @@ static int ensure_workspace(DevScene& ds, Workspace& w, size_t slots, int n_ligh
         }
         w.cap_slots = cs; w.cap_lights = cl; w.cap_depth = cd;
     }
-    YRT_TRY(w.counters.alloc(sizeof(unsigned) * YRT_WORK_BLOCK_WORDS * YRT_WORK_BLOCKS, dev));
-    YRT_TRY(w.stats.alloc(sizeof(FrameCounters) + 64, dev));   // counters + the next-wave count
+    YRT_TRY(w.counters.alloc(sizeof(unsigned) * YRT_WORK_BLOCKS, dev));
+    YRT_TRY(w.stats.alloc(STATS_BYTES, dev));
+    if (reflective && !w.h_counts) {
+        YRT_CUDA(cudaHostAlloc((void**)&w.h_counts, sizeof(unsigned) * (YRT_MAX_WAVES + 2), cudaHostAllocDefault));
+        for (int k = 0; k < YRT_MAX_WAVES + 2; k++) YRT_CUDA(cudaEventCreateWithFlags(&w.ev_counts[k], cudaEventDisableTiming));
+    }
+#if YRT_COUNTERS
+    if (!ds.dctr.p) {
+        YRT_TRY(ds.dctr.alloc(sizeof(unsigned long long) * 3 * YRT_DCTR_WORDS, dev));
+        YRT_CUDA(cudaMemset(ds.dctr.p, 0, sizeof(unsigned long long) * 3 * YRT_DCTR_WORDS));
+    }
+#endif
     return YRT_OK;
+}
+
+int presize_workspace_device(DevScene& ds, int width, int height, int samples) {
+    RenderParams rp;
+    rp.width = width; rp.height = height; rp.samples = samples; rp.tile_rows = std::max(height, 1); rp.rank = 0; rp.world = 1;
+    YRT_CUDA(cudaSetDevice(ds.device));
+    int depth_cap = std::min(YRT_MAX_WAVES, std::max(1, env_int("YRT_MAX_DEPTH", 16)));
+    size_t cap_slots = (size_t)batch_rows_for(rp, ds.view.n_lights, height, ds.has_reflective) * width * samples * samples;
+    return ensure_workspace(ds, ds.ws, cap_slots, ds.view.n_lights, depth_cap, ds.has_reflective);
 }
 
 static int persistent_grid(DevScene& ds, const void* kernel) {
     int per_sm = 0;
-    // experiment switch: shared-memory carve-out (percent of the 256 KB L1/shared array) forced for the traversal kernels, which
-    // use no shared memory themselves — what is carved out is taken from their L1 (profiles/r1_experiments.md)
-    int carve = env_int("YRT_CARVEOUT", -1);
-    if (carve >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(carve, 100));
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRACE_THREADS, TRACE_DSMEM) != cudaSuccess || per_sm < 1) per_sm = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRACE_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     int cap = env_int("YRT_BLOCKS_PER_SM", 0);
     if (cap > 0 && cap < per_sm) per_sm = cap;
     return ds.sm_count * per_sm;
 }
 
-// per-launch work records (chunk counter + per-SM state words, yrt_work.cuh), zeroed in one go and handed out in turn
+// per-launch work counters, zeroed in one go and handed out in turn
 struct CounterRing {
     unsigned* base; int next; int cap; cudaStream_t st;
     int init(Workspace& w, cudaStream_t s) {
         base = w.counters.as<unsigned>(); next = 0; cap = YRT_WORK_BLOCKS; st = s;
-        YRT_CUDA(cudaMemsetAsync(base, 0, sizeof(unsigned) * YRT_WORK_BLOCK_WORDS * cap, st));
+        YRT_CUDA(cudaMemsetAsync(base, 0, sizeof(unsigned) * cap, st));
         return YRT_OK;
     }
     int get(unsigned** out) {
-        if (next == cap) { YRT_CUDA(cudaMemsetAsync(base, 0, sizeof(unsigned) * YRT_WORK_BLOCK_WORDS * cap, st)); next = 0; }
-        *out = base + (size_t)YRT_WORK_BLOCK_WORDS * next++;
+        if (next == cap) { YRT_CUDA(cudaMemsetAsync(base, 0, sizeof(unsigned) * cap, st)); next = 0; }
+        *out = base + next++;
         return YRT_OK;
     }
 };
 
-// Work distribution of one persistent launch over `n` items.  tiles: the items are the slots of a batch of nrows x width
-// pixels (camera rays and their shadow rays) -> SM-affine pixel tiles; otherwise SM-affine runs of queue entries.
-// YRT_TILE=0 restores the first scheme (every warp takes the next 32 items from one counter).
-// rec = a zeroed record of YRT_WORK_BLOCK_WORDS words (or at least one word when YRT_TILE=0 / legacy).
-static WorkDist make_workdist(unsigned* rec, unsigned n, bool tiles, int width, int nrows, int spp, int sm_count) {
-    if (env_int("YRT_TILE", YRT_TILE_DEFAULT) == 0) return workdist_linear(rec, n);
-    if (tiles) {
-        // Default tile 16 x 8 pixels (x 16 spp = 64 tasks of 32 rays: two per resident warp; sweep in profiles/r1_experiments.md).
-        // A launch with few tiles per SM (a rank's share of a multi-GPU frame) halves the tile until every SM gets enough of
-        // them to keep the end of the kernel balanced; a tile smaller than the SM's warp count just means the SM works on
-        // several neighbouring tiles at once.
-        int tw = env_int("YRT_TILE_W", 16), th = env_int("YRT_TILE_H", 8);
-        const long long want = (long long)env_int("YRT_TILES_PER_SM", 32) * sm_count;
-        while ((long long)((width + tw - 1) / tw) * ((nrows + th - 1) / th) < want && tw * th > 8) {
-            if (tw >= 2 * th) tw /= 2; else th = std::max(1, th / 2);
-        }
-        return workdist_tiles(rec, width, nrows, spp, tw, th);
-    }
-    unsigned ci = (unsigned)std::max(32, env_int("YRT_CHUNK_ITEMS", 1024));
-    while ((long long)((n + ci - 1) / ci) < 32ll * sm_count && ci > 128u) ci /= 2;
-    return workdist_runs(rec, n, ci);
-}
-
-// batch of rows [lr0, lr0+nrows) of the rank's packed rows; primary hits only when ids_mode
+// batch of rows [lr0, lr0+nrows) of the rank's packed rows; primary hits only when primary_only
 static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0, int nrows, size_t cap_slots, float4* d_out, cudaStream_t st,
-                     PhaseTimer& pt, CounterRing& ring, int depth_cap, bool reflective, bool primary_only, int& max_depth_seen) {
+                     PhaseTimer& pt, CounterRing& ring, int depth_cap, bool reflective, bool primary_only) {
     BatchParams bp;
     bp.cam = rp.cam; bp.amb = rp.amb; bp.width = rp.width; bp.height = rp.height; bp.samples = rp.samples;
     bp.spp = rp.samples * rp.samples; bp.lr0 = lr0; bp.tile_rows = rp.tile_rows; bp.rank = rp.rank; bp.world = rp.world;
     bp.cap_slots = cap_slots;
     unsigned n = (unsigned)((size_t)nrows * rp.width * bp.spp);
     int nl = ds.view.n_lights;
-    const bool packet = env_int("YRT_PACKET", 0) != 0;   // warp-cooperative packet traversal: measured slower here (profiles/r1_experiments.md)
-    if (ds.grid_packet != (int)packet) { ds.grid_closest_primary = ds.grid_any = 0; ds.grid_packet = (int)packet; }
-    if (!ds.grid_closest_primary) ds.grid_closest_primary = persistent_grid(ds, packet ? (const void*)k_trace_closest<true, true> : (const void*)k_trace_closest<true, false>);
-    if (!ds.grid_closest_queue) ds.grid_closest_queue = persistent_grid(ds, (const void*)k_trace_closest<false, false>);
-    if (!ds.grid_any) ds.grid_any = persistent_grid(ds, packet ? (const void*)k_trace_any_lights<true> : (const void*)k_trace_any_lights<false>);
-    const int g_closest_p = ds.grid_closest_primary, g_closest_q = ds.grid_closest_queue, g_any = ds.grid_any;
+    if (!ds.grid_closest_primary) ds.grid_closest_primary = persistent_grid(ds, (const void*)k_trace_closest<true>);
+    if (!ds.grid_closest_queue) ds.grid_closest_queue = persistent_grid(ds, (const void*)k_trace_closest<false>);
+    if (!ds.grid_any) ds.grid_any = persistent_grid(ds, (const void*)k_trace_any_lights);
     auto grid_of = [](int g, unsigned items) { unsigned need = (items + TRACE_THREADS - 1) / TRACE_THREADS; return (int)std::max(1u, std::min((unsigned)g, need)); };
+    unsigned long long* dctr = YRT_COUNTERS ? ds.dctr.as<unsigned long long>() : nullptr;
 
     unsigned* ctr = nullptr;
     YRT_TRY(ring.get(&ctr));
     pt.begin(CAT_CLOSEST);
-    if (packet)
-        k_trace_closest<true, true><<<grid_of(g_closest_p, n), TRACE_THREADS, TRACE_DSMEM, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(),
-                                                                                     w.P.as<float4>(), make_workdist(ctr, n, true, rp.width, nrows, bp.spp, ds.sm_count));
-    else
-        k_trace_closest<true, false><<<grid_of(g_closest_p, n), TRACE_THREADS, TRACE_DSMEM, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(),
-                                                                                      w.P.as<float4>(), make_workdist(ctr, n, true, rp.width, nrows, bp.spp, ds.sm_count));
+    k_trace_closest<true><<<grid_of(ds.grid_closest_primary, n), TRACE_THREADS, 0, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(), w.P.as<float4>(),
+                                                                                          workdist_linear(ctr, n), dctr);
     pt.end();
     if (primary_only) { YRT_CUDA(cudaGetLastError()); return YRT_OK; }
 
-    FrameCounters* fc = ds.ws.stats.as<FrameCounters>();   // one set of frame counters for both pipelines
-    int* next_count = (int*)((char*)w.stats.p + sizeof(FrameCounters));
-    const int* act = nullptr;
+    // Wave loop.  Wave d traces the shadow rays of its active samples, shades them, and appends the mirror rays it spawns to
+    // the queue of wave d + 1, whose length is counts[d + 1] in device memory: every kernel of a later wave reads its item
+    // count from there, so the host enqueues waves without waiting for the device.  It stops enqueuing when a count that
+    // has reached it in the meantime (asynchronous copy into pinned memory + event, polled, never waited for) is zero —
+    // at most a couple of empty waves are launched beyond the last real one, and none at all for scenes without mirrors.
+    FrameCounters* fc = ds.ws.stats.as<FrameCounters>();   // one set of frame counters for all pipelines
+    unsigned* counts = (unsigned*)((char*)w.stats.p + STATS_WAVE_COUNTS_OFFSET);
+    if (reflective) YRT_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned) * (YRT_MAX_WAVES + 2), st));
     int* act_bufs[2] = {w.act0.as<int>(), w.act1.as<int>()};
-    unsigned n_act = n;
     for (int depth = 0;; depth++) {
-        if (depth + 1 > max_depth_seen) max_depth_seen = depth + 1;
-        if (reflective) YRT_CUDA(cudaMemsetAsync(next_count, 0, sizeof(int), st));
-        int* next_act = reflective ? act_bufs[depth & 1] : nullptr;
-        ShadeBuffers sb;
-        sb.hit = w.hit.as<float4>(); sb.ray_o = w.ray_o.as<float4>(); sb.ray_d = w.ray_d.as<float4>(); sb.pstack = w.pstack.as<float4>();
-        sb.rad = w.rad.as<float4>(); sb.next_act = next_act; sb.next_count = next_count; sb.fc = fc;
-        const bool fused = nl <= 32 && !packet && env_int("YRT_FUSE_SHADE", 0) != 0;   // measured: 16.76 vs 16.57 ms unfused at N=1 (spills at the 64-register cap); option only
-        if (fused) {
-            // shadow rays + shading in one persistent kernel (visibility stays in a register mask)
-            if (!ds.grid_shadow_shade) ds.grid_shadow_shade = persistent_grid(ds, (const void*)k_shadow_shade);
+        const int* act = depth == 0 ? nullptr : act_bufs[(depth - 1) & 1];
+        const unsigned* n_dev = depth == 0 ? nullptr : counts + depth;
+        if (depth > 0) {
             YRT_TRY(ring.get(&ctr));
-            pt.begin(CAT_ANY);
-            k_shadow_shade<<<grid_of(ds.grid_shadow_shade, n_act), TRACE_THREADS, TRACE_DSMEM, st>>>(ds.view, bp, sb, depth, depth_cap, act, w.P.as<float4>(),
-                                                                                          make_workdist(ctr, n_act, act == nullptr, rp.width, nrows, bp.spp, ds.sm_count));
-            pt.end();
-        } else {
-            if (nl > 0) {
-                YRT_TRY(ring.get(&ctr));
-                pt.begin(CAT_ANY);
-                // shadow rays of the camera hits are as coherent as the camera rays; those of reflection waves are not
-                if (packet && depth == 0)
-                    k_trace_any_lights<true><<<grid_of(g_any, n_act), TRACE_THREADS, TRACE_DSMEM, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
-                                                                                             w.vis.as<uint8_t>(), make_workdist(ctr, n_act, act == nullptr, rp.width, nrows, bp.spp, ds.sm_count));
-                else
-                    k_trace_any_lights<false><<<grid_of(g_any, n_act), TRACE_THREADS, TRACE_DSMEM, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(),
-                                                                                              w.vis.as<uint8_t>(), make_workdist(ctr, n_act, act == nullptr, rp.width, nrows, bp.spp, ds.sm_count));
-                pt.end();
-            }
-            pt.begin(CAT_SHADE);
-            k_shade<<<(n_act + 255) / 256, 256, 0, st>>>(ds.view, bp, sb, depth, depth_cap, act, n_act, w.vis.as<uint8_t>());
+            pt.begin(CAT_CLOSEST);
+            k_trace_closest<false><<<grid_of(ds.grid_closest_queue, n), TRACE_THREADS, 0, st>>>(ds.view, bp, act, w.ray_o.as<float4>(), w.ray_d.as<float4>(), w.hit.as<float4>(),
+                                                                                               w.P.as<float4>(), workdist_linear(ctr, n, n_dev), dctr ? dctr + YRT_DCTR_WORDS : nullptr);
             pt.end();
         }
-        if (!reflective || depth + 1 >= depth_cap) break;
-        int h_next = 0;
-        YRT_CUDA(cudaMemcpyAsync(&h_next, next_count, sizeof(int), cudaMemcpyDeviceToHost, st));
-        YRT_CUDA(cudaStreamSynchronize(st));
-        if (h_next <= 0) break;
-        n_act = (unsigned)h_next;
-        act = next_act;
-        YRT_TRY(ring.get(&ctr));
-        pt.begin(CAT_CLOSEST);
-        k_trace_closest<false, false><<<grid_of(g_closest_q, n_act), TRACE_THREADS, TRACE_DSMEM, st>>>(ds.view, bp, act, w.ray_o.as<float4>(), w.ray_d.as<float4>(),
-                                                                                    w.hit.as<float4>(), w.P.as<float4>(),
-                                                                                    make_workdist(ctr, n_act, false, rp.width, nrows, bp.spp, ds.sm_count));
+        ShadeBuffers sb;
+        sb.hit = w.hit.as<float4>(); sb.ray_o = w.ray_o.as<float4>(); sb.ray_d = w.ray_d.as<float4>(); sb.pstack = w.pstack.as<float4>();
+        sb.rad = w.rad.as<float4>(); sb.next_act = reflective ? act_bufs[depth & 1] : nullptr; sb.next_count = (int*)(counts + depth + 1); sb.fc = fc;
+        if (nl > 0) {
+            YRT_TRY(ring.get(&ctr));
+            pt.begin(CAT_ANY);
+            k_trace_any_lights<<<grid_of(ds.grid_any, n), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(), w.vis.as<uint8_t>(),
+                                                                                 workdist_linear(ctr, n, n_dev), dctr ? dctr + 2 * YRT_DCTR_WORDS : nullptr);
+            pt.end();
+        }
+        pt.begin(CAT_SHADE);
+        k_shade<<<(n + 255) / 256, 256, 0, st>>>(ds.view, bp, sb, depth, depth_cap, act, n, n_dev, w.vis.as<uint8_t>());
         pt.end();
+        if (!reflective || depth + 1 >= depth_cap) break;
+        YRT_CUDA(cudaMemcpyAsync(w.h_counts + depth + 1, counts + depth + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        YRT_CUDA(cudaEventRecord(w.ev_counts[depth + 1], st));
+        // counts that have arrived so far: wave k has no rays => no later wave has any
+        bool stop = false;
+        for (int k = 1; k <= depth + 1 && !stop; k++)
+            if (cudaEventQuery(w.ev_counts[k]) == cudaSuccess && w.h_counts[k] == 0) stop = true;
+        cudaGetLastError();   // cudaErrorNotReady is not an error
+        if (stop) break;
     }
     int n_pix = nrows * rp.width;
     pt.begin(CAT_OTHER);
@@ -679,9 +579,10 @@ static int check_params(const RenderParams& rp) {
 }
 
 static int batch_rows_for(const RenderParams& rp, int n_lights, int own_rows, bool reflective) {
-    // slots (camera samples) per batch: a whole 1080p/16spp frame (33.2 M slots, 51 B each) when nothing
-    // reflects — fewer launches and kernel tails; 4 M when the per-slot recursion stack must be allocated too
-    long long target = env_int("YRT_BATCH_SLOTS", reflective ? (4 << 20) : (48 << 20));
+    // slots (camera samples) per batch: a whole 1080p/16spp frame (33.2 M slots, 51 B each) when nothing reflects —
+    // fewer launches and kernel tails; 8.5 M (a 1280x720, 9 spp frame) when the per-slot recursion stack
+    // (48 B x depth cap per slot) must be allocated too
+    long long target = env_int("YRT_BATCH_SLOTS", reflective ? 8500000 : (48 << 20));
     long long per_row = (long long)rp.width * rp.samples * rp.samples;
     if (target > 0x7fffff00ll) target = 0x7fffff00ll;
     (void)n_lights;
@@ -696,14 +597,13 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
     int spp = rp.samples * rp.samples;
     int nl = ds.view.n_lights;
     bool reflective = ds.has_reflective;
-    int depth_cap = std::max(1, env_int("YRT_MAX_DEPTH", 16));
+    int depth_cap = std::min(YRT_MAX_WAVES, std::max(1, env_int("YRT_MAX_DEPTH", 16)));
     int batch_rows = batch_rows_for(rp, nl, own, reflective);
     // two pipelines: the rank's rows are cut into (at least) two batches that run on two streams, so the ramp-up of one
     // batch's kernel fills the tail of the other's (each persistent kernel ends with ~one 32-ray task of idle SMs).
-    // Reflective scenes synchronise with the host between waves and stay on one stream.
     // Default: 2 when this call renders one rank's share of a frame (measured at 1/8 frame: 2.265 -> 2.150 ms, 3 pipelines
     // 2.146, 4: 2.223), 1 for a whole frame (16.56 -> 16.46 ms only, and the per-kernel event spans stay unambiguous).
-    const int n_pipes = (!reflective) ? std::max(1, std::min(std::min(4, own), env_int("YRT_STREAMS", rp.world > 1 ? YRT_DEFAULT_STREAMS : 1))) : 1;
+    const int n_pipes = std::max(1, std::min(std::min(4, own), env_int("YRT_STREAMS", rp.world > 1 ? YRT_DEFAULT_STREAMS : 1)));
     if (n_pipes > 1) batch_rows = std::min(batch_rows, (own + n_pipes - 1) / n_pipes);
     size_t cap_slots = (size_t)batch_rows * rp.width * spp;
     YRT_TRY(ensure_workspace(ds, ds.ws, cap_slots, nl, depth_cap, reflective));
@@ -734,20 +634,19 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
         YRT_CUDA(cudaStreamWaitEvent(ds.aux_stream[k - 1], ds.ev_fork, 0));
         YRT_TRY(ring[k].init(ds.ws_aux[k - 1], ds.aux_stream[k - 1]));
     }
-    int max_depth_seen = 0, b = 0;
+    int b = 0;
     for (int lr0 = 0; lr0 < own; lr0 += batch_rows, b++) {
         int nrows = std::min(batch_rows, own - lr0);
         int pipe = b % n_pipes;
         Workspace& w = pipe ? ds.ws_aux[pipe - 1] : ds.ws;
         pt.st = pipe ? ds.aux_stream[pipe - 1] : st;
-        YRT_TRY(run_batch(ds, w, rp, lr0, nrows, w.cap_slots, d_out, pt.st, pt, ring[pipe], depth_cap, reflective, false, max_depth_seen));
+        YRT_TRY(run_batch(ds, w, rp, lr0, nrows, w.cap_slots, d_out, pt.st, pt, ring[pipe], depth_cap, reflective, false));
     }
     pt.st = st;
     for (int k = 1; k < n_pipes; k++) {
         YRT_CUDA(cudaEventRecord(ds.ev_join[k - 1], ds.aux_stream[k - 1]));
         YRT_CUDA(cudaStreamWaitEvent(st, ds.ev_join[k - 1], 0));
     }
-    pt.max_depth_seen = pt.deferred ? std::max(pt.max_depth_seen, max_depth_seen) : max_depth_seen;
     if (pt.on) {
         cudaEventRecord(pt.spans[frame_span - 1].b, st);
         pt.frames++;
@@ -780,7 +679,8 @@ int collect_stats_device(DevScene& ds, const RenderParams& rp, yrt_stats* stats)
     stats->ms_trace_any = cat[CAT_ANY];
     stats->ms_shade = cat[CAT_SHADE];
     stats->ms_other = cat[CAT_OTHER];
-    stats->max_depth = pt.max_depth_seen;
+    stats->max_depth = pt.primary > 0 ? std::max(1, (int)fc.max_depth) : 0;
+    stats->truncated_paths = (int64_t)fc.truncated;
     stats->n_gpus = 1;
     stats->n_closest = cnt[CAT_CLOSEST]; stats->n_any = cnt[CAT_ANY]; stats->n_shade = cnt[CAT_SHADE]; stats->n_other = cnt[CAT_OTHER];
     stats->frames = pt.frames;
@@ -788,16 +688,31 @@ int collect_stats_device(DevScene& ds, const RenderParams& rp, yrt_stats* stats)
     return YRT_OK;
 }
 
+int read_counters_device(DevScene& ds, uint64_t out[24]) {
+#if YRT_COUNTERS
+    YRT_CUDA(cudaSetDevice(ds.device));
+    YRT_CUDA(cudaDeviceSynchronize());
+    if (!ds.dctr.p) { memset(out, 0, sizeof(uint64_t) * 24); return YRT_OK; }
+    YRT_CUDA(cudaMemcpy(out, ds.dctr.p, sizeof(uint64_t) * 24, cudaMemcpyDeviceToHost));
+    YRT_CUDA(cudaMemset(ds.dctr.p, 0, sizeof(uint64_t) * 24));
+    return YRT_OK;
+#else
+    (void)ds; (void)out;
+    set_error("this build of the library does not count per-ray work (rebuild with -DYRT_COUNTERS=1, tools/build_variants.sh)");
+    return YRT_ERR_UNSUPPORTED;
+#endif
+}
+
 int stats_begin_device(DevScene& ds) {
     if (!ds.timer) ds.timer = new PhaseTimer();
     PhaseTimer& pt = *ds.timer;
     YRT_CUDA(cudaSetDevice(ds.device));
-    YRT_TRY(ds.ws.stats.alloc(sizeof(FrameCounters) + 64, ds.device));
+    YRT_TRY(ds.ws.stats.alloc(STATS_BYTES, ds.device));
     if (pt.main || ds.stream) YRT_CUDA(cudaStreamSynchronize(pt.main ? pt.main : ds.stream));
     YRT_CUDA(cudaMemset(ds.ws.stats.p, 0, sizeof(FrameCounters)));
     for (auto& sp : pt.spans) { pt.pool.push_back(sp.a); pt.pool.push_back(sp.b); }
     pt.spans.clear();
-    pt.frames = 0; pt.primary = 0; pt.max_depth_seen = 0;
+    pt.frames = 0; pt.primary = 0;
     pt.deferred = true;
     return YRT_OK;
 }
@@ -828,11 +743,10 @@ int trace_primary_device(DevScene& ds, const RenderParams& rp_in, int32_t* h_ids
     PhaseTimer pt;
     CounterRing ring;
     YRT_TRY(ring.init(ds.ws, st));
-    int mds = 0;
     for (int lr0 = 0; lr0 < rp.height; lr0 += batch_rows) {
         int nrows = std::min(batch_rows, rp.height - lr0);
         size_t n = (size_t)nrows * rp.width * spp;
-        YRT_TRY(run_batch(ds, ds.ws, rp, lr0, nrows, ds.ws.cap_slots, nullptr, st, pt, ring, 1, false, true, mds));
+        YRT_TRY(run_batch(ds, ds.ws, rp, lr0, nrows, ds.ws.cap_slots, nullptr, st, pt, ring, 1, false, true));
         k_hit_ids<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ds.view, ds.ws.hit.as<float4>(), ds.ws.P.as<float4>(), (int)n, d_ids.as<int>(),
                                                              d_dist.as<float>(), d_uv.as<float>());
         YRT_CUDA(cudaGetLastError());
@@ -862,9 +776,9 @@ int intersect_rays_device(DevScene& ds, const float* h_rays, int64_t n, bool any
     YRT_TRY(dist.alloc(sizeof(float) * c, ds.device));
     YRT_TRY(uv.alloc(sizeof(float) * 2 * c, ds.device));
     YRT_TRY(occ.alloc((size_t)c, ds.device));
-    YRT_TRY(ctr.alloc(sizeof(unsigned) * YRT_WORK_BLOCK_WORDS, ds.device));
+    YRT_TRY(ctr.alloc(sizeof(unsigned) * 4, ds.device));
     std::vector<float4> ho(c), hd(c);
-    int g_c = persistent_grid(ds, (const void*)k_trace_closest<false, false>);
+    int g_c = persistent_grid(ds, (const void*)k_trace_closest<false>);
     int g_a = persistent_grid(ds, (const void*)k_trace_any_rays);
     BatchParams bp;
     memset(&bp, 0, sizeof(bp));
@@ -877,18 +791,16 @@ int intersect_rays_device(DevScene& ds, const float* h_rays, int64_t n, bool any
         }
         YRT_CUDA(cudaMemcpyAsync(ro.p, ho.data(), sizeof(float4) * m, cudaMemcpyHostToDevice, st));
         YRT_CUDA(cudaMemcpyAsync(rd.p, hd.data(), sizeof(float4) * m, cudaMemcpyHostToDevice, st));
-        YRT_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(unsigned) * YRT_WORK_BLOCK_WORDS, st));
+        YRT_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(unsigned) * 4, st));
         unsigned need = (unsigned)((m + TRACE_THREADS - 1) / TRACE_THREADS);
         if (any) {
-            k_trace_any_rays<<<std::max(1u, std::min((unsigned)g_a, need)), TRACE_THREADS, TRACE_DSMEM, st>>>(ds.view, ro.as<float4>(), rd.as<float4>(),
-                                                                                                  occ.as<uint8_t>(),
-                                                                                                  make_workdist(ctr.as<unsigned>(), (unsigned)m, false, 0, 0, 1, ds.sm_count));
+            k_trace_any_rays<<<std::max(1u, std::min((unsigned)g_a, need)), TRACE_THREADS, 0, st>>>(ds.view, ro.as<float4>(), rd.as<float4>(), occ.as<uint8_t>(),
+                                                                                                 workdist_linear(ctr.as<unsigned>(), (unsigned)m));
             YRT_CUDA(cudaGetLastError());
             YRT_CUDA(cudaMemcpyAsync(h_occ + off, occ.p, (size_t)m, cudaMemcpyDeviceToHost, st));
         } else {
-            k_trace_closest<false, false><<<std::max(1u, std::min((unsigned)g_c, need)), TRACE_THREADS, TRACE_DSMEM, st>>>(
-                ds.view, bp, nullptr, ro.as<float4>(), rd.as<float4>(), hit.as<float4>(), P.as<float4>(),
-                make_workdist(ctr.as<unsigned>(), (unsigned)m, false, 0, 0, 1, ds.sm_count));
+            k_trace_closest<false><<<std::max(1u, std::min((unsigned)g_c, need)), TRACE_THREADS, 0, st>>>(
+                ds.view, bp, nullptr, ro.as<float4>(), rd.as<float4>(), hit.as<float4>(), P.as<float4>(), workdist_linear(ctr.as<unsigned>(), (unsigned)m), nullptr);
             k_hit_ids<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(ds.view, hit.as<float4>(), P.as<float4>(), (int)m, ids.as<int>(),
                                                                  dist.as<float>(), uv.as<float>());
             YRT_CUDA(cudaGetLastError());

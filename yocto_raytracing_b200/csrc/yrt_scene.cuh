@@ -1,9 +1,10 @@
 // yrt_scene.cuh — device-resident scene layout (what lives in HBM) and node/leaf references.
 //
 // All records are multiples of 16 bytes and are fetched with 128-bit loads.
-//   BVH node (64 B, TLAS and BLAS alike; two-child-box layout, boxes as centre / half-extent):
-//     q0 = child0.centre.xyz | child0 ref  q1 = child0.half.xyz | child1 ref
-//     q2 = child1.centre.xyz | -           q3 = child1.half.xyz | -        (half-extents inflated by 1 + 16u)
+//   BVH node (TLAS and BLAS alike, boxes as centre / half-extent inflated by 1 + 16u, two children interleaved per
+//   48-byte "pair" so that the slab test runs on packed FFMA2 — see "traversal node" below):
+//     YRT_WIDE == 4 (default): 128 B = pair(children 0,1) | pair(children 2,3) | 4 child refs | spare
+//     YRT_WIDE == 2          :  64 B = pair(children 0,1) | 2 child refs
 //   prim record (48 B, in BLAS leaf order, all shapes concatenated):
 //     triangle: q0 = v0.xyz | ei     q1 = v1.xyz | -      q2 = v2.xyz | -
 //     line:     q0 = v0.xyz | ei     q1 = v1.xyz | r0     q2 = r1, -, -, -
@@ -64,87 +65,111 @@ YRT_HD float4 ld4(const float4* p) {
 #endif
 }
 
-// two adjacent 16-byte records, optionally with ONE 256-bit load (LDG.E.256, new on sm_100; p 32-byte aligned).
-// Measured (profiles/r1_experiments.md): 16.78 ms with LDG.256 vs 16.63 ms with 2 x LDG.128 per pair, so off by default.
-YRT_HD void ld8(const float4* p, float4& a, float4& b) {
-#if defined(__CUDA_ARCH__) && defined(YRT_LDG256)
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                 : "l"(p));
-#else
-    a = ld4(p);
-    b = ld4(p + 1);
-#endif
-}
-
 YRT_HD float4 mk4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 
-// ---- 64-byte traversal node ------------------------------------------------------------------
-//   q0 = (c0.x, c0.y, c1.x, c1.y)   q1 = (h0.x, h0.y, h1.x, h1.y)   q2 = (c0.z, c1.z, h0.z, h1.z)   q3 = (ref0, ref1, -, -)
-// The two child boxes are interleaved so that every FMA of the slab test has a partner with which it shares one packed
+// ---- traversal node ---------------------------------------------------------------------------
+// A "pair" is the 48-byte record of two sibling child boxes:
+//   p0 = (c0.x, c0.y, c1.x, c1.y)   p1 = (h0.x, h0.y, h1.x, h1.y)   p2 = (c0.z, c1.z, h0.z, h1.z)
+// The two boxes are interleaved so that every FMA of the slab test has a partner with which it shares one packed
 // FFMA2 (sm_100: two fp32 FMAs per issue slot on an aligned register pair): x and y of one child pair up against the
 // ray's (invd.x, invd.y) / (noi.x, noi.y) / (ainv.x, ainv.y) pairs, and the z of child 0 pairs with the z of child 1
-// against a broadcast scalar.  20 FFMA per node become 10 FFMA2; the values are the same IEEE FMAs, so the accept
+// against a broadcast scalar.  20 FFMA per pair become 10 FFMA2; the values are the same IEEE FMAs, so the accept
 // decisions are bit-identical to slab_test_ch on the same boxes (the host build below uses exactly that).
+//
+// Node = YRT_WIDE children (tree arity of the traversal; the LBVH itself is binary, wide nodes are collapsed from it at
+// emit time, yrt_lbvh.cuh):
+//   YRT_WIDE == 4: 8 float4, 128-byte aligned = one L1 line: pair(0,1) | pair(2,3) | (ref0, ref1, ref2, ref3) | spare.
+//                  A visit tests the four (grand)children of a binary node at once: one dependent fetch and one round of
+//                  loop / stack overhead for what the binary tree does in 1 + (children entered) visits, and no test of
+//                  the intermediate boxes.  Unused child slots hold a box no ray can enter (h = -FLT_MAX).
+//   YRT_WIDE == 2: 4 float4: pair(0,1) | (ref0, ref1, -, -)                       (round 1's layout, kept for A/B builds)
+// YRT_PACK_REFS (build option): the child references ride in the low 16 bits of the four x / y half-extents of their
+// pair, whose upper 16 bits hold the half-extent rounded UP to bfloat16 — the stored value (reference bits included) is
+// never below the inflated half-extent the slab test's error analysis asks for, at most 2^-7 above it.  A visit then
+// reads one 16-byte quad less for two byte permutes per pair.
+#ifndef YRT_WIDE
+#define YRT_WIDE 4
+#endif
+#ifndef YRT_PACK_REFS
+#define YRT_PACK_REFS 0
+#endif
+#if YRT_WIDE == 4
+#define YRT_NODE_STRIDE 8   /* float4 per node */
+#else
+#define YRT_NODE_STRIDE (YRT_PACK_REFS ? 3 : 4)
+#endif
+
 struct nodebox { float cx, cy, cz, hx, hy, hz; };
-YRT_HD nodebox node_child(const float4& q0, const float4& q1, const float4& q2, int k) {
+YRT_HD nodebox pair_child(const float4& p0, const float4& p1, const float4& p2, int k) {
     nodebox b;
-    if (k == 0) { b.cx = q0.x; b.cy = q0.y; b.cz = q2.x; b.hx = q1.x; b.hy = q1.y; b.hz = q2.z; }
-    else        { b.cx = q0.z; b.cy = q0.w; b.cz = q2.y; b.hx = q1.z; b.hy = q1.w; b.hz = q2.w; }
+    if (k == 0) { b.cx = p0.x; b.cy = p0.y; b.cz = p2.x; b.hx = p1.x; b.hy = p1.y; b.hz = p2.z; }
+    else        { b.cx = p0.z; b.cy = p0.w; b.cz = p2.y; b.hx = p1.z; b.hy = p1.w; b.hz = p2.w; }
     return b;
 }
-// YRT_NODE48 (build option, off): a 48-byte node.  The two child references ride in the low 16 bits of the four x / y
-// half-extents, whose upper 16 bits hold the half-extent rounded UP to bfloat16 — so the stored value (reference bits
-// included) is never below the inflated half-extent the slab test's error analysis asks for, at most 2^-7 above it.  A
-// node visit then returns 48 instead of 56 bytes per lane over the L1 data path (12 instead of 14 cycles per warp,
-// DESIGN.md 3.2) for two byte permutes.
-#ifndef YRT_NODE48
-#define YRT_NODE48 0
-#endif
-#define YRT_NODE_STRIDE (YRT_NODE48 ? 3 : 4)   /* float4 per node */
+// a box no ray enters: t0 = +huge, t1 = -huge on every axis (fused test), lo > hi (reference formula)
+YRT_HD nodebox nodebox_empty() { nodebox b; b.cx = b.cy = b.cz = 0.f; b.hx = b.hy = b.hz = -FLT_MAX; return b; }
+
 YRT_HD float half_with_payload_(float h, unsigned payload16) {
+    if (!(h >= 0.f)) return h;                  // empty slot: stays unreachable, carries no reference
     unsigned b = (unsigned)float_as_int(h);
     b = (b + 0xffffu) & 0xffff0000u;            // round up to a bfloat16 (h >= 0, finite)
     if (b >= 0x7f800000u) b = 0x7f7f0000u;      // (never for real scenes: stay finite)
     return int_as_float((int)(b | (payload16 & 0xffffu)));
 }
-YRT_HD void node_pack(float4* n, const nodebox& b0, const nodebox& b1, int ref0, int ref1) {
-    n[0] = mk4(b0.cx, b0.cy, b1.cx, b1.cy);
-#if YRT_NODE48
-    n[1] = mk4(half_with_payload_(b0.hx, (unsigned)ref0), half_with_payload_(b0.hy, (unsigned)ref0 >> 16),
+YRT_HD void pair_pack(float4* p, const nodebox& b0, const nodebox& b1, int ref0, int ref1) {
+    p[0] = mk4(b0.cx, b0.cy, b1.cx, b1.cy);
+#if YRT_PACK_REFS
+    p[1] = mk4(half_with_payload_(b0.hx, (unsigned)ref0), half_with_payload_(b0.hy, (unsigned)ref0 >> 16),
                half_with_payload_(b1.hx, (unsigned)ref1), half_with_payload_(b1.hy, (unsigned)ref1 >> 16));
-    n[2] = mk4(b0.cz, b1.cz, b0.hz, b1.hz);
 #else
-    n[1] = mk4(b0.hx, b0.hy, b1.hx, b1.hy);
-    n[2] = mk4(b0.cz, b1.cz, b0.hz, b1.hz);
-    n[3] = mk4(int_as_float(ref0), int_as_float(ref1), 0.f, 0.f);
+    (void)ref0; (void)ref1;
+    p[1] = mk4(b0.hx, b0.hy, b1.hx, b1.hy);
 #endif
+    p[2] = mk4(b0.cz, b1.cz, b0.hz, b1.hz);
 }
-// the two child references of a node record (q1 = second float4; q3 = fourth float4 of the 64-byte layout)
-YRT_HD void node_refs(const float4& q1, const float4& q3, int& ref0, int& ref1) {
-#if YRT_NODE48
-    (void)q3;
+#if YRT_PACK_REFS
+// the two child references of a pair (p1 = its second float4)
+YRT_HD void pair_refs(const float4& p1, int& ref0, int& ref1) {
 #if defined(__CUDA_ARCH__)
-    ref0 = (int)__byte_perm((unsigned)float_as_int(q1.x), (unsigned)float_as_int(q1.y), 0x5410);
-    ref1 = (int)__byte_perm((unsigned)float_as_int(q1.z), (unsigned)float_as_int(q1.w), 0x5410);
+    ref0 = (int)__byte_perm((unsigned)float_as_int(p1.x), (unsigned)float_as_int(p1.y), 0x5410);
+    ref1 = (int)__byte_perm((unsigned)float_as_int(p1.z), (unsigned)float_as_int(p1.w), 0x5410);
 #else
-    ref0 = (int)(((unsigned)float_as_int(q1.x) & 0xffffu) | ((unsigned)float_as_int(q1.y) << 16));
-    ref1 = (int)(((unsigned)float_as_int(q1.z) & 0xffffu) | ((unsigned)float_as_int(q1.w) << 16));
-#endif
-#else
-    (void)q1;
-    ref0 = float_as_int(q3.x); ref1 = float_as_int(q3.y);
+    ref0 = (int)(((unsigned)float_as_int(p1.x) & 0xffffu) | ((unsigned)float_as_int(p1.y) << 16));
+    ref1 = (int)(((unsigned)float_as_int(p1.z) & 0xffffu) | ((unsigned)float_as_int(p1.w) << 16));
 #endif
 }
-// loads one node record
-YRT_HD void node_load(const float4* nodes, int node, float4& q0, float4& q1, float4& q2, float4& q3) {
-    const float4* n = nodes + YRT_NODE_STRIDE * (size_t)node;
-    ld8(n, q0, q1);
-#if YRT_NODE48
-    q2 = ld4(n + 2);
-    q3 = q2;
+#endif
+
+// writes one node record: nb child boxes (2 <= nb <= YRT_WIDE) and their references; the remaining slots are empty
+YRT_HD void node_pack(float4* n, const nodebox* box, const int* ref, int nb) {
+    nodebox b[YRT_WIDE];
+    int r[YRT_WIDE];
+    for (int k = 0; k < YRT_WIDE; k++) {
+        b[k] = k < nb ? box[k] : nodebox_empty();
+        r[k] = k < nb ? ref[k] : YRT_REF_DONE;   // never read: the slot's box cannot be entered
+    }
+    pair_pack(n, b[0], b[1], r[0], r[1]);
+#if YRT_WIDE == 4
+    pair_pack(n + 3, b[2], b[3], r[2], r[3]);
+    n[6] = mk4(int_as_float(r[0]), int_as_float(r[1]), int_as_float(r[2]), int_as_float(r[3]));
+    n[7] = mk4(int_as_float(nb), 0.f, 0.f, 0.f);
+#elif !YRT_PACK_REFS
+    n[3] = mk4(int_as_float(r[0]), int_as_float(r[1]), 0.f, 0.f);
+#endif
+}
+// child k of a node record held in host-visible memory (tools and tests; the traversal reads the quads itself)
+YRT_HD void node_child(const float4* n, int k, nodebox& b, int& ref) {
+    const float4* p = n + 3 * (k >> 1);
+    b = pair_child(p[0], p[1], p[2], k & 1);
+#if YRT_PACK_REFS
+    int r0, r1;
+    pair_refs(p[1], r0, r1);
+    ref = (k & 1) ? r1 : r0;
+#elif YRT_WIDE == 4
+    const float4 q = n[6];
+    ref = float_as_int(k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w)));
 #else
-    ld8(n + 2, q2, q3);
+    ref = float_as_int(k == 0 ? n[3].x : n[3].y);
 #endif
 }
 
@@ -155,8 +180,8 @@ __device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 #endif
 
-// both children of one node against one ray; e0/e1 = entry distances (ordering only)
-YRT_HD void slab_test_node(const slabray& r, float rtmin, float rtmax, const float4& q0, const float4& q1, const float4& q2,
+// both children of one pair against one ray; e0/e1 = entry distances (ordering only)
+YRT_HD void slab_test_pair(const slabray& r, float rtmin, float rtmax, const float4& q0, const float4& q1, const float4& q2,
                            bool& h0, bool& h1, float& e0, float& e1) {
 #if defined(__CUDA_ARCH__) && !defined(YRT_NO_FFMA2)
     f32x2 ixy = pk2(r.invd.x, r.invd.y), nxy = pk2(r.noi.x, r.noi.y), axy = pk2(r.ainv.x, r.ainv.y), naxy = pk2(-r.ainv.x, -r.ainv.y);
@@ -185,7 +210,7 @@ YRT_HD vec3 xyz(const float4& q) { return mk3(q.x, q.y, q.z); }
 
 // ---- what a kernel sees ------------------------------------------------------------------
 struct SceneView {
-    const float4* nodes;        // 4 per node; BLAS nodes of all shapes first, TLAS nodes after them — one
+    const float4* nodes;        // YRT_NODE_STRIDE per node; BLAS nodes of all shapes first, TLAS nodes after them — one
                                 // array and one index space, so a node visit needs no level test
     const float4* inst_recs;    // 4 per instance, TLAS leaf order
     const float4* prim_recs;    // 3 per prim, BLAS leaf order

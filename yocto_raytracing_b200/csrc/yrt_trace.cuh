@@ -14,39 +14,21 @@
 #pragma once
 #include "yrt_scene.cuh"
 
-#ifndef YRT_VISIT_V2
-#define YRT_VISIT_V2 1
+#ifndef YRT_POP_CULL
+#define YRT_POP_CULL 1   /* closest hit: a stack entry carries the entry distance of its box and is dropped at pop time if the hit found since then is nearer */
 #endif
 #ifndef YRT_ANY_UNORDERED
-#define YRT_ANY_UNORDERED 1  /* any-hit rays: skip the near/far ordering of the two children (the answer is order independent; -6 % kernel time) */
+#define YRT_ANY_UNORDERED 1  /* any-hit rays: children are entered in stored order, no entry-distance compare (the answer is order independent) */
 #endif
-
-#ifndef YRT_STACK_TOP_REG
-#define YRT_STACK_TOP_REG 0   /* 1: the top of the traversal stack lives in a register (a pop hands out the next node without waiting for a load) */
-#endif
-#ifndef YRT_PREFETCH_PUSH
-#define YRT_PREFETCH_PUSH 0   /* 1: a postponed child node is prefetched into L1 when it is pushed */
-#endif
-#ifndef YRT_RESTORE_OD
-#define YRT_RESTORE_OD 0   /* 1: an instance exit also restores the ray's origin and direction (the first version; dead values) */
-#endif
-#ifndef YRT_WORLD_SMEM
-#define YRT_WORLD_SMEM 0   /* 1: the world-space ray waits in shared memory while the lane is inside an instance (13 registers less) */
-#endif
-#if YRT_WORLD_SMEM && defined(__CUDA_ARCH__)
-#define YRT_WORLD_IN_SMEM 1
-#else
-#define YRT_WORLD_IN_SMEM 0
-#endif
-#define YRT_WORLD_WORDS 13    /* o, d, 1/d, -o/d, pad */
 
 namespace yrt {
 
-struct TraceCounters {   // optional per-ray work counters (roofline inputs), host_emu / debug kernels
+struct TraceCounters {   // optional per-ray work counters (roofline inputs): host emulation and the -DYRT_COUNTERS build of the library
     int box_tests, prim_tests, inst_entries, max_stack;
-    int slab_false_rejects;   // boxes the reference's slab test accepts but the fused one rejects (must stay 0)
-    int slab_extra_accepts;   // the other way round (harmless, costs a visit)
+    int slab_false_rejects;   // boxes the reference's slab test accepts but the fused one rejects (must stay 0; host audit only)
+    int slab_extra_accepts;   // the other way round (harmless, costs a visit; host audit only)
     int tlas_box_tests;       // part of box_tests spent in the instance tree
+    int node_visits;          // node records fetched (YRT_WIDE box tests each)
 };
 
 // test the prims of one BLAS leaf; returns true if any was hit (tmax/hit updated)
@@ -126,57 +108,13 @@ YRT_HD vec3 inv3_slab(const vec3& d) { return mk3(rcp_slab(d.x), rcp_slab(d.y), 
 // kernels hand a finished lane a new ray while the rest of the warp keeps going.
 template <bool ANY, bool EXACT = false>
 struct Tracer {
-#if YRT_WORLD_IN_SMEM
-    // the world-space ray is needed again only when the lane leaves an instance: it waits in shared memory
-    // (word w of thread t at [w * blockDim.x + t]: conflict-free), kernels launch with YRT_WORLD_WORDS * 4 bytes per thread
-    __device__ __forceinline__ static float* wsave() {
-        extern __shared__ float yrt_world_save[];
-        return yrt_world_save + threadIdx.x;
-    }
-    __device__ __forceinline__ void save_world() {
-        float* w = wsave();
-        const unsigned T = blockDim.x;
-        w[0] = o.x; w[T] = o.y; w[2 * T] = o.z; w[3 * T] = d.x; w[4 * T] = d.y; w[5 * T] = d.z;
-        w[6 * T] = sr.invd.x; w[7 * T] = sr.invd.y; w[8 * T] = sr.invd.z;
-        w[9 * T] = sr.noi.x; w[10 * T] = sr.noi.y; w[11 * T] = sr.noi.z; w[12 * T] = sr.pad;
-    }
-    __device__ __forceinline__ void restore_world() {
-        const float* w = wsave();
-        const unsigned T = blockDim.x;
-        o = mk3(w[0], w[T], w[2 * T]); d = mk3(w[3 * T], w[4 * T], w[5 * T]);
-        sr.invd = mk3(w[6 * T], w[7 * T], w[8 * T]);
-        sr.noi = mk3(w[9 * T], w[10 * T], w[11 * T]);
-        sr.ainv = mk3(fabsf(sr.invd.x), fabsf(sr.invd.y), fabsf(sr.invd.z));
-        sr.pad = w[12 * T];
-    }
-    __device__ __forceinline__ const vec3& world_o() const { return o; }
-    __device__ __forceinline__ const vec3& world_d() const { return d; }
-#else
     vec3 wo, wd;          // world-space ray
     slabray wsr;
-    YRT_HD void save_world() { wo = o; wd = d; wsr = sr; }
-    // At the top level only the slab-test operands are read (the fused test needs neither o nor d, and the instance entry
-    // transforms wo / wd): (o, d) may keep the last instance's values there — six moves less per instance exit.  The
-    // reference's slab formula (EXACT) reads o.
-    YRT_HD void restore_world() {
-#if YRT_RESTORE_OD
-        o = wo; d = wd;
-#else
-        if (EXACT) o = wo;
-#endif
-        sr = wsr;
-    }
-    YRT_HD const vec3& world_o() const { return wo; }
-    YRT_HD const vec3& world_d() const { return wd; }
-#endif
     vec3 o, d;            // ray in the current space (world, or local to instance `si`)
     slabray sr;
     float tmin, tmax;     // tmin is copied unchanged into every instance space (vmath.h:277)
     int cur, si, kind;
     int* sp;              // next free stack slot; stack[0] holds a YRT_REF_DONE guard, so a pop needs no emptiness test
-#if YRT_STACK_TOP_REG
-    int tos;              // top of the stack (the entries below it are in memory)
-#endif
     bool top, found;
     HitRec hit;
 
@@ -186,114 +124,181 @@ struct Tracer {
         hit.si = -1; hit.prim = -1; hit.w1 = hit.w2 = 0.f; hit.dist = 0.f;
         o = wray.o; d = wray.d;
         sr = make_slabray(o, EXACT ? inv3(d) : inv3_slab(d));
-        save_world();
+        wo = o; wd = d; wsr = sr;
         tmin = wray.tmin; tmax = wray.tmax;
-        stack[0] = YRT_REF_DONE; sp = stack + 1;
-#if YRT_STACK_TOP_REG
-        tos = YRT_REF_DONE;   // logical stack = [guard in memory, DONE in the register]: the last pop reads the guard, never below it
-#endif
+        sp = stack;
+        push(YRT_REF_DONE, -FLT_MAX);
         si = -1; kind = 0; top = true; found = false;
         cur = sv.n_active_instances > 0 ? sv.tlas_root : YRT_REF_DONE;
     }
 
-    // pop the next reference.  Leaving an instance (sentinel) restores the world-space ray and pops once more: only one
-    // sentinel is ever on the stack (instances are entered from the top level only), and the guard below everything
-    // (YRT_REF_DONE) ends the traversal without an emptiness test.
-    YRT_HD int take() {
-#if YRT_STACK_TOP_REG
-        int r = tos;
-        tos = *--sp;
-        return r;
-#else
-        return *--sp;
-#endif
-    }
-    YRT_HD void push(int ref) {
-#if YRT_STACK_TOP_REG
-        *sp++ = tos;
-        tos = ref;
-#else
-        *sp++ = ref;
-#endif
-    }
+    // Stack entries.  Closest hit (YRT_POP_CULL): (reference, entry distance of its box); the pop re-applies the accept
+    // rule of the slab test with the tmax of NOW — exactly the decision the box test would take if it ran at pop time
+    // (its exit-side operands have not changed), so a postponed subtree or instance that a nearer hit has made
+    // irrelevant costs one compare instead of a visit.  Wide nodes need this more than binary ones: up to three siblings
+    // wait on the stack per visit, and instance leaves are entered straight from it.  Any hit: the reference only.
+    static constexpr bool CULL = !ANY && YRT_POP_CULL;
+    static constexpr int ENTRY = CULL ? 2 : 1;
+    YRT_HD float accept_limit() const { return EXACT ? tmax * 1.00000024f : fmaf(tmax, YRT_SLAB_ACCEPT, sr.pad); }
+
+    // pop the next reference.  Leaving an instance (sentinel) restores the world-space slab operands and pops on: only
+    // one sentinel is ever on the stack (instances are entered from the top level only), and the guard below everything
+    // (YRT_REF_DONE, entry distance -inf like the sentinel's) ends the traversal without an emptiness test.  At the top
+    // level only the slab-test operands are read (the fused test needs neither o nor d, and the instance entry
+    // transforms wo / wd), so (o, d) keep the last instance's values there; the reference's slab formula (EXACT) reads o.
     YRT_HD void pop() {
-        cur = take();
-        if (cur == YRT_REF_SENTINEL) {
+        for (;;) {
+            sp -= ENTRY;
+            cur = sp[0];
+            if (CULL && !(int_as_float(sp[1]) <= accept_limit())) continue;
+            if (cur != YRT_REF_SENTINEL) return;
             top = true;
-            restore_world();
-            cur = take();
+            if (EXACT) o = wo;
+            sr = wsr;
         }
     }
-    // a node whose visit is postponed: start pulling its record towards the SM
-    YRT_HD void prefetch_node(const SceneView& sv, int ref) {
-#if YRT_PREFETCH_PUSH && defined(__CUDA_ARCH__)
-        if (ref >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(sv.nodes + YRT_NODE_STRIDE * (size_t)ref));
-#else
-        (void)sv; (void)ref;
-#endif
+    YRT_HD void push(int ref, float e) {
+        sp[0] = ref;
+        if (CULL) sp[1] = float_as_int(e);
+        sp += ENTRY;
     }
+    YRT_HD int depth_of(const int* stack) const { return (int)(sp - stack) / ENTRY; }
 
-    // one internal node: test both child boxes against the current ray and current tmax, near child first
-    YRT_HD void visit(const SceneView& sv, int* stack, TraceCounters* ctr) {
-        float4 q0, q1, q2, q3;
-        node_load(sv.nodes, cur, q0, q1, q2, q3);
-        float e0, e1;
-        bool h0, h1;
+    // both boxes of one pair against the current ray and the current tmax
+    YRT_HD void test_pair(const float4& p0, const float4& p1, const float4& p2, bool& h0, bool& h1, float& e0, float& e1, TraceCounters* ctr) {
         if (EXACT) {
             // rays (nearly) parallel to an axis plane: |invd| is huge there and so is the per-box pad of the fused
             // test (it would accept half the scene); they take the reference's own formula on the stored box instead
             raysigns sgn = signs_of(sr.invd);
-            nodebox b0 = node_child(q0, q1, q2, 0), b1 = node_child(q0, q1, q2, 1);
+            nodebox b0 = pair_child(p0, p1, p2, 0), b1 = pair_child(p0, p1, p2, 1);
             h0 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, b0.cx - b0.hx, b0.cy - b0.hy, b0.cz - b0.hz, b0.cx + b0.hx, b0.cy + b0.hy, b0.cz + b0.hz, e0);
             h1 = intersect_check_bbox(o, sr.invd, sgn, tmin, tmax, b1.cx - b1.hx, b1.cy - b1.hy, b1.cz - b1.hz, b1.cx + b1.hx, b1.cy + b1.hy, b1.cz + b1.hz, e1);
         } else {
-            slab_test_node(sr, tmin, tmax, q0, q1, q2, h0, h1, e0, e1);
+            slab_test_pair(sr, tmin, tmax, p0, p1, p2, h0, h1, e0, e1);
         }
-        if (ctr) {   // host-side audit against the reference's own test
-            ctr->box_tests += 2;
-            if (top) ctr->tlas_box_tests += 2;
+#if !defined(__CUDA_ARCH__)
+        if (ctr) {   // host-side audit against the reference's own test on the stored box [c-h, c+h] (a superset of the true box)
             float e;
-            raysigns sgn = signs_of(sr.invd);   // the reference's test on the stored box [c-h, c+h] (a superset of the true box)
-            nodebox b0 = node_child(q0, q1, q2, 0), b1 = node_child(q0, q1, q2, 1);
-            const vec3 ao = top ? world_o() : o;   // (o is not restored at the top level)
-            bool r0 = intersect_check_bbox(ao, sr.invd, sgn, tmin, tmax, b0.cx - b0.hx, b0.cy - b0.hy, b0.cz - b0.hz, b0.cx + b0.hx, b0.cy + b0.hy, b0.cz + b0.hz, e);
-            bool r1 = intersect_check_bbox(ao, sr.invd, sgn, tmin, tmax, b1.cx - b1.hx, b1.cy - b1.hy, b1.cz - b1.hz, b1.cx + b1.hx, b1.cy + b1.hy, b1.cz + b1.hz, e);
+            raysigns sgn = signs_of(sr.invd);
+            nodebox b0 = pair_child(p0, p1, p2, 0), b1 = pair_child(p0, p1, p2, 1);
+            const vec3 ao = top ? wo : o;   // (o is not restored at the top level)
+            bool r0 = b0.hx >= 0.f && intersect_check_bbox(ao, sr.invd, sgn, tmin, tmax, b0.cx - b0.hx, b0.cy - b0.hy, b0.cz - b0.hz, b0.cx + b0.hx, b0.cy + b0.hy, b0.cz + b0.hz, e);
+            bool r1 = b1.hx >= 0.f && intersect_check_bbox(ao, sr.invd, sgn, tmin, tmax, b1.cx - b1.hx, b1.cy - b1.hy, b1.cz - b1.hz, b1.cx + b1.hx, b1.cy + b1.hy, b1.cz + b1.hz, e);
             ctr->slab_false_rejects += (r0 && !h0) + (r1 && !h1);
             ctr->slab_extra_accepts += (!r0 && h0) + (!r1 && h1);
         }
+#else
+        (void)ctr;
+#endif
+    }
+
+#if YRT_WIDE == 4
+    // One wide node: the four child boxes against the current ray and current tmax.
+    // Any hit: the entered children are taken in stored order.  Closest hit: nearest child first; the others are pushed
+    // so that they come off the stack in the order [far child of the nearest child's pair | near child of the other
+    // pair | far child of the other pair], the last two swapped if the entry distances say so — i.e. sorted by entry
+    // distance except that a pair is never split by more than one position (a tournament, not a full sort).
+    YRT_HD void visit(const SceneView& sv, int* stack, TraceCounters* ctr) {
+        const float4* n = sv.nodes + YRT_NODE_STRIDE * (size_t)cur;
+        float4 a0 = ld4(n), a1 = ld4(n + 1), a2 = ld4(n + 2), b0 = ld4(n + 3), b1 = ld4(n + 4), b2 = ld4(n + 5);
+        int c0, c1, c2, c3;
+#if YRT_PACK_REFS
+        pair_refs(a1, c0, c1);
+        pair_refs(b1, c2, c3);
+#else
+        {
+            float4 r = ld4(n + 6);
+            c0 = float_as_int(r.x); c1 = float_as_int(r.y); c2 = float_as_int(r.z); c3 = float_as_int(r.w);
+        }
+#endif
+        bool h0, h1, h2, h3;
+        float e0, e1, e2, e3;
+        test_pair(a0, a1, a2, h0, h1, e0, e1, ctr);
+        test_pair(b0, b1, b2, h2, h3, e2, e3, ctr);
+        if (ctr) {
+            ctr->node_visits++;
+            int nb = float_as_int(ld4(n + 7).x);
+            ctr->box_tests += nb;
+            if (top) ctr->tlas_box_tests += nb;
+        }
+        if (ANY && YRT_ANY_UNORDERED) {
+            // entered children in stored order: the first becomes the next node, the others wait on the stack
+            int nxt = YRT_REF_DONE;
+            bool have = false;
+            if (h3) { nxt = c3; have = true; }
+            if (h2) { if (have) push(nxt, 0.f); nxt = c2; have = true; }
+            if (h1) { if (have) push(nxt, 0.f); nxt = c1; have = true; }
+            if (h0) { if (have) push(nxt, 0.f); nxt = c0; have = true; }
+            if (ctr && depth_of(stack) > ctr->max_stack) ctr->max_stack = depth_of(stack);
+            if (have) cur = nxt; else pop();
+        } else {
+            const float inf = int_as_float(0x7f800000);
+            if (!h0) e0 = inf;
+            if (!h1) e1 = inf;
+            if (!h2) e2 = inf;
+            if (!h3) e3 = inf;
+            // tournament: winner and loser of each pair, then of the two winners
+            bool sa = e1 < e0, sb = e3 < e2;
+            int wa = sa ? c1 : c0, la = sa ? c0 : c1, wb = sb ? c3 : c2, lb = sb ? c2 : c3;
+            float ewa = fminf(e0, e1), ela = fmaxf(e0, e1), ewb = fminf(e2, e3), elb = fmaxf(e2, e3);
+            bool sf = ewb < ewa;
+            int w = sf ? wb : wa;            // nearest entered child
+            int m = sf ? wa : wb;            // winner of the other pair
+            float em = fmaxf(ewa, ewb);
+            int l1 = sf ? lb : la, l2 = sf ? la : lb;      // loser of the winner's pair, loser of the other pair
+            float el1 = sf ? elb : ela, el2 = sf ? ela : elb;
+            if (fminf(ewa, ewb) < inf) {
+                // farthest first onto the stack: l2 | (m, l1) in entry order
+                if (el2 < inf) push(l2, el2);
+                bool swap = el1 < em;      // l1 nearer than m: m goes below it
+                int x = swap ? m : l1, y = swap ? l1 : m;
+                float ex = swap ? em : el1, ey = swap ? el1 : em;
+                if (ex < inf) push(x, ex);
+                if (ey < inf) push(y, ey);
+                if (ctr && depth_of(stack) > ctr->max_stack) ctr->max_stack = depth_of(stack);
+                cur = w;
+            } else {
+                pop();
+            }
+        }
+    }
+#else
+    // one binary node: test both child boxes against the current ray and current tmax, near child first
+    YRT_HD void visit(const SceneView& sv, int* stack, TraceCounters* ctr) {
+        const float4* n = sv.nodes + YRT_NODE_STRIDE * (size_t)cur;
+        float4 q0 = ld4(n), q1 = ld4(n + 1), q2 = ld4(n + 2);
         int c0, c1;
-        node_refs(q1, q3, c0, c1);
-#if YRT_VISIT_V2
+#if YRT_PACK_REFS
+        pair_refs(q1, c0, c1);
+#else
+        {
+            float4 r = ld4(n + 3);
+            c0 = float_as_int(r.x); c1 = float_as_int(r.y);
+        }
+#endif
+        float e0, e1;
+        bool h0, h1;
+        test_pair(q0, q1, q2, h0, h1, e0, e1, ctr);
+        if (ctr) {
+            ctr->node_visits++;
+            ctr->box_tests += 2;
+            if (top) ctr->tlas_box_tests += 2;
+        }
         // one select for the next node, one predicated push when both children are entered, one branch for the pop
         if (h0 || h1) {
             int nxt = h0 ? c0 : c1;
             if (h0 && h1) {
                 bool swap = (ANY && YRT_ANY_UNORDERED) ? false : (e1 < e0);   // near child first
-                const int later = swap ? c0 : c1;
-                push(later);
-                prefetch_node(sv, later);
-                if (ctr && (int)(sp - stack) > ctr->max_stack) ctr->max_stack = (int)(sp - stack);
+                push(swap ? c0 : c1, swap ? e0 : e1);
+                if (ctr && depth_of(stack) > ctr->max_stack) ctr->max_stack = depth_of(stack);
                 if (swap) nxt = c1;
             }
             cur = nxt;
         } else {
             pop();
         }
-#else
-        if (h0 && h1) {
-            bool swap = (ANY && YRT_ANY_UNORDERED) ? false : (e1 < e0);   // near child first
-            push(swap ? c0 : c1);
-            if (ctr && (int)(sp - stack) > ctr->max_stack) ctr->max_stack = (int)(sp - stack);
-            cur = swap ? c1 : c0;
-        } else if (h0) {
-            cur = c0;
-        } else if (h1) {
-            cur = c1;
-        } else {
-            pop();
-        }
-#endif
     }
+#endif
 
     // internal nodes until the lane holds a leaf
     YRT_HD void nodes(const SceneView& sv, int* stack, TraceCounters* ctr) {
@@ -305,22 +310,21 @@ struct Tracer {
         int first = leaf_first(cur), count = leaf_count(cur);
         if (top) {
             // TLAS leaf: enter its first instance, keep the rest for later
-            if (count > 1) push(make_leaf_ref(first + 1, count - 1));
+            if (count > 1) push(make_leaf_ref(first + 1, count - 1), -FLT_MAX);
             const float4* ir = sv.inst_recs + 4 * (size_t)first;
             float4 q0, q1, q2, q3;
-            ld8(ir, q0, q1);
-            ld8(ir + 2, q2, q3);
+            q0 = ld4(ir); q1 = ld4(ir + 1); q2 = ld4(ir + 2); q3 = ld4(ir + 3);
             frame3 f;
             f.x = xyz(q0); f.y = xyz(q1); f.z = xyz(q2); f.o = xyz(q3);
-            vec3 lo = transform_point_inverse(f, world_o());   // transform_ray_inverse, scene.cpp:468
-            d = transform_direction_inverse(f, world_d());
+            vec3 lo = transform_point_inverse(f, wo);   // transform_ray_inverse, scene.cpp:468
+            d = transform_direction_inverse(f, wd);
             o = lo;
             sr = make_slabray(o, EXACT ? inv3(d) : inv3_slab(d));
             si = first;
             kind = ((unsigned)float_as_int(q3.w)) >> 28;
             top = false;
-            push(YRT_REF_SENTINEL);
-            if (ctr) { ctr->inst_entries++; if ((int)(sp - stack) > ctr->max_stack) ctr->max_stack = (int)(sp - stack); }
+            push(YRT_REF_SENTINEL, -FLT_MAX);
+            if (ctr) { ctr->inst_entries++; if (depth_of(stack) > ctr->max_stack) ctr->max_stack = depth_of(stack); }
             cur = float_as_int(q0.w);   // BLAS root ref of the instance's shape
         } else {
             ray3 lray;
