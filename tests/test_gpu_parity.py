@@ -412,3 +412,65 @@ def test_run_sh_configs_full_size(gpu, oracle_mod, name):
     assert st.primary_rays == cnt["primary_rays"] == w * h * 9
     assert abs(st.shadow_rays - cnt["shadow_rays"]) <= 1e-5 * cnt["shadow_rays"] + 4
     assert abs(st.reflection_rays - cnt["reflection_rays"]) <= 1e-5 * cnt["reflection_rays"] + 4
+
+
+def _full_golden(name):
+    import os
+    from conftest import GOLDEN
+    with np.load(os.path.join(GOLDEN, name + ".ref.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def test_target_config_on_the_real_scene_1080p_16spp(gpu, oracle_mod):
+    """BASELINE target: the reference's own in/instance10000_pointlight at 1920x1080.  (a) closest-hit (instance, element) of
+    all 2 073 600 primary rays at 1 spp against ref_probe's dump, distances bit-identical on equal ids; (b) the 16 spp frame,
+    through the reference's tonemap, against the PNG the unmodified reference CLI wrote (`-r 1080 -s 4`; SURVEY 8c digest
+    22bc1ac0e6f98ba9): >= 99.9 % of pixels within 1/255.  Goldens: tools/make_golden_full.py."""
+    import hashlib
+    import os
+    from PIL import Image
+    from conftest import GOLDEN
+    flat, _ = load_golden("instance10000")
+    ref = _full_golden("instance10000_1080p")
+    w, h = int(ref["ids_width"]), int(ref["ids_height"])
+    assert (w, h) == (1920, 1080) == (flat.image_width(1080), 1080)
+    png = np.array(Image.open(os.path.join(GOLDEN, "instance10000_1080p_s4.png")))
+    assert hashlib.sha256(png.tobytes()).hexdigest()[:16] == "22bc1ac0e6f98ba9"
+    with gpu.Scene(flat) as scn:
+        ids, dist, _ = scn.trace_primary(w, h, 1)
+        img, st = scn.render(w, h, 4, 0.1)
+        ldr_dev, _ = scn.render_ldr(w, h, 4, 0.1)
+    same = (ids[:, 0] == ref["inst"]) & (ids[:, 2] == ref["ei"])
+    assert same.mean() >= ID_BAR, (same.mean(), int((~same).sum()))
+    assert np.array_equal(dist[same].view(np.uint32), ref["dist"][same].view(np.uint32))
+    assert st.primary_rays == w * h * 16 and st.reflection_rays == 0 and st.truncated_paths == 0
+    assert st.total_rays == 132710394          # SURVEY 8a: 33 177 600 primary + 99 532 794 shadow rays per frame
+    within1, ident, mx = ldr_stats(oracle_mod.tonemap(img), png)
+    assert within1 >= PIXEL_BAR, (within1, ident, mx)
+    assert ident >= 0.999, (within1, ident, mx)
+    within1d, identd, mxd = ldr_stats(ldr_dev, png)      # device tonemap (yrt_render_ldr) against the same file
+    assert within1d >= PIXEL_BAR, (within1d, identd, mxd)
+
+
+def test_lines_config4_full_size(gpu, oracle_mod):
+    """BASELINE configs[3] at the size SURVEY 8d specifies: 2 x 65 536 hairs x 8 segments (1 048 576 line elements in two
+    bottom-level trees), 1280x720: ids of every primary ray at 1 spp and the 9 spp frame against the unmodified reference
+    (ref_probe dump / CLI PNG of the same generated scene, tools/make_golden_full.py)."""
+    import os
+    from PIL import Image
+    from conftest import GOLDEN
+    flat = synth.lines_config4().flat()
+    ref = _full_golden("lines_config4")
+    w, h = int(ref["ids_width"]), int(ref["ids_height"])
+    assert (w, h) == (1280, 720) and flat.n_elements > 1048576
+    png = np.array(Image.open(os.path.join(GOLDEN, "lines_config4_720p_s3.png")))
+    with gpu.Scene(flat) as scn:
+        info = scn.info()
+        ids, dist, _ = scn.trace_primary(w, h, 1)
+        img, st = scn.render(w, h, 3, 0.1)
+    same = (ids[:, 0] == ref["inst"]) & (ids[:, 2] == ref["ei"])
+    assert same.mean() >= ID_BAR, (same.mean(), int((~same).sum()), info)
+    assert np.array_equal(dist[same].view(np.uint32), ref["dist"][same].view(np.uint32))
+    within1, ident, mx = ldr_stats(oracle_mod.tonemap(img), png)
+    assert within1 >= PIXEL_BAR, (within1, ident, mx)
+    assert st.primary_rays == w * h * 9 and st.shadow_rays % 2 == 0

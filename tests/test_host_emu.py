@@ -117,3 +117,21 @@ def test_stack_need_bounds_the_stack_actually_used():
             es = _emu.EmuScene(flat, variant=variant)
             ids, dist, uv, ctr = es.trace_primary(128, 72, 1)
             assert ctr[3] <= es.info()[6] <= 128, (ctr[3], es.info())
+
+
+@pytest.mark.parametrize("case", ["instance10000_1080p", "lines_config4"])
+def test_emulated_device_hit_ids_full_size(case):
+    """The device traversal code (host build) on the two full-size goldens of the unmodified reference: the real
+    instance10000 scene at 1920x1080 (2 073 600 primary rays) and the 1 048 576-segment lines config at 1280x720."""
+    import os
+    from conftest import GOLDEN
+    from yocto_raytracing_b200 import synth
+    flat = load_golden("instance10000")[0] if case == "instance10000_1080p" else synth.lines_config4().flat()
+    with np.load(os.path.join(GOLDEN, case + ".ref.npz")) as z:
+        inst, ei, dist, w, h = z["inst"], z["ei"], z["dist"], int(z["ids_width"]), int(z["ids_height"])
+    es = _emu.EmuScene(flat)
+    ids, d, uv, ctr = es.trace_primary(w, h, 1)
+    same = (ids[:, 0] == inst) & (ids[:, 2] == ei)
+    assert same.mean() >= 0.9999, (same.mean(), int((~same).sum()))
+    assert np.array_equal(d[same].view(np.uint32), dist[same].view(np.uint32))
+    assert ctr[4] == 0 and ctr[3] <= es.info()[6] <= 128

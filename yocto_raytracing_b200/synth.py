@@ -361,6 +361,60 @@ def hair_scene(n_hairs: int = 4096, segments: int = 8, seed: int = 1234) -> Synt
     return sc
 
 
+def _hair_shape(name: str, n_hairs: int, segments: int, rng: np.random.RandomState) -> Shape:
+    """n_hairs polylines of `segments` segments (length 0.3) rooted on a Fibonacci lattice of the unit sphere; direction =
+    normal + seeded noise, bending down along the hair; radius 0.001 root -> 0.0005 tip; every vertex carries a texcoord."""
+    k = np.arange(n_hairs) + 0.5
+    phi = np.arccos(1 - 2 * k / n_hairs)
+    theta = math.pi * (1 + 5 ** 0.5) * k
+    roots = np.stack([np.cos(theta) * np.sin(phi), np.cos(phi), np.sin(theta) * np.sin(phi)], -1)
+    d = roots + 0.35 * rng.normal(size=roots.shape)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p = roots.copy()
+    pos = np.empty((n_hairs, segments + 1, 3))
+    tan = np.empty((n_hairs, segments + 1, 3))
+    step = 0.3 / segments
+    for s_ in range(segments + 1):
+        pos[:, s_] = p
+        tan[:, s_] = d
+        d = d + np.array([0, -step, 0]) + 0.05 * rng.normal(size=d.shape)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        p = p + d * step
+    hs, ss = np.meshgrid(np.arange(n_hairs), np.arange(segments + 1), indexing="ij")
+    uv = np.stack([hs / n_hairs, ss / segments], -1)
+    rad = 0.001 + (0.0005 - 0.001) * ss / segments
+    base = (hs * (segments + 1) + ss)[:, :-1].reshape(-1)
+    lines = np.stack([base, base + 1], 1)
+    return Shape(name, LINES, pos.reshape(-1, 3).astype(F), tan.reshape(-1, 3).astype(F), lines.astype(np.int32), "lines",
+                 uv.reshape(-1, 2).astype(F), rad.reshape(-1).astype(F))
+
+
+def lines_config4(n_hairs: int = 65536, segments: int = 8, seed: int = 1234, texture: Optional[np.ndarray] = None) -> SynthScene:
+    """SURVEY 8d config 4 (BASELINE.json configs[3]) at its specified size — the reference's in/lines_pointlight has its
+    materials and texture but no OBJ, so the scene is synthetic: camera and lights of simple_pointlight (cam: fovy 0.261799,
+    focus 10.4403 at (0, 4, 10); two point lights Ke 100 at (+-1.4, 8, 6)), a 64x64-quad floor over [-20, 20]^2 with a grid
+    texture, two unit spheres at x = +-1.25, y = 1 (material `interior`), each with its OWN n_hairs hairs of 8 segments
+    (MT19937 seeded 1234): 2 x 65 536 x 8 = 1 048 576 line elements in two BLAS of 524 288 — the one config whose
+    bottom-level trees, not the instance tree, are large."""
+    rng = np.random.RandomState(seed)
+    sc = SynthScene(name="lines_config4")
+    sc.textures["grid.png"] = texture if texture is not None else checker_texture(512, 16)
+    sc.materials += [Material("floor_txt", kd=(1, 1, 1), ns=1, map_kd="grid.png"), Material("lines", kd=(0.2, 0.2, 0.2), ns=1),
+                     Material("interior", kd=(0.2, 0.2, 0.2), ns=1), Material("pointlight", kd=(0, 0, 0), ke=(100, 100, 100), ns=1)]
+    sc.shapes.append(grid_floor("floor", "floor_txt", 20.0, 64, 40.0))
+    sc.shapes.append(uv_sphere("interior", "interior", 64, 32))
+    sc.shapes.append(_hair_shape("hair_l", n_hairs, segments, rng))
+    sc.shapes.append(_hair_shape("hair_r", n_hairs, segments, rng))
+    sc.shapes.append(point_light("pointlight01", "pointlight", with_uv=True))
+    sc.shapes.append(point_light("pointlight02", "pointlight", with_uv=True))
+    sc.instances += [("floor", 0, translation_frame((0, 0, 0))),
+                     ("sphere_l", 1, translation_frame((-1.25, 1, 0))), ("sphere_r", 1, translation_frame((1.25, 1, 0))),
+                     ("hair_l", 2, translation_frame((-1.25, 1, 0))), ("hair_r", 3, translation_frame((1.25, 1, 0))),
+                     ("pointlight01", 4, translation_frame((1.4, 8.0, 6.0))), ("pointlight02", 5, translation_frame((-1.4, 8.0, 6.0)))]
+    sc.camera = np.array([1, 0, 0, 0, 0.957826, -0.287348, 0, 0.287348, 0.957826, 0, 4, 10, 0.261799, 1.77778, 0, 10.4403], F)
+    return sc
+
+
 # ---- small mixed scene for edge cases ------------------------------------------------------------------
 def mixed_scene(seed: int = 7, n_objects: int = 24, reflective_floor: bool = True, textured: bool = True) -> SynthScene:
     """Small scene touching every code path: textured + mirror floor (recursion), rotated instances of
