@@ -22,14 +22,24 @@ REFFLAGS := -std=c++14 -O3 -DNDEBUG -DYOBJ_NO_IMAGE -DYGLTF_NO_IMAGE -DYSCN_NO_I
 REFSRC   := image scene yocto_scn yocto_obj yocto_gltf
 REFOBJ   := $(addprefix oracle/_ref/,$(addsuffix .o,$(REFSRC)))
 
-.PHONY: all lib oracle ref hostemu clean
-all: lib oracle hostemu $(if $(wildcard $(REF)/src/raytrace.cpp),ref)
+.PHONY: all lib counters oracle ref hostemu clean
+all: lib counters oracle hostemu $(if $(wildcard $(REF)/src/raytrace.cpp),ref)
 
 lib: $(LIB)
 build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
 $(LIB): build/yrt_host.o build/yrt_build.o build/yrt_render.o build/yrt_api.o build/yrt_png.o
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lz
+
+# the same library with per-ray work counters in the traversal kernels (-DYRT_COUNTERS=1): used by tools/frame_counters.py
+# (bench.py runs it in a separate process after its timed region) — never the timed build
+COUNTERS_LIB := yocto_raytracing_b200/libyrt_b200_counters.so
+counters: $(COUNTERS_LIB)
+build/ctr_%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -DYRT_COUNTERS=1 -c $< -o $@
+$(COUNTERS_LIB): build/ctr_yrt_host.o build/ctr_yrt_build.o build/ctr_yrt_render.o build/ctr_yrt_api.o build/ctr_yrt_png.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lz
 
 oracle: oracle/liboracle.so
@@ -67,4 +77,4 @@ bin/yrt_flatten: $(HOST)/yrt_flatten_tool.cpp $(HOST)/yrt_flatten.cpp $(HOST)/yr
 	$(CXX) $(REFFLAGS) -I$(REF)/src -I$(HOST) -o $@ $(HOST)/yrt_flatten_tool.cpp $(HOST)/yrt_flatten.cpp $(REFOBJ)
 
 clean:
-	rm -rf build bin oracle/_ref oracle/liboracle.so tests/host_emu/libyrt_hostemu*.so $(LIB)
+	rm -rf build bin oracle/_ref oracle/liboracle.so tests/host_emu/libyrt_hostemu*.so $(LIB) $(COUNTERS_LIB)

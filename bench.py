@@ -7,9 +7,13 @@ an instance10000_pointlight-shaped scene (10 004 instances of 14 shapes, 3 point
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...     # the reference's own CPU implementation on this box's host cores
+    python bench.py --config refl            # another BASELINE config as the timed workload (simple|basic|refl|lines|instance_real)
 
 A step is one frame.  Rays are counted by reference semantics (intersect_first + intersect_any calls the
-reference would make: primary + reflection + shadow).  One JSON line on stdout (rank 0).
+reference would make: primary + reflection + shadow).  One JSON line on stdout (rank 0).  At N = 1 the line also
+carries `other_configs` (BASELINE configs 1-4: Mrays/s, per-kernel split and ray counts of a few frames each) and the
+roofline record is built from the kernels' OWN per-ray counters (a -DYRT_COUNTERS=1 build run in a separate process
+after the timed region).
 """
 import argparse
 import json
@@ -26,13 +30,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-# per-ray algorithmic work of the reference on this config (measured with counters in the
-# reference's BVH): 2.84 KB of node/primitive/instance bytes and 2.45 kflop per ray
-ALG_BYTES_PER_RAY = 2840.0
-ALG_FLOPS_PER_RAY = 2450.0
-# dram bytes of one k_trace_any_lights launch (whole 1080p/16spp frame) from the ncu --set full capture in profiles/
-NCU_DRAM_BYTES_PER_ANY_LAUNCH = 1.1833e9   # profiles/r1j_final_ncu_summary.txt: 1.0755 GB read + 0.1078 GB write (algorithmic: 33.2 M hits x 35 B)
+# per-ray algorithmic work of the REFERENCE's BVH on the headline config (measured with counters at
+# src/scene.cpp:371,229,468): 2.84 KB of node/primitive/instance bytes and 2.45 kflop per ray, averaged over primary and shadow rays
+REF_BYTES_PER_RAY = 2840.0
+REF_FLOPS_PER_RAY = 2450.0
 FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+COUNTERS_LIB = os.path.join(ROOT, "yocto_raytracing_b200", "libyrt_b200_counters.so")
+NCU_KERNELS = os.path.join(ROOT, "profiles", "r2_ncu_kernels.json")   # tools/ncu_summary.py --json of the committed ncu capture
 
 
 def parse():
@@ -41,22 +45,22 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--resolution", type=int, default=1080)
-    ap.add_argument("--samples", type=int, default=4)
-    ap.add_argument("--n-side", type=int, default=100, help="instances per grid side (100 -> 10 004 instances)")
+    ap.add_argument("--config", default="instance", help="timed workload: instance (headline) | instance_real | simple | basic | refl | lines")
+    ap.add_argument("--resolution", type=int, default=0, help="0 = the config's own (1080 for the headline)")
+    ap.add_argument("--samples", type=int, default=0, help="0 = the config's own (4 for the headline)")
     ap.add_argument("--tile-rows", type=int, default=1, help="rows per interleaved tile (1: rows r, r+N, r+2N, ...)")
     ap.add_argument("--gather", default="ipc", choices=["ipc", "nccl"],
-                    help="multi-GPU framebuffer exchange: ipc = every rank's resolve kernel stores its rows into rank 0's frame over "
-                         "NVLink peer memory + 1-element all-reduce; nccl = packed rows, NCCL gather, unpack on rank 0")
+                    help="device-resident multi-GPU frame (the `value` measurement): ipc = every rank's resolve kernel stores its rows into rank "
+                         "0's frame over NVLink peer memory, bracketed by two 1-element all-reduces; nccl = packed rows, NCCL gather, unpack on rank 0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip other_configs and the device-counter pass (N = 1 extras)")
     ap.add_argument("--cpu-baseline-resolution", type=int, default=0, help="0 = sized for ~15 s of CPU work")
     return ap.parse_args()
 
 
-def workload_name(args, flat):
-    w = flat.image_width(args.resolution)
-    return (f"instance10000_pointlight-shaped synthetic scene ({flat.n_instances} instances, {flat.n_shapes} shapes, "
-            f"{flat.n_elements} elements, {len(flat.light_instances())} point lights), {w}x{args.resolution}, {args.samples ** 2} spp")
+def workload_name(desc, flat, w, h, s):
+    return (f"{desc}: {flat.n_instances} instances, {flat.n_shapes} shapes, {flat.n_elements} elements, "
+            f"{len(flat.light_instances())} point lights, {w}x{h}, {s * s} spp")
 
 
 # ---- clocks during the timed region -----------------------------------------------------------------
@@ -104,20 +108,16 @@ class ClockSampler:
 
 
 # ---- the reference's CPU implementation, bounded sample ------------------------------------------------
-def cpu_reference_sample(synth_scene, flat, resolution, samples, ray_counter):
+def cpu_reference_sample(obj_path, flat, resolution, samples, rays):
     """Time the reference's raytrace() on this box's host cores for one bounded frame.  Prefers the UNMODIFIED
     reference (oracle/_ref/ref_probe, compiled from /root/reference/src; single-threaded like the reference),
-    else the C port (oracle/yrt_oracle.c) on one thread.  ray_counter(resolution, samples) -> rays by
-    reference semantics."""
+    else the C port (oracle/yrt_oracle.c) on one thread.  rays = ray count of that frame by reference semantics."""
     import ref_probe
     w = flat.image_width(resolution)
     cores_total = os.cpu_count() or 1
-    if ref_probe.available():
-        with tempfile.TemporaryDirectory() as td:
-            obj = synth_scene.write_obj(td)
-            _, info = ref_probe.image(obj, resolution, samples, 0.1)
+    if ref_probe.available() and obj_path:
+        _, info = ref_probe.image(obj_path, resolution, samples, 0.1)
         secs, kind = float(info["raytrace_s"]), "reference"
-        rays = ray_counter(resolution, samples)
     else:
         from oracle import oracle
         o = oracle.OracleScene(flat)
@@ -132,47 +132,67 @@ def cpu_reference_sample(synth_scene, flat, resolution, samples, ray_counter):
 
 
 def oracle_ray_count(flat, resolution, samples):
-    """Ray count by reference semantics without a GPU and without rendering: for this scene family every hit
-    casts n_lights shadow rays and nothing reflects; hits come from the C oracle's closest-hit pass."""
+    """Ray count by reference semantics without a GPU: the C oracle's own counters for that frame (all host cores)."""
     from oracle import oracle
     o = oracle.OracleScene(flat)
     w = flat.image_width(resolution)
-    ids, _, _ = o.trace_primary(w, resolution, samples)
-    hits = int((ids[:, 0] >= 0).sum())
-    return ids.shape[0] + hits * len(flat.light_instances())
+    if not any(flat.arrays["mat_kr"] > 0):      # nothing reflects: every hit casts n_lights shadow rays, the closest-hit pass gives the hits
+        ids, _, _ = o.trace_primary(w, resolution, samples)
+        hits = int((ids[:, 0] >= 0).sum())
+        return ids.shape[0] + hits * len(flat.light_instances())
+    _, cnt = o.render(w, resolution, samples, 0.1, threads=os.cpu_count() or 1)
+    return cnt["primary_rays"] + cnt["reflection_rays"] + cnt["shadow_rays"]
 
 
-def sample_resolution_for(seconds, mrays_per_s=0.16, n_lights=3):
+def sample_resolution_for(seconds, mrays_per_s, rays_per_pixel):
     rays = seconds * mrays_per_s * 1e6
-    r = int((rays / ((1 + n_lights) * 16.0 / 9.0)) ** 0.5)
+    r = int((rays / (rays_per_pixel * 16.0 / 9.0)) ** 0.5)
     return max(36, min(1080, r - r % 2))
+
+
+def headline_scene_and_obj(args, need_obj):
+    """(FlatScene, res, samples, description, obj path | None).  The OBJ (the reference's own input format) is only written
+    for the CPU arm; synthetic configs are written from their generator, the reference's own scenes do not travel."""
+    from yocto_raytracing_b200 import configs, synth
+    flat, res, smp, desc = configs.load(args.config)
+    obj = None
+    if need_obj:
+        sc = {"instance": lambda: synth.instance_grid_scene(100), "lines": synth.lines_config4}.get(args.config)
+        if sc is not None:
+            td = tempfile.mkdtemp(prefix="yrt_bench_")
+            obj = sc().write_obj(td)
+    return flat, args.resolution or res, args.samples or smp, desc, obj
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0      # one CPU arm per job: rank 0 alone runs it
-    from yocto_raytracing_b200 import synth
-    sc = synth.instance_grid_scene(args.n_side)
-    flat = sc.flat()
+    flat, res_full, smp_full, desc, obj = headline_scene_and_obj(args, True)
+    nl = len(flat.light_instances())
     total = max(1, args.steps + args.warmup)
-    res = args.cpu_baseline_resolution or sample_resolution_for(min(20.0, 150.0 / total))
+    budget = min(20.0, 150.0 / total)
+    # size the bounded sample from a measured rate (a 64-row probe frame), not from a guess
+    probe_rays = oracle_ray_count(flat, 64, 1)
+    probe = cpu_reference_sample(obj, flat, 64, 1, probe_rays)
+    res = args.cpu_baseline_resolution or min(res_full, sample_resolution_for(budget, probe["value"], 1 + nl))
     rays = oracle_ray_count(flat, res, 1)
     times, last = [], None
     for i in range(total):
-        last = cpu_reference_sample(sc, flat, res, 1, lambda r, s: rays)
+        last = cpu_reference_sample(obj, flat, res, 1, rays)
         if i >= args.warmup:
             times.append(last["seconds"])
     secs = float(np.mean(times))
     value = rays / secs / 1e6
-    w = flat.image_width(args.resolution)
-    full_rays = None
+    w_full = flat.image_width(res_full)
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args, flat), "step": f"bounded sample per step: one frame of the same scene at "
-                   f"{flat.image_width(res)}x{res}, 1 spp ({rays} rays); Mrays/s is resolution-independent for this path"},
+        "config": {"workload": workload_name(desc, flat, w_full, res_full, smp_full),
+                   "step": f"BOUNDED SAMPLE of that workload per step: one frame of the same scene at {flat.image_width(res)}x{res}, 1 spp ({rays} rays, "
+                           f"sized from a measured {probe['value']:.3f} Mrays/s probe for ~{budget:.0f} s per step); the metric is a rate (rays/s) and the "
+                           f"reference's cost per ray does not depend on resolution or spp for this path (same rays, same trees)"},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": 1, "kind": last["kind"], "host_cores_total": last["host_cores_total"],
                          "sample": last["sample"]},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -182,13 +202,48 @@ def run_reference(args):
     return 0
 
 
+# ---- helpers of the B200 arm --------------------------------------------------------------------------------
+def time_config(y, name, frames=5, warm=2):
+    """A few frames of another BASELINE config through Scene.render (device-timed by the library's own CUDA events)."""
+    from yocto_raytracing_b200 import configs
+    flat, res, smp, desc = configs.load(name)
+    w = flat.image_width(res)
+    with y.Scene(flat) as scn:
+        info = scn.info()
+        for _ in range(warm):
+            scn.render(w, res, smp, 0.1)
+        st = []
+        for _ in range(frames):
+            _, s = scn.render(w, res, smp, 0.1)
+            st.append(s.as_dict())
+    med = lambda k: float(np.median([s[k] for s in st]))
+    rays = st[-1]["primary_rays"] + st[-1]["reflection_rays"] + st[-1]["shadow_rays"]
+    ms = med("ms_total")
+    return {"workload": workload_name(desc, flat, w, res, smp), "ms_per_frame": ms, "mrays_s": rays / ms / 1e3,
+            "rays": {"primary": st[-1]["primary_rays"], "reflection": st[-1]["reflection_rays"], "shadow": st[-1]["shadow_rays"]},
+            "ms_by_kernel": {"trace_closest": med("ms_trace_closest"), "trace_any": med("ms_trace_any"), "shade": med("ms_shade"), "resolve": med("ms_other")},
+            "launches_per_frame": st[-1]["launches"], "max_depth": st[-1]["max_depth"], "truncated_paths": st[-1]["truncated_paths"],
+            "timing": f"median of {frames} frames after {warm} warm-up frames, CUDA events inside yrt_render", "lbvh": info}
+
+
+def device_counters(config):
+    """Per-ray work of the shipped kernels from the -DYRT_COUNTERS=1 build of the library, in a separate process."""
+    if not os.path.exists(COUNTERS_LIB):
+        return {"unavailable": "libyrt_b200_counters.so not built (make counters)"}
+    env = dict(os.environ, YRT_B200_LIB=COUNTERS_LIB)
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "frame_counters.py"), "--config", config], env=env, capture_output=True, text=True, timeout=300)
+        return json.loads(p.stdout.strip().splitlines()[-1])
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": f"counter pass failed: {e}"}
+
+
 # ---- the B200 arm -----------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
     import torch.distributed as dist
     import yocto_raytracing_b200 as y
     from yocto_raytracing_b200 import distributed as D
-    from yocto_raytracing_b200 import synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -201,13 +256,15 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     y.init_device(local)
 
-    sc = synth.instance_grid_scene(args.n_side)
-    flat = sc.flat()
-    W, H, S = flat.image_width(args.resolution), args.resolution, args.samples
+    flat, H, S, desc, obj = headline_scene_and_obj(args, rank == 0 and not multi and not args.no_cpu_baseline)
+    W = flat.image_width(H)
     t_up = time.perf_counter()
     scene = y.Scene(flat)           # validate + upload + GPU LBVH build (reported separately, not in the timed region)
     info = scene.info()
     info["scene_create_ms_wall"] = round((time.perf_counter() - t_up) * 1e3, 3)
+    t_up = time.perf_counter()
+    y.Scene(flat).close()           # a second creation in the same process: no first-use costs (module load, arena growth)
+    info["scene_create_ms_wall_second"] = round((time.perf_counter() - t_up) * 1e3, 3)
     dev = torch.device("cuda", local)
     tr = args.tile_rows if multi else H
 
@@ -272,10 +329,10 @@ def run_b200(args):
         for key in ("ms_trace_closest", "ms_trace_any", "ms_shade", "ms_other", "n_closest", "n_any", "n_shade", "n_other"):
             per_frame[key] = getattr(k3, key) / 3.0
         kernel_timing = "single-pipeline pass of 3 frames right after the timed region (in the timed region two pipelines overlap kernels)"
-    stats_all = [per_frame]
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     rays_local = float(tot_stats.primary_rays + tot_stats.reflection_rays + tot_stats.shadow_rays)
-    tot = torch.tensor([rays_local, float(tot_stats.launches)], device=dev, dtype=torch.float64)
+    tot = torch.tensor([rays_local, float(tot_stats.launches), float(tot_stats.primary_rays), float(tot_stats.reflection_rays), float(tot_stats.shadow_rays)],
+                       device=dev, dtype=torch.float64)
     if multi:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -292,16 +349,40 @@ def run_b200(args):
     ms_total = float(ms.item())
     rays_total, launches = float(tot[0].item()), int(tot[1].item())
     if multi:
-        launches += args.steps * (world if shared is not None else world + 1)      # + the exchange: all-reduce per rank / NCCL gather + unpack kernels
+        launches += args.steps * (2 * world if shared is not None else world + 1)      # + the exchange: two all-reduces per rank / NCCL gather + unpack kernels
     value = rays_total / (ms_total * 1e-3) / 1e6
 
     # ---- end to end through the public API with HOST buffers (`e2e`) ----
-    pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
-    host_np = pinned.numpy() if rank == 0 else None
+    # N = 1: Scene.render -> yrt_render (camera in, host framebuffer out).  N > 1: every rank renders its rows and copies them
+    # itself into ONE host frame shared by the ranks (POSIX shared memory, page-locked by every rank): N PCIe links at once.
+    host_frame, e2e_api = None, "Scene.render -> yrt_render (host framebuffer out)"
+    pinned = host_np = None
+    if multi:
+        ok = torch.ones(1, device=dev)
+        try:
+            host_frame = D.SharedHostFrame(W, H)
+            if not host_frame._pinned:
+                print(f"[bench] rank {rank}: cudaHostRegister of the shared host frame failed; copies are staged", file=sys.stderr)
+        except Exception as e:      # noqa: BLE001
+            ok.zero_()
+            print(f"[bench] rank {rank}: shared host frame unavailable ({e}); e2e falls back to a D2H copy on rank 0", file=sys.stderr)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            host_frame = None
+        if host_frame is not None:
+            e2e_api = "distributed.SharedHostFrame.render: yrt_render_rows_to_host on every rank into one shared page-locked host frame (one pitched D2H copy per rank, one barrier)"
+        else:
+            pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+            e2e_api = "device-resident gather + D2H on rank 0"
+    else:
+        pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+        host_np = pinned.numpy()
 
     def frame_e2e():
         if not multi:
-            scene.render(W, H, S, 0.1, out=host_np, want_stats=False)      # yrt_render: camera in, host framebuffer out
+            scene.render(W, H, S, 0.1, out=host_np, want_stats=False)
+        elif host_frame is not None:
+            host_frame.render(scene, S, 0.1, tr, False)
         else:
             full, _ = frame(False)
             if rank == 0:
@@ -319,79 +400,134 @@ def run_b200(args):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = rays_total / float(dt.item()) / 1e6
 
+    # ---- N > 1: is the frame the N GPUs produced the frame one GPU produces?  (bitwise; outside the timed regions) ----
+    frame_check = None
+    if multi:
+        full, _ = frame(False)
+        barrier()
+        if rank == 0:
+            single, _ = scene.render(W, H, S, 0.1, want_stats=False)           # rank 0 alone, whole frame
+            dev_ok = bool(np.array_equal(full.cpu().numpy().view(np.uint32), single.view(np.uint32)))
+            host_ok = bool(np.array_equal(host_frame.array.view(np.uint32), single.view(np.uint32))) if host_frame is not None else None
+            frame_check = {"device_gathered_frame": dev_ok, "shared_host_frame": host_ok, "compared": "bitwise, all float32 words of the frame, after the timed regions"}
+        dist.barrier()
+    if host_frame is not None:
+        host_frame.close()
+
     if rank != 0:
         if multi:
             dist.barrier()
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (k_trace_any_lights: 75 % of the rays), rank 0 ----
+    # ---- roofline (rank 0) ----
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         hbm_peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
-    any_ms = float(np.mean([s["ms_trace_any"] for s in stats_all]))
-    any_n = max(1, int(round(np.mean([s["n_any"] for s in stats_all]))))
-    closest_ms = float(np.mean([s["ms_trace_closest"] for s in stats_all]))
-    shade_ms = float(np.mean([s["ms_shade"] for s in stats_all]))
-    other_ms = float(np.mean([s["ms_other"] for s in stats_all]))
-    shadow_per_frame = float(np.mean([s["shadow_rays"] for s in stats_all]))
-    primary_per_frame = float(np.mean([s["primary_rays"] for s in stats_all]))
-    any_launch_ms = any_ms / any_n
-    rays_per_launch = shadow_per_frame / any_n
+    any_ms, any_n = float(per_frame["ms_trace_any"]), max(1, int(round(per_frame["n_any"])))
+    closest_ms, closest_n = float(per_frame["ms_trace_closest"]), max(1, int(round(per_frame["n_closest"])))
+    shade_ms, other_ms = float(per_frame["ms_shade"]), float(per_frame["ms_other"])
+    # rays of rank 0's share per frame
+    shadow_pf, primary_pf, refl_pf = float(per_frame["shadow_rays"]), float(per_frame["primary_rays"]), float(per_frame["reflection_rays"])
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    # this path is bound by FP32 issue and by L1/L2 node fetch, NOT by HBM or tensor cores, so the
-    # roofline is stated against the FP32 pipe: algorithmic flops = 2.45 kflop per ray (the reference's own
-    # box/triangle/transform counts) over 148 SMs x 128 lanes x 2 flop x the SM clock seen during the run.
-    # Exact (unfused) arithmetic in the primitive tests and min/max/select-heavy slab tests cap what is reachable.
-    fp32_peak_tflops = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    achieved_tflops = rays_per_launch * ALG_FLOPS_PER_RAY / (any_launch_ms * 1e-3) / 1e12
-    cache_gbs = rays_per_launch * ALG_BYTES_PER_RAY / (any_launch_ms * 1e-3) / 1e9
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12      # TFLOP/s, FMA = 2
+    ctr = None if (multi or args.no_extras) else device_counters(args.config)
+    ncu = json.load(open(NCU_KERNELS)) if os.path.exists(NCU_KERNELS) else None
+
+    def kernel_roof(cls, rays, ms_):
+        """achieved flop/s and L1 bytes/s of one kernel class from its OWN counters (None without the counter pass)."""
+        c = (ctr or {}).get(cls)
+        if not c or not ms_:
+            return None
+        tf = rays * c["flops_per_ray"] / (ms_ * 1e-3) / 1e12
+        return {"rays_per_frame": rays, "ms_per_frame": ms_, "node_visits_per_ray": c["node_visits_per_ray"], "box_tests_per_ray": c["box_tests_per_ray"],
+                "element_tests_per_ray": c["element_tests_per_ray"], "instance_entries_per_ray": c["instance_entries_per_ray"],
+                "flops_per_ray": c["flops_per_ray"], "l1_bytes_per_ray": c["l1_bytes_per_ray"],
+                "achieved_tflops": tf, "frac_of_fp32_peak": tf / fp32_peak,
+                "l1_gbs": rays * c["l1_bytes_per_ray"] / (ms_ * 1e-3) / 1e9}
+    own_any = kernel_roof("shadow_rays", shadow_pf, any_ms)
+    own_closest = kernel_roof("camera_rays", primary_pf, closest_ms) if refl_pf == 0 else None
+    frame_ms = ms_total / args.steps
+    # headline record: the dominant kernel (k_trace_any_lights).  `achieved` = the kernel's OWN algorithmic flops (device
+    # counters x the unit costs of SURVEY 8d) when the counter pass ran, else the reference-BVH figure, labelled as such
+    if own_any:
+        achieved, flops_src = own_any["achieved_tflops"], "own per-ray counters (-DYRT_COUNTERS=1 build, one extra frame outside the timed region) x SURVEY 8d unit costs (26 flop/box test, 54/element test, 43/instance entry)"
+        flops_per_ray = own_any["flops_per_ray"]
+    else:
+        achieved = (shadow_pf / any_n) * REF_FLOPS_PER_RAY / (any_ms / any_n * 1e-3) / 1e12
+        flops_src, flops_per_ray = "REFERENCE-BVH work per ray (SURVEY 8d, 2.45 kflop averaged over primary and shadow rays) — not this build's own count", REF_FLOPS_PER_RAY
     roofline = {
-        "kernel": "k_trace_any_lights", "bound": "fp32", "bound_note": "FP32 instruction issue — neither hbm nor tensor (SURVEY 8d): the 3 MB scene is cache resident and nothing is a contraction", "achieved": achieved_tflops,
-        "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,
-        "peak_source": f"148 SMs x 128 FP32 lanes x 2 flop x {sm_mhz:.0f} MHz (SM clock sampled during the timed region)",
-        "traffic": NCU_DRAM_BYTES_PER_ANY_LAUNCH, "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/",
-        "launch_ms": any_launch_ms, "launch_timing": kernel_timing, "launches_per_frame": any_n, "rays_per_launch": rays_per_launch,
-        "algorithmic_flops_per_ray": ALG_FLOPS_PER_RAY, "algorithmic_bytes_per_ray": ALG_BYTES_PER_RAY,
-        "hbm": {"note": "literal bytes roofline: 2.84 KB/ray is CACHE-level (L1/L2) node+primitive traffic of the reference's traversal; "
-                        "compulsory HBM traffic is ~11 B/ray (hit record + position + visibility), so frac > 1 here only says the "
-                        "scene is cache-resident, not that HBM binds",
-                "achieved": cache_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": cache_gbs / hbm_peak, "peak_source": peak_src},
-        "kernel_share_of_step": any_ms / (ms_total / args.steps),
+        "kernel": "k_trace_any_lights", "bound": "fp32",
+        "bound_note": "FP32 instruction issue + L1 data-path wavefronts — neither hbm nor tensor (SURVEY 8d): the scene is cache resident and nothing is a contraction",
+        "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+        "algorithmic_flops_per_ray": flops_per_ray, "algorithmic_flops_source": flops_src,
+        "peak_source": f"148 SMs x 128 FP32 lanes x 2 flop x {sm_mhz:.0f} MHz (SM clock sampled during the timed region); the exact primitive tests may not fuse multiply-add, so <= 0.5 is reachable for that part",
+        "launch_ms": any_ms / any_n, "launch_timing": kernel_timing, "launches_per_frame": any_n, "rays_per_launch": shadow_pf / any_n,
+        "kernel_share_of_step": any_ms / frame_ms,
+        "traffic": (ncu or {}).get("k_trace_any_lights", {}).get("dram_bytes", None) if not multi else None,
+        "traffic_source": (f"ncu dram__bytes_read.sum + dram__bytes_write.sum of one whole-frame launch, {os.path.relpath(NCU_KERNELS, ROOT)}" if (ncu and not multi)
+                           else "not reported at N > 1 (the capture is of a whole-frame launch; a rank's launch covers 1/N of it)"),
+        "per_kernel_own_counters": {"k_trace_closest(primary)": own_closest, "k_trace_any_lights": own_any},
+        "reference_bvh_equivalent": {
+            "note": "SURVEY 8d's figure for comparison across builds: the REFERENCE's tree needs 2.45 kflop and 2.84 KB of cache-level bytes per ray (average over "
+                    "primary + shadow rays); time of the whole frame, all kernels",
+            "whole_frame_tflops": (rays_total / args.steps) * REF_FLOPS_PER_RAY / (frame_ms * 1e-3) / 1e12,
+            "whole_frame_frac": (rays_total / args.steps) * REF_FLOPS_PER_RAY / (frame_ms * 1e-3) / 1e12 / fp32_peak,
+            "any_kernel_frac": (shadow_pf * REF_FLOPS_PER_RAY / (any_ms * 1e-3) / 1e12 / fp32_peak) if any_ms else None},
+        "whole_frame": ({"tflops_own": ((primary_pf * own_closest["flops_per_ray"] + shadow_pf * own_any["flops_per_ray"]) / (per_rank_ms[0][0] * 1e-3) / 1e12),
+                         "frac_own": ((primary_pf * own_closest["flops_per_ray"] + shadow_pf * own_any["flops_per_ray"]) / (per_rank_ms[0][0] * 1e-3) / 1e12) / fp32_peak}
+                        if (own_any and own_closest) else None),
+        "ncu_roofs": ({k: {m: v[m] for m in ("issue_active_pct", "l1_lsu_wavefronts_pct", "lanes_per_instruction", "fma_pipe_pct", "alu_pipe_pct", "l1_hit_pct", "warp_instructions", "duration_ms") if m in v}
+                       for k, v in ncu.items() if isinstance(v, dict)} | {"source": os.path.relpath(NCU_KERNELS, ROOT), "note": "issue slots: 148 SMs x 4 per clock; L1 data path: 148 x 128 B per clock; percentages of those peaks, from the committed ncu --set full capture (a whole-frame launch, N = 1)"}
+                      if ncu else None),
+        "hbm": {"note": "HBM does not bind: compulsory traffic per hit is ~35 B (hit record + position + visibility)", "peak": hbm_peak, "peak_source": peak_src,
+                "achieved_gbs": ((ncu or {}).get("k_trace_any_lights", {}).get("dram_bytes", 0.0) / (any_ms / any_n * 1e-3) / 1e9) if (ncu and not multi and any_ms) else None},
     }
 
     cpu_baseline = None
     if not multi and not args.no_cpu_baseline:
-        res = args.cpu_baseline_resolution or sample_resolution_for(15.0)
-
-        def count(r, s):
-            _, st = scene.render(flat.image_width(r), r, s, 0.1)
-            return st.total_rays
-        cb = cpu_reference_sample(sc, flat, res, 1, count)
+        nl = len(flat.light_instances())
+        probe_rays = scene.render(flat.image_width(64), 64, 1, 0.1)[1].total_rays
+        probe = cpu_reference_sample(obj, flat, 64, 1, probe_rays)
+        res = args.cpu_baseline_resolution or min(H, sample_resolution_for(15.0, probe["value"], 1 + nl))
+        rays_s = scene.render(flat.image_width(res), res, 1, 0.1)[1].total_rays
+        cb = cpu_reference_sample(obj, flat, res, 1, rays_s)
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "host_cores_total", "sample")}
+
+    other = None
+    if not multi and not args.no_extras:
+        other = {}
+        for name in ("simple", "basic", "refl", "lines", "instance_real"):
+            if name == args.config:
+                continue
+            try:
+                other[name] = time_config(y, name)
+            except Exception as e:      # noqa: BLE001
+                other[name] = {"error": str(e)}
 
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(args, flat), "rays_per_frame": rays_total / args.steps, "parallelism": f"row-tiles x{world}", "exchange": args.gather if multi else "none",
-                   "tile_rows": tr, "l2": "per-frame ray/hit queues (~1.7 GB streamed per frame) exceed the 126 MB L2; the 3 MB scene is "
+        "config": {"workload": workload_name(desc, flat, W, H, S), "rays_per_frame": rays_total / args.steps,
+                   "rays_per_frame_by_kind": {"primary": float(tot[2].item()) / args.steps, "reflection": float(tot[3].item()) / args.steps, "shadow": float(tot[4].item()) / args.steps},
+                   "parallelism": f"row-tiles x{world}", "exchange": args.gather if multi else "none",
+                   "tile_rows": tr, "l2": "per-frame ray/hit queues (~1.7 GB streamed per frame) exceed the 126 MB L2; the scene is "
                    "cache-resident by design", "lbvh": info},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 64 + 12, "d2h_bytes_per_step": W * H * 16,
-                "ms_per_step": float(dt.item()) * 1e3 / args.steps,
-                "api": "Scene.render -> yrt_render (host framebuffer out)" if not multi else
-                (f"distributed.SharedFrame.render (peer stores into rank 0's frame + all-reduce) + D2H on rank 0" if shared is not None
-                 else "distributed.render_sharded + NCCL gather + D2H on rank 0")},
+                "ms_per_step": float(dt.item()) * 1e3 / args.steps, "api": e2e_api},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "frame_matches_single_gpu": frame_check,
         "per_rank_render_ms_and_kernel_sum": per_rank_ms,
         "breakdown_ms_per_frame_rank0": {"trace_closest": closest_ms, "trace_any": any_ms, "shade": shade_ms, "resolve": other_ms},
-        "mrays_s_by_kernel_rank0": {"closest": primary_per_frame / (closest_ms * 1e-3) / 1e6 if closest_ms else None,
-                                    "any": shadow_per_frame / (any_ms * 1e-3) / 1e6 if any_ms else None},
+        "mrays_s_by_kernel_rank0": {"closest": (primary_pf + refl_pf) / (closest_ms * 1e-3) / 1e6 if closest_ms else None,
+                                    "any": shadow_pf / (any_ms * 1e-3) / 1e6 if any_ms else None},
+        "other_configs": other,
     }
     emit(line)
     scene.close()

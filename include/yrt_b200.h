@@ -173,8 +173,10 @@ int yrt_image_width(const yrt_camera* cam, int resolution);
 /* replaces raytrace(scn, amb, resolution, samples) (src/raytrace.cpp:213-254).
  * `samples` is the per-axis count N (N*N samples per pixel, src/raytrace.cpp:232-234).
  * rgba_out: HOST buffer, width*height*4 floats, row-major pixels[j*width+i] like image4f
- * (src/image.h:15).  Uses every GPU given to yrt_init (interleaved row tiles, gathered
- * on device 0, one device->host copy). */
+ * (src/image.h:15).  Uses every GPU given to yrt_init: interleaved row tiles, and every GPU copies its
+ * own rows into rgba_out over its own PCIe link (no exchange between GPUs).  A large rgba_out that is not
+ * page-locked yet is registered with the driver on first sight and stays registered while the same buffer
+ * keeps coming back. */
 int yrt_render(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height,
                int samples, float* rgba_out, yrt_stats* stats);
 
@@ -196,11 +198,21 @@ int yrt_render_rows(yrt_scene* scn, const yrt_camera* cam, const float amb[3], i
                     int samples, int tile_rows, int rank, int world, void* d_rgba, void* stream,
                     yrt_stats* stats);
 int yrt_rows_owned(int height, int tile_rows, int rank, int world);
+/* Same rows, delivered to their final positions of a row-major HOST frame of the whole image (width*height*4 floats) —
+ * for one-process-per-GPU drivers whose ranks share one host frame (POSIX shared memory, page-locked by every rank):
+ * each rank moves only its own rows, over its own PCIe link, with one pitched copy; the ranks exchange nothing.
+ * Asynchronous on `stream` unless stats != NULL.  The caller orders frames: rank r may overwrite its rows of frame k
+ * as soon as it is called for frame k+1, so the consumer must be done with frame k by then (a barrier, or two frames). */
+int yrt_render_rows_to_host(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height,
+                            int samples, int tile_rows, int rank, int world, float* h_frame, void* stream,
+                            yrt_stats* stats);
 /* Fused gather for one-process-per-GPU drivers: rank 0 allocates the full frame (yrt_frame_alloc) and exports a
  * 64-byte CUDA IPC handle; the other ranks map it (yrt_frame_import: peer mapping over NVLink) and every rank's
  * resolve kernel stores its rows at their final position in that ONE buffer (yrt_render_rows_into_frame) — no
- * packed rows, no gather copy, no unpack; the caller only needs a completion barrier (e.g. a 1-element all-reduce
- * on the same stream) before rank 0 reads the frame. */
+ * packed rows, no gather copy, no unpack.  The caller brackets every frame with two stream-ordered barriers (e.g.
+ * 1-element all-reduces on the same stream): one AFTER the call, before rank 0 reads the frame, and one BEFORE the
+ * next call, after rank 0 has finished reading — otherwise another rank's stores of frame k+1 can overtake rank 0's
+ * read of frame k (distributed.SharedFrame does both). */
 int yrt_render_rows_into_frame(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height,
                                int samples, int tile_rows, int rank, int world, void* d_full, void* stream,
                                yrt_stats* stats);
@@ -209,9 +221,10 @@ int yrt_frame_free(void* d_full);
 int yrt_frame_export(void* d_full, unsigned char handle[64]);
 int yrt_frame_import(const unsigned char handle[64], void** d_full);
 int yrt_frame_release(void* d_full);
-/* deferred statistics for yrt_render_rows: frames rendered between begin and end record per-launch CUDA events
- * and ray counters WITHOUT any host synchronisation; yrt_stats_end waits for the device and returns the totals
- * over those frames (stats->frames says how many). */
+/* deferred statistics for yrt_render_rows*: frames rendered between begin and end record per-launch CUDA events
+ * and ray counters without waiting for the device; yrt_stats_end waits for it and returns the totals over those
+ * frames (stats->frames says how many).  (Scenes with mirrors: the host waits, one wave behind the device, for the
+ * size of each reflection wave — see yrt_render.cu; the device is never idle because of it.) */
 int yrt_stats_begin(yrt_scene* scn);
 int yrt_stats_end(yrt_scene* scn, yrt_stats* totals);
 /* scatter a rank's packed rows into the full row-major framebuffer (both DEVICE pointers) */

@@ -355,19 +355,36 @@ def test_large_scene_and_deep_trees(gpu, oracle_mod):
 
 
 def test_in_process_multi_gpu_matches_single(gpu):
-    """yrt_init(n) + yrt_render: rows interleaved over the GPUs of this process, peer copies to GPU 0; bit-identical."""
+    """yrt_init(n) + yrt_render / yrt_render_ldr: rows interleaved over the GPUs of this process, every GPU copies its own
+    rows into the caller's host frame; bit-identical to one GPU, for the float frame, the RGBA8 frame, a moving camera and a
+    frame height that the GPU count does not divide."""
     n = gpu.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs in this process")
     flat, _ = load_golden("instance10000")
+    cams = [flat.arrays["camera"].copy() for _ in range(3)]
+    cams[1][9] += 3.0
+    cams[2][10] -= 5.0
+    sizes = [(320, 180), (322, 181), (64, 3)]
+    one = []
     with gpu.Scene(flat) as scn:
-        one, _ = scn.render(320, 180, 2, 0.1)
+        for cam in cams:
+            scn.set_camera(cam)
+            for (w, h) in sizes:
+                one.append((scn.render(w, h, 2, 0.1)[0].copy(), scn.render_ldr(w, h, 2, 0.1)[0].copy()))
     try:
         gpu.init(min(n, 4))
         with gpu.Scene(flat) as scn:
-            many, st = scn.render(320, 180, 2, 0.1)
-        assert st.n_gpus == min(n, 4)
-        assert np.array_equal(one.view(np.uint32), many.view(np.uint32))
+            k = 0
+            for cam in cams:
+                scn.set_camera(cam)
+                for (w, h) in sizes:
+                    many, st = scn.render(w, h, 2, 0.1)
+                    ldr, _ = scn.render_ldr(w, h, 2, 0.1)
+                    assert st.n_gpus == min(n, 4)
+                    assert np.array_equal(one[k][0].view(np.uint32), many.view(np.uint32)), (k, w, h)
+                    assert np.array_equal(one[k][1], ldr), (k, w, h)
+                    k += 1
     finally:
         gpu.init(1)
 
@@ -474,3 +491,38 @@ def test_lines_config4_full_size(gpu, oracle_mod):
     within1, ident, mx = ldr_stats(oracle_mod.tonemap(img), png)
     assert within1 >= PIXEL_BAR, (within1, ident, mx)
     assert st.primary_rays == w * h * 9 and st.shadow_rays % 2 == 0
+
+
+def test_torchrun_moving_camera_frames_match_single_gpu(gpu):
+    """One process per GPU (torchrun, NCCL), a different camera every frame, both multi-GPU frame paths (peer stores into
+    rank 0's device frame; per-rank copies into a shared host frame): every frame bit-identical to the single-GPU render.
+    A missing barrier (frame k+1 overtaking the consumer of frame k) shows up as a torn frame here."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    n = gpu.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = min(n, 4)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29577", os.path.join(ROOT, "tests", "_mgpu_worker.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "MGPU_OK" in r.stdout, r.stdout[-2000:]
+
+
+def test_rows_to_host_assembles_the_frame(gpu):
+    """yrt_render_rows_to_host: every rank's pitched device->host copy lands its rows at their final positions of ONE host
+    frame (what the ranks do into shared memory); all ranks of several partitions, ragged last tiles included, emulated on
+    one GPU.  Must equal the whole-frame render bit for bit."""
+    import torch
+    flat, _ = load_golden("instance10000")
+    w, h, s = 160, 91, 2
+    with gpu.Scene(flat) as scn:
+        whole, _ = scn.render(w, h, s, 0.1)
+        for world, tr in ((2, 1), (8, 1), (3, 7), (4, 16), (2, 91), (5, 100)):
+            host = torch.zeros((h, w, 4), dtype=torch.float32).pin_memory()
+            for rank in range(world):
+                scn.render_rows_to_host(host.data_ptr(), w, h, s, 0.1, tr, rank, world, 0, rank == world - 1)
+            torch.cuda.synchronize()
+            assert np.array_equal(host.numpy().view(np.uint32), whole.view(np.uint32)), (world, tr)

@@ -165,7 +165,7 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     tiny bounded sample: stdout carries the one JSON line of the contract and nothing else; no GPU involved."""
     import json
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--cpu-baseline-resolution", "24", "--n-side", "8"], capture_output=True, text=True, timeout=300)
+                        "--cpu-baseline-resolution", "24", "--config", "basic"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-500:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout

@@ -12,5 +12,5 @@ if [ -f build/variants/counters.so ]; then
   YRT_B200_LIB=$PWD/build/variants/counters.so timeout 300 python tools/frame_counters.py > $out/${tag}_counters.json 2> $out/${tag}_counters.err
 fi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $out/${tag}_launches.csv python tools/profile_frame.py --frames 2 > $out/${tag}_ncu_launch.log 2>&1
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_trace --launch-skip 2 -c 2 -f -o $out/${tag}_trace python tools/profile_frame.py --frames 2 > $out/${tag}_ncu_full.log 2>&1
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_trace\|k_shade\|k_resolve --launch-skip 4 -c 4 -f -o $out/${tag}_trace python tools/profile_frame.py --frames 2 > $out/${tag}_ncu_full.log 2>&1
 echo done > $out/${tag}_done.txt

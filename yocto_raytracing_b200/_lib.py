@@ -82,6 +82,8 @@ SYMBOLS = {
     "yrt_render_rows": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
     "yrt_rows_owned": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "yrt_render_rows_to_host": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
     "yrt_render_rows_into_frame": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
     "yrt_frame_alloc": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

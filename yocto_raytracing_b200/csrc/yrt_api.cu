@@ -1,10 +1,10 @@
 // yrt_api.cu — the extern "C" boundary declared in include/yrt_b200.h.
 //
-// Multi-GPU inside one process (yrt_render with yrt_init(n>1)): the scene is replicated, GPU g
-// renders the interleaved row tiles t with t % n == g, its packed rows travel to GPU 0 with one
-// peer copy over NVLink, GPU 0 scatters them into the full framebuffer and does the single
-// device->host copy.  One process per GPU (torchrun): yrt_init_device + yrt_render_rows, the
-// gather is the caller's NCCL collective.
+// Multi-GPU inside one process (yrt_render with yrt_init(n>1)): the scene is replicated, GPU g renders the interleaved
+// row tiles t with t % n == g and copies its rows ITSELF into the caller's host frame (one pitched device->host copy per
+// GPU, each over its own PCIe link, all concurrent) — there is no exchange between GPUs at all.
+// One process per GPU (torchrun): yrt_init_device + yrt_render_rows_to_host into a host frame shared by the ranks, or
+// yrt_render_rows_into_frame when the frame is wanted in rank 0's device memory (peer stores over NVLink).
 #include <algorithm>
 #include <cstring>
 #include <mutex>
@@ -17,21 +17,49 @@ using namespace yrt;
 namespace {
 std::mutex g_mu;
 std::vector<int> g_devices;   // empty until yrt_init*
-std::vector<int> g_peer_ok;   // per initialised device: can it store into device 0's memory (NVLink peer access)?
 
-struct GatherState {          // device-0 side buffers of the in-process multi-GPU path
-    std::vector<DevBuf*> packed;   // per device, on that device
-    std::vector<DevBuf*> staged;   // per device, on device 0
-    DevBuf full, ldr;
-    std::vector<cudaEvent_t> done;
-    std::vector<int> direct;       // per device: stored straight into `full` (peer stores), nothing to unpack
-    ~GatherState() {
-        for (auto p : packed) delete p;
-        for (auto p : staged) delete p;
-    }
-};
-GatherState* g_gather = nullptr;
 int g_allow_nonrigid = 0;    // yrt_set_option("allow_nonrigid")
+
+// Rows of one rank -> their places in a row-major HOST frame (elem = bytes per pixel), as 2-D copies on `st`: the rows of
+// tile k of rank r are one contiguous block of the frame ((k * world + r) * tile_rows rows down), and the rank's packed
+// buffer holds the blocks back to back — a pitched copy moves all full tiles at once; a ragged last tile follows.
+int copy_rows_to_host(const void* d_packed, void* h_frame, int width, int height, int tile_rows, int rank, int world, size_t elem, cudaStream_t st) {
+    const size_t row = elem * (size_t)width;
+    const int n_tiles = (height + tile_rows - 1) / tile_rows;
+    int mine = 0, last = -1;
+    for (int t = rank; t < n_tiles; t += world) { mine++; last = t; }
+    if (mine == 0) return YRT_OK;
+    const bool ragged = (last + 1) * tile_rows > height;
+    const int full = ragged ? mine - 1 : mine;
+    const size_t block = row * (size_t)tile_rows;
+    if (full > 0)
+        YRT_CUDA(cudaMemcpy2DAsync((char*)h_frame + block * (size_t)rank, block * (size_t)world, d_packed, block, block, (size_t)full, cudaMemcpyDeviceToHost, st));
+    if (ragged)
+        YRT_CUDA(cudaMemcpyAsync((char*)h_frame + block * (size_t)last, (const char*)d_packed + block * (size_t)full, row * (size_t)(height - last * tile_rows),
+                                 cudaMemcpyDeviceToHost, st));
+    return YRT_OK;
+}
+
+// the caller's frame buffers are page-locked on first sight (and stay so until another buffer takes the slot or the library
+// is re-initialised): device->host copies into pageable memory are staged and serialised by the driver
+struct HostPin { void* p = nullptr; size_t n = 0; };
+HostPin g_pins[2];
+void pin_host(int slot, void* p, size_t n) {
+    if (getenv("YRT_NO_HOST_REGISTER") || n < ((size_t)1 << 20)) return;
+    HostPin& h = g_pins[slot];
+    if (h.p == p && h.n == n) return;
+    if (h.p) { cudaHostUnregister(h.p); h.p = nullptr; }
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) { cudaGetLastError(); return; }   // pinned already
+    cudaGetLastError();
+    if (cudaHostRegister(p, n, cudaHostRegisterPortable) == cudaSuccess) { h.p = p; h.n = n; }
+    cudaGetLastError();
+}
+void unpin_all() {
+    for (HostPin& h : g_pins)
+        if (h.p) { cudaHostUnregister(h.p); h.p = nullptr; h.n = 0; }
+    cudaGetLastError();
+}
 
 int ensure_init() {
     if (!g_devices.empty()) return YRT_OK;
@@ -59,24 +87,12 @@ int yrt_init(int n_gpus) {
         return YRT_ERR_NO_DEVICE;
     }
     g_devices.clear();
-    g_peer_ok.assign(n_gpus, 0);
-    g_peer_ok[0] = 1;
     for (int i = 0; i < n_gpus; i++) g_devices.push_back(i);
-    for (int i = 1; i < n_gpus; i++) {   // NVLink peer access between GPU 0 and every other GPU (both ways)
-        int can = 0;
-        if (cudaDeviceCanAccessPeer(&can, 0, i) == cudaSuccess && can) { cudaSetDevice(0); cudaDeviceEnablePeerAccess(i, 0); }
-        cudaGetLastError();
-        can = 0;
-        if (cudaDeviceCanAccessPeer(&can, i, 0) == cudaSuccess && can) {
-            cudaSetDevice(i);
-            cudaError_t e = cudaDeviceEnablePeerAccess(0, 0);
-            if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) g_peer_ok[i] = 1;
-        }
-        cudaGetLastError();
+    for (int i = n_gpus - 1; i >= 0; i--) {   // create the contexts now, not inside the first scene build
+        YRT_CUDA(cudaSetDevice(i));
+        YRT_CUDA(cudaFree(0));
     }
-    YRT_CUDA(cudaSetDevice(0));
-    delete g_gather;
-    g_gather = nullptr;
+    unpin_all();
     return YRT_OK;
 }
 
@@ -88,10 +104,9 @@ int yrt_init_device(int device) {
         return YRT_ERR_NO_DEVICE;
     }
     g_devices.assign(1, device);
-    g_peer_ok.assign(1, 1);
     YRT_CUDA(cudaSetDevice(device));
-    delete g_gather;
-    g_gather = nullptr;
+    YRT_CUDA(cudaFree(0));
+    unpin_all();
     return YRT_OK;
 }
 
@@ -99,7 +114,7 @@ int yrt_scene_create(const yrt_scene_desc* desc, yrt_scene** out) {
     if (!out) { set_error("yrt_scene_create: out is null"); return YRT_ERR_INVALID; }
     *out = nullptr;
     yrt_scene* s = new yrt_scene();
-    int st = host_scene_from_desc(desc, s->host);
+    int st = host_scene_from_desc(desc, s->host, true);
     if (st != YRT_OK) { delete s; return st; }
     if (!g_allow_nonrigid && !getenv("YRT_ALLOW_NONRIGID")) {
         int nr = yrt_desc_nonrigid_instances(desc);
@@ -270,6 +285,22 @@ int yrt_unpack_rows(const void* d_packed, void* d_full, int width, int height, i
     return unpack_rows_device((const float4*)d_packed, (float4*)d_full, width, height, tile_rows, rank, world, (cudaStream_t)stream);
 }
 
+int yrt_render_rows_to_host(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height, int samples, int tile_rows,
+                            int rank, int world, float* h_frame, void* stream, yrt_stats* stats) {
+    if (!scn || scn->dev.empty() || !h_frame) { set_error("yrt_render_rows_to_host: bad arguments"); return YRT_ERR_INVALID; }
+    RenderParams rp;
+    YRT_TRY(fill_params(cam, amb, width, height, samples, rp));
+    rp.tile_rows = tile_rows; rp.rank = rank; rp.world = world;
+    DevScene& ds = *scn->dev[0];
+    const int own = rows_owned(height, tile_rows, rank, world);
+    YRT_TRY(ds.ws.rows.alloc(sizeof(float4) * (size_t)std::max(own, 1) * width, ds.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    YRT_TRY(render_rows_device(ds, rp, ds.ws.rows.as<float4>(), st, stats, false));
+    YRT_TRY(copy_rows_to_host(ds.ws.rows.p, h_frame, width, height, tile_rows, rank, world, sizeof(float4), st));
+    if (stats) { YRT_CUDA(cudaStreamSynchronize(st)); return collect_stats_device(ds, rp, stats); }
+    return YRT_OK;
+}
+
 static int render_impl(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height, int samples, float* rgba_out,
                        uint8_t* ldr_out, yrt_stats* stats) {
     if (!scn || scn->dev.empty() || (!rgba_out && !ldr_out)) { set_error("yrt_render: bad arguments"); return YRT_ERR_INVALID; }
@@ -279,52 +310,27 @@ static int render_impl(yrt_scene* scn, const yrt_camera* cam, const float amb[3]
     const char* etr = getenv("YRT_TILE_ROWS");
     int tile_rows = etr ? std::max(1, atoi(etr)) : 1;   // 1-row tiles: rows r, r+G, r+2G, ... balance best (cost varies smoothly down the image)
     if (G == 1) tile_rows = std::max(1, height);
-    if (!g_gather) g_gather = new GatherState();
-    GatherState& gs = *g_gather;
-    while ((int)gs.packed.size() < G) { gs.packed.push_back(new DevBuf()); gs.staged.push_back(new DevBuf()); gs.done.push_back(nullptr); gs.direct.push_back(0); }
-    DevScene& d0 = *scn->dev[0];
-    size_t full_bytes = sizeof(float4) * (size_t)width * height;
-    YRT_TRY(gs.full.alloc(full_bytes, d0.device));
+    const size_t npx = (size_t)width * height;
+    if (rgba_out) pin_host(0, rgba_out, sizeof(float4) * npx);
+    if (ldr_out) pin_host(1, ldr_out, 4 * npx);
 
+    // every GPU renders its interleaved rows and copies them itself into the caller's frame(s), over its own PCIe link
     std::vector<int> status(G, YRT_OK);
     std::vector<std::string> errs(G);
-    std::vector<yrt_stats> dstats(G);
     auto work = [&](int g) {
         DevScene& ds = *scn->dev[g];
         RenderParams rp = rp0;
         rp.tile_rows = tile_rows; rp.rank = g; rp.world = G;
-        int own = rows_owned(height, tile_rows, g, G);
-        size_t bytes = sizeof(float4) * (size_t)own * width;
-        int s = YRT_OK;
-        float4* dst = nullptr;
-        const bool direct = G > 1 && g < (int)g_peer_ok.size() && g_peer_ok[g] && !getenv("YRT_NO_PEER_STORES");
-        if (G == 1) {
-            dst = gs.full.as<float4>();   // one GPU: packed order == row order
-        } else if (direct) {
-            // fused gather: this GPU's resolve kernel stores its rows straight into GPU 0's frame over NVLink
-            dst = gs.full.as<float4>();
-            rp.scatter = true;
-        } else {
-            s = gs.packed[g]->alloc(bytes, ds.device);
-            dst = gs.packed[g]->as<float4>();
+        const int own = rows_owned(height, tile_rows, g, G);
+        int s = ds.ws.rows.alloc(sizeof(float4) * (size_t)std::max(own, 1) * width, ds.device);
+        if (s == YRT_OK) s = render_rows_device(ds, rp, ds.ws.rows.as<float4>(), ds.stream, stats, false);
+        if (s == YRT_OK && rgba_out) s = copy_rows_to_host(ds.ws.rows.p, rgba_out, width, height, tile_rows, g, G, sizeof(float4), ds.stream);
+        if (s == YRT_OK && ldr_out && own > 0) {   // tonemap on the device: a quarter of the bytes cross to the host
+            s = ds.ws.rows8.alloc(4 * (size_t)own * width, ds.device);
+            if (s == YRT_OK) s = tonemap_launch(ds.ws.rows.as<float4>(), ds.ws.rows8.as<uint8_t>(), (size_t)own * width, ds.stream);
+            if (s == YRT_OK) s = copy_rows_to_host(ds.ws.rows8.p, ldr_out, width, height, tile_rows, g, G, 4, ds.stream);
         }
-        if (s == YRT_OK) s = render_rows_device(ds, rp, dst, ds.stream, stats ? &dstats[g] : nullptr, false);
-        gs.direct[g] = direct ? 1 : 0;
-        if (s == YRT_OK && G > 1 && g > 0 && own > 0 && !direct) {
-            s = gs.staged[g]->alloc(bytes, d0.device);
-            if (s == YRT_OK) {
-                cudaSetDevice(ds.device);
-                if (cudaMemcpyPeerAsync(gs.staged[g]->p, d0.device, gs.packed[g]->p, ds.device, bytes, ds.stream) != cudaSuccess) {
-                    set_error("peer copy of rank %d rows failed: %s", g, cudaGetErrorString(cudaGetLastError()));
-                    s = YRT_ERR_CUDA;
-                }
-            }
-        }
-        if (s == YRT_OK) {
-            cudaSetDevice(ds.device);
-            if (!gs.done[g]) cudaEventCreateWithFlags(&gs.done[g], cudaEventDisableTiming);
-            cudaEventRecord(gs.done[g], ds.stream);
-        }
+        if (s == YRT_OK && cudaStreamSynchronize(ds.stream) != cudaSuccess) { set_error("device %d: %s", ds.device, cudaGetErrorString(cudaGetLastError())); s = YRT_ERR_CUDA; }
         status[g] = s;
         if (s != YRT_OK) errs[g] = get_error();
     };
@@ -337,38 +343,10 @@ static int render_impl(yrt_scene* scn, const yrt_camera* cam, const float amb[3]
     }
     for (int g = 0; g < G; g++)
         if (status[g] != YRT_OK) { set_error("%s", errs[g].c_str()); return status[g]; }
-
-    // gather on GPU 0: wait for every rank's rows, scatter into the full framebuffer, one D2H copy
-    YRT_CUDA(cudaSetDevice(d0.device));
-    cudaStream_t s0 = d0.stream;
-    cudaEvent_t g0 = nullptr, g1 = nullptr;
-    if (stats) { cudaEventCreate(&g0); cudaEventCreate(&g1); }
-    if (G > 1) {
-        for (int g = 0; g < G; g++) YRT_CUDA(cudaStreamWaitEvent(s0, gs.done[g], 0));
-        if (stats) cudaEventRecord(g0, s0);
-        for (int g = 0; g < G; g++) {
-            if (gs.direct[g]) continue;   // rows already in place
-            const float4* src = g == 0 ? gs.packed[0]->as<float4>() : gs.staged[g]->as<float4>();
-            if (rows_owned(height, tile_rows, g, G) > 0)
-                YRT_TRY(unpack_rows_device(src, gs.full.as<float4>(), width, height, tile_rows, g, G, s0));
-        }
-        if (stats) cudaEventRecord(g1, s0);
-    }
-    if (rgba_out) YRT_CUDA(cudaMemcpyAsync(rgba_out, gs.full.p, full_bytes, cudaMemcpyDeviceToHost, s0));
-    if (ldr_out) {   // tonemap on the device: a quarter of the bytes cross to the host
-        size_t npx = (size_t)width * height;
-        YRT_TRY(gs.ldr.alloc(4 * npx, d0.device));
-        YRT_TRY(tonemap_launch(gs.full.as<float4>(), gs.ldr.as<uint8_t>(), npx, s0));
-        YRT_CUDA(cudaMemcpyAsync(ldr_out, gs.ldr.p, 4 * npx, cudaMemcpyDeviceToHost, s0));
-    }
-    YRT_CUDA(cudaStreamSynchronize(s0));
     if (stats) {
-        // every device is idle now (GPU 0 waited for all of them): collect per-device stats
         memset(stats, 0, sizeof(*stats));
         for (int g = 0; g < G; g++) {
             DevScene& ds = *scn->dev[g];
-            cudaSetDevice(ds.device);
-            cudaStreamSynchronize(ds.stream);
             RenderParams rp = rp0;
             rp.tile_rows = tile_rows; rp.rank = g; rp.world = G;
             yrt_stats one;
@@ -376,6 +354,7 @@ static int render_impl(yrt_scene* scn, const yrt_camera* cam, const float amb[3]
             stats->primary_rays += one.primary_rays;
             stats->reflection_rays += one.reflection_rays;
             stats->shadow_rays += one.shadow_rays;
+            stats->truncated_paths += one.truncated_paths;
             stats->launches += one.launches;
             stats->ms_total = std::max(stats->ms_total, one.ms_total);
             stats->max_depth = std::max(stats->max_depth, one.max_depth);
@@ -385,10 +364,7 @@ static int render_impl(yrt_scene* scn, const yrt_camera* cam, const float amb[3]
                 stats->n_closest = one.n_closest; stats->n_any = one.n_any; stats->n_shade = one.n_shade; stats->n_other = one.n_other;
             }
         }
-        cudaSetDevice(d0.device);
-        if (G > 1) { float ms = 0.f; cudaEventElapsedTime(&ms, g0, g1); stats->ms_gather = ms; stats->launches += G; }
         stats->n_gpus = G;
-        cudaEventDestroy(g0); cudaEventDestroy(g1);
     }
     return YRT_OK;
 }

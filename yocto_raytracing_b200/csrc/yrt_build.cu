@@ -6,6 +6,7 @@
 // stable scatter} LSD radix sort -> Karras topology -> atomic bottom-up refit -> node emit.
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -44,12 +45,10 @@ __global__ void k_stackneed(LbvhArrays a) { int i = YRT_TID(); if (i < a.n) stac
 
 // prim + attribute records in BLAS leaf order
 __global__ void k_gather_prims(GeomView g, const int* __restrict__ order, float4* __restrict__ prim_recs,
-                               float4* __restrict__ prim_attrs, const int* __restrict__ shape_has_uv,
-                               const int* __restrict__ rank_in, int* __restrict__ rank_out) {
+                               float4* __restrict__ prim_attrs, const int* __restrict__ shape_has_uv) {
     int k = YRT_TID();
     if (k >= g.n_prims) return;
     int gp = order[k];
-    rank_out[k] = rank_in[gp];
     int s = g.prim_shape[gp];
     int e = gp - g.shape_prim_off[s];
     int kind = g.shape_kind[s];
@@ -95,12 +94,10 @@ __global__ void k_inst_boxes(int n_active, const int* __restrict__ active_inst, 
 __global__ void k_inst_recs(int n_active, const int* __restrict__ order, const int* __restrict__ active_inst,
                             const float* __restrict__ inst_frame, const int* __restrict__ inst_shape,
                             const int* __restrict__ inst_mat, const int* __restrict__ shape_kind,
-                            const int* __restrict__ blas_root, float4* __restrict__ recs,
-                            const int* __restrict__ rank_in, int* __restrict__ rank_out) {
+                            const int* __restrict__ blas_root, float4* __restrict__ recs) {
     int k = YRT_TID();
     if (k >= n_active) return;
     int inst = active_inst[order[k]];
-    rank_out[k] = rank_in[inst];
     int s = inst_shape[inst];
     const float* fr = inst_frame + 12 * (size_t)inst;
     float4* r = recs + 4 * (size_t)k;
@@ -223,12 +220,10 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const unsigned long l
     }
 }
 
-static int radix_sort_pairs(int dev, cudaStream_t st, unsigned long long*& keys, int*& vals, unsigned long long*& keys_alt,
-                            int*& vals_alt, int n, DevBuf& ghist_buf) {
+static int radix_sort_pairs(cudaStream_t st, unsigned long long*& keys, int*& vals, unsigned long long*& keys_alt,
+                            int*& vals_alt, int n, int* ghist) {
     if (n <= 1) return YRT_OK;
     int nblocks = (n + RS_TILE - 1) / RS_TILE;
-    YRT_TRY(ghist_buf.alloc(sizeof(int) * 256 * (size_t)nblocks, dev));
-    int* ghist = ghist_buf.as<int>();
     for (int pass = 0; pass < 8; pass++) {
         int shift = pass * 8;
         k_rs_hist<<<nblocks, RS_THREADS, 0, st>>>(keys, n, shift, ghist, nblocks);
@@ -240,8 +235,9 @@ static int radix_sort_pairs(int dev, cudaStream_t st, unsigned long long*& keys,
     YRT_CUDA(cudaGetLastError());
     return YRT_OK;
 }
+static size_t radix_hist_ints(int n) { return 256 * (size_t)((std::max(n, 1) + RS_TILE - 1) / RS_TILE); }
 
-// exported for tests (python ctypes): sort n (key, value) pairs held in HOST arrays on the device
+// test hook declared in include/yrt_b200.h: sort n (key, value) pairs held in HOST arrays on the device
 extern "C" int yrt_debug_sort_pairs(unsigned long long* h_keys, int* h_vals, int n) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { set_error("no CUDA device"); return YRT_ERR_NO_DEVICE; }
@@ -250,123 +246,92 @@ extern "C" int yrt_debug_sort_pairs(unsigned long long* h_keys, int* h_vals, int
     YRT_TRY(v0.upload(h_vals, sizeof(int) * (size_t)n, dev, 0));
     YRT_TRY(k1.alloc(sizeof(unsigned long long) * (size_t)n, dev));
     YRT_TRY(v1.alloc(sizeof(int) * (size_t)n, dev));
+    YRT_TRY(gh.alloc(sizeof(int) * radix_hist_ints(n), dev));
     unsigned long long *ka = k0.as<unsigned long long>(), *kb = k1.as<unsigned long long>();
     int *va = v0.as<int>(), *vb = v1.as<int>();
-    YRT_TRY(radix_sort_pairs(dev, 0, ka, va, kb, vb, n, gh));
+    YRT_TRY(radix_sort_pairs(0, ka, va, kb, vb, n, gh.as<int>()));
     YRT_CUDA(cudaMemcpy(h_keys, ka, sizeof(unsigned long long) * (size_t)n, cudaMemcpyDeviceToHost));
     YRT_CUDA(cudaMemcpy(h_vals, va, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
     return YRT_OK;
 }
 
 // ------------------------------------------------------------------------------------------
-// one LBVH build (many segments)
+// device memory of one scene: two arenas (what stays / what the build needs), each ONE cudaMalloc.
+// An Arena is walked twice with the same sequence of take() calls: a dry pass that only adds up sizes, then the real
+// one — so the layout is written down once, in the order the build uses it.
 // ------------------------------------------------------------------------------------------
-struct LbvhOut {
-    float4* nodes;        // YRT_NODE_STRIDE float4 per internal node, preallocated by the caller
-    int ref_offset;       // index of this tree set's node 0 in the shared node array
-    int size_bits;        // size-class bits in the sort key (see morton_item)
-    int rotate_rounds;    // bottom-up tree-rotation passes after the refit (see rotate_refit_item)
-    int rotate_pairs;     // ... that also try grandchild pair exchanges
-    DevBuf* seg_root;     // [n_seg]
-    DevBuf* seg_depth;    // [n_seg]
-    DevBuf* seg_need;     // [n_seg] traversal stack entries needed below the segment root
-    DevBuf* order;        // [n] item id at sorted slot
-    DevBuf* seg_box_lo;   // [3*n_seg] ordered ints (may be null)
-    DevBuf* seg_box_hi;
+struct Arena {
+    char* base = nullptr;
+    size_t off = 0;
+    template <class T> T* take(size_t count) {
+        size_t a = (off + 255) & ~(size_t)255;
+        off = a + std::max(sizeof(T) * count, (size_t)16);
+        return base ? (T*)(base + a) : nullptr;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// one LBVH build (many segments): enqueues everything on `st`, never synchronises
+// ------------------------------------------------------------------------------------------
+struct LbvhIo {
+    // in
+    int n, n_seg, leaf_size, ref_offset, size_bits, rotate_rounds, rotate_pairs;
+    float4 *box_lo, *box_hi;       // [n] item bounds
+    const int *seg_of, *seg_first;
+    float4* nodes;                 // [YRT_NODE_STRIDE * (n-1)] in the shared node array
+    // out (persistent arena)
+    int *seg_root, *seg_depth, *seg_need;   // [n_seg]
+    int *seg_box_lo, *seg_box_hi;           // [3*n_seg] ordered ints
+    int* order;                             // [n] item id at sorted slot (temp arena, read by the gather kernels)
 };
 
 static inline int grid_for(int n, int t = 256) { return n > 0 ? (n + t - 1) / t : 1; }
 
-static int lbvh_build(int dev, cudaStream_t st, int n, int n_seg, float4* box_lo, float4* box_hi, const int* d_seg_of,
-                      const int* d_seg_first, int leaf_size, LbvhOut& out) {
-    DevBuf cent_lo, cent_hi, sbox_lo_tmp, sbox_hi_tmp, keys, keys_alt, order_alt, left, right, rfirst, rlast, pint, pleaf,
-        flags, nlo, nhi, ghist, count, new_slot, order_tmp, pleaf_tmp, need;
-    DevBuf* sbl = out.seg_box_lo ? out.seg_box_lo : &sbox_lo_tmp;
-    DevBuf* sbh = out.seg_box_hi ? out.seg_box_hi : &sbox_hi_tmp;
-    size_t ni = n > 1 ? (size_t)(n - 1) : 1;
-    YRT_TRY(cent_lo.alloc(sizeof(int) * 3 * (size_t)n_seg, dev));
-    YRT_TRY(cent_hi.alloc(sizeof(int) * 3 * (size_t)n_seg, dev));
-    YRT_TRY(sbl->alloc(sizeof(int) * 3 * (size_t)n_seg, dev));
-    YRT_TRY(sbh->alloc(sizeof(int) * 3 * (size_t)n_seg, dev));
-    YRT_TRY(keys.alloc(sizeof(unsigned long long) * (size_t)std::max(n, 1), dev));
-    YRT_TRY(keys_alt.alloc(sizeof(unsigned long long) * (size_t)std::max(n, 1), dev));
-    YRT_TRY(out.order->alloc(sizeof(int) * (size_t)std::max(n, 1), dev));
-    YRT_TRY(order_alt.alloc(sizeof(int) * (size_t)std::max(n, 1), dev));
-    YRT_TRY(left.alloc(sizeof(int) * ni, dev));
-    YRT_TRY(right.alloc(sizeof(int) * ni, dev));
-    YRT_TRY(rfirst.alloc(sizeof(int) * ni, dev));
-    YRT_TRY(rlast.alloc(sizeof(int) * ni, dev));
-    YRT_TRY(pint.alloc(sizeof(int) * ni, dev));
-    YRT_TRY(pleaf.alloc(sizeof(int) * (size_t)std::max(n, 1), dev));
-    YRT_TRY(flags.alloc(sizeof(int) * ni, dev));
-    YRT_TRY(nlo.alloc(sizeof(float4) * ni, dev));
-    YRT_TRY(nhi.alloc(sizeof(float4) * ni, dev));
-    if (out.rotate_rounds > 0) {
-        YRT_TRY(count.alloc(sizeof(int) * ni, dev));
-        YRT_TRY(new_slot.alloc(sizeof(int) * (size_t)std::max(n, 1), dev));
-        YRT_TRY(order_tmp.alloc(sizeof(int) * (size_t)std::max(n, 1), dev));
-        YRT_TRY(pleaf_tmp.alloc(sizeof(int) * (size_t)std::max(n, 1), dev));
-    }
-    YRT_TRY(out.seg_root->alloc(sizeof(int) * (size_t)n_seg, dev));
-    YRT_TRY(out.seg_depth->alloc(sizeof(int) * (size_t)n_seg, dev));
-    YRT_TRY(out.seg_need->alloc(sizeof(int) * (size_t)n_seg, dev));
-    YRT_TRY(need.alloc(sizeof(int) * ni, dev));
-    YRT_CUDA(cudaMemsetAsync(pleaf.p, 0xff, sizeof(int) * (size_t)std::max(n, 1), st));   // -1: no parent
-    YRT_CUDA(cudaMemsetAsync(out.nodes, 0, sizeof(float4) * YRT_NODE_STRIDE * ni, st));
-
+// temporaries of one build from `tmp` (dry or real), then — if real — the launches
+static int lbvh_build(cudaStream_t st, Arena& tmp, LbvhIo& io) {
+    const int n = io.n, n_seg = io.n_seg;
+    const size_t nn = (size_t)std::max(n, 1), ni = n > 1 ? (size_t)(n - 1) : 1;
     LbvhArrays a;
-    a.n = n;
-    a.n_seg = n_seg;
-    a.box_lo = box_lo;
-    a.box_hi = box_hi;
-    a.seg_of = d_seg_of;
-    a.seg_first = d_seg_first;
-    a.seg_cent_lo = cent_lo.as<int>();
-    a.seg_cent_hi = cent_hi.as<int>();
-    a.seg_box_lo = sbl->as<int>();
-    a.seg_box_hi = sbh->as<int>();
-    a.keys = keys.as<unsigned long long>();
-    a.order = out.order->as<int>();
-    a.left = left.as<int>();
-    a.right = right.as<int>();
-    a.range_first = rfirst.as<int>();
-    a.range_last = rlast.as<int>();
-    a.parent_int = pint.as<int>();
-    a.parent_leaf = pleaf.as<int>();
-    a.flags = flags.as<int>();
-    a.count = count.as<int>();
-    a.new_slot = new_slot.as<int>();
-    a.order_tmp = order_tmp.as<int>();
-    a.parent_leaf_tmp = pleaf_tmp.as<int>();
-    a.node_lo = nlo.as<float4>();
-    a.node_hi = nhi.as<float4>();
-    a.nodes = out.nodes;
-    a.ref_offset = out.ref_offset;
-    a.size_bits = out.size_bits;
-    a.rotate_pairs = out.rotate_pairs;
-    a.seg_root = out.seg_root->as<int>();
-    a.seg_depth = out.seg_depth->as<int>();
-    a.seg_need = out.seg_need->as<int>();
-    a.need = need.as<int>();
-    a.leaf_size = leaf_size;
+    a.n = n; a.n_seg = n_seg;
+    a.box_lo = io.box_lo; a.box_hi = io.box_hi; a.seg_of = io.seg_of; a.seg_first = io.seg_first;
+    a.seg_cent_lo = tmp.take<int>(3 * (size_t)n_seg);
+    a.seg_cent_hi = tmp.take<int>(3 * (size_t)n_seg);
+    a.seg_box_lo = io.seg_box_lo; a.seg_box_hi = io.seg_box_hi;
+    a.keys = tmp.take<unsigned long long>(nn);
+    unsigned long long* keys_alt = tmp.take<unsigned long long>(nn);
+    io.order = a.order = tmp.take<int>(nn);
+    int* order_alt = tmp.take<int>(nn);
+    a.left = tmp.take<int>(ni); a.right = tmp.take<int>(ni);
+    a.range_first = tmp.take<int>(ni); a.range_last = tmp.take<int>(ni);
+    a.parent_int = tmp.take<int>(ni); a.parent_leaf = tmp.take<int>(nn);
+    a.flags = tmp.take<int>(ni);
+    a.node_lo = tmp.take<float4>(ni); a.node_hi = tmp.take<float4>(ni);
+    a.count = tmp.take<int>(ni); a.new_slot = tmp.take<int>(nn);
+    a.order_tmp = tmp.take<int>(nn); a.parent_leaf_tmp = tmp.take<int>(nn);
+    a.need = tmp.take<int>(ni);
+    int* ghist = tmp.take<int>(radix_hist_ints(n));
+    if (!tmp.base) return YRT_OK;   // dry pass
 
+    a.nodes = io.nodes; a.ref_offset = io.ref_offset; a.size_bits = io.size_bits; a.rotate_pairs = io.rotate_pairs;
+    a.seg_root = io.seg_root; a.seg_depth = io.seg_depth; a.seg_need = io.seg_need; a.leaf_size = io.leaf_size;
+    YRT_CUDA(cudaMemsetAsync(a.parent_leaf, 0xff, sizeof(int) * nn, st));   // -1: no parent
+    YRT_CUDA(cudaMemsetAsync(io.nodes, 0, sizeof(float4) * YRT_NODE_STRIDE * ni, st));
     k_seg_init<<<grid_for(n_seg), 256, 0, st>>>(a);
     if (n > 0) {
         k_seg_bounds<<<grid_for(n), 256, 0, st>>>(a);
         k_morton<<<grid_for(n), 256, 0, st>>>(a);
-        unsigned long long* kalt = keys_alt.as<unsigned long long>();
-        int* oalt = order_alt.as<int>();
-        YRT_TRY(radix_sort_pairs(dev, st, a.keys, a.order, kalt, oalt, n, ghist));
+        int* order0 = a.order;
+        YRT_TRY(radix_sort_pairs(st, a.keys, a.order, keys_alt, order_alt, n, ghist));
         // an even number of passes leaves the result in the original buffers
-        if (a.order != out.order->as<int>()) { set_error("radix sort ended in the wrong buffer"); return YRT_ERR_CUDA; }
+        if (a.order != order0) { set_error("radix sort ended in the wrong buffer"); return YRT_ERR_CUDA; }
         if (n > 1) {
             k_karras<<<grid_for(n - 1), 256, 0, st>>>(a);
             k_refit<<<grid_for(n), 256, 0, st>>>(a);
-            for (int r = 0; r < out.rotate_rounds; r++) {
+            for (int r = 0; r < io.rotate_rounds; r++) {
                 YRT_CUDA(cudaMemsetAsync(a.flags, 0, sizeof(int) * ni, st));
                 k_rotate_refit<<<grid_for(n), 256, 0, st>>>(a);
             }
-            if (out.rotate_rounds > 0) {   // leaf slots in tree order again (leaf references are (first, count) ranges)
+            if (io.rotate_rounds > 0) {   // leaf slots in tree order again (leaf references are (first, count) ranges)
                 k_relayout_slot<<<grid_for(n), 256, 0, st>>>(a);
                 k_relayout_move<<<grid_for(n), 256, 0, st>>>(a);
                 k_relayout_refs<<<grid_for(n - 1), 256, 0, st>>>(a);
@@ -382,176 +347,207 @@ static int lbvh_build(int dev, cudaStream_t st, int n, int n_seg, float4* box_lo
         }
     }
     YRT_CUDA(cudaGetLastError());
-    // temporaries are freed when this returns: wait for the work that uses them
-    YRT_CUDA(cudaStreamSynchronize(st));
     return YRT_OK;
+}
+
+// rank tables into leaf order (the ranks are computed on a host thread while the trees are built)
+__global__ void k_permute_prim_rank(int n, const int* __restrict__ order, const int* __restrict__ rank_in, int* __restrict__ rank_out) {
+    int k = YRT_TID();
+    if (k < n) rank_out[k] = rank_in[order[k]];
+}
+__global__ void k_permute_inst_rank(int n, const int* __restrict__ order, const int* __restrict__ active_inst, const int* __restrict__ rank_in,
+                                    int* __restrict__ rank_out) {
+    int k = YRT_TID();
+    if (k < n) rank_out[k] = rank_in[active_inst[order[k]]];
 }
 
 // ------------------------------------------------------------------------------------------
 // upload + build on one device
 // ------------------------------------------------------------------------------------------
-template <class T> static int up(DevBuf& b, const std::vector<T>& v, int dev, cudaStream_t st) {
-    return b.upload(v.data(), sizeof(T) * v.size(), dev, st);
-}
+// The build arena (geometry inputs + LBVH temporaries) is kept per device for the life of the process and reused by the next
+// scene: cudaFree synchronises the device and took 1 - 900 ms here, far more than the build itself.
+static std::mutex g_build_mu;
+static DevBuf g_build_arena[64];
 
-int build_device_scene(const HostScene& hs, int device, DevScene& ds) {
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+int build_device_scene(HostScene& hs, int device, DevScene& ds) {
+    if (device < 0 || device >= 64) { set_error("device index out of range"); return YRT_ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(g_build_mu);
+    DevBuf& build_arena = g_build_arena[device];
+    const bool trace = getenv("YRT_BUILD_TRACE") != nullptr;
+    double t0 = now_ms();
     ds.device = device;
     YRT_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    YRT_CUDA(cudaGetDeviceProperties(&prop, device));
-    ds.sm_count = prop.multiProcessorCount;
+    YRT_CUDA(cudaDeviceGetAttribute(&ds.sm_count, cudaDevAttrMultiProcessorCount, device));
     if (!ds.stream) YRT_CUDA(cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking));
     cudaStream_t st = ds.stream;
 
-    YRT_TRY(up(ds.shape_kind, hs.shape_kind, device, st));
-    YRT_TRY(up(ds.shape_elem_off, hs.shape_elem_off, device, st));
-    YRT_TRY(up(ds.shape_elem_cnt, hs.shape_elem_cnt, device, st));
-    YRT_TRY(up(ds.shape_vert_off, hs.shape_vert_off, device, st));
-    YRT_TRY(up(ds.shape_prim_off, hs.shape_prim_off, device, st));
-    YRT_TRY(up(ds.elem_idx, hs.elem_idx, device, st));
-    YRT_TRY(up(ds.pos, hs.pos, device, st));
-    YRT_TRY(up(ds.norm, hs.norm, device, st));
-    YRT_TRY(up(ds.uv, hs.uv, device, st));
-    YRT_TRY(up(ds.radius, hs.radius, device, st));
-    YRT_TRY(up(ds.prim_shape, hs.prim_shape, device, st));
-    YRT_TRY(up(ds.inst_frame, hs.inst_frame, device, st));
-    YRT_TRY(up(ds.inst_shape, hs.inst_shape, device, st));
-    YRT_TRY(up(ds.inst_mat, hs.inst_mat, device, st));
-    YRT_TRY(up(ds.active_inst, hs.active_inst, device, st));
-    YRT_TRY(up(ds.prim_rank_in, hs.prim_rank, device, st));
-    YRT_TRY(up(ds.inst_rank_in, hs.inst_rank, device, st));
-    YRT_TRY(up(ds.mat_recs, hs.mat_recs, device, st));
-    YRT_TRY(up(ds.light_recs, hs.light_recs, device, st));
-    YRT_TRY(up(ds.tex, hs.tex_rgba8, device, st));
-    YRT_TRY(up(ds.tex_info, hs.tex_info, device, st));
-    YRT_TRY(ds.lut.upload(hs.srgb_lut, sizeof(hs.srgb_lut), device, st));
-    DevBuf shape_has_uv;
-    YRT_TRY(up(shape_has_uv, hs.shape_has_uv, device, st));
-    YRT_CUDA(cudaStreamSynchronize(st));   // uploads done: time the build alone
+    auto env_or = [](const char* name, int def, int lo, int hi) { const char* e = getenv(name); return std::min(std::max(e ? atoi(e) : def, lo), hi); };
+    const int leaf_blas = env_or("YRT_LEAF_BLAS", YRT_LEAF_SIZE_BLAS, 1, YRT_LEAF_MAX_COUNT), leaf_tlas = env_or("YRT_LEAF_TLAS", YRT_LEAF_SIZE_TLAS, 1, YRT_LEAF_MAX_COUNT);
+    const int size_bits_blas = env_or("YRT_SIZE_BITS_BLAS", YRT_SIZE_BITS_BLAS, 0, 3), size_bits_tlas = env_or("YRT_SIZE_BITS_TLAS", YRT_SIZE_BITS_TLAS, 0, 3);
+    const int rotate_blas = env_or("YRT_ROTATE_BLAS", YRT_ROTATE_ROUNDS_BLAS, 0, 8), rotate_tlas = env_or("YRT_ROTATE_TLAS", YRT_ROTATE_ROUNDS_TLAS, 0, 8);
+    const int rotate_pairs_blas = env_or("YRT_ROTATE_PAIRS_BLAS", YRT_ROTATE_PAIRS_BLAS, 0, 1), rotate_pairs_tlas = env_or("YRT_ROTATE_PAIRS_TLAS", YRT_ROTATE_PAIRS_TLAS, 0, 1);
+
+    const int np = hs.n_prims, na = (int)hs.active_inst.size(), nsh = std::max(hs.n_shapes, 1);
+    const int nb_int = np > 1 ? np - 1 : 0, nt_int = na > 1 ? na - 1 : 0;
+    ds.n_prims = np; ds.n_active = na; ds.has_reflective = hs.n_reflective > 0;
+
+    // ---- layout: persistent arena `keep`, build arena `tmp`; the same code runs dry (sizes) and real (pointers) ----
+    struct Up { void* dst; const void* src; size_t bytes; };
+    std::vector<Up> ups;
+    GeomView g;
+    SceneView& v = ds.view;
+    int *d_inst_shape = nullptr, *d_inst_mat = nullptr, *d_active = nullptr, *d_prim_rank_in = nullptr, *d_inst_rank_in = nullptr, *d_has_uv = nullptr,
+        *d_tl_seg_of = nullptr, *d_tl_seg_first = nullptr, *d_results = nullptr, *d_shape_kind = nullptr;
+    float* d_inst_frame = nullptr;
+    float4 *plo = nullptr, *phi = nullptr, *ilo = nullptr, *ihi = nullptr, *d_nodes = nullptr, *d_prim_recs = nullptr, *d_prim_attrs = nullptr, *d_inst_recs = nullptr;
+    int *d_prim_rank = nullptr, *d_inst_rank = nullptr;
+    LbvhIo bo, to;
+    const int tl_sf[2] = {0, na};
+    // results block read back in one copy: [blas depth | blas need | tlas depth, need, root]
+    const size_t n_results = 2 * (size_t)nsh + 3;
+    Arena keep, tmp;
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) {
+            YRT_TRY(ds.arena.alloc(keep.off + 256, device));
+            YRT_TRY(build_arena.alloc(tmp.off + 256, device));
+            keep.base = (char*)ds.arena.p; tmp.base = (char*)build_arena.p;
+            keep.off = tmp.off = 0;
+        }
+        ups.clear();
+        auto up_keep = [&](auto* tag, const auto& vec) {
+            using T = typename std::remove_pointer<decltype(tag)>::type;
+            T* p = keep.take<T>(vec.size());
+            ups.push_back({p, vec.data(), sizeof(T) * vec.size()});
+            return p;
+        };
+        auto up_tmp = [&](auto* tag, const auto& vec) {
+            using T = typename std::remove_pointer<decltype(tag)>::type;
+            T* p = tmp.take<T>(vec.size());
+            ups.push_back({p, vec.data(), sizeof(T) * vec.size()});
+            return p;
+        };
+        // products and what the kernels of a frame read
+        d_nodes = keep.take<float4>(YRT_NODE_STRIDE * (size_t)(nb_int + nt_int + 2));
+        d_prim_recs = keep.take<float4>(3 * (size_t)std::max(np, 1));
+        d_prim_attrs = keep.take<float4>(YRT_ATTR_STRIDE * (size_t)std::max(np, 1));
+        d_inst_recs = keep.take<float4>(4 * (size_t)std::max(na, 1));
+        d_prim_rank = keep.take<int>((size_t)std::max(np, 1));
+        d_inst_rank = keep.take<int>((size_t)std::max(na, 1));
+        v.mat_recs = up_keep((float4*)nullptr, hs.mat_recs);
+        v.light_recs = up_keep((float4*)nullptr, hs.light_recs);
+        v.tex_rgba8 = up_keep((uint8_t*)nullptr, hs.tex_rgba8);
+        v.tex_info = up_keep((int4*)nullptr, hs.tex_info);
+        {
+            float* lut = keep.take<float>(256);
+            ups.push_back({lut, hs.srgb_lut, sizeof(hs.srgb_lut)});
+            v.srgb_lut = lut;
+        }
+        d_results = keep.take<int>(n_results);
+        // geometry inputs: only the build reads them
+        d_shape_kind = up_tmp((int*)nullptr, hs.shape_kind);
+        g.shape_kind = d_shape_kind;
+        g.shape_elem_off = up_tmp((int*)nullptr, hs.shape_elem_off);
+        g.shape_elem_cnt = up_tmp((int*)nullptr, hs.shape_elem_cnt);
+        g.shape_vert_off = up_tmp((int*)nullptr, hs.shape_vert_off);
+        g.shape_prim_off = up_tmp((int*)nullptr, hs.shape_prim_off);
+        g.elem_idx = up_tmp((int*)nullptr, hs.elem_idx);
+        g.pos = up_tmp((float*)nullptr, hs.pos);
+        g.norm = up_tmp((float*)nullptr, hs.norm);
+        g.uv = up_tmp((float*)nullptr, hs.uv);
+        g.radius = up_tmp((float*)nullptr, hs.radius);
+        g.prim_shape = up_tmp((int*)nullptr, hs.prim_shape);
+        g.n_prims = np;
+        d_inst_frame = up_tmp((float*)nullptr, hs.inst_frame);
+        d_inst_shape = up_tmp((int*)nullptr, hs.inst_shape);
+        d_inst_mat = up_tmp((int*)nullptr, hs.inst_mat);
+        d_active = up_tmp((int*)nullptr, hs.active_inst);
+        d_has_uv = up_tmp((int*)nullptr, hs.shape_has_uv);
+        d_prim_rank_in = tmp.take<int>((size_t)std::max(np, 1));        // uploaded late (rank thread)
+        d_inst_rank_in = tmp.take<int>((size_t)std::max(hs.n_instances, 1));
+        d_tl_seg_of = tmp.take<int>((size_t)std::max(na, 1));
+        d_tl_seg_first = tmp.take<int>(2);
+        ups.push_back({d_tl_seg_first, tl_sf, sizeof(tl_sf)});
+        plo = tmp.take<float4>((size_t)std::max(np, 1)); phi = tmp.take<float4>((size_t)std::max(np, 1));
+        ilo = tmp.take<float4>((size_t)std::max(na, 1)); ihi = tmp.take<float4>((size_t)std::max(na, 1));
+        int* shape_box_lo = tmp.take<int>(3 * (size_t)nsh);
+        int* shape_box_hi = tmp.take<int>(3 * (size_t)nsh);
+        int* blas_root = tmp.take<int>((size_t)nsh);
+        int* tl_box_lo = tmp.take<int>(3);
+        int* tl_box_hi = tmp.take<int>(3);
+        // ---- BLAS: all shapes in one build ----
+        bo.n = np; bo.n_seg = nsh; bo.leaf_size = leaf_blas; bo.ref_offset = 0; bo.size_bits = size_bits_blas; bo.rotate_rounds = rotate_blas; bo.rotate_pairs = rotate_pairs_blas;
+        bo.box_lo = plo; bo.box_hi = phi; bo.seg_of = g.prim_shape; bo.seg_first = g.shape_prim_off; bo.nodes = d_nodes;
+        bo.seg_root = blas_root; bo.seg_depth = d_results; bo.seg_need = d_results + nsh; bo.seg_box_lo = shape_box_lo; bo.seg_box_hi = shape_box_hi;
+        // ---- TLAS over active instances ----
+        to.n = na; to.n_seg = 1; to.leaf_size = leaf_tlas; to.ref_offset = nb_int; to.size_bits = size_bits_tlas; to.rotate_rounds = rotate_tlas; to.rotate_pairs = rotate_pairs_tlas;
+        to.box_lo = ilo; to.box_hi = ihi; to.seg_of = d_tl_seg_of; to.seg_first = d_tl_seg_first; to.nodes = d_nodes ? d_nodes + YRT_NODE_STRIDE * (size_t)nb_int : nullptr;
+        to.seg_root = d_results + 2 * nsh + 2; to.seg_depth = d_results + 2 * nsh; to.seg_need = d_results + 2 * nsh + 1; to.seg_box_lo = tl_box_lo; to.seg_box_hi = tl_box_hi;
+        if (pass == 0) {   // sizes of the two builds' temporaries (not shared: the BLAS order is read again at the very end)
+            YRT_TRY(lbvh_build(st, tmp, bo));
+            YRT_TRY(lbvh_build(st, tmp, to));
+        }
+    }
+    const double t_layout = now_ms();
+    for (const Up& u : ups)
+        if (u.bytes) YRT_CUDA(cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, st));
+    YRT_CUDA(cudaMemsetAsync(d_tl_seg_of, 0, sizeof(int) * (size_t)std::max(na, 1), st));
+    const double t_upload = now_ms();
 
     cudaEvent_t e0, e1;
     YRT_CUDA(cudaEventCreate(&e0));
     YRT_CUDA(cudaEventCreate(&e1));
     YRT_CUDA(cudaEventRecord(e0, st));
-
-    const char* env_lb = getenv("YRT_LEAF_BLAS");
-    const char* env_lt = getenv("YRT_LEAF_TLAS");
-    int leaf_blas = env_lb ? atoi(env_lb) : YRT_LEAF_SIZE_BLAS;
-    int leaf_tlas = env_lt ? atoi(env_lt) : YRT_LEAF_SIZE_TLAS;
-    const char* env_sb = getenv("YRT_SIZE_BITS_BLAS");
-    const char* env_st = getenv("YRT_SIZE_BITS_TLAS");
-    int size_bits_blas = std::min(std::max(env_sb ? atoi(env_sb) : YRT_SIZE_BITS_BLAS, 0), 3);
-    int size_bits_tlas = std::min(std::max(env_st ? atoi(env_st) : YRT_SIZE_BITS_TLAS, 0), 3);
-    const char* env_rb = getenv("YRT_ROTATE_BLAS");
-    const char* env_rt = getenv("YRT_ROTATE_TLAS");
-    int rotate_blas = std::min(std::max(env_rb ? atoi(env_rb) : YRT_ROTATE_ROUNDS_BLAS, 0), 8);
-    int rotate_tlas = std::min(std::max(env_rt ? atoi(env_rt) : YRT_ROTATE_ROUNDS_TLAS, 0), 8);
-    int rotate_pairs_blas = getenv("YRT_ROTATE_PAIRS_BLAS") ? atoi(getenv("YRT_ROTATE_PAIRS_BLAS")) : YRT_ROTATE_PAIRS_BLAS;
-    int rotate_pairs_tlas = getenv("YRT_ROTATE_PAIRS_TLAS") ? atoi(getenv("YRT_ROTATE_PAIRS_TLAS")) : YRT_ROTATE_PAIRS_TLAS;
-    leaf_blas = std::min(std::max(leaf_blas, 1), YRT_LEAF_MAX_COUNT);
-    leaf_tlas = std::min(std::max(leaf_tlas, 1), YRT_LEAF_MAX_COUNT);
-
-    GeomView g;
-    g.shape_kind = ds.shape_kind.as<int>();
-    g.shape_elem_off = ds.shape_elem_off.as<int>();
-    g.shape_elem_cnt = ds.shape_elem_cnt.as<int>();
-    g.shape_vert_off = ds.shape_vert_off.as<int>();
-    g.shape_prim_off = ds.shape_prim_off.as<int>();
-    g.elem_idx = ds.elem_idx.as<int>();
-    g.pos = ds.pos.as<float>();
-    g.norm = ds.norm.as<float>();
-    g.uv = ds.uv.as<float>();
-    g.radius = ds.radius.as<float>();
-    g.prim_shape = ds.prim_shape.as<int>();
-    g.n_prims = hs.n_prims;
-    ds.n_prims = hs.n_prims;
-    ds.n_active = (int)hs.active_inst.size();
-    ds.has_reflective = hs.n_reflective > 0;
-
-    // ---- BLAS: all shapes in one build ----
-    DevBuf plo, phi, blas_order;
-    YRT_TRY(plo.alloc(sizeof(float4) * (size_t)std::max(hs.n_prims, 1), device));
-    YRT_TRY(phi.alloc(sizeof(float4) * (size_t)std::max(hs.n_prims, 1), device));
-    if (hs.n_prims > 0) k_prim_boxes<<<grid_for(hs.n_prims), 256, 0, st>>>(g, plo.as<float4>(), phi.as<float4>());
-    int nb_int = hs.n_prims > 1 ? hs.n_prims - 1 : 0, nt_int = ds.n_active > 1 ? ds.n_active - 1 : 0;
-    YRT_TRY(ds.nodes.alloc(sizeof(float4) * YRT_NODE_STRIDE * (size_t)(nb_int + nt_int + 2), device));
-    LbvhOut bo;
-    bo.nodes = ds.nodes.as<float4>(); bo.ref_offset = 0; bo.size_bits = size_bits_blas; bo.rotate_rounds = rotate_blas; bo.rotate_pairs = rotate_pairs_blas; bo.seg_root = &ds.blas_seg_root; bo.seg_depth = &ds.blas_seg_depth; bo.seg_need = &ds.blas_seg_need; bo.order = &blas_order;
-    bo.seg_box_lo = &ds.shape_box_lo; bo.seg_box_hi = &ds.shape_box_hi;
-    YRT_TRY(lbvh_build(device, st, hs.n_prims, std::max(hs.n_shapes, 1), plo.as<float4>(), phi.as<float4>(), g.prim_shape,
-                       g.shape_prim_off, leaf_blas, bo));
-    YRT_TRY(ds.prim_recs.alloc(sizeof(float4) * 3 * (size_t)std::max(hs.n_prims, 1), device));
-    YRT_TRY(ds.prim_attrs.alloc(sizeof(float4) * YRT_ATTR_STRIDE * (size_t)std::max(hs.n_prims, 1), device));
-    YRT_TRY(ds.prim_rank.alloc(sizeof(int) * (size_t)std::max(hs.n_prims, 1), device));
-    if (hs.n_prims > 0)
-        k_gather_prims<<<grid_for(hs.n_prims), 256, 0, st>>>(g, blas_order.as<int>(), ds.prim_recs.as<float4>(),
-                                                           ds.prim_attrs.as<float4>(), shape_has_uv.as<int>(),
-                                                           ds.prim_rank_in.as<int>(), ds.prim_rank.as<int>());
-
-    // ---- TLAS over active instances ----
-    int na = ds.n_active;
-    DevBuf ilo, ihi, tl_seg_of, tl_seg_first, tlas_order;
-    YRT_TRY(ilo.alloc(sizeof(float4) * (size_t)std::max(na, 1), device));
-    YRT_TRY(ihi.alloc(sizeof(float4) * (size_t)std::max(na, 1), device));
-    YRT_TRY(tl_seg_of.alloc(sizeof(int) * (size_t)std::max(na, 1), device));
-    YRT_CUDA(cudaMemsetAsync(tl_seg_of.p, 0, sizeof(int) * (size_t)std::max(na, 1), st));
-    int sf[2] = {0, na};
-    YRT_TRY(tl_seg_first.upload(sf, sizeof(sf), device, st));
-    if (na > 0)
-        k_inst_boxes<<<grid_for(na), 256, 0, st>>>(na, ds.active_inst.as<int>(), ds.inst_frame.as<float>(), ds.inst_shape.as<int>(),
-                                                 ds.shape_box_lo.as<int>(), ds.shape_box_hi.as<int>(), ilo.as<float4>(), ihi.as<float4>());
-    LbvhOut to;
-    to.nodes = ds.nodes.as<float4>() + YRT_NODE_STRIDE * (size_t)nb_int; to.ref_offset = nb_int; to.size_bits = size_bits_tlas; to.rotate_rounds = rotate_tlas; to.rotate_pairs = rotate_pairs_tlas; to.seg_root = &ds.tlas_seg_root; to.seg_depth = &ds.tlas_seg_depth; to.seg_need = &ds.tlas_seg_need; to.order = &tlas_order;
-    to.seg_box_lo = nullptr; to.seg_box_hi = nullptr;
-    YRT_TRY(lbvh_build(device, st, na, 1, ilo.as<float4>(), ihi.as<float4>(), tl_seg_of.as<int>(), tl_seg_first.as<int>(), leaf_tlas, to));
-    YRT_TRY(ds.inst_recs.alloc(sizeof(float4) * 4 * (size_t)std::max(na, 1), device));
-    YRT_TRY(ds.inst_rank.alloc(sizeof(int) * (size_t)std::max(na, 1), device));
-    if (na > 0)
-        k_inst_recs<<<grid_for(na), 256, 0, st>>>(na, tlas_order.as<int>(), ds.active_inst.as<int>(), ds.inst_frame.as<float>(),
-                                                ds.inst_shape.as<int>(), ds.inst_mat.as<int>(), ds.shape_kind.as<int>(),
-                                                ds.blas_seg_root.as<int>(), ds.inst_recs.as<float4>(),
-                                                ds.inst_rank_in.as<int>(), ds.inst_rank.as<int>());
+    if (np > 0) k_prim_boxes<<<grid_for(np), 256, 0, st>>>(g, plo, phi);
+    YRT_TRY(lbvh_build(st, tmp, bo));
+    if (np > 0) k_gather_prims<<<grid_for(np), 256, 0, st>>>(g, bo.order, d_prim_recs, d_prim_attrs, d_has_uv);
+    if (na > 0) k_inst_boxes<<<grid_for(na), 256, 0, st>>>(na, d_active, d_inst_frame, d_inst_shape, bo.seg_box_lo, bo.seg_box_hi, ilo, ihi);
+    YRT_TRY(lbvh_build(st, tmp, to));
+    if (na > 0) k_inst_recs<<<grid_for(na), 256, 0, st>>>(na, to.order, d_active, d_inst_frame, d_inst_shape, d_inst_mat, d_shape_kind, bo.seg_root, d_inst_recs);
     YRT_CUDA(cudaGetLastError());
+    const double t_enqueued = now_ms();
+    // tie-break ranks: computed on a host thread since yrt_scene_create started (yrt_host.cu); needed only now
+    hs.wait_ranks();
+    const double t_ranks = now_ms();
+    YRT_CUDA(cudaMemcpyAsync(d_prim_rank_in, hs.prim_rank.data(), sizeof(int) * hs.prim_rank.size(), cudaMemcpyHostToDevice, st));
+    YRT_CUDA(cudaMemcpyAsync(d_inst_rank_in, hs.inst_rank.data(), sizeof(int) * hs.inst_rank.size(), cudaMemcpyHostToDevice, st));
+    if (np > 0) k_permute_prim_rank<<<grid_for(np), 256, 0, st>>>(np, bo.order, d_prim_rank_in, d_prim_rank);
+    if (na > 0) k_permute_inst_rank<<<grid_for(na), 256, 0, st>>>(na, to.order, d_active, d_inst_rank_in, d_inst_rank);
     YRT_CUDA(cudaEventRecord(e1, st));
-    YRT_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> results(n_results, 0);
+    YRT_CUDA(cudaMemcpyAsync(results.data(), d_results, sizeof(int) * n_results, cudaMemcpyDeviceToHost, st));
+    YRT_CUDA(cudaStreamSynchronize(st));     // the only wait of the build
+    const double t_done = now_ms();
     float ms = 0.f;
     YRT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     ds.build_us = ms * 1000.f;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    if (trace)
+        fprintf(stderr, "[yrt build] device %d: layout %.3f ms, uploads enqueued %.3f, build enqueued %.3f, waited for ranks %.3f, device done %.3f (kernels %.3f); "
+                        "arenas %.1f + %.1f MB\n", device, t_layout - t0, t_upload - t_layout, t_enqueued - t_upload, t_ranks - t_enqueued, t_done - t_ranks, ms,
+                keep.off / 1e6, tmp.off / 1e6);
 
-    // depths / root back to the host
-    std::vector<int> bdepth(std::max(hs.n_shapes, 1), 0), bneed(std::max(hs.n_shapes, 1), 0);
-    int tdepth = 0, tneed = 0, troot = YRT_REF_SENTINEL;
-    YRT_CUDA(cudaMemcpy(bdepth.data(), ds.blas_seg_depth.p, sizeof(int) * bdepth.size(), cudaMemcpyDeviceToHost));
-    YRT_CUDA(cudaMemcpy(bneed.data(), ds.blas_seg_need.p, sizeof(int) * bneed.size(), cudaMemcpyDeviceToHost));
-    YRT_CUDA(cudaMemcpy(&tdepth, ds.tlas_seg_depth.p, sizeof(int), cudaMemcpyDeviceToHost));
-    YRT_CUDA(cudaMemcpy(&tneed, ds.tlas_seg_need.p, sizeof(int), cudaMemcpyDeviceToHost));
-    YRT_CUDA(cudaMemcpy(&troot, ds.tlas_seg_root.p, sizeof(int), cudaMemcpyDeviceToHost));
-    ds.blas_depth = *std::max_element(bdepth.begin(), bdepth.end());
-    ds.tlas_depth = tdepth;
-    ds.n_blas_nodes = hs.n_prims > 1 ? hs.n_prims - 1 : 0;
-    ds.n_tlas_nodes = na > 1 ? na - 1 : 0;
+    ds.blas_depth = *std::max_element(results.begin(), results.begin() + nsh);
+    const int blas_need = *std::max_element(results.begin() + nsh, results.begin() + 2 * nsh);
+    ds.tlas_depth = results[2 * nsh];
+    const int tlas_need = results[2 * nsh + 1], troot = results[2 * nsh + 2];
+    ds.n_blas_nodes = nb_int;
+    ds.n_tlas_nodes = nt_int;
     if (na > 0 && troot == YRT_REF_SENTINEL) { set_error("internal: TLAS root not found"); return YRT_ERR_CUDA; }
     // entries below the TLAS root + entries below the deepest BLAS root + guard + sentinel + the "rest of a TLAS leaf" entry
-    ds.stack_need = tneed + *std::max_element(bneed.begin(), bneed.end()) + 3;
+    ds.stack_need = tlas_need + blas_need + 3;
     if (ds.stack_need > YRT_STACK_CAP) {
         set_error("traversal tree too deep for the stack (%d entries needed: tlas %d + blas %d levels, capacity %d)", ds.stack_need, ds.tlas_depth, ds.blas_depth, YRT_STACK_CAP);
         return YRT_ERR_UNSUPPORTED;
     }
-
-    SceneView& v = ds.view;
-    v.nodes = ds.nodes.as<float4>();
-    v.inst_recs = ds.inst_recs.as<float4>();
-    v.prim_recs = ds.prim_recs.as<float4>();
-    v.prim_attrs = ds.prim_attrs.as<float4>();
-    v.mat_recs = ds.mat_recs.as<float4>();
-    v.light_recs = ds.light_recs.as<float4>();
-    v.tex_rgba8 = ds.tex.as<uint8_t>();
-    v.tex_info = ds.tex_info.as<int4>();
-    v.srgb_lut = ds.lut.as<float>();
-    v.inst_rank = ds.inst_rank.as<int>();
-    v.prim_rank = ds.prim_rank.as<int>();
+    v.nodes = d_nodes;
+    v.inst_recs = d_inst_recs;
+    v.prim_recs = d_prim_recs;
+    v.prim_attrs = d_prim_attrs;
+    v.inst_rank = d_inst_rank;
+    v.prim_rank = d_prim_rank;
     v.tlas_root = troot;
     v.n_lights = (int)hs.light_inst.size();
     v.n_active_instances = na;

@@ -53,7 +53,7 @@ void DevBuf::release() {
 // ------------------------------------------------------------------------------------------
 // host scene from the C description
 // ------------------------------------------------------------------------------------------
-int host_scene_from_desc(const yrt_scene_desc* d, HostScene& hs) {
+int host_scene_from_desc(const yrt_scene_desc* d, HostScene& hs, bool ranks_async) {
     if (!d) { set_error("null scene description"); return YRT_ERR_INVALID; }
     if (d->n_shapes < 0 || d->n_instances < 0 || d->n_materials < 0 || d->n_textures < 0 || d->n_verts < 0 || d->n_elem_idx < 0) {
         set_error("negative count in scene description");
@@ -169,7 +169,8 @@ int host_scene_from_desc(const yrt_scene_desc* d, HostScene& hs) {
         hs.light_recs.push_back(mk4(p0[0], p0[1], p0[2], 0.f));
         hs.light_inst.push_back(i);
     }
-    reference_visit_ranks(hs);
+    if (ranks_async) hs.rank_thread = std::thread([&hs]() { reference_visit_ranks(hs); });
+    else reference_visit_ranks(hs);
     return YRT_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/yrt_b200.h"
@@ -63,9 +64,14 @@ struct HostScene {
     std::vector<uint8_t> tex_rgba8;
     float srgb_lut[256];
     int n_reflective = 0;
+    // the rank tables are computed on a worker thread that yrt_scene_create starts; the build waits for it at the end
+    std::thread rank_thread;
+    void wait_ranks() { if (rank_thread.joinable()) rank_thread.join(); }
+    ~HostScene() { wait_ranks(); }
 };
 
-int host_scene_from_desc(const yrt_scene_desc* d, HostScene& hs);
+// validates and copies the description; ranks_async: reference_visit_ranks runs on hs.rank_thread instead of inline
+int host_scene_from_desc(const yrt_scene_desc* d, HostScene& hs, bool ranks_async = false);
 // visit ranks of the reference's top-down BVHs (make_node/split_prims, src/scene.cpp:572-639), for tie-breaking
 void reference_visit_ranks(HostScene& hs);
 
@@ -73,7 +79,7 @@ struct PhaseTimer;
 
 // per-device render workspace (grown on demand, reused across frames)
 struct Workspace {
-    DevBuf hit, P, vis, rad, ray_o, ray_d, pstack, act0, act1, counters, stats, rows;
+    DevBuf hit, P, vis, rad, ray_o, ray_d, pstack, act0, act1, counters, stats, rows, rows8;
     size_t cap_slots = 0;
     int cap_lights = 0;
     int cap_depth = 0;
@@ -87,12 +93,7 @@ struct Workspace {
 struct DevScene {
     int device = 0;
     SceneView view;
-    // geometry inputs
-    DevBuf shape_kind, shape_elem_off, shape_elem_cnt, shape_vert_off, shape_prim_off, elem_idx, pos, norm, uv, radius, prim_shape;
-    DevBuf inst_frame, inst_shape, inst_mat, active_inst, prim_rank_in, inst_rank_in, prim_rank, inst_rank;
-    // build products
-    DevBuf nodes, prim_recs, prim_attrs, inst_recs, mat_recs, light_recs, tex, tex_info, lut;
-    DevBuf blas_seg_root, blas_seg_depth, blas_seg_need, tlas_seg_root, tlas_seg_depth, tlas_seg_need, shape_box_lo, shape_box_hi;
+    DevBuf arena;          // everything a frame reads: nodes, element / instance / material / light records, textures, rank tables
     int n_prims = 0, n_active = 0, n_blas_nodes = 0, n_tlas_nodes = 0;
     int blas_depth = 0, tlas_depth = 0, stack_need = 0;
     float build_us = 0.f;
@@ -108,7 +109,7 @@ struct DevScene {
     PhaseTimer* timer = nullptr;     // owned (yrt_render.cu)
 };
 
-int build_device_scene(const HostScene& hs, int device, DevScene& ds);
+int build_device_scene(HostScene& hs, int device, DevScene& ds);
 void destroy_device_scene(DevScene& ds);
 
 struct RenderParams {

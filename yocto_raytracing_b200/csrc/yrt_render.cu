@@ -286,25 +286,26 @@ __device__ __forceinline__ void shade_epilogue(const ShadeBuffers& sb, int depth
 __global__ void __launch_bounds__(256, 4) k_shade(SceneView sv, BatchParams bp, ShadeBuffers sb, int depth, int max_depth,
                                                   const int* __restrict__ act, unsigned n_act, const unsigned* __restrict__ n_act_dev,
                                                   const uint8_t* __restrict__ vis) {
-    if (n_act_dev) {
-        n_act = min(n_act, *n_act_dev);
-        if (blockIdx.x * blockDim.x >= n_act) return;
-    }
+    if (n_act_dev) n_act = min(n_act, *n_act_dev);
+    if (blockIdx.x * blockDim.x >= n_act) return;
     __shared__ float lut[256];
     lut[threadIdx.x] = sv.srgb_lut[threadIdx.x];
     __syncthreads();
-    unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = a < n_act;
-    bool is_hit = false, spawn = false, truncated = false;
-    unsigned slot = 0;
-    if (valid) {
-        slot = act ? (unsigned)act[a] : a;
-        float4 h = sb.hit[slot];
-        const uint8_t* vrow = vis + slot;
-        size_t cap = bp.cap_slots;
-        spawn = shade_slot(sv, bp, sb, depth, max_depth, slot, h, lut, [&](int k) { return vrow[(size_t)k * cap] != 0; }, is_hit, truncated);
+    // (grid-stride: waves whose size is only known on the device are launched with a bounded grid)
+    for (unsigned base = blockIdx.x * blockDim.x; base < n_act; base += gridDim.x * blockDim.x) {
+        unsigned a = base + threadIdx.x;
+        bool valid = a < n_act;
+        bool is_hit = false, spawn = false, truncated = false;
+        unsigned slot = 0;
+        if (valid) {
+            slot = act ? (unsigned)act[a] : a;
+            float4 h = sb.hit[slot];
+            const uint8_t* vrow = vis + slot;
+            size_t cap = bp.cap_slots;
+            spawn = shade_slot(sv, bp, sb, depth, max_depth, slot, h, lut, [&](int k) { return vrow[(size_t)k * cap] != 0; }, is_hit, truncated);
+        }
+        shade_epilogue(sb, depth, valid, is_hit, spawn, truncated, slot, threadIdx.x & 31);
     }
-    shade_epilogue(sb, depth, valid, is_hit, spawn, truncated, slot, threadIdx.x & 31);
 }
 
 // scatter != 0: `out` is the FULL frame (possibly another GPU's memory mapped over NVLink) and every pixel goes to
@@ -522,9 +523,10 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0
 
     // Wave loop.  Wave d traces the shadow rays of its active samples, shades them, and appends the mirror rays it spawns to
     // the queue of wave d + 1, whose length is counts[d + 1] in device memory: every kernel of a later wave reads its item
-    // count from there, so the host enqueues waves without waiting for the device.  It stops enqueuing when a count that
-    // has reached it in the meantime (asynchronous copy into pinned memory + event, polled, never waited for) is zero —
-    // at most a couple of empty waves are launched beyond the last real one, and none at all for scenes without mirrors.
+    // count from there, so a wave is enqueued before the previous one has run.  To know when to stop, the host reads the
+    // counts back (asynchronous copy into pinned memory + event) ONE WAVE LATE: before it enqueues wave d it waits for the
+    // count of wave d - 1, while the kernels of wave d - 1 are still queued behind it on the device — the GPU never idles,
+    // and at most one empty wave is launched beyond the last real one (none at all for scenes without mirrors).
     FrameCounters* fc = ds.ws.stats.as<FrameCounters>();   // one set of frame counters for all pipelines
     unsigned* counts = (unsigned*)((char*)w.stats.p + STATS_WAVE_COUNTS_OFFSET);
     if (reflective) YRT_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned) * (YRT_MAX_WAVES + 2), st));
@@ -550,17 +552,15 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0
             pt.end();
         }
         pt.begin(CAT_SHADE);
-        k_shade<<<(n + 255) / 256, 256, 0, st>>>(ds.view, bp, sb, depth, depth_cap, act, n, n_dev, w.vis.as<uint8_t>());
+        k_shade<<<depth == 0 ? (n + 255) / 256 : std::min((n + 255) / 256, (unsigned)ds.sm_count * 16u), 256, 0, st>>>(ds.view, bp, sb, depth, depth_cap, act, n, n_dev, w.vis.as<uint8_t>());
         pt.end();
         if (!reflective || depth + 1 >= depth_cap) break;
         YRT_CUDA(cudaMemcpyAsync(w.h_counts + depth + 1, counts + depth + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         YRT_CUDA(cudaEventRecord(w.ev_counts[depth + 1], st));
-        // counts that have arrived so far: wave k has no rays => no later wave has any
-        bool stop = false;
-        for (int k = 1; k <= depth + 1 && !stop; k++)
-            if (cudaEventQuery(w.ev_counts[k]) == cudaSuccess && w.h_counts[k] == 0) stop = true;
-        cudaGetLastError();   // cudaErrorNotReady is not an error
-        if (stop) break;
+        if (depth >= 1) {   // about to enqueue wave depth + 1: the count of wave `depth` must have arrived
+            YRT_CUDA(cudaEventSynchronize(w.ev_counts[depth]));
+            if (w.h_counts[depth] == 0) break;
+        }
     }
     int n_pix = nrows * rp.width;
     pt.begin(CAT_OTHER);

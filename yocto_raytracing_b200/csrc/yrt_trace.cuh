@@ -17,6 +17,9 @@
 #ifndef YRT_POP_CULL
 #define YRT_POP_CULL 1   /* closest hit: a stack entry carries the entry distance of its box and is dropped at pop time if the hit found since then is nearer */
 #endif
+#ifndef YRT_WIDE_ORDER
+#define YRT_WIDE_ORDER 0   /* closest hit, 4-wide nodes: 0 = entered children sorted by entry distance (tournament), 1 = nearest first, the rest in stored order */
+#endif
 #ifndef YRT_ANY_UNORDERED
 #define YRT_ANY_UNORDERED 1  /* any-hit rays: children are entered in stored order, no entry-distance compare (the answer is order independent) */
 #endif
@@ -114,7 +117,8 @@ struct Tracer {
     slabray sr;
     float tmin, tmax;     // tmin is copied unchanged into every instance space (vmath.h:277)
     int cur, si, kind;
-    int* sp;              // next free stack slot; stack[0] holds a YRT_REF_DONE guard, so a pop needs no emptiness test
+    int* stk;             // the lane's stack (local memory)
+    int sp;               // next free word of it; the first entry is a YRT_REF_DONE guard, so a pop needs no emptiness test
     bool top, found;
     HitRec hit;
 
@@ -126,7 +130,7 @@ struct Tracer {
         sr = make_slabray(o, EXACT ? inv3(d) : inv3_slab(d));
         wo = o; wd = d; wsr = sr;
         tmin = wray.tmin; tmax = wray.tmax;
-        sp = stack;
+        stk = stack; sp = 0;
         push(YRT_REF_DONE, -FLT_MAX);
         si = -1; kind = 0; top = true; found = false;
         cur = sv.n_active_instances > 0 ? sv.tlas_root : YRT_REF_DONE;
@@ -146,23 +150,31 @@ struct Tracer {
     // (YRT_REF_DONE, entry distance -inf like the sentinel's) ends the traversal without an emptiness test.  At the top
     // level only the slab-test operands are read (the fused test needs neither o nor d, and the instance entry
     // transforms wo / wd), so (o, d) keep the last instance's values there; the reference's slab formula (EXACT) reads o.
+    YRT_HD void pop_entry() {
+        if (CULL) {
+            // only the stack pointer moves inside the loop (no other state is live across its back edge)
+            const float lim = accept_limit();
+            do { sp -= 2; } while (!(int_as_float(stk[sp + 1]) <= lim));
+            cur = stk[sp];
+        } else {
+            cur = stk[--sp];
+        }
+    }
     YRT_HD void pop() {
-        for (;;) {
-            sp -= ENTRY;
-            cur = sp[0];
-            if (CULL && !(int_as_float(sp[1]) <= accept_limit())) continue;
-            if (cur != YRT_REF_SENTINEL) return;
+        pop_entry();
+        if (cur == YRT_REF_SENTINEL) {
             top = true;
             if (EXACT) o = wo;
             sr = wsr;
+            pop_entry();
         }
     }
     YRT_HD void push(int ref, float e) {
-        sp[0] = ref;
-        if (CULL) sp[1] = float_as_int(e);
+        stk[sp] = ref;
+        if (CULL) stk[sp + 1] = float_as_int(e);
         sp += ENTRY;
     }
-    YRT_HD int depth_of(const int* stack) const { return (int)(sp - stack) / ENTRY; }
+    YRT_HD int depth_of(const int*) const { return sp / ENTRY; }
 
     // both boxes of one pair against the current ray and the current tmax
     YRT_HD void test_pair(const float4& p0, const float4& p1, const float4& p2, bool& h0, bool& h1, float& e0, float& e1, TraceCounters* ctr) {
@@ -222,21 +234,23 @@ struct Tracer {
             if (top) ctr->tlas_box_tests += nb;
         }
         if (ANY && YRT_ANY_UNORDERED) {
-            // entered children in stored order: the first becomes the next node, the others wait on the stack
-            int nxt = YRT_REF_DONE;
-            bool have = false;
-            if (h3) { nxt = c3; have = true; }
-            if (h2) { if (have) push(nxt, 0.f); nxt = c2; have = true; }
-            if (h1) { if (have) push(nxt, 0.f); nxt = c1; have = true; }
-            if (h0) { if (have) push(nxt, 0.f); nxt = c0; have = true; }
+            // entered children in stored order: the first becomes the next node, the others wait on the stack.
+            // Branch-free: every entered child stores the candidate it displaces at *sp, and sp advances only if there
+            // was one (a store that is not followed by an advance is overwritten or never read).
+            int nxt = YRT_REF_DONE, adv = 0;
+            if (h3) { nxt = c3; adv = 1; }
+            if (h2) { stk[sp] = nxt; sp += adv; nxt = c2; adv = 1; }
+            if (h1) { stk[sp] = nxt; sp += adv; nxt = c1; adv = 1; }
+            if (h0) { stk[sp] = nxt; sp += adv; nxt = c0; adv = 1; }
             if (ctr && depth_of(stack) > ctr->max_stack) ctr->max_stack = depth_of(stack);
-            if (have) cur = nxt; else pop();
+            if (adv) cur = nxt; else pop();
         } else {
             const float inf = int_as_float(0x7f800000);
             if (!h0) e0 = inf;
             if (!h1) e1 = inf;
             if (!h2) e2 = inf;
             if (!h3) e3 = inf;
+#if YRT_WIDE_ORDER == 0
             // tournament: winner and loser of each pair, then of the two winners
             bool sa = e1 < e0, sb = e3 < e2;
             int wa = sa ? c1 : c0, la = sa ? c0 : c1, wb = sb ? c3 : c2, lb = sb ? c2 : c3;
@@ -260,6 +274,27 @@ struct Tracer {
             } else {
                 pop();
             }
+#else
+            // nearest entered child next; the others go onto the stack in stored order (their entry distances decide at
+            // pop time whether they are still worth a visit)
+            float em = fminf(fminf(e0, e1), fminf(e2, e3));
+            if (em < inf) {
+                int w = c3;
+                bool t2 = e2 == em, t1 = e1 == em, t0 = e0 == em;
+                if (t2) w = c2;
+                if (t1) w = c1;
+                if (t0) w = c0;
+                const bool p3 = h3 && (t0 || t1 || t2), p2 = h2 && !(t2 && !t1 && !t0), p1 = h1 && !(t1 && !t0), p0 = h0 && !t0;
+                if (p3) push(c3, e3);
+                if (p2) push(c2, e2);
+                if (p1) push(c1, e1);
+                if (p0) push(c0, e0);
+                if (ctr && depth_of(stack) > ctr->max_stack) ctr->max_stack = depth_of(stack);
+                cur = w;
+            } else {
+                pop();
+            }
+#endif
         }
     }
 #else

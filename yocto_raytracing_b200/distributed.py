@@ -136,12 +136,17 @@ class SharedFrame:
         return torch.as_tensor(holder, device=torch.device("cuda", torch.cuda.current_device()))
 
     def render(self, scene, samples: int, amb=0.1, tile_rows: int = 1, want_stats: bool = False):
-        """Render this rank's rows into the shared frame and join the completion barrier (stream-ordered, no host sync)."""
+        """Render this rank's rows into the shared frame between two stream-ordered barriers (no host sync): the first keeps
+        any rank from storing rows of this frame while rank 0 may still be reading the previous one (rank 0 joins it only
+        when it is called for this frame, i.e. after its reads of the previous frame were enqueued on the same stream); the
+        second completes on rank 0 only after every rank's stores of this frame."""
         dev = torch.device("cuda", torch.cuda.current_device())
         st = torch.cuda.current_stream(dev).cuda_stream
+        if self.world > 1:
+            dist.all_reduce(self._token, group=self.group)
         stats = scene.render_rows_into_frame(self.ptr, self.width, self.height, samples, amb, tile_rows, self.rank, self.world, st, want_stats)
         if self.world > 1:
-            dist.all_reduce(self._token, group=self.group)   # completes on rank 0 only after every rank's stores were issued
+            dist.all_reduce(self._token, group=self.group)
         return stats
 
     def close(self):
@@ -152,3 +157,59 @@ class SharedFrame:
             else:
                 lib.yrt_frame_release(self._ptr)
             self._ptr = None
+
+
+class SharedHostFrame:
+    """The full framebuffer in HOST memory shared by all ranks of the node (POSIX shared memory, page-locked by every rank):
+    each rank renders its interleaved rows and copies them itself into their final positions — one pitched device->host
+    copy per rank over that GPU's own PCIe link, all ranks at once — so the frame reaches the host N times faster than
+    through rank 0's single link, and the GPUs exchange nothing.  The per-frame synchronisation is one barrier: after it,
+    every rank's rows are in the frame.  A second barrier at the start of the next frame keeps ranks from overwriting rows
+    the consumer (rank 0) is still reading."""
+
+    def __init__(self, width: int, height: int, group=None):
+        from multiprocessing import shared_memory
+        self.width, self.height, self.group = width, height, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        nbytes = width * height * 16
+        name = [None]
+        if self.rank == 0:
+            self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            name[0] = self._shm.name
+        if self.world > 1:
+            dist.broadcast_object_list(name, src=0, group=group)
+            if self.rank != 0:
+                self._shm = shared_memory.SharedMemory(name=name[0])
+        self.array = np.ndarray((height, width, 4), np.float32, buffer=self._shm.buf)
+        self._ptr = self.array.ctypes.data
+        self._pinned = False
+        if torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(self._ptr, nbytes, 1)   # cudaHostRegisterPortable
+            self._pinned = int(rc) == 0
+        self._token = torch.zeros(1, device=torch.device("cuda", torch.cuda.current_device())) if torch.cuda.is_available() else None
+        self._frames = 0
+
+    def render(self, scene, samples: int, amb=0.1, tile_rows: int = 1, want_stats: bool = False):
+        """Render this rank's rows into the shared host frame; returns after every rank's rows of this frame have landed."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        st = torch.cuda.current_stream(dev).cuda_stream
+        if self.world > 1 and self._frames > 0:
+            dist.barrier(group=self.group)        # the consumer is done with the previous frame (it called render again)
+        stats = scene.render_rows_to_host(self._ptr, self.width, self.height, samples, amb, tile_rows, self.rank, self.world, st, want_stats)
+        torch.cuda.current_stream(dev).synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)        # every rank's copies have completed
+        self._frames += 1
+        return stats
+
+    def close(self):
+        try:
+            if self._pinned:
+                torch.cuda.cudart().cudaHostUnregister(self._ptr)
+            self.array = None
+            self._shm.close()
+            if self.rank == 0:
+                self._shm.unlink()
+        except Exception:
+            pass

@@ -125,6 +125,28 @@ class Scene:
                                                      C.byref(st) if st is not None else None))
         return st
 
+    def render_rows_to_host(self, h_ptr: int, width: int, height: int, samples: int, amb=0.1, tile_rows: int = 1, rank: int = 0,
+                            world: int = 1, stream: int = 0, want_stats: bool = False):
+        """yrt_render_rows_to_host: this rank's rows to their final positions of a HOST frame at h_ptr (whole image, float4)."""
+        a = np.broadcast_to(np.asarray(amb, np.float32), (3,))
+        amb3 = (C.c_float * 3)(*[float(x) for x in a])
+        st = Stats() if want_stats else None
+        check(_lib.load().yrt_render_rows_to_host(self._h, C.byref(self._cam), amb3, int(width), int(height), int(samples), int(tile_rows),
+                                                  int(rank), int(world), C.c_void_p(h_ptr), C.c_void_p(stream),
+                                                  C.byref(st) if st is not None else None))
+        return st
+
+    def set_camera(self, cam16) -> None:
+        """Replace the camera (16 floats: frame x, y, z, o, then fovy, aspect, aperture, focus) used by the render calls."""
+        c = np.asarray(cam16, np.float32).reshape(16)
+        for i in range(12):
+            self._cam.frame[i] = float(c[i])
+        self._cam.fovy, self._cam.aspect, self._cam.aperture, self._cam.focus = (float(x) for x in c[12:16])
+
+    def prepare(self, width: int, height: int, samples: int) -> None:
+        """yrt_scene_prepare: allocate the render workspace of that frame size now."""
+        check(_lib.load().yrt_scene_prepare(self._h, int(width), int(height), int(samples)))
+
     def stats_begin(self) -> None:
         """Open deferred statistics: following render_rows_into frames record events/counters without host syncs."""
         check(_lib.load().yrt_stats_begin(self._h))
