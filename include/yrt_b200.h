@@ -156,7 +156,12 @@ int yrt_scene_prepare(yrt_scene* scn, int width, int height, int samples);
  * opted in with yrt_set_option("allow_nonrigid", 1) — then the same per-instance arithmetic runs in this library's visit
  * order and the image may differ from the reference's where such instances overlap.  Pure host function, needs no GPU. */
 int yrt_desc_nonrigid_instances(const yrt_scene_desc* desc);
-/* process-wide options; unknown names return YRT_ERR_INVALID.  "allow_nonrigid" (0/1, default 0): see above. */
+/* process-wide options; unknown names return YRT_ERR_INVALID.
+ *   "allow_nonrigid"  (0/1, default 0): see above.
+ *   "pin_host_frames" (0/1, default 0): yrt_render / yrt_render_ldr page-lock the caller's output buffer the first time they
+ *                     see it and keep it registered while the same buffer keeps coming back (device->host copies into
+ *                     pageable memory are staged by the driver).  The registration outlives the call: only for callers
+ *                     that keep the buffer alive, like the CLI. */
 int yrt_set_option(const char* name, int value);
 
 /* Optional replacement of save_image(filename, image4b) (src/image.cpp:41-44, stb_image_write's single-threaded PNG
@@ -174,9 +179,8 @@ int yrt_image_width(const yrt_camera* cam, int resolution);
  * `samples` is the per-axis count N (N*N samples per pixel, src/raytrace.cpp:232-234).
  * rgba_out: HOST buffer, width*height*4 floats, row-major pixels[j*width+i] like image4f
  * (src/image.h:15).  Uses every GPU given to yrt_init: interleaved row tiles, and every GPU copies its
- * own rows into rgba_out over its own PCIe link (no exchange between GPUs).  A large rgba_out that is not
- * page-locked yet is registered with the driver on first sight and stays registered while the same buffer
- * keeps coming back. */
+ * own rows into rgba_out over its own PCIe link (no exchange between GPUs); see "pin_host_frames" for
+ * pageable output buffers. */
 int yrt_render(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height,
                int samples, float* rgba_out, yrt_stats* stats);
 

@@ -40,12 +40,15 @@ int copy_rows_to_host(const void* d_packed, void* h_frame, int width, int height
     return YRT_OK;
 }
 
-// the caller's frame buffers are page-locked on first sight (and stay so until another buffer takes the slot or the library
-// is re-initialised): device->host copies into pageable memory are staged and serialised by the driver
+// With the option "pin_host_frames" the caller's frame buffers are page-locked on first sight and stay so until another
+// buffer takes the slot or the library is re-initialised (device->host copies into pageable memory are staged by the
+// driver).  Opt-in, because the registration outlives the call: the caller must keep such a buffer alive (and not hand its
+// address range back to the allocator) while it is registered.
 struct HostPin { void* p = nullptr; size_t n = 0; };
 HostPin g_pins[2];
+int g_pin_host_frames = 0;   // yrt_set_option("pin_host_frames")
 void pin_host(int slot, void* p, size_t n) {
-    if (getenv("YRT_NO_HOST_REGISTER") || n < ((size_t)1 << 20)) return;
+    if (!g_pin_host_frames || n < ((size_t)1 << 20)) return;
     HostPin& h = g_pins[slot];
     if (h.p == p && h.n == n) return;
     if (h.p) { cudaHostUnregister(h.p); h.p = nullptr; }
@@ -170,6 +173,7 @@ int yrt_desc_nonrigid_instances(const yrt_scene_desc* desc) {
 
 int yrt_set_option(const char* name, int value) {
     if (name && !strcmp(name, "allow_nonrigid")) { g_allow_nonrigid = value != 0; return YRT_OK; }
+    if (name && !strcmp(name, "pin_host_frames")) { g_pin_host_frames = value != 0; if (!value) unpin_all(); return YRT_OK; }
     set_error("yrt_set_option: unknown option '%s'", name ? name : "(null)");
     return YRT_ERR_INVALID;
 }

@@ -79,7 +79,10 @@ struct PhaseTimer;
 
 // per-device render workspace (grown on demand, reused across frames)
 struct Workspace {
-    DevBuf hit, P, vis, rad, ray_o, ray_d, pstack, act0, act1, counters, stats, rows, rows8;
+    DevBuf hit, P, vis, rad, ray_o, ray_d, act0, act1, counters, stats, rows, rows8;
+    DevBuf pstack_lvl[66], pstack_tab;   // per recursion level: {c, kr, la} per slot, allocated when first reached; table of their pointers
+    float4** h_pstack_tab = nullptr;     // pinned host copy of the table
+    int pstack_levels = 0;
     size_t cap_slots = 0;
     int cap_lights = 0;
     int cap_depth = 0;
@@ -87,6 +90,7 @@ struct Workspace {
     cudaEvent_t ev_counts[66] = {};      // one per wave (YRT_MAX_WAVES + 2)
     ~Workspace() {
         if (h_counts) { cudaFreeHost(h_counts); for (auto e : ev_counts) if (e) cudaEventDestroy(e); }
+        if (h_pstack_tab) cudaFreeHost(h_pstack_tab);
     }
 };
 

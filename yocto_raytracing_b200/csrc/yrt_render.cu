@@ -212,7 +212,8 @@ struct FrameCounters { unsigned long long hits, reflections, misses, truncated, 
 
 struct ShadeBuffers {
     const float4* hit;
-    float4 *ray_o, *ray_d, *pstack, *rad;
+    float4 *ray_o, *ray_d, *rad;
+    float4* const* pstack;        // one plane of {c, kr, la} per recursion level (device table of device pointers)
     int* next_act;
     int* next_count;
     FrameCounters* fc;
@@ -241,7 +242,7 @@ __device__ __forceinline__ bool shade_slot(const SceneView& sv, const BatchParam
             value = c + la;
         }
         if (spawn) {
-            float4* f = sb.pstack + ((size_t)depth * cap + slot) * 3;
+            float4* f = sb.pstack[depth] + (size_t)slot * 3;
             f[0] = mk4(c.x, c.y, c.z, 0.f);
             f[1] = mk4(kr.x, kr.y, kr.z, 0.f);
             f[2] = mk4(la.x, la.y, la.z, 0.f);
@@ -252,7 +253,7 @@ __device__ __forceinline__ bool shade_slot(const SceneView& sv, const BatchParam
     if (!spawn) {
         // unwind the recursion: each level closes with c + col*kr, then + la (raytrace.cpp:203,206)
         for (int d = depth - 1; d >= 0; d--) {
-            const float4* f = sb.pstack + ((size_t)d * cap + slot) * 3;
+            const float4* f = sb.pstack[d] + (size_t)slot * 3;
             value = combine_reflection(xyz(f[0]), value, xyz(f[1]), xyz(f[2]));
         }
         sb.rad[slot] = mk4(value.x, value.y, value.z, 1.0f);
@@ -445,7 +446,8 @@ static int ensure_workspace(DevScene& ds, Workspace& w, size_t slots, int n_ligh
         if (cd > 0) {
             YRT_TRY(w.ray_o.alloc(sizeof(float4) * cs, dev));
             YRT_TRY(w.ray_d.alloc(sizeof(float4) * cs, dev));
-            YRT_TRY(w.pstack.alloc(sizeof(float4) * 3 * cs * (size_t)cd, dev));
+            for (DevBuf& b : w.pstack_lvl) b.release();   // per-level planes are (re)allocated on demand at the new size
+            w.pstack_levels = 0;
             YRT_TRY(w.act0.alloc(sizeof(int) * cs, dev));
             YRT_TRY(w.act1.alloc(sizeof(int) * cs, dev));
         }
@@ -463,6 +465,22 @@ static int ensure_workspace(DevScene& ds, Workspace& w, size_t slots, int n_ligh
         YRT_CUDA(cudaMemset(ds.dctr.p, 0, sizeof(unsigned long long) * 3 * YRT_DCTR_WORDS));
     }
 #endif
+    return YRT_OK;
+}
+
+// The {c, kr, la} plane of recursion level `level` (48 B per slot) is allocated when a wave first gets that deep — the
+// host is at most one wave ahead of the counts (run_batch), so the memory follows the depth the scene really reaches
+// (+ 2 levels), not the depth cap.  The table of plane pointers lives in device memory and is updated in stream order.
+static int ensure_pstack_level(DevScene& ds, Workspace& w, int level, cudaStream_t st) {
+    if (level < w.pstack_levels) return YRT_OK;
+    YRT_TRY(w.pstack_tab.alloc(sizeof(float4*) * (YRT_MAX_WAVES + 2), ds.device));
+    if (!w.h_pstack_tab) YRT_CUDA(cudaHostAlloc((void**)&w.h_pstack_tab, sizeof(float4*) * (YRT_MAX_WAVES + 2), cudaHostAllocDefault));
+    for (int l = w.pstack_levels; l <= level; l++) {
+        YRT_TRY(w.pstack_lvl[l].alloc(sizeof(float4) * 3 * w.cap_slots, ds.device));
+        w.h_pstack_tab[l] = w.pstack_lvl[l].as<float4>();
+    }
+    w.pstack_levels = level + 1;
+    YRT_CUDA(cudaMemcpyAsync(w.pstack_tab.p, w.h_pstack_tab, sizeof(float4*) * (size_t)w.pstack_levels, cudaMemcpyHostToDevice, st));
     return YRT_OK;
 }
 
@@ -541,8 +559,9 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0
                                                                                                w.P.as<float4>(), workdist_linear(ctr, n, n_dev), dctr ? dctr + YRT_DCTR_WORDS : nullptr);
             pt.end();
         }
+        if (reflective && depth + 1 < depth_cap) YRT_TRY(ensure_pstack_level(ds, w, depth, st));
         ShadeBuffers sb;
-        sb.hit = w.hit.as<float4>(); sb.ray_o = w.ray_o.as<float4>(); sb.ray_d = w.ray_d.as<float4>(); sb.pstack = w.pstack.as<float4>();
+        sb.hit = w.hit.as<float4>(); sb.ray_o = w.ray_o.as<float4>(); sb.ray_d = w.ray_d.as<float4>(); sb.pstack = w.pstack_tab.as<float4*>();
         sb.rad = w.rad.as<float4>(); sb.next_act = reflective ? act_bufs[depth & 1] : nullptr; sb.next_count = (int*)(counts + depth + 1); sb.fc = fc;
         if (nl > 0) {
             YRT_TRY(ring.get(&ctr));

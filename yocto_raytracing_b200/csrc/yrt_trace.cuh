@@ -17,9 +17,6 @@
 #ifndef YRT_POP_CULL
 #define YRT_POP_CULL 1   /* closest hit: a stack entry carries the entry distance of its box and is dropped at pop time if the hit found since then is nearer */
 #endif
-#ifndef YRT_WIDE_ORDER
-#define YRT_WIDE_ORDER 0   /* closest hit, 4-wide nodes: 0 = entered children sorted by entry distance (tournament), 1 = nearest first, the rest in stored order */
-#endif
 #ifndef YRT_ANY_UNORDERED
 #define YRT_ANY_UNORDERED 1  /* any-hit rays: children are entered in stored order, no entry-distance compare (the answer is order independent) */
 #endif
@@ -250,7 +247,6 @@ struct Tracer {
             if (!h1) e1 = inf;
             if (!h2) e2 = inf;
             if (!h3) e3 = inf;
-#if YRT_WIDE_ORDER == 0
             // tournament: winner and loser of each pair, then of the two winners
             bool sa = e1 < e0, sb = e3 < e2;
             int wa = sa ? c1 : c0, la = sa ? c0 : c1, wb = sb ? c3 : c2, lb = sb ? c2 : c3;
@@ -274,27 +270,6 @@ struct Tracer {
             } else {
                 pop();
             }
-#else
-            // nearest entered child next; the others go onto the stack in stored order (their entry distances decide at
-            // pop time whether they are still worth a visit)
-            float em = fminf(fminf(e0, e1), fminf(e2, e3));
-            if (em < inf) {
-                int w = c3;
-                bool t2 = e2 == em, t1 = e1 == em, t0 = e0 == em;
-                if (t2) w = c2;
-                if (t1) w = c1;
-                if (t0) w = c0;
-                const bool p3 = h3 && (t0 || t1 || t2), p2 = h2 && !(t2 && !t1 && !t0), p1 = h1 && !(t1 && !t0), p0 = h0 && !t0;
-                if (p3) push(c3, e3);
-                if (p2) push(c2, e2);
-                if (p1) push(c1, e1);
-                if (p0) push(c0, e0);
-                if (ctr && depth_of(stack) > ctr->max_stack) ctr->max_stack = depth_of(stack);
-                cur = w;
-            } else {
-                pop();
-            }
-#endif
         }
     }
 #else
