@@ -46,14 +46,14 @@ oracle: oracle/liboracle.so
 oracle/liboracle.so: oracle/yrt_oracle.c oracle/yrt_oracle.h include/yrt_b200.h
 	$(ORACLE_CC) -std=c11 -O2 -fPIC -shared -ffp-contract=off -fopenmp -o $@ oracle/yrt_oracle.c -lm
 
-hostemu: tests/host_emu/libyrt_hostemu.so tests/host_emu/libyrt_hostemu_bin.so tests/host_emu/libyrt_hostemu_pack.so
-# the same emulation with the library's other node layouts (build options, see yrt_scene.cuh): binary nodes (-DYRT_WIDE=2) and
-# child references packed into the half-extents (-DYRT_PACK_REFS=1) — keeps them under test without a GPU
+hostemu: tests/host_emu/libyrt_hostemu.so tests/host_emu/libyrt_hostemu_bin.so tests/host_emu/libyrt_hostemu_wide.so
+# the same emulation with the other assignments of node arity to ray kind (build options, see yrt_scene.cuh): both ray kinds on
+# binary records / both on 4-wide records — keeps every visit routine under test without a GPU
 EMUFLAGS := -O2 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-ffp-contract=off,-fopenmp -shared
 tests/host_emu/libyrt_hostemu_bin.so: tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu $(HDRS)
-	$(NVCC) $(EMUFLAGS) -DYRT_WIDE=2 -I$(CSRC) -o $@ tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu -lgomp
-tests/host_emu/libyrt_hostemu_pack.so: tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu $(HDRS)
-	$(NVCC) $(EMUFLAGS) -DYRT_PACK_REFS=1 -I$(CSRC) -o $@ tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu -lgomp
+	$(NVCC) $(EMUFLAGS) -DYRT_WIDE_CLOSEST=2 -DYRT_WIDE_ANY=2 -I$(CSRC) -o $@ tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu -lgomp
+tests/host_emu/libyrt_hostemu_wide.so: tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu $(HDRS)
+	$(NVCC) $(EMUFLAGS) -DYRT_WIDE_CLOSEST=4 -DYRT_WIDE_ANY=4 -I$(CSRC) -o $@ tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu -lgomp
 tests/host_emu/libyrt_hostemu.so: tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu $(HDRS)
 	$(NVCC) $(EMUFLAGS) $(EXTRA) -I$(CSRC) -o $@ tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu -lgomp
 

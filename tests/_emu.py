@@ -22,7 +22,8 @@ _libs = {}
 
 
 def lib(variant=""):
-    """The emulation library; variants: "bin" = -DYRT_WIDE=2 (binary traversal nodes), "pack" = -DYRT_PACK_REFS=1."""
+    """The emulation library; variants: "bin" = both ray kinds on binary node records, "wide" = both on 4-wide records
+    (the default build: closest-hit rays binary, any-hit rays 4-wide)."""
     if variant not in _libs:
         l = C.CDLL(_path(variant))
         l.emu_last_error.restype = C.c_char_p

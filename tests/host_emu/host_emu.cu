@@ -21,8 +21,8 @@ using namespace yrt;
 namespace {
 
 struct EmuLbvh {
-    std::vector<float4> nodes;
-    std::vector<int> order, seg_root, seg_depth, seg_need, seg_box_lo, seg_box_hi;
+    std::vector<float4> nodes2, nodes4;
+    std::vector<int> order, seg_root, seg_depth, seg_need2, seg_need4, seg_box_lo, seg_box_hi;
 };
 
 void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi, const int* seg_of, const int* seg_first, int leaf_size,
@@ -36,19 +36,21 @@ void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi
     std::vector<int> left(ni), right(ni), rfirst(ni), rlast(ni), pint(ni), pleaf(std::max(n, 1), -1), flags(ni);
     std::vector<float4> nlo(ni), nhi(ni);
     std::vector<int> count(ni), new_slot(std::max(n, 1)), order_tmp(std::max(n, 1)), pleaf_tmp(std::max(n, 1));
-    out.nodes.assign(YRT_NODE_STRIDE * ni, mk4(0, 0, 0, 0));
+    out.nodes2.assign(YRT_NODE_STRIDE(2) * ni, mk4(0, 0, 0, 0));
+    out.nodes4.assign(YRT_NODE_STRIDE(4) * ni, mk4(0, 0, 0, 0));
     out.seg_root.assign(n_seg, 0);
     out.seg_depth.assign(n_seg, 0);
-    out.seg_need.assign(n_seg, 0);
-    std::vector<int> need(ni, 0);
+    out.seg_need2.assign(n_seg, 0);
+    out.seg_need4.assign(n_seg, 0);
+    std::vector<int> need2(ni, 0), need4(ni, 0);
     LbvhArrays a;
     a.n = n; a.n_seg = n_seg; a.box_lo = lo.data(); a.box_hi = hi.data(); a.seg_of = seg_of; a.seg_first = seg_first;
     a.seg_cent_lo = cent_lo.data(); a.seg_cent_hi = cent_hi.data(); a.seg_box_lo = out.seg_box_lo.data(); a.seg_box_hi = out.seg_box_hi.data();
     a.keys = keys.data(); a.order = out.order.data(); a.left = left.data(); a.right = right.data();
     a.range_first = rfirst.data(); a.range_last = rlast.data(); a.parent_int = pint.data(); a.parent_leaf = pleaf.data();
     a.count = count.data(); a.new_slot = new_slot.data(); a.order_tmp = order_tmp.data(); a.parent_leaf_tmp = pleaf_tmp.data();
-    a.flags = flags.data(); a.node_lo = nlo.data(); a.node_hi = nhi.data(); a.nodes = out.nodes.data();
-    a.seg_root = out.seg_root.data(); a.seg_depth = out.seg_depth.data(); a.seg_need = out.seg_need.data(); a.need = need.data(); a.leaf_size = leaf_size; a.ref_offset = ref_offset; a.size_bits = size_bits;
+    a.flags = flags.data(); a.node_lo = nlo.data(); a.node_hi = nhi.data(); a.nodes2 = out.nodes2.data(); a.nodes4 = out.nodes4.data();
+    a.seg_root = out.seg_root.data(); a.seg_depth = out.seg_depth.data(); a.seg_need2 = out.seg_need2.data(); a.seg_need4 = out.seg_need4.data(); a.need2 = need2.data(); a.need4 = need4.data(); a.leaf_size = leaf_size; a.ref_offset = ref_offset; a.size_bits = size_bits;
     a.rotate_pairs = rotate_pairs;
     for (int s = 0; s < n_seg; s++) seg_bounds_init_item(a, s);
     for (int i = 0; i < n; i++) seg_bounds_item(a, i);
@@ -91,7 +93,7 @@ struct EmuScene {
     EmuLbvh blas, tlas;
     std::vector<float4> prim_recs, prim_attrs, inst_recs;
     std::vector<int> prim_rank, inst_rank;
-    std::vector<float4> nodes;   // BLAS nodes then TLAS nodes, like the device array
+    std::vector<float4> nodes2, nodes4;   // BLAS nodes then TLAS nodes, like the device arrays
     SceneView view;
     int blas_depth = 0, tlas_depth = 0, stack_need = 0;
 };
@@ -165,8 +167,10 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
     emu_lbvh(na, 1, ilo, ihi, seg_of.data(), sf, leaf_tlas, es.tlas, nb_int, getenv("YRT_SIZE_BITS_TLAS") ? atoi(getenv("YRT_SIZE_BITS_TLAS")) : YRT_SIZE_BITS_TLAS,
              getenv("YRT_ROTATE_TLAS") ? atoi(getenv("YRT_ROTATE_TLAS")) : YRT_ROTATE_ROUNDS_TLAS,
              getenv("YRT_ROTATE_PAIRS_TLAS") ? atoi(getenv("YRT_ROTATE_PAIRS_TLAS")) : YRT_ROTATE_PAIRS_TLAS);
-    es.nodes.assign(es.blas.nodes.begin(), es.blas.nodes.begin() + YRT_NODE_STRIDE * (size_t)nb_int);
-    es.nodes.insert(es.nodes.end(), es.tlas.nodes.begin(), es.tlas.nodes.end());
+    es.nodes2.assign(es.blas.nodes2.begin(), es.blas.nodes2.begin() + YRT_NODE_STRIDE(2) * (size_t)nb_int);
+    es.nodes2.insert(es.nodes2.end(), es.tlas.nodes2.begin(), es.tlas.nodes2.end());
+    es.nodes4.assign(es.blas.nodes4.begin(), es.blas.nodes4.begin() + YRT_NODE_STRIDE(4) * (size_t)nb_int);
+    es.nodes4.insert(es.nodes4.end(), es.tlas.nodes4.begin(), es.tlas.nodes4.end());
     es.inst_recs.assign(4 * (size_t)std::max(na, 1), mk4(0, 0, 0, 0));
     es.inst_rank.assign(std::max(na, 1), 0);
     for (int k = 0; k < na; k++) {
@@ -182,10 +186,14 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
     }
     es.blas_depth = es.blas.seg_depth.empty() ? 0 : *std::max_element(es.blas.seg_depth.begin(), es.blas.seg_depth.end());
     es.tlas_depth = es.tlas.seg_depth[0];
-    es.stack_need = es.tlas.seg_need[0] + (es.blas.seg_need.empty() ? 0 : *std::max_element(es.blas.seg_need.begin(), es.blas.seg_need.end())) + 3;
+    {
+        const int n2 = es.tlas.seg_need2[0] + (es.blas.seg_need2.empty() ? 0 : *std::max_element(es.blas.seg_need2.begin(), es.blas.seg_need2.end())) + 3;
+        const int n4 = es.tlas.seg_need4[0] + (es.blas.seg_need4.empty() ? 0 : *std::max_element(es.blas.seg_need4.begin(), es.blas.seg_need4.end())) + 3;
+        es.stack_need = std::max(YRT_WIDE_CLOSEST == 4 ? n4 : n2, YRT_WIDE_ANY == 4 ? n4 : n2);
+    }
     if (es.stack_need > YRT_STACK_CAP) { set_error("emu: tree too deep"); return YRT_ERR_UNSUPPORTED; }
     SceneView& v = es.view;
-    v.nodes = es.nodes.data(); v.inst_recs = es.inst_recs.data();
+    v.nodes2 = es.nodes2.data(); v.nodes4 = es.nodes4.data(); v.inst_recs = es.inst_recs.data();
     v.prim_recs = es.prim_recs.data(); v.prim_attrs = es.prim_attrs.data(); v.mat_recs = hs.mat_recs.data();
     v.light_recs = hs.light_recs.data(); v.tex_rgba8 = hs.tex_rgba8.data(); v.tex_info = hs.tex_info.data();
     v.inst_rank = es.inst_rank.data(); v.prim_rank = es.prim_rank.data();

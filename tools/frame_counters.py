@@ -14,7 +14,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 FLOP_BOX, FLOP_ELEM, FLOP_INST = 26.0, 54.0, 43.0       # SURVEY 8d unit costs (reference arithmetic)
-BYTES_NODE4, BYTES_ELEM, BYTES_INST = 112.0, 48.0, 64.0   # bytes a lane reads per 4-wide node visit / element test / instance entry
+BYTES_NODE = {2: 56.0, 4: 112.0}                          # bytes a lane reads per node visit: binary record (3 quads + 8 B) / 4-wide record (7 quads)
+BYTES_ELEM, BYTES_INST = 48.0, 64.0                       # ... per element test / instance entry
+ARITY = {"camera_rays": 2, "mirror_rays": 2, "shadow_rays": 4}   # default build: YRT_WIDE_CLOSEST = 2, YRT_WIDE_ANY = 4 (csrc/yrt_scene.cuh)
 
 
 def main():
@@ -48,8 +50,8 @@ def main():
             continue
         r = float(rays)
         flops = (box * FLOP_BOX + elem * FLOP_ELEM + inst * FLOP_INST) / r
-        byts = (visits * BYTES_NODE4 + elem * BYTES_ELEM + inst * BYTES_INST) / r
-        res_[cls] = {"rays": rays, "node_visits_per_ray": visits / r, "box_tests_per_ray": box / r, "tlas_box_tests_per_ray": tbox / r,
+        byts = (visits * BYTES_NODE[ARITY[cls]] + elem * BYTES_ELEM + inst * BYTES_INST) / r
+        res_[cls] = {"rays": rays, "node_arity": ARITY[cls], "node_visits_per_ray": visits / r, "box_tests_per_ray": box / r, "tlas_box_tests_per_ray": tbox / r,
                      "element_tests_per_ray": elem / r, "instance_entries_per_ray": inst / r, "flops_per_ray": flops, "l1_bytes_per_ray": byts}
     print(json.dumps(res_))
     return 0

@@ -278,9 +278,9 @@ struct LbvhIo {
     int n, n_seg, leaf_size, ref_offset, size_bits, rotate_rounds, rotate_pairs;
     float4 *box_lo, *box_hi;       // [n] item bounds
     const int *seg_of, *seg_first;
-    float4* nodes;                 // [YRT_NODE_STRIDE * (n-1)] in the shared node array
+    float4 *nodes2, *nodes4;       // this tree set's records in the two shared node arrays (binary: 4, 4-wide: 8 float4 per node)
     // out (persistent arena)
-    int *seg_root, *seg_depth, *seg_need;   // [n_seg]
+    int *seg_root, *seg_depth, *seg_need2, *seg_need4;   // [n_seg]
     int *seg_box_lo, *seg_box_hi;           // [3*n_seg] ordered ints
     int* order;                             // [n] item id at sorted slot (temp arena, read by the gather kernels)
 };
@@ -308,14 +308,16 @@ static int lbvh_build(cudaStream_t st, Arena& tmp, LbvhIo& io) {
     a.node_lo = tmp.take<float4>(ni); a.node_hi = tmp.take<float4>(ni);
     a.count = tmp.take<int>(ni); a.new_slot = tmp.take<int>(nn);
     a.order_tmp = tmp.take<int>(nn); a.parent_leaf_tmp = tmp.take<int>(nn);
-    a.need = tmp.take<int>(ni);
+    a.need2 = tmp.take<int>(ni);
+    a.need4 = tmp.take<int>(ni);
     int* ghist = tmp.take<int>(radix_hist_ints(n));
     if (!tmp.base) return YRT_OK;   // dry pass
 
-    a.nodes = io.nodes; a.ref_offset = io.ref_offset; a.size_bits = io.size_bits; a.rotate_pairs = io.rotate_pairs;
-    a.seg_root = io.seg_root; a.seg_depth = io.seg_depth; a.seg_need = io.seg_need; a.leaf_size = io.leaf_size;
+    a.nodes2 = io.nodes2; a.nodes4 = io.nodes4; a.ref_offset = io.ref_offset; a.size_bits = io.size_bits; a.rotate_pairs = io.rotate_pairs;
+    a.seg_root = io.seg_root; a.seg_depth = io.seg_depth; a.seg_need2 = io.seg_need2; a.seg_need4 = io.seg_need4; a.leaf_size = io.leaf_size;
     YRT_CUDA(cudaMemsetAsync(a.parent_leaf, 0xff, sizeof(int) * nn, st));   // -1: no parent
-    YRT_CUDA(cudaMemsetAsync(io.nodes, 0, sizeof(float4) * YRT_NODE_STRIDE * ni, st));
+    YRT_CUDA(cudaMemsetAsync(io.nodes2, 0, sizeof(float4) * YRT_NODE_STRIDE(2) * ni, st));
+    YRT_CUDA(cudaMemsetAsync(io.nodes4, 0, sizeof(float4) * YRT_NODE_STRIDE(4) * ni, st));
     k_seg_init<<<grid_for(n_seg), 256, 0, st>>>(a);
     if (n > 0) {
         k_seg_bounds<<<grid_for(n), 256, 0, st>>>(a);
@@ -401,12 +403,12 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
     int *d_inst_shape = nullptr, *d_inst_mat = nullptr, *d_active = nullptr, *d_prim_rank_in = nullptr, *d_inst_rank_in = nullptr, *d_has_uv = nullptr,
         *d_tl_seg_of = nullptr, *d_tl_seg_first = nullptr, *d_results = nullptr, *d_shape_kind = nullptr;
     float* d_inst_frame = nullptr;
-    float4 *plo = nullptr, *phi = nullptr, *ilo = nullptr, *ihi = nullptr, *d_nodes = nullptr, *d_prim_recs = nullptr, *d_prim_attrs = nullptr, *d_inst_recs = nullptr;
+    float4 *plo = nullptr, *phi = nullptr, *ilo = nullptr, *ihi = nullptr, *d_nodes2 = nullptr, *d_nodes4 = nullptr, *d_prim_recs = nullptr, *d_prim_attrs = nullptr, *d_inst_recs = nullptr;
     int *d_prim_rank = nullptr, *d_inst_rank = nullptr;
     LbvhIo bo, to;
     const int tl_sf[2] = {0, na};
-    // results block read back in one copy: [blas depth | blas need | tlas depth, need, root]
-    const size_t n_results = 2 * (size_t)nsh + 3;
+    // results block read back in one copy: [blas depth | blas need (binary) | blas need (4-wide) | tlas depth, need2, need4, root]
+    const size_t n_results = 3 * (size_t)nsh + 4;
     Arena keep, tmp;
     for (int pass = 0; pass < 2; pass++) {
         if (pass == 1) {
@@ -429,7 +431,8 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
             return p;
         };
         // products and what the kernels of a frame read
-        d_nodes = keep.take<float4>(YRT_NODE_STRIDE * (size_t)(nb_int + nt_int + 2));
+        d_nodes4 = keep.take<float4>(YRT_NODE_STRIDE(4) * (size_t)(nb_int + nt_int + 2));   // (first in the arena: 256-byte aligned, one line per record)
+        d_nodes2 = keep.take<float4>(YRT_NODE_STRIDE(2) * (size_t)(nb_int + nt_int + 2));
         d_prim_recs = keep.take<float4>(3 * (size_t)std::max(np, 1));
         d_prim_attrs = keep.take<float4>(YRT_ATTR_STRIDE * (size_t)std::max(np, 1));
         d_inst_recs = keep.take<float4>(4 * (size_t)std::max(na, 1));
@@ -478,12 +481,12 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
         int* tl_box_hi = tmp.take<int>(3);
         // ---- BLAS: all shapes in one build ----
         bo.n = np; bo.n_seg = nsh; bo.leaf_size = leaf_blas; bo.ref_offset = 0; bo.size_bits = size_bits_blas; bo.rotate_rounds = rotate_blas; bo.rotate_pairs = rotate_pairs_blas;
-        bo.box_lo = plo; bo.box_hi = phi; bo.seg_of = g.prim_shape; bo.seg_first = g.shape_prim_off; bo.nodes = d_nodes;
-        bo.seg_root = blas_root; bo.seg_depth = d_results; bo.seg_need = d_results + nsh; bo.seg_box_lo = shape_box_lo; bo.seg_box_hi = shape_box_hi;
+        bo.box_lo = plo; bo.box_hi = phi; bo.seg_of = g.prim_shape; bo.seg_first = g.shape_prim_off; bo.nodes2 = d_nodes2; bo.nodes4 = d_nodes4;
+        bo.seg_root = blas_root; bo.seg_depth = d_results; bo.seg_need2 = d_results + nsh; bo.seg_need4 = d_results + 2 * nsh; bo.seg_box_lo = shape_box_lo; bo.seg_box_hi = shape_box_hi;
         // ---- TLAS over active instances ----
         to.n = na; to.n_seg = 1; to.leaf_size = leaf_tlas; to.ref_offset = nb_int; to.size_bits = size_bits_tlas; to.rotate_rounds = rotate_tlas; to.rotate_pairs = rotate_pairs_tlas;
-        to.box_lo = ilo; to.box_hi = ihi; to.seg_of = d_tl_seg_of; to.seg_first = d_tl_seg_first; to.nodes = d_nodes ? d_nodes + YRT_NODE_STRIDE * (size_t)nb_int : nullptr;
-        to.seg_root = d_results + 2 * nsh + 2; to.seg_depth = d_results + 2 * nsh; to.seg_need = d_results + 2 * nsh + 1; to.seg_box_lo = tl_box_lo; to.seg_box_hi = tl_box_hi;
+        to.box_lo = ilo; to.box_hi = ihi; to.seg_of = d_tl_seg_of; to.seg_first = d_tl_seg_first; to.nodes2 = d_nodes2 ? d_nodes2 + YRT_NODE_STRIDE(2) * (size_t)nb_int : nullptr; to.nodes4 = d_nodes4 ? d_nodes4 + YRT_NODE_STRIDE(4) * (size_t)nb_int : nullptr;
+        to.seg_root = d_results + 3 * nsh + 3; to.seg_depth = d_results + 3 * nsh; to.seg_need2 = d_results + 3 * nsh + 1; to.seg_need4 = d_results + 3 * nsh + 2; to.seg_box_lo = tl_box_lo; to.seg_box_hi = tl_box_hi;
         if (pass == 0) {   // sizes of the two builds' temporaries (not shared: the BLAS order is read again at the very end)
             YRT_TRY(lbvh_build(st, tmp, bo));
             YRT_TRY(lbvh_build(st, tmp, to));
@@ -530,19 +533,22 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
                 keep.off / 1e6, tmp.off / 1e6);
 
     ds.blas_depth = *std::max_element(results.begin(), results.begin() + nsh);
-    const int blas_need = *std::max_element(results.begin() + nsh, results.begin() + 2 * nsh);
-    ds.tlas_depth = results[2 * nsh];
-    const int tlas_need = results[2 * nsh + 1], troot = results[2 * nsh + 2];
+    const int blas_need2 = *std::max_element(results.begin() + nsh, results.begin() + 2 * nsh);
+    const int blas_need4 = *std::max_element(results.begin() + 2 * nsh, results.begin() + 3 * nsh);
+    ds.tlas_depth = results[3 * nsh];
+    const int tlas_need2 = results[3 * nsh + 1], tlas_need4 = results[3 * nsh + 2], troot = results[3 * nsh + 3];
     ds.n_blas_nodes = nb_int;
     ds.n_tlas_nodes = nt_int;
     if (na > 0 && troot == YRT_REF_SENTINEL) { set_error("internal: TLAS root not found"); return YRT_ERR_CUDA; }
     // entries below the TLAS root + entries below the deepest BLAS root + guard + sentinel + the "rest of a TLAS leaf" entry
-    ds.stack_need = tlas_need + blas_need + 3;
+    const int need2 = tlas_need2 + blas_need2 + 3, need4 = tlas_need4 + blas_need4 + 3;
+    ds.stack_need = std::max(YRT_WIDE_CLOSEST == 4 ? need4 : need2, YRT_WIDE_ANY == 4 ? need4 : need2);
     if (ds.stack_need > YRT_STACK_CAP) {
         set_error("traversal tree too deep for the stack (%d entries needed: tlas %d + blas %d levels, capacity %d)", ds.stack_need, ds.tlas_depth, ds.blas_depth, YRT_STACK_CAP);
         return YRT_ERR_UNSUPPORTED;
     }
-    v.nodes = d_nodes;
+    v.nodes2 = d_nodes2;
+    v.nodes4 = d_nodes4;
     v.inst_recs = d_inst_recs;
     v.prim_recs = d_prim_recs;
     v.prim_attrs = d_prim_attrs;

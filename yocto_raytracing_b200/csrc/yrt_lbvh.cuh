@@ -141,11 +141,14 @@ struct LbvhArrays {
     float4* node_lo;       // [n-1] refit bounds of internal nodes
     float4* node_hi;
     // outputs
-    float4* nodes;         // [YRT_NODE_STRIDE*(n-1)]
+    float4* nodes2;        // [4*(n-1)] binary node records
+    float4* nodes4;        // [8*(n-1)] 4-wide node records
     int* seg_root;         // [n_seg] root ref per segment
     int* seg_depth;        // [n_seg] max depth (levels of internal nodes) per segment
-    int* need;             // [n-1] traversal stack entries the subtree below a node can occupy (stackneed_item)
-    int* seg_need;         // [n_seg] ... below the segment's root
+    int* need2;            // [n-1] traversal stack entries the subtree below a node can occupy (stackneed_item), binary records
+    int* need4;            // ... 4-wide records
+    int* seg_need2;        // [n_seg] ... below the segment's root
+    int* seg_need4;
     int leaf_size;
     int ref_offset;        // added to every internal-node reference (position of this tree set in the shared node array)
     int size_bits;         // 0..3: top bits of the Morton part hold a size class (see morton_item)
@@ -161,7 +164,8 @@ YRT_HD void seg_bounds_init_item(const LbvhArrays& a, int s) {
     }
     a.seg_root[s] = YRT_REF_SENTINEL;
     a.seg_depth[s] = 0;
-    a.seg_need[s] = 0;
+    a.seg_need2[s] = 0;
+    a.seg_need4[s] = 0;
 }
 
 YRT_HD vec3 box_centroid(const float4& lo, const float4& hi) {   // (bbox.min + bbox.max) / 2, scene.cpp:531
@@ -497,21 +501,30 @@ YRT_HD bool is_leaf_child_(const LbvhArrays& a, int c) {
     return c < 0 || a.range_last[c] - a.range_first[c] + 1 <= a.leaf_size;
 }
 
-// Emit the traversal node of binary internal node i and, if i is exactly a segment, its root ref.
-// YRT_WIDE == 4: the node's slots start as the two binary children; while a slot is free, the internal (non-leaf) slot
-// with the largest surface area is replaced by its own two children (the usual greedy binary -> wide collapse: the box
-// most likely to be entered is the one opened).  Every binary internal node gets a record at its own index, so segment
-// roots and child references need no renumbering; only the records reachable from a root through these wide links are
-// ever read (about one in three), and each is exactly one 128-byte line.
+// Emit the two traversal records of binary internal node i and, if i is exactly a segment, its root ref.
+// Binary record: the two children.  4-wide record: the slots start as the two binary children; while a slot is free, the
+// internal (non-leaf) slot with the largest surface area is replaced by its own two children (the usual greedy binary ->
+// wide collapse: the box most likely to be entered is the one opened).  Every binary internal node gets both records at
+// its own index, so segment roots and child references need no renumbering; of the wide records only those reachable
+// from a root through wide links are ever read (about one in three), and each is exactly one 128-byte line.
 YRT_HD void emit_item(const LbvhArrays& a, int i) {
-    int c[YRT_WIDE];
-    float4 lo[YRT_WIDE], hi[YRT_WIDE];
-    int nb = 2;
+    int c[4];
+    float4 lo[4], hi[4];
+    nodebox bx[4];
+    int ref[4];
     c[0] = a.left[i]; c[1] = a.right[i];
     child_box_(a, c[0], lo[0], hi[0]);
     child_box_(a, c[1], lo[1], hi[1]);
-#if YRT_WIDE == 4
-    while (nb < YRT_WIDE) {
+    auto finish = [&](int k) {
+        box_center_half(lo[k].x, hi[k].x, bx[k].cx, bx[k].hx);
+        box_center_half(lo[k].y, hi[k].y, bx[k].cy, bx[k].hy);
+        box_center_half(lo[k].z, hi[k].z, bx[k].cz, bx[k].hz);
+        ref[k] = child_ref_(a, c[k]);
+    };
+    finish(0); finish(1);
+    node_pack<2>(a.nodes2 + YRT_NODE_STRIDE(2) * (size_t)i, bx, ref, 2);
+    int nb = 2;
+    while (nb < 4) {
         int best = -1;
         float best_area = -1.f;
         for (int k = 0; k < nb; k++) {
@@ -529,16 +542,8 @@ YRT_HD void emit_item(const LbvhArrays& a, int i) {
         child_box_(a, r, lo[best + 1], hi[best + 1]);
         nb++;
     }
-#endif
-    nodebox bx[YRT_WIDE];
-    int ref[YRT_WIDE];
-    for (int k = 0; k < nb; k++) {
-        box_center_half(lo[k].x, hi[k].x, bx[k].cx, bx[k].hx);
-        box_center_half(lo[k].y, hi[k].y, bx[k].cy, bx[k].hy);
-        box_center_half(lo[k].z, hi[k].z, bx[k].cz, bx[k].hz);
-        ref[k] = child_ref_(a, c[k]);
-    }
-    node_pack(a.nodes + YRT_NODE_STRIDE * (size_t)i, bx, ref, nb);
+    for (int k = 0; k < nb; k++) finish(k);
+    node_pack<4>(a.nodes4 + YRT_NODE_STRIDE(4) * (size_t)i, bx, ref, nb);
     int first = a.range_first[i], last = a.range_last[i];
     int s = a.seg_of[a.order[first]];
     if (s == a.seg_of[a.order[last]] && first == a.seg_first[s] && last == a.seg_first[s + 1] - 1) {
@@ -568,9 +573,23 @@ YRT_HD void depth_item(const LbvhArrays& a, int leaf) {
 }
 
 // Traversal-stack entries the subtree below node record i can occupy at once: a visit leaves at most (children - 1)
-// siblings on the stack while it descends into one child, so need(i) = children(i) - 1 + max over internal children.
-// Bottom-up with the arrival counters of the refit (flags zeroed before): a node is handled by the second thread to
-// reach it, when every record below it has its value.  Runs after emit; reads the emitted records.
+// siblings on the stack while it descends into one child, so need(i) = children(i) - 1 + max over internal children —
+// for the binary and for the 4-wide records.  Bottom-up with the arrival counters of the refit (flags zeroed before): a
+// node is handled by the second thread to reach it, when every record below it has its value.  Runs after emit.
+template <int W>
+YRT_HD int stackneed_of_(const LbvhArrays& a, int p, const float4* nodes, const int* need) {
+    const float4* n = nodes + YRT_NODE_STRIDE(W) * (size_t)p;
+    int nb = 0, deepest = 0;
+    for (int k = 0; k < W; k++) {
+        nodebox b;
+        int ref;
+        node_child<W>(n, k, b, ref);
+        if (!(b.hx >= 0.f)) continue;    // empty slot
+        nb++;
+        if (ref >= 0) { int c = YRT_LDCG(&need[ref - a.ref_offset]); if (c > deepest) deepest = c; }
+    }
+    return nb - 1 + deepest;
+}
 YRT_HD void stackneed_item(const LbvhArrays& a, int leaf) {
     int p = a.parent_leaf[leaf];
     while (p >= 0) {
@@ -578,21 +597,12 @@ YRT_HD void stackneed_item(const LbvhArrays& a, int leaf) {
         int old = YRT_ATOMIC_ADD(&a.flags[p], 1);
         if (old == 0) return;
         YRT_FENCE();
-        const float4* n = a.nodes + YRT_NODE_STRIDE * (size_t)p;
-        int nb = 0, deepest = 0;
-        for (int k = 0; k < YRT_WIDE; k++) {
-            nodebox b;
-            int ref;
-            node_child(n, k, b, ref);
-            if (!(b.hx >= 0.f)) continue;    // empty slot
-            nb++;
-            if (ref >= 0) { int c = YRT_LDCG(&a.need[ref - a.ref_offset]); if (c > deepest) deepest = c; }
-        }
-        int need = nb - 1 + deepest;
-        a.need[p] = need;
+        int n2 = stackneed_of_<2>(a, p, a.nodes2, a.need2), n4 = stackneed_of_<4>(a, p, a.nodes4, a.need4);
+        a.need2[p] = n2;
+        a.need4[p] = n4;
         int first = a.range_first[p], last = a.range_last[p];
         int s = a.seg_of[a.order[first]];
-        if (s == a.seg_of[a.order[last]] && first == a.seg_first[s] && last == a.seg_first[s + 1] - 1) a.seg_need[s] = need;
+        if (s == a.seg_of[a.order[last]] && first == a.seg_first[s] && last == a.seg_first[s + 1] - 1) { a.seg_need2[s] = n2; a.seg_need4[s] = n4; }
         p = YRT_LDCG(&a.parent_int[p]);
     }
 }

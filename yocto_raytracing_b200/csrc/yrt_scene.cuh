@@ -3,8 +3,8 @@
 // All records are multiples of 16 bytes and are fetched with 128-bit loads.
 //   BVH node (TLAS and BLAS alike, boxes as centre / half-extent inflated by 1 + 16u, two children interleaved per
 //   48-byte "pair" so that the slab test runs on packed FFMA2 — see "traversal node" below):
-//     YRT_WIDE == 4 (default): 128 B = pair(children 0,1) | pair(children 2,3) | 4 child refs | spare
-//     YRT_WIDE == 2          :  64 B = pair(children 0,1) | 2 child refs
+//     4-wide: 128 B = pair(children 0,1) | pair(children 2,3) | 4 child refs | child count
+//     binary:  64 B = pair(children 0,1) | 2 child refs            (both arrays are built; see YRT_WIDE_CLOSEST / YRT_WIDE_ANY)
 //   prim record (48 B, in BLAS leaf order, all shapes concatenated):
 //     triangle: q0 = v0.xyz | ei     q1 = v1.xyz | -      q2 = v2.xyz | -
 //     line:     q0 = v0.xyz | ei     q1 = v1.xyz | r0     q2 = r1, -, -, -
@@ -76,28 +76,22 @@ YRT_HD float4 mk4(float x, float y, float z, float w) { float4 r; r.x = x; r.y =
 // against a broadcast scalar.  20 FFMA per pair become 10 FFMA2; the values are the same IEEE FMAs, so the accept
 // decisions are bit-identical to slab_test_ch on the same boxes (the host build below uses exactly that).
 //
-// Node = YRT_WIDE children (tree arity of the traversal; the LBVH itself is binary, wide nodes are collapsed from it at
-// emit time, yrt_lbvh.cuh):
-//   YRT_WIDE == 4: 8 float4, 128-byte aligned = one L1 line: pair(0,1) | pair(2,3) | (ref0, ref1, ref2, ref3) | spare.
-//                  A visit tests the four (grand)children of a binary node at once: one dependent fetch and one round of
-//                  loop / stack overhead for what the binary tree does in 1 + (children entered) visits, and no test of
-//                  the intermediate boxes.  Unused child slots hold a box no ray can enter (h = -FLT_MAX).
-//   YRT_WIDE == 2: 4 float4: pair(0,1) | (ref0, ref1, -, -)                       (round 1's layout, kept for A/B builds)
-// YRT_PACK_REFS (build option): the child references ride in the low 16 bits of the four x / y half-extents of their
-// pair, whose upper 16 bits hold the half-extent rounded UP to bfloat16 — the stored value (reference bits included) is
-// never below the inflated half-extent the slab test's error analysis asks for, at most 2^-7 above it.  A visit then
-// reads one 16-byte quad less for two byte permutes per pair.
-#ifndef YRT_WIDE
-#define YRT_WIDE 4
+// Two node arrays are built from the same binary LBVH and share its node indices (record i of either array belongs to
+// binary node i, so child references and roots are the same numbers in both):
+//   4-wide: 8 float4, 128-byte aligned = one L1 line: pair(0,1) | pair(2,3) | (ref0, ref1, ref2, ref3) | (children, -, -, -).
+//           A visit tests up to four (grand)children of a binary node at once: half as many dependent fetches and loop
+//           trips; unused child slots hold a box no ray can enter (h = -FLT_MAX).  Collapsed at emit time (yrt_lbvh.cuh).
+//   binary: 4 float4: pair(0,1) | (ref0, ref1, -, -).
+// Which kernel walks which array is a build-time choice per ray kind, measured on B200 (profiles/r2_experiments.md):
+// any-hit (shadow) rays are faster on the 4-wide nodes (no child ordering: the visit is lean, the halved trip count
+// pays), closest-hit rays on the binary ones (ordering four children costs more than the saved trips).
+#ifndef YRT_WIDE_CLOSEST
+#define YRT_WIDE_CLOSEST 2
 #endif
-#ifndef YRT_PACK_REFS
-#define YRT_PACK_REFS 0
+#ifndef YRT_WIDE_ANY
+#define YRT_WIDE_ANY 4
 #endif
-#if YRT_WIDE == 4
-#define YRT_NODE_STRIDE 8   /* float4 per node */
-#else
-#define YRT_NODE_STRIDE (YRT_PACK_REFS ? 3 : 4)
-#endif
+#define YRT_NODE_STRIDE(W) ((W) == 4 ? 8 : 4)   /* float4 per node record */
 
 struct nodebox { float cx, cy, cz, hx, hy, hz; };
 YRT_HD nodebox pair_child(const float4& p0, const float4& p1, const float4& p2, int k) {
@@ -109,68 +103,37 @@ YRT_HD nodebox pair_child(const float4& p0, const float4& p1, const float4& p2, 
 // a box no ray enters: t0 = +huge, t1 = -huge on every axis (fused test), lo > hi (reference formula)
 YRT_HD nodebox nodebox_empty() { nodebox b; b.cx = b.cy = b.cz = 0.f; b.hx = b.hy = b.hz = -FLT_MAX; return b; }
 
-YRT_HD float half_with_payload_(float h, unsigned payload16) {
-    if (!(h >= 0.f)) return h;                  // empty slot: stays unreachable, carries no reference
-    unsigned b = (unsigned)float_as_int(h);
-    b = (b + 0xffffu) & 0xffff0000u;            // round up to a bfloat16 (h >= 0, finite)
-    if (b >= 0x7f800000u) b = 0x7f7f0000u;      // (never for real scenes: stay finite)
-    return int_as_float((int)(b | (payload16 & 0xffffu)));
-}
-YRT_HD void pair_pack(float4* p, const nodebox& b0, const nodebox& b1, int ref0, int ref1) {
+YRT_HD void pair_pack(float4* p, const nodebox& b0, const nodebox& b1) {
     p[0] = mk4(b0.cx, b0.cy, b1.cx, b1.cy);
-#if YRT_PACK_REFS
-    p[1] = mk4(half_with_payload_(b0.hx, (unsigned)ref0), half_with_payload_(b0.hy, (unsigned)ref0 >> 16),
-               half_with_payload_(b1.hx, (unsigned)ref1), half_with_payload_(b1.hy, (unsigned)ref1 >> 16));
-#else
-    (void)ref0; (void)ref1;
     p[1] = mk4(b0.hx, b0.hy, b1.hx, b1.hy);
-#endif
     p[2] = mk4(b0.cz, b1.cz, b0.hz, b1.hz);
 }
-#if YRT_PACK_REFS
-// the two child references of a pair (p1 = its second float4)
-YRT_HD void pair_refs(const float4& p1, int& ref0, int& ref1) {
-#if defined(__CUDA_ARCH__)
-    ref0 = (int)__byte_perm((unsigned)float_as_int(p1.x), (unsigned)float_as_int(p1.y), 0x5410);
-    ref1 = (int)__byte_perm((unsigned)float_as_int(p1.z), (unsigned)float_as_int(p1.w), 0x5410);
-#else
-    ref0 = (int)(((unsigned)float_as_int(p1.x) & 0xffffu) | ((unsigned)float_as_int(p1.y) << 16));
-    ref1 = (int)(((unsigned)float_as_int(p1.z) & 0xffffu) | ((unsigned)float_as_int(p1.w) << 16));
-#endif
-}
-#endif
 
-// writes one node record: nb child boxes (2 <= nb <= YRT_WIDE) and their references; the remaining slots are empty
+// writes one node record of arity W: nb child boxes (2 <= nb <= W) and their references; the remaining slots are empty
+template <int W>
 YRT_HD void node_pack(float4* n, const nodebox* box, const int* ref, int nb) {
-    nodebox b[YRT_WIDE];
-    int r[YRT_WIDE];
-    for (int k = 0; k < YRT_WIDE; k++) {
+    nodebox b[W];
+    int r[W];
+    for (int k = 0; k < W; k++) {
         b[k] = k < nb ? box[k] : nodebox_empty();
         r[k] = k < nb ? ref[k] : YRT_REF_DONE;   // never read: the slot's box cannot be entered
     }
-    pair_pack(n, b[0], b[1], r[0], r[1]);
-#if YRT_WIDE == 4
-    pair_pack(n + 3, b[2], b[3], r[2], r[3]);
-    n[6] = mk4(int_as_float(r[0]), int_as_float(r[1]), int_as_float(r[2]), int_as_float(r[3]));
-    n[7] = mk4(int_as_float(nb), 0.f, 0.f, 0.f);
-#elif !YRT_PACK_REFS
-    n[3] = mk4(int_as_float(r[0]), int_as_float(r[1]), 0.f, 0.f);
-#endif
+    pair_pack(n, b[0], b[1]);
+    if (W == 4) {
+        pair_pack(n + 3, b[2], b[3]);
+        n[6] = mk4(int_as_float(r[0]), int_as_float(r[1]), int_as_float(r[W - 2]), int_as_float(r[W - 1]));
+        n[7] = mk4(int_as_float(nb), 0.f, 0.f, 0.f);
+    } else {
+        n[3] = mk4(int_as_float(r[0]), int_as_float(r[1]), 0.f, 0.f);
+    }
 }
-// child k of a node record held in host-visible memory (tools and tests; the traversal reads the quads itself)
+// child k of a node record held in host-visible memory (build passes, tools and tests; the traversal reads the quads itself)
+template <int W>
 YRT_HD void node_child(const float4* n, int k, nodebox& b, int& ref) {
     const float4* p = n + 3 * (k >> 1);
     b = pair_child(p[0], p[1], p[2], k & 1);
-#if YRT_PACK_REFS
-    int r0, r1;
-    pair_refs(p[1], r0, r1);
-    ref = (k & 1) ? r1 : r0;
-#elif YRT_WIDE == 4
-    const float4 q = n[6];
+    const float4 q = n[W == 4 ? 6 : 3];
     ref = float_as_int(k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w)));
-#else
-    ref = float_as_int(k == 0 ? n[3].x : n[3].y);
-#endif
 }
 
 #if defined(__CUDA_ARCH__)
@@ -210,8 +173,9 @@ YRT_HD vec3 xyz(const float4& q) { return mk3(q.x, q.y, q.z); }
 
 // ---- what a kernel sees ------------------------------------------------------------------
 struct SceneView {
-    const float4* nodes;        // YRT_NODE_STRIDE per node; BLAS nodes of all shapes first, TLAS nodes after them — one
-                                // array and one index space, so a node visit needs no level test
+    const float4* nodes2;       // binary node records (4 float4 each): BLAS nodes of all shapes first, TLAS nodes after them —
+                                // one array and one index space, so a node visit needs no level test
+    const float4* nodes4;       // the same tree as 4-wide records (8 float4 each), same indices
     const float4* inst_recs;    // 4 per instance, TLAS leaf order
     const float4* prim_recs;    // 3 per prim, BLAS leaf order
     const float4* prim_attrs;   // YRT_ATTR_STRIDE per prim: normals + uv (4), triangles: v1, v2 (the trace record holds edges)

@@ -28,7 +28,7 @@ struct TraceCounters {   // optional per-ray work counters (roofline inputs): ho
     int slab_false_rejects;   // boxes the reference's slab test accepts but the fused one rejects (must stay 0; host audit only)
     int slab_extra_accepts;   // the other way round (harmless, costs a visit; host audit only)
     int tlas_box_tests;       // part of box_tests spent in the instance tree
-    int node_visits;          // node records fetched (YRT_WIDE box tests each)
+    int node_visits;          // node records fetched (2 or up to 4 box tests each)
 };
 
 // test the prims of one BLAS leaf; returns true if any was hit (tmax/hit updated)
@@ -138,6 +138,7 @@ struct Tracer {
     // (its exit-side operands have not changed), so a postponed subtree or instance that a nearer hit has made
     // irrelevant costs one compare instead of a visit.  Wide nodes need this more than binary ones: up to three siblings
     // wait on the stack per visit, and instance leaves are entered straight from it.  Any hit: the reference only.
+    static constexpr int W = ANY ? YRT_WIDE_ANY : YRT_WIDE_CLOSEST;   // arity of the node records this ray kind walks
     static constexpr bool CULL = !ANY && YRT_POP_CULL;
     static constexpr int ENTRY = CULL ? 2 : 1;
     YRT_HD float accept_limit() const { return EXACT ? tmax * 1.00000024f : fmaf(tmax, YRT_SLAB_ACCEPT, sr.pad); }
@@ -201,25 +202,19 @@ struct Tracer {
 #endif
     }
 
-#if YRT_WIDE == 4
     // One wide node: the four child boxes against the current ray and current tmax.
     // Any hit: the entered children are taken in stored order.  Closest hit: nearest child first; the others are pushed
     // so that they come off the stack in the order [far child of the nearest child's pair | near child of the other
     // pair | far child of the other pair], the last two swapped if the entry distances say so — i.e. sorted by entry
     // distance except that a pair is never split by more than one position (a tournament, not a full sort).
-    YRT_HD void visit(const SceneView& sv, int* stack, TraceCounters* ctr) {
-        const float4* n = sv.nodes + YRT_NODE_STRIDE * (size_t)cur;
+    YRT_HD void visit4(const SceneView& sv, int* stack, TraceCounters* ctr) {
+        const float4* n = sv.nodes4 + YRT_NODE_STRIDE(4) * (size_t)cur;
         float4 a0 = ld4(n), a1 = ld4(n + 1), a2 = ld4(n + 2), b0 = ld4(n + 3), b1 = ld4(n + 4), b2 = ld4(n + 5);
         int c0, c1, c2, c3;
-#if YRT_PACK_REFS
-        pair_refs(a1, c0, c1);
-        pair_refs(b1, c2, c3);
-#else
         {
             float4 r = ld4(n + 6);
             c0 = float_as_int(r.x); c1 = float_as_int(r.y); c2 = float_as_int(r.z); c3 = float_as_int(r.w);
         }
-#endif
         bool h0, h1, h2, h3;
         float e0, e1, e2, e3;
         test_pair(a0, a1, a2, h0, h1, e0, e1, ctr);
@@ -272,20 +267,16 @@ struct Tracer {
             }
         }
     }
-#else
+
     // one binary node: test both child boxes against the current ray and current tmax, near child first
-    YRT_HD void visit(const SceneView& sv, int* stack, TraceCounters* ctr) {
-        const float4* n = sv.nodes + YRT_NODE_STRIDE * (size_t)cur;
+    YRT_HD void visit2(const SceneView& sv, int* stack, TraceCounters* ctr) {
+        const float4* n = sv.nodes2 + YRT_NODE_STRIDE(2) * (size_t)cur;
         float4 q0 = ld4(n), q1 = ld4(n + 1), q2 = ld4(n + 2);
         int c0, c1;
-#if YRT_PACK_REFS
-        pair_refs(q1, c0, c1);
-#else
         {
             float4 r = ld4(n + 3);
             c0 = float_as_int(r.x); c1 = float_as_int(r.y);
         }
-#endif
         float e0, e1;
         bool h0, h1;
         test_pair(q0, q1, q2, h0, h1, e0, e1, ctr);
@@ -308,7 +299,9 @@ struct Tracer {
             pop();
         }
     }
-#endif
+    YRT_HD void visit(const SceneView& sv, int* stack, TraceCounters* ctr) {
+        if (W == 4) visit4(sv, stack, ctr); else visit2(sv, stack, ctr);
+    }
 
     // internal nodes until the lane holds a leaf
     YRT_HD void nodes(const SceneView& sv, int* stack, TraceCounters* ctr) {

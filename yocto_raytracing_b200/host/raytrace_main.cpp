@@ -97,22 +97,25 @@ int main(int argc, char** argv) {
         printf("%s\n", yrt_last_error());
         exit(1);
     }
-    double t_built = now_ms();
-
-    printf("tracing scene\n");
     int width = yrt_image_width(&flat.cam, resolution);   // (int)std::round(cam->aspect * resolution), src/raytrace.cpp:216
     bool want_hdr = imageout.length() >= 4 && imageout.substr(imageout.length() - 4) == ".hdr";   // src/image.cpp:82
     bool ldr_on_device = device_ldr && !want_hdr;
-    auto hdr = image4f();
-    auto ldr = image4b();
+    // the frame buffers and the render workspace belong to the set-up, like the reference's image allocation (raytrace.cpp:217)
+    auto hdr = ldr_on_device ? image4f() : image4f(width, resolution);
+    auto ldr = ldr_on_device ? image4b(width, resolution) : image4b();
+    if (yrt_scene_prepare(gscn, width, resolution, samples) != YRT_OK) {
+        printf("%s\n", yrt_last_error());
+        exit(1);
+    }
+    double t_built = now_ms();
+
+    printf("tracing scene\n");
     float ambient[3] = {amb, amb, amb};
     yrt_stats st;
     int rc;
     if (ldr_on_device) {
-        ldr = image4b(width, resolution);
         rc = yrt_render_ldr(gscn, &flat.cam, ambient, width, resolution, samples, (uint8_t*)ldr.pixels.data(), nullptr, &st);
     } else {
-        hdr = image4f(width, resolution);
         rc = yrt_render(gscn, &flat.cam, ambient, width, resolution, samples, (float*)hdr.pixels.data(), &st);
     }
     if (rc != YRT_OK) {
@@ -134,6 +137,9 @@ int main(int argc, char** argv) {
     else save_hdr_or_ldr(imageout, hdr);
     double t_saved = now_ms();
 
+    if (verbose && st.truncated_paths > 0)
+        printf("note: %lld mirror bounce(s) were cut at the recursion cap of this path (YRT_MAX_DEPTH, default 16); the reference recurses without a bound\n",
+               (long long)st.truncated_paths);
     if (verbose) {
         long long rays = (long long)(st.primary_rays + st.reflection_rays + st.shadow_rays);
         double ms = t_traced - t_built;
