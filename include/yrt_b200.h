@@ -257,6 +257,13 @@ int yrt_intersect_any(yrt_scene* scn, const float* rays, int64_t n, uint8_t* occ
  * element tests, instance entries, 0, 0 — totals since the last call (reading resets them). */
 int yrt_counters_read(yrt_scene* scn, uint64_t out[24]);
 
+/* test hook: copies the scene's node records (arity 2: 4 float4 per node, arity 4: 8 float4 per node; BLAS nodes of all
+ * shapes, then TLAS nodes) of device 0 into out (HOST, capacity max_float4 float4s); returns the number of float4s the
+ * array holds (also when out is NULL), or a negative yrt_status.  The LBVH build is deterministic — its lock-free bottom-up
+ * passes included — so these arrays must equal, bit for bit, those of a serial execution of the same per-item functions
+ * (tests/host_emu): that comparison is the race detector of the build (tests/test_gpu_parity.py). */
+int64_t yrt_debug_read_nodes(yrt_scene* scn, int arity, float* out, int64_t max_float4);
+
 /* test hook: sorts n (key, value) pairs held in HOST arrays with the device radix sort of the LBVH build */
 int yrt_debug_sort_pairs(unsigned long long* h_keys, int* h_vals, int n);
 

@@ -46,6 +46,15 @@ class EmuScene:
         self._lib.emu_scene_info(self.h, out)
         return list(out)
 
+    def nodes(self, arity):
+        """Node records (arity 2 or 4) of the emulated build as a float32 array (n, 4)."""
+        self._lib.emu_read_nodes.restype = C.c_int64
+        n = self._lib.emu_read_nodes(self.h, arity, None)
+        out = np.zeros((max(n, 0), 4), np.float32)
+        if n > 0:
+            self._lib.emu_read_nodes(self.h, arity, C.c_void_p(out.ctypes.data))
+        return out
+
     def trace_primary(self, width, height, samples):
         n = width * height * samples * samples
         ids = np.empty((n, 3), np.int32)

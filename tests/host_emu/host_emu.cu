@@ -230,6 +230,17 @@ int emu_scene_info(void* p, int64_t out[8]) {
     return YRT_OK;
 }
 
+// node records (arity 2 or 4) of the emulated build, BLAS nodes then TLAS nodes: returns the float4 count; copies when out != NULL
+int64_t emu_read_nodes(void* p, int arity, float* out) {
+    EmuScene* es = (EmuScene*)p;
+    const std::vector<float4>& v = arity == 4 ? es->nodes4 : es->nodes2;
+    // (a tree set of one item has no internal node but the arrays keep one zero record for it: report what the device reports)
+    int np = es->hs.n_prims, na = es->view.n_active_instances;
+    int64_t n = (int64_t)YRT_NODE_STRIDE(arity) * ((np > 1 ? np - 1 : 0) + (na > 1 ? na - 1 : 0));
+    if (out) memcpy(out, v.data(), sizeof(float4) * (size_t)std::min<int64_t>(n, (int64_t)v.size()));
+    return n;
+}
+
 // counters_out (optional, 8 int64): box tests, prim tests, instance entries, max stack, fused-slab false rejects / extra accepts,
 // box tests in the instance tree, node visits
 int emu_trace_primary(void* p, const yrt_camera* cam, int width, int height, int samples, int32_t* ids, float* dist, float* uv,

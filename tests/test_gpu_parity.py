@@ -526,3 +526,27 @@ def test_rows_to_host_assembles_the_frame(gpu):
                 scn.render_rows_to_host(host.data_ptr(), w, h, s, 0.1, tr, rank, world, 0, rank == world - 1)
             torch.cuda.synchronize()
             assert np.array_equal(host.numpy().view(np.uint32), whole.view(np.uint32)), (world, tr)
+
+
+@pytest.mark.parametrize("maker", [lambda: load_golden("instance10000")[0], lambda: synth.mixed_scene(7).flat(), lambda: synth.hair_scene(4096, seed=2).flat(),
+                                   lambda: synth.instance_grid_scene(60, seed=4).flat()])
+def test_device_lbvh_equals_serial_execution_bit_for_bit(gpu, maker):
+    """Race detector of the GPU build (compute-sanitizer is not available on this pool): Morton keys, the multi-CTA stable
+    radix sort, Karras topology and the lock-free bottom-up passes (refit, tree rotations, re-layout, stack need — arrival
+    counters + fences) are deterministic, so the node arrays the device builds must equal, bit for bit, those of a SERIAL
+    execution of the same per-item functions on the host (tests/host_emu) — for both node arities, on every one of 10
+    builds of the same scene (a stale read of a child's box shows up as a different box)."""
+    import _emu
+    if not _emu.available():
+        pytest.skip("host emulation not built")
+    flat = maker()
+    es = _emu.EmuScene(flat)
+    want = {a: es.nodes(a) for a in (2, 4)}
+    for rep in range(10):
+        with gpu.Scene(flat) as scn:
+            info = scn.info()
+            for a in (2, 4):
+                got = scn.debug_nodes(a)
+                assert got.shape == want[a].shape, (a, got.shape, want[a].shape, info)
+                same = (got.view(np.uint32) == want[a].view(np.uint32)).all(axis=1)
+                assert same.all(), (rep, a, int((~same).sum()), np.flatnonzero(~same)[:8])

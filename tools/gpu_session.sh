@@ -13,4 +13,5 @@ if [ -f build/variants/counters.so ]; then
 fi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $out/${tag}_launches.csv python tools/profile_frame.py --frames 2 > $out/${tag}_ncu_launch.log 2>&1
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_trace\|k_shade\|k_resolve --launch-skip 4 -c 4 -f -o $out/${tag}_trace python tools/profile_frame.py --frames 2 > $out/${tag}_ncu_full.log 2>&1
+timeout 300 python tools/gpu_dump_frames.py > $out/${tag}_frames.log 2>&1
 echo done > $out/${tag}_done.txt

@@ -30,6 +30,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2_vs_author.md"))
     ap.add_argument("--gpu", action="store_true", help="also render with the CUDA path (needs a GPU)")
+    ap.add_argument("--frames-dir", default=os.path.join(ROOT, "gpurun_out", "frames"), help="PNGs of the CUDA path rendered on the GPU box (tools/gpu_dump_frames.py)")
+    ap.add_argument("--only-frames", action="store_true", help="skip the CPU renderers, compare only the PNGs in --frames-dir")
     a = ap.parse_args()
     from oracle import oracle
     from yocto_raytracing_b200.scene import FlatScene
@@ -44,6 +46,14 @@ def main():
         out_png = np.array(Image.open(f"{REF}/out/{short}.png").convert("RGBA"))
         chk_png = np.array(Image.open(f"{REF}/check/{short}.png").convert("RGBA"))
         imgs = {}
+        fp = os.path.join(a.frames_dir, short + ".png")
+        if os.path.exists(fp):
+            imgs["CUDA path on B200 (libyrt_b200.so, tools/gpu_dump_frames.py) + reference tonemap"] = np.array(Image.open(fp).convert("RGBA"))
+        if a.only_frames:
+            for k, v in imgs.items():
+                lines.append(f"| {short} | {k} | {stats(v, out_png)} | {stats(v, chk_png)} |")
+                print(lines[-1], flush=True)
+            continue
         with tempfile.TemporaryDirectory() as td:
             p = os.path.join(td, "ref.png")
             subprocess.run([cli, "-r", "720", "-s", "3", "-o", p, os.path.basename(obj)], cwd=os.path.dirname(obj), check=True, stdout=subprocess.DEVNULL)

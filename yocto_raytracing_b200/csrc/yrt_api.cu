@@ -185,6 +185,17 @@ int yrt_scene_prepare(yrt_scene* scn, int width, int height, int samples) {
     return YRT_OK;
 }
 
+int64_t yrt_debug_read_nodes(yrt_scene* scn, int arity, float* out, int64_t max_float4) {
+    if (!scn || scn->dev.empty() || (arity != 2 && arity != 4)) { set_error("yrt_debug_read_nodes: bad arguments"); return YRT_ERR_INVALID; }
+    DevScene& ds = *scn->dev[0];
+    const int64_t n = (int64_t)YRT_NODE_STRIDE(arity) * (ds.n_blas_nodes + ds.n_tlas_nodes);
+    if (!out) return n;
+    if (max_float4 < n) { set_error("yrt_debug_read_nodes: buffer too small"); return YRT_ERR_INVALID; }
+    YRT_CUDA(cudaSetDevice(ds.device));
+    YRT_CUDA(cudaMemcpy(out, arity == 4 ? ds.view.nodes4 : ds.view.nodes2, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost));
+    return n;
+}
+
 int yrt_counters_read(yrt_scene* scn, uint64_t out[24]) {
     if (!scn || scn->dev.empty() || !out) { set_error("yrt_counters_read: bad arguments"); return YRT_ERR_INVALID; }
     return read_counters_device(*scn->dev[0], out);

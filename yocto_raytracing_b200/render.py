@@ -147,6 +147,19 @@ class Scene:
         """yrt_scene_prepare: allocate the render workspace of that frame size now."""
         check(_lib.load().yrt_scene_prepare(self._h, int(width), int(height), int(samples)))
 
+    def debug_nodes(self, arity: int) -> np.ndarray:
+        """yrt_debug_read_nodes: the node records (arity 2 or 4) of device 0 as a float32 array (n, 4)."""
+        lib = _lib.load()
+        n = lib.yrt_debug_read_nodes(self._h, int(arity), None, 0)
+        if n < 0:
+            check(int(n))
+        out = np.zeros((n, 4), np.float32)
+        if n:
+            r = lib.yrt_debug_read_nodes(self._h, int(arity), C.c_void_p(out.ctypes.data), n)
+            if r < 0:
+                check(int(r))
+        return out
+
     def stats_begin(self) -> None:
         """Open deferred statistics: following render_rows_into frames record events/counters without host syncs."""
         check(_lib.load().yrt_stats_begin(self._h))
