@@ -304,6 +304,16 @@ def test_cli_scene_cache_and_device_ldr(gpu, tmp_path):
     r = subprocess.run([ours] + args + ["--cache", "-o", os.path.join(cwd, "ours3.png"), name], cwd=cwd, capture_output=True, text=True)
     assert r.returncode == 0 and "(scene cache)" not in r.stdout
     assert os.stat(obj + ".yrts").st_mtime > 1
+    # ... and so is a cache older than the material library or a texture next to the scene
+    import time
+    for dep in (obj[:-4] + ".mtl", os.path.join(cwd, "grid.png")):
+        r = subprocess.run([ours] + args + ["--cache", "-o", os.path.join(cwd, "ours3.png"), name], cwd=cwd, capture_output=True, text=True)
+        assert r.returncode == 0 and "(scene cache)" in r.stdout          # fresh now
+        future = time.time() + 5
+        os.utime(dep, (future, future))
+        r = subprocess.run([ours] + args + ["--cache", "-o", os.path.join(cwd, "ours3.png"), name], cwd=cwd, capture_output=True, text=True)
+        assert r.returncode == 0 and "(scene cache)" not in r.stdout, dep
+        os.utime(obj + ".yrts", (future + 1, future + 1))
     # .hdr output keeps the float path even with --device-ldr
     r = subprocess.run([ours] + args + ["--device-ldr", "-o", os.path.join(cwd, "ours.hdr"), name], cwd=cwd, capture_output=True, text=True)
     assert r.returncode == 0 and os.path.getsize(os.path.join(cwd, "ours.hdr")) > 0

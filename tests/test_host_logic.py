@@ -179,3 +179,24 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     if not torch.cuda.is_available():
         r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
         assert r2.returncode != 0 and r2.stdout.strip() == ""
+
+
+def test_scene_cache_loader_rejects_corrupt_counts(tmp_path):
+    """The CLI's scene cache (<scene>.yrts, host/yrt_flatten.cpp): a count that promises more bytes than the file holds is
+    rejected before anything is allocated; an intact file reads back with the counts it was written with."""
+    import struct
+    tool = os.path.join(ROOT, "bin", "yrt_flatten")
+    if not os.path.exists(tool):
+        pytest.skip("bin/yrt_flatten not built (needs the reference sources at build time)")
+    from yocto_raytracing_b200 import synth
+    obj = synth.mixed_scene(7).write_obj(str(tmp_path))
+    good = str(tmp_path / "s.yrts")
+    assert subprocess.run([tool, os.path.basename(obj), good], cwd=str(tmp_path), capture_output=True).returncode == 0
+    r = subprocess.run([tool, "--check", good], capture_output=True, text=True)
+    assert r.returncode == 0 and "instances" in r.stdout
+    b = bytearray(open(good, "rb").read())
+    struct.pack_into("<q", b, 16 + 24 + 4, 1 << 40)          # count of the first array: 2^40 elements
+    bad = str(tmp_path / "bad.yrts")
+    open(bad, "wb").write(b)
+    r = subprocess.run([tool, "--check", bad], capture_output=True, text=True, timeout=30)
+    assert r.returncode != 0 and "malformed" in r.stderr

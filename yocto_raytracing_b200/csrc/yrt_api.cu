@@ -20,26 +20,6 @@ std::vector<int> g_devices;   // empty until yrt_init*
 
 int g_allow_nonrigid = 0;    // yrt_set_option("allow_nonrigid")
 
-// Rows of one rank -> their places in a row-major HOST frame (elem = bytes per pixel), as 2-D copies on `st`: the rows of
-// tile k of rank r are one contiguous block of the frame ((k * world + r) * tile_rows rows down), and the rank's packed
-// buffer holds the blocks back to back — a pitched copy moves all full tiles at once; a ragged last tile follows.
-int copy_rows_to_host(const void* d_packed, void* h_frame, int width, int height, int tile_rows, int rank, int world, size_t elem, cudaStream_t st) {
-    const size_t row = elem * (size_t)width;
-    const int n_tiles = (height + tile_rows - 1) / tile_rows;
-    int mine = 0, last = -1;
-    for (int t = rank; t < n_tiles; t += world) { mine++; last = t; }
-    if (mine == 0) return YRT_OK;
-    const bool ragged = (last + 1) * tile_rows > height;
-    const int full = ragged ? mine - 1 : mine;
-    const size_t block = row * (size_t)tile_rows;
-    if (full > 0)
-        YRT_CUDA(cudaMemcpy2DAsync((char*)h_frame + block * (size_t)rank, block * (size_t)world, d_packed, block, block, (size_t)full, cudaMemcpyDeviceToHost, st));
-    if (ragged)
-        YRT_CUDA(cudaMemcpyAsync((char*)h_frame + block * (size_t)last, (const char*)d_packed + block * (size_t)full, row * (size_t)(height - last * tile_rows),
-                                 cudaMemcpyDeviceToHost, st));
-    return YRT_OK;
-}
-
 // With the option "pin_host_frames" the caller's frame buffers are page-locked on first sight and stay so until another
 // buffer takes the slot or the library is re-initialised (device->host copies into pageable memory are staged by the
 // driver).  Opt-in, because the registration outlives the call: the caller must keep such a buffer alive (and not hand its
@@ -310,8 +290,8 @@ int yrt_render_rows_to_host(yrt_scene* scn, const yrt_camera* cam, const float a
     const int own = rows_owned(height, tile_rows, rank, world);
     YRT_TRY(ds.ws.rows.alloc(sizeof(float4) * (size_t)std::max(own, 1) * width, ds.device));
     cudaStream_t st = (cudaStream_t)stream;
+    rp.h_rgba = h_frame;
     YRT_TRY(render_rows_device(ds, rp, ds.ws.rows.as<float4>(), st, stats, false));
-    YRT_TRY(copy_rows_to_host(ds.ws.rows.p, h_frame, width, height, tile_rows, rank, world, sizeof(float4), st));
     if (stats) { YRT_CUDA(cudaStreamSynchronize(st)); return collect_stats_device(ds, rp, stats); }
     return YRT_OK;
 }
@@ -338,13 +318,13 @@ static int render_impl(yrt_scene* scn, const yrt_camera* cam, const float amb[3]
         rp.tile_rows = tile_rows; rp.rank = g; rp.world = G;
         const int own = rows_owned(height, tile_rows, g, G);
         int s = ds.ws.rows.alloc(sizeof(float4) * (size_t)std::max(own, 1) * width, ds.device);
-        if (s == YRT_OK) s = render_rows_device(ds, rp, ds.ws.rows.as<float4>(), ds.stream, stats, false);
-        if (s == YRT_OK && rgba_out) s = copy_rows_to_host(ds.ws.rows.p, rgba_out, width, height, tile_rows, g, G, sizeof(float4), ds.stream);
-        if (s == YRT_OK && ldr_out && own > 0) {   // tonemap on the device: a quarter of the bytes cross to the host
-            s = ds.ws.rows8.alloc(4 * (size_t)own * width, ds.device);
-            if (s == YRT_OK) s = tonemap_launch(ds.ws.rows.as<float4>(), ds.ws.rows8.as<uint8_t>(), (size_t)own * width, ds.stream);
-            if (s == YRT_OK) s = copy_rows_to_host(ds.ws.rows8.p, ldr_out, width, height, tile_rows, g, G, 4, ds.stream);
+        rp.h_rgba = rgba_out;
+        if (s == YRT_OK && ldr_out) {   // tonemap on the device: a quarter of the bytes cross to the host
+            s = ds.ws.rows8.alloc(4 * (size_t)std::max(own, 1) * width, ds.device);
+            rp.h_ldr = ldr_out;
+            rp.d_ldr_rows = ds.ws.rows8.as<uint8_t>();
         }
+        if (s == YRT_OK) s = render_rows_device(ds, rp, ds.ws.rows.as<float4>(), ds.stream, stats, false);
         if (s == YRT_OK && cudaStreamSynchronize(ds.stream) != cudaSuccess) { set_error("device %d: %s", ds.device, cudaGetErrorString(cudaGetLastError())); s = YRT_ERR_CUDA; }
         status[g] = s;
         if (s != YRT_OK) errs[g] = get_error();

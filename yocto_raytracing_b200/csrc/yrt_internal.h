@@ -122,6 +122,11 @@ struct RenderParams {
     int width, height, samples;
     int tile_rows, rank, world;   // interleaved row tiles
     bool scatter = false;         // d_out is the full frame: rows go to their final position (fused gather)
+    // optional host destinations (whole-image, row-major): every batch's rows are copied to their final positions right
+    // behind its resolve, on the batch's own stream — the copy of one batch runs under the kernels of the next
+    float* h_rgba = nullptr;      // width*height*4 floats
+    uint8_t* h_ldr = nullptr;     // width*height*4 bytes: tonemap(hdr, 0, false) on the device first (needs d_ldr_rows)
+    uint8_t* d_ldr_rows = nullptr;   // device scratch for the rank's tonemapped packed rows
 };
 
 YRT_HD int rows_owned(int height, int tile_rows, int rank, int world) {
@@ -158,6 +163,9 @@ int intersect_rays_device(DevScene& ds, const float* h_rays, int64_t n, bool any
 int unpack_rows_device(const float4* d_packed, float4* d_full, int width, int height, int tile_rows, int rank,
                        int world, cudaStream_t st);
 int tonemap_launch(const float4* d_in, uint8_t* d_out, size_t n, cudaStream_t st);
+// packed local rows [lr0, lr0 + nrows) of a rank -> their places in a row-major HOST frame (elem bytes per pixel), on `st`
+int copy_rows_to_host(const void* d_packed, void* h_frame, int width, int height, int tile_rows, int rank, int world, size_t elem, int lr0, int nrows,
+                      cudaStream_t st);
 int tonemap_device(int device, const float* h_rgba, int width, int height, uint8_t* h_out);
 
 camera_k make_camera_k(const yrt_camera* cam);

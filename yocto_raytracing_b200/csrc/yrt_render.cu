@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_close
 // per hit instead of once per (hit, light).
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS_ANY) k_trace_any_lights(SceneView sv, size_t cap_slots, const int* __restrict__ act,
                                                                     const float4* __restrict__ hit, const float4* __restrict__ P,
-                                                                    uint8_t* __restrict__ vis, WorkDist wd, unsigned long long* dctr) {
+                                                                    unsigned* __restrict__ vis, WorkDist wd, unsigned long long* dctr) {
     const int lane = threadIdx.x & 31;
     const unsigned n_items = item_count(wd);
     int stack[STACK_INTS_ANY];
@@ -167,6 +167,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS_ANY) k_trace_a
         float4 h = hit[slot];
         if (float_as_int(h.x) < 0) continue;   // a miss casts no shadow rays: shade() returns before the light loop (raytrace.cpp:93)
         vec3 p = xyz(P[slot]);
+        // visibility of the lights as bit masks: word w of a slot holds lights 32 w .. 32 w + 31 (one store per hit for up to 32 lights)
+        unsigned vm = 0u;
         for (int k = 0; k < sv.n_lights; k++) {
             vec3 l, ke;
             float r;
@@ -177,7 +179,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS_ANY) k_trace_a
 #if YRT_COUNTERS
             rays_++;
 #endif
-            vis[(size_t)k * cap_slots + slot] = occ ? 0 : 1;
+            if (!occ) vm |= 1u << (k & 31);
+            if ((k & 31) == 31 || k == sv.n_lights - 1) {
+                vis[(size_t)(k >> 5) * cap_slots + slot] = vm;
+                vm = 0u;
+            }
         }
     }
 #if YRT_COUNTERS
@@ -261,32 +267,44 @@ __device__ __forceinline__ bool shade_slot(const SceneView& sv, const BatchParam
     return spawn;
 }
 
-// compacted queue of the next wave + frame counters (warp-aggregated; every lane of the warp must call it)
-__device__ __forceinline__ void shade_epilogue(const ShadeBuffers& sb, int depth, bool valid, bool is_hit, bool spawn, bool truncated, unsigned slot, int lane) {
-    unsigned m_spawn = __ballot_sync(0xffffffffu, spawn);
-    unsigned m_trunc = __ballot_sync(0xffffffffu, truncated);
-    unsigned m_hit = __ballot_sync(0xffffffffu, is_hit);
-    unsigned m_valid = __ballot_sync(0xffffffffu, valid);
-    if (m_spawn) {
-        int basei = 0;
-        if (lane == 0) basei = atomicAdd(sb.next_count, __popc(m_spawn));
-        basei = __shfl_sync(0xffffffffu, basei, 0);
-        if (spawn) sb.next_act[basei + __popc(m_spawn & ((1u << lane) - 1u))] = (int)slot;
+// Compacted queue of the next wave + frame counters, aggregated per BLOCK: the warps leave their counts in shared memory,
+// one thread adds the block's totals to the global counters (one atomic per counter and block instead of one per warp:
+// a million same-address atomics per frame serialise in L2) and publishes the block's base in the next wave's queue;
+// queue order = slot order inside a block.  Every thread of the block must call it (it synchronises the block).
+__device__ __forceinline__ void shade_epilogue(const ShadeBuffers& sb, int depth, bool valid, bool is_hit, bool spawn, bool truncated, unsigned slot) {
+    __shared__ int s_cnt[8][4];      // per warp: spawned, hits, valid, truncated
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m_spawn = __ballot_sync(0xffffffffu, spawn);
+    const unsigned m_trunc = __ballot_sync(0xffffffffu, truncated);
+    const unsigned m_hit = __ballot_sync(0xffffffffu, is_hit);
+    const unsigned m_valid = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) { s_cnt[warp][0] = __popc(m_spawn); s_cnt[warp][1] = __popc(m_hit); s_cnt[warp][2] = __popc(m_valid); s_cnt[warp][3] = __popc(m_trunc); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t[4] = {0, 0, 0, 0};
+        for (int w = 0; w < 8; w++)
+            for (int k = 0; k < 4; k++) t[k] += s_cnt[w][k];
+        s_base = t[0] ? atomicAdd(sb.next_count, t[0]) : 0;
+        if (t[1]) atomicAdd(&sb.fc->hits, (unsigned long long)t[1]);
+        if (t[0]) atomicAdd(&sb.fc->reflections, (unsigned long long)t[0]);
+        if (t[2] - t[1]) atomicAdd(&sb.fc->misses, (unsigned long long)(t[2] - t[1]));
+        if (t[3]) atomicAdd(&sb.fc->truncated, (unsigned long long)t[3]);
+        if (depth > 0 && t[2]) atomicMax(&sb.fc->max_depth, (unsigned long long)(depth + 1));
     }
-    if (lane == 0 && m_valid) {
-        if (m_hit) atomicAdd(&sb.fc->hits, (unsigned long long)__popc(m_hit));
-        if (m_spawn) atomicAdd(&sb.fc->reflections, (unsigned long long)__popc(m_spawn));
-        unsigned miss = m_valid & ~m_hit;
-        if (miss) atomicAdd(&sb.fc->misses, (unsigned long long)__popc(miss));
-        if (m_trunc) atomicAdd(&sb.fc->truncated, (unsigned long long)__popc(m_trunc));
-        if (depth > 0) atomicMax(&sb.fc->max_depth, (unsigned long long)(depth + 1));
+    __syncthreads();
+    if (spawn) {
+        int off = s_base;
+        for (int w = 0; w < warp; w++) off += s_cnt[w][0];
+        sb.next_act[off + __popc(m_spawn & ((1u << lane) - 1u))] = (int)slot;
     }
+    __syncthreads();     // s_cnt / s_base are reused by the next round of the grid-stride loop
 }
 
 // one thread per active sample; n_act_dev (if not null) holds the number of active samples of this wave
 __global__ void __launch_bounds__(256, 4) k_shade(SceneView sv, BatchParams bp, ShadeBuffers sb, int depth, int max_depth,
                                                   const int* __restrict__ act, unsigned n_act, const unsigned* __restrict__ n_act_dev,
-                                                  const uint8_t* __restrict__ vis) {
+                                                  const unsigned* __restrict__ vis) {
     if (n_act_dev) n_act = min(n_act, *n_act_dev);
     if (blockIdx.x * blockDim.x >= n_act) return;
     __shared__ float lut[256];
@@ -301,20 +319,13 @@ __global__ void __launch_bounds__(256, 4) k_shade(SceneView sv, BatchParams bp, 
         if (valid) {
             slot = act ? (unsigned)act[a] : a;
             float4 h = sb.hit[slot];
-            const uint8_t* vrow = vis + slot;
-            size_t cap = bp.cap_slots;
-            if (sv.n_lights <= 32) {
-                // all visibility bytes of the hit are requested before the first one is needed (the light loop would
-                // otherwise wait for them one at a time: 22 % of this kernel's stall samples sat on that load)
-                unsigned vmask = 0u;
-                if (float_as_int(h.x) >= 0)
-                    for (int k = 0; k < sv.n_lights; k++) vmask |= (vrow[(size_t)k * cap] != 0 ? 1u : 0u) << k;
-                spawn = shade_slot(sv, bp, sb, depth, max_depth, slot, h, lut, [&](int k) { return ((vmask >> k) & 1u) != 0u; }, is_hit, truncated);
-            } else {
-                spawn = shade_slot(sv, bp, sb, depth, max_depth, slot, h, lut, [&](int k) { return vrow[(size_t)k * cap] != 0; }, is_hit, truncated);
-            }
+            const unsigned* vrow = vis + slot;
+            const size_t cap = bp.cap_slots;
+            const unsigned v0 = vrow[0];      // lights 0..31: requested together with the hit record, used after eval_hit
+            spawn = shade_slot(sv, bp, sb, depth, max_depth, slot, h, lut,
+                               [&](int k) { return (((k < 32 ? v0 : vrow[(size_t)(k >> 5) * cap]) >> (k & 31)) & 1u) != 0u; }, is_hit, truncated);
         }
-        shade_epilogue(sb, depth, valid, is_hit, spawn, truncated, slot, threadIdx.x & 31);
+        shade_epilogue(sb, depth, valid, is_hit, spawn, truncated, slot);
     }
 }
 
@@ -451,7 +462,7 @@ static int ensure_workspace(DevScene& ds, Workspace& w, size_t slots, int n_ligh
         YRT_TRY(w.hit.alloc(sizeof(float4) * cs, dev));
         YRT_TRY(w.P.alloc(sizeof(float4) * cs, dev));
         YRT_TRY(w.rad.alloc(sizeof(float4) * cs, dev));
-        YRT_TRY(w.vis.alloc((size_t)std::max(cl, 1) * cs, dev));
+        YRT_TRY(w.vis.alloc(sizeof(unsigned) * (size_t)((std::max(cl, 1) + 31) / 32) * cs, dev));
         if (cd > 0) {
             YRT_TRY(w.ray_o.alloc(sizeof(float4) * cs, dev));
             YRT_TRY(w.ray_d.alloc(sizeof(float4) * cs, dev));
@@ -575,12 +586,12 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0
         if (nl > 0) {
             YRT_TRY(ring.get(&ctr));
             pt.begin(CAT_ANY);
-            k_trace_any_lights<<<grid_of(ds.grid_any, n), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(), w.vis.as<uint8_t>(),
+            k_trace_any_lights<<<grid_of(ds.grid_any, n), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(), w.vis.as<unsigned>(),
                                                                                  workdist_linear(ctr, n, n_dev), dctr ? dctr + 2 * YRT_DCTR_WORDS : nullptr);
             pt.end();
         }
         pt.begin(CAT_SHADE);
-        k_shade<<<depth == 0 ? (n + 255) / 256 : std::min((n + 255) / 256, (unsigned)ds.sm_count * 16u), 256, 0, st>>>(ds.view, bp, sb, depth, depth_cap, act, n, n_dev, w.vis.as<uint8_t>());
+        k_shade<<<depth == 0 ? (n + 255) / 256 : std::min((n + 255) / 256, (unsigned)ds.sm_count * 16u), 256, 0, st>>>(ds.view, bp, sb, depth, depth_cap, act, n, n_dev, w.vis.as<unsigned>());
         pt.end();
         if (!reflective || depth + 1 >= depth_cap) break;
         YRT_CUDA(cudaMemcpyAsync(w.h_counts + depth + 1, counts + depth + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
@@ -596,6 +607,49 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0
                                                   rp.tile_rows, rp.rank, rp.world);
     pt.end();
     YRT_CUDA(cudaGetLastError());
+    return YRT_OK;
+}
+
+// Packed local rows [lr0, lr0 + nrows) of one rank -> their places in a row-major HOST frame (elem = bytes per pixel), as
+// 2-D copies on `st`: the rows of tile k of rank r are one contiguous block of the frame ((k * world + r) * tile_rows rows
+// down) and the rank's packed buffer holds its blocks back to back, so a pitched copy moves a run of full tiles at once;
+// ragged ends (a batch that starts or stops inside a tile, the short last tile of the image) go row block by row block.
+int copy_rows_to_host(const void* d_packed, void* h_frame, int width, int height, int tile_rows, int rank, int world, size_t elem, int lr0, int nrows,
+                      cudaStream_t st) {
+    const size_t row = elem * (size_t)width;
+    int lr = lr0;
+    const int end = lr0 + nrows;
+    while (lr < end) {
+        const int k = lr / tile_rows, in_tile = lr - k * tile_rows;            // k-th tile of this rank
+        const int g0 = (k * world + rank) * tile_rows;                          // its first global row
+        const int tile_len = std::min(tile_rows, height - g0);                  // (the image's last tile may be short)
+        if (in_tile == 0 && tile_len == tile_rows && end - lr >= tile_rows) {
+            // run of full tiles: stop before a tile that is cut by the batch end or by the image end
+            int full = (end - lr) / tile_rows;
+            while (full > 0 && ((k + full - 1) * world + rank + 1) * tile_rows > height) full--;
+            if (full > 0) {
+                const size_t block = row * (size_t)tile_rows;
+                YRT_CUDA(cudaMemcpy2DAsync((char*)h_frame + row * (size_t)g0, block * (size_t)world, (const char*)d_packed + row * (size_t)lr, block, block, (size_t)full,
+                                           cudaMemcpyDeviceToHost, st));
+                lr += full * tile_rows;
+                continue;
+            }
+        }
+        const int n = std::min(tile_len - in_tile, end - lr);
+        YRT_CUDA(cudaMemcpyAsync((char*)h_frame + row * (size_t)(g0 + in_tile), (const char*)d_packed + row * (size_t)lr, row * (size_t)n, cudaMemcpyDeviceToHost, st));
+        lr += n;
+    }
+    return YRT_OK;
+}
+
+// rows [lr0, lr0 + nrows) of the rank's packed rows -> the host destinations of rp (float frame and / or tonemapped RGBA8)
+static int rows_to_host(const RenderParams& rp, const float4* d_out, int lr0, int nrows, cudaStream_t st) {
+    if (nrows <= 0) return YRT_OK;
+    if (rp.h_rgba) YRT_TRY(copy_rows_to_host(d_out, rp.h_rgba, rp.width, rp.height, rp.tile_rows, rp.rank, rp.world, sizeof(float4), lr0, nrows, st));
+    if (rp.h_ldr) {
+        YRT_TRY(tonemap_launch(d_out + (size_t)lr0 * rp.width, rp.d_ldr_rows + 4 * (size_t)lr0 * rp.width, (size_t)nrows * rp.width, st));
+        YRT_TRY(copy_rows_to_host(rp.d_ldr_rows, rp.h_ldr, rp.width, rp.height, rp.tile_rows, rp.rank, rp.world, 4, lr0, nrows, st));
+    }
     return YRT_OK;
 }
 
@@ -631,7 +685,10 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
     // batch's kernel fills the tail of the other's (each persistent kernel ends with ~one 32-ray task of idle SMs).
     // Default: 2 when this call renders one rank's share of a frame (measured at 1/8 frame: 2.265 -> 2.150 ms, 3 pipelines
     // 2.146, 4: 2.223), 1 for a whole frame (16.56 -> 16.46 ms only, and the per-kernel event spans stay unambiguous).
-    const int n_pipes = std::max(1, std::min(std::min(4, own), env_int("YRT_STREAMS", rp.world > 1 ? YRT_DEFAULT_STREAMS : 1)));
+    // ... and 2 whenever the rows go on to the host: the copy of the first batch then runs under the kernels of the second
+    // (unless per-kernel statistics were asked for: their event spans are only unambiguous on one stream).
+    const bool to_host = rp.h_rgba != nullptr || rp.h_ldr != nullptr;
+    const int n_pipes = std::max(1, std::min(std::min(4, own), env_int("YRT_STREAMS", (rp.world > 1 || (to_host && !stats)) ? YRT_DEFAULT_STREAMS : 1)));
     if (n_pipes > 1) batch_rows = std::min(batch_rows, (own + n_pipes - 1) / n_pipes);
     size_t cap_slots = (size_t)batch_rows * rp.width * spp;
     YRT_TRY(ensure_workspace(ds, ds.ws, cap_slots, nl, depth_cap, reflective));
@@ -669,6 +726,7 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
         Workspace& w = pipe ? ds.ws_aux[pipe - 1] : ds.ws;
         pt.st = pipe ? ds.aux_stream[pipe - 1] : st;
         YRT_TRY(run_batch(ds, w, rp, lr0, nrows, w.cap_slots, d_out, pt.st, pt, ring[pipe], depth_cap, reflective, false));
+        if (to_host && !rp.scatter && !pt.on) YRT_TRY(rows_to_host(rp, d_out, lr0, nrows, pt.st));
     }
     pt.st = st;
     for (int k = 1; k < n_pipes; k++) {
@@ -679,6 +737,8 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
         cudaEventRecord(pt.spans[frame_span - 1].b, st);
         pt.frames++;
         pt.primary += (int64_t)own * rp.width * spp;
+        // with statistics the frame span is the rendering alone: the rows go to the host behind it, in one piece
+        if (to_host && !rp.scatter) YRT_TRY(rows_to_host(rp, d_out, 0, own, st));
     }
     if (stats && sync_for_stats && !pt.deferred) YRT_TRY(collect_stats_device(ds, rp, stats));
     return YRT_OK;

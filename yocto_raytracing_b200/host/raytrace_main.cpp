@@ -5,7 +5,7 @@
 // (src/ext/yocto_utils.h:1085+).  Same flags, same four progress lines; additive flags only:
 //   --gpus N       interleaved row tiles over N GPUs
 //   --cache        keep the flattened scene next to the OBJ (<scene>.yrts) and reuse it while it is not older than
-//                  the OBJ: skips load_scene (SURVEY 8f.2 — the OBJ parse costs more than a frame)
+//                  the scene file or any material / texture / buffer file next to it: skips load_scene (SURVEY 8f.2 — the OBJ parse costs more than a frame)
 //   --device-ldr   tonemap on the GPU (yrt_render_ldr): a quarter of the bytes cross to the host and
 //                  the host tonemap (src/image.cpp:55-78) is skipped; ignored for .hdr outputs
 //   --fast-png     8-bit PNG outputs are written by yrt_write_png (parallel deflate) instead of stb_image_write: same pixels,
@@ -13,10 +13,12 @@
 //   --stats        ray counts and the time of every phase
 //   --allow-nonrigid  scenes with scaled / sheared instance frames are refused by default (the reference's result for them
 //                  depends on its own BVH visit order, include/yrt_b200.h); this flag renders them anyway
+#include <dirent.h>
 #include <sys/stat.h>
 
 #include <chrono>
 #include <cstdio>
+#include <cctype>
 #include <cstdlib>
 
 #include "ext/yocto_utils.h"   // reference
@@ -26,11 +28,33 @@
 namespace {
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-// the cache is valid if it exists and is not older than the scene file
+// The cache is valid if it exists and is not older than the scene file NOR than anything the scene may refer to: the loader
+// resolves mtllib / map_* / glTF buffer and image URIs relative to the scene's directory, so every scene-like, material,
+// texture or buffer file next to the scene counts as a dependency (a superset: a needless re-parse is cheap, a stale
+// render is not).
 bool cache_is_fresh(const std::string& scene_path, const std::string& cache_path) {
     struct stat a, b;
     if (stat(scene_path.c_str(), &a) != 0 || stat(cache_path.c_str(), &b) != 0) return false;
-    return b.st_mtime >= a.st_mtime;
+    if (b.st_mtime < a.st_mtime) return false;
+    auto slash = scene_path.find_last_of('/');
+    std::string dir = slash == std::string::npos ? "." : scene_path.substr(0, slash);
+    DIR* d = opendir(dir.c_str());
+    if (!d) return true;
+    static const char* exts[] = {".obj", ".mtl", ".gltf", ".glb", ".bin", ".png", ".jpg", ".jpeg", ".tga", ".bmp", ".hdr", ".ppm", ".pfm"};
+    bool fresh = true;
+    while (dirent* e = readdir(d)) {
+        std::string name = e->d_name;
+        auto dot = name.find_last_of('.');
+        if (dot == std::string::npos) continue;
+        std::string ext = name.substr(dot);
+        for (auto& c : ext) c = (char)tolower(c);
+        bool dep = false;
+        for (const char* x : exts) dep = dep || ext == x;
+        struct stat s;
+        if (dep && stat((dir + "/" + name).c_str(), &s) == 0 && S_ISREG(s.st_mode) && s.st_mtime > b.st_mtime) { fresh = false; break; }
+    }
+    closedir(d);
+    return fresh;
 }
 }  // namespace
 

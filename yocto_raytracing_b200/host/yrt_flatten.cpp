@@ -205,6 +205,15 @@ bool yrt_flat_load(const std::string& path, yrt_flat_scene& fs, std::string& err
     if (!ok) { fclose(f); err = path + ": not a YRTSCN01 file"; return false; }
     fs = yrt_flat_scene();
     std::vector<float> cam;
+    // no count may promise more bytes than the file still holds (a corrupt cache must not cause a huge allocation)
+    long file_size = 0;
+    {
+        long here = ftell(f);
+        fseek(f, 0, SEEK_END);
+        file_size = ftell(f);
+        fseek(f, here, SEEK_SET);
+    }
+    ok = n_arrays >= 0 && n_arrays <= 1024;
     for (int a = 0; a < n_arrays && ok; a++) {
         char nm[25] = {0};
         int32_t dt = 0;
@@ -212,6 +221,7 @@ bool yrt_flat_load(const std::string& path, yrt_flat_scene& fs, std::string& err
         ok = fread(nm, 1, 24, f) == 24 && fread(&dt, 4, 1, f) == 1 && fread(&count, 8, 1, f) == 1 && count >= 0 && dt >= 0 && dt <= 3;
         if (!ok) break;
         static const size_t esz[4] = {4, 4, 1, 8};
+        if ((unsigned long long)count > (unsigned long long)(file_size - ftell(f)) / esz[dt]) { ok = false; break; }
         size_t bytes = (size_t)count * esz[dt];
         std::string name(nm);
         void* dst = nullptr;
