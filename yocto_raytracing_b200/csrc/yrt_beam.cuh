@@ -176,89 +176,109 @@ __device__ __forceinline__ float warp_max_f(float v, bool nonneg) {
 
 // per-warp scratch in shared memory
 struct BeamScratch {
-    int stack[YRT_BEAM_STACK];
+    int stack[2 * YRT_BEAM_STACK];          // (level << 26 | number of children, first child) pairs
     int cand[YRT_BEAM_CAND_CAP];
     float cand_e[YRT_BEAM_CAND_CAP];
 };
 
-// The rays of the lanes in `rays_mask` (each with its slab operands) -> candidate instance slots in sc.cand[0 .. n),
-// sorted by DESCENDING beam entry distance (pushing them in this order leaves the nearest on top of a lane's stack).
+// bounds of the warp's ray origins (mirrored later, per light / per beam): computed once per warp of shadow rays, whose
+// origins are the same for every light; camera rays share one origin and need none of it
+struct BeamOrigins { vec3 lo, hi; };
+__device__ __forceinline__ BeamOrigins warp_beam_origins(const vec3& o, bool mine) {
+    const float big = 3.0e38f;
+    BeamOrigins r;
+    r.lo = mk3(warp_min_f(mine ? o.x : big, false), warp_min_f(mine ? o.y : big, false), warp_min_f(mine ? o.z : big, false));
+    r.hi = mk3(warp_max_f(mine ? o.x : -big, false), warp_max_f(mine ? o.y : -big, false), warp_max_f(mine ? o.z : -big, false));
+    return r;
+}
+
+// The rays of the lanes in `rays_mask` (each with its slab operands) -> candidate instance slots in sc.cand[0 .. n); with SORT
+// in DESCENDING beam entry distance (pushing them in this order leaves the nearest on top of a lane's stack).
 // Returns n >= 0, or -1 when the warp must fall back to the per-lane instance tree.  Every lane of the warp must call it
-// (lanes outside rays_mask help with the box tests); rays_mask must not be empty.
-__device__ __forceinline__ int warp_beam_candidates(const SceneView& sv, const ray3& ray, const slabray& sr, unsigned rays_mask, int lane, BeamScratch& sc,
-                                                    int* visits_out) {
+// (lanes outside rays_mask help with the box tests); rays_mask must not be empty.  org = bounds of the rays' origins.
+template <bool SORT>
+__device__ __forceinline__ int warp_beam_candidates(const SceneView& sv, const ray3& ray, const slabray& sr, const BeamOrigins& org, unsigned rays_mask, int lane,
+                                                    BeamScratch& sc, int* visits_out) {
     const unsigned FULL = 0xffffffffu;
     const bool mine = (rays_mask >> lane) & 1u;
-    // the mirror: the sign of the first ray's reciprocal direction on each axis; every ray must agree
-    const int first = __ffs(rays_mask) - 1;
-    const bool neg_x = __shfl_sync(FULL, sr.invd.x < 0.f ? 1 : 0, first) != 0, neg_y = __shfl_sync(FULL, sr.invd.y < 0.f ? 1 : 0, first) != 0,
-               neg_z = __shfl_sync(FULL, sr.invd.z < 0.f ? 1 : 0, first) != 0;
-    BeamLane bl;
-    const bool ok = mine && beam_lane_terms(ray, sr, neg_x, neg_y, neg_z, bl);
-    if (__ballot_sync(FULL, mine && !ok) != 0u) return -1;
-    // lanes without a ray take part in the reductions with neutral values
-    const float big = 3.0e38f;
-    const vec3 o_lo = ok ? bl.o : mk3(big, big, big), o_hi = ok ? bl.o : mk3(-big, -big, -big);
-    const vec3 i_lo = ok ? bl.i : mk3(big, big, big), i_hi = ok ? bl.i : mk3(0.f, 0.f, 0.f);
+    // one vote decides: every ray far enough from the axis planes (the rays that take the reference's slab formula never
+    // join a beam) and all reciprocal directions of one sign per axis
+    const float ax = fabsf(ray.d.x), ay = fabsf(ray.d.y), az = fabsf(ray.d.z);
+    const bool fit = fminf(fminf(ax, ay), az) >= 1.0f / 4096.0f && fmaxf(fmaxf(ax, ay), az) <= 1.0e30f;
+    if (__ballot_sync(FULL, mine && !fit) != 0u) return -1;
+    const unsigned nx = __ballot_sync(FULL, mine && sr.invd.x < 0.f), ny = __ballot_sync(FULL, mine && sr.invd.y < 0.f), nz = __ballot_sync(FULL, mine && sr.invd.z < 0.f);
+    if ((nx != 0u && nx != rays_mask) || (ny != 0u && ny != rays_mask) || (nz != 0u && nz != rays_mask)) return -1;
     Beam b;
-    b.sx = neg_x ? -1.f : 1.f; b.sy = neg_y ? -1.f : 1.f; b.sz = neg_z ? -1.f : 1.f;
-    b.omin = mk3(warp_min_f(o_lo.x, false), warp_min_f(o_lo.y, false), warp_min_f(o_lo.z, false));
-    b.omax = mk3(warp_max_f(o_hi.x, false), warp_max_f(o_hi.y, false), warp_max_f(o_hi.z, false));
-    b.imin = mk3(warp_min_f(i_lo.x, true), warp_min_f(i_lo.y, true), warp_min_f(i_lo.z, true));
-    b.imax = mk3(warp_max_f(i_hi.x, true), warp_max_f(i_hi.y, true), warp_max_f(i_hi.z, true));
-    b.tmin = warp_min_f(ok ? bl.tmin : big, false);
-    b.tmax = warp_max_f(ok ? bl.tmax : -big, false);
-    b.pad = 4.0f * warp_max_f(ok ? bl.pad : 0.f, true) + 1.0e-30f;
+    b.sx = nx ? -1.f : 1.f; b.sy = ny ? -1.f : 1.f; b.sz = nz ? -1.f : 1.f;
+    // mirrored origin bounds: min / max swap under the mirror
+    b.omin = mk3(nx ? -org.hi.x : org.lo.x, ny ? -org.hi.y : org.lo.y, nz ? -org.hi.z : org.lo.z);
+    b.omax = mk3(nx ? -org.lo.x : org.hi.x, ny ? -org.lo.y : org.hi.y, nz ? -org.lo.z : org.hi.z);
+    const float big = 3.0e38f;
+    b.imin = mk3(warp_min_f(mine ? sr.ainv.x : big, true), warp_min_f(mine ? sr.ainv.y : big, true), warp_min_f(mine ? sr.ainv.z : big, true));
+    b.imax = mk3(warp_max_f(mine ? sr.ainv.x : 0.f, true), warp_max_f(mine ? sr.ainv.y : 0.f, true), warp_max_f(mine ? sr.ainv.z : 0.f, true));
+    b.tmin = warp_min_f(mine ? fmaxf(ray.tmin, 0.f) : big, true);
+    b.tmax = warp_max_f(mine ? fmaxf(ray.tmax, 0.f) : 0.f, true);
+    b.pad = 4.0f * warp_max_f(mine ? sr.pad : 0.f, true) + 1.0e-30f;
 
     const unsigned lt = (1u << lane) - 1u;
     const int ns = sv.n_active_instances;
     int sp = 0, n = 0, visits = 0;
-    if (lane == 0) sc.stack[0] = (sv.beam_levels - 1) << 24;      // the top level is the single group of the root
-    sp = 1;
+    {   // the top level is the single group of the root: its record holds its run of children
+        const float4* grp = sv.beam_boxes + 2 * beam_box_index(ns, sv.beam_levels - 1, 0);
+        if (lane == 0) { sc.stack[0] = ((sv.beam_levels - 1) << 26) | float_as_int(ld4(grp + 1).w); sc.stack[1] = float_as_int(ld4(grp).w); }
+        sp = 1;
+    }
     while (sp > 0) {
         __syncwarp();
-        const int ent = sc.stack[--sp];
-        const int lvl = ent >> 24, g = ent & 0xffffff;
-        const float4* grp = sv.beam_boxes + 2 * beam_box_index(ns, lvl, g);
-        const int child_first = float_as_int(ld4(grp).w), child_count = float_as_int(ld4(grp + 1).w);
+        sp--;
+        const int ent = sc.stack[2 * sp], child_first = sc.stack[2 * sp + 1];
+        const int lvl = ent >> 26, child_count = ent & 0x3ffffff;
+        const float4* boxes = sv.beam_boxes + 2 * beam_box_index(ns, lvl - 1, child_first);
         for (int c0 = 0; c0 < child_count; c0 += YRT_BEAM_FANOUT) {      // (one round, except for the few groups with more than 32 children)
-            const int c = child_first + c0 + lane;
             bool hit = false;
             float e = 0.f;
+            float4 lo = mk4(0.f, 0.f, 0.f, 0.f), hi = lo;
             if (c0 + lane < child_count) {
-                const float4* bx = sv.beam_boxes + 2 * beam_box_index(ns, lvl - 1, c);
-                hit = beam_test(b, ld4(bx), ld4(bx + 1), e);
+                lo = ld4(boxes + 2 * (size_t)(c0 + lane));
+                hi = ld4(boxes + 2 * (size_t)(c0 + lane) + 1);
+                hit = beam_test(b, lo, hi, e);
             }
             visits++;
             const unsigned m = __ballot_sync(FULL, hit);
             const int k = __popc(m);
             if (lvl == 0) {
                 if (n + k > YRT_BEAM_CAND_CAP) return -1;
-                if (hit) { const int p = n + __popc(m & lt); sc.cand[p] = c; sc.cand_e[p] = e; }
+                if (hit) { const int p = n + __popc(m & lt); sc.cand[p] = child_first + c0 + lane; if (SORT) sc.cand_e[p] = e; }
                 n += k;
             } else {
                 if (sp + k > YRT_BEAM_STACK) return -1;
                 __syncwarp();      // every lane has read its entry before a slot is written again
-                if (hit) sc.stack[sp + __popc(m & lt)] = ((lvl - 1) << 24) | c;
+                if (hit) {         // the child's own record carries its run of children: nothing to fetch when it is popped
+                    const int p = sp + __popc(m & lt);
+                    sc.stack[2 * p] = ((lvl - 1) << 26) | float_as_int(hi.w);
+                    sc.stack[2 * p + 1] = float_as_int(lo.w);
+                }
                 sp += k;
             }
         }
     }
     __syncwarp();
     if (visits_out) *visits_out = visits;
-    // descending entry distance: lane j ranks candidate j (ties by position), then the list is rewritten in that order
-    int slot = 0, rank = 0;
-    float e = 0.f;
-    if (lane < n) {
-        slot = sc.cand[lane]; e = sc.cand_e[lane];
-        for (int k = 0; k < n; k++) {
-            const float ek = sc.cand_e[k];
-            rank += (ek > e || (ek == e && k < lane)) ? 1 : 0;
+    if (SORT && n > 1) {
+        // descending entry distance: lane j ranks candidate j (ties by position), then the list is rewritten in that order
+        int slot = 0, rank = 0;
+        float e = 0.f;
+        if (lane < n) {
+            slot = sc.cand[lane]; e = sc.cand_e[lane];
+            for (int k = 0; k < n; k++) {
+                const float ek = sc.cand_e[k];
+                rank += (ek > e || (ek == e && k < lane)) ? 1 : 0;
+            }
         }
+        __syncwarp();
+        if (lane < n) sc.cand[rank] = slot;
+        __syncwarp();
     }
-    __syncwarp();
-    if (lane < n) { sc.cand[rank] = slot; sc.cand_e[rank] = e; }
-    __syncwarp();
     return n;
 }
 #endif   // __CUDACC__

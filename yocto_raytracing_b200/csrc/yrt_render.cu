@@ -33,8 +33,11 @@ namespace yrt {
 #ifndef YRT_COUNTERS
 #define YRT_COUNTERS 0          /* 1: the traversal kernels count their own per-ray work (node visits, box / element tests, instance entries) — a separate build of the library, never the timed one */
 #endif
-#ifndef YRT_BEAM
-#define YRT_BEAM 1              /* camera rays and their shadow rays: the instance tree is walked once per warp (yrt_beam.cuh); 0 = per lane, as before */
+#ifndef YRT_BEAM_CLOSEST
+#define YRT_BEAM_CLOSEST 1      /* camera rays: the instance tree is walked once per warp (yrt_beam.cuh); 0 = per lane */
+#endif
+#ifndef YRT_BEAM_ANY
+#define YRT_BEAM_ANY 1          /* shadow rays of camera hits: likewise */
 #endif
 #define TRACE_THREADS 128
 #ifndef TRACE_MIN_BLOCKS
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_close
     const int lane = threadIdx.x & 31;
     const unsigned n_items = item_count(wd);
     int stack[STACK_INTS_CLOSEST];
-    __shared__ BeamScratch s_beam[(PRIMARY && YRT_BEAM) ? TRACE_THREADS / 32 : 1];
+    __shared__ BeamScratch s_beam[(PRIMARY && YRT_BEAM_CLOSEST) ? TRACE_THREADS / 32 : 1];
     YRT_CTR_DECL;
     for (;;) {
         unsigned idx = 0;
@@ -140,9 +143,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_close
         // camera rays: neighbouring samples form a beam — the warp walks the instance tree once (yrt_beam.cuh); mirror rays
         // (and warps whose rays do not form a beam) walk it per lane
         int n_cand = -1;
-        if (PRIMARY && YRT_BEAM && sv.beam_levels > 0) {
+        if (PRIMARY && YRT_BEAM_CLOSEST && sv.beam_levels > 0) {
             int visits = 0;
-            n_cand = warp_beam_candidates(sv, ray, make_slabray(ray.o, inv3_slab(ray.d)), __ballot_sync(0xffffffffu, alive), lane, s_beam[threadIdx.x >> 5], &visits);
+            BeamOrigins org;
+            org.lo = org.hi = bp.cam.frame.o;      // camera rays share their origin (raytrace.cpp:32)
+            n_cand = warp_beam_candidates<true>(sv, ray, make_slabray(ray.o, inv3_slab(ray.d)), org, __ballot_sync(0xffffffffu, alive), lane, s_beam[threadIdx.x >> 5],
+                                                YRT_COUNTERS ? &visits : nullptr);
             YRT_CTR_BEAM(n_cand, visits);
         }
         if (!alive) continue;
@@ -178,11 +184,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS_ANY) k_trace_a
     const int lane = threadIdx.x & 31;
     const unsigned n_items = item_count(wd);
     int stack[STACK_INTS_ANY];
-    __shared__ BeamScratch s_beam[YRT_BEAM ? TRACE_THREADS / 32 : 1];
+    __shared__ BeamScratch s_beam[YRT_BEAM_ANY ? TRACE_THREADS / 32 : 1];
     YRT_CTR_DECL;
     // the shadow rays of camera hits (act == null: slots in image order) towards one light form a beam like the camera
     // rays; those of mirror-ray hits (compacted queue) are traced per lane
-    const bool beams = YRT_BEAM && act == nullptr && sv.beam_levels > 0;
+    const bool beams = YRT_BEAM_ANY && act == nullptr && sv.beam_levels > 0;
     for (;;) {
         unsigned a = 0;
         bool alive = false;
@@ -197,6 +203,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS_ANY) k_trace_a
         }
         const unsigned rays_mask = __ballot_sync(0xffffffffu, alive);
         if (rays_mask == 0u) continue;
+        BeamOrigins org;
+        if (beams) org = warp_beam_origins(p, alive);      // the hit points: the same for every light
         // visibility of the lights as bit masks: word w of a slot holds lights 32 w .. 32 w + 31 (one store per hit for up to 32 lights)
         unsigned vm = 0u;
         for (int k = 0; k < sv.n_lights; k++) {
@@ -207,7 +215,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS_ANY) k_trace_a
             int n_cand = -1;
             if (beams) {
                 int visits = 0;
-                n_cand = warp_beam_candidates(sv, sr, make_slabray(sr.o, inv3_slab(sr.d)), rays_mask, lane, s_beam[threadIdx.x >> 5], &visits);
+                n_cand = warp_beam_candidates<false>(sv, sr, make_slabray(sr.o, inv3_slab(sr.d)), org, rays_mask, lane, s_beam[threadIdx.x >> 5], YRT_COUNTERS ? &visits : nullptr);
                 YRT_CTR_BEAM(n_cand, visits);
             }
             if (alive) {
