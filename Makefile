@@ -49,7 +49,7 @@ oracle/liboracle.so: oracle/yrt_oracle.c oracle/yrt_oracle.h include/yrt_b200.h
 hostemu: tests/host_emu/libyrt_hostemu.so tests/host_emu/libyrt_hostemu_bin.so tests/host_emu/libyrt_hostemu_wide.so
 # the same emulation with the other assignments of node arity to ray kind (build options, see yrt_scene.cuh): both ray kinds on
 # binary records / both on 4-wide records — keeps every visit routine under test without a GPU
-EMUFLAGS := $(ARCH) -O2 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-ffp-contract=off,-fopenmp -shared
+EMUFLAGS := -O2 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-ffp-contract=off,-fopenmp -shared
 tests/host_emu/libyrt_hostemu_bin.so: tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu $(HDRS)
 	$(NVCC) $(EMUFLAGS) -DYRT_WIDE_CLOSEST=2 -DYRT_WIDE_ANY=2 -I$(CSRC) -o $@ tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu -lgomp
 tests/host_emu/libyrt_hostemu_wide.so: tests/host_emu/host_emu.cu $(CSRC)/yrt_host.cu $(HDRS)

@@ -253,10 +253,9 @@ int yrt_intersect_any(yrt_scene* scn, const float* rays, int64_t n, uint8_t* occ
 /* Per-ray work counters of the traversal kernels, for the roofline record ("the builder must also report its
  * own per-ray counters"; the reference's sit at src/scene.cpp:371,229,468).  Only a library built with -DYRT_COUNTERS=1
  * counts (tools/build_variants.sh; never the timed build): the regular build returns YRT_ERR_UNSUPPORTED.  out = 3 kernel
- * classes (camera rays, mirror rays, shadow rays) x 12 words: rays, node visits, box tests, box tests in the instance tree,
- * element tests, instance entries; then per warp: beam walks of the instance tree, their node visits, the candidates they
- * produced, walks that fell back to the per-lane tree; 0, 0 — totals since the last call (reading resets them). */
-int yrt_counters_read(yrt_scene* scn, uint64_t out[36]);
+ * classes (camera rays, mirror rays, shadow rays) x 8 words: rays, node visits, box tests, box tests in the instance tree,
+ * element tests, instance entries, 0, 0 — totals since the last call (reading resets them). */
+int yrt_counters_read(yrt_scene* scn, uint64_t out[24]);
 
 /* test hook: copies the scene's node records (arity 2: 4 float4 per node, arity 4: 8 float4 per node; BLAS nodes of all
  * shapes, then TLAS nodes) of device 0 into out (HOST, capacity max_float4 float4s); returns the number of float4s the

@@ -55,19 +55,12 @@ class EmuScene:
             self._lib.emu_read_nodes(self.h, arity, C.c_void_p(out.ctypes.data))
         return out
 
-    def beam_audit(self, width, height, samples):
-        """(missed, groups walked, groups fallen back, accepted (ray, instance box) pairs) of the warp-level beam walk."""
-        out = (C.c_int64 * 4)()
-        cam = self.flat.camera_struct()
-        assert self._lib.emu_beam_audit(self.h, C.byref(cam), width, height, samples, out) == 0
-        return list(out)
-
     def trace_primary(self, width, height, samples):
         n = width * height * samples * samples
         ids = np.empty((n, 3), np.int32)
         dist = np.empty(n, np.float32)
         uv = np.empty((n, 2), np.float32)
-        ctr = (C.c_int64 * 12)()
+        ctr = (C.c_int64 * 8)()
         cam = self.flat.camera_struct()
         st = self._lib.emu_trace_primary(self.h, C.byref(cam), width, height, samples, C.c_void_p(ids.ctypes.data),
                                      C.c_void_p(dist.ctypes.data), C.c_void_p(uv.ctypes.data), ctr)
@@ -90,7 +83,7 @@ class EmuScene:
         img = np.empty((height, width, 4), np.float32)
         cam = self.flat.camera_struct()
         a = (C.c_float * 3)(amb, amb, amb)
-        rc = (C.c_int64 * 13)()
+        rc = (C.c_int64 * 9)()
         st = self._lib.emu_render(self.h, C.byref(cam), a, width, height, samples, max_depth, C.c_void_p(img.ctypes.data), rc)
         assert st == 0
         return img, list(rc)

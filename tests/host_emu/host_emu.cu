@@ -14,7 +14,6 @@
 
 #include "yrt_internal.h"
 #include "yrt_shade.cuh"
-#include "yrt_beam.cuh"
 #include "yrt_trace.cuh"
 
 using namespace yrt;
@@ -24,8 +23,6 @@ namespace {
 struct EmuLbvh {
     std::vector<float4> nodes2, nodes4;
     std::vector<int> order, seg_root, seg_depth, seg_need2, seg_need4, seg_box_lo, seg_box_hi;
-    std::vector<int> parent_int, parent_leaf, range_first, range_last;   // kept for the beam hierarchy
-    std::vector<float4> node_lo, node_hi;
 };
 
 void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi, const int* seg_of, const int* seg_first, int leaf_size,
@@ -83,7 +80,6 @@ void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi
         }
         for (int i = 0; i < n - 1; i++) emit_item(a, i);
     }
-    out.parent_int = pint; out.parent_leaf = pleaf; out.range_first = rfirst; out.range_last = rlast; out.node_lo = nlo; out.node_hi = nhi;
     for (int s = 0; s < n_seg; s++) single_root_item(a, s);
     if (n > 1) {
         for (int i = 0; i < n; i++) depth_item(a, i);
@@ -95,7 +91,7 @@ void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi
 struct EmuScene {
     HostScene hs;
     EmuLbvh blas, tlas;
-    std::vector<float4> prim_recs, prim_attrs, inst_recs, tlas_ch, beam_boxes;
+    std::vector<float4> prim_recs, prim_attrs, inst_recs;
     std::vector<int> prim_rank, inst_rank;
     std::vector<float4> nodes2, nodes4;   // BLAS nodes then TLAS nodes, like the device arrays
     SceneView view;
@@ -188,34 +184,6 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
         r[2] = mk4(fr[6], fr[7], fr[8], int_as_float(hs.inst_mat[inst]));
         r[3] = mk4(fr[9], fr[10], fr[11], int_as_float((int)((unsigned)s | ((unsigned)hs.shape_kind[s] << 28))));
     }
-    {   // the wide hierarchy over the instance slots (mirrors k_beam_leaf / k_beam_flag / k_beam_groups)
-        const BeamLevels beam = beam_levels_for(na);
-        es.tlas_ch.assign(2 * (size_t)std::max(na, 1), mk4(0, 0, 0, 0));
-        es.beam_boxes.assign(2 * (size_t)(beam.levels + 1) * (size_t)std::max(na, 1), mk4(0, 0, 0, 0));
-        for (int k = 0; k < na; k++) {
-            int it = es.tlas.order[k];
-            beam_leaf_item(ilo[it], ihi[it], &es.tlas_ch[2 * (size_t)k], &es.beam_boxes[2 * beam_box_index(na, -1, k)]);
-        }
-        BeamTree bt;
-        bt.n = na; bt.parent_int = es.tlas.parent_int.data(); bt.parent_leaf = es.tlas.parent_leaf.data(); bt.range_first = es.tlas.range_first.data();
-        bt.range_last = es.tlas.range_last.data(); bt.node_lo = es.tlas.node_lo.data(); bt.node_hi = es.tlas.node_hi.data();
-        std::vector<std::vector<int>> gidx(beam.levels), gnode(beam.levels);
-        std::vector<int> count(beam.levels, 0);
-        const int NONE = (int)0x80000000;
-        for (int l = 0; l < beam.levels; l++) {
-            std::vector<int> flag(na, 0);
-            gnode[l].assign(na, NONE);
-            for (int i = 0; i < na - 1; i++) beam_flag_node_item(bt, i, beam.threshold[l], flag.data(), gnode[l].data());
-            for (int k = 0; k < na; k++) beam_flag_slot_item(bt, k, beam.threshold[l], flag.data(), gnode[l].data());
-            gidx[l].assign(na, 0);
-            int run = 0;
-            for (int k = 0; k < na; k++) { gidx[l][k] = run; run += flag[k]; }
-            count[l] = run;
-            for (int k = 0; k < na; k++)
-                if (gnode[l][k] != NONE) beam_group_item(bt, k, l, gnode[l].data(), gidx[l].data(), l ? gidx[l - 1].data() : nullptr, l ? count[l - 1] : 0, es.beam_boxes.data());
-        }
-        es.view.beam_levels = beam.levels;
-    }
     es.blas_depth = es.blas.seg_depth.empty() ? 0 : *std::max_element(es.blas.seg_depth.begin(), es.blas.seg_depth.end());
     es.tlas_depth = es.tlas.seg_depth[0];
     {
@@ -225,7 +193,6 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
     }
     if (es.stack_need > YRT_STACK_CAP) { set_error("emu: tree too deep"); return YRT_ERR_UNSUPPORTED; }
     SceneView& v = es.view;
-    v.beam_boxes = es.beam_boxes.data(); v.tlas_ch = es.tlas_ch.data();
     v.nodes2 = es.nodes2.data(); v.nodes4 = es.nodes4.data(); v.inst_recs = es.inst_recs.data();
     v.prim_recs = es.prim_recs.data(); v.prim_attrs = es.prim_attrs.data(); v.mat_recs = hs.mat_recs.data();
     v.light_recs = hs.light_recs.data(); v.tex_rgba8 = hs.tex_rgba8.data(); v.tex_info = hs.tex_info.data();
@@ -241,49 +208,6 @@ void hit_to_ids(const SceneView& sv, const HitRec& h, int* ids) {
     ids[1] = float_as_int(ir[3].w) & 0x0fffffff;
     ids[2] = float_as_int(sv.prim_recs[3 * (size_t)h.prim].w);
 }
-
-}  // namespace
-
-namespace {
-// One warp's worth of rays (<= 32 consecutive work items) traced the way the kernels trace camera rays and their shadow
-// rays: the beam walk of the instance tree once for the group (host_beam_candidates = the device's warp_beam_candidates with
-// loops for lanes), then every ray on its own from the candidates; groups without a beam walk the instance tree per ray.
-struct GroupStats { long long beam_walks = 0, beam_visits = 0, beam_cands = 0, beam_fallbacks = 0; };
-template <bool ANY>
-void emu_trace_group(const SceneView& sv, const ray3* rays, const bool* alive, int n, HitRec* hits, bool* found, TraceCounters* tcs, int* stack, GroupStats* gs, bool use_beam) {
-    int cand[YRT_BEAM_CAND_CAP];
-    int n_cand = -1;
-    bool any_alive = false;
-    for (int l = 0; l < n; l++) any_alive = any_alive || alive[l];
-    if (use_beam && any_alive && sv.beam_levels > 0) {
-        slabray srs[32];
-        for (int l = 0; l < n; l++) srs[l] = make_slabray(rays[l].o, inv3_slab(rays[l].d));
-        int visits = 0;
-        n_cand = host_beam_candidates(sv, rays, srs, alive, n, cand, &visits);
-        if (gs) { if (n_cand >= 0) { gs->beam_walks++; gs->beam_visits += visits; gs->beam_cands += n_cand; } else gs->beam_fallbacks++; }
-    }
-    for (int l = 0; l < n; l++) {
-        if (!alive[l]) continue;
-        found[l] = n_cand >= 0 ? trace_ray_candidates<ANY>(sv, rays[l], hits[l], stack, cand, n_cand, tcs ? &tcs[l] : nullptr)
-                               : trace_ray<ANY>(sv, rays[l], hits[l], stack, tcs ? &tcs[l] : nullptr);
-    }
-}
-
-static camera_k emu_camera(const yrt_camera* cam) {
-    camera_k ck;
-    const float* f = cam->frame;
-    ck.frame.x = mk3(f[0], f[1], f[2]); ck.frame.y = mk3(f[3], f[4], f[5]); ck.frame.z = mk3(f[6], f[7], f[8]); ck.frame.o = mk3(f[9], f[10], f[11]);
-    ck.h = 2.0f * cam->focus * tanf(cam->fovy / 2.0f); ck.w = ck.h * cam->aspect; ck.focus = cam->focus;
-    return ck;
-}
-static ray3 emu_camera_ray(const camera_k& ck, size_t slot, int width, int height, int samples) {
-    size_t spp = (size_t)samples * samples, pix = slot / spp, s_ = slot - pix * spp;
-    int j = (int)(pix / width), i = (int)(pix - (size_t)j * width), jj = (int)(s_ / samples), ii = (int)(s_ - (size_t)jj * samples);
-    float u, v;
-    sample_uv(i, j, ii, jj, samples, width, height, u, v);
-    return eval_camera(ck, u, v);
-}
-static bool emu_use_beam() { const char* e = getenv("YRT_EMU_BEAM"); return !e || atoi(e) != 0; }
 
 }  // namespace
 
@@ -317,106 +241,39 @@ int64_t emu_read_nodes(void* p, int arity, float* out) {
     return n;
 }
 
-// counters_out (optional, 12 int64): box tests, prim tests, instance entries, max stack, fused-slab false rejects / extra accepts,
-// box tests in the instance tree, node visits, beam walks, their node visits, their candidates, fallbacks
+// counters_out (optional, 8 int64): box tests, prim tests, instance entries, max stack, fused-slab false rejects / extra accepts,
+// box tests in the instance tree, node visits
 int emu_trace_primary(void* p, const yrt_camera* cam, int width, int height, int samples, int32_t* ids, float* dist, float* uv,
                       int64_t* counters_out) {
     EmuScene* es = (EmuScene*)p;
-    const camera_k ck = emu_camera(cam);
-    const size_t n_slots = (size_t)width * height * samples * samples;
-    const long long n_groups = (long long)((n_slots + 31) / 32);
-    const bool beam = emu_use_beam();
-    long long cb = 0, cp = 0, ci = 0, cfr = 0, cea = 0, ctb = 0, cnv = 0, bw = 0, bv = 0, bc = 0, bf = 0; int cm = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(+ : cb, cp, ci, cfr, cea, ctb, cnv, bw, bv, bc, bf) reduction(max : cm)
-    for (long long g = 0; g < n_groups; g++) {
-        int stack[2 * YRT_STACK_CAP];
-        ray3 rays[32];
-        bool alive[32], found[32];
-        HitRec hits[32];
-        TraceCounters tcs[32];
-        const size_t base = (size_t)g * 32;
-        const int n = (int)std::min<size_t>(32, n_slots - base);
-        for (int l = 0; l < n; l++) { rays[l] = emu_camera_ray(ck, base + l, width, height, samples); alive[l] = true; tcs[l] = TraceCounters{0, 0, 0, 0, 0, 0, 0, 0}; }
-        GroupStats gs;
-        emu_trace_group<false>(es->view, rays, alive, n, hits, found, tcs, stack, &gs, beam);
-        bw += gs.beam_walks; bv += gs.beam_visits; bc += gs.beam_cands; bf += gs.beam_fallbacks;
-        for (int l = 0; l < n; l++) {
-            const TraceCounters& tc = tcs[l];
-            cb += tc.box_tests; cp += tc.prim_tests; ci += tc.inst_entries; cm = std::max(cm, tc.max_stack);
-            cfr += tc.slab_false_rejects; cea += tc.slab_extra_accepts; ctb += tc.tlas_box_tests; cnv += tc.node_visits;
-            const size_t r = base + l;
-            hit_to_ids(es->view, hits[l], ids + 3 * r);
-            if (dist) dist[r] = hits[l].dist;
-            if (uv) { uv[2 * r] = hits[l].w1; uv[2 * r + 1] = hits[l].w2; }
-        }
+    camera_k ck;
+    {
+        const float* f = cam->frame;
+        ck.frame.x = mk3(f[0], f[1], f[2]); ck.frame.y = mk3(f[3], f[4], f[5]); ck.frame.z = mk3(f[6], f[7], f[8]); ck.frame.o = mk3(f[9], f[10], f[11]);
+        ck.h = 2.0f * cam->focus * tanf(cam->fovy / 2.0f); ck.w = ck.h * cam->aspect; ck.focus = cam->focus;
     }
-    if (counters_out) { counters_out[0] = cb; counters_out[1] = cp; counters_out[2] = ci; counters_out[3] = cm; counters_out[4] = cfr; counters_out[5] = cea; counters_out[6] = ctb; counters_out[7] = cnv;
-        counters_out[8] = bw; counters_out[9] = bv; counters_out[10] = bc; counters_out[11] = bf; }
-    return YRT_OK;
-}
-
-// Audit of the beam walk (yrt_beam.cuh): for every group of 32 camera rays, and for the group's shadow rays towards every
-// light, every instance slot whose box the ray's OWN fused slab test accepts must be among the group's candidates (brute force
-// over all slots).  out[0] = instance boxes accepted by some ray but missing from its group's candidates (must be 0),
-// out[1] = groups walked, out[2] = groups that fell back to the per-ray tree, out[3] = (ray, slot) pairs checked and accepted.
-int emu_beam_audit(void* p, const yrt_camera* cam, int width, int height, int samples, int64_t* out) {
-    EmuScene* es = (EmuScene*)p;
-    const SceneView& sv = es->view;
-    const camera_k ck = emu_camera(cam);
-    const size_t n_slots = (size_t)width * height * samples * samples;
-    const long long n_groups = (long long)((n_slots + 31) / 32);
-    const int ns = sv.n_active_instances;
-    long long missed = 0, walked = 0, fell = 0, accepted = 0;
-#pragma omp parallel for schedule(dynamic, 16) reduction(+ : missed, walked, fell, accepted)
-    for (long long g = 0; g < n_groups; g++) {
+    long long cb = 0, cp = 0, ci = 0, cfr = 0, cea = 0, ctb = 0, cnv = 0; int cm = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : cb, cp, ci, cfr, cea, ctb, cnv) reduction(max : cm)
+    for (int j = 0; j < height; j++) {
         int stack[2 * YRT_STACK_CAP];
-        ray3 rays[32];
-        bool alive[32], found[32];
-        HitRec hits[32];
-        const size_t base = (size_t)g * 32;
-        const int n = (int)std::min<size_t>(32, n_slots - base);
-        for (int l = 0; l < n; l++) { rays[l] = emu_camera_ray(ck, base + l, width, height, samples); alive[l] = true; }
-        auto audit = [&](const ray3* rr, const bool* al) {
-            slabray srs[32];
-            int cand[YRT_BEAM_CAND_CAP];
-            bool any = false;
-            for (int l = 0; l < n; l++) { srs[l] = make_slabray(rr[l].o, inv3_slab(rr[l].d)); any = any || al[l]; }
-            if (!any || sv.beam_levels == 0) return;
-            int nc = host_beam_candidates(sv, rr, srs, al, n, cand, nullptr);
-            if (nc < 0) { fell++; return; }
-            walked++;
-            for (int l = 0; l < n; l++) {
-                if (!al[l]) continue;
-                for (int k = 0; k < ns; k++) {
-                    const float4* ch = sv.tlas_ch + 2 * (size_t)k;
-                    float e;
-                    if (!slab_test_ch(srs[l], rr[l].tmin, rr[l].tmax, ch[0].x, ch[0].y, ch[0].z, ch[1].x, ch[1].y, ch[1].z, e)) continue;
-                    accepted++;
-                    bool in = false;
-                    for (int j = 0; j < nc; j++) in = in || cand[j] == k;
-                    if (!in) missed++;
+        for (int i = 0; i < width; i++)
+            for (int jj = 0; jj < samples; jj++)
+                for (int ii = 0; ii < samples; ii++) {
+                    size_t r = (((size_t)j * width + i) * samples + jj) * samples + ii;
+                    float u, v;
+                    sample_uv(i, j, ii, jj, samples, width, height, u, v);
+                    ray3 ray = eval_camera(ck, u, v);
+                    HitRec h;
+                    TraceCounters tc = {0, 0, 0, 0, 0, 0, 0, 0};
+                    trace_ray<false>(es->view, ray, h, stack, &tc);
+                    cb += tc.box_tests; cp += tc.prim_tests; ci += tc.inst_entries; cm = std::max(cm, tc.max_stack);
+                    cfr += tc.slab_false_rejects; cea += tc.slab_extra_accepts; ctb += tc.tlas_box_tests; cnv += tc.node_visits;
+                    hit_to_ids(es->view, h, ids + 3 * r);
+                    if (dist) dist[r] = h.dist;
+                    if (uv) { uv[2 * r] = h.w1; uv[2 * r + 1] = h.w2; }
                 }
-            }
-        };
-        audit(rays, alive);
-        emu_trace_group<false>(sv, rays, alive, n, hits, found, nullptr, stack, nullptr, true);
-        ray3 srays[32];
-        bool ok[32];
-        for (int k = 0; k < sv.n_lights; k++) {
-            for (int l = 0; l < n; l++) {
-                ok[l] = hits[l].si >= 0;
-                srays[l] = rays[l];
-                if (!ok[l]) continue;
-                int kind;
-                vec3 P = eval_hit_pos(sv, hits[l].si, hits[l].prim, hits[l].w1, hits[l].w2, kind);
-                vec3 lv, ke; float r;
-                light_vector(sv, k, P, lv, r, ke);
-                srays[l] = shadow_ray(P, lv, r);
-            }
-            audit(srays, ok);
-        }
     }
-    out[0] = missed; out[1] = walked; out[2] = fell; out[3] = accepted;
+    if (counters_out) { counters_out[0] = cb; counters_out[1] = cp; counters_out[2] = ci; counters_out[3] = cm; counters_out[4] = cfr; counters_out[5] = cea; counters_out[6] = ctb; counters_out[7] = cnv; }
     return YRT_OK;
 }
 
@@ -443,112 +300,72 @@ int emu_intersect(void* p, const float* rays, int64_t n, int32_t* ids, float* di
     return YRT_OK;
 }
 
-// the whole frame with the device functions and the kernels' grouping: per group of 32 consecutive camera samples the beam
-// walk + closest hit, per light the beam walk of the group's shadow rays + any hit, shade; mirror paths continue per ray
-// (like the compacted queue launches) with the same explicit {c, kr, la} stack as k_shade; ordered per-pixel sum at the end.
-// ray_counts (optional, 13 int64): primary, reflection, shadow, then for the shadow rays: box tests, tlas box tests,
-// prim tests, instance entries, occluded, node visits, beam walks, their node visits, their candidates, fallbacks
+// the whole frame with the device functions: raygen -> closest -> shadow (any) -> shade -> reflection
+// loop with the same explicit {c, kr, la} stack as k_shade -> ordered per-pixel sum.
+// ray_counts (optional, 9 int64): primary, reflection, shadow, then for the shadow rays: box tests, tlas box tests,
+// prim tests, instance entries, occluded, node visits
 int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, int height, int samples, int max_depth, float* rgba,
                int64_t* ray_counts) {
     EmuScene* es = (EmuScene*)p;
     const SceneView& sv = es->view;
-    const camera_k ck = emu_camera(cam);
+    camera_k ck;
+    {
+        const float* f = cam->frame;
+        ck.frame.x = mk3(f[0], f[1], f[2]); ck.frame.y = mk3(f[3], f[4], f[5]); ck.frame.z = mk3(f[6], f[7], f[8]); ck.frame.o = mk3(f[9], f[10], f[11]);
+        ck.h = 2.0f * cam->focus * tanf(cam->fovy / 2.0f); ck.w = ck.h * cam->aspect; ck.focus = cam->focus;
+    }
     vec3 ambv = mk3(amb[0], amb[1], amb[2]);
     if (max_depth <= 0) max_depth = 16;
-    const int spp = samples * samples;
-    const size_t n_slots = (size_t)width * height * spp;
-    const long long n_groups = (long long)((n_slots + 31) / 32);
-    const bool beam = emu_use_beam();
-    std::vector<vec3> rad(n_slots);
-    long long n_refl = 0, n_shadow = 0, sb = 0, stb = 0, sp_ = 0, si_ = 0, socc = 0, snv = 0, bw = 0, bv = 0, bc = 0, bf = 0;
-#pragma omp parallel for schedule(dynamic, 16) reduction(+ : n_refl, n_shadow, sb, stb, sp_, si_, socc, snv, bw, bv, bc, bf)
-    for (long long g = 0; g < n_groups; g++) {
+    long long n_refl = 0, n_shadow = 0, sb = 0, stb = 0, sp_ = 0, si_ = 0, socc = 0, snv = 0;
+#pragma omp parallel for schedule(dynamic, 2) reduction(+ : n_refl, n_shadow, sb, stb, sp_, si_, socc, snv)
+    for (int j = 0; j < height; j++) {
         int stack[2 * YRT_STACK_CAP];
-        ray3 rays[32], srays[32];
-        bool alive[32], found[32], occl[32];
-        HitRec hits[32], shits[32];
-        TraceCounters tcs[32];
-        std::vector<uint8_t> vis((size_t)32 * std::max(sv.n_lights, 1));
-        const size_t base = (size_t)g * 32;
-        const int n = (int)std::min<size_t>(32, n_slots - base);
-        for (int l = 0; l < n; l++) { rays[l] = emu_camera_ray(ck, base + l, width, height, samples); alive[l] = true; }
-        emu_trace_group<false>(sv, rays, alive, n, hits, found, nullptr, stack, nullptr, beam);
-        // shadow rays of the camera hits, one light at a time for the whole group
-        vec3 P[32];
-        bool hit_ok[32];
-        for (int l = 0; l < n; l++) {
-            hit_ok[l] = hits[l].si >= 0;
-            int kind;
-            if (hit_ok[l]) P[l] = eval_hit_pos(sv, hits[l].si, hits[l].prim, hits[l].w1, hits[l].w2, kind);
-        }
-        for (int k = 0; k < sv.n_lights; k++) {
-            for (int l = 0; l < n; l++) {
-                tcs[l] = TraceCounters{0, 0, 0, 0, 0, 0, 0, 0};
-                if (!hit_ok[l]) { srays[l] = rays[l]; continue; }
-                vec3 lv, ke; float r;
-                light_vector(sv, k, P[l], lv, r, ke);
-                srays[l] = shadow_ray(P[l], lv, r);
-            }
-            GroupStats gs;
-            emu_trace_group<true>(sv, srays, hit_ok, n, shits, occl, tcs, stack, &gs, beam);
-            bw += gs.beam_walks; bv += gs.beam_visits; bc += gs.beam_cands; bf += gs.beam_fallbacks;
-            for (int l = 0; l < n; l++) {
-                if (!hit_ok[l]) continue;
-                vis[(size_t)l * sv.n_lights + k] = occl[l] ? 0 : 1;
-                n_shadow++;
-                sb += tcs[l].box_tests; stb += tcs[l].tlas_box_tests; sp_ += tcs[l].prim_tests; si_ += tcs[l].inst_entries; socc += occl[l] ? 1 : 0; snv += tcs[l].node_visits;
-            }
-        }
-        // shade; mirror paths go on per ray
-        for (int l = 0; l < n; l++) {
-            std::vector<vec3> sc, skr, sla;      // the {c, kr, la} stack of the path (grows with the depth really reached)
-            vec3 value = mk3(0.f, 0.f, 0.f);
-            int depth = 0;
-            ray3 ray = rays[l];
-            HitRec h = hits[l];
-            std::vector<uint8_t> v1(std::max(sv.n_lights, 1));
-            const uint8_t* vrow = &vis[(size_t)l * sv.n_lights];
-            for (;;) {
-                if (h.si < 0) { value = mk3(0.f, 0.f, 0.f); break; }
-                vec3 c, kr, la; ray3 rr;
-                bool spawn = shade_hit(sv, h.si, h.prim, h.w1, h.w2, ray.o, ambv, sv.srgb_lut, [&](int k) { return vrow[k] != 0; },
-                                       depth + 1 < max_depth, value, c, kr, la, rr);
-                if (!spawn) break;
-                sc.push_back(c); skr.push_back(kr); sla.push_back(la);
-                ray = rr;
-                depth++;
-                trace_ray<false>(sv, ray, h, stack, nullptr);
-                n_refl++;
-                if (h.si >= 0) {
-                    int kind;
-                    vec3 Pm = eval_hit_pos(sv, h.si, h.prim, h.w1, h.w2, kind);
-                    for (int k = 0; k < sv.n_lights; k++) {
-                        vec3 lv, ke; float r;
-                        light_vector(sv, k, Pm, lv, r, ke);
-                        ray3 sr = shadow_ray(Pm, lv, r);
-                        HitRec hr;
-                        TraceCounters tc = {0, 0, 0, 0, 0, 0, 0, 0};
-                        v1[k] = trace_ray<true>(sv, sr, hr, stack, &tc) ? 0 : 1;
-                        n_shadow++;
-                        sb += tc.box_tests; stb += tc.tlas_box_tests; sp_ += tc.prim_tests; si_ += tc.inst_entries; socc += v1[k] ? 0 : 1; snv += tc.node_visits;
+        std::vector<vec3> sc(max_depth), skr(max_depth), sla(max_depth);
+        std::vector<uint8_t> vis(std::max(sv.n_lights, 1));
+        for (int i = 0; i < width; i++) {
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            for (int jj = 0; jj < samples; jj++)
+                for (int ii = 0; ii < samples; ii++) {
+                    float u, v;
+                    sample_uv(i, j, ii, jj, samples, width, height, u, v);
+                    ray3 ray = eval_camera(ck, u, v);
+                    vec3 value = mk3(0.f, 0.f, 0.f);
+                    int depth = 0;
+                    for (;;) {
+                        HitRec h;
+                        trace_ray<false>(sv, ray, h, stack, nullptr);
+                        if (depth > 0) n_refl++;
+                        if (h.si < 0) { value = mk3(0.f, 0.f, 0.f); break; }
+                        int kind;
+                        vec3 P = eval_hit_pos(sv, h.si, h.prim, h.w1, h.w2, kind);
+                        for (int k = 0; k < sv.n_lights; k++) {
+                            vec3 l, ke; float r;
+                            light_vector(sv, k, P, l, r, ke);
+                            ray3 sr = shadow_ray(P, l, r);
+                            HitRec hr;
+                            TraceCounters tc = {0, 0, 0, 0, 0, 0, 0, 0};
+                            vis[k] = trace_ray<true>(sv, sr, hr, stack, &tc) ? 0 : 1;
+                            n_shadow++;
+                            sb += tc.box_tests; stb += tc.tlas_box_tests; sp_ += tc.prim_tests; si_ += tc.inst_entries; socc += vis[k] ? 0 : 1; snv += tc.node_visits;
+                        }
+                        vec3 c, kr, la; ray3 rr;
+                        bool spawn = shade_hit(sv, h.si, h.prim, h.w1, h.w2, ray.o, ambv, sv.srgb_lut, [&](int k) { return vis[k] != 0; },
+                                               depth + 1 < max_depth, value, c, kr, la, rr);
+                        if (!spawn) break;
+                        sc[depth] = c; skr[depth] = kr; sla[depth] = la;
+                        ray = rr;
+                        depth++;
                     }
-                    vrow = v1.data();
+                    for (int d = depth - 1; d >= 0; d--) value = combine_reflection(sc[d], value, skr[d], sla[d]);
+                    sx += value.x; sy += value.y; sz += value.z;
                 }
-            }
-            for (int d = depth - 1; d >= 0; d--) value = combine_reflection(sc[d], value, skr[d], sla[d]);
-            rad[base + l] = value;
+            float dn = (float)(samples * samples);
+            float* o = rgba + 4 * ((size_t)j * width + i);
+            o[0] = sx / dn; o[1] = sy / dn; o[2] = sz / dn; o[3] = 1.0f;
         }
     }
-    for (size_t pix = 0; pix < (size_t)width * height; pix++) {
-        float sx = 0.f, sy = 0.f, sz = 0.f;
-        for (int s_ = 0; s_ < spp; s_++) { const vec3& v = rad[pix * spp + s_]; sx += v.x; sy += v.y; sz += v.z; }
-        float dn = (float)spp;
-        float* o = rgba + 4 * pix;
-        o[0] = sx / dn; o[1] = sy / dn; o[2] = sz / dn; o[3] = 1.0f;
-    }
-    if (ray_counts) { ray_counts[0] = (long long)n_slots; ray_counts[1] = n_refl; ray_counts[2] = n_shadow;
-        ray_counts[3] = sb; ray_counts[4] = stb; ray_counts[5] = sp_; ray_counts[6] = si_; ray_counts[7] = socc; ray_counts[8] = snv;
-        ray_counts[9] = bw; ray_counts[10] = bv; ray_counts[11] = bc; ray_counts[12] = bf; }
+    if (ray_counts) { ray_counts[0] = (long long)width * height * samples * samples; ray_counts[1] = n_refl; ray_counts[2] = n_shadow;
+        ray_counts[3] = sb; ray_counts[4] = stb; ray_counts[5] = sp_; ray_counts[6] = si_; ray_counts[7] = socc; ray_counts[8] = snv; }
     return YRT_OK;
 }
 

@@ -136,16 +136,3 @@ def test_emulated_device_hit_ids_full_size(case):
     assert same.mean() >= 0.9999, (same.mean(), int((~same).sum()))
     assert np.array_equal(d[same].view(np.uint32), dist[same].view(np.uint32))
     assert ctr[4] == 0 and ctr[3] <= es.info()[6] <= 128
-
-
-@pytest.mark.parametrize("maker,w,h,s", [(lambda: load_golden("instance10000")[0], 64, 36, 4), (lambda: load_golden("instance10000")[0], 128, 72, 1),
-                                         (lambda: load_golden("simple")[0], 96, 54, 3), (lambda: load_golden("mixed7")[0], 96, 54, 2),
-                                         (lambda: load_golden("gltf7")[0], 64, 36, 2), (lambda: load_golden("lines_synth")[0], 64, 36, 2)])
-def test_beam_walk_never_loses_an_instance(maker, w, h, s):
-    """The warp-level walk of the instance tree (csrc/yrt_beam.cuh) may only ADD candidates: for every group of 32 camera
-    rays and for its shadow rays towards every light, every instance box that a ray's own slab test accepts (brute force
-    over all instances) is in the group's candidate list."""
-    es = _emu.EmuScene(maker())
-    missed, walked, fell, accepted = es.beam_audit(w, h, s)
-    assert missed == 0, (missed, walked, fell, accepted)
-    assert walked > 0 and accepted > 0

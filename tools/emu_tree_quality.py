@@ -14,17 +14,16 @@ from yocto_raytracing_b200 import synth  # noqa: E402
 
 variant = sys.argv[1] if len(sys.argv) > 1 else ""
 flat = synth.instance_grid_scene(100).flat()
-w, h, smp = 480, 270, 4      # 16 spp like the headline config: a group of 32 work items = the samples of two neighbouring pixels
+w, h = 640, 360
 t0 = time.time()
 es = _emu.EmuScene(flat, variant=variant)
 t1 = time.time()
-ids, dist, uv, c = es.trace_primary(w, h, smp)
-n = w * h * smp * smp
+ids, dist, uv, c = es.trace_primary(w, h, 1)
+n = w * h
 print(f"variant '{variant or 'default'}' primary: visits/ray {c[7] / n:.2f}, box tests/ray {c[0] / n:.2f} (tlas {c[6] / n:.2f}, blas {(c[0] - c[6]) / n:.2f}), "
       f"element tests {c[1] / n:.2f}, instance entries {c[2] / n:.2f}, max stack {c[3]}, false rejects {c[4]}, depth blas/tlas {es.info()[2]}/{es.info()[3]}, "
-      f"beam walks {c[8]} ({c[9] / max(c[8], 1):.2f} visits, {c[10] / max(c[8], 1):.2f} candidates each, {c[11]} fallbacks), "
       f"build {t1 - t0:.2f} s, hits {(ids[:, 0] >= 0).mean():.4f}, checksum {int(ids.astype('int64').sum())} {float(dist[ids[:,0]>=0].astype('float64').sum()):.6f}")
-img, rc = es.render(w // 2, h // 2, smp)
+img, rc = es.render(w // 2, h // 2, 1)
 ns = max(rc[2], 1)
 print(f"  shadow rays: visits/ray {rc[8] / ns:.2f}, box tests/ray {rc[3] / ns:.2f} (tlas {rc[4] / ns:.2f}), element tests {rc[5] / ns:.2f}, "
-      f"instance entries {rc[6] / ns:.2f}, occluded {rc[7] / ns:.3f}, beam walks {rc[9]} ({rc[10] / max(rc[9], 1):.2f} visits, {rc[11] / max(rc[9], 1):.2f} candidates each, {rc[12]} fallbacks)")
+      f"instance entries {rc[6] / ns:.2f}, occluded {rc[7] / ns:.3f}")

@@ -176,7 +176,7 @@ int64_t yrt_debug_read_nodes(yrt_scene* scn, int arity, float* out, int64_t max_
     return n;
 }
 
-int yrt_counters_read(yrt_scene* scn, uint64_t out[36]) {
+int yrt_counters_read(yrt_scene* scn, uint64_t out[24]) {
     if (!scn || scn->dev.empty() || !out) { set_error("yrt_counters_read: bad arguments"); return YRT_ERR_INVALID; }
     return read_counters_device(*scn->dev[0], out);
 }

@@ -283,7 +283,6 @@ struct LbvhIo {
     int *seg_root, *seg_depth, *seg_need2, *seg_need4;   // [n_seg]
     int *seg_box_lo, *seg_box_hi;           // [3*n_seg] ordered ints
     int* order;                             // [n] item id at sorted slot (temp arena, read by the gather kernels)
-    LbvhArrays arr;                         // all arrays of the finished build (temp arena)
 };
 
 static inline int grid_for(int n, int t = 256) { return n > 0 ? (n + t - 1) / t : 1; }
@@ -312,7 +311,6 @@ static int lbvh_build(cudaStream_t st, Arena& tmp, LbvhIo& io) {
     a.need2 = tmp.take<int>(ni);
     a.need4 = tmp.take<int>(ni);
     int* ghist = tmp.take<int>(radix_hist_ints(n));
-    io.arr = a;
     if (!tmp.base) return YRT_OK;   // dry pass
 
     a.nodes2 = io.nodes2; a.nodes4 = io.nodes4; a.ref_offset = io.ref_offset; a.size_bits = io.size_bits; a.rotate_pairs = io.rotate_pairs;
@@ -350,30 +348,8 @@ static int lbvh_build(cudaStream_t st, Arena& tmp, LbvhIo& io) {
             k_stackneed<<<grid_for(n), 256, 0, st>>>(a);
         }
     }
-    io.arr = a;
     YRT_CUDA(cudaGetLastError());
     return YRT_OK;
-}
-
-// the wide hierarchy over the instance slots for the warp-level beam walk (yrt_beam.cuh)
-#define YRT_BEAM_NONE ((int)0x80000000)
-__global__ void k_beam_leaf(int n, const int* __restrict__ order, const float4* __restrict__ ilo, const float4* __restrict__ ihi, float4* __restrict__ ch,
-                            float4* __restrict__ boxes) {
-    int k = YRT_TID();
-    if (k >= n) return;
-    int it = order[k];
-    beam_leaf_item(ilo[it], ihi[it], ch + 2 * (size_t)k, boxes + 2 * beam_box_index(n, -1, k));
-}
-__global__ void k_beam_init(int n, int* flag, int* gnode) { int k = YRT_TID(); if (k < n) { flag[k] = 0; gnode[k] = YRT_BEAM_NONE; } }
-__global__ void k_beam_flag(BeamTree t, int T, int* flag, int* gnode) {
-    int k = YRT_TID();
-    if (k < t.n - 1) beam_flag_node_item(t, k, T, flag, gnode);
-    if (k < t.n) beam_flag_slot_item(t, k, T, flag, gnode);
-}
-__global__ void k_beam_count(int n, const int* gidx, const int* gnode, int* count) { if (YRT_TID() == 0) *count = gidx[n - 1] + (gnode[n - 1] != YRT_BEAM_NONE ? 1 : 0); }
-__global__ void k_beam_groups(BeamTree t, int level, const int* gnode, const int* gidx, const int* gidx_below, const int* n_below, float4* boxes) {
-    int k = YRT_TID();
-    if (k < t.n && gnode[k] != YRT_BEAM_NONE) beam_group_item(t, k, level, gnode, gidx, gidx_below, n_below ? *n_below : 0, boxes);
 }
 
 // rank tables into leaf order (the ranks are computed on a host thread while the trees are built)
@@ -429,9 +405,6 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
     float* d_inst_frame = nullptr;
     float4 *plo = nullptr, *phi = nullptr, *ilo = nullptr, *ihi = nullptr, *d_nodes2 = nullptr, *d_nodes4 = nullptr, *d_prim_recs = nullptr, *d_prim_attrs = nullptr, *d_inst_recs = nullptr;
     int *d_prim_rank = nullptr, *d_inst_rank = nullptr;
-    float4 *d_tlas_ch = nullptr, *d_beam_boxes = nullptr;
-    const BeamLevels beam = beam_levels_for(na);
-    int *beam_gidx[YRT_BEAM_MAX_LEVELS] = {}, *beam_gnode[YRT_BEAM_MAX_LEVELS] = {}, *beam_count = nullptr;
     LbvhIo bo, to;
     const int tl_sf[2] = {0, na};
     // results block read back in one copy: [blas depth | blas need (binary) | blas need (4-wide) | tlas depth, need2, need4, root]
@@ -465,8 +438,6 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
         d_inst_recs = keep.take<float4>(4 * (size_t)std::max(na, 1));
         d_prim_rank = keep.take<int>((size_t)std::max(np, 1));
         d_inst_rank = keep.take<int>((size_t)std::max(na, 1));
-        d_tlas_ch = keep.take<float4>(2 * (size_t)std::max(na, 1));
-        d_beam_boxes = keep.take<float4>(2 * (size_t)(beam.levels + 1) * (size_t)std::max(na, 1));
         v.mat_recs = up_keep((float4*)nullptr, hs.mat_recs);
         v.light_recs = up_keep((float4*)nullptr, hs.light_recs);
         v.tex_rgba8 = up_keep((uint8_t*)nullptr, hs.tex_rgba8);
@@ -508,8 +479,6 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
         int* blas_root = tmp.take<int>((size_t)nsh);
         int* tl_box_lo = tmp.take<int>(3);
         int* tl_box_hi = tmp.take<int>(3);
-        for (int l = 0; l < beam.levels; l++) { beam_gidx[l] = tmp.take<int>((size_t)std::max(na, 1)); beam_gnode[l] = tmp.take<int>((size_t)std::max(na, 1)); }
-        beam_count = tmp.take<int>(YRT_BEAM_MAX_LEVELS);
         // ---- BLAS: all shapes in one build ----
         bo.n = np; bo.n_seg = nsh; bo.leaf_size = leaf_blas; bo.ref_offset = 0; bo.size_bits = size_bits_blas; bo.rotate_rounds = rotate_blas; bo.rotate_pairs = rotate_pairs_blas;
         bo.box_lo = plo; bo.box_hi = phi; bo.seg_of = g.prim_shape; bo.seg_first = g.shape_prim_off; bo.nodes2 = d_nodes2; bo.nodes4 = d_nodes4;
@@ -539,19 +508,6 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
     if (na > 0) k_inst_boxes<<<grid_for(na), 256, 0, st>>>(na, d_active, d_inst_frame, d_inst_shape, bo.seg_box_lo, bo.seg_box_hi, ilo, ihi);
     YRT_TRY(lbvh_build(st, tmp, to));
     if (na > 0) k_inst_recs<<<grid_for(na), 256, 0, st>>>(na, to.order, d_active, d_inst_frame, d_inst_shape, d_inst_mat, d_shape_kind, bo.seg_root, d_inst_recs);
-    if (na > 0) {
-        k_beam_leaf<<<grid_for(na), 256, 0, st>>>(na, to.order, ilo, ihi, d_tlas_ch, d_beam_boxes);
-        BeamTree bt;
-        bt.n = na; bt.parent_int = to.arr.parent_int; bt.parent_leaf = to.arr.parent_leaf; bt.range_first = to.arr.range_first; bt.range_last = to.arr.range_last;
-        bt.node_lo = to.arr.node_lo; bt.node_hi = to.arr.node_hi;
-        for (int l = 0; l < beam.levels; l++) {
-            k_beam_init<<<grid_for(na), 256, 0, st>>>(na, beam_gidx[l], beam_gnode[l]);
-            k_beam_flag<<<grid_for(na), 256, 0, st>>>(bt, beam.threshold[l], beam_gidx[l], beam_gnode[l]);
-            k_rs_scan<<<1, 1024, 0, st>>>(beam_gidx[l], na);     // flags -> exclusive prefix sums = group indices
-            k_beam_count<<<1, 32, 0, st>>>(na, beam_gidx[l], beam_gnode[l], beam_count + l);
-            k_beam_groups<<<grid_for(na), 256, 0, st>>>(bt, l, beam_gnode[l], beam_gidx[l], l ? beam_gidx[l - 1] : nullptr, l ? beam_count + l - 1 : nullptr, d_beam_boxes);
-        }
-    }
     YRT_CUDA(cudaGetLastError());
     const double t_enqueued = now_ms();
     // tie-break ranks: computed on a host thread since yrt_scene_create started (yrt_host.cu); needed only now
@@ -601,9 +557,6 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
     v.tlas_root = troot;
     v.n_lights = (int)hs.light_inst.size();
     v.n_active_instances = na;
-    v.beam_boxes = d_beam_boxes;
-    v.tlas_ch = d_tlas_ch;
-    v.beam_levels = beam.levels;
     return YRT_OK;
 }
 

@@ -7,7 +7,6 @@
 #include <vector>
 
 #include "../../include/yrt_b200.h"
-#include "yrt_beam.cuh"
 #include "yrt_lbvh.cuh"
 #include "yrt_scene.cuh"
 
@@ -154,8 +153,8 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
 int collect_stats_device(DevScene& ds, const RenderParams& rp, yrt_stats* stats);
 // allocates the render workspace of a (width x height, samples) frame now instead of inside the first render call
 int presize_workspace_device(DevScene& ds, int width, int height, int samples);
-// per-ray work counters (-DYRT_COUNTERS=1 builds): 3 kernel classes x 12 words, read and reset
-int read_counters_device(DevScene& ds, uint64_t out[36]);
+// per-ray work counters (-DYRT_COUNTERS=1 builds): 3 kernel classes x 8 words, read and reset
+int read_counters_device(DevScene& ds, uint64_t out[24]);
 int stats_begin_device(DevScene& ds);
 int stats_end_device(DevScene& ds, yrt_stats* stats);
 int trace_primary_device(DevScene& ds, const RenderParams& rp, int32_t* h_ids, float* h_dist, float* h_uv);

@@ -21,7 +21,6 @@
 
 #include "yrt_internal.h"
 #include "yrt_shade.cuh"
-#include "yrt_beam.cuh"
 #include "yrt_trace.cuh"
 #include "yrt_work.cuh"
 
@@ -32,12 +31,6 @@ namespace yrt {
 #endif
 #ifndef YRT_COUNTERS
 #define YRT_COUNTERS 0          /* 1: the traversal kernels count their own per-ray work (node visits, box / element tests, instance entries) — a separate build of the library, never the timed one */
-#endif
-#ifndef YRT_BEAM_CLOSEST
-#define YRT_BEAM_CLOSEST 1      /* camera rays: the instance tree is walked once per warp (yrt_beam.cuh); 0 = per lane */
-#endif
-#ifndef YRT_BEAM_ANY
-#define YRT_BEAM_ANY 1          /* shadow rays of camera hits: likewise */
 #endif
 #define TRACE_THREADS 128
 #ifndef TRACE_MIN_BLOCKS
@@ -83,18 +76,15 @@ __device__ __forceinline__ unsigned item_count(const WorkDist& wd) { return wd.n
 
 // ---- per-ray work counters of the traversal kernels (-DYRT_COUNTERS=1 builds only) --------------------------------
 // dctr = YRT_DCTR_WORDS words per kernel class (0 primary closest, 1 queue closest, 2 any): rays, node visits, box tests,
-// box tests in the instance tree, element tests, instance entries, then per WARP: beam walks, node visits of those walks,
-// candidates they produced, walks that fell back to the per-lane instance tree
-#define YRT_DCTR_WORDS 12
+// box tests in the instance tree, element tests, instance entries, warp-level node-loop trips x 32
+#define YRT_DCTR_WORDS 8
 #if YRT_COUNTERS
-#define YRT_CTR_DECL TraceCounters tc_ = {0, 0, 0, 0, 0, 0, 0, 0}; unsigned long long rays_ = 0, bw_ = 0, bv_ = 0, bc_ = 0, bf_ = 0
+#define YRT_CTR_DECL TraceCounters tc_ = {0, 0, 0, 0, 0, 0, 0, 0}; unsigned long long rays_ = 0
 #define YRT_CTR_PTR (&tc_)
-#define YRT_CTR_BEAM(n_c, visits) do { if ((threadIdx.x & 31) == 0) { if ((n_c) >= 0) { bw_++; bv_ += (visits); bc_ += (n_c); } else bf_++; } } while (0)
-__device__ __forceinline__ void flush_counters(unsigned long long* dctr, const TraceCounters& tc, unsigned long long rays, unsigned long long bw,
-                                               unsigned long long bv, unsigned long long bc, unsigned long long bf) {
-    unsigned long long v[10] = {rays, (unsigned long long)tc.node_visits, (unsigned long long)tc.box_tests, (unsigned long long)tc.tlas_box_tests,
-                                (unsigned long long)tc.prim_tests, (unsigned long long)tc.inst_entries, bw, bv, bc, bf};
-    for (int k = 0; k < 10; k++) {
+__device__ __forceinline__ void flush_counters(unsigned long long* dctr, const TraceCounters& tc, unsigned long long rays) {
+    unsigned long long v[6] = {rays, (unsigned long long)tc.node_visits, (unsigned long long)tc.box_tests, (unsigned long long)tc.tlas_box_tests,
+                               (unsigned long long)tc.prim_tests, (unsigned long long)tc.inst_entries};
+    for (int k = 0; k < 6; k++) {
         unsigned long long x = v[k];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if ((threadIdx.x & 31) == 0 && x) atomicAdd(dctr + k, x);
@@ -103,7 +93,6 @@ __device__ __forceinline__ void flush_counters(unsigned long long* dctr, const T
 #else
 #define YRT_CTR_DECL
 #define YRT_CTR_PTR ((TraceCounters*)nullptr)
-#define YRT_CTR_BEAM(n_c, visits) do { } while (0)
 #endif
 
 // ---- closest hit --------------------------------------------------------------------------
@@ -117,44 +106,28 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_close
     const int lane = threadIdx.x & 31;
     const unsigned n_items = item_count(wd);
     int stack[STACK_INTS_CLOSEST];
-    __shared__ BeamScratch s_beam[(PRIMARY && YRT_BEAM_CLOSEST) ? TRACE_THREADS / 32 : 1];
     YRT_CTR_DECL;
     for (;;) {
         unsigned idx = 0;
         bool alive = false;
         if (!warp_next(wd, n_items, lane, idx, alive)) break;
-        unsigned slot = 0;
-        ray3 ray;
-        ray.o = mk3(0.f, 0.f, 0.f); ray.d = mk3(0.f, 0.f, 1.f); ray.tmin = 0.f; ray.tmax = 0.f;
-        if (alive) {
-            if (PRIMARY) {
-                slot = idx;
-                int i, j, ii, jj;
-                slot_to_sample(bp, slot, i, j, ii, jj);
-                float u, v;
-                sample_uv(i, j, ii, jj, bp.samples, bp.width, bp.height, u, v);
-                ray = eval_camera(bp.cam, u, v);
-            } else {
-                slot = act ? (unsigned)act[idx] : idx;
-                float4 o = ray_o[slot], d = ray_d[slot];
-                ray.o = xyz(o); ray.d = xyz(d); ray.tmin = o.w; ray.tmax = d.w;
-            }
-        }
-        // camera rays: neighbouring samples form a beam — the warp walks the instance tree once (yrt_beam.cuh); mirror rays
-        // (and warps whose rays do not form a beam) walk it per lane
-        int n_cand = -1;
-        if (PRIMARY && YRT_BEAM_CLOSEST && sv.beam_levels > 0) {
-            int visits = 0;
-            BeamOrigins org;
-            org.lo = org.hi = bp.cam.frame.o;      // camera rays share their origin (raytrace.cpp:32)
-            n_cand = warp_beam_candidates<true>(sv, ray, make_slabray(ray.o, inv3_slab(ray.d)), org, __ballot_sync(0xffffffffu, alive), lane, s_beam[threadIdx.x >> 5],
-                                                YRT_COUNTERS ? &visits : nullptr);
-            YRT_CTR_BEAM(n_cand, visits);
-        }
         if (!alive) continue;
+        unsigned slot;
+        ray3 ray;
+        if (PRIMARY) {
+            slot = idx;
+            int i, j, ii, jj;
+            slot_to_sample(bp, slot, i, j, ii, jj);
+            float u, v;
+            sample_uv(i, j, ii, jj, bp.samples, bp.width, bp.height, u, v);
+            ray = eval_camera(bp.cam, u, v);
+        } else {
+            slot = act ? (unsigned)act[idx] : idx;
+            float4 o = ray_o[slot], d = ray_d[slot];
+            ray.o = xyz(o); ray.d = xyz(d); ray.tmin = o.w; ray.tmax = d.w;
+        }
         HitRec h;
-        if (n_cand >= 0) trace_ray_candidates<false>(sv, ray, h, stack, s_beam[threadIdx.x >> 5].cand, n_cand, YRT_CTR_PTR);
-        else trace_ray<false>(sv, ray, h, stack, YRT_CTR_PTR);
+        trace_ray<false>(sv, ray, h, stack, YRT_CTR_PTR);
 #if YRT_COUNTERS
         rays_++;
 #endif
@@ -168,7 +141,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_close
         P_out[slot] = P;
     }
 #if YRT_COUNTERS
-    if (dctr) flush_counters(dctr, tc_, rays_, bw_, bv_, bc_, bf_);
+    if (dctr) flush_counters(dctr, tc_, rays_);
 #else
     (void)dctr;
 #endif
@@ -184,27 +157,16 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS_ANY) k_trace_a
     const int lane = threadIdx.x & 31;
     const unsigned n_items = item_count(wd);
     int stack[STACK_INTS_ANY];
-    __shared__ BeamScratch s_beam[YRT_BEAM_ANY ? TRACE_THREADS / 32 : 1];
     YRT_CTR_DECL;
-    // the shadow rays of camera hits (act == null: slots in image order) towards one light form a beam like the camera
-    // rays; those of mirror-ray hits (compacted queue) are traced per lane
-    const bool beams = YRT_BEAM_ANY && act == nullptr && sv.beam_levels > 0;
     for (;;) {
         unsigned a = 0;
         bool alive = false;
         if (!warp_next(wd, n_items, lane, a, alive)) break;
-        unsigned slot = 0;
-        vec3 p = mk3(0.f, 0.f, 0.f);
-        if (alive) {
-            slot = act ? (unsigned)act[a] : a;
-            float4 h = hit[slot];
-            alive = float_as_int(h.x) >= 0;   // a miss casts no shadow rays: shade() returns before the light loop (raytrace.cpp:93)
-            if (alive) p = xyz(P[slot]);
-        }
-        const unsigned rays_mask = __ballot_sync(0xffffffffu, alive);
-        if (rays_mask == 0u) continue;
-        BeamOrigins org;
-        if (beams) org = warp_beam_origins(p, alive);      // the hit points: the same for every light
+        if (!alive) continue;
+        unsigned slot = act ? (unsigned)act[a] : a;
+        float4 h = hit[slot];
+        if (float_as_int(h.x) < 0) continue;   // a miss casts no shadow rays: shade() returns before the light loop (raytrace.cpp:93)
+        vec3 p = xyz(P[slot]);
         // visibility of the lights as bit masks: word w of a slot holds lights 32 w .. 32 w + 31 (one store per hit for up to 32 lights)
         unsigned vm = 0u;
         for (int k = 0; k < sv.n_lights; k++) {
@@ -212,30 +174,20 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS_ANY) k_trace_a
             float r;
             light_vector(sv, k, p, l, r, ke);
             ray3 sr = shadow_ray(p, l, r);
-            int n_cand = -1;
-            if (beams) {
-                int visits = 0;
-                n_cand = warp_beam_candidates<false>(sv, sr, make_slabray(sr.o, inv3_slab(sr.d)), org, rays_mask, lane, s_beam[threadIdx.x >> 5], YRT_COUNTERS ? &visits : nullptr);
-                YRT_CTR_BEAM(n_cand, visits);
-            }
-            if (alive) {
-                HitRec hr;
-                const bool occ = n_cand >= 0 ? trace_ray_candidates<true>(sv, sr, hr, stack, s_beam[threadIdx.x >> 5].cand, n_cand, YRT_CTR_PTR)
-                                             : trace_ray<true>(sv, sr, hr, stack, YRT_CTR_PTR);
+            HitRec hr;
+            bool occ = trace_ray<true>(sv, sr, hr, stack, YRT_CTR_PTR);
 #if YRT_COUNTERS
-                rays_++;
+            rays_++;
 #endif
-                if (!occ) vm |= 1u << (k & 31);
-                if ((k & 31) == 31 || k == sv.n_lights - 1) {
-                    vis[(size_t)(k >> 5) * cap_slots + slot] = vm;
-                    vm = 0u;
-                }
+            if (!occ) vm |= 1u << (k & 31);
+            if ((k & 31) == 31 || k == sv.n_lights - 1) {
+                vis[(size_t)(k >> 5) * cap_slots + slot] = vm;
+                vm = 0u;
             }
-            if (beams) __syncwarp();      // every lane has read the candidates before the next light's walk rewrites them
         }
     }
 #if YRT_COUNTERS
-    if (dctr) flush_counters(dctr, tc_, rays_, bw_, bv_, bc_, bf_);
+    if (dctr) flush_counters(dctr, tc_, rays_);
 #else
     (void)dctr;
 #endif
@@ -824,13 +776,13 @@ int collect_stats_device(DevScene& ds, const RenderParams& rp, yrt_stats* stats)
     return YRT_OK;
 }
 
-int read_counters_device(DevScene& ds, uint64_t out[36]) {
+int read_counters_device(DevScene& ds, uint64_t out[24]) {
 #if YRT_COUNTERS
     YRT_CUDA(cudaSetDevice(ds.device));
     YRT_CUDA(cudaDeviceSynchronize());
-    if (!ds.dctr.p) { memset(out, 0, sizeof(uint64_t) * 36); return YRT_OK; }
-    YRT_CUDA(cudaMemcpy(out, ds.dctr.p, sizeof(uint64_t) * 36, cudaMemcpyDeviceToHost));
-    YRT_CUDA(cudaMemset(ds.dctr.p, 0, sizeof(uint64_t) * 36));
+    if (!ds.dctr.p) { memset(out, 0, sizeof(uint64_t) * 24); return YRT_OK; }
+    YRT_CUDA(cudaMemcpy(out, ds.dctr.p, sizeof(uint64_t) * 24, cudaMemcpyDeviceToHost));
+    YRT_CUDA(cudaMemset(ds.dctr.p, 0, sizeof(uint64_t) * 24));
     return YRT_OK;
 #else
     (void)ds; (void)out;

@@ -191,11 +191,6 @@ struct SceneView {
     int tlas_root;              // ref
     int n_lights;
     int n_active_instances;
-    // the instance tree as up-to-32-wide levels for the warp-level beam walk (yrt_beam.cuh): (lo, hi) pairs of the instance
-    // slots, then of the groups of every level; and the (c, h') pair of every instance slot that the lanes test themselves
-    const float4* beam_boxes;
-    const float4* tlas_ch;
-    int beam_levels;            // group levels (0: no beam walk)
 };
 
 // trace record (3 float4) + the vertex positions shading needs, for one element in BLAS leaf order.

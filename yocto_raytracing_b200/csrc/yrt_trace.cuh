@@ -143,22 +143,6 @@ struct Tracer {
     static constexpr int ENTRY = CULL ? 2 : 1;
     YRT_HD float accept_limit() const { return EXACT ? tmax * 1.00000024f : fmaf(tmax, YRT_SLAB_ACCEPT, sr.pad); }
 
-    // Start from a list of candidate instance slots (the warp's beam walk, yrt_beam.cuh) instead of the root of the instance
-    // tree: the lane applies its own slab test to each candidate's box — the test it would have met at that instance's leaf —
-    // and pushes the instances it enters; cand is in descending beam entry order, so the nearest ends up on top.
-    YRT_HD void begin_candidates(const SceneView& sv, const ray3& wray, int* stack, const int* cand, int n_cand, TraceCounters* ctr) {
-        begin(sv, wray, stack);
-        for (int k = 0; k < n_cand; k++) {
-            const int slot = cand[k];
-            const float4* ch = sv.tlas_ch + 2 * (size_t)slot;
-            const float4 c = ld4(ch), h = ld4(ch + 1);
-            float e;
-            if (slab_test_ch(sr, tmin, tmax, c.x, c.y, c.z, h.x, h.y, h.z, e)) push(make_leaf_ref(slot, 1), e);
-        }
-        if (ctr) { ctr->box_tests += n_cand; ctr->tlas_box_tests += n_cand; if (depth_of(stack) > ctr->max_stack) ctr->max_stack = depth_of(stack); }
-        pop();
-    }
-
     // pop the next reference.  Leaving an instance (sentinel) restores the world-space slab operands and pops on: only
     // one sentinel is ever on the stack (instances are entered from the top level only), and the guard below everything
     // (YRT_REF_DONE, entry distance -inf like the sentinel's) ends the traversal without an emptiness test.  At the top
@@ -367,20 +351,6 @@ YRT_HD bool trace_ray_impl(const SceneView& sv, const ray3& wray, HitRec& hit, i
     t.begin(sv, wray, stack);
     for (;;) {
         t.nodes(sv, stack, ctr);
-        if (t.done()) break;
-        t.leaf(sv, stack, ctr);
-    }
-    hit = t.hit;
-    return t.found;
-}
-
-// a ray of a beam (never one of the reference-formula rays): per-lane part after the warp's beam walk
-template <bool ANY>
-YRT_HD bool trace_ray_candidates(const SceneView& sv, const ray3& wray, HitRec& hit, int* stack, const int* cand, int n_cand, TraceCounters* ctr) {
-    Tracer<ANY, false> t;
-    t.begin_candidates(sv, wray, stack, cand, n_cand, ctr);
-    while (!t.done()) {
-        if (t.cur >= 0) t.nodes(sv, stack, ctr);
         if (t.done()) break;
         t.leaf(sv, stack, ctr);
     }

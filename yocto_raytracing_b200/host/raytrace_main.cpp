@@ -5,7 +5,7 @@
 // (src/ext/yocto_utils.h:1085+).  Same flags, same four progress lines; additive flags only:
 //   --gpus N       interleaved row tiles over N GPUs
 //   --cache        keep the flattened scene next to the OBJ (<scene>.yrts) and reuse it while it is not older than
-//                  the scene file or any material / texture / buffer file next to it: skips load_scene (SURVEY 8f.2 — the OBJ parse costs more than a frame)
+//                  the scene file, any material library / buffer file next to it or any texture it uses: skips load_scene (SURVEY 8f.2 — the OBJ parse costs more than a frame)
 //   --device-ldr   tonemap on the GPU (yrt_render_ldr): a quarter of the bytes cross to the host and
 //                  the host tonemap (src/image.cpp:55-78) is skipped; ignored for .hdr outputs
 //   --fast-png     8-bit PNG outputs are written by yrt_write_png (parallel deflate) instead of stb_image_write: same pixels,
@@ -28,19 +28,20 @@
 namespace {
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-// The cache is valid if it exists and is not older than the scene file NOR than anything the scene may refer to: the loader
-// resolves mtllib / map_* / glTF buffer and image URIs relative to the scene's directory, so every scene-like, material,
-// texture or buffer file next to the scene counts as a dependency (a superset: a needless re-parse is cheap, a stale
-// render is not).
+// The cache is valid if it exists and is not older than the scene file, nor than any material library / buffer file next
+// to it (the loader resolves mtllib and glTF buffer URIs relative to the scene's directory; which of them a scene uses is
+// only known after parsing, so all count), nor — checked after loading it — than any texture file it lists.
+std::string dir_of(const std::string& path) {
+    auto slash = path.find_last_of('/');
+    return slash == std::string::npos ? std::string(".") : path.substr(0, slash);
+}
 bool cache_is_fresh(const std::string& scene_path, const std::string& cache_path) {
     struct stat a, b;
     if (stat(scene_path.c_str(), &a) != 0 || stat(cache_path.c_str(), &b) != 0) return false;
     if (b.st_mtime < a.st_mtime) return false;
-    auto slash = scene_path.find_last_of('/');
-    std::string dir = slash == std::string::npos ? "." : scene_path.substr(0, slash);
+    const std::string dir = dir_of(scene_path);
     DIR* d = opendir(dir.c_str());
     if (!d) return true;
-    static const char* exts[] = {".obj", ".mtl", ".gltf", ".glb", ".bin", ".png", ".jpg", ".jpeg", ".tga", ".bmp", ".hdr", ".ppm", ".pfm"};
     bool fresh = true;
     while (dirent* e = readdir(d)) {
         std::string name = e->d_name;
@@ -48,13 +49,19 @@ bool cache_is_fresh(const std::string& scene_path, const std::string& cache_path
         if (dot == std::string::npos) continue;
         std::string ext = name.substr(dot);
         for (auto& c : ext) c = (char)tolower(c);
-        bool dep = false;
-        for (const char* x : exts) dep = dep || ext == x;
         struct stat s;
-        if (dep && stat((dir + "/" + name).c_str(), &s) == 0 && S_ISREG(s.st_mode) && s.st_mtime > b.st_mtime) { fresh = false; break; }
+        if ((ext == ".mtl" || ext == ".bin") && stat((dir + "/" + name).c_str(), &s) == 0 && S_ISREG(s.st_mode) && s.st_mtime > b.st_mtime) { fresh = false; break; }
     }
     closedir(d);
     return fresh;
+}
+bool textures_older_than_cache(const yrt_flat_scene& flat, const std::string& scene_path, const std::string& cache_path) {
+    struct stat b, s;
+    if (stat(cache_path.c_str(), &b) != 0) return false;
+    const std::string dir = dir_of(scene_path);
+    for (const auto& f : flat.tex_files)
+        if (stat((dir + "/" + f).c_str(), &s) != 0 || s.st_mtime > b.st_mtime) return false;
+    return true;
 }
 }  // namespace
 
@@ -83,6 +90,7 @@ int main(int argc, char** argv) {
     if (use_cache && cache_is_fresh(scenein, cache_path)) {
         from_cache = yrt_flat_load(cache_path, flat, err);
         if (!from_cache) printf("ignoring scene cache: %s\n", err.c_str());
+        else if (!textures_older_than_cache(flat, scenein, cache_path)) from_cache = false;   // a texture changed since
     }
     double t_loaded = now_ms(), t_flat = t_loaded;
     if (!from_cache) {

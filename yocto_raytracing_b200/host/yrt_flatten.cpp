@@ -68,6 +68,7 @@ bool yrt_flatten(const scene* scn, yrt_flat_scene& out, std::string& err) {
         int id = (int)tex_id.size();
         tex_id[txt] = id;
         // eval_texture only ever reads texture::ldr (src/raytrace.cpp:43); an .hdr texture leaves it 0x0
+        out.tex_files.push_back(txt->filename);
         out.tex_w.push_back(txt->ldr.width);
         out.tex_h.push_back(txt->ldr.height);
         out.tex_off.push_back((int64_t)out.tex_rgba8.size());
@@ -187,6 +188,11 @@ bool yrt_flat_save(const yrt_flat_scene& fs, const std::string& path, std::strin
     cam.push_back(fs.cam.fovy); cam.push_back(fs.cam.aspect); cam.push_back(fs.cam.aperture); cam.push_back(fs.cam.focus);
     // camera rides as a 27th array; the count in the header is patched below
     w.f32("camera", cam);
+    {   // file names of the textures, one per line: what the cache depends on besides the scene file itself
+        std::string names;
+        for (const auto& n : fs.tex_files) names += n + "\n";
+        w.arr("tex_files", 2, names.data(), (int64_t)names.size(), 1);
+    }
     fseek(f, 8, SEEK_SET);
     int32_t n = w.n;
     fwrite(&n, 4, 1, f);
@@ -205,6 +211,7 @@ bool yrt_flat_load(const std::string& path, yrt_flat_scene& fs, std::string& err
     if (!ok) { fclose(f); err = path + ": not a YRTSCN01 file"; return false; }
     fs = yrt_flat_scene();
     std::vector<float> cam;
+    std::string tex_names;
     // no count may promise more bytes than the file still holds (a corrupt cache must not cause a huge allocation)
     long file_size = 0;
     {
@@ -238,12 +245,19 @@ bool yrt_flat_load(const std::string& path, yrt_flat_scene& fs, std::string& err
         if (want("tex_off", 3)) { fs.tex_off.resize((size_t)count); dst = fs.tex_off.data(); }
         if (want("tex_rgba8", 2)) { fs.tex_rgba8.resize((size_t)count); dst = fs.tex_rgba8.data(); }
         if (want("camera", 1)) { cam.resize((size_t)count); dst = cam.data(); }
+        if (want("tex_files", 2)) { tex_names.resize((size_t)count); dst = &tex_names[0]; }
         if (dst) ok = bytes == 0 || fread(dst, 1, bytes, f) == bytes;
         else ok = fseek(f, (long)bytes, SEEK_CUR) == 0;   // unknown array: skip
         if (ok && bytes % 8) ok = fseek(f, (long)(8 - bytes % 8), SEEK_CUR) == 0;
     }
     fclose(f);
     if (!ok) { err = path + ": truncated or malformed"; return false; }
+    for (size_t a0 = 0; a0 < tex_names.size();) {
+        size_t e = tex_names.find('\n', a0);
+        if (e == std::string::npos) e = tex_names.size();
+        fs.tex_files.push_back(tex_names.substr(a0, e - a0));
+        a0 = e + 1;
+    }
     if (cam.size() == 16) {
         memcpy(fs.cam.frame, cam.data(), 12 * sizeof(float));
         fs.cam.fovy = cam[12]; fs.cam.aspect = cam[13]; fs.cam.aperture = cam[14]; fs.cam.focus = cam[15];

@@ -26,6 +26,7 @@ struct yrt_flat_scene {
     std::vector<int32_t> tex_w, tex_h;
     std::vector<int64_t> tex_off;
     std::vector<uint8_t> tex_rgba8;
+    std::vector<std::string> tex_files;   // texture::filename of every texture (relative to the scene's directory): the cache's dependencies
     yrt_camera cam;          // scn->cameras.front() (src/raytrace.cpp:215)
     bool has_camera = false;
 
