@@ -371,7 +371,7 @@ def run_b200(args):
         if ok.item() == 0:
             host_frame = None
         if host_frame is not None:
-            e2e_api = "distributed.SharedHostFrame.render: yrt_render_rows_to_host on every rank into one shared page-locked host frame (one pitched D2H copy per rank, one barrier)"
+            e2e_api = "distributed.SharedHostFrame.render: yrt_render_rows_to_host on every rank into one shared page-locked host frame (pitched D2H copies per rank under the next batch's kernels, two alternating buffers, one shared-memory barrier per frame)"
         else:
             pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
             e2e_api = "device-resident gather + D2H on rank 0"

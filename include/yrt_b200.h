@@ -225,6 +225,11 @@ int yrt_frame_free(void* d_full);
 int yrt_frame_export(void* d_full, unsigned char handle[64]);
 int yrt_frame_import(const unsigned char handle[64], void** d_full);
 int yrt_frame_release(void* d_full);
+/* Barrier between the processes of one node through a counter in memory they share (8 bytes, zero-initialised, e.g. the tail of
+ * the shared host frame): adds one arrival and returns when world * generation arrivals have been counted; generation =
+ * 1, 2, 3, ... (the counter only grows).  Microseconds instead of a collective launch + stream wait per frame.  Host only. */
+int yrt_host_barrier(void* counter, int world, int64_t generation);
+
 /* deferred statistics for yrt_render_rows*: frames rendered between begin and end record per-launch CUDA events
  * and ray counters without waiting for the device; yrt_stats_end waits for it and returns the totals over those
  * frames (stats->frames says how many).  (Scenes with mirrors: the host waits, one wave behind the device, for the

@@ -200,3 +200,50 @@ def test_scene_cache_loader_rejects_corrupt_counts(tmp_path):
     open(bad, "wb").write(b)
     r = subprocess.run([tool, "--check", bad], capture_output=True, text=True, timeout=30)
     assert r.returncode != 0 and "malformed" in r.stderr
+
+
+_BARRIER_WORKER = r"""
+import ctypes as C, sys
+from multiprocessing import shared_memory
+sys.path.insert(0, sys.argv[1])
+from yocto_raytracing_b200 import _lib
+import numpy as np
+rank, world, name = int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+shm = shared_memory.SharedMemory(name=name)
+try:                                       # (Python < 3.13 registers attached segments for unlinking at exit: the owner unlinks)
+    from multiprocessing import resource_tracker
+    resource_tracker.unregister(shm._name, "shared_memory")
+except Exception:
+    pass
+ctr = np.ndarray((8,), np.int64, buffer=shm.buf)
+data = np.ndarray((world,), np.int64, buffer=shm.buf, offset=64)
+lib = _lib.load()
+bad = 0
+for gen in range(1, 301):
+    data[rank] = gen                       # "my rows of frame gen have landed"
+    assert lib.yrt_host_barrier(ctr.ctypes.data, world, gen) == 0
+    if (data[:world] < gen).any():         # after the barrier every rank's write of this generation is visible
+        bad += 1
+    assert lib.yrt_host_barrier(ctr[1:].ctypes.data, world, gen) == 0     # second counter: nobody runs ahead into gen + 1 while we check
+print("BARRIER_OK" if bad == 0 else f"BARRIER_BAD {bad}")
+del ctr, data
+shm.close()
+"""
+
+
+def test_host_barrier_orders_processes(tmp_path):
+    """yrt_host_barrier (the per-frame barrier of distributed.SharedHostFrame): three processes, 300 generations, a counter in
+    POSIX shared memory — after the barrier of generation g every process sees every other process's writes of g."""
+    from multiprocessing import shared_memory
+    shm = shared_memory.SharedMemory(create=True, size=256)
+    try:
+        shm.buf[:256] = bytes(256)
+        script = tmp_path / "w.py"
+        script.write_text(_BARRIER_WORKER)
+        procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), "3", shm.name], stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(3)]
+        outs = [p.communicate(timeout=120)[0].decode() for p in procs]
+        assert all(p.returncode == 0 for p in procs), outs
+        assert all("BARRIER_OK" in o for o in outs), outs
+    finally:
+        shm.close()
+        shm.unlink()

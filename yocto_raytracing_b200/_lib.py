@@ -86,6 +86,7 @@ SYMBOLS = {
                                           C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
     "yrt_render_rows_into_frame": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
+    "yrt_host_barrier": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "yrt_frame_alloc": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "yrt_frame_free": (C.c_int, [C.c_void_p]),
     "yrt_frame_export": (C.c_int, [C.c_void_p, C.c_char_p]),

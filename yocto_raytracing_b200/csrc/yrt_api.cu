@@ -225,6 +225,16 @@ int yrt_render_rows_into_frame(yrt_scene* scn, const yrt_camera* cam, const floa
     return render_rows_device(*scn->dev[0], rp, (float4*)d_full, (cudaStream_t)stream, stats, true);
 }
 
+int yrt_host_barrier(void* counter, int world, int64_t generation) {
+    if (!counter || world <= 0 || generation <= 0) { set_error("yrt_host_barrier: bad arguments"); return YRT_ERR_INVALID; }
+    volatile int64_t* c = (volatile int64_t*)counter;
+    __atomic_fetch_add((int64_t*)counter, (int64_t)1, __ATOMIC_ACQ_REL);
+    const int64_t target = (int64_t)world * generation;
+    for (unsigned spins = 0; __atomic_load_n((int64_t*)c, __ATOMIC_ACQUIRE) < target; spins++)
+        if (spins > 2000) std::this_thread::yield();
+    return YRT_OK;
+}
+
 int yrt_frame_alloc(int width, int height, void** d_full) {
     if (!d_full || width <= 0 || height <= 0) { set_error("yrt_frame_alloc: bad arguments"); return YRT_ERR_INVALID; }
     YRT_TRY(ensure_init());

@@ -302,7 +302,10 @@ __device__ __forceinline__ void shade_epilogue(const ShadeBuffers& sb, int depth
 }
 
 // one thread per active sample; n_act_dev (if not null) holds the number of active samples of this wave
-__global__ void __launch_bounds__(256, 4) k_shade(SceneView sv, BatchParams bp, ShadeBuffers sb, int depth, int max_depth,
+#ifndef SHADE_MIN_BLOCKS
+#define SHADE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, SHADE_MIN_BLOCKS) k_shade(SceneView sv, BatchParams bp, ShadeBuffers sb, int depth, int max_depth,
                                                   const int* __restrict__ act, unsigned n_act, const unsigned* __restrict__ n_act_dev,
                                                   const unsigned* __restrict__ vis) {
     if (n_act_dev) n_act = min(n_act, *n_act_dev);

@@ -161,53 +161,69 @@ class SharedFrame:
 
 class SharedHostFrame:
     """The full framebuffer in HOST memory shared by all ranks of the node (POSIX shared memory, page-locked by every rank):
-    each rank renders its interleaved rows and copies them itself into their final positions — one pitched device->host
-    copy per rank over that GPU's own PCIe link, all ranks at once — so the frame reaches the host N times faster than
-    through rank 0's single link, and the GPUs exchange nothing.  The per-frame synchronisation is one barrier: after it,
-    every rank's rows are in the frame.  A second barrier at the start of the next frame keeps ranks from overwriting rows
-    the consumer (rank 0) is still reading."""
+    each rank renders its interleaved rows and copies them itself into their final positions — pitched device->host copies
+    per rank over that GPU's own PCIe link, all ranks at once — so the frame reaches the host N times faster than through
+    rank 0's single link, and the GPUs exchange nothing.
+
+    Frames alternate between TWO buffers and every frame ends with one barrier (a counter in the same shared memory,
+    yrt_host_barrier: microseconds, no collective).  That orders everything: render(k) returns on every rank after all rows
+    of frame k have landed; the consumer (rank 0) reads frame k and then calls render(k+1); a rank can only write into frame
+    k's buffer again in render(k+2), i.e. after the barrier of frame k+1, which rank 0 joins after it is done with frame k."""
 
     def __init__(self, width: int, height: int, group=None):
         from multiprocessing import shared_memory
         self.width, self.height, self.group = width, height, group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        nbytes = width * height * 16
+        self._fbytes = width * height * 16
+        nbytes = 2 * self._fbytes + 64
         name = [None]
         if self.rank == 0:
             self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            self._shm.buf[2 * self._fbytes: 2 * self._fbytes + 64] = bytes(64)      # the barrier counter starts at zero
             name[0] = self._shm.name
         if self.world > 1:
             dist.broadcast_object_list(name, src=0, group=group)
             if self.rank != 0:
                 self._shm = shared_memory.SharedMemory(name=name[0])
-        self.array = np.ndarray((height, width, 4), np.float32, buffer=self._shm.buf)
-        self._ptr = self.array.ctypes.data
+                try:      # Python < 3.13 registers attached segments for unlinking at process exit; only the owner (rank 0) unlinks
+                    from multiprocessing import resource_tracker
+                    resource_tracker.unregister(self._shm._name, "shared_memory")
+                except Exception:
+                    pass
+        self._frames_np = [np.ndarray((height, width, 4), np.float32, buffer=self._shm.buf, offset=k * self._fbytes) for k in range(2)]
+        self._ctr = np.ndarray((8,), np.int64, buffer=self._shm.buf, offset=2 * self._fbytes)
+        self._base = self._frames_np[0].ctypes.data
         self._pinned = False
         if torch.cuda.is_available():
-            rc = torch.cuda.cudart().cudaHostRegister(self._ptr, nbytes, 1)   # cudaHostRegisterPortable
+            rc = torch.cuda.cudart().cudaHostRegister(self._base, 2 * self._fbytes, 1)   # cudaHostRegisterPortable
             self._pinned = int(rc) == 0
-        self._token = torch.zeros(1, device=torch.device("cuda", torch.cuda.current_device())) if torch.cuda.is_available() else None
         self._frames = 0
+        self.array = self._frames_np[0]
+        if self.world > 1:
+            dist.barrier(group=group)     # every rank has mapped (and page-locked) the memory before the first frame
 
     def render(self, scene, samples: int, amb=0.1, tile_rows: int = 1, want_stats: bool = False):
-        """Render this rank's rows into the shared host frame; returns after every rank's rows of this frame have landed."""
+        """Render this rank's rows into the current buffer; returns after every rank's rows of this frame have landed.
+        self.array is the frame (valid until the next-but-one render call)."""
         dev = torch.device("cuda", torch.cuda.current_device())
         st = torch.cuda.current_stream(dev).cuda_stream
-        if self.world > 1 and self._frames > 0:
-            dist.barrier(group=self.group)        # the consumer is done with the previous frame (it called render again)
-        stats = scene.render_rows_to_host(self._ptr, self.width, self.height, samples, amb, tile_rows, self.rank, self.world, st, want_stats)
+        buf = self._frames_np[self._frames % 2]
+        stats = scene.render_rows_to_host(buf.ctypes.data, self.width, self.height, samples, amb, tile_rows, self.rank, self.world, st, want_stats)
         torch.cuda.current_stream(dev).synchronize()
-        if self.world > 1:
-            dist.barrier(group=self.group)        # every rank's copies have completed
         self._frames += 1
+        if self.world > 1:
+            check(_lib.load().yrt_host_barrier(self._ctr.ctypes.data, self.world, self._frames))
+        self.array = buf
         return stats
 
     def close(self):
         try:
             if self._pinned:
-                torch.cuda.cudart().cudaHostUnregister(self._ptr)
+                torch.cuda.cudart().cudaHostUnregister(self._base)
             self.array = None
+            self._frames_np = None
+            self._ctr = None
             self._shm.close()
             if self.rank == 0:
                 self._shm.unlink()
