@@ -115,7 +115,7 @@ typedef struct yrt_stats {
     int32_t n_closest, n_any, n_shade, n_other;   /* launches per category (device 0)          */
     int32_t frames;           /* frames the totals cover (1, or all frames between yrt_stats_begin/end) */
     int32_t reserved;
-    int64_t truncated_paths;  /* mirror bounces dropped at the recursion cap (YRT_MAX_DEPTH, default 16); the
+    int64_t truncated_paths;  /* mirror bounces dropped at the recursion cap (YRT_MAX_DEPTH, default 64); the
                                  reference recurses without a bound (src/raytrace.cpp:190-204) — 0 means the
                                  frame is what unbounded recursion gives                                      */
 } yrt_stats;

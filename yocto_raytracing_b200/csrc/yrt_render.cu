@@ -452,7 +452,7 @@ struct PhaseTimer {
 enum { CAT_CLOSEST = 0, CAT_ANY = 1, CAT_SHADE = 2, CAT_OTHER = 3, CAT_FRAME = 4 };
 
 static int batch_rows_for(const RenderParams& rp, int n_lights, int own_rows, bool reflective);
-#define YRT_MAX_WAVES 64                                   /* upper limit of the reflection depth cap (YRT_MAX_DEPTH) */
+#define YRT_MAX_WAVES 64                                   /* the reflection depth cap: default and upper limit of YRT_MAX_DEPTH (the reference recurses without a bound; a mirror chain of 64 bounces carries kr^64 of its light) */
 #define STATS_WAVE_COUNTS_OFFSET 64                          /* bytes: FrameCounters, then one active-sample count per wave */
 #define STATS_BYTES (STATS_WAVE_COUNTS_OFFSET + sizeof(unsigned) * (YRT_MAX_WAVES + 2))
 
@@ -511,7 +511,7 @@ int presize_workspace_device(DevScene& ds, int width, int height, int samples) {
     RenderParams rp;
     rp.width = width; rp.height = height; rp.samples = samples; rp.tile_rows = std::max(height, 1); rp.rank = 0; rp.world = 1;
     YRT_CUDA(cudaSetDevice(ds.device));
-    int depth_cap = std::min(YRT_MAX_WAVES, std::max(1, env_int("YRT_MAX_DEPTH", 16)));
+    int depth_cap = std::min(YRT_MAX_WAVES, std::max(1, env_int("YRT_MAX_DEPTH", YRT_MAX_WAVES)));
     size_t cap_slots = (size_t)batch_rows_for(rp, ds.view.n_lights, height, ds.has_reflective) * width * samples * samples;
     return ensure_workspace(ds, ds.ws, cap_slots, ds.view.n_lights, depth_cap, ds.has_reflective);
 }
@@ -682,7 +682,7 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
     int spp = rp.samples * rp.samples;
     int nl = ds.view.n_lights;
     bool reflective = ds.has_reflective;
-    int depth_cap = std::min(YRT_MAX_WAVES, std::max(1, env_int("YRT_MAX_DEPTH", 16)));
+    int depth_cap = std::min(YRT_MAX_WAVES, std::max(1, env_int("YRT_MAX_DEPTH", YRT_MAX_WAVES)));
     int batch_rows = batch_rows_for(rp, nl, own, reflective);
     // two pipelines: the rank's rows are cut into (at least) two batches that run on two streams, so the ramp-up of one
     // batch's kernel fills the tail of the other's (each persistent kernel ends with ~one 32-ray task of idle SMs).

@@ -170,7 +170,7 @@ int main(int argc, char** argv) {
     double t_saved = now_ms();
 
     if (verbose && st.truncated_paths > 0)
-        printf("note: %lld mirror bounce(s) were cut at the recursion cap of this path (YRT_MAX_DEPTH, default 16); the reference recurses without a bound\n",
+        printf("note: %lld mirror bounce(s) were cut at the recursion cap of this path (YRT_MAX_DEPTH, default 64); the reference recurses without a bound\n",
                (long long)st.truncated_paths);
     if (verbose) {
         long long rays = (long long)(st.primary_rays + st.reflection_rays + st.shadow_rays);
