@@ -94,3 +94,12 @@ class EmuScene:
                 self._lib.emu_scene_destroy(self.h)
         except Exception:
             pass
+
+
+def set_grids(scene, light_R=0, cam_shift=-1):
+    """Apex grids of the emulation on / off (csrc/yrt_pgrid.cuh): light_R > 0 = cube grids of light_R x light_R cells per face
+    around the point lights, cam_shift >= 0 = a camera grid of 2^cam_shift-pixel cells per trace_primary / render call.
+    Returns (light-grid list entries, cells not served, lights with a grid, chain nodes)."""
+    st = (C.c_int64 * 4)()
+    assert scene._lib.emu_set_grids(scene.h, light_R, cam_shift, st) == 0
+    return st[0], st[1], st[2], st[3]

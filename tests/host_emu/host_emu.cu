@@ -88,8 +88,55 @@ void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi
     }
 }
 
+// one apex grid built by serial loops over the item functions of yrt_pgrid.cuh (the device runs the same functions per thread)
+struct EmuGrid {
+    PGridDesc d;
+    std::vector<int> roots;
+    long long n_entries = 0, n_fallback_cells = 0, n_nodes = 0;
+    GridRef ref() const {
+        GridRef g = gridref_none();
+        if (d.mode != 0) { g.roots = roots.data(); g.nx = d.nx; g.shift = 0; }
+        return g;
+    }
+};
+
+// chain nodes go to records [node_first, node_first + node_cap) of `nodes` (arity W); *node_total counts them (shared by the lights)
+void emu_build_grid(const PGridDesc& d, const std::vector<float4>& inst_box, int n_inst, int arity, float4* nodes, int node_first, int node_cap,
+                    int* node_total, int tlas_root, EmuGrid& out) {
+    out.d = d;
+    out.roots.assign(std::max(d.n_cells, 1), tlas_root);
+    out.n_entries = out.n_fallback_cells = out.n_nodes = 0;
+    if (d.mode == 0) return;
+    std::vector<int> cnt((size_t)d.n_cells + 2 + n_inst, 0);
+    std::vector<int2> cells(std::max(d.n_cells, 1), int2{0, 0});
+    std::vector<unsigned long long> keys(std::max(d.capacity, 1));
+    PGridArrays a;
+    a.d = d; a.inst_box = inst_box.data(); a.n_inst = n_inst;
+    a.cnt = cnt.data(); a.total = a.cnt + d.n_cells; a.big = a.cnt + d.n_cells + 1;
+    a.cells = cells.data(); a.keys = keys.data(); a.roots = out.roots.data();
+    a.nodes = nodes; a.arity = arity; a.node_first = node_first; a.node_capacity = node_cap; a.node_total = node_total;
+    a.tlas_root = tlas_root; a.tlas_root_dev = nullptr;
+    const int before = *node_total;
+    for (int fill = 0; fill < 2; fill++) {
+        for (int k = 0; k < n_inst; k++) pgrid_scatter_item(a, k, 0, 1, fill != 0, false);
+        for (int b = 0; b < a.big[0]; b++) pgrid_scatter_item(a, a.big[1 + b], 0, 1, fill != 0, true);
+        if (!fill) for (int c = 0; c < d.n_cells; c++) pgrid_alloc_item(a, c);
+    }
+    for (int c = 0; c < d.n_cells; c++) pgrid_emit_item(a, c);
+    out.n_entries = *a.total;
+    out.n_nodes = *node_total - before;
+    for (int c = 0; c < d.n_cells; c++) out.n_fallback_cells += cells[c].y < 0 || (cells[c].y > 0 && out.roots[c] == tlas_root);
+}
+
 struct EmuScene {
     HostScene hs;
+    std::vector<float4> inst_box;
+    std::vector<EmuGrid> light_grids;     // one per light (mode 0: none)
+    LightGrids lg;
+    int cam_shift = -1;                   // >= 0: trace_primary / render build a camera grid per call
+    float extent = 0.f;
+    int tree_nodes = 0;                   // records of the two trees in either node array; the grids' chain nodes follow
+    int light_node_cap = 0, cam_node_first = 0, cam_node_cap = 0;
     EmuLbvh blas, tlas;
     std::vector<float4> prim_recs, prim_attrs, inst_recs;
     std::vector<int> prim_rank, inst_rank;
@@ -184,6 +231,17 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
         r[2] = mk4(fr[6], fr[7], fr[8], int_as_float(hs.inst_mat[inst]));
         r[3] = mk4(fr[9], fr[10], fr[11], int_as_float((int)((unsigned)s | ((unsigned)hs.shape_kind[s] << 28))));
     }
+    es.inst_box.assign(2 * (size_t)std::max(na, 1), mk4(0, 0, 0, 0));
+    for (int k = 0; k < na; k++) {   // mirrors k_inst_box
+        const float4 l = ilo[es.tlas.order[k]], h = ihi[es.tlas.order[k]];
+        float cx, cy, cz, hx, hy, hz;
+        box_center_half(l.x, h.x, cx, hx); box_center_half(l.y, h.y, cy, hy); box_center_half(l.z, h.z, cz, hz);
+        es.inst_box[2 * (size_t)k] = mk4(cx, cy, cz, 0.f);
+        es.inst_box[2 * (size_t)k + 1] = mk4(hx, hy, hz, 0.f);
+    }
+    es.extent = hs.extent;
+    es.tree_nodes = nb_int + (na > 1 ? na - 1 : 1) + 2;
+    for (int k = 0; k < YRT_MAX_LIGHT_GRIDS; k++) es.lg.g[k] = gridref_none();
     es.blas_depth = es.blas.seg_depth.empty() ? 0 : *std::max_element(es.blas.seg_depth.begin(), es.blas.seg_depth.end());
     es.tlas_depth = es.tlas.seg_depth[0];
     {
@@ -193,7 +251,7 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
     }
     if (es.stack_need > YRT_STACK_CAP) { set_error("emu: tree too deep"); return YRT_ERR_UNSUPPORTED; }
     SceneView& v = es.view;
-    v.nodes2 = es.nodes2.data(); v.nodes4 = es.nodes4.data(); v.inst_recs = es.inst_recs.data();
+    v.nodes2 = es.nodes2.data(); v.nodes4 = es.nodes4.data(); v.inst_recs = es.inst_recs.data(); v.inst_box = es.inst_box.data();
     v.prim_recs = es.prim_recs.data(); v.prim_attrs = es.prim_attrs.data(); v.mat_recs = hs.mat_recs.data();
     v.light_recs = hs.light_recs.data(); v.tex_rgba8 = hs.tex_rgba8.data(); v.tex_info = hs.tex_info.data();
     v.inst_rank = es.inst_rank.data(); v.prim_rank = es.prim_rank.data();
@@ -209,11 +267,78 @@ void hit_to_ids(const SceneView& sv, const HitRec& h, int* ids) {
     ids[2] = float_as_int(sv.prim_recs[3 * (size_t)h.prim].w);
 }
 
+camera_k emu_camera(const yrt_camera* cam) {
+    camera_k ck;
+    const float* f = cam->frame;
+    ck.frame.x = mk3(f[0], f[1], f[2]); ck.frame.y = mk3(f[3], f[4], f[5]); ck.frame.z = mk3(f[6], f[7], f[8]); ck.frame.o = mk3(f[9], f[10], f[11]);
+    ck.h = 2.0f * cam->focus * tanf(cam->fovy / 2.0f); ck.w = ck.h * cam->aspect; ck.focus = cam->focus;
+    return ck;
+}
+
+// the camera grid of one call (mirrors camera_grid_enqueue in yrt_build.cu)
+void emu_camera_grid(EmuScene& es, const camera_k& ck, int width, int height, EmuGrid& g) {
+    g.d.mode = 0;
+    if (es.cam_shift < 0 || !es.hs.all_rigid || es.view.n_active_instances <= 0 || es.cam_node_cap <= 0) return;
+    const float reach = es.extent + fmaxf(fmaxf(fabsf(ck.frame.o.x), fabsf(ck.frame.o.y)), fabsf(ck.frame.o.z));
+    const long long cells = (long long)((width + (1 << es.cam_shift) - 1) >> es.cam_shift) * ((height + (1 << es.cam_shift) - 1) >> es.cam_shift);
+    PGridDesc d = pgrid_camera_desc(ck, width, height, es.cam_shift, reach, (int)(16 * cells + 65536));
+    int total = 0;
+    std::vector<float4>& arr = YRT_WIDE_CLOSEST == 4 ? es.nodes4 : es.nodes2;
+    emu_build_grid(d, es.inst_box, es.view.n_active_instances, YRT_WIDE_CLOSEST, arr.data(), es.cam_node_first, es.cam_node_cap, &total, es.view.tlas_root, g);
+}
+GridRef emu_camera_ref(const EmuScene& es, const EmuGrid& g) {
+    GridRef r = g.ref();
+    r.shift = es.cam_shift;
+    return r;
+}
+
 }  // namespace
 
 extern "C" {
 
 const char* emu_last_error(void) { return get_error(); }
+
+// apex grids on / off: light_R > 0 builds one cube grid per point light whose frame does not rotate (like build_device_scene),
+// cam_shift >= 0 makes trace_primary / render build a camera grid per call (cells of 2^shift pixels).  stats (optional, 4
+// int64): light-grid entries, light-grid cells that fall back to the tree, lights with a grid, 0
+int emu_set_grids(void* p, int light_R, int cam_shift, int64_t* stats) {
+    EmuScene* es = (EmuScene*)p;
+    es->cam_shift = cam_shift;
+    es->light_grids.clear();
+    long long ne = 0, nf = 0, nl = 0, nn = 0;
+    for (int k = 0; k < YRT_MAX_LIGHT_GRIDS; k++) es->lg.g[k] = gridref_none();
+    const int n_lights = es->view.n_lights, na = es->view.n_active_instances;
+    const bool lights_on = light_R > 0 && es->hs.all_rigid && na > 0;
+    // room for the chain nodes behind the trees (same regions as build_device_scene)
+    const int n_grids = lights_on ? std::min(n_lights, YRT_MAX_LIGHT_GRIDS) : 0;
+    es->light_node_cap = n_grids ? n_grids * 6 * light_R * light_R * 3 / 4 + 1024 : 0;
+    es->cam_node_cap = cam_shift >= 0 ? 1 << 18 : 0;
+    es->cam_node_first = es->tree_nodes + (YRT_WIDE_CLOSEST == YRT_WIDE_ANY ? es->light_node_cap : 0);
+    const size_t total_nodes = (size_t)es->tree_nodes + es->light_node_cap + es->cam_node_cap;
+    es->nodes2.resize(YRT_NODE_STRIDE(2) * total_nodes, mk4(0, 0, 0, 0));
+    es->nodes4.resize(YRT_NODE_STRIDE(4) * total_nodes, mk4(0, 0, 0, 0));
+    es->view.nodes2 = es->nodes2.data(); es->view.nodes4 = es->nodes4.data();
+    if (lights_on) {
+        es->light_grids.resize(n_grids);
+        int node_total = 0;
+        std::vector<float4>& arr = YRT_WIDE_ANY == 4 ? es->nodes4 : es->nodes2;
+        for (int k = 0; k < n_grids; k++) {
+            const float4* lr = &es->hs.light_recs[5 * (size_t)k];
+            const bool identity = lr[0].x == 1.f && lr[0].y == 0.f && lr[0].z == 0.f && lr[1].x == 0.f && lr[1].y == 1.f && lr[1].z == 0.f &&
+                                  lr[2].x == 0.f && lr[2].y == 0.f && lr[2].z == 1.f;
+            es->light_grids[k].d.mode = 0;
+            if (!identity) continue;
+            const vec3 apex = mk3(lr[4].x + lr[3].x, lr[4].y + lr[3].y, lr[4].z + lr[3].z);
+            const float reach = es->extent + fmaxf(fmaxf(fabsf(apex.x), fabsf(apex.y)), fabsf(apex.z));
+            emu_build_grid(pgrid_cube_desc(apex, light_R, reach, 4 * 6 * light_R * light_R), es->inst_box, na, YRT_WIDE_ANY, arr.data(), es->tree_nodes,
+                           es->light_node_cap, &node_total, es->view.tlas_root, es->light_grids[k]);
+            es->lg.g[k] = es->light_grids[k].ref();
+            ne += es->light_grids[k].n_entries; nf += es->light_grids[k].n_fallback_cells; nl++; nn += es->light_grids[k].n_nodes;
+        }
+    }
+    if (stats) { stats[0] = ne; stats[1] = nf; stats[2] = nl; stats[3] = nn; }
+    return YRT_OK;
+}
 
 int emu_scene_create(const yrt_scene_desc* d, int leaf_blas, int leaf_tlas, void** out) {
     EmuScene* es = new EmuScene();
@@ -246,12 +371,10 @@ int64_t emu_read_nodes(void* p, int arity, float* out) {
 int emu_trace_primary(void* p, const yrt_camera* cam, int width, int height, int samples, int32_t* ids, float* dist, float* uv,
                       int64_t* counters_out) {
     EmuScene* es = (EmuScene*)p;
-    camera_k ck;
-    {
-        const float* f = cam->frame;
-        ck.frame.x = mk3(f[0], f[1], f[2]); ck.frame.y = mk3(f[3], f[4], f[5]); ck.frame.z = mk3(f[6], f[7], f[8]); ck.frame.o = mk3(f[9], f[10], f[11]);
-        ck.h = 2.0f * cam->focus * tanf(cam->fovy / 2.0f); ck.w = ck.h * cam->aspect; ck.focus = cam->focus;
-    }
+    camera_k ck = emu_camera(cam);
+    EmuGrid cgrid;
+    emu_camera_grid(*es, ck, width, height, cgrid);
+    const GridRef cg = emu_camera_ref(*es, cgrid);
     long long cb = 0, cp = 0, ci = 0, cfr = 0, cea = 0, ctb = 0, cnv = 0; int cm = 0;
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : cb, cp, ci, cfr, cea, ctb, cnv) reduction(max : cm)
     for (int j = 0; j < height; j++) {
@@ -265,7 +388,7 @@ int emu_trace_primary(void* p, const yrt_camera* cam, int width, int height, int
                     ray3 ray = eval_camera(ck, u, v);
                     HitRec h;
                     TraceCounters tc = {0, 0, 0, 0, 0, 0, 0, 0};
-                    trace_ray<false>(es->view, ray, h, stack, &tc);
+                    trace_camera_ray(es->view, cg, ray, i, j, h, stack, &tc);
                     cb += tc.box_tests; cp += tc.prim_tests; ci += tc.inst_entries; cm = std::max(cm, tc.max_stack);
                     cfr += tc.slab_false_rejects; cea += tc.slab_extra_accepts; ctb += tc.tlas_box_tests; cnv += tc.node_visits;
                     hit_to_ids(es->view, h, ids + 3 * r);
@@ -308,12 +431,10 @@ int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, in
                int64_t* ray_counts) {
     EmuScene* es = (EmuScene*)p;
     const SceneView& sv = es->view;
-    camera_k ck;
-    {
-        const float* f = cam->frame;
-        ck.frame.x = mk3(f[0], f[1], f[2]); ck.frame.y = mk3(f[3], f[4], f[5]); ck.frame.z = mk3(f[6], f[7], f[8]); ck.frame.o = mk3(f[9], f[10], f[11]);
-        ck.h = 2.0f * cam->focus * tanf(cam->fovy / 2.0f); ck.w = ck.h * cam->aspect; ck.focus = cam->focus;
-    }
+    camera_k ck = emu_camera(cam);
+    EmuGrid cgrid;
+    emu_camera_grid(*es, ck, width, height, cgrid);
+    const GridRef cg = emu_camera_ref(*es, cgrid);
     vec3 ambv = mk3(amb[0], amb[1], amb[2]);
     if (max_depth <= 0) max_depth = 16;
     long long n_refl = 0, n_shadow = 0, sb = 0, stb = 0, sp_ = 0, si_ = 0, socc = 0, snv = 0;
@@ -333,7 +454,8 @@ int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, in
                     int depth = 0;
                     for (;;) {
                         HitRec h;
-                        trace_ray<false>(sv, ray, h, stack, nullptr);
+                        if (depth == 0) trace_camera_ray(sv, cg, ray, i, j, h, stack, nullptr);
+                        else trace_ray<false>(sv, ray, h, stack, nullptr);
                         if (depth > 0) n_refl++;
                         if (h.si < 0) { value = mk3(0.f, 0.f, 0.f); break; }
                         int kind;
@@ -344,7 +466,7 @@ int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, in
                             ray3 sr = shadow_ray(P, l, r);
                             HitRec hr;
                             TraceCounters tc = {0, 0, 0, 0, 0, 0, 0, 0};
-                            vis[k] = trace_ray<true>(sv, sr, hr, stack, &tc) ? 0 : 1;
+                            vis[k] = trace_shadow_ray(sv, es->lg, k, sr, hr, stack, &tc) ? 0 : 1;
                             n_shadow++;
                             sb += tc.box_tests; stb += tc.tlas_box_tests; sp_ += tc.prim_tests; si_ += tc.inst_entries; socc += vis[k] ? 0 : 1; snv += tc.node_visits;
                         }

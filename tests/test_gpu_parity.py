@@ -301,17 +301,17 @@ def test_cli_scene_cache_and_device_ldr(gpu, tmp_path):
     assert within1 >= PIXEL_BAR, (within1, ident, mx)
     # a stale cache (older than the OBJ) is ignored and rewritten
     os.utime(obj + ".yrts", (1, 1))
-    r = subprocess.run([ours] + args + ["--cache", "-o", os.path.join(cwd, "ours3.png"), name], cwd=cwd, capture_output=True, text=True)
+    r = subprocess.run([ours] + args + ["--cache", "--stats", "-o", os.path.join(cwd, "ours3.png"), name], cwd=cwd, capture_output=True, text=True)
     assert r.returncode == 0 and "(scene cache)" not in r.stdout
     assert os.stat(obj + ".yrts").st_mtime > 1
     # ... and so is a cache older than the material library or a texture next to the scene
     import time
     for dep in (obj[:-4] + ".mtl", os.path.join(cwd, "grid.png")):
-        r = subprocess.run([ours] + args + ["--cache", "-o", os.path.join(cwd, "ours3.png"), name], cwd=cwd, capture_output=True, text=True)
+        r = subprocess.run([ours] + args + ["--cache", "--stats", "-o", os.path.join(cwd, "ours3.png"), name], cwd=cwd, capture_output=True, text=True)
         assert r.returncode == 0 and "(scene cache)" in r.stdout          # fresh now
-        future = time.time() + 5
+        future = max(time.time(), os.stat(obj + ".yrts").st_mtime) + 5      # (whole seconds later than the cache, whatever the runs took)
         os.utime(dep, (future, future))
-        r = subprocess.run([ours] + args + ["--cache", "-o", os.path.join(cwd, "ours3.png"), name], cwd=cwd, capture_output=True, text=True)
+        r = subprocess.run([ours] + args + ["--cache", "--stats", "-o", os.path.join(cwd, "ours3.png"), name], cwd=cwd, capture_output=True, text=True)
         assert r.returncode == 0 and "(scene cache)" not in r.stdout, dep
         os.utime(obj + ".yrts", (future + 1, future + 1))
     # .hdr output keeps the float path even with --device-ldr
@@ -560,3 +560,27 @@ def test_device_lbvh_equals_serial_execution_bit_for_bit(gpu, maker):
                 assert got.shape == want[a].shape, (a, got.shape, want[a].shape, info)
                 same = (got.view(np.uint32) == want[a].view(np.uint32)).all(axis=1)
                 assert same.all(), (rep, a, int((~same).sum()), np.flatnonzero(~same)[:8])
+
+
+@pytest.mark.parametrize("maker,w,h,s", [(lambda: load_golden("instance10000")[0], 640, 360, 2), (lambda: synth.mixed_scene(11).flat(), 131, 73, 3),
+                                         (lambda: load_golden("refl")[0], 320, 180, 2), (lambda: synth.hair_scene(512, seed=5).flat(), 160, 90, 2)])
+def test_apex_grids_do_not_change_the_frame(gpu, monkeypatch, maker, w, h, s):
+    """The apex grids (csrc/yrt_pgrid.cuh: camera rays / shadow rays start at the root of their cell's short chain of
+    instance-level nodes instead of the instance tree's root) must not change a single bit: frame, hit ids, distances and
+    ray counts with the grids (default), without them, and with other cell sizes."""
+    flat = maker()
+    with gpu.Scene(flat) as scn:
+        a, sa = scn.render(w, h, s, 0.1)
+        ia, da, _ = scn.trace_primary(w, h, s)
+    for env in ({"YRT_PGRID": "0"}, {"YRT_CAM_CELL_SHIFT": "0", "YRT_LIGHT_GRID_R": "16"}, {"YRT_CAM_CELL_SHIFT": "5", "YRT_LIGHT_GRID_R": "256"},
+                {"YRT_CAM_GRID_NODES": "64", "YRT_LIGHT_GRID_R": "8"}):      # (64 chain nodes: most cells fall back to the tree's root)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with gpu.Scene(flat) as scn:
+            b, sb = scn.render(w, h, s, 0.1)
+            ib, db, _ = scn.trace_primary(w, h, s)
+        for k in env:
+            monkeypatch.delenv(k)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), env
+        assert np.array_equal(ia, ib) and np.array_equal(da.view(np.uint32), db.view(np.uint32)), env
+        assert (sa.primary_rays, sa.shadow_rays, sa.reflection_rays, sa.max_depth) == (sb.primary_rays, sb.shadow_rays, sb.reflection_rays, sb.max_depth), env

@@ -136,3 +136,69 @@ def test_emulated_device_hit_ids_full_size(case):
     assert same.mean() >= 0.9999, (same.mean(), int((~same).sum()))
     assert np.array_equal(d[same].view(np.uint32), dist[same].view(np.uint32))
     assert ctr[4] == 0 and ctr[3] <= es.info()[6] <= 128
+
+
+# ---- apex grids (csrc/yrt_pgrid.cuh): rays of the camera / towards a point light start at the root of their cell ----------
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_apex_grids_change_nothing(name):
+    """Same hits (ids, distances, barycentrics, tie winners) and the same image, bit for bit, with and without the grids —
+    i.e. every cell's candidate list holds all instances a ray of that cell can hit — and against the reference's goldens."""
+    flat, ref = load_golden(name)
+    w, h = int(ref["ids_width"]), int(ref["ids_height"])
+    ih, iw = ref["image"].shape[:2]
+    e = _emu.EmuScene(flat)
+    ids0, d0, uv0, c0 = e.trace_primary(w, h, 1)
+    img0, r0 = e.render(iw, ih, int(ref["image_samples"]), float(ref["ambient"]), max_depth=64)
+    for light_R, shift in ((16, 3), (64, 1), (128, 5)):
+        entries, fallback, n_grids, nodes = _emu.set_grids(e, light_R, shift)
+        assert n_grids == min(e.info()[4], 8)                 # every point light of the golden scenes gets a grid
+        ids1, d1, uv1, c1 = e.trace_primary(w, h, 1)
+        img1, r1 = e.render(iw, ih, int(ref["image_samples"]), float(ref["ambient"]), max_depth=64)
+        assert np.array_equal(ids0, ids1) and np.array_equal(d0, d1) and np.array_equal(uv0, uv1)
+        assert np.array_equal(img0, img1) and r0[:3] == r1[:3]
+        assert c1[4] == 0                                      # the slab audit holds on the chain nodes too
+    assert id_match(ids1, ref["ids"]) >= 0.9999
+
+
+def test_apex_grids_do_less_work():
+    """instance10000: the box tests of the instance level shrink to a few per ray (what the grids are for)."""
+    flat, ref = load_golden("instance10000")
+    e = _emu.EmuScene(flat)
+    w, h = 480, 270
+    _, _, _, c0 = e.trace_primary(w, h, 1)
+    _, r0 = e.render(w // 2, h // 2, 1)
+    _emu.set_grids(e, 128, 3)
+    _, _, _, c1 = e.trace_primary(w, h, 1)
+    _, r1 = e.render(w // 2, h // 2, 1)
+    n = w * h
+    assert c0[6] / n > 30 and c1[6] / n < 12, (c0[6] / n, c1[6] / n)          # instance-level box tests per camera ray
+    assert r0[4] / r0[2] > 18 and r1[4] / r1[2] < 6, (r0[4] / r0[2], r1[4] / r1[2])   # ... per shadow ray
+    assert c1[0] < 0.75 * c0[0] and r1[3] < 0.65 * r0[3]                       # all box tests
+
+
+def test_apex_grids_moving_camera_and_odd_sizes():
+    """Camera grids for cameras inside / beside / far from the scene, odd image sizes and every cell size: same hits as the tree walk."""
+    from yocto_raytracing_b200 import synth
+    rng = np.random.default_rng(5)
+    sc = synth.mixed_scene(7)
+    for trial in range(6):
+        eye = rng.uniform(-6, 6, 3).astype(np.float32)
+        if trial == 0:
+            eye = np.array([0.0, 1.0, 0.0], np.float32)       # inside the scene: boxes around and behind the pinhole
+        at = rng.uniform(-1, 1, 3).astype(np.float32)
+        z = (eye - at) / np.linalg.norm(eye - at)
+        x = np.cross(np.array([0, 1, 0], np.float32), z); x /= np.linalg.norm(x)
+        yv = np.cross(z, x)
+        fr = np.concatenate([x, yv, z, eye]).astype(np.float32)
+        sc.camera = np.concatenate([fr, np.array([rng.uniform(0.3, 1.2), 16 / 9, 0, rng.uniform(0.5, 9.0)], np.float32)])
+        flat = sc.flat()
+        e = _emu.EmuScene(flat)
+        w, h = int(rng.integers(33, 160)), int(rng.integers(17, 90))
+        ids0, d0, _, _ = e.trace_primary(w, h, 2)
+        img0, _ = e.render(w, h, 1)
+        for shift in (0, 2, 4):
+            _emu.set_grids(e, 32, shift)
+            ids1, d1, _, _ = e.trace_primary(w, h, 2)
+            img1, _ = e.render(w, h, 1)
+            assert np.array_equal(ids0, ids1) and np.array_equal(d0, d1), (trial, shift)
+            assert np.array_equal(img0, img1), (trial, shift)

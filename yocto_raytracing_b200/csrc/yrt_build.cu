@@ -20,6 +20,8 @@ namespace yrt {
 // kernels: one thread per item, bodies in yrt_lbvh.cuh
 // ------------------------------------------------------------------------------------------
 #define YRT_TID() ((int)(blockIdx.x * blockDim.x + threadIdx.x))
+static inline int grid_for(int n, int t = 256) { return n > 0 ? (n + t - 1) / t : 1; }
+static inline int grid_for_warps(int n_warps) { return n_warps > 0 ? (n_warps + 7) / 8 : 1; }   // 256-thread blocks, one warp per item
 
 __global__ void k_prim_boxes(GeomView g, float4* lo, float4* hi) {
     int i = YRT_TID();
@@ -105,6 +107,71 @@ __global__ void k_inst_recs(int n_active, const int* __restrict__ order, const i
     r[1] = mk4(fr[3], fr[4], fr[5], int_as_float(inst));
     r[2] = mk4(fr[6], fr[7], fr[8], int_as_float(inst_mat[inst]));
     r[3] = mk4(fr[9], fr[10], fr[11], int_as_float((int)((unsigned)s | ((unsigned)shape_kind[s] << 28))));
+}
+
+// world boxes of the instances in TLAS leaf order, as (centre, inflated half-extent): the boxes the apex grids are built from
+__global__ void k_inst_box(int n_active, const int* __restrict__ order, const float4* __restrict__ lo, const float4* __restrict__ hi,
+                           float4* __restrict__ out) {
+    int k = YRT_TID();
+    if (k >= n_active) return;
+    const float4 l = lo[order[k]], h = hi[order[k]];
+    float cx, cy, cz, hx, hy, hz;
+    box_center_half(l.x, h.x, cx, hx);
+    box_center_half(l.y, h.y, cy, hy);
+    box_center_half(l.z, h.z, cz, hz);
+    out[2 * (size_t)k] = mk4(cx, cy, cz, 0.f);
+    out[2 * (size_t)k + 1] = mk4(hx, hy, hz, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------
+// apex grids (yrt_pgrid.cuh): count -> allocate -> fill -> sort, per grid
+// ------------------------------------------------------------------------------------------
+#define PGRID_BIG_BLOCKS 64
+__global__ void __launch_bounds__(256) k_pgrid_scatter(PGridArrays a, int fill) {   // one warp per instance slot
+    const int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w < a.n_inst) pgrid_scatter_item(a, w, lane, 32, fill != 0, false);
+}
+__global__ void __launch_bounds__(256) k_pgrid_scatter_big(PGridArrays a, int fill) {   // all threads of the grid per large instance
+    const int n_big = a.big[0], t = YRT_TID(), nt = (int)(gridDim.x * blockDim.x);
+    for (int b = 0; b < n_big; b++) pgrid_scatter_item(a, a.big[1 + b], t, nt, fill != 0, true);
+}
+__global__ void __launch_bounds__(256) k_pgrid_alloc(PGridArrays a) {
+    const int cell = YRT_TID(), lane = threadIdx.x & 31;
+    const bool ok = cell < a.d.n_cells;
+    const int n = ok ? a.cnt[cell] : 0;
+    if (ok) a.cnt[cell] = 0;
+    const int need = pgrid_alloc_need(a, n);
+    int x = need;   // inclusive prefix over the warp: one atomic on the running total per warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    const int tot = __shfl_sync(0xffffffffu, x, 31);
+    int base = 0;
+    if (lane == 0 && tot) base = atomicAdd(a.total, tot);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (ok) a.cells[cell] = pgrid_alloc_cell(a, n, base + x - need);
+}
+__global__ void __launch_bounds__(128) k_pgrid_emit(PGridArrays a) { int c = YRT_TID(); if (c < a.d.n_cells) pgrid_emit_item(a, c); }
+
+int pgrid_build_enqueue(const PGridArrays& a, cudaStream_t st) {
+    if (a.d.mode == 0 || a.d.n_cells <= 0) return YRT_OK;
+    // cnt | total | big[0] are one allocation (see the callers): cleared together (a.node_total is the caller's: grids may share a pool)
+    YRT_CUDA(cudaMemsetAsync(a.cnt, 0, sizeof(int) * ((size_t)a.d.n_cells + 2), st));
+    const int warps_grid = grid_for_warps(a.n_inst);
+    if (a.n_inst > 0) {
+        k_pgrid_scatter<<<warps_grid, 256, 0, st>>>(a, 0);
+        k_pgrid_scatter_big<<<PGRID_BIG_BLOCKS, 256, 0, st>>>(a, 0);
+    }
+    k_pgrid_alloc<<<(a.d.n_cells + 255) / 256, 256, 0, st>>>(a);
+    if (a.n_inst > 0) {
+        k_pgrid_scatter<<<warps_grid, 256, 0, st>>>(a, 1);
+        k_pgrid_scatter_big<<<PGRID_BIG_BLOCKS, 256, 0, st>>>(a, 1);
+    }
+    k_pgrid_emit<<<(a.d.n_cells + 127) / 128, 128, 0, st>>>(a);
+    YRT_CUDA(cudaGetLastError());
+    return YRT_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -285,7 +352,7 @@ struct LbvhIo {
     int* order;                             // [n] item id at sorted slot (temp arena, read by the gather kernels)
 };
 
-static inline int grid_for(int n, int t = 256) { return n > 0 ? (n + t - 1) / t : 1; }
+
 
 // temporaries of one build from `tmp` (dry or real), then — if real — the launches
 static int lbvh_build(cudaStream_t st, Arena& tmp, LbvhIo& io) {
@@ -405,6 +472,49 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
     float* d_inst_frame = nullptr;
     float4 *plo = nullptr, *phi = nullptr, *ilo = nullptr, *ihi = nullptr, *d_nodes2 = nullptr, *d_nodes4 = nullptr, *d_prim_recs = nullptr, *d_prim_attrs = nullptr, *d_inst_recs = nullptr;
     int *d_prim_rank = nullptr, *d_inst_rank = nullptr;
+    float4* d_inst_box = nullptr;
+    // apex grids of the point lights (yrt_pgrid.cuh).  A light converges its shadow rays on ONE point only if its frame does
+    // not rotate: shade() aims at transform_point(frame, pos - p) (src/raytrace.cpp:129-130), i.e. at (pos + o) - p for an
+    // identity rotation; other lights, lights beyond the first YRT_MAX_LIGHT_GRIDS and scenes with non-rigid instance
+    // frames keep the instance tree.
+    const int n_lights = (int)hs.light_inst.size();
+    ds.grids_allowed = hs.all_rigid && env_or("YRT_PGRID", 1, 0, 1) != 0 && na > 0;
+    ds.extent = hs.extent;
+    int light_R = env_or("YRT_LIGHT_GRID_R", -1, -1, 1024);
+    if (light_R < 0) { light_R = 8; while (light_R < 256 && light_R * light_R < na) light_R *= 2; }   // ~ one cell per instance and face
+    if (!ds.grids_allowed) light_R = 0;
+    ds.light_grid_R = light_R;
+    PGridArrays lga[YRT_MAX_LIGHT_GRIDS];
+    bool lg_on[YRT_MAX_LIGHT_GRIDS];
+    int n_light_grids = 0;
+    for (int k = 0; k < YRT_MAX_LIGHT_GRIDS; k++) {
+        ds.light_grids.g[k] = gridref_none();
+        lg_on[k] = false;
+        if (k >= n_lights || light_R <= 0) continue;
+        const float4* lr = &hs.light_recs[5 * (size_t)k];
+        const bool identity = lr[0].x == 1.f && lr[0].y == 0.f && lr[0].z == 0.f && lr[1].x == 0.f && lr[1].y == 1.f && lr[1].z == 0.f &&
+                              lr[2].x == 0.f && lr[2].y == 0.f && lr[2].z == 1.f;
+        if (!identity) continue;
+        const vec3 apex = mk3(lr[4].x + lr[3].x, lr[4].y + lr[3].y, lr[4].z + lr[3].z);
+        const float reach = hs.extent + fmaxf(fmaxf(fabsf(apex.x), fabsf(apex.y)), fabsf(apex.z));
+        if (!(reach < 1.0e18f)) continue;
+        lga[k].d = pgrid_cube_desc(apex, light_R, reach, 4 * 6 * light_R * light_R);
+        lg_on[k] = true;
+        n_light_grids++;
+    }
+    // chain nodes of the grids live behind the two trees in the node arrays (one index space per array).  The lights' chains go
+    // into the array the any-hit rays walk, the camera's (rebuilt per frame, room reserved here) into the closest-hit rays';
+    // if both ray kinds walk the same array the two regions follow each other, otherwise both start right behind the trees.
+    const int grid_node_first = nb_int + nt_int + 2;
+    const int light_node_cap = n_light_grids ? (int)std::min<long long>((long long)n_light_grids * 6 * light_R * light_R * 3 / 4 + 1024, 1 << 26) : 0;
+    const int cam_node_cap = ds.grids_allowed ? env_or("YRT_CAM_GRID_NODES", 1 << 18, 0, 1 << 24) : 0;
+    const int cam_node_first = grid_node_first + (YRT_WIDE_CLOSEST == YRT_WIDE_ANY ? light_node_cap : 0);
+    const size_t nodes_any = (size_t)grid_node_first + light_node_cap + (YRT_WIDE_CLOSEST == YRT_WIDE_ANY ? cam_node_cap : 0);
+    const size_t nodes_closest = YRT_WIDE_CLOSEST == YRT_WIDE_ANY ? nodes_any : (size_t)cam_node_first + cam_node_cap;
+    const size_t n_nodes4 = std::max<size_t>(grid_node_first, std::max(YRT_WIDE_ANY == 4 ? nodes_any : 0, YRT_WIDE_CLOSEST == 4 ? nodes_closest : 0));
+    const size_t n_nodes2 = std::max<size_t>(grid_node_first, std::max(YRT_WIDE_ANY == 2 ? nodes_any : 0, YRT_WIDE_CLOSEST == 2 ? nodes_closest : 0));
+    ds.cam_node_first = cam_node_first; ds.cam_node_cap = cam_node_cap;
+    int* d_light_node_total = nullptr;
     LbvhIo bo, to;
     const int tl_sf[2] = {0, na};
     // results block read back in one copy: [blas depth | blas need (binary) | blas need (4-wide) | tlas depth, need2, need4, root]
@@ -431,13 +541,29 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
             return p;
         };
         // products and what the kernels of a frame read
-        d_nodes4 = keep.take<float4>(YRT_NODE_STRIDE(4) * (size_t)(nb_int + nt_int + 2));   // (first in the arena: 256-byte aligned, one line per record)
-        d_nodes2 = keep.take<float4>(YRT_NODE_STRIDE(2) * (size_t)(nb_int + nt_int + 2));
+        d_nodes4 = keep.take<float4>(YRT_NODE_STRIDE(4) * n_nodes4);   // (first in the arena: 256-byte aligned, one line per record)
+        d_nodes2 = keep.take<float4>(YRT_NODE_STRIDE(2) * n_nodes2);
         d_prim_recs = keep.take<float4>(3 * (size_t)std::max(np, 1));
         d_prim_attrs = keep.take<float4>(YRT_ATTR_STRIDE * (size_t)std::max(np, 1));
         d_inst_recs = keep.take<float4>(4 * (size_t)std::max(na, 1));
         d_prim_rank = keep.take<int>((size_t)std::max(np, 1));
         d_inst_rank = keep.take<int>((size_t)std::max(na, 1));
+        d_inst_box = keep.take<float4>(2 * (size_t)std::max(na, 1));
+        for (int k = 0; k < YRT_MAX_LIGHT_GRIDS; k++) {
+            if (!lg_on[k]) continue;
+            PGridArrays& a = lga[k];
+            a.roots = keep.take<int>((size_t)a.d.n_cells);
+            a.cells = tmp.take<int2>((size_t)a.d.n_cells);
+            a.cnt = tmp.take<int>((size_t)a.d.n_cells + 2 + (size_t)na);
+            a.total = a.cnt ? a.cnt + a.d.n_cells : nullptr;
+            a.big = a.cnt ? a.cnt + a.d.n_cells + 1 : nullptr;
+            a.keys = tmp.take<unsigned long long>((size_t)a.d.capacity);
+            a.inst_box = d_inst_box;
+            a.n_inst = na;
+            a.arity = YRT_WIDE_ANY; a.nodes = YRT_WIDE_ANY == 4 ? d_nodes4 : d_nodes2;
+            a.node_first = grid_node_first; a.node_capacity = light_node_cap;
+        }
+        d_light_node_total = tmp.take<int>(1);
         v.mat_recs = up_keep((float4*)nullptr, hs.mat_recs);
         v.light_recs = up_keep((float4*)nullptr, hs.light_recs);
         v.tex_rgba8 = up_keep((uint8_t*)nullptr, hs.tex_rgba8);
@@ -508,6 +634,17 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
     if (na > 0) k_inst_boxes<<<grid_for(na), 256, 0, st>>>(na, d_active, d_inst_frame, d_inst_shape, bo.seg_box_lo, bo.seg_box_hi, ilo, ihi);
     YRT_TRY(lbvh_build(st, tmp, to));
     if (na > 0) k_inst_recs<<<grid_for(na), 256, 0, st>>>(na, to.order, d_active, d_inst_frame, d_inst_shape, d_inst_mat, d_shape_kind, bo.seg_root, d_inst_recs);
+    if (na > 0) k_inst_box<<<grid_for(na), 256, 0, st>>>(na, to.order, ilo, ihi, d_inst_box);
+    if (n_light_grids) YRT_CUDA(cudaMemsetAsync(d_light_node_total, 0, sizeof(int), st));
+    for (int k = 0; k < YRT_MAX_LIGHT_GRIDS; k++) {
+        if (!lg_on[k]) continue;
+        lga[k].node_total = d_light_node_total;
+        lga[k].tlas_root = 0;
+        lga[k].tlas_root_dev = to.seg_root;      // (the root is only known on the device at this point)
+        YRT_TRY(pgrid_build_enqueue(lga[k], st));
+        GridRef& g = ds.light_grids.g[k];
+        g.roots = lga[k].roots; g.nx = light_R; g.shift = 0;
+    }
     YRT_CUDA(cudaGetLastError());
     const double t_enqueued = now_ms();
     // tie-break ranks: computed on a host thread since yrt_scene_create started (yrt_host.cu); needed only now
@@ -547,9 +684,19 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
         set_error("traversal tree too deep for the stack (%d entries needed: tlas %d + blas %d levels, capacity %d)", ds.stack_need, ds.tlas_depth, ds.blas_depth, YRT_STACK_CAP);
         return YRT_ERR_UNSUPPORTED;
     }
+    // a cell's chain postpones up to YRT_PGRID_MAX_LIST + 2 entries on a ray's stack where the instance tree postpones its depth's worth
+    {
+        const int chain = YRT_PGRID_MAX_LIST + 2;
+        const int g2 = std::max(tlas_need2, chain) + blas_need2 + 3, g4 = std::max(tlas_need4, chain) + blas_need4 + 3;
+        if (ds.grids_allowed && std::max(YRT_WIDE_CLOSEST == 4 ? g4 : g2, YRT_WIDE_ANY == 4 ? g4 : g2) > YRT_STACK_CAP) {
+            ds.grids_allowed = false;
+            for (int k = 0; k < YRT_MAX_LIGHT_GRIDS; k++) ds.light_grids.g[k] = gridref_none();
+        }
+    }
     v.nodes2 = d_nodes2;
     v.nodes4 = d_nodes4;
     v.inst_recs = d_inst_recs;
+    v.inst_box = d_inst_box;
     v.prim_recs = d_prim_recs;
     v.prim_attrs = d_prim_attrs;
     v.inst_rank = d_inst_rank;
@@ -557,6 +704,39 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
     v.tlas_root = troot;
     v.n_lights = (int)hs.light_inst.size();
     v.n_active_instances = na;
+    return YRT_OK;
+}
+
+// The apex grid of one frame's camera (pinhole = eval_camera's ray origin, src/raytrace.cpp:6-37): cells are tiles of
+// 2^shift x 2^shift pixels.  Rebuilt for every frame — the camera is an argument of the render call — on the frame's own
+// stream ahead of the primary-ray kernel: a memset and six small launches, no host synchronisation.
+int camera_grid_enqueue(DevScene& ds, const camera_k& cam, int width, int height, cudaStream_t st, GridRef* out) {
+    *out = gridref_none();
+    auto env_or = [](const char* name, int def, int lo, int hi) { const char* e = getenv(name); return std::min(std::max(e ? atoi(e) : def, lo), hi); };
+    if (!ds.grids_allowed || ds.n_active <= 0 || env_or("YRT_CAM_GRID", 1, 0, 1) == 0) return YRT_OK;
+    const int shift = env_or("YRT_CAM_CELL_SHIFT", 3, 0, 8);
+    const float reach = ds.extent + fmaxf(fmaxf(fabsf(cam.frame.o.x), fabsf(cam.frame.o.y)), fabsf(cam.frame.o.z));
+    if (!(reach < 1.0e18f)) return YRT_OK;
+    const long long cells = (long long)((width + (1 << shift) - 1) >> shift) * ((height + (1 << shift) - 1) >> shift);
+    if (cells > (1ll << 24) || ds.cam_node_cap <= 0) return YRT_OK;
+    const int capacity = (int)std::min<long long>(16 * cells + 65536, 1ll << 28);
+    PGridArrays a;
+    a.d = pgrid_camera_desc(cam, width, height, shift, reach, capacity);
+    if (a.d.mode == 0) return YRT_OK;
+    YRT_TRY(ds.cg_roots.alloc(sizeof(int) * (size_t)a.d.n_cells, ds.device));
+    YRT_TRY(ds.cg_cells.alloc(sizeof(int2) * (size_t)a.d.n_cells, ds.device));
+    YRT_TRY(ds.cg_keys.alloc(sizeof(unsigned long long) * (size_t)capacity, ds.device));
+    YRT_TRY(ds.cg_cnt.alloc(sizeof(int) * ((size_t)a.d.n_cells + 3 + (size_t)ds.n_active), ds.device));
+    a.inst_box = ds.view.inst_box; a.n_inst = ds.n_active;
+    a.cnt = ds.cg_cnt.as<int>(); a.total = a.cnt + a.d.n_cells; a.big = a.cnt + a.d.n_cells + 1;
+    a.node_total = a.big + 1 + ds.n_active;
+    a.cells = ds.cg_cells.as<int2>(); a.keys = ds.cg_keys.as<unsigned long long>(); a.roots = ds.cg_roots.as<int>();
+    a.arity = YRT_WIDE_CLOSEST; a.nodes = const_cast<float4*>(YRT_WIDE_CLOSEST == 4 ? ds.view.nodes4 : ds.view.nodes2);
+    a.node_first = ds.cam_node_first; a.node_capacity = ds.cam_node_cap;
+    a.tlas_root = ds.view.tlas_root; a.tlas_root_dev = nullptr;
+    YRT_CUDA(cudaMemsetAsync(a.node_total, 0, sizeof(int), st));
+    YRT_TRY(pgrid_build_enqueue(a, st));
+    out->roots = a.roots; out->nx = a.d.nx; out->shift = shift;
     return YRT_OK;
 }
 

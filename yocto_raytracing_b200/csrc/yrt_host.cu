@@ -169,6 +169,31 @@ int host_scene_from_desc(const yrt_scene_desc* d, HostScene& hs, bool ranks_asyn
         hs.light_recs.push_back(mk4(p0[0], p0[1], p0[2], 0.f));
         hs.light_inst.push_back(i);
     }
+    // bound of every world coordinate (error budget of the apex grids) and rigidity of the instance frames
+    {
+        std::vector<float> shape_r(std::max(hs.n_shapes, 1), 0.f);
+        for (int s = 0; s < hs.n_shapes; s++) {
+            float m = 0.f;
+            for (int v = hs.shape_vert_off[s]; v < hs.shape_vert_off[s] + hs.shape_vert_cnt[s]; v++) {
+                float rad = hs.radius.empty() ? 0.f : fabsf(hs.radius[v]);
+                for (int c = 0; c < 3; c++) m = std::max(m, fabsf(hs.pos[3 * (size_t)v + c]) + rad);
+            }
+            shape_r[s] = m;
+        }
+        hs.extent = 0.f; hs.all_rigid = true;
+        for (int i = 0; i < hs.n_instances; i++) {
+            const float* f = &hs.inst_frame[12 * (size_t)i];
+            float rows = 0.f;
+            for (int c = 0; c < 3; c++) rows = std::max(rows, fabsf(f[c]) + fabsf(f[3 + c]) + fabsf(f[6 + c]));
+            float e = std::max(std::max(fabsf(f[9]), fabsf(f[10])), fabsf(f[11])) + rows * shape_r[hs.inst_shape[i]];
+            if (e > hs.extent || !(e == e)) hs.extent = e;
+            auto dot3 = [](const float* a, const float* b) { return (double)a[0] * b[0] + (double)a[1] * b[1] + (double)a[2] * b[2]; };
+            const double tol = 1e-4;
+            bool rigid = fabs(dot3(f, f) - 1.0) <= tol && fabs(dot3(f + 3, f + 3) - 1.0) <= tol && fabs(dot3(f + 6, f + 6) - 1.0) <= tol &&
+                         fabs(dot3(f, f + 3)) <= tol && fabs(dot3(f, f + 6)) <= tol && fabs(dot3(f + 3, f + 6)) <= tol;
+            if (!rigid) hs.all_rigid = false;
+        }
+    }
     if (ranks_async) hs.rank_thread = std::thread([&hs]() { reference_visit_ranks(hs); });
     else reference_visit_ranks(hs);
     return YRT_OK;

@@ -8,6 +8,7 @@
 
 #include "../../include/yrt_b200.h"
 #include "yrt_lbvh.cuh"
+#include "yrt_pgrid.cuh"
 #include "yrt_scene.cuh"
 
 namespace yrt {
@@ -64,6 +65,8 @@ struct HostScene {
     std::vector<uint8_t> tex_rgba8;
     float srgb_lut[256];
     int n_reflective = 0;
+    float extent = 0.f;                      // bound of |coordinate| over everything in the scene (instances' world boxes)
+    bool all_rigid = true;                   // every instance frame is orthonormal (to 1e-4): a local hit distance is the world distance
     // the rank tables are computed on a worker thread that yrt_scene_create starts; the build waits for it at the end
     std::thread rank_thread;
     void wait_ranks() { if (rank_thread.joinable()) rank_thread.join(); }
@@ -110,10 +113,22 @@ struct DevScene {
     bool has_reflective = false;
     int grid_closest_primary = 0, grid_closest_queue = 0, grid_any = 0;   // persistent grids (SMs x resident CTAs)
     DevBuf dctr;                     // per-ray work counters of the traversal kernels (-DYRT_COUNTERS=1 builds)
+    // apex grids (yrt_pgrid.cuh): one cube grid per point light, built with the scene (in `arena`); the camera grid is
+    // rebuilt by every render call into cg_* (grown on demand)
+    LightGrids light_grids;
+    int light_grid_R = 0;
+    bool grids_allowed = false;      // rigid frames only: the lists are sorted and cut by world-space distances
+    float extent = 0.f;
+    DevBuf cg_roots, cg_cells, cg_keys, cg_cnt;     // cg_cnt: [n_cells] counts | total | big list (1 + n_active) | chain nodes handed out
+    int cam_node_first = 0, cam_node_cap = 0;       // region of the closest-hit rays' node array kept for the camera grid's chains
     PhaseTimer* timer = nullptr;     // owned (yrt_render.cu)
 };
 
 int build_device_scene(HostScene& hs, int device, DevScene& ds);
+// enqueues the build of one apex grid on `st` (no host synchronisation): a.cnt / a.total / a.big are cleared first
+int pgrid_build_enqueue(const PGridArrays& a, cudaStream_t st);
+// this frame's camera grid (ds.cg_*): enqueued on `st`; `out` is what the primary-ray kernel reads (nx = 0: none)
+int camera_grid_enqueue(DevScene& ds, const camera_k& cam, int width, int height, cudaStream_t st, GridRef* out);
 void destroy_device_scene(DevScene& ds);
 
 struct RenderParams {

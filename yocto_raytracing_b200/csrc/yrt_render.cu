@@ -49,6 +49,7 @@ struct BatchParams {
     int lr0;                      // first packed local row of the batch
     int tile_rows, rank, world;
     size_t cap_slots;             // stride of per-light / per-depth planes
+    GridRef cam_grid;             // apex grid of this frame's camera (nx = 0: none), read by the primary rays only
 };
 
 // slot -> (i, j, ii, jj)
@@ -114,9 +115,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_close
         if (!alive) continue;
         unsigned slot;
         ray3 ray;
+        int i = 0, j = 0;
         if (PRIMARY) {
             slot = idx;
-            int i, j, ii, jj;
+            int ii, jj;
             slot_to_sample(bp, slot, i, j, ii, jj);
             float u, v;
             sample_uv(i, j, ii, jj, bp.samples, bp.width, bp.height, u, v);
@@ -127,7 +129,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_close
             ray.o = xyz(o); ray.d = xyz(d); ray.tmin = o.w; ray.tmax = d.w;
         }
         HitRec h;
-        trace_ray<false>(sv, ray, h, stack, YRT_CTR_PTR);
+        if (PRIMARY) trace_camera_ray(sv, bp.cam_grid, ray, i, j, h, stack, YRT_CTR_PTR);
+        else trace_ray<false>(sv, ray, h, stack, YRT_CTR_PTR);
 #if YRT_COUNTERS
         rays_++;
 #endif
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace_close
 // per hit instead of once per (hit, light).
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS_ANY) k_trace_any_lights(SceneView sv, size_t cap_slots, const int* __restrict__ act,
                                                                     const float4* __restrict__ hit, const float4* __restrict__ P,
-                                                                    unsigned* __restrict__ vis, WorkDist wd, unsigned long long* dctr) {
+                                                                    unsigned* __restrict__ vis, WorkDist wd, unsigned long long* dctr, const LightGrids lg) {
     const int lane = threadIdx.x & 31;
     const unsigned n_items = item_count(wd);
     int stack[STACK_INTS_ANY];
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS_ANY) k_trace_a
             light_vector(sv, k, p, l, r, ke);
             ray3 sr = shadow_ray(p, l, r);
             HitRec hr;
-            bool occ = trace_ray<true>(sv, sr, hr, stack, YRT_CTR_PTR);
+            const bool occ = trace_shadow_ray(sv, lg, k, sr, hr, stack, YRT_CTR_PTR);
 #if YRT_COUNTERS
             rays_++;
 #endif
@@ -540,9 +543,10 @@ struct CounterRing {
 };
 
 // batch of rows [lr0, lr0+nrows) of the rank's packed rows; primary hits only when primary_only
-static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0, int nrows, size_t cap_slots, float4* d_out, cudaStream_t st,
+static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, const GridRef& cam_grid, int lr0, int nrows, size_t cap_slots, float4* d_out, cudaStream_t st,
                      PhaseTimer& pt, CounterRing& ring, int depth_cap, bool reflective, bool primary_only) {
     BatchParams bp;
+    bp.cam_grid = cam_grid;
     bp.cam = rp.cam; bp.amb = rp.amb; bp.width = rp.width; bp.height = rp.height; bp.samples = rp.samples;
     bp.spp = rp.samples * rp.samples; bp.lr0 = lr0; bp.tile_rows = rp.tile_rows; bp.rank = rp.rank; bp.world = rp.world;
     bp.cap_slots = cap_slots;
@@ -590,7 +594,7 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, int lr0
             YRT_TRY(ring.get(&ctr));
             pt.begin(CAT_ANY);
             k_trace_any_lights<<<grid_of(ds.grid_any, n), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(), w.vis.as<unsigned>(),
-                                                                                 workdist_linear(ctr, n, n_dev), dctr ? dctr + 2 * YRT_DCTR_WORDS : nullptr);
+                                                                                 workdist_linear(ctr, n, n_dev), dctr ? dctr + 2 * YRT_DCTR_WORDS : nullptr, ds.light_grids);
             pt.end();
         }
         pt.begin(CAT_SHADE);
@@ -717,6 +721,11 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
     const size_t frame_span = pt.spans.size();
     CounterRing ring[4];
     YRT_TRY(ring[0].init(ds.ws, st));
+    // this frame's camera grid (yrt_pgrid.cuh): built on the frame's stream, inside its time, before the pipelines fork
+    GridRef cam_grid;
+    pt.begin(CAT_OTHER);
+    YRT_TRY(camera_grid_enqueue(ds, rp.cam, rp.width, rp.height, st, &cam_grid));
+    pt.end();
     if (n_pipes > 1) YRT_CUDA(cudaEventRecord(ds.ev_fork, st));
     for (int k = 1; k < n_pipes; k++) {
         YRT_CUDA(cudaStreamWaitEvent(ds.aux_stream[k - 1], ds.ev_fork, 0));
@@ -728,7 +737,7 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
         int pipe = b % n_pipes;
         Workspace& w = pipe ? ds.ws_aux[pipe - 1] : ds.ws;
         pt.st = pipe ? ds.aux_stream[pipe - 1] : st;
-        YRT_TRY(run_batch(ds, w, rp, lr0, nrows, w.cap_slots, d_out, pt.st, pt, ring[pipe], depth_cap, reflective, false));
+        YRT_TRY(run_batch(ds, w, rp, cam_grid, lr0, nrows, w.cap_slots, d_out, pt.st, pt, ring[pipe], depth_cap, reflective, false));
         if (to_host && !rp.scatter && !pt.on) YRT_TRY(rows_to_host(rp, d_out, lr0, nrows, pt.st));
     }
     pt.st = st;
@@ -834,10 +843,12 @@ int trace_primary_device(DevScene& ds, const RenderParams& rp_in, int32_t* h_ids
     PhaseTimer pt;
     CounterRing ring;
     YRT_TRY(ring.init(ds.ws, st));
+    GridRef cam_grid;
+    YRT_TRY(camera_grid_enqueue(ds, rp.cam, rp.width, rp.height, st, &cam_grid));
     for (int lr0 = 0; lr0 < rp.height; lr0 += batch_rows) {
         int nrows = std::min(batch_rows, rp.height - lr0);
         size_t n = (size_t)nrows * rp.width * spp;
-        YRT_TRY(run_batch(ds, ds.ws, rp, lr0, nrows, ds.ws.cap_slots, nullptr, st, pt, ring, 1, false, true));
+        YRT_TRY(run_batch(ds, ds.ws, rp, cam_grid, lr0, nrows, ds.ws.cap_slots, nullptr, st, pt, ring, 1, false, true));
         k_hit_ids<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ds.view, ds.ws.hit.as<float4>(), ds.ws.P.as<float4>(), (int)n, d_ids.as<int>(),
                                                              d_dist.as<float>(), d_uv.as<float>());
         YRT_CUDA(cudaGetLastError());

@@ -177,6 +177,7 @@ struct SceneView {
                                 // one array and one index space, so a node visit needs no level test
     const float4* nodes4;       // the same tree as 4-wide records (8 float4 each), same indices
     const float4* inst_recs;    // 4 per instance, TLAS leaf order
+    const float4* inst_box;     // 2 per instance, same order: world box as (centre, inflated half-extent) — what the apex grids are built from (yrt_pgrid.cuh)
     const float4* prim_recs;    // 3 per prim, BLAS leaf order
     const float4* prim_attrs;   // YRT_ATTR_STRIDE per prim: normals + uv (4), triangles: v1, v2 (the trace record holds edges)
     const float4* mat_recs;     // 4 per material

@@ -12,6 +12,7 @@
 // The same code runs on the device (kernels in yrt_render.cu) and on the host (tools/host_emu,
 // tests only).
 #pragma once
+#include "yrt_pgrid.cuh"
 #include "yrt_scene.cuh"
 
 #ifndef YRT_POP_CULL
@@ -121,7 +122,9 @@ struct Tracer {
 
     YRT_HD bool done() const { return cur == YRT_REF_DONE; }
 
-    YRT_HD void begin(const SceneView& sv, const ray3& wray, int* stack) {
+    // root: the node the walk starts from — the instance tree's root, or the root of the ray's cell in an apex grid
+    // (yrt_pgrid.cuh: a chain of instance-level nodes over the few instances a ray of that cell can touch)
+    YRT_HD void begin(const SceneView& sv, const ray3& wray, int* stack, int root) {
         hit.si = -1; hit.prim = -1; hit.w1 = hit.w2 = 0.f; hit.dist = 0.f;
         o = wray.o; d = wray.d;
         sr = make_slabray(o, EXACT ? inv3(d) : inv3_slab(d));
@@ -130,7 +133,7 @@ struct Tracer {
         stk = stack; sp = 0;
         push(YRT_REF_DONE, -FLT_MAX);
         si = -1; kind = 0; top = true; found = false;
-        cur = sv.n_active_instances > 0 ? sv.tlas_root : YRT_REF_DONE;
+        cur = sv.n_active_instances > 0 ? root : YRT_REF_DONE;
     }
 
     // Stack entries.  Closest hit (YRT_POP_CULL): (reference, entry distance of its box); the pop re-applies the accept
@@ -346,9 +349,9 @@ struct Tracer {
 #define YRT_EXACT_SLAB_INVD 4096.0f
 
 template <bool ANY, bool EXACT>
-YRT_HD bool trace_ray_impl(const SceneView& sv, const ray3& wray, HitRec& hit, int* stack, TraceCounters* ctr) {
+YRT_HD bool trace_ray_impl(const SceneView& sv, const ray3& wray, HitRec& hit, int* stack, TraceCounters* ctr, int root) {
     Tracer<ANY, EXACT> t;
-    t.begin(sv, wray, stack);
+    t.begin(sv, wray, stack, root);
     for (;;) {
         t.nodes(sv, stack, ctr);
         if (t.done()) break;
@@ -358,16 +361,43 @@ YRT_HD bool trace_ray_impl(const SceneView& sv, const ray3& wray, HitRec& hit, i
     return t.found;
 }
 
+// walk from `root` (see Tracer::begin)
 template <bool ANY>
-YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* stack, TraceCounters* ctr) {
+YRT_HD bool trace_ray_from(const SceneView& sv, const ray3& wray, HitRec& hit, int* stack, TraceCounters* ctr, int root) {
     // decided on the world-space direction (instance frames of the configs are pure translations, so the local
     // direction is the same; a rotated instance may still meet a large pad — slower, never wrong).
     // |1/d| > 4096  <=>  |d| < 2^-12 (the correctly rounded quotient is monotonic and exact at the power of two)
     float ax = fabsf(wray.d.x), ay = fabsf(wray.d.y), az = fabsf(wray.d.z);
     float m = fminf(fminf(ax, ay), az), big = fmaxf(fmaxf(ax, ay), az);
     // (directions beyond 1e30 would underflow the flush-to-zero MUFU reciprocal: exact path as well; NaN goes there too)
-    if (!(m >= 1.0f / YRT_EXACT_SLAB_INVD && big <= 1.0e30f)) return trace_ray_impl<ANY, true>(sv, wray, hit, stack, ctr);
-    return trace_ray_impl<ANY, false>(sv, wray, hit, stack, ctr);
+    if (!(m >= 1.0f / YRT_EXACT_SLAB_INVD && big <= 1.0e30f)) return trace_ray_impl<ANY, true>(sv, wray, hit, stack, ctr, root);
+    return trace_ray_impl<ANY, false>(sv, wray, hit, stack, ctr, root);
+}
+template <bool ANY>
+YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* stack, TraceCounters* ctr) {
+    return trace_ray_from<ANY>(sv, wray, hit, stack, ctr, sv.tlas_root);
+}
+
+YRT_HD int ld_root(const int* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// closest hit of the camera ray of pixel (i, j): starts at the root of the pixel's cell when the frame has a camera grid
+YRT_HD void trace_camera_ray(const SceneView& sv, const GridRef& cg, const ray3& ray, int i, int j, HitRec& h, int* stack, TraceCounters* ctr) {
+    int root = sv.tlas_root;
+    if (cg.nx > 0) root = ld_root(cg.roots + (size_t)(j >> cg.shift) * cg.nx + (i >> cg.shift));
+    trace_ray_from<false>(sv, ray, h, stack, ctr, root);
+}
+
+// occlusion of the shadow ray `sr` towards light k: starts at the root of the cell that -d falls into, seen from the light
+YRT_HD bool trace_shadow_ray(const SceneView& sv, const LightGrids& lg, int k, const ray3& sr, HitRec& hr, int* stack, TraceCounters* ctr) {
+    int root = sv.tlas_root;
+    if (k < YRT_MAX_LIGHT_GRIDS && lg.g[k].nx > 0) root = ld_root(lg.g[k].roots + pgrid_cube_cell(-sr.d, lg.g[k].nx));
+    return trace_ray_from<true>(sv, sr, hr, stack, ctr, root);
 }
 
 }  // namespace yrt
