@@ -91,30 +91,38 @@ void emu_lbvh(int n, int n_seg, std::vector<float4>& lo, std::vector<float4>& hi
 // one apex grid built by serial loops over the item functions of yrt_pgrid.cuh (the device runs the same functions per thread)
 struct EmuGrid {
     PGridDesc d;
-    std::vector<int> roots;
+    std::vector<int> roots;           // chain form
+    std::vector<int2> cells;          // list form
+    std::vector<float4> entries;
     long long n_entries = 0, n_fallback_cells = 0, n_nodes = 0;
     GridRef ref() const {
         GridRef g = gridref_none();
-        if (d.mode != 0) { g.roots = roots.data(); g.nx = d.nx; g.shift = 0; }
+        if (d.mode != 0) { g.roots = roots.data(); g.cells = cells.data(); g.entries = entries.data(); g.nx = d.nx; g.shift = 0; }
         return g;
     }
 };
 
-// chain nodes go to records [node_first, node_first + node_cap) of `nodes` (arity W); *node_total counts them (shared by the lights)
+// chain form (nodes != null): chain nodes go to records [node_first, node_first + node_cap) of `nodes` (arity W); *node_total counts
+// them (shared by the lights).  List form (nodes == null): out.cells + out.entries.
 void emu_build_grid(const PGridDesc& d, const std::vector<float4>& inst_box, int n_inst, int arity, float4* nodes, int node_first, int node_cap,
                     int* node_total, int tlas_root, EmuGrid& out) {
     out.d = d;
     out.roots.assign(std::max(d.n_cells, 1), tlas_root);
+    out.cells.assign(std::max(d.n_cells, 1), int2{0, 0});
+    out.entries.assign(nodes ? 2 : 2 * (size_t)std::max(d.capacity, 1), mk4(0, 0, 0, 0));
     out.n_entries = out.n_fallback_cells = out.n_nodes = 0;
     if (d.mode == 0) return;
     std::vector<int> cnt((size_t)d.n_cells + 2 + n_inst, 0);
-    std::vector<int2> cells(std::max(d.n_cells, 1), int2{0, 0});
+    std::vector<int2>& cells = out.cells;
     std::vector<unsigned long long> keys(std::max(d.capacity, 1));
+    int dummy_total = 0;
+    if (!node_total) node_total = &dummy_total;
     PGridArrays a;
     a.d = d; a.inst_box = inst_box.data(); a.n_inst = n_inst;
     a.cnt = cnt.data(); a.total = a.cnt + d.n_cells; a.big = a.cnt + d.n_cells + 1;
     a.cells = cells.data(); a.keys = keys.data(); a.roots = out.roots.data();
     a.nodes = nodes; a.arity = arity; a.node_first = node_first; a.node_capacity = node_cap; a.node_total = node_total;
+    a.as_list = nodes ? 0 : 1; a.entries = out.entries.data();
     a.tlas_root = tlas_root; a.tlas_root_dev = nullptr;
     const int before = *node_total;
     for (int fill = 0; fill < 2; fill++) {
@@ -125,7 +133,7 @@ void emu_build_grid(const PGridDesc& d, const std::vector<float4>& inst_box, int
     for (int c = 0; c < d.n_cells; c++) pgrid_emit_item(a, c);
     out.n_entries = *a.total;
     out.n_nodes = *node_total - before;
-    for (int c = 0; c < d.n_cells; c++) out.n_fallback_cells += cells[c].y < 0 || (cells[c].y > 0 && out.roots[c] == tlas_root);
+    for (int c = 0; c < d.n_cells; c++) out.n_fallback_cells += cells[c].y < 0 || (nodes && cells[c].y > 0 && out.roots[c] == tlas_root);
 }
 
 struct EmuScene {
@@ -136,7 +144,7 @@ struct EmuScene {
     int cam_shift = -1;                   // >= 0: trace_primary / render build a camera grid per call
     float extent = 0.f;
     int tree_nodes = 0;                   // records of the two trees in either node array; the grids' chain nodes follow
-    int light_node_cap = 0, cam_node_first = 0, cam_node_cap = 0;
+    int light_node_cap = 0;
     EmuLbvh blas, tlas;
     std::vector<float4> prim_recs, prim_attrs, inst_recs;
     std::vector<int> prim_rank, inst_rank;
@@ -278,13 +286,11 @@ camera_k emu_camera(const yrt_camera* cam) {
 // the camera grid of one call (mirrors camera_grid_enqueue in yrt_build.cu)
 void emu_camera_grid(EmuScene& es, const camera_k& ck, int width, int height, EmuGrid& g) {
     g.d.mode = 0;
-    if (es.cam_shift < 0 || !es.hs.all_rigid || es.view.n_active_instances <= 0 || es.cam_node_cap <= 0) return;
+    if (es.cam_shift < 0 || !es.hs.all_rigid || es.view.n_active_instances <= 0) return;
     const float reach = es.extent + fmaxf(fmaxf(fabsf(ck.frame.o.x), fabsf(ck.frame.o.y)), fabsf(ck.frame.o.z));
     const long long cells = (long long)((width + (1 << es.cam_shift) - 1) >> es.cam_shift) * ((height + (1 << es.cam_shift) - 1) >> es.cam_shift);
     PGridDesc d = pgrid_camera_desc(ck, width, height, es.cam_shift, reach, (int)(16 * cells + 65536));
-    int total = 0;
-    std::vector<float4>& arr = YRT_WIDE_CLOSEST == 4 ? es.nodes4 : es.nodes2;
-    emu_build_grid(d, es.inst_box, es.view.n_active_instances, YRT_WIDE_CLOSEST, arr.data(), es.cam_node_first, es.cam_node_cap, &total, es.view.tlas_root, g);
+    emu_build_grid(d, es.inst_box, es.view.n_active_instances, 0, nullptr, 0, 0, nullptr, es.view.tlas_root, g);
 }
 GridRef emu_camera_ref(const EmuScene& es, const EmuGrid& g) {
     GridRef r = g.ref();
@@ -312,9 +318,7 @@ int emu_set_grids(void* p, int light_R, int cam_shift, int64_t* stats) {
     // room for the chain nodes behind the trees (same regions as build_device_scene)
     const int n_grids = lights_on ? std::min(n_lights, YRT_MAX_LIGHT_GRIDS) : 0;
     es->light_node_cap = n_grids ? n_grids * 6 * light_R * light_R * 3 / 4 + 1024 : 0;
-    es->cam_node_cap = cam_shift >= 0 ? 1 << 18 : 0;
-    es->cam_node_first = es->tree_nodes + (YRT_WIDE_CLOSEST == YRT_WIDE_ANY ? es->light_node_cap : 0);
-    const size_t total_nodes = (size_t)es->tree_nodes + es->light_node_cap + es->cam_node_cap;
+    const size_t total_nodes = (size_t)es->tree_nodes + es->light_node_cap;
     es->nodes2.resize(YRT_NODE_STRIDE(2) * total_nodes, mk4(0, 0, 0, 0));
     es->nodes4.resize(YRT_NODE_STRIDE(4) * total_nodes, mk4(0, 0, 0, 0));
     es->view.nodes2 = es->nodes2.data(); es->view.nodes4 = es->nodes4.data();

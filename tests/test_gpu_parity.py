@@ -569,11 +569,13 @@ def test_apex_grids_do_not_change_the_frame(gpu, monkeypatch, maker, w, h, s):
     instance-level nodes instead of the instance tree's root) must not change a single bit: frame, hit ids, distances and
     ray counts with the grids (default), without them, and with other cell sizes."""
     flat = maker()
+    monkeypatch.setenv("YRT_PGRID_MIN_INSTANCES", "1")         # grids on small scenes too
     with gpu.Scene(flat) as scn:
         a, sa = scn.render(w, h, s, 0.1)
         ia, da, _ = scn.trace_primary(w, h, s)
     for env in ({"YRT_PGRID": "0"}, {"YRT_CAM_CELL_SHIFT": "0", "YRT_LIGHT_GRID_R": "16"}, {"YRT_CAM_CELL_SHIFT": "5", "YRT_LIGHT_GRID_R": "256"},
-                {"YRT_CAM_GRID_NODES": "64", "YRT_LIGHT_GRID_R": "8"}):      # (64 chain nodes: most cells fall back to the tree's root)
+                {"YRT_PGRID_MIN_INSTANCES": "1000000"}, {"YRT_LIGHT_GRID_R": "8", "YRT_CAM_CELL_SHIFT": "8"}):
+        monkeypatch.setenv("YRT_PGRID_MIN_INSTANCES", "1")
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         with gpu.Scene(flat) as scn:

@@ -478,7 +478,9 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
     // identity rotation; other lights, lights beyond the first YRT_MAX_LIGHT_GRIDS and scenes with non-rigid instance
     // frames keep the instance tree.
     const int n_lights = (int)hs.light_inst.size();
-    ds.grids_allowed = hs.all_rigid && env_or("YRT_PGRID", 1, 0, 1) != 0 && na > 0;
+    // (an instance tree of a few dozen leaves is 5 levels deep: nothing to save, and the per-frame camera grid would cost more than it gains;
+    //  YRT_PGRID_MIN_INSTANCES moves the threshold, the tests set it to 1 to exercise the grids on small scenes)
+    ds.grids_allowed = hs.all_rigid && env_or("YRT_PGRID", 1, 0, 1) != 0 && na >= env_or("YRT_PGRID_MIN_INSTANCES", 32, 1, 1 << 30);
     ds.extent = hs.extent;
     int light_R = env_or("YRT_LIGHT_GRID_R", -1, -1, 1024);
     if (light_R < 0) { light_R = 8; while (light_R < 256 && light_R * light_R < na) light_R *= 2; }   // ~ one cell per instance and face
@@ -502,18 +504,11 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
         lg_on[k] = true;
         n_light_grids++;
     }
-    // chain nodes of the grids live behind the two trees in the node arrays (one index space per array).  The lights' chains go
-    // into the array the any-hit rays walk, the camera's (rebuilt per frame, room reserved here) into the closest-hit rays';
-    // if both ray kinds walk the same array the two regions follow each other, otherwise both start right behind the trees.
+    // the chain nodes of the light grids live behind the two trees in the node array the any-hit rays walk
     const int grid_node_first = nb_int + nt_int + 2;
     const int light_node_cap = n_light_grids ? (int)std::min<long long>((long long)n_light_grids * 6 * light_R * light_R * 3 / 4 + 1024, 1 << 26) : 0;
-    const int cam_node_cap = ds.grids_allowed ? env_or("YRT_CAM_GRID_NODES", 1 << 18, 0, 1 << 24) : 0;
-    const int cam_node_first = grid_node_first + (YRT_WIDE_CLOSEST == YRT_WIDE_ANY ? light_node_cap : 0);
-    const size_t nodes_any = (size_t)grid_node_first + light_node_cap + (YRT_WIDE_CLOSEST == YRT_WIDE_ANY ? cam_node_cap : 0);
-    const size_t nodes_closest = YRT_WIDE_CLOSEST == YRT_WIDE_ANY ? nodes_any : (size_t)cam_node_first + cam_node_cap;
-    const size_t n_nodes4 = std::max<size_t>(grid_node_first, std::max(YRT_WIDE_ANY == 4 ? nodes_any : 0, YRT_WIDE_CLOSEST == 4 ? nodes_closest : 0));
-    const size_t n_nodes2 = std::max<size_t>(grid_node_first, std::max(YRT_WIDE_ANY == 2 ? nodes_any : 0, YRT_WIDE_CLOSEST == 2 ? nodes_closest : 0));
-    ds.cam_node_first = cam_node_first; ds.cam_node_cap = cam_node_cap;
+    const size_t n_nodes4 = (size_t)grid_node_first + (YRT_WIDE_ANY == 4 ? light_node_cap : 0);
+    const size_t n_nodes2 = (size_t)grid_node_first + (YRT_WIDE_ANY == 2 ? light_node_cap : 0);
     int* d_light_node_total = nullptr;
     LbvhIo bo, to;
     const int tl_sf[2] = {0, na};
@@ -560,6 +555,7 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
             a.keys = tmp.take<unsigned long long>((size_t)a.d.capacity);
             a.inst_box = d_inst_box;
             a.n_inst = na;
+            a.as_list = 0; a.entries = nullptr;
             a.arity = YRT_WIDE_ANY; a.nodes = YRT_WIDE_ANY == 4 ? d_nodes4 : d_nodes2;
             a.node_first = grid_node_first; a.node_capacity = light_node_cap;
         }
@@ -643,7 +639,8 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
         lga[k].tlas_root_dev = to.seg_root;      // (the root is only known on the device at this point)
         YRT_TRY(pgrid_build_enqueue(lga[k], st));
         GridRef& g = ds.light_grids.g[k];
-        g.roots = lga[k].roots; g.nx = light_R; g.shift = 0;
+        g = gridref_none();
+        g.roots = lga[k].roots; g.nx = light_R;
     }
     YRT_CUDA(cudaGetLastError());
     const double t_enqueued = now_ms();
@@ -718,25 +715,23 @@ int camera_grid_enqueue(DevScene& ds, const camera_k& cam, int width, int height
     const float reach = ds.extent + fmaxf(fmaxf(fabsf(cam.frame.o.x), fabsf(cam.frame.o.y)), fabsf(cam.frame.o.z));
     if (!(reach < 1.0e18f)) return YRT_OK;
     const long long cells = (long long)((width + (1 << shift) - 1) >> shift) * ((height + (1 << shift) - 1) >> shift);
-    if (cells > (1ll << 24) || ds.cam_node_cap <= 0) return YRT_OK;
-    const int capacity = (int)std::min<long long>(16 * cells + 65536, 1ll << 28);
+    if (cells > (1ll << 24)) return YRT_OK;
+    const int capacity = (int)std::min<long long>(16 * cells + 65536, 1ll << 26);
     PGridArrays a;
     a.d = pgrid_camera_desc(cam, width, height, shift, reach, capacity);
     if (a.d.mode == 0) return YRT_OK;
-    YRT_TRY(ds.cg_roots.alloc(sizeof(int) * (size_t)a.d.n_cells, ds.device));
     YRT_TRY(ds.cg_cells.alloc(sizeof(int2) * (size_t)a.d.n_cells, ds.device));
+    YRT_TRY(ds.cg_entries.alloc(sizeof(float4) * 2 * (size_t)capacity, ds.device));
     YRT_TRY(ds.cg_keys.alloc(sizeof(unsigned long long) * (size_t)capacity, ds.device));
-    YRT_TRY(ds.cg_cnt.alloc(sizeof(int) * ((size_t)a.d.n_cells + 3 + (size_t)ds.n_active), ds.device));
+    YRT_TRY(ds.cg_cnt.alloc(sizeof(int) * ((size_t)a.d.n_cells + 2 + (size_t)ds.n_active), ds.device));
     a.inst_box = ds.view.inst_box; a.n_inst = ds.n_active;
     a.cnt = ds.cg_cnt.as<int>(); a.total = a.cnt + a.d.n_cells; a.big = a.cnt + a.d.n_cells + 1;
-    a.node_total = a.big + 1 + ds.n_active;
-    a.cells = ds.cg_cells.as<int2>(); a.keys = ds.cg_keys.as<unsigned long long>(); a.roots = ds.cg_roots.as<int>();
-    a.arity = YRT_WIDE_CLOSEST; a.nodes = const_cast<float4*>(YRT_WIDE_CLOSEST == 4 ? ds.view.nodes4 : ds.view.nodes2);
-    a.node_first = ds.cam_node_first; a.node_capacity = ds.cam_node_cap;
+    a.cells = ds.cg_cells.as<int2>(); a.keys = ds.cg_keys.as<unsigned long long>();
+    a.as_list = 1; a.entries = ds.cg_entries.as<float4>();
+    a.roots = nullptr; a.nodes = nullptr; a.arity = 0; a.node_first = a.node_capacity = 0; a.node_total = nullptr;
     a.tlas_root = ds.view.tlas_root; a.tlas_root_dev = nullptr;
-    YRT_CUDA(cudaMemsetAsync(a.node_total, 0, sizeof(int), st));
     YRT_TRY(pgrid_build_enqueue(a, st));
-    out->roots = a.roots; out->nx = a.d.nx; out->shift = shift;
+    out->cells = a.cells; out->entries = a.entries; out->nx = a.d.nx; out->shift = shift;
     return YRT_OK;
 }
 

@@ -119,8 +119,7 @@ struct DevScene {
     int light_grid_R = 0;
     bool grids_allowed = false;      // rigid frames only: the lists are sorted and cut by world-space distances
     float extent = 0.f;
-    DevBuf cg_roots, cg_cells, cg_keys, cg_cnt;     // cg_cnt: [n_cells] counts | total | big list (1 + n_active) | chain nodes handed out
-    int cam_node_first = 0, cam_node_cap = 0;       // region of the closest-hit rays' node array kept for the camera grid's chains
+    DevBuf cg_cells, cg_entries, cg_keys, cg_cnt;   // cg_cnt: [n_cells] counts | total | big list (1 + n_active)
     PhaseTimer* timer = nullptr;     // owned (yrt_render.cu)
 };
 

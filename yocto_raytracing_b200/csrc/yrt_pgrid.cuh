@@ -33,13 +33,15 @@ namespace yrt {
 
 // what a traversal kernel needs to find a ray's starting node (kernel parameter: lives in the constant bank)
 struct GridRef {
-    const int* roots;   // per cell: node reference to start from
-    int nx;             // cells per row (camera) / per face edge (cube); 0: no grid, the rays start at the instance tree's root
-    int shift;          // camera: log2(pixels per cell edge)
+    const int* roots;       // chain form (light grids): per cell the node reference to start from
+    const int2* cells;      // list form (camera grid): per cell (first entry, count); count < 0: the cell is not served
+    const float4* entries;  // list form: 2 per entry = (box centre | instance slot), (inflated half-extent | distance bound)
+    int nx;                 // cells per row (camera) / per face edge (cube); 0: no grid, the rays start at the instance tree's root
+    int shift;              // camera: log2(pixels per cell edge)
 };
 struct LightGrids { GridRef g[YRT_MAX_LIGHT_GRIDS]; };
 
-YRT_HD GridRef gridref_none() { GridRef g; g.roots = nullptr; g.nx = 0; g.shift = 0; return g; }
+YRT_HD GridRef gridref_none() { GridRef g; g.roots = nullptr; g.cells = nullptr; g.entries = nullptr; g.nx = 0; g.shift = 0; return g; }
 
 // build-time description of one grid
 struct PGridDesc {
@@ -67,7 +69,10 @@ struct PGridArrays {
     int2* cells;                   // [n_cells] (first key, count) of each cell's list; count < 0: not served
     unsigned long long* keys;      // [capacity] (distance bound bits << 32 | slot), unsorted
     int* big;                      // [1 + n_inst] number and slots of the instances that cover more than YRT_PGRID_BIG cells
-    // output
+    // output, list form (as_list != 0): cells + entries, the candidates of a cell in order, each with its own box
+    int as_list;
+    float4* entries;               // [2 * capacity]
+    // output, chain form
     int* roots;                    // [n_cells]
     float4* nodes;                 // the scene's node array of arity `arity` (record i at nodes + stride * i)
     int arity;                     // 2 or 4
@@ -381,8 +386,42 @@ YRT_HD void pgrid_emit_item(const PGridArrays& a, int cell) {
     }
     a.roots[cell] = rest_ref;
 }
+// List form of one cell: its candidates ordered by (distance bound, slot), each with the part of its box the cell's rays
+// can reach; the traversal takes them in this order (Tracer<…, GRID>::next_candidate) and stops at the first whose bound
+// lies beyond what the ray has already found.
+YRT_HD void pgrid_emit_list_item(const PGridArrays& a, int cell) {
+    const int2 c = a.cells[cell];
+    if (c.y <= 0) return;
+    unsigned long long* k = a.keys + c.x;
+    const int n = c.y;
+    for (int i = 1; i < n; i++) {
+        const unsigned long long v = k[i];
+        int j = i - 1;
+        while (j >= 0 && k[j] > v) { k[j + 1] = k[j]; j--; }
+        k[j + 1] = v;
+    }
+    const int per_face = a.d.nx * a.d.ny, face = cell / per_face, in_face = cell - face * per_face;
+    const PCellDirs cd = pgrid_cell_dirs(a.d, face, in_face % a.d.nx, in_face / a.d.nx);
+    for (int i = 0; i < n; i++) {
+        const int slot = (int)(unsigned)(k[i] & 0xffffffffull);
+        const nodebox wb = pgrid_inst_nodebox(a, slot);
+        const vec3 wlo = mk3(wb.cx - wb.hx, wb.cy - wb.hy, wb.cz - wb.hz), whi = mk3(wb.cx + wb.hx, wb.cy + wb.hy, wb.cz + wb.hz);
+        vec3 clo = wlo - a.d.apex, chi = whi - a.d.apex;
+        if (pgrid_box_distance(a.d, wlo, whi) >= a.d.near_all) pgrid_cell_clip(a.d, cd, clo, chi, clo, chi);
+        clo = clo + a.d.apex; chi = chi + a.d.apex;
+        nodebox cb;
+        box_center_half(fmaxf(clo.x, wlo.x), fminf(chi.x, whi.x), cb.cx, cb.hx);
+        box_center_half(fmaxf(clo.y, wlo.y), fminf(chi.y, whi.y), cb.cy, cb.hy);
+        box_center_half(fmaxf(clo.z, wlo.z), fminf(chi.z, whi.z), cb.cz, cb.hz);
+        float4* e = a.entries + 2 * ((size_t)c.x + i);
+        e[0] = mk4(cb.cx, cb.cy, cb.cz, int_as_float(slot));
+        e[1] = mk4(cb.hx, cb.hy, cb.hz, int_as_float((int)(unsigned)(k[i] >> 32)));
+    }
+}
 YRT_HD void pgrid_emit_item(const PGridArrays& a, int cell) {
-    if (a.arity == 4) pgrid_emit_item<4>(a, cell); else pgrid_emit_item<2>(a, cell);
+    if (a.as_list) pgrid_emit_list_item(a, cell);
+    else if (a.arity == 4) pgrid_emit_item<4>(a, cell);
+    else pgrid_emit_item<2>(a, cell);
 }
 
 // ---- descriptions (host) ----------------------------------------------------------------------------------------------

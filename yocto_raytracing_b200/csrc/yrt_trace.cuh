@@ -107,7 +107,12 @@ YRT_HD vec3 inv3_slab(const vec3& d) { return mk3(rcp_slab(d.x), rcp_slab(d.y), 
 // if-if loop the node path and the leaf paths would be issued in every iteration for partial warps;
 // the kernels are issue bound, so that matters (profiles/).  Being resumable lets the persistent
 // kernels hand a finished lane a new ray while the rest of the warp keeps going.
-template <bool ANY, bool EXACT = false>
+//
+// GRID: the ray belongs to an apex grid in list form (yrt_pgrid.cuh, the camera's) — its instance level is the candidate
+// list of its cell: entries are taken in list order (nearest first), each one's box is tested with the same slab test,
+// and the instances it touches are entered; only the shapes' trees are walked.  The top level is the state
+// cur == YRT_REF_SENTINEL ("take the next candidate"), reached at the start and whenever the walk of an instance ends.
+template <bool ANY, bool EXACT = false, bool GRID = false>
 struct Tracer {
     vec3 wo, wd;          // world-space ray
     slabray wsr;
@@ -118,6 +123,7 @@ struct Tracer {
     int* stk;             // the lane's stack (local memory)
     int sp;               // next free word of it; the first entry is a YRT_REF_DONE guard, so a pop needs no emptiness test
     bool top, found;
+    int gi, gend;         // GRID: next and end entry of the cell's candidate list
     HitRec hit;
 
     YRT_HD bool done() const { return cur == YRT_REF_DONE; }
@@ -133,7 +139,13 @@ struct Tracer {
         stk = stack; sp = 0;
         push(YRT_REF_DONE, -FLT_MAX);
         si = -1; kind = 0; top = true; found = false;
+        gi = gend = 0;
         cur = sv.n_active_instances > 0 ? root : YRT_REF_DONE;
+    }
+    // GRID: the ray's candidates are entries [first, first + count) of its grid
+    YRT_HD void begin_list(const SceneView& sv, const ray3& wray, int* stack, int first, int count) {
+        begin(sv, wray, stack, YRT_REF_SENTINEL);
+        gi = first; gend = first + count;
     }
 
     // Stack entries.  Closest hit (YRT_POP_CULL): (reference, entry distance of its box); the pop re-applies the accept
@@ -167,7 +179,7 @@ struct Tracer {
             top = true;
             if (EXACT) o = wo;
             sr = wsr;
-            pop_entry();
+            if (!GRID) pop_entry();   // GRID: cur stays the sentinel = "next candidate of the list" (next_candidate())
         }
     }
     YRT_HD void push(int ref, float e) {
@@ -311,12 +323,47 @@ struct Tracer {
         while (cur >= 0) visit(sv, stack, ctr);
     }
 
+    // GRID, top level: candidates in list order until one's box is touched (-> enter it) or the list ends / the rest lies
+    // beyond the ray's reach (-> done).  The .w of an entry's second quad is a lower bound of the distance from the apex to
+    // anything of the instance a ray of this cell can reach; camera rays measure t from the apex: a candidate whose bound
+    // exceeds tmax cannot be hit any more, and neither can the ones sorted behind it.
+    YRT_HD void next_candidate(const SceneView& sv, const GridRef& g, int* stack, TraceCounters* ctr) {
+        for (;;) {
+            if (gi >= gend) { cur = YRT_REF_DONE; return; }
+            const float4* e = g.entries + 2 * (size_t)gi;
+            const float4 e0 = ld4(e), e1 = ld4(e + 1);
+            gi++;
+            if (e1.w > tmax) { cur = YRT_REF_DONE; return; }
+            float te;
+            if (ctr) { ctr->box_tests++; ctr->tlas_box_tests++; }
+            if (slab_test_ch(wsr, tmin, tmax, e0.x, e0.y, e0.z, e1.x, e1.y, e1.z, te)) {
+                enter_instance(sv, float_as_int(e0.w), stack, ctr);
+                return;
+            }
+        }
+    }
+
     // one leaf (cur < 0 and not done)
     YRT_HD void leaf(const SceneView& sv, int* stack, TraceCounters* ctr) {
         int first = leaf_first(cur), count = leaf_count(cur);
         if (top) {
             // TLAS leaf: enter its first instance, keep the rest for later
             if (count > 1) push(make_leaf_ref(first + 1, count - 1), -FLT_MAX);
+            enter_instance(sv, first, stack, ctr);
+        } else {
+            ray3 lray;
+            lray.o = o; lray.d = d; lray.tmin = tmin; lray.tmax = tmax;
+            if (leaf_prims<ANY>(sv, kind, first, count, lray, tmax, si, hit, ctr)) {
+                found = true;
+                if (ANY) { cur = YRT_REF_DONE; return; }
+            }
+            pop();
+        }
+    }
+
+    // the ray enters instance slot `first`: exact transform_ray_inverse (scene.cpp:468), then the root of the shape's tree
+    YRT_HD void enter_instance(const SceneView& sv, int first, int* stack, TraceCounters* ctr) {
+        {
             const float4* ir = sv.inst_recs + 4 * (size_t)first;
             float4 q0, q1, q2, q3;
             q0 = ld4(ir); q1 = ld4(ir + 1); q2 = ld4(ir + 2); q3 = ld4(ir + 3);
@@ -332,14 +379,6 @@ struct Tracer {
             push(YRT_REF_SENTINEL, -FLT_MAX);
             if (ctr) { ctr->inst_entries++; if (depth_of(stack) > ctr->max_stack) ctr->max_stack = depth_of(stack); }
             cur = float_as_int(q0.w);   // BLAS root ref of the instance's shape
-        } else {
-            ray3 lray;
-            lray.o = o; lray.d = d; lray.tmin = tmin; lray.tmax = tmax;
-            if (leaf_prims<ANY>(sv, kind, first, count, lray, tmax, si, hit, ctr)) {
-                found = true;
-                if (ANY) { cur = YRT_REF_DONE; return; }
-            }
-            pop();
         }
     }
 };
@@ -386,11 +425,47 @@ YRT_HD int ld_root(const int* p) {
 #endif
 }
 
-// closest hit of the camera ray of pixel (i, j): starts at the root of the pixel's cell when the frame has a camera grid
+// rays the fused slab test cannot serve (see trace_ray_from): they walk from the tree's root with the reference's formula
+YRT_HD bool ray_needs_exact_slabs(const ray3& wray) {
+    float ax = fabsf(wray.d.x), ay = fabsf(wray.d.y), az = fabsf(wray.d.z);
+    float m = fminf(fminf(ax, ay), az), big = fmaxf(fmaxf(ax, ay), az);
+    return !(m >= 1.0f / YRT_EXACT_SLAB_INVD && big <= 1.0e30f);
+}
+
+// a ray of an apex grid in list form whose cell holds the candidates [first, first + count)
+template <bool ANY>
+YRT_HD bool trace_ray_list(const SceneView& sv, const ray3& wray, const GridRef& g, int first, int count, HitRec& hit, int* stack, TraceCounters* ctr) {
+    Tracer<ANY, false, true> t;
+    t.begin_list(sv, wray, stack, first, count);
+    for (;;) {
+        t.nodes(sv, stack, ctr);
+        if (t.done()) break;
+        if (t.cur == YRT_REF_SENTINEL) t.next_candidate(sv, g, stack, ctr);
+        else t.leaf(sv, stack, ctr);
+    }
+    hit = t.hit;
+    return t.found;
+}
+
+YRT_HD int2 ld_cell(const int2* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// closest hit of the camera ray of pixel (i, j): the candidate list of the pixel's cell replaces the instance tree when
+// the frame has a camera grid and the cell is served
 YRT_HD void trace_camera_ray(const SceneView& sv, const GridRef& cg, const ray3& ray, int i, int j, HitRec& h, int* stack, TraceCounters* ctr) {
-    int root = sv.tlas_root;
-    if (cg.nx > 0) root = ld_root(cg.roots + (size_t)(j >> cg.shift) * cg.nx + (i >> cg.shift));
-    trace_ray_from<false>(sv, ray, h, stack, ctr, root);
+    if (cg.nx > 0) {
+        const int2 c = ld_cell(cg.cells + (size_t)(j >> cg.shift) * cg.nx + (i >> cg.shift));
+        if (c.y >= 0 && !ray_needs_exact_slabs(ray)) {
+            trace_ray_list<false>(sv, ray, cg, c.x, c.y, h, stack, ctr);
+            return;
+        }
+    }
+    trace_ray<false>(sv, ray, h, stack, ctr);
 }
 
 // occlusion of the shadow ray `sr` towards light k: starts at the root of the cell that -d falls into, seen from the light
