@@ -123,6 +123,17 @@ void emu_build_grid(const PGridDesc& d, const std::vector<float4>& inst_box, int
     a.cells = cells.data(); a.keys = keys.data(); a.roots = out.roots.data();
     a.nodes = nodes; a.arity = arity; a.node_first = node_first; a.node_capacity = node_cap; a.node_total = node_total;
     a.as_list = nodes ? 0 : 1; a.entries = out.entries.data();
+    a.fixed_k = nodes ? 0 : 16;
+    if (a.fixed_k) {   // (mirrors camera_grid_enqueue: one scatter pass into the cells' own slots, one item per slot)
+        a.d.max_list = std::min(a.d.max_list, a.fixed_k);
+        keys.assign((size_t)d.n_cells * a.fixed_k, 0ull); a.keys = keys.data();
+        out.entries.assign(2 * (size_t)d.n_cells * a.fixed_k, mk4(0, 0, 0, 0)); a.entries = out.entries.data();
+        for (int k = 0; k < n_inst; k++) pgrid_scatter_item(a, k, 0, 1, false, false);
+        for (int b = 0; b < a.big[0]; b++) pgrid_scatter_item(a, a.big[1 + b], 0, 1, false, true);
+        for (int t = 0; t < d.n_cells * a.fixed_k; t++) pgrid_emit_slot_item(a, t);
+        for (int c = 0; c < d.n_cells; c++) { out.n_fallback_cells += cells[c].y < 0; out.n_entries += std::max(cells[c].y, 0); }
+        return;
+    }
     a.tlas_root = tlas_root; a.tlas_root_dev = nullptr;
     const int before = *node_total;
     for (int fill = 0; fill < 2; fill++) {

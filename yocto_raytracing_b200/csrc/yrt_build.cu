@@ -154,12 +154,23 @@ __global__ void __launch_bounds__(256) k_pgrid_alloc(PGridArrays a) {
     if (ok) a.cells[cell] = pgrid_alloc_cell(a, n, base + x - need);
 }
 __global__ void __launch_bounds__(128) k_pgrid_emit(PGridArrays a) { int c = YRT_TID(); if (c < a.d.n_cells) pgrid_emit_item(a, c); }
+__global__ void __launch_bounds__(256) k_pgrid_emit_slots(PGridArrays a) { int t = YRT_TID(); if (t < a.d.n_cells * a.fixed_k) pgrid_emit_slot_item(a, t); }
 
 int pgrid_build_enqueue(const PGridArrays& a, cudaStream_t st) {
     if (a.d.mode == 0 || a.d.n_cells <= 0) return YRT_OK;
     // cnt | total | big[0] are one allocation (see the callers): cleared together (a.node_total is the caller's: grids may share a pool)
     YRT_CUDA(cudaMemsetAsync(a.cnt, 0, sizeof(int) * ((size_t)a.d.n_cells + 2), st));
     const int warps_grid = grid_for_warps(a.n_inst);
+    if (a.as_list && a.fixed_k > 0) {
+        // one scatter pass into the cells' own slots, then one thread per (cell, slot)
+        if (a.n_inst > 0) {
+            k_pgrid_scatter<<<warps_grid, 256, 0, st>>>(a, 0);
+            k_pgrid_scatter_big<<<PGRID_BIG_BLOCKS, 256, 0, st>>>(a, 0);
+        }
+        k_pgrid_emit_slots<<<(a.d.n_cells * a.fixed_k + 255) / 256, 256, 0, st>>>(a);
+        YRT_CUDA(cudaGetLastError());
+        return YRT_OK;
+    }
     if (a.n_inst > 0) {
         k_pgrid_scatter<<<warps_grid, 256, 0, st>>>(a, 0);
         k_pgrid_scatter_big<<<PGRID_BIG_BLOCKS, 256, 0, st>>>(a, 0);
@@ -555,7 +566,7 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
             a.keys = tmp.take<unsigned long long>((size_t)a.d.capacity);
             a.inst_box = d_inst_box;
             a.n_inst = na;
-            a.as_list = 0; a.entries = nullptr;
+            a.as_list = 0; a.fixed_k = 0; a.entries = nullptr;
             a.arity = YRT_WIDE_ANY; a.nodes = YRT_WIDE_ANY == 4 ? d_nodes4 : d_nodes2;
             a.node_first = grid_node_first; a.node_capacity = light_node_cap;
         }
@@ -716,9 +727,11 @@ int camera_grid_enqueue(DevScene& ds, const camera_k& cam, int width, int height
     if (!(reach < 1.0e18f)) return YRT_OK;
     const long long cells = (long long)((width + (1 << shift) - 1) >> shift) * ((height + (1 << shift) - 1) >> shift);
     if (cells > (1ll << 24)) return YRT_OK;
-    const int capacity = (int)std::min<long long>(16 * cells + 65536, 1ll << 26);
+    const int K = 16;                                                 // slots per cell (YRT_PGRID_MAX_LIST or fewer candidates are served)
+    const int capacity = (int)(K * cells);
     PGridArrays a;
     a.d = pgrid_camera_desc(cam, width, height, shift, reach, capacity);
+    a.d.max_list = std::min(a.d.max_list, K);
     if (a.d.mode == 0) return YRT_OK;
     YRT_TRY(ds.cg_cells.alloc(sizeof(int2) * (size_t)a.d.n_cells, ds.device));
     YRT_TRY(ds.cg_entries.alloc(sizeof(float4) * 2 * (size_t)capacity, ds.device));
@@ -727,7 +740,7 @@ int camera_grid_enqueue(DevScene& ds, const camera_k& cam, int width, int height
     a.inst_box = ds.view.inst_box; a.n_inst = ds.n_active;
     a.cnt = ds.cg_cnt.as<int>(); a.total = a.cnt + a.d.n_cells; a.big = a.cnt + a.d.n_cells + 1;
     a.cells = ds.cg_cells.as<int2>(); a.keys = ds.cg_keys.as<unsigned long long>();
-    a.as_list = 1; a.entries = ds.cg_entries.as<float4>();
+    a.as_list = 1; a.fixed_k = K; a.entries = ds.cg_entries.as<float4>();
     a.roots = nullptr; a.nodes = nullptr; a.arity = 0; a.node_first = a.node_capacity = 0; a.node_total = nullptr;
     a.tlas_root = ds.view.tlas_root; a.tlas_root_dev = nullptr;
     YRT_TRY(pgrid_build_enqueue(a, st));

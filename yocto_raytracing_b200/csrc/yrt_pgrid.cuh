@@ -71,6 +71,8 @@ struct PGridArrays {
     int* big;                      // [1 + n_inst] number and slots of the instances that cover more than YRT_PGRID_BIG cells
     // output, list form (as_list != 0): cells + entries, the candidates of a cell in order, each with its own box
     int as_list;
+    int fixed_k;                   // list form only, > 0: every cell owns fixed_k consecutive keys / entries (first = cell * fixed_k), so one
+                                   // scatter pass suffices (no count -> allocate -> fill); a cell with more candidates is not served
     float4* entries;               // [2 * capacity]
     // output, chain form
     int* roots;                    // [n_cells]
@@ -275,10 +277,12 @@ YRT_HD void pgrid_scatter_item(const PGridArrays& a, int slot, int lane, int n_l
         for (int t = lane; t < n; t += n_lanes) {
             const int cy = r.y0 + t / w, cx = r.x0 + (t - (t / w) * w);
             const int cell = f * per_face + cy * d.nx + cx;
-            if (!fill) {
+            if (!fill && a.fixed_k <= 0) {
                 YRT_ATOMIC_ADD(&a.cnt[cell], 1);
             } else {
-                const int2 c = a.cells[cell];
+                int2 c;
+                if (a.fixed_k > 0) { c.x = cell * a.fixed_k; c.y = a.fixed_k; }
+                else c = a.cells[cell];
                 if (c.y > 0) {
                     // the entry's distance bound: the box's distance from the apex, or — tighter for large boxes — the
                     // nearest point at which a ray of THIS cell can enter it; a hair below either (dist_scale, dist_bias)
@@ -288,7 +292,7 @@ YRT_HD void pgrid_scatter_item(const PGridArrays& a, int slot, int lane, int n_l
                     const float near = fmaxf(dist, s_lo * cd.len_min);
                     const float bound = fmaxf(near * d.dist_scale - d.dist_bias, 0.f);
                     const int pos = YRT_ATOMIC_ADD(&a.cnt[cell], 1);
-                    a.keys[(size_t)c.x + pos] = ((unsigned long long)(unsigned)float_as_int(bound) << 32) | (unsigned)slot;
+                    if (pos < c.y) a.keys[(size_t)c.x + pos] = ((unsigned long long)(unsigned)float_as_int(bound) << 32) | (unsigned)slot;
                 }
             }
         }
@@ -418,6 +422,37 @@ YRT_HD void pgrid_emit_list_item(const PGridArrays& a, int cell) {
         e[1] = mk4(cb.hx, cb.hy, cb.hz, int_as_float((int)(unsigned)(k[i] >> 32)));
     }
 }
+// List form with fixed_k slots per cell, one item per (cell, slot): the header of the cell (slot 0), and — if the cell is
+// served and the slot holds a candidate — that candidate's entry at its place in the order, i.e. at the number of the
+// cell's keys below its own (the keys of a cell differ at least in the instance slot).  No per-cell sort, no serial loop
+// over a cell's candidates: one short thread per entry.
+YRT_HD void pgrid_emit_slot_item(const PGridArrays& a, int t) {
+    const int K = a.fixed_k, cell = t / K, i = t - cell * K;
+    const int n = a.cnt[cell];
+    const bool served = n <= K && n <= a.d.max_list;
+    if (i == 0) { int2 c; c.x = cell * K; c.y = served ? n : -1; a.cells[cell] = c; }
+    if (!served || i >= n) return;
+    const unsigned long long* k = a.keys + (size_t)cell * K;
+    const unsigned long long mine = k[i];
+    int rank = 0;
+    for (int j = 0; j < n; j++) rank += k[j] < mine;
+    const int slot = (int)(unsigned)(mine & 0xffffffffull);
+    const int per_face = a.d.nx * a.d.ny, face = cell / per_face, in_face = cell - face * per_face;
+    const PCellDirs cd = pgrid_cell_dirs(a.d, face, in_face % a.d.nx, in_face / a.d.nx);
+    const nodebox wb = pgrid_inst_nodebox(a, slot);
+    const vec3 wlo = mk3(wb.cx - wb.hx, wb.cy - wb.hy, wb.cz - wb.hz), whi = mk3(wb.cx + wb.hx, wb.cy + wb.hy, wb.cz + wb.hz);
+    vec3 clo = wlo - a.d.apex, chi = whi - a.d.apex;
+    if (pgrid_box_distance(a.d, wlo, whi) >= a.d.near_all) pgrid_cell_clip(a.d, cd, clo, chi, clo, chi);
+    clo = clo + a.d.apex; chi = chi + a.d.apex;
+    nodebox cb;
+    box_center_half(fmaxf(clo.x, wlo.x), fminf(chi.x, whi.x), cb.cx, cb.hx);
+    box_center_half(fmaxf(clo.y, wlo.y), fminf(chi.y, whi.y), cb.cy, cb.hy);
+    box_center_half(fmaxf(clo.z, wlo.z), fminf(chi.z, whi.z), cb.cz, cb.hz);
+    float4* e = a.entries + 2 * ((size_t)cell * K + rank);
+    e[0] = mk4(cb.cx, cb.cy, cb.cz, int_as_float(slot));
+    e[1] = mk4(cb.hx, cb.hy, cb.hz, int_as_float((int)(unsigned)(mine >> 32)));
+}
+
 YRT_HD void pgrid_emit_item(const PGridArrays& a, int cell) {
     if (a.as_list) pgrid_emit_list_item(a, cell);
     else if (a.arity == 4) pgrid_emit_item<4>(a, cell);

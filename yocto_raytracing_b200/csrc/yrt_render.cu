@@ -438,9 +438,11 @@ struct PhaseTimer {
     }
     void begin(int cat) { if (!on) return; Span s; s.cat = cat; s.a = get(); s.b = get(); cudaEventRecord(s.a, st); spans.push_back(s); }
     void end() { if (!on) return; cudaEventRecord(spans.back().b, st); }
+    int64_t extra_launches = 0;   // kernels inside spans that hold more than one launch (the camera grid build: 6 kernels in one span)
     void collect(float out[5], int cnt[5], int64_t& launches) {
         for (int i = 0; i < 5; i++) { out[i] = 0.f; cnt[i] = 0; }
-        launches = 0;
+        launches = extra_launches;
+        extra_launches = 0;
         for (auto& s : spans) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, s.a, s.b);
@@ -714,7 +716,7 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
     if (!pt.deferred) {   // a stand-alone frame starts from clean counters; deferred frames accumulate
         for (auto& sp : pt.spans) { pt.pool.push_back(sp.a); pt.pool.push_back(sp.b); }
         pt.spans.clear();
-        pt.frames = 0; pt.primary = 0;
+        pt.frames = 0; pt.primary = 0; pt.extra_launches = 0;
         YRT_CUDA(cudaMemsetAsync(ds.ws.stats.p, 0, sizeof(FrameCounters), st));
     }
     pt.begin(CAT_FRAME);
@@ -726,6 +728,7 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
     pt.begin(CAT_OTHER);
     YRT_TRY(camera_grid_enqueue(ds, rp.cam, rp.width, rp.height, st, &cam_grid));
     pt.end();
+    if (pt.on && cam_grid.nx > 0) pt.extra_launches += 2;    // scatter, scatter (large instances), emit: 3 kernels, one span
     if (n_pipes > 1) YRT_CUDA(cudaEventRecord(ds.ev_fork, st));
     for (int k = 1; k < n_pipes; k++) {
         YRT_CUDA(cudaStreamWaitEvent(ds.aux_stream[k - 1], ds.ev_fork, 0));
@@ -812,7 +815,7 @@ int stats_begin_device(DevScene& ds) {
     YRT_CUDA(cudaMemset(ds.ws.stats.p, 0, sizeof(FrameCounters)));
     for (auto& sp : pt.spans) { pt.pool.push_back(sp.a); pt.pool.push_back(sp.b); }
     pt.spans.clear();
-    pt.frames = 0; pt.primary = 0;
+    pt.frames = 0; pt.primary = 0; pt.extra_launches = 0;
     pt.deferred = true;
     return YRT_OK;
 }
