@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--tile-rows", type=int, default=1, help="rows per interleaved tile (1: rows r, r+N, r+2N, ...)")
     ap.add_argument("--gather", default="ipc", choices=["ipc", "nccl"],
                     help="device-resident multi-GPU frame (the `value` measurement): ipc = every rank's resolve kernel stores its rows into rank "
-                         "0's frame over NVLink peer memory, bracketed by two 1-element all-reduces; nccl = packed rows, NCCL gather, unpack on rank 0")
+                         "0's frame over NVLink peer memory (two alternating frames), one peer-memory barrier kernel per rank and frame; nccl = packed rows, NCCL gather, unpack on rank 0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip other_configs and the device-counter pass (N = 1 extras)")
     ap.add_argument("--cpu-baseline-resolution", type=int, default=0, help="0 = sized for ~15 s of CPU work")
@@ -266,6 +266,10 @@ def run_b200(args):
     scene2 = y.Scene(flat)          # a second creation in the same process: no first-use costs (module load, arena growth)
     info["scene_create_ms_wall_second"] = round((time.perf_counter() - t_up) * 1e3, 3)
     scene2.close()
+    t_up = time.perf_counter()
+    scene3 = y.Scene(flat)          # ... and a rebuild after a scene was destroyed: its arena is reused (no cudaMalloc / cudaFree in the build)
+    info["scene_create_ms_wall_rebuild"] = round((time.perf_counter() - t_up) * 1e3, 3)
+    scene3.close()
     dev = torch.device("cuda", local)
     tr = args.tile_rows if multi else H
 
@@ -350,7 +354,7 @@ def run_b200(args):
     ms_total = float(ms.item())
     rays_total, launches = float(tot[0].item()), int(tot[1].item())
     if multi:
-        launches += args.steps * (2 * world if shared is not None else world + 1)      # + the exchange: two all-reduces per rank / NCCL gather + unpack kernels
+        launches += args.steps * (world if shared is not None else world + 1)      # + the exchange: one barrier kernel per rank / NCCL gather + unpack kernels
     value = rays_total / (ms_total * 1e-3) / 1e6
 
     # ---- end to end through the public API with HOST buffers (`e2e`) ----

@@ -213,10 +213,15 @@ int yrt_render_rows_to_host(yrt_scene* scn, const yrt_camera* cam, const float a
 /* Fused gather for one-process-per-GPU drivers: rank 0 allocates the full frame (yrt_frame_alloc) and exports a
  * 64-byte CUDA IPC handle; the other ranks map it (yrt_frame_import: peer mapping over NVLink) and every rank's
  * resolve kernel stores its rows at their final position in that ONE buffer (yrt_render_rows_into_frame) — no
- * packed rows, no gather copy, no unpack.  The caller brackets every frame with two stream-ordered barriers (e.g.
- * 1-element all-reduces on the same stream): one AFTER the call, before rank 0 reads the frame, and one BEFORE the
- * next call, after rank 0 has finished reading — otherwise another rank's stores of frame k+1 can overtake rank 0's
- * read of frame k (distributed.SharedFrame does both). */
+ * packed rows, no gather copy, no unpack.  The allocation holds TWO frames back to back (frame k goes to d_full +
+ * (k % 2) * width*height*16 bytes) and an arrival counter behind them; every frame ends with ONE barrier:
+ * yrt_frame_barrier(base, width, height, world, k + 1, stream) enqueues a one-thread kernel that fences this rank's
+ * stores, adds its arrival to the counter in rank 0's memory (a peer atomic over NVLink) and waits until all `world`
+ * ranks of frame k have arrived — no collective library call, no host synchronisation.  That orders everything: rank 0
+ * may read frame k once its own barrier kernel has completed (stream order); a rank writes into frame k's buffer
+ * again only in frame k + 2, i.e. after barrier k + 1, which rank 0 joins after the reads of frame k it enqueued on
+ * the same stream (a consumer that reads on another stream or on the host finishes before it calls frame k + 1).
+ * generation counts frames from 1 and only grows (distributed.SharedFrame does all of this). */
 int yrt_render_rows_into_frame(yrt_scene* scn, const yrt_camera* cam, const float amb[3], int width, int height,
                                int samples, int tile_rows, int rank, int world, void* d_full, void* stream,
                                yrt_stats* stats);
@@ -225,6 +230,7 @@ int yrt_frame_free(void* d_full);
 int yrt_frame_export(void* d_full, unsigned char handle[64]);
 int yrt_frame_import(const unsigned char handle[64], void** d_full);
 int yrt_frame_release(void* d_full);
+int yrt_frame_barrier(void* d_full_base, int width, int height, int world, int64_t generation, void* stream);
 /* Barrier between the processes of one node through a counter in memory they share (8 bytes, zero-initialised, e.g. the tail of
  * the shared host frame): adds one arrival and returns when world * generation arrivals have been counted; generation =
  * 1, 2, 3, ... (the counter only grows).  Microseconds instead of a collective launch + stream wait per frame.  Host only. */

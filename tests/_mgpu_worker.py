@@ -25,16 +25,20 @@ def main():
     flat = sc.flat()
     w, h, s = 384, 216, 2
     scene = y.Scene(flat)
-    dev_frame = D.SharedFrame(w, h)
+    dev_frame = D.SharedFrame(w, h)                         # two frames, one peer-memory barrier kernel per frame
+    nccl_frame = D.SharedFrame(w, h, barrier="nccl")        # round 1's protocol: one frame between two all-reduces
     host_frame = D.SharedHostFrame(w, h)
     cams = [synth.make_camera((12.0 * np.cos(a), 14.0 + 3 * k, 12.0 * np.sin(a)), (0, 1, 0), 0.6) for k, a in enumerate(np.linspace(0.3, 2.5, 5))]
     bad = 0
-    got_dev, got_host = [], []
+    got_dev, got_host, got_nccl = [], [], []
     for cam in cams:
         scene.set_camera(cam)
         dev_frame.render(scene, s, 0.1, 1)
         if rank == 0:
             got_dev.append(dev_frame.tensor().cpu().numpy().copy())     # read the frame; the next render call follows at once
+        nccl_frame.render(scene, s, 0.1, 1)
+        if rank == 0:
+            got_nccl.append(nccl_frame.tensor().cpu().numpy().copy())
         host_frame.render(scene, s, 0.1, 1)
         if rank == 0:
             got_host.append(host_frame.array.copy())
@@ -46,12 +50,16 @@ def main():
             if not np.array_equal(ref.view(np.uint32), got_dev[k].view(np.uint32)):
                 bad += 1
                 print(f"frame {k}: device frame differs from the single-GPU frame", flush=True)
+            if not np.array_equal(ref.view(np.uint32), got_nccl[k].view(np.uint32)):
+                bad += 1
+                print(f"frame {k}: device frame (NCCL barriers) differs from the single-GPU frame", flush=True)
             if not np.array_equal(ref.view(np.uint32), got_host[k].view(np.uint32)):
                 bad += 1
                 print(f"frame {k}: host frame differs from the single-GPU frame", flush=True)
         assert len({a.tobytes() for a in got_dev}) == len(cams)            # the cameras really differ
         print("MGPU_OK" if bad == 0 else f"MGPU_BAD {bad}", flush=True)
     host_frame.close()
+    nccl_frame.close()
     dev_frame.close()
     scene.close()
     dist.barrier()

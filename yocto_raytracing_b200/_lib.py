@@ -92,6 +92,7 @@ SYMBOLS = {
     "yrt_frame_export": (C.c_int, [C.c_void_p, C.c_char_p]),
     "yrt_frame_import": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "yrt_frame_release": (C.c_int, [C.c_void_p]),
+    "yrt_frame_barrier": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p]),
     "yrt_stats_begin": (C.c_int, [C.c_void_p]),
     "yrt_stats_end": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "yrt_unpack_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -235,11 +235,34 @@ int yrt_host_barrier(void* counter, int world, int64_t generation) {
     return YRT_OK;
 }
 
+// The shared frame allocation holds TWO frames back to back and, behind them, the arrival counter of yrt_frame_barrier
+// (256 bytes, zeroed): [frame 0 | frame 1 | counter].
+static size_t frame_bytes(int width, int height) { return sizeof(float4) * (size_t)width * height; }
+
 int yrt_frame_alloc(int width, int height, void** d_full) {
     if (!d_full || width <= 0 || height <= 0) { set_error("yrt_frame_alloc: bad arguments"); return YRT_ERR_INVALID; }
     YRT_TRY(ensure_init());
     YRT_CUDA(cudaSetDevice(g_devices[0]));
-    YRT_CUDA(cudaMalloc(d_full, sizeof(float4) * (size_t)width * height));
+    YRT_CUDA(cudaMalloc(d_full, 2 * frame_bytes(width, height) + 256));
+    YRT_CUDA(cudaMemset((char*)*d_full + 2 * frame_bytes(width, height), 0, 256));
+    return YRT_OK;
+}
+
+// One thread per rank: this rank's arrival, then wait until `target` arrivals have been counted.  The counter lives in rank
+// 0's HBM; the other ranks reach it through their CUDA-IPC mapping of the frame (NVLink peer atomics and loads).  The
+// stores of this rank's rows (earlier kernels of the same stream, into the same peer memory) are fenced before the arrival.
+__global__ void k_frame_barrier(unsigned long long* ctr, unsigned long long target) {
+    __threadfence_system();
+    atomicAdd_system(ctr, 1ull);
+    while (*(volatile unsigned long long*)ctr < target) __nanosleep(100);
+    __threadfence_system();
+}
+
+int yrt_frame_barrier(void* d_full, int width, int height, int world, int64_t generation, void* stream) {
+    if (!d_full || width <= 0 || height <= 0 || world <= 0 || generation <= 0) { set_error("yrt_frame_barrier: bad arguments"); return YRT_ERR_INVALID; }
+    unsigned long long* ctr = (unsigned long long*)((char*)d_full + 2 * frame_bytes(width, height));
+    k_frame_barrier<<<1, 1, 0, (cudaStream_t)stream>>>(ctr, (unsigned long long)world * (unsigned long long)generation);
+    YRT_CUDA(cudaGetLastError());
     return YRT_OK;
 }
 

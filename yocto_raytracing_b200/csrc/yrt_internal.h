@@ -129,6 +129,7 @@ int pgrid_build_enqueue(const PGridArrays& a, cudaStream_t st);
 // this frame's camera grid (ds.cg_*): enqueued on `st`; `out` is what the primary-ray kernel reads (nx = 0: none)
 int camera_grid_enqueue(DevScene& ds, const camera_k& cam, int width, int height, cudaStream_t st, GridRef* out);
 void destroy_device_scene(DevScene& ds);
+void arena_give_back(DevBuf& arena);   // a destroyed scene's arena goes to a small per-device pool for the next build (yrt_build.cu)
 
 struct RenderParams {
     camera_k cam;

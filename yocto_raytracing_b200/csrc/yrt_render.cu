@@ -49,18 +49,31 @@ struct BatchParams {
     int lr0;                      // first packed local row of the batch
     int tile_rows, rank, world;
     size_t cap_slots;             // stride of per-light / per-depth planes
+    unsigned m_spp, m_width, m_samples;   // floor(2^32 / d) for the three divisors of slot_to_sample (udiv_by)
     GridRef cam_grid;             // apex grid of this frame's camera (nx = 0: none), read by the primary rays only
 };
 
+// n / d and n % d for a divisor known on the host: with m = floor(2^32 / d) the estimate umulhi(n, m) is the quotient or one
+// below it (n / d - n m / 2^32 = n (2^32 - m d) / (d 2^32) < n / 2^32 < 1), so one compare settles it — 5 instructions
+// where the generic 32-bit division takes ~20 (the ray set-up of k_trace_closest<primary> has four of them per ray)
+__host__ __device__ __forceinline__ unsigned udiv_magic(unsigned d) { return d <= 1u ? 0xffffffffu : (unsigned)(0x100000000ull / d); }
+__device__ __forceinline__ unsigned udiv_by(unsigned n, unsigned d, unsigned m, unsigned& rem) {
+    unsigned q = d <= 1u ? n : __umulhi(n, m);
+    unsigned r = n - q * d;
+    if (r >= d) { q++; r -= d; }
+    rem = r;
+    return q;
+}
+
 // slot -> (i, j, ii, jj)
 __device__ __forceinline__ void slot_to_sample(const BatchParams& bp, unsigned slot, int& i, int& j, int& ii, int& jj) {
-    unsigned pix = slot / (unsigned)bp.spp;
-    unsigned s = slot - pix * (unsigned)bp.spp;
-    unsigned lr = pix / (unsigned)bp.width;
-    i = (int)(pix - lr * (unsigned)bp.width);
-    j = global_row(bp.lr0 + (int)lr, bp.tile_rows, bp.rank, bp.world);
-    jj = (int)(s / (unsigned)bp.samples);
-    ii = (int)(s - (unsigned)jj * (unsigned)bp.samples);
+    unsigned s, ui, uii;
+    const unsigned pix = udiv_by(slot, (unsigned)bp.spp, bp.m_spp, s);
+    const unsigned lr = udiv_by(pix, (unsigned)bp.width, bp.m_width, ui);
+    i = (int)ui;
+    j = bp.world == 1 ? bp.lr0 + (int)lr : global_row(bp.lr0 + (int)lr, bp.tile_rows, bp.rank, bp.world);   // (one rank: its packed rows are the image's rows)
+    jj = (int)udiv_by(s, (unsigned)bp.samples, bp.m_samples, uii);
+    ii = (int)uii;
 }
 
 // next 32 work items of the warp: false = the launch has no work left; `alive` = this lane has an item
@@ -550,6 +563,7 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, const G
     BatchParams bp;
     bp.cam_grid = cam_grid;
     bp.cam = rp.cam; bp.amb = rp.amb; bp.width = rp.width; bp.height = rp.height; bp.samples = rp.samples;
+    bp.m_spp = udiv_magic((unsigned)(rp.samples * rp.samples)); bp.m_width = udiv_magic((unsigned)rp.width); bp.m_samples = udiv_magic((unsigned)rp.samples);
     bp.spp = rp.samples * rp.samples; bp.lr0 = lr0; bp.tile_rows = rp.tile_rows; bp.rank = rp.rank; bp.world = rp.world;
     bp.cap_slots = cap_slots;
     unsigned n = (unsigned)((size_t)nrows * rp.width * bp.spp);
@@ -932,6 +946,8 @@ void destroy_device_scene(DevScene& ds) {
     if (ds.ev_fork) { cudaEventDestroy(ds.ev_fork); ds.ev_fork = nullptr; }
     delete ds.timer;
     ds.timer = nullptr;
+    cudaDeviceSynchronize();        // nothing of this scene is in flight any more: its arena may serve the next build
+    arena_give_back(ds.arena);
 }
 
 int unpack_rows_device(const float4* d_packed, float4* d_full, int width, int height, int tile_rows, int rank, int world, cudaStream_t st) {

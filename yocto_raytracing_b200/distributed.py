@@ -92,14 +92,19 @@ def render_sharded(scene, width: int, height: int, samples: int, amb=0.1, tile_r
 
 class SharedFrame:
     """The full framebuffer in rank 0's HBM, mapped into every other rank over NVLink (CUDA IPC).  Every rank's
-    resolve kernel stores its rows at their final position, so the per-frame exchange is the stores themselves plus
-    one 1-element all-reduce as completion barrier — no gather copy and no unpack."""
+    resolve kernel stores its rows at their final position, so the per-frame exchange is the stores themselves plus one
+    barrier — no gather copy, no unpack, no collective: the barrier is a one-thread kernel per rank that adds its arrival
+    to a counter in the same peer memory and waits for the others (yrt_frame_barrier).  Frames alternate between two
+    buffers, which is what makes ONE barrier per frame enough (see include/yrt_b200.h).  barrier="nccl" keeps round 1's
+    protocol (one buffer, two 1-element all-reduces per frame) for systems without peer atomics."""
 
-    def __init__(self, width: int, height: int, group=None):
+    def __init__(self, width: int, height: int, group=None, barrier: str = "peer"):
         import ctypes as C
         self.width, self.height, self.group = width, height, group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.barrier = barrier
+        self._frames = 0
         lib = _lib.load()
         self._ptr = C.c_void_p()
         self._owner = self.rank == 0
@@ -128,25 +133,35 @@ class SharedFrame:
     def ptr(self) -> int:
         return self._ptr.value
 
+    def _buffer(self, frame: int) -> int:
+        return self.ptr + (frame % 2 if self.barrier == "peer" else 0) * self.width * self.height * 16
+
     def tensor(self) -> torch.Tensor:
-        """Rank 0: the frame as a (height, width, 4) float32 CUDA tensor view (no copy)."""
+        """Rank 0: the last rendered frame as a (height, width, 4) float32 CUDA tensor view (no copy); valid until the
+        next-but-one render call (read it on the current stream, or finish reading before the next render call)."""
         assert self._owner
-        iface = {"shape": (self.height, self.width, 4), "typestr": "<f4", "data": (self.ptr, False), "version": 3, "strides": None}
+        iface = {"shape": (self.height, self.width, 4), "typestr": "<f4", "data": (self._buffer(max(self._frames - 1, 0)), False), "version": 3, "strides": None}
         holder = type("_Frame", (), {"__cuda_array_interface__": iface})()
         return torch.as_tensor(holder, device=torch.device("cuda", torch.cuda.current_device()))
 
     def render(self, scene, samples: int, amb=0.1, tile_rows: int = 1, want_stats: bool = False):
-        """Render this rank's rows into the shared frame between two stream-ordered barriers (no host sync): the first keeps
-        any rank from storing rows of this frame while rank 0 may still be reading the previous one (rank 0 joins it only
-        when it is called for this frame, i.e. after its reads of the previous frame were enqueued on the same stream); the
-        second completes on rank 0 only after every rank's stores of this frame."""
+        """Render this rank's rows into the current buffer of the shared frame, then the frame's barrier — all enqueued on the
+        current stream, no host synchronisation.  Frame k's buffer is written again in frame k + 2, after barrier k + 1, which
+        rank 0 joins only after the reads of frame k it enqueued before calling render(k + 1)."""
         dev = torch.device("cuda", torch.cuda.current_device())
         st = torch.cuda.current_stream(dev).cuda_stream
+        if self.barrier != "peer":
+            if self.world > 1:
+                dist.all_reduce(self._token, group=self.group)
+            stats = scene.render_rows_into_frame(self.ptr, self.width, self.height, samples, amb, tile_rows, self.rank, self.world, st, want_stats)
+            if self.world > 1:
+                dist.all_reduce(self._token, group=self.group)
+            self._frames += 1
+            return stats
+        stats = scene.render_rows_into_frame(self._buffer(self._frames), self.width, self.height, samples, amb, tile_rows, self.rank, self.world, st, want_stats)
+        self._frames += 1
         if self.world > 1:
-            dist.all_reduce(self._token, group=self.group)
-        stats = scene.render_rows_into_frame(self.ptr, self.width, self.height, samples, amb, tile_rows, self.rank, self.world, st, want_stats)
-        if self.world > 1:
-            dist.all_reduce(self._token, group=self.group)
+            check(_lib.load().yrt_frame_barrier(self.ptr, self.width, self.height, self.world, self._frames, st))
         return stats
 
     def close(self):
