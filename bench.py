@@ -320,8 +320,8 @@ def run_b200(args):
     assert tot_stats.frames == args.steps, (tot_stats.frames, args.steps)
     per_frame = {k: (v / args.steps if isinstance(v, (int, float)) else v) for k, v in tot_stats.as_dict().items()}
     kernel_timing = "CUDA events around every launch inside the timed region"
-    if multi and os.environ.get("YRT_STREAMS", "2") != "1":
-        # a rank's share runs as two pipelines on two streams, so kernels of the two half shares overlap and an event
+    if os.environ.get("YRT_STREAMS", "2") != "1":
+        # a frame (a rank's share of it) runs as two pipelines on two streams, so kernels of the two half shares overlap and an event
         # span includes queueing behind the other pipeline: per-kernel durations come from a single-pipeline pass of
         # 3 frames right after the timed region (same buffers, same kernels)
         os.environ["YRT_STREAMS"] = "1"

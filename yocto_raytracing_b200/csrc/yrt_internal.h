@@ -120,6 +120,11 @@ struct DevScene {
     bool grids_allowed = false;      // rigid frames only: the lists are sorted and cut by world-space distances
     float extent = 0.f;
     DevBuf cg_cells, cg_entries, cg_keys, cg_cnt;   // cg_cnt: [n_cells] counts | total | big list (1 + n_active)
+    // The camera grid is built on its own stream: its only readers are the primary-ray kernels, so the build of frame k + 1
+    // may run as soon as those of frame k are done — under frame k's shadow / shade kernels when frames are enqueued back to back
+    cudaStream_t grid_stream = nullptr;             // owned
+    cudaEvent_t ev_grid = nullptr, ev_primary_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool primary_recorded[4] = {false, false, false, false};
     PhaseTimer* timer = nullptr;     // owned (yrt_render.cu)
 };
 

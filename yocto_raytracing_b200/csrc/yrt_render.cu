@@ -451,7 +451,7 @@ struct PhaseTimer {
     }
     void begin(int cat) { if (!on) return; Span s; s.cat = cat; s.a = get(); s.b = get(); cudaEventRecord(s.a, st); spans.push_back(s); }
     void end() { if (!on) return; cudaEventRecord(spans.back().b, st); }
-    int64_t extra_launches = 0;   // kernels inside spans that hold more than one launch (the camera grid build: 6 kernels in one span)
+    int64_t extra_launches = 0;   // kernels launched without an event span (the camera grid build on its own stream)
     void collect(float out[5], int cnt[5], int64_t& launches) {
         for (int i = 0; i < 5; i++) { out[i] = 0.f; cnt[i] = 0; }
         launches = extra_launches;
@@ -559,7 +559,7 @@ struct CounterRing {
 
 // batch of rows [lr0, lr0+nrows) of the rank's packed rows; primary hits only when primary_only
 static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, const GridRef& cam_grid, int lr0, int nrows, size_t cap_slots, float4* d_out, cudaStream_t st,
-                     PhaseTimer& pt, CounterRing& ring, int depth_cap, bool reflective, bool primary_only) {
+                     PhaseTimer& pt, CounterRing& ring, int depth_cap, bool reflective, bool primary_only, int pipe = -1) {
     BatchParams bp;
     bp.cam_grid = cam_grid;
     bp.cam = rp.cam; bp.amb = rp.amb; bp.width = rp.width; bp.height = rp.height; bp.samples = rp.samples;
@@ -580,6 +580,10 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, const G
     k_trace_closest<true><<<grid_of(ds.grid_closest_primary, n), TRACE_THREADS, 0, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(), w.P.as<float4>(),
                                                                                           workdist_linear(ctr, n), dctr);
     pt.end();
+    if (pipe >= 0 && cam_grid.nx > 0 && ds.ev_primary_done[pipe]) {     // the last reader of this frame's camera grid on this pipeline so far
+        YRT_CUDA(cudaEventRecord(ds.ev_primary_done[pipe], st));
+        ds.primary_recorded[pipe] = true;
+    }
     if (primary_only) { YRT_CUDA(cudaGetLastError()); return YRT_OK; }
 
     // Wave loop.  Wave d traces the shadow rays of its active samples, shades them, and appends the mirror rays it spawns to
@@ -704,14 +708,13 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
     bool reflective = ds.has_reflective;
     int depth_cap = std::min(YRT_MAX_WAVES, std::max(1, env_int("YRT_MAX_DEPTH", YRT_MAX_WAVES)));
     int batch_rows = batch_rows_for(rp, nl, own, reflective);
-    // two pipelines: the rank's rows are cut into (at least) two batches that run on two streams, so the ramp-up of one
-    // batch's kernel fills the tail of the other's (each persistent kernel ends with ~one 32-ray task of idle SMs).
-    // Default: 2 when this call renders one rank's share of a frame (measured at 1/8 frame: 2.265 -> 2.150 ms, 3 pipelines
-    // 2.146, 4: 2.223), 1 for a whole frame (16.56 -> 16.46 ms only, and the per-kernel event spans stay unambiguous).
-    // ... and 2 whenever the rows go on to the host: the copy of the first batch then runs under the kernels of the second
-    // (unless per-kernel statistics were asked for: their event spans are only unambiguous on one stream).
+    // two pipelines: the rows are cut into (at least) two batches that run on two streams, so the ramp-up of one
+    // batch's kernel fills the tail of the other's (each persistent kernel ends with ~one 32-ray task of idle SMs), and a
+    // batch's rows go to the host under the other batch's kernels.  Measured on the final kernels (tools/diag_streams.py):
+    // 1/8 frame 1.475 -> 1.361 ms (3 pipelines 1.372, 4: 1.375), 1/4 frame 2.706 -> 2.566, whole frame 9.964 -> 9.865 ms.
+    // One pipeline only when per-kernel statistics of THIS call are asked for (event spans are unambiguous on one stream).
     const bool to_host = rp.h_rgba != nullptr || rp.h_ldr != nullptr;
-    const int n_pipes = std::max(1, std::min(std::min(4, own), env_int("YRT_STREAMS", (rp.world > 1 || (to_host && !stats)) ? YRT_DEFAULT_STREAMS : 1)));
+    const int n_pipes = std::max(1, std::min(std::min(4, own), env_int("YRT_STREAMS", stats ? 1 : YRT_DEFAULT_STREAMS)));
     if (n_pipes > 1) batch_rows = std::min(batch_rows, (own + n_pipes - 1) / n_pipes);
     size_t cap_slots = (size_t)batch_rows * rp.width * spp;
     YRT_TRY(ensure_workspace(ds, ds.ws, cap_slots, nl, depth_cap, reflective));
@@ -737,12 +740,25 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
     const size_t frame_span = pt.spans.size();
     CounterRing ring[4];
     YRT_TRY(ring[0].init(ds.ws, st));
-    // this frame's camera grid (yrt_pgrid.cuh): built on the frame's stream, inside its time, before the pipelines fork
+    // This frame's camera grid (yrt_pgrid.cuh), rebuilt for every frame, on its own stream: it waits for the primary-ray
+    // kernels of the previous frame (the only readers of the grid's buffers), so with frames enqueued back to back it runs
+    // under the previous frame's shadow / shade kernels; the pipelines wait for it before their first kernel.
     GridRef cam_grid;
-    pt.begin(CAT_OTHER);
-    YRT_TRY(camera_grid_enqueue(ds, rp.cam, rp.width, rp.height, st, &cam_grid));
-    pt.end();
-    if (pt.on && cam_grid.nx > 0) pt.extra_launches += 2;    // scatter, scatter (large instances), emit: 3 kernels, one span
+    if (!ds.grid_stream) {
+        YRT_CUDA(cudaStreamCreateWithFlags(&ds.grid_stream, cudaStreamNonBlocking));
+        YRT_CUDA(cudaEventCreateWithFlags(&ds.ev_grid, cudaEventDisableTiming));
+        for (int k = 0; k < 4; k++) YRT_CUDA(cudaEventCreateWithFlags(&ds.ev_primary_done[k], cudaEventDisableTiming));
+    }
+    for (int k = 0; k < 4; k++)
+        if (ds.primary_recorded[k]) { YRT_CUDA(cudaStreamWaitEvent(ds.grid_stream, ds.ev_primary_done[k], 0)); ds.primary_recorded[k] = false; }
+    // (no event span around it: on its own stream the three small kernels wait for SMs the previous frame's persistent kernels
+    //  hold, so a span would measure that wait; their own time is in the ncu launch lists, 39 us)
+    YRT_TRY(camera_grid_enqueue(ds, rp.cam, rp.width, rp.height, ds.grid_stream, &cam_grid));
+    if (pt.on && cam_grid.nx > 0) pt.extra_launches += 3;    // scatter, scatter (large instances), emit
+    if (cam_grid.nx > 0) {
+        YRT_CUDA(cudaEventRecord(ds.ev_grid, ds.grid_stream));
+        YRT_CUDA(cudaStreamWaitEvent(st, ds.ev_grid, 0));
+    }
     if (n_pipes > 1) YRT_CUDA(cudaEventRecord(ds.ev_fork, st));
     for (int k = 1; k < n_pipes; k++) {
         YRT_CUDA(cudaStreamWaitEvent(ds.aux_stream[k - 1], ds.ev_fork, 0));
@@ -754,7 +770,7 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
         int pipe = b % n_pipes;
         Workspace& w = pipe ? ds.ws_aux[pipe - 1] : ds.ws;
         pt.st = pipe ? ds.aux_stream[pipe - 1] : st;
-        YRT_TRY(run_batch(ds, w, rp, cam_grid, lr0, nrows, w.cap_slots, d_out, pt.st, pt, ring[pipe], depth_cap, reflective, false));
+        YRT_TRY(run_batch(ds, w, rp, cam_grid, lr0, nrows, w.cap_slots, d_out, pt.st, pt, ring[pipe], depth_cap, reflective, false, pipe));
         if (to_host && !rp.scatter && !pt.on) YRT_TRY(rows_to_host(rp, d_out, lr0, nrows, pt.st));
     }
     pt.st = st;
@@ -944,6 +960,9 @@ void destroy_device_scene(DevScene& ds) {
         if (ds.ev_join[k]) { cudaEventDestroy(ds.ev_join[k]); ds.ev_join[k] = nullptr; }
     }
     if (ds.ev_fork) { cudaEventDestroy(ds.ev_fork); ds.ev_fork = nullptr; }
+    if (ds.grid_stream) { cudaStreamSynchronize(ds.grid_stream); cudaStreamDestroy(ds.grid_stream); ds.grid_stream = nullptr; }
+    if (ds.ev_grid) { cudaEventDestroy(ds.ev_grid); ds.ev_grid = nullptr; }
+    for (int k = 0; k < 4; k++) if (ds.ev_primary_done[k]) { cudaEventDestroy(ds.ev_primary_done[k]); ds.ev_primary_done[k] = nullptr; }
     delete ds.timer;
     ds.timer = nullptr;
     cudaDeviceSynchronize();        // nothing of this scene is in flight any more: its arena may serve the next build
