@@ -65,12 +65,48 @@ def workload_name(desc, flat, w, h, s):
 
 # ---- clocks during the timed region -----------------------------------------------------------------
 class ClockSampler:
+    """SM clock, power and throttle reasons of this rank's GPU, sampled DURING the timed region.  In-process NVML on a thread
+    (three cheap queries every 10 ms: 8 samples in a 50 ms timed region at N = 4 where `nvidia-smi -lms 25` delivers 2);
+    `nvidia-smi -lms` in a child process is the fallback (YRT_BENCH_SAMPLER = nvml | smi | none)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t, self.stop_flag, self.kind = [], None, index, None, False, os.environ.get("YRT_BENCH_SAMPLER", "nvml")
+
+    def _nvml_loop(self, h, nv, period):
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(sm), str(mx), str(pw)] + ["Active" if (r & b) else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            time.sleep(period)
 
     def start(self):
+        if self.kind == "none":
+            return
+        if self.kind == "nvml":
+            try:
+                import pynvml as nv
+                nv.nvmlInit()
+                try:        # the CUDA device of this rank, whatever CUDA_VISIBLE_DEVICES maps it to
+                    import torch
+                    uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                    h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+                except Exception:
+                    h = nv.nvmlDeviceGetHandleByIndex(self.index)
+                self.t = threading.Thread(target=self._nvml_loop, args=(h, nv, 0.01), daemon=True)
+                self.t.start()
+                return
+            except Exception:
+                self.kind = "smi"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -84,13 +120,17 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        self.stop_flag = True
+        if self.kind == "nvml" and self.t is not None:
+            self.t.join(timeout=2)
+        elif not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sampler (" + self.kind + ")"]}
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
@@ -104,7 +144,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         load = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
         return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
-                "power_w_max": float(max(pw))}
+                "power_w_max": float(max(pw)), "sampler": self.kind}
 
 
 # ---- the reference's CPU implementation, bounded sample ------------------------------------------------
@@ -305,7 +345,7 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
-        frame()
+        frame(False)            # the same call as in the timed region (same number of pipelines, same workspaces: nothing is allocated in it)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # deferred statistics: per-launch CUDA events and ray counters are recorded in-stream, nothing synchronises

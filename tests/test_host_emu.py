@@ -202,3 +202,22 @@ def test_apex_grids_moving_camera_and_odd_sizes():
             img1, _ = e.render(w, h, 1)
             assert np.array_equal(ids0, ids1) and np.array_equal(d0, d1), (trial, shift)
             assert np.array_equal(img0, img1), (trial, shift)
+
+
+def test_apex_grids_skip_rotated_lights():
+    """shade() aims at transform_point(frame, pos - p) (raytrace.cpp:129-130): only a light whose frame does not rotate
+    converges its shadow rays on one point.  A rotated light must keep the instance tree — and the frame must not change."""
+    flat, ref = load_golden("instance10000")
+    a = {k: v.copy() for k, v in flat.arrays.items()}
+    lights = flat.light_instances()
+    fr = a["inst_frame"].reshape(-1, 12)
+    c, s = np.float32(np.cos(0.3)), np.float32(np.sin(0.3))
+    fr[lights[1], :9] = np.array([c, 0, s, 0, 1, 0, -s, 0, c], np.float32)        # rotation about y
+    from yocto_raytracing_b200.scene import FlatScene
+    flat2 = FlatScene._normalise(a)
+    e = _emu.EmuScene(flat2)
+    img0, r0 = e.render(160, 90, 1)
+    entries, fallback, n_grids, nodes = _emu.set_grids(e, 64, 3)
+    assert n_grids == len(lights) - 1
+    img1, r1 = e.render(160, 90, 1)
+    assert np.array_equal(img0, img1) and r0[:3] == r1[:3]

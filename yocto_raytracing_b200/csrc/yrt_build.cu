@@ -752,17 +752,18 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
 }
 
 // The apex grid of one frame's camera (pinhole = eval_camera's ray origin, src/raytrace.cpp:6-37): cells are tiles of
-// 2^shift x 2^shift pixels.  Rebuilt for every frame — the camera is an argument of the render call — on the frame's own
-// stream ahead of the primary-ray kernel: a memset and six small launches, no host synchronisation.
+// 2^shift x 2^shift pixels.  Rebuilt for every frame — the camera is an argument of the render call — on `st` (the scene's grid
+// stream, see render_rows_device): a memset and three small launches, no host synchronisation.
 int camera_grid_enqueue(DevScene& ds, const camera_k& cam, int width, int height, cudaStream_t st, GridRef* out) {
     *out = gridref_none();
     auto env_or = [](const char* name, int def, int lo, int hi) { const char* e = getenv(name); return std::min(std::max(e ? atoi(e) : def, lo), hi); };
     if (!ds.grids_allowed || ds.n_active <= 0 || env_or("YRT_CAM_GRID", 1, 0, 1) == 0) return YRT_OK;
-    const int shift = env_or("YRT_CAM_CELL_SHIFT", 3, 0, 8);
+    int shift = env_or("YRT_CAM_CELL_SHIFT", 3, 0, 8);
     const float reach = ds.extent + fmaxf(fmaxf(fabsf(cam.frame.o.x), fabsf(cam.frame.o.y)), fabsf(cam.frame.o.z));
     if (!(reach < 1.0e18f)) return YRT_OK;
-    const long long cells = (long long)((width + (1 << shift) - 1) >> shift) * ((height + (1 << shift) - 1) >> shift);
-    if (cells > (1ll << 24)) return YRT_OK;
+    auto cells_at = [&](int sh) { return (long long)((width + (1 << sh) - 1) >> sh) * ((height + (1 << sh) - 1) >> sh); };
+    while (shift < 12 && cells_at(shift) > (1ll << 18)) shift++;      // at most 262 144 cells (8x8-pixel cells up to 4K frames): 16 slots x 40 B each
+    const long long cells = cells_at(shift);
     const int K = 16;                                                 // slots per cell (YRT_PGRID_MAX_LIST or fewer candidates are served)
     const int capacity = (int)(K * cells);
     PGridArrays a;

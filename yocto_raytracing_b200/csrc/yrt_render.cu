@@ -749,13 +749,15 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
         YRT_CUDA(cudaEventCreateWithFlags(&ds.ev_grid, cudaEventDisableTiming));
         for (int k = 0; k < 4; k++) YRT_CUDA(cudaEventCreateWithFlags(&ds.ev_primary_done[k], cudaEventDisableTiming));
     }
+    const bool own_stream = env_int("YRT_GRID_STREAM", 1) != 0;
+    cudaStream_t gst = own_stream ? ds.grid_stream : st;
     for (int k = 0; k < 4; k++)
-        if (ds.primary_recorded[k]) { YRT_CUDA(cudaStreamWaitEvent(ds.grid_stream, ds.ev_primary_done[k], 0)); ds.primary_recorded[k] = false; }
+        if (ds.primary_recorded[k]) { if (own_stream) YRT_CUDA(cudaStreamWaitEvent(ds.grid_stream, ds.ev_primary_done[k], 0)); ds.primary_recorded[k] = false; }
     // (no event span around it: on its own stream the three small kernels wait for SMs the previous frame's persistent kernels
     //  hold, so a span would measure that wait; their own time is in the ncu launch lists, 39 us)
-    YRT_TRY(camera_grid_enqueue(ds, rp.cam, rp.width, rp.height, ds.grid_stream, &cam_grid));
+    YRT_TRY(camera_grid_enqueue(ds, rp.cam, rp.width, rp.height, gst, &cam_grid));
     if (pt.on && cam_grid.nx > 0) pt.extra_launches += 3;    // scatter, scatter (large instances), emit
-    if (cam_grid.nx > 0) {
+    if (cam_grid.nx > 0 && own_stream) {
         YRT_CUDA(cudaEventRecord(ds.ev_grid, ds.grid_stream));
         YRT_CUDA(cudaStreamWaitEvent(st, ds.ev_grid, 0));
     }
