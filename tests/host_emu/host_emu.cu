@@ -328,7 +328,7 @@ int emu_set_grids(void* p, int light_R, int cam_shift, int64_t* stats) {
     const bool lights_on = light_R > 0 && es->hs.all_rigid && na > 0;
     // room for the chain nodes behind the trees (same regions as build_device_scene)
     const int n_grids = lights_on ? std::min(n_lights, YRT_MAX_LIGHT_GRIDS) : 0;
-    es->light_node_cap = n_grids ? n_grids * 6 * light_R * light_R * 3 / 4 + 1024 : 0;
+    es->light_node_cap = n_grids ? (getenv("YRT_LIGHT_GRID_NODES") ? atoi(getenv("YRT_LIGHT_GRID_NODES")) : n_grids * 6 * light_R * light_R * 3 / 4 + 1024) : 0;
     const size_t total_nodes = (size_t)es->tree_nodes + es->light_node_cap;
     es->nodes2.resize(YRT_NODE_STRIDE(2) * total_nodes, mk4(0, 0, 0, 0));
     es->nodes4.resize(YRT_NODE_STRIDE(4) * total_nodes, mk4(0, 0, 0, 0));
@@ -345,7 +345,7 @@ int emu_set_grids(void* p, int light_R, int cam_shift, int64_t* stats) {
             if (!identity) continue;
             const vec3 apex = mk3(lr[4].x + lr[3].x, lr[4].y + lr[3].y, lr[4].z + lr[3].z);
             const float reach = es->extent + fmaxf(fmaxf(fabsf(apex.x), fabsf(apex.y)), fabsf(apex.z));
-            emu_build_grid(pgrid_cube_desc(apex, light_R, reach, 4 * 6 * light_R * light_R), es->inst_box, na, YRT_WIDE_ANY, arr.data(), es->tree_nodes,
+            emu_build_grid(pgrid_cube_desc(apex, light_R, reach, getenv("YRT_LIGHT_GRID_KEYS") ? atoi(getenv("YRT_LIGHT_GRID_KEYS")) : 4 * 6 * light_R * light_R), es->inst_box, na, YRT_WIDE_ANY, arr.data(), es->tree_nodes,
                            es->light_node_cap, &node_total, es->view.tlas_root, es->light_grids[k]);
             es->lg.g[k] = es->light_grids[k].ref();
             ne += es->light_grids[k].n_entries; nf += es->light_grids[k].n_fallback_cells; nl++; nn += es->light_grids[k].n_nodes;

@@ -574,7 +574,8 @@ def test_apex_grids_do_not_change_the_frame(gpu, monkeypatch, maker, w, h, s):
         a, sa = scn.render(w, h, s, 0.1)
         ia, da, _ = scn.trace_primary(w, h, s)
     for env in ({"YRT_PGRID": "0"}, {"YRT_CAM_CELL_SHIFT": "0", "YRT_LIGHT_GRID_R": "16"}, {"YRT_CAM_CELL_SHIFT": "5", "YRT_LIGHT_GRID_R": "256"},
-                {"YRT_PGRID_MIN_INSTANCES": "1000000"}, {"YRT_LIGHT_GRID_R": "8", "YRT_CAM_CELL_SHIFT": "8"}):
+                {"YRT_PGRID_MIN_INSTANCES": "1000000"}, {"YRT_LIGHT_GRID_R": "8", "YRT_CAM_CELL_SHIFT": "8"},
+                {"YRT_LIGHT_GRID_NODES": "300", "YRT_LIGHT_GRID_KEYS": "2000"}, {"YRT_GRID_STREAM": "0", "YRT_STREAMS": "3"}):   # no room for most cells' chains; grid on the frame's stream
         monkeypatch.setenv("YRT_PGRID_MIN_INSTANCES", "1")
         for k, v in env.items():
             monkeypatch.setenv(k, v)

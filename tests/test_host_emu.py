@@ -221,3 +221,22 @@ def test_apex_grids_skip_rotated_lights():
     assert n_grids == len(lights) - 1
     img1, r1 = e.render(160, 90, 1)
     assert np.array_equal(img0, img1) and r0[:3] == r1[:3]
+
+
+def test_apex_grids_without_room(monkeypatch):
+    """Cells that find no room for their keys or chain nodes (and cells with too many candidates) start at the tree's root:
+    tiny capacities must cost speed only, never a hit."""
+    flat, ref = load_golden("instance10000")
+    e = _emu.EmuScene(flat)
+    ids0, d0, _, _ = e.trace_primary(160, 90, 1)
+    img0, r0 = e.render(160, 90, 1)
+    for env in ({"YRT_LIGHT_GRID_NODES": "500"}, {"YRT_LIGHT_GRID_KEYS": "3000"}, {"YRT_LIGHT_GRID_NODES": "1", "YRT_LIGHT_GRID_KEYS": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        entries, fallback, n_grids, nodes = _emu.set_grids(e, 64, 6)        # (64-pixel camera cells: many hold more than 16 candidates)
+        for k in env:
+            monkeypatch.delenv(k)
+        assert fallback > 0, env
+        ids1, d1, _, _ = e.trace_primary(160, 90, 1)
+        img1, r1 = e.render(160, 90, 1)
+        assert np.array_equal(ids0, ids1) and np.array_equal(d0, d1) and np.array_equal(img0, img1), env

@@ -547,13 +547,14 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
         const vec3 apex = mk3(lr[4].x + lr[3].x, lr[4].y + lr[3].y, lr[4].z + lr[3].z);
         const float reach = hs.extent + fmaxf(fmaxf(fabsf(apex.x), fabsf(apex.y)), fabsf(apex.z));
         if (!(reach < 1.0e18f)) continue;
-        lga[k].d = pgrid_cube_desc(apex, light_R, reach, 4 * 6 * light_R * light_R);
+        lga[k].d = pgrid_cube_desc(apex, light_R, reach, env_or("YRT_LIGHT_GRID_KEYS", 4 * 6 * light_R * light_R, 1, 1 << 28));   // (the switch: tests of the overflow path)
         lg_on[k] = true;
         n_light_grids++;
     }
     // the chain nodes of the light grids live behind the two trees in the node array the any-hit rays walk
     const int grid_node_first = nb_int + nt_int + 2;
-    const int light_node_cap = n_light_grids ? (int)std::min<long long>((long long)n_light_grids * 6 * light_R * light_R * 3 / 4 + 1024, 1 << 26) : 0;
+    // (cells that find no room — keys or chain nodes — start at the tree's root like cells that are not served; YRT_LIGHT_GRID_NODES: tests)
+    const int light_node_cap = n_light_grids ? env_or("YRT_LIGHT_GRID_NODES", (int)std::min<long long>((long long)n_light_grids * 6 * light_R * light_R * 3 / 4 + 1024, 1 << 26), 1, 1 << 26) : 0;
     const size_t n_nodes4 = (size_t)grid_node_first + (YRT_WIDE_ANY == 4 ? light_node_cap : 0);
     const size_t n_nodes2 = (size_t)grid_node_first + (YRT_WIDE_ANY == 2 ? light_node_cap : 0);
     int* d_light_node_total = nullptr;
