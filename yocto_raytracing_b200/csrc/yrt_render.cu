@@ -716,6 +716,10 @@ int render_rows_device(DevScene& ds, const RenderParams& rp, float4* d_out, cuda
     const bool to_host = rp.h_rgba != nullptr || rp.h_ldr != nullptr;
     const int n_pipes = std::max(1, std::min(std::min(4, own), env_int("YRT_STREAMS", stats ? 1 : YRT_DEFAULT_STREAMS)));
     if (n_pipes > 1) batch_rows = std::min(batch_rows, (own + n_pipes - 1) / n_pipes);
+    // rows that go on to the host: two batches per pipeline, so that the copy left exposed at the end of the frame (the last
+    // batch's) is a quarter of the frame, not half (tools/e2e_streams.py: 10.44 -> 10.37 ms per 1080p frame end to end)
+    // (only for large shares: the launches of a small share are short as it is)
+    if (n_pipes > 1 && to_host && !rp.scatter && (long long)own * rp.width * spp >= (16ll << 20)) batch_rows = std::min(batch_rows, (own + 2 * n_pipes - 1) / (2 * n_pipes));
     size_t cap_slots = (size_t)batch_rows * rp.width * spp;
     YRT_TRY(ensure_workspace(ds, ds.ws, cap_slots, nl, depth_cap, reflective));
     for (int k = 1; k < n_pipes; k++) {
