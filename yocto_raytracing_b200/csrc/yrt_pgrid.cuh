@@ -1,23 +1,29 @@
-// yrt_pgrid.cuh — apex grids: a small instance tree per cell of directions, for rays that all pass through one point.
+// yrt_pgrid.cuh — apex grids: the instance level decided per cell of directions, for rays that all pass through one point.
 //
 // Every camera ray of raytrace() starts at the pinhole (eval_camera, src/raytrace.cpp:6-37: the reference ignores the
 // aperture), and every shadow ray of shade() ends at a point light (src/raytrace.cpp:126-133).  For such a bundle most of
 // the instance level of the two-level BVH (intersect_bvh(scene…), src/scene.cpp:446-479) can be decided once per
 // direction instead of once per ray: the directions through the apex are cut into cells (pixel tiles of the image plane
-// for the camera, the six faces of a cube around a light), every cell gets the list of the instances whose world box a ray
-// of that cell can touch, nearest first, and that list is written out as a short chain of ordinary traversal nodes
-// (instance leaves + "the rest of the list") in the scene's node array.  A ray looks up the root of its cell and walks
-// from there with the unchanged traversal code — same node visit, same slab test and accept rule, same instance entry
-// (exact transform_ray_inverse) — instead of starting at the root of the instance tree: 2-3 box tests instead of 25-35.
-// What a ray finds is unchanged: a cell's list is a superset of the instances the full tree walk would reach for any of
-// its rays (conservative margins below; audited on the host emulation against the tree walk), the primitive tests are the
-// same, ties are settled by the rank tables, and rays or cells the grids cannot serve start at the tree's root as before.
+// for the camera, the six faces of a cube around a light), and every cell gets the list of the instances whose world box a
+// ray of that cell can touch, nearest first, each with the part of its box the cell's pyramid can reach.  Two forms:
+//   * list form (camera grid): cells[n_cells] = (first entry, count), entries = (clipped box | instance slot | distance
+//     bound); a ray walks its cell's entries in order (Tracer<…, GRID>, yrt_trace.cuh), tests each box with the usual slab
+//     test, enters the instances it touches, and stops at the first entry whose bound lies beyond the hit it has.  A warp
+//     is two neighbouring pixels, i.e. one cell: the walk is coherent;
+//   * chain form (light grids): the list is written out as a short chain of ordinary traversal nodes (instance leaves +
+//     "the rest of the list") behind the trees in the scene's node array, roots[n_cells] holds where a ray of the cell
+//     starts (YRT_REF_DONE for an empty cell) — the traversal code is unchanged, the ray just does not start at the
+//     instance tree's root, and chain visits share the instruction stream with the shape-tree visits of other lanes.
+// Either way a ray does 2-4 box tests at the instance level instead of 25-35.  What it finds is unchanged: a cell's list
+// is a superset of the instances the full tree walk would reach for any of its rays (conservative margins below; audited
+// on the host emulation against the tree walk), the primitive tests are the same, ties are settled by the rank tables,
+// and rays or cells the grids cannot serve (too many candidates, no room, near-axis-parallel directions, rotated lights,
+// mirror rays) start at the tree's root as before.
 //
-// Per grid in HBM: roots[n_cells] (a node reference per cell: YRT_REF_DONE for an empty cell, the instance tree's root
-// for a cell that is not served) and the chain nodes, appended to the scene's node array of the arity the ray kind walks.
-// Built on the device: count (one warp per instance, lanes over the cells its projection covers) -> allocate (one thread
-// per cell, one atomic per warp) -> fill -> per cell: insertion sort by distance bound, node chain.
-// The light grids are part of the scene build; the camera grid is rebuilt for every frame (the camera is a per-call argument).
+// Built on the device.  Light grids, with the scene: count (one warp per instance, lanes over the cells its projection
+// covers; instances covering more than YRT_PGRID_BIG cells by a whole grid of threads) -> allocate (one atomic per warp)
+// -> fill -> per cell: insertion sort by distance bound, node chain.  Camera grid, EVERY frame (the camera is a per-call
+// argument): one scatter pass into 16 fixed slots per cell, then one thread per slot writes its entry at its rank.
 //
 // Item functions are __host__ __device__ like the LBVH's: kernels call them per thread, tests/host_emu in serial loops.
 #pragma once
