@@ -240,3 +240,30 @@ def test_apex_grids_without_room(monkeypatch):
         ids1, d1, _, _ = e.trace_primary(160, 90, 1)
         img1, r1 = e.render(160, 90, 1)
         assert np.array_equal(ids0, ids1) and np.array_equal(d0, d1) and np.array_equal(img0, img1), env
+
+
+def test_apex_grids_lights_anywhere():
+    """Point lights inside the object layer, inside / at an instance, and very far away: frames with the light grids equal the
+    tree walk's bit for bit (boxes around the light go into every cell; margins scale with the extent of the scene)."""
+    from yocto_raytracing_b200 import synth
+    from yocto_raytracing_b200.scene import FlatScene
+    rng = np.random.default_rng(11)
+    for trial in range(8):
+        flat = synth.instance_grid_scene(12, seed=3 + trial).flat()
+        a = {k: v.copy() for k, v in flat.arrays.items()}
+        fr = a["inst_frame"].reshape(-1, 12)
+        for li in flat.light_instances():
+            mode = trial % 4
+            if mode == 0:
+                fr[li, 9:12] = rng.uniform(-10, 10, 3) * np.array([1, 0.15, 1]) + np.array([0, 1.0, 0])
+            elif mode == 1:
+                fr[li, 9:12] = fr[int(rng.integers(0, len(fr) - 4)), 9:12] + rng.uniform(-0.3, 0.3, 3)
+            elif mode == 2:
+                fr[li, 9:12] = rng.uniform(-1, 1, 3) * 1e4
+            else:
+                fr[li, 9:12] = rng.uniform(-20, 20, 3) + np.array([0, 25, 0])
+        e = _emu.EmuScene(FlatScene._normalise(a))
+        img0, r0 = e.render(96, 54, 1)
+        _emu.set_grids(e, int(rng.choice([8, 64, 128])), int(rng.integers(0, 5)))
+        img1, r1 = e.render(96, 54, 1)
+        assert np.array_equal(img0, img1) and r0[:3] == r1[:3], trial
