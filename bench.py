@@ -505,6 +505,10 @@ def run_b200(args):
         flops_src, flops_per_ray = "REFERENCE-BVH work per ray (SURVEY 8d, 2.45 kflop averaged over primary and shadow rays) — not this build's own count", REF_FLOPS_PER_RAY
     roofline = {
         "kernel": "k_trace_any_lights", "bound": "fp32",
+        "note": "achieved / frac count the kernel's OWN arithmetic (device counters), as round 1's review asked; SURVEY 8d's own definition (rays x the "
+                "2.45 kflop the REFERENCE's tree needs per ray) is in reference_bvh_equivalent.  The two move in opposite directions when work is removed: "
+                "the apex grids of round 2 cut the shadow kernel's own work from 1.22 to 0.67 kflop per ray, so its own-counter fraction fell (0.27 -> 0.17) "
+                "while its rays/s rose by 35 % and the 8d fraction went from 0.45 to 0.62",
         "bound_note": "FP32 instruction issue + L1 data-path wavefronts — neither hbm nor tensor (SURVEY 8d): the scene is cache resident and nothing is a contraction",
         "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
         "algorithmic_flops_per_ray": flops_per_ray, "algorithmic_flops_source": flops_src,
