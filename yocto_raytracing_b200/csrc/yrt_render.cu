@@ -525,13 +525,34 @@ static int ensure_pstack_level(DevScene& ds, Workspace& w, int level, cudaStream
     return YRT_OK;
 }
 
+static int persistent_grid(DevScene& ds, const void* kernel);
+
+// Everything the first frame of that size would otherwise pay for inside the render call: the workspace, the camera grid's
+// buffers, and the frame kernels' modules (CUDA loads a kernel lazily at its first launch or attribute query).
 int presize_workspace_device(DevScene& ds, int width, int height, int samples) {
     RenderParams rp;
     rp.width = width; rp.height = height; rp.samples = samples; rp.tile_rows = std::max(height, 1); rp.rank = 0; rp.world = 1;
     YRT_CUDA(cudaSetDevice(ds.device));
     int depth_cap = std::min(YRT_MAX_WAVES, std::max(1, env_int("YRT_MAX_DEPTH", YRT_MAX_WAVES)));
     size_t cap_slots = (size_t)batch_rows_for(rp, ds.view.n_lights, height, ds.has_reflective) * width * samples * samples;
-    return ensure_workspace(ds, ds.ws, cap_slots, ds.view.n_lights, depth_cap, ds.has_reflective);
+    YRT_TRY(ensure_workspace(ds, ds.ws, cap_slots, ds.view.n_lights, depth_cap, ds.has_reflective));
+    if (!ds.grid_closest_primary) ds.grid_closest_primary = persistent_grid(ds, (const void*)k_trace_closest<true>);
+    if (!ds.grid_closest_queue) ds.grid_closest_queue = persistent_grid(ds, (const void*)k_trace_closest<false>);
+    if (!ds.grid_any) ds.grid_any = persistent_grid(ds, (const void*)k_trace_any_lights);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, (const void*)k_shade);
+    cudaFuncGetAttributes(&fa, (const void*)k_resolve);
+    cudaFuncGetAttributes(&fa, (const void*)k_tonemap);
+    {   // a camera grid for a stand-in camera of this frame size: allocates the grid's buffers and loads its kernels
+        camera_k c;
+        c.frame.x = mk3(1.f, 0.f, 0.f); c.frame.y = mk3(0.f, 1.f, 0.f); c.frame.z = mk3(0.f, 0.f, 1.f); c.frame.o = mk3(0.f, 0.f, 0.f);
+        c.h = 1.0f; c.w = (float)width / (float)std::max(height, 1); c.focus = 1.0f;
+        GridRef g;
+        YRT_TRY(camera_grid_enqueue(ds, c, width, height, ds.stream, &g));
+        YRT_CUDA(cudaStreamSynchronize(ds.stream));
+    }
+    cudaGetLastError();
+    return YRT_OK;
 }
 
 static int persistent_grid(DevScene& ds, const void* kernel) {

@@ -18,6 +18,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <cstring>
 #include <cctype>
 #include <cstdlib>
 
@@ -144,11 +145,13 @@ int main(int argc, char** argv) {
     printf("tracing scene\n");
     float ambient[3] = {amb, amb, amb};
     yrt_stats st;
+    memset(&st, 0, sizeof(st));
+    yrt_stats* want = verbose ? &st : nullptr;     // (without per-kernel statistics the frame runs as two overlapping pipelines)
     int rc;
     if (ldr_on_device) {
-        rc = yrt_render_ldr(gscn, &flat.cam, ambient, width, resolution, samples, (uint8_t*)ldr.pixels.data(), nullptr, &st);
+        rc = yrt_render_ldr(gscn, &flat.cam, ambient, width, resolution, samples, (uint8_t*)ldr.pixels.data(), nullptr, want);
     } else {
-        rc = yrt_render(gscn, &flat.cam, ambient, width, resolution, samples, (float*)hdr.pixels.data(), &st);
+        rc = yrt_render(gscn, &flat.cam, ambient, width, resolution, samples, (float*)hdr.pixels.data(), want);
     }
     if (rc != YRT_OK) {
         printf("%s\n", yrt_last_error());
