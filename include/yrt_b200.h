@@ -261,6 +261,12 @@ int yrt_intersect_first(yrt_scene* scn, const float* rays, int64_t n, int32_t* i
                         float* dist_out, float* uv_out);
 int yrt_intersect_any(yrt_scene* scn, const float* rays, int64_t n, uint8_t* occluded_out);
 
+/* Mirror bounces the LAST frame of yrt_render / yrt_render_ldr dropped at the recursion cap, summed over the GPUs — the same
+ * number as yrt_stats.truncated_paths, for callers that render without per-call statistics (a frame without statistics runs as
+ * two overlapping pipelines and reads nothing back).  Waits for the devices; one 40-byte read per GPU.  0 = the frame is what
+ * the reference's unbounded recursion (src/raytrace.cpp:190-204) gives.  The drop-in CLI warns whenever it is not 0. */
+int yrt_frame_truncated_paths(yrt_scene* scn, int64_t* out);
+
 /* Per-ray work counters of the traversal kernels, for the roofline record ("the builder must also report its
  * own per-ray counters"; the reference's sit at src/scene.cpp:371,229,468).  Only a library built with -DYRT_COUNTERS=1
  * counts (tools/build_variants.sh; never the timed build): the regular build returns YRT_ERR_UNSUPPORTED.  out = 3 kernel

@@ -189,6 +189,33 @@ def test_edge_cases(gpu, oracle_mod):
     assert img[18, 32, 0] == np.float32(0.2) * np.float32(0.5)
 
 
+def test_truncated_paths_are_reported_without_statistics(gpu, monkeypatch):
+    """The recursion cap is this path's one deliberate difference from the reference's unbounded shade() recursion
+    (src/raytrace.cpp:190-204): a frame rendered WITHOUT per-call statistics must still be able to say how many mirror
+    bounces it dropped (yrt_frame_truncated_paths; the CLI's warning), and the count equals the one in yrt_stats."""
+    flat, _ = load_golden("refl")             # a mirror floor under matte objects: exactly one bounce
+    with gpu.Scene(flat) as scn:
+        assert scn.truncated_paths() == 0                       # nothing rendered yet
+        a, sa = scn.render(160, 90, 2, 0.1)
+        assert sa.truncated_paths == 0 and scn.truncated_paths() == 0 and sa.max_depth == 2 and sa.reflection_rays > 0
+        monkeypatch.setenv("YRT_MAX_DEPTH", "1")                # no bounce at all: every mirror ray of frame a is dropped
+        b, sb = scn.render(160, 90, 2, 0.1)
+        assert sb.truncated_paths == sa.reflection_rays and sb.reflection_rays == 0 and sb.max_depth == 1
+        assert scn.truncated_paths() == sb.truncated_paths
+        c, _ = scn.render(160, 90, 2, 0.1, want_stats=False)    # two pipelines, nothing read back by the call itself
+        assert scn.truncated_paths() == sb.truncated_paths
+        assert np.array_equal(b.view(np.uint32), c.view(np.uint32)) and not np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        monkeypatch.delenv("YRT_MAX_DEPTH")
+        d, _ = scn.render(160, 90, 2, 0.1, want_stats=False)
+        assert scn.truncated_paths() == 0 and np.array_equal(a.view(np.uint32), d.view(np.uint32))
+    flat, _ = load_golden("mixed7")           # facing mirrors: the reference recurses hundreds of levels, the default cap is 64
+    with gpu.Scene(flat) as scn:
+        _, st = scn.render(160, 90, 2, 0.1)
+        assert st.truncated_paths > 0 and st.max_depth == 64
+        scn.render(160, 90, 2, 0.1, want_stats=False)
+        assert scn.truncated_paths() == st.truncated_paths
+
+
 def test_device_tonemap_vs_reference_tonemap(gpu, oracle_mod):
     _, ref = load_golden("simple")
     a = gpu.tonemap(ref["image"])

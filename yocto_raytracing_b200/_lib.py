@@ -103,6 +103,7 @@ SYMBOLS = {
     "yrt_tonemap": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "yrt_scene_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "yrt_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "yrt_frame_truncated_paths": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "yrt_counters_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "yrt_debug_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "yrt_debug_read_nodes": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),

@@ -181,6 +181,18 @@ int yrt_counters_read(yrt_scene* scn, uint64_t out[24]) {
     return read_counters_device(*scn->dev[0], out);
 }
 
+int yrt_frame_truncated_paths(yrt_scene* scn, int64_t* out) {
+    if (!scn || scn->dev.empty() || !out) { set_error("yrt_frame_truncated_paths: bad arguments"); return YRT_ERR_INVALID; }
+    int64_t total = 0;
+    for (DevScene* ds : scn->dev) {
+        int64_t n = 0;
+        YRT_TRY(read_truncated_device(*ds, &n));
+        total += n;
+    }
+    *out = total;
+    return YRT_OK;
+}
+
 int yrt_write_png(const char* path, const uint8_t* rgba8, int width, int height, int threads, int level) {
     return write_png_parallel(path, rgba8, width, height, threads, level <= 0 ? 1 : (level > 9 ? 9 : level));
 }

@@ -175,6 +175,8 @@ int collect_stats_device(DevScene& ds, const RenderParams& rp, yrt_stats* stats)
 int presize_workspace_device(DevScene& ds, int width, int height, int samples);
 // per-ray work counters (-DYRT_COUNTERS=1 builds): 3 kernel classes x 8 words, read and reset
 int read_counters_device(DevScene& ds, uint64_t out[24]);
+// mirror bounces the last stand-alone frame of this device dropped at the recursion cap (waits for the device)
+int read_truncated_device(DevScene& ds, int64_t* out);
 int stats_begin_device(DevScene& ds);
 int stats_end_device(DevScene& ds, yrt_stats* stats);
 int trace_primary_device(DevScene& ds, const RenderParams& rp, int32_t* h_ids, float* h_dist, float* h_uv);

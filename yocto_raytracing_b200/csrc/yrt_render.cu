@@ -863,6 +863,17 @@ int read_counters_device(DevScene& ds, uint64_t out[24]) {
 #endif
 }
 
+int read_truncated_device(DevScene& ds, int64_t* out) {
+    *out = 0;
+    if (!ds.timer || !ds.ws.stats.p) return YRT_OK;   // nothing rendered yet (the counters are cleared at the start of a frame)
+    YRT_CUDA(cudaSetDevice(ds.device));
+    YRT_CUDA(cudaDeviceSynchronize());
+    FrameCounters fc;
+    YRT_CUDA(cudaMemcpy(&fc, ds.ws.stats.p, sizeof(fc), cudaMemcpyDeviceToHost));
+    *out = (int64_t)fc.truncated;
+    return YRT_OK;
+}
+
 int stats_begin_device(DevScene& ds) {
     if (!ds.timer) ds.timer = new PhaseTimer();
     PhaseTimer& pt = *ds.timer;

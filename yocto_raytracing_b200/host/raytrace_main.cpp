@@ -158,6 +158,11 @@ int main(int argc, char** argv) {
         exit(1);
     }
     double t_traced = now_ms();
+    // mirror bounces dropped at the recursion cap (only scenes with mirrors can have any; one small read per GPU)
+    int64_t truncated = st.truncated_paths;
+    bool mirrors = false;
+    for (float kr : flat.mat_kr) mirrors = mirrors || kr > 0.0f;   // src/raytrace.cpp:190
+    if (!verbose && mirrors && yrt_frame_truncated_paths(gscn, &truncated) != YRT_OK) truncated = 0;
     yrt_scene_destroy(gscn);
 
     printf("saving image %s\n", imageout.c_str());
@@ -172,9 +177,9 @@ int main(int argc, char** argv) {
     else save_hdr_or_ldr(imageout, hdr);
     double t_saved = now_ms();
 
-    if (verbose && st.truncated_paths > 0)
-        printf("note: %lld mirror bounce(s) were cut at the recursion cap of this path (YRT_MAX_DEPTH, default 64); the reference recurses without a bound\n",
-               (long long)st.truncated_paths);
+    if (truncated > 0)
+        fprintf(stderr, "warning: %lld mirror bounce(s) were cut at the recursion cap of this path (YRT_MAX_DEPTH, default 64); the reference recurses without a bound\n",
+                (long long)truncated);
     if (verbose) {
         long long rays = (long long)(st.primary_rays + st.reflection_rays + st.shadow_rays);
         double ms = t_traced - t_built;

@@ -97,6 +97,13 @@ class Scene:
                                          C.c_void_p(out.ctypes.data), None, C.byref(st) if st is not None else None))
         return out, st
 
+    def truncated_paths(self) -> int:
+        """yrt_frame_truncated_paths: mirror bounces the last frame dropped at the recursion cap (0 = the frame is what the
+        reference's unbounded recursion gives, src/raytrace.cpp:190-204)."""
+        n = C.c_int64(0)
+        check(_lib.load().yrt_frame_truncated_paths(self._h, C.byref(n)))
+        return int(n.value)
+
     def raytrace(self, amb: float, resolution: int, samples: int) -> np.ndarray:
         """image4f raytrace(scn, {amb,amb,amb}, resolution, samples) — src/raytrace.cpp:213."""
         w, h = self.image_size(resolution)
