@@ -149,15 +149,15 @@ int yrt_scene_prepare(yrt_scene* scn, int width, int height, int samples);
 /* Number of instances whose frame is not rigid (x, y, z orthonormal within 1e-4).  The reference hands every instance
  * the ray through transform_ray_inverse (src/vmath.h:275-278: dot products with the frame axes, direction re-normalised),
  * which is the inverse only of a rigid frame, and then compares the LOCAL hit distances of different instances with each
- * other and with the world-space boxes (src/scene.cpp:468-473): for scaled or sheared frames its result depends on the
- * order in which its own BVH happens to visit the instances, which no other tree can reproduce.  This library reproduces
- * the reference for rigid frames (every scene of the reference; its OBJ `i` lines and glTF node transforms may carry
- * others) and REJECTS scenes with non-rigid frames: yrt_scene_create returns YRT_ERR_UNSUPPORTED, unless the caller has
- * opted in with yrt_set_option("allow_nonrigid", 1) — then the same per-instance arithmetic runs in this library's visit
- * order and the image may differ from the reference's where such instances overlap.  Pure host function, needs no GPU. */
+ * other and with the world-space boxes (src/scene.cpp:468-473): for scaled or sheared frames (its OBJ `i` lines and glTF node
+ * transforms may carry them; none of its own scenes does) what it returns depends on which instances its own BVH lets a
+ * ray test, and in which order.  A scene with such frames is therefore traced through a copy of the reference's own
+ * instance tree — same nodes, same boxes, same slab test, same stack order — and matches the reference like any other
+ * scene; it only runs slower (no LBVH over the instances, no apex grids).  This count tells a caller which case it is in.
+ * Pure host function, needs no GPU. */
 int yrt_desc_nonrigid_instances(const yrt_scene_desc* desc);
 /* process-wide options; unknown names return YRT_ERR_INVALID.
- *   "allow_nonrigid"  (0/1, default 0): see above.
+ *   "allow_nonrigid"  accepted and ignored (ABI 1 refused scenes with non-rigid instance frames unless this was set).
  *   "pin_host_frames" (0/1, default 0): yrt_render / yrt_render_ldr page-lock the caller's output buffer the first time they
  *                     see it and keep it registered while the same buffer keeps coming back (device->host copies into
  *                     pageable memory are staged by the driver).  The registration outlives the call: only for callers

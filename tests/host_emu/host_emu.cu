@@ -161,6 +161,8 @@ struct EmuScene {
     std::vector<int> prim_rank, inst_rank;
     std::vector<float4> nodes2, nodes4;   // BLAS nodes then TLAS nodes, like the device arrays
     SceneView view;
+    RefTlas ref = {nullptr, nullptr, nullptr, 0};   // scenes with non-rigid instance frames (mirrors build_device_scene + k_slot_of_inst)
+    std::vector<int> slot_of_inst;
     int blas_depth = 0, tlas_depth = 0, stack_need = 0;
 };
 
@@ -258,6 +260,12 @@ int emu_build(const yrt_scene_desc* d, EmuScene& es, int leaf_blas, int leaf_tla
         es.inst_box[2 * (size_t)k] = mk4(cx, cy, cz, 0.f);
         es.inst_box[2 * (size_t)k + 1] = mk4(hx, hy, hz, 0.f);
     }
+    if (!hs.all_rigid && hs.n_instances > 0 && !getenv("YRT_EMU_NO_REF_TLAS")) {   // (the switch: tests show that the LBVH alone does not reproduce such scenes)
+        es.slot_of_inst.assign(hs.n_instances, -1);
+        for (int k = 0; k < na; k++) es.slot_of_inst[hs.active_inst[items[es.tlas.order[k]].active]] = k;
+        es.ref.nodes = hs.ref_nodes.data(); es.ref.leaf_inst = hs.ref_leaf_inst.data(); es.ref.slot_of_inst = es.slot_of_inst.data();
+        es.ref.n_nodes = (int)(hs.ref_nodes.size() / 2);
+    }
     es.extent = hs.extent;
     es.tree_nodes = nb_int + (na > 1 ? na - 1 : 1) + 2;
     for (int k = 0; k < YRT_MAX_LIGHT_GRIDS; k++) es.lg.g[k] = gridref_none();
@@ -307,6 +315,17 @@ GridRef emu_camera_ref(const EmuScene& es, const EmuGrid& g) {
     GridRef r = g.ref();
     r.shift = es.cam_shift;
     return r;
+}
+
+// the kernels' choice (run_batch / intersect_rays_device in yrt_render.cu): scenes with non-rigid frames walk the reference's instance tree
+bool emu_closest(const EmuScene& es, const GridRef& cg, const ray3& ray, int i, int j, bool primary, HitRec& h, int* stack, TraceCounters* tc) {
+    if (es.ref.n_nodes > 0) { int tstack[YRT_REF_TLAS_STACK]; return trace_ray_ref<false>(es.view, es.ref, ray, h, stack, tstack, tc); }
+    if (primary) { trace_camera_ray(es.view, cg, ray, i, j, h, stack, tc); return h.si >= 0; }
+    return trace_ray<false>(es.view, ray, h, stack, tc);
+}
+bool emu_any(const EmuScene& es, const ray3& ray, HitRec& h, int* stack, TraceCounters* tc) {
+    if (es.ref.n_nodes > 0) { int tstack[YRT_REF_TLAS_STACK]; return trace_ray_ref<true>(es.view, es.ref, ray, h, stack, tstack, tc); }
+    return trace_ray<true>(es.view, ray, h, stack, tc);
 }
 
 }  // namespace
@@ -403,7 +422,7 @@ int emu_trace_primary(void* p, const yrt_camera* cam, int width, int height, int
                     ray3 ray = eval_camera(ck, u, v);
                     HitRec h;
                     TraceCounters tc = {0, 0, 0, 0, 0, 0, 0, 0};
-                    trace_camera_ray(es->view, cg, ray, i, j, h, stack, &tc);
+                    emu_closest(*es, cg, ray, i, j, true, h, stack, &tc);
                     cb += tc.box_tests; cp += tc.prim_tests; ci += tc.inst_entries; cm = std::max(cm, tc.max_stack);
                     cfr += tc.slab_false_rejects; cea += tc.slab_extra_accepts; ctb += tc.tlas_box_tests; cnv += tc.node_visits;
                     hit_to_ids(es->view, h, ids + 3 * r);
@@ -427,11 +446,11 @@ int emu_intersect(void* p, const float* rays, int64_t n, int32_t* ids, float* di
         ray.o = mk3(q[0], q[1], q[2]); ray.d = mk3(q[3], q[4], q[5]); ray.tmin = q[6]; ray.tmax = q[7];
         HitRec h;
         TraceCounters tc = {0, 0, 0, 0, 0, 0, 0, 0};
-        trace_ray<false>(es->view, ray, h, stack, &tc);
+        emu_closest(*es, gridref_none(), ray, 0, 0, false, h, stack, &tc);
         hit_to_ids(es->view, h, ids + 3 * r);
         dist[r] = h.dist;
         HitRec h2;
-        occ[r] = trace_ray<true>(es->view, ray, h2, stack, &tc) ? 1 : 0;
+        occ[r] = emu_any(*es, ray, h2, stack, &tc) ? 1 : 0;
         fr += tc.slab_false_rejects;
     }
     if (false_rejects) *false_rejects = fr;
@@ -469,8 +488,7 @@ int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, in
                     int depth = 0;
                     for (;;) {
                         HitRec h;
-                        if (depth == 0) trace_camera_ray(sv, cg, ray, i, j, h, stack, nullptr);
-                        else trace_ray<false>(sv, ray, h, stack, nullptr);
+                        emu_closest(*es, cg, ray, i, j, depth == 0, h, stack, nullptr);
                         if (depth > 0) n_refl++;
                         if (h.si < 0) { value = mk3(0.f, 0.f, 0.f); break; }
                         int kind;
@@ -481,7 +499,7 @@ int emu_render(void* p, const yrt_camera* cam, const float amb[3], int width, in
                             ray3 sr = shadow_ray(P, l, r);
                             HitRec hr;
                             TraceCounters tc = {0, 0, 0, 0, 0, 0, 0, 0};
-                            vis[k] = trace_shadow_ray(sv, es->lg, k, sr, hr, stack, &tc) ? 0 : 1;
+                            vis[k] = (es->ref.n_nodes > 0 ? emu_any(*es, sr, hr, stack, &tc) : trace_shadow_ray(sv, es->lg, k, sr, hr, stack, &tc)) ? 0 : 1;
                             n_shadow++;
                             sb += tc.box_tests; stb += tc.tlas_box_tests; sp_ += tc.prim_tests; si_ += tc.inst_entries; socc += vis[k] ? 0 : 1; snv += tc.node_visits;
                         }

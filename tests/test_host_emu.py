@@ -267,3 +267,39 @@ def test_apex_grids_lights_anywhere():
         _emu.set_grids(e, int(rng.choice([8, 64, 128])), int(rng.integers(0, 5)))
         img1, r1 = e.render(96, 54, 1)
         assert np.array_equal(img0, img1) and r0[:3] == r1[:3], trial
+
+
+@pytest.mark.parametrize("seed,frame_seed,every,mirror_floor", [(31, 5, 3, False), (7, 1, 2, False), (101, 9, 1, False), (31, 5, 3, True)])
+def test_nonrigid_frames_walk_the_reference_instance_tree(oracle_mod, monkeypatch, seed, frame_seed, every, mirror_floor):
+    """Scaled / sheared instance frames: transform_ray_inverse (src/vmath.h:275-278) does not invert them, so what the reference
+    returns depends on which instances its own tree lets a ray test and in which order (src/scene.cpp:446-479).  The device
+    path walks a copy of that tree (RefTlas, trace_ray_ref) and must agree with the oracle — which is pinned to the
+    unmodified reference on such a scene (test_oracle_vs_live_reference_on_fresh_scenes) — on every ray: ids, distances,
+    barycentrics, shadow rays, mirror rays, the image.  The LBVH alone does not (second half)."""
+    from yocto_raytracing_b200 import synth
+    flat = synth.nonrigid_scene(seed, frame_seed, every, mirror_floor).flat()
+    assert flat.nonrigid_instances() > 0
+    w, h = 128, 72
+    o = oracle_mod.OracleScene(flat)
+    e = _emu.EmuScene(flat)
+    rids, rdist, ruv = o.trace_primary(w, h, 1)
+    ids, dist, uv, ctr = e.trace_primary(w, h, 1)
+    assert np.array_equal(ids, rids) and np.array_equal(dist, rdist) and np.array_equal(uv, ruv) and ctr[4] == 0
+    rimg, rc = o.render(w, h, 2, 0.1, threads=4)
+    img, rays = e.render(w, h, 2, 0.1, max_depth=10 ** 6)
+    assert np.array_equal(img.view(np.uint32), rimg.view(np.uint32))
+    assert rays[:3] == [rc["primary_rays"], rc["reflection_rays"], rc["shadow_rays"]] and (rc["reflection_rays"] > 0) == mirror_floor
+    rng = np.random.RandomState(seed)
+    n = 8000
+    ro = rng.uniform(-6, 6, (n, 3)); ro[:, 1] = rng.uniform(0.2, 6, n)
+    rd = rng.normal(size=(n, 3)); rd /= np.linalg.norm(rd, axis=1, keepdims=True)
+    gen = np.concatenate([ro, rd, np.full((n, 1), 1e-4), rng.uniform(0.5, 30, (n, 1))], 1).astype(np.float32)
+    gen[:50, 3:6] = [0, -1, 0]                       # exactly axis-parallel rays: the reference's slab formula inside the shapes too
+    gids, gdist, gocc, false_rejects = e.intersect(gen)
+    oids, odist, _ = o.intersect_first(gen)
+    assert np.array_equal(gids, oids) and np.array_equal(gdist, odist) and np.array_equal(gocc, o.intersect_any(gen)) and false_rejects == 0
+    # the same scene through the LBVH's own instance tree: different instances tested, different local distances kept
+    monkeypatch.setenv("YRT_EMU_NO_REF_TLAS", "1")
+    ids2, _, _, _ = _emu.EmuScene(flat).trace_primary(w, h, 1)
+    assert not np.array_equal(ids2, rids)
+

@@ -108,8 +108,8 @@ def test_world2_gather_gloo():
 
 
 def test_nonrigid_instance_frames_are_counted():
-    """Rigid frames (rotations + translations) are the domain where the reference is well defined; scaled / sheared ones
-    are only counted so that the host can warn (include/yrt_b200.h, yrt_desc_nonrigid_instances)."""
+    """Scaled / sheared frames are counted on the host (include/yrt_b200.h, yrt_desc_nonrigid_instances): a scene that has any
+    is traced through a copy of the reference's own instance tree instead of the LBVH."""
     sc = synth.mixed_scene(31)
     assert sc.flat().nonrigid_instances() == 0
     inst = list(sc.instances)

@@ -18,7 +18,7 @@ namespace {
 std::mutex g_mu;
 std::vector<int> g_devices;   // empty until yrt_init*
 
-int g_allow_nonrigid = 0;    // yrt_set_option("allow_nonrigid")
+int g_allow_nonrigid = 0;    // yrt_set_option("allow_nonrigid"): accepted for ABI compatibility, no effect (such scenes are traced through the reference's instance tree)
 
 // With the option "pin_host_frames" the caller's frame buffers are page-locked on first sight and stay so until another
 // buffer takes the slot or the library is re-initialised (device->host copies into pageable memory are staged by the
@@ -99,15 +99,6 @@ int yrt_scene_create(const yrt_scene_desc* desc, yrt_scene** out) {
     yrt_scene* s = new yrt_scene();
     int st = host_scene_from_desc(desc, s->host, true);
     if (st != YRT_OK) { delete s; return st; }
-    if (!g_allow_nonrigid && !getenv("YRT_ALLOW_NONRIGID")) {
-        int nr = yrt_desc_nonrigid_instances(desc);
-        if (nr > 0) {
-            set_error("%d instance frame(s) are not rigid: the reference's result for them depends on the visit order of its own BVH "
-                      "(src/scene.cpp:468-473) and cannot be reproduced; opt in with yrt_set_option(\"allow_nonrigid\", 1)", nr);
-            delete s;
-            return YRT_ERR_UNSUPPORTED;
-        }
-    }
     st = ensure_init();
     if (st != YRT_OK) { delete s; return st; }
     for (int dev : g_devices) {

@@ -437,6 +437,13 @@ __global__ void k_permute_prim_rank(int n, const int* __restrict__ order, const 
     int k = YRT_TID();
     if (k < n) rank_out[k] = rank_in[order[k]];
 }
+// slot_of[instance] = its slot in inst_recs (scenes traced through the reference's instance tree, RefTlas in yrt_scene.cuh)
+__global__ void k_slot_of_inst(int n_active, const int* __restrict__ order, const int* __restrict__ active_inst, int* __restrict__ slot_of) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_active) return;
+    slot_of[active_inst[order[k]]] = k;
+}
+
 __global__ void k_permute_inst_rank(int n, const int* __restrict__ order, const int* __restrict__ active_inst, const int* __restrict__ rank_in,
                                     int* __restrict__ rank_out) {
     int k = YRT_TID();
@@ -520,6 +527,11 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
     float4 *plo = nullptr, *phi = nullptr, *ilo = nullptr, *ihi = nullptr, *d_nodes2 = nullptr, *d_nodes4 = nullptr, *d_prim_recs = nullptr, *d_prim_attrs = nullptr, *d_inst_recs = nullptr;
     int *d_prim_rank = nullptr, *d_inst_rank = nullptr;
     float4* d_inst_box = nullptr;
+    // scenes with non-rigid instance frames: room for the reference's instance tree (at most 2 n - 1 nodes, scene.cpp:646), filled in
+    // once the rank thread has built it
+    float4* d_ref_nodes = nullptr;
+    int *d_ref_leaf = nullptr, *d_slot_of = nullptr;
+    const bool ref_tlas = !hs.all_rigid && hs.n_instances > 0;
     // apex grids of the point lights (yrt_pgrid.cuh).  A light converges its shadow rays on ONE point only if its frame does
     // not rotate: shade() aims at transform_point(frame, pos - p) (src/raytrace.cpp:129-130), i.e. at (pos + o) - p for an
     // identity rotation; other lights, lights beyond the first YRT_MAX_LIGHT_GRIDS and scenes with non-rigid instance
@@ -592,6 +604,11 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
         d_prim_rank = keep.take<int>((size_t)std::max(np, 1));
         d_inst_rank = keep.take<int>((size_t)std::max(na, 1));
         d_inst_box = keep.take<float4>(2 * (size_t)std::max(na, 1));
+        if (ref_tlas) {
+            d_ref_nodes = keep.take<float4>(2 * (size_t)(2 * hs.n_instances));
+            d_ref_leaf = keep.take<int>((size_t)hs.n_instances);
+            d_slot_of = keep.take<int>((size_t)hs.n_instances);
+        }
         for (int k = 0; k < YRT_MAX_LIGHT_GRIDS; k++) {
             if (!lg_on[k]) continue;
             PGridArrays& a = lga[k];
@@ -699,6 +716,13 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
     YRT_CUDA(cudaMemcpyAsync(d_inst_rank_in, hs.inst_rank.data(), sizeof(int) * hs.inst_rank.size(), cudaMemcpyHostToDevice, st));
     if (np > 0) k_permute_prim_rank<<<grid_for(np), 256, 0, st>>>(np, bo.order, d_prim_rank_in, d_prim_rank);
     if (na > 0) k_permute_inst_rank<<<grid_for(na), 256, 0, st>>>(na, to.order, d_active, d_inst_rank_in, d_inst_rank);
+    if (ref_tlas) {
+        if (hs.ref_nodes.size() > 2 * (size_t)(2 * hs.n_instances) || hs.ref_leaf_inst.size() != (size_t)hs.n_instances) { set_error("internal: reference instance tree out of bounds"); return YRT_ERR_CUDA; }
+        YRT_CUDA(cudaMemcpyAsync(d_ref_nodes, hs.ref_nodes.data(), sizeof(float4) * hs.ref_nodes.size(), cudaMemcpyHostToDevice, st));
+        YRT_CUDA(cudaMemcpyAsync(d_ref_leaf, hs.ref_leaf_inst.data(), sizeof(int) * hs.ref_leaf_inst.size(), cudaMemcpyHostToDevice, st));
+        YRT_CUDA(cudaMemsetAsync(d_slot_of, 0xff, sizeof(int) * (size_t)hs.n_instances, st));
+        if (na > 0) k_slot_of_inst<<<grid_for(na), 256, 0, st>>>(na, to.order, d_active, d_slot_of);
+    }
     YRT_CUDA(cudaEventRecord(e1, st));
     std::vector<int> results(n_results, 0);
     YRT_CUDA(cudaMemcpyAsync(results.data(), d_results, sizeof(int) * n_results, cudaMemcpyDeviceToHost, st));
@@ -749,6 +773,10 @@ int build_device_scene(HostScene& hs, int device, DevScene& ds) {
     v.tlas_root = troot;
     v.n_lights = (int)hs.light_inst.size();
     v.n_active_instances = na;
+    ds.ref.nodes = d_ref_nodes;
+    ds.ref.leaf_inst = d_ref_leaf;
+    ds.ref.slot_of_inst = d_slot_of;
+    ds.ref.n_nodes = ref_tlas ? (int)(hs.ref_nodes.size() / 2) : 0;
     return YRT_OK;
 }
 

@@ -212,7 +212,7 @@ int host_scene_from_desc(const yrt_scene_desc* d, HostScene& hs, bool ranks_asyn
 // LBVH; these ranks are consulted on exact ties only (yrt_trace.cuh).
 // ------------------------------------------------------------------------------------------
 namespace {
-struct RankItem { vec3 center; int pid; };
+struct RankItem { vec3 center; int pid; Box box; };
 
 // std::partition as libstdc++ implements it for bidirectional iterators (the reference is compiled
 // against libstdc++ here; the element order inside each side depends on this exact algorithm)
@@ -232,8 +232,14 @@ template <class Pred> int partition_like_libstdcxx(std::vector<RankItem>& v, int
     }
 }
 
-// ranks[pid] = position of pid in the visit sequence of the tree make_node() builds over items
-void visit_ranks(std::vector<RankItem>& items, std::vector<int>& ranks, int rank_base_index) {
+// ranks[pid] = position of pid in the visit sequence of the tree make_node() builds over items.
+// ref_nodes / ref_leaf (optional): the tree itself, for scenes whose result depends on it (RefTlas, yrt_scene.cuh) —
+// per node two quads {bbox.min | a}, {bbox.max | b}: inner node a = left child, b = right child (the reference pushes
+// `start`, `start + 1` and pops the second first, scene.cpp:462-464); leaf a = ~(first entry of ref_leaf), b = count;
+// ref_leaf = the pids in partition order (bvh->leaf_prims, scene.cpp:652-655).  A node's box is the union of its items'
+// boxes in array order (scene.cpp:573-576).
+void visit_ranks(std::vector<RankItem>& items, std::vector<int>& ranks, int rank_base_index, std::vector<float4>* ref_nodes = nullptr,
+                 std::vector<int>* ref_leaf = nullptr) {
     struct Range { int start, end; bool expanded; };
     // phase 1: partition exactly like make_node (pre-order: node, then left subtree, then right subtree;
     // the two recursions are independent, so only the split points matter); remember the tree
@@ -273,6 +279,19 @@ void visit_ranks(std::vector<RankItem>& items, std::vector<int>& ranks, int rank
         todo.push_back(l);
         todo.push_back(l + 1);
     }
+    if (ref_nodes && ref_leaf) {
+        ref_nodes->assign(2 * nodes.size(), mk4(0.f, 0.f, 0.f, 0.f));
+        ref_leaf->resize(items.size());
+        for (size_t i = 0; i < items.size(); i++) (*ref_leaf)[i] = items[i].pid;
+        for (size_t k = 0; k < nodes.size(); k++) {
+            const Node& n = nodes[k];
+            Box b = box_invalid();
+            for (int i = n.start; i < n.end; i++) box_expand(b, items[i].box.lo, items[i].box.hi);   // expand_bbox(node->bbox, leaf_prims[i].bbox)
+            const int qa = n.left >= 0 ? n.left : ~n.start, qb = n.left >= 0 ? n.right : n.end - n.start;
+            (*ref_nodes)[2 * k] = mk4(b.lo.x, b.lo.y, b.lo.z, int_as_float(qa));
+            (*ref_nodes)[2 * k + 1] = mk4(b.hi.x, b.hi.y, b.hi.z, int_as_float(qb));
+        }
+    }
     // phase 2: visit order = stack traversal that pushes (first, first+1) and pops first+1 first
     int counter = 0;
     std::vector<int> st(1, 0);
@@ -310,6 +329,7 @@ void reference_visit_ranks(HostScene& hs) {
             RankItem it;
             it.center = (b.lo + b.hi) / 2.0f;
             it.pid = gp - p0;
+            it.box = b;
             items.push_back(it);
             box_expand(sb, b.lo, b.hi);
         }
@@ -325,9 +345,14 @@ void reference_visit_ranks(HostScene& hs) {
         RankItem it;
         it.center = (w.lo + w.hi) / 2.0f;
         it.pid = i;
+        it.box = w;
         items.push_back(it);
     }
-    visit_ranks(items, hs.inst_rank, 0);
+    hs.ref_nodes.clear();
+    hs.ref_leaf_inst.clear();
+    // scaled / sheared instance frames: the rays walk the reference's own instance tree, in its order (see RefTlas, yrt_scene.cuh)
+    if (hs.all_rigid) visit_ranks(items, hs.inst_rank, 0);
+    else visit_ranks(items, hs.inst_rank, 0, &hs.ref_nodes, &hs.ref_leaf_inst);
 }
 
 }  // namespace yrt

@@ -67,6 +67,8 @@ struct HostScene {
     int n_reflective = 0;
     float extent = 0.f;                      // bound of |coordinate| over everything in the scene (instances' world boxes)
     bool all_rigid = true;                   // every instance frame is orthonormal (to 1e-4): a local hit distance is the world distance
+    std::vector<float4> ref_nodes;           // !all_rigid: the reference's instance tree (RefTlas, yrt_scene.cuh), 2 quads per node ...
+    std::vector<int> ref_leaf_inst;          // ... and its leaf_prims (instance ids in partition order); filled by reference_visit_ranks
     // the rank tables are computed on a worker thread that yrt_scene_create starts; the build waits for it at the end
     std::thread rank_thread;
     void wait_ranks() { if (rank_thread.joinable()) rank_thread.join(); }
@@ -100,6 +102,7 @@ struct Workspace {
 struct DevScene {
     int device = 0;
     SceneView view;
+    RefTlas ref = {nullptr, nullptr, nullptr, 0};   // n_nodes > 0: the scene has non-rigid instance frames and is traced through the reference's instance tree
     DevBuf arena;          // everything a frame reads: nodes, element / instance / material / light records, textures, rank tables
     int n_prims = 0, n_active = 0, n_blas_nodes = 0, n_tlas_nodes = 0;
     int blas_depth = 0, tlas_depth = 0, stack_need = 0;

@@ -229,6 +229,100 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_any_rays(SceneView sv, 
     }
 }
 
+// ---- scenes with non-rigid instance frames: the same three kernels over the reference's own instance tree -----------------
+// (RefTlas in yrt_scene.cuh, trace_ray_ref in yrt_trace.cuh).  Separate kernels rather than a switch in the ones above: those are
+// tuned to the register (64 registers, 8 CTAs per SM) and must not change for a case the reference's own scenes never reach.
+template <bool PRIMARY>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_closest_ref(SceneView sv, RefTlas rt, BatchParams bp, const int* __restrict__ act,
+                                                                      const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                                                                      float4* __restrict__ hit_out, float4* __restrict__ P_out, WorkDist wd) {
+    const int lane = threadIdx.x & 31;
+    const unsigned n_items = item_count(wd);
+    int stack[STACK_INTS_CLOSEST];
+    int tstack[YRT_REF_TLAS_STACK];
+    for (;;) {
+        unsigned idx = 0;
+        bool alive = false;
+        if (!warp_next(wd, n_items, lane, idx, alive)) break;
+        if (!alive) continue;
+        unsigned slot;
+        ray3 ray;
+        if (PRIMARY) {
+            slot = idx;
+            int i, j, ii, jj;
+            slot_to_sample(bp, slot, i, j, ii, jj);
+            float u, v;
+            sample_uv(i, j, ii, jj, bp.samples, bp.width, bp.height, u, v);
+            ray = eval_camera(bp.cam, u, v);
+        } else {
+            slot = act ? (unsigned)act[idx] : idx;
+            float4 o = ray_o[slot], d = ray_d[slot];
+            ray.o = xyz(o); ray.d = xyz(d); ray.tmin = o.w; ray.tmax = d.w;
+        }
+        HitRec h;
+        trace_ray_ref<false>(sv, rt, ray, h, stack, tstack, nullptr);
+        float4 P = mk4(0.f, 0.f, 0.f, h.dist);
+        if (h.si >= 0) {
+            int kind;
+            vec3 p = eval_hit_pos(sv, h.si, h.prim, h.w1, h.w2, kind);
+            P.x = p.x; P.y = p.y; P.z = p.z;
+        }
+        hit_out[slot] = mk4(int_as_float(h.si), int_as_float(h.prim), h.w1, h.w2);
+        P_out[slot] = P;
+    }
+}
+
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_any_lights_ref(SceneView sv, RefTlas rt, size_t cap_slots, const int* __restrict__ act,
+                                                                         const float4* __restrict__ hit, const float4* __restrict__ P,
+                                                                         unsigned* __restrict__ vis, WorkDist wd) {
+    const int lane = threadIdx.x & 31;
+    const unsigned n_items = item_count(wd);
+    int stack[STACK_INTS_ANY];
+    int tstack[YRT_REF_TLAS_STACK];
+    for (;;) {
+        unsigned a = 0;
+        bool alive = false;
+        if (!warp_next(wd, n_items, lane, a, alive)) break;
+        if (!alive) continue;
+        unsigned slot = act ? (unsigned)act[a] : a;
+        float4 h = hit[slot];
+        if (float_as_int(h.x) < 0) continue;
+        vec3 p = xyz(P[slot]);
+        unsigned vm = 0u;
+        for (int k = 0; k < sv.n_lights; k++) {
+            vec3 l, ke;
+            float r;
+            light_vector(sv, k, p, l, r, ke);
+            ray3 sr = shadow_ray(p, l, r);
+            HitRec hr;
+            if (!trace_ray_ref<true>(sv, rt, sr, hr, stack, tstack, nullptr)) vm |= 1u << (k & 31);
+            if ((k & 31) == 31 || k == sv.n_lights - 1) {
+                vis[(size_t)(k >> 5) * cap_slots + slot] = vm;
+                vm = 0u;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_any_rays_ref(SceneView sv, RefTlas rt, const float4* __restrict__ ray_o,
+                                                                       const float4* __restrict__ ray_d, uint8_t* __restrict__ occ_out, WorkDist wd) {
+    const int lane = threadIdx.x & 31;
+    const unsigned n_items = item_count(wd);
+    int stack[STACK_INTS_ANY];
+    int tstack[YRT_REF_TLAS_STACK];
+    for (;;) {
+        unsigned idx = 0;
+        bool alive = false;
+        if (!warp_next(wd, n_items, lane, idx, alive)) break;
+        if (!alive) continue;
+        float4 o = ray_o[idx], d = ray_d[idx];
+        ray3 ray;
+        ray.o = xyz(o); ray.d = xyz(d); ray.tmin = o.w; ray.tmax = d.w;
+        HitRec hr;
+        occ_out[idx] = trace_ray_ref<true>(sv, rt, ray, hr, stack, tstack, nullptr) ? 1 : 0;
+    }
+}
+
 // ---- shade ------------------------------------------------------------------------------------
 struct FrameCounters { unsigned long long hits, reflections, misses, truncated, max_depth; };   // truncated: mirror bounces dropped at the depth cap
 
@@ -536,9 +630,10 @@ int presize_workspace_device(DevScene& ds, int width, int height, int samples) {
     int depth_cap = std::min(YRT_MAX_WAVES, std::max(1, env_int("YRT_MAX_DEPTH", YRT_MAX_WAVES)));
     size_t cap_slots = (size_t)batch_rows_for(rp, ds.view.n_lights, height, ds.has_reflective) * width * samples * samples;
     YRT_TRY(ensure_workspace(ds, ds.ws, cap_slots, ds.view.n_lights, depth_cap, ds.has_reflective));
-    if (!ds.grid_closest_primary) ds.grid_closest_primary = persistent_grid(ds, (const void*)k_trace_closest<true>);
-    if (!ds.grid_closest_queue) ds.grid_closest_queue = persistent_grid(ds, (const void*)k_trace_closest<false>);
-    if (!ds.grid_any) ds.grid_any = persistent_grid(ds, (const void*)k_trace_any_lights);
+    const bool ref = ds.ref.n_nodes > 0;
+    if (!ds.grid_closest_primary) ds.grid_closest_primary = persistent_grid(ds, ref ? (const void*)k_trace_closest_ref<true> : (const void*)k_trace_closest<true>);
+    if (!ds.grid_closest_queue) ds.grid_closest_queue = persistent_grid(ds, ref ? (const void*)k_trace_closest_ref<false> : (const void*)k_trace_closest<false>);
+    if (!ds.grid_any) ds.grid_any = persistent_grid(ds, ref ? (const void*)k_trace_any_lights_ref : (const void*)k_trace_any_lights);
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, (const void*)k_shade);
     cudaFuncGetAttributes(&fa, (const void*)k_resolve);
@@ -589,16 +684,18 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, const G
     bp.cap_slots = cap_slots;
     unsigned n = (unsigned)((size_t)nrows * rp.width * bp.spp);
     int nl = ds.view.n_lights;
-    if (!ds.grid_closest_primary) ds.grid_closest_primary = persistent_grid(ds, (const void*)k_trace_closest<true>);
-    if (!ds.grid_closest_queue) ds.grid_closest_queue = persistent_grid(ds, (const void*)k_trace_closest<false>);
-    if (!ds.grid_any) ds.grid_any = persistent_grid(ds, (const void*)k_trace_any_lights);
+    const bool ref = ds.ref.n_nodes > 0;
+    if (!ds.grid_closest_primary) ds.grid_closest_primary = persistent_grid(ds, ref ? (const void*)k_trace_closest_ref<true> : (const void*)k_trace_closest<true>);
+    if (!ds.grid_closest_queue) ds.grid_closest_queue = persistent_grid(ds, ref ? (const void*)k_trace_closest_ref<false> : (const void*)k_trace_closest<false>);
+    if (!ds.grid_any) ds.grid_any = persistent_grid(ds, ref ? (const void*)k_trace_any_lights_ref : (const void*)k_trace_any_lights);
     auto grid_of = [](int g, unsigned items) { unsigned need = (items + TRACE_THREADS - 1) / TRACE_THREADS; return (int)std::max(1u, std::min((unsigned)g, need)); };
     unsigned long long* dctr = YRT_COUNTERS ? ds.dctr.as<unsigned long long>() : nullptr;
 
     unsigned* ctr = nullptr;
     YRT_TRY(ring.get(&ctr));
     pt.begin(CAT_CLOSEST);
-    k_trace_closest<true><<<grid_of(ds.grid_closest_primary, n), TRACE_THREADS, 0, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(), w.P.as<float4>(),
+    if (ref) k_trace_closest_ref<true><<<grid_of(ds.grid_closest_primary, n), TRACE_THREADS, 0, st>>>(ds.view, ds.ref, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(), w.P.as<float4>(), workdist_linear(ctr, n));
+    else k_trace_closest<true><<<grid_of(ds.grid_closest_primary, n), TRACE_THREADS, 0, st>>>(ds.view, bp, nullptr, nullptr, nullptr, w.hit.as<float4>(), w.P.as<float4>(),
                                                                                           workdist_linear(ctr, n), dctr);
     pt.end();
     if (pipe >= 0 && cam_grid.nx > 0 && ds.ev_primary_done[pipe]) {     // the last reader of this frame's camera grid on this pipeline so far
@@ -623,7 +720,9 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, const G
         if (depth > 0) {
             YRT_TRY(ring.get(&ctr));
             pt.begin(CAT_CLOSEST);
-            k_trace_closest<false><<<grid_of(ds.grid_closest_queue, n), TRACE_THREADS, 0, st>>>(ds.view, bp, act, w.ray_o.as<float4>(), w.ray_d.as<float4>(), w.hit.as<float4>(),
+            if (ref) k_trace_closest_ref<false><<<grid_of(ds.grid_closest_queue, n), TRACE_THREADS, 0, st>>>(ds.view, ds.ref, bp, act, w.ray_o.as<float4>(), w.ray_d.as<float4>(), w.hit.as<float4>(),
+                                                                                                         w.P.as<float4>(), workdist_linear(ctr, n, n_dev));
+            else k_trace_closest<false><<<grid_of(ds.grid_closest_queue, n), TRACE_THREADS, 0, st>>>(ds.view, bp, act, w.ray_o.as<float4>(), w.ray_d.as<float4>(), w.hit.as<float4>(),
                                                                                                w.P.as<float4>(), workdist_linear(ctr, n, n_dev), dctr ? dctr + YRT_DCTR_WORDS : nullptr);
             pt.end();
         }
@@ -634,7 +733,9 @@ static int run_batch(DevScene& ds, Workspace& w, const RenderParams& rp, const G
         if (nl > 0) {
             YRT_TRY(ring.get(&ctr));
             pt.begin(CAT_ANY);
-            k_trace_any_lights<<<grid_of(ds.grid_any, n), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(), w.vis.as<unsigned>(),
+            if (ref) k_trace_any_lights_ref<<<grid_of(ds.grid_any, n), TRACE_THREADS, 0, st>>>(ds.view, ds.ref, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(), w.vis.as<unsigned>(),
+                                                                                          workdist_linear(ctr, n, n_dev));
+            else k_trace_any_lights<<<grid_of(ds.grid_any, n), TRACE_THREADS, 0, st>>>(ds.view, cap_slots, act, w.hit.as<float4>(), w.P.as<float4>(), w.vis.as<unsigned>(),
                                                                                  workdist_linear(ctr, n, n_dev), dctr ? dctr + 2 * YRT_DCTR_WORDS : nullptr, ds.light_grids);
             pt.end();
         }
@@ -951,8 +1052,9 @@ int intersect_rays_device(DevScene& ds, const float* h_rays, int64_t n, bool any
     YRT_TRY(occ.alloc((size_t)c, ds.device));
     YRT_TRY(ctr.alloc(sizeof(unsigned) * 4, ds.device));
     std::vector<float4> ho(c), hd(c);
-    int g_c = persistent_grid(ds, (const void*)k_trace_closest<false>);
-    int g_a = persistent_grid(ds, (const void*)k_trace_any_rays);
+    const bool ref = ds.ref.n_nodes > 0;
+    int g_c = persistent_grid(ds, ref ? (const void*)k_trace_closest_ref<false> : (const void*)k_trace_closest<false>);
+    int g_a = persistent_grid(ds, ref ? (const void*)k_trace_any_rays_ref : (const void*)k_trace_any_rays);
     BatchParams bp;
     memset(&bp, 0, sizeof(bp));
     for (int64_t off = 0; off < n; off += chunk) {
@@ -967,12 +1069,16 @@ int intersect_rays_device(DevScene& ds, const float* h_rays, int64_t n, bool any
         YRT_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(unsigned) * 4, st));
         unsigned need = (unsigned)((m + TRACE_THREADS - 1) / TRACE_THREADS);
         if (any) {
-            k_trace_any_rays<<<std::max(1u, std::min((unsigned)g_a, need)), TRACE_THREADS, 0, st>>>(ds.view, ro.as<float4>(), rd.as<float4>(), occ.as<uint8_t>(),
+            if (ref) k_trace_any_rays_ref<<<std::max(1u, std::min((unsigned)g_a, need)), TRACE_THREADS, 0, st>>>(ds.view, ds.ref, ro.as<float4>(), rd.as<float4>(), occ.as<uint8_t>(),
+                                                                                                          workdist_linear(ctr.as<unsigned>(), (unsigned)m));
+            else k_trace_any_rays<<<std::max(1u, std::min((unsigned)g_a, need)), TRACE_THREADS, 0, st>>>(ds.view, ro.as<float4>(), rd.as<float4>(), occ.as<uint8_t>(),
                                                                                                  workdist_linear(ctr.as<unsigned>(), (unsigned)m));
             YRT_CUDA(cudaGetLastError());
             YRT_CUDA(cudaMemcpyAsync(h_occ + off, occ.p, (size_t)m, cudaMemcpyDeviceToHost, st));
         } else {
-            k_trace_closest<false><<<std::max(1u, std::min((unsigned)g_c, need)), TRACE_THREADS, 0, st>>>(
+            if (ref) k_trace_closest_ref<false><<<std::max(1u, std::min((unsigned)g_c, need)), TRACE_THREADS, 0, st>>>(
+                ds.view, ds.ref, bp, nullptr, ro.as<float4>(), rd.as<float4>(), hit.as<float4>(), P.as<float4>(), workdist_linear(ctr.as<unsigned>(), (unsigned)m));
+            else k_trace_closest<false><<<std::max(1u, std::min((unsigned)g_c, need)), TRACE_THREADS, 0, st>>>(
                 ds.view, bp, nullptr, ro.as<float4>(), rd.as<float4>(), hit.as<float4>(), P.as<float4>(), workdist_linear(ctr.as<unsigned>(), (unsigned)m), nullptr);
             k_hit_ids<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(ds.view, hit.as<float4>(), P.as<float4>(), (int)m, ids.as<int>(),
                                                                  dist.as<float>(), uv.as<float>());

@@ -194,6 +194,20 @@ struct SceneView {
     int n_active_instances;
 };
 
+// RefTlas — only for scenes with scaled / sheared instance frames (n_nodes > 0), which the LBVH cannot serve:
+// transform_ray_inverse (vmath.h:275-278) inverts rigid frames only, so for any other frame the geometry the reference
+// "sees" is not inside the instance's world box, and the local hit distance it keeps as tray.tmax (scene.cpp:470) is not
+// a world distance.  What the reference returns then depends on WHICH instances its own tree lets a ray test and in which
+// order.  Such scenes are traced through a copy of that tree (yrt_host.cu: visit_ranks): same nodes, same boxes, same slab
+// formula, same stack order (trace_ray_ref, yrt_trace.cuh); the shapes' trees below stay the LBVH's.  Kept out of SceneView
+// so that the kernels of every other scene do not change by a byte.
+struct RefTlas {
+    const float4* nodes;        // 2 per node: {bbox.min | a}, {bbox.max | b}; inner: a, b = children; leaf: a = ~first, b = count
+    const int* leaf_inst;       // the reference's leaf_prims: instance ids
+    const int* slot_of_inst;    // instance id -> slot in inst_recs (-1: its shape has no elements)
+    int n_nodes;
+};
+
 // trace record (3 float4) + the vertex positions shading needs, for one element in BLAS leaf order.
 //   triangle: (v0 | element, e1 = v1 - v0, e2 = v2 - v0)  — the edges of scene.cpp:236-237, subtracted once here
 //   line:     (v0 | element, v1 | r0, r1)        point: (v0 | element, r0)

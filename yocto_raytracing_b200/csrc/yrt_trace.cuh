@@ -417,19 +417,77 @@ YRT_HD bool trace_ray(const SceneView& sv, const ray3& wray, HitRec& hit, int* s
     return trace_ray_from<ANY>(sv, wray, hit, stack, ctr, sv.tlas_root);
 }
 
-YRT_HD int ld_root(const int* p) {
+// rays the fused slab test cannot serve (see trace_ray_from): they walk from the tree's root with the reference's formula
+YRT_HD bool ray_needs_exact_slabs(const ray3& wray) {
+    float ax = fabsf(wray.d.x), ay = fabsf(wray.d.y), az = fabsf(wray.d.z);
+    float m = fminf(fminf(ax, ay), az), big = fmaxf(fmaxf(ax, ay), az);
+    return !(m >= 1.0f / YRT_EXACT_SLAB_INVD && big <= 1.0e30f);
+}
+
+// Scenes with non-rigid instance frames (RefTlas, yrt_scene.cuh): intersect_bvh(scene…) of src/scene.cpp:446-479 restated on a
+// copy of the reference's own instance tree — node popped, slab test of scene.cpp:371-383 on the node's exact box with the
+// tmax of now, inner nodes push (start, start + 1), leaves run their instances in array order; each instance is entered
+// with transform_ray_inverse and the current tmax, and a hit's LOCAL distance becomes the new tmax (scene.cpp:468-470).
+// The shapes' trees are the LBVH's: inside one instance the closest element with t <= tmax (ties by the reference's visit
+// rank) does not depend on the tree.  `tstack`: YRT_REF_TLAS_STACK ints (the reference's own node_stack has 64).
+#define YRT_REF_TLAS_STACK 64
+YRT_HD int ldi(const int* p) {
 #if defined(__CUDA_ARCH__)
     return __ldg(p);
 #else
     return *p;
 #endif
 }
+template <bool ANY, bool EXACT>
+YRT_HD bool trace_ray_ref_impl(const SceneView& sv, const RefTlas& rt, const ray3& wray, HitRec& hit, int* stack, int* tstack, TraceCounters* ctr) {
+    Tracer<ANY, EXACT> t;
+    t.begin(sv, wray, stack, YRT_REF_DONE);
+    const vec3 invd = inv3(wray.d);                     // scene.cpp:372 (the same three quotients on every call)
+    const raysigns sgn = signs_of(invd);
+    int tsp = 0;
+    if (rt.n_nodes > 0) tstack[tsp++] = 0;
+    while (tsp) {
+        const float4* n = rt.nodes + 2 * (size_t)tstack[--tsp];
+        const float4 q0 = ld4(n), q1 = ld4(n + 1);
+        float te;
+        if (ctr) { ctr->box_tests++; ctr->tlas_box_tests++; ctr->node_visits++; }
+        if (!intersect_check_bbox(wray.o, invd, sgn, t.tmin, t.tmax, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, te)) continue;
+        const int a = float_as_int(q0.w), b = float_as_int(q1.w);
+        if (a >= 0) {
+            if (tsp + 2 > YRT_REF_TLAS_STACK) continue;   // (deeper than the reference's own stack: it would have overrun it)
+            tstack[tsp++] = a;
+            tstack[tsp++] = b;
+            continue;
+        }
+        for (int i = ~a; i < ~a + b; i++) {
+            const int slot = ldi(rt.slot_of_inst + ldi(rt.leaf_inst + i));
+            if (slot < 0) continue;                     // a shape without elements: its tree is one empty leaf, never a hit
+            t.sp = 0;
+            t.push(YRT_REF_DONE, -FLT_MAX);
+            t.enter_instance(sv, slot, stack, ctr);
+            for (;;) {
+                t.nodes(sv, stack, ctr);
+                if (t.done()) break;
+                t.leaf(sv, stack, ctr);
+            }
+            if (ANY && t.found) { hit = t.hit; return true; }
+        }
+    }
+    hit = t.hit;
+    return t.found;
+}
+template <bool ANY>
+YRT_HD bool trace_ray_ref(const SceneView& sv, const RefTlas& rt, const ray3& wray, HitRec& hit, int* stack, int* tstack, TraceCounters* ctr) {
+    if (ray_needs_exact_slabs(wray)) return trace_ray_ref_impl<ANY, true>(sv, rt, wray, hit, stack, tstack, ctr);
+    return trace_ray_ref_impl<ANY, false>(sv, rt, wray, hit, stack, tstack, ctr);
+}
 
-// rays the fused slab test cannot serve (see trace_ray_from): they walk from the tree's root with the reference's formula
-YRT_HD bool ray_needs_exact_slabs(const ray3& wray) {
-    float ax = fabsf(wray.d.x), ay = fabsf(wray.d.y), az = fabsf(wray.d.z);
-    float m = fminf(fminf(ax, ay), az), big = fmaxf(fmaxf(ax, ay), az);
-    return !(m >= 1.0f / YRT_EXACT_SLAB_INVD && big <= 1.0e30f);
+YRT_HD int ld_root(const int* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
 }
 
 // a ray of an apex grid in list form whose cell holds the candidates [first, first + count)

@@ -11,8 +11,8 @@
 //   --fast-png     8-bit PNG outputs are written by yrt_write_png (parallel deflate) instead of stb_image_write: same pixels,
 //                  a fraction of the time (stbi_write_png costs 45 frames' worth of rendering at 1080p)
 //   --stats        ray counts and the time of every phase
-//   --allow-nonrigid  scenes with scaled / sheared instance frames are refused by default (the reference's result for them
-//                  depends on its own BVH visit order, include/yrt_b200.h); this flag renders them anyway
+//   --allow-nonrigid  accepted and ignored (earlier versions refused scenes with scaled / sheared instance frames without it; they are
+//                  now traced through a copy of the reference's own instance tree and match it, include/yrt_b200.h)
 #include <dirent.h>
 #include <sys/stat.h>
 
@@ -75,7 +75,7 @@ int main(int argc, char** argv) {
     // additive (not in the reference)
     auto gpus = yu::cmdline::parse_opti(parser, "--gpus", "-g", "number of GPUs (interleaved row tiles)", 1);
     auto verbose = yu::cmdline::parse_flag(parser, "--stats", "", "print ray counts and timings", false);
-    auto allow_nonrigid = yu::cmdline::parse_flag(parser, "--allow-nonrigid", "", "render scenes with scaled / sheared instance frames (may differ from the reference)", false);
+    auto allow_nonrigid = yu::cmdline::parse_flag(parser, "--allow-nonrigid", "", "ignored (scenes with scaled / sheared instance frames are always rendered)", false);
     auto use_cache = yu::cmdline::parse_flag(parser, "--cache", "", "reuse / write the flattened scene <scene>.yrts", false);
     auto device_ldr = yu::cmdline::parse_flag(parser, "--device-ldr", "", "tonemap on the GPU (8-bit outputs)", false);
     auto fast_png = yu::cmdline::parse_flag(parser, "--fast-png", "", "write .png outputs with the parallel encoder", false);
@@ -116,15 +116,9 @@ int main(int argc, char** argv) {
         exit(1);
     }
     yrt_scene_desc desc = flat.desc();
-    if (int nonrigid = yrt_desc_nonrigid_instances(&desc)) {
-        // the reference's own result for such frames depends on its BVH visit order (include/yrt_b200.h): refused unless asked for
-        if (!allow_nonrigid) {
-            printf("%d instance frame(s) are not rigid: not reproducible against the reference; pass --allow-nonrigid to render anyway\n", nonrigid);
-            exit(1);
-        }
-        fprintf(stderr, "warning: %d instance frame(s) are not rigid; the image may differ from the reference's where they overlap\n", nonrigid);
-        yrt_set_option("allow_nonrigid", 1);
-    }
+    (void)allow_nonrigid;   // scenes with scaled / sheared instance frames are traced through the reference's own instance tree (include/yrt_b200.h)
+    if (verbose)
+        if (int nonrigid = yrt_desc_nonrigid_instances(&desc)) printf("%d instance frame(s) are not rigid: tracing through the reference's instance tree\n", nonrigid);
     yrt_scene* gscn = nullptr;
     if (yrt_scene_create(&desc, &gscn) != YRT_OK) {
         printf("%s\n", yrt_last_error());

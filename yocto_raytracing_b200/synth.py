@@ -470,3 +470,25 @@ def mixed_scene(seed: int = 7, n_objects: int = 24, reflective_floor: bool = Tru
                      ("half", 8, translation_frame((0, 3, 0)))]
     sc.camera = make_camera((0, 4, 10), (0, 1, 0), 0.6)
     return sc
+
+
+def nonrigid_scene(seed: int = 31, frame_seed: int = 5, every: int = 3, mirror_floor: bool = False) -> SynthScene:
+    """mixed_scene with every `every`-th object instance scaled per axis and sheared: frames transform_ray_inverse
+    (src/vmath.h:275-278) does not invert.  The reference's result for such a scene depends on its own instance tree and visit
+    order (src/scene.cpp:446-479) — the case the RefTlas path of the library exists for.  Object mirrors are switched off (a sheared
+    mirror traps rays and the reference recurses until its stack overflows); mirror_floor keeps the rigid floor reflective, so
+    that mirror rays meet the non-rigid instances too."""
+    sc = mixed_scene(seed, reflective_floor=mirror_floor)
+    sc.name = f"nonrigid{seed}"
+    rng = np.random.default_rng(frame_seed)
+    for m in sc.materials:
+        if m.name != "floor":
+            m.kr = (0.0, 0.0, 0.0)
+    for k, (iname, si, fr) in enumerate(list(sc.instances)):
+        if iname.startswith("obj") and k % every == 0:
+            f = np.array(fr, np.float32).reshape(4, 3).copy()
+            f[0] *= rng.uniform(0.5, 1.8); f[1] *= rng.uniform(0.5, 1.8); f[2] *= rng.uniform(0.6, 1.5)
+            f[0] += 0.3 * f[1]
+            sc.instances[k] = (iname, si, f.reshape(-1))
+    return sc
+
