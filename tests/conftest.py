@@ -10,7 +10,9 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
         sys.path.insert(0, p)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["simple", "basic", "refl", "instance10000", "lines_synth", "mixed7", "gltf7"]
+RIGID_GOLDEN_CASES = ["simple", "basic", "refl", "instance10000", "lines_synth", "mixed7", "gltf7"]
+# + scenes with scaled / sheared instance frames (OBJ `i` lines; glTF node scales), traced through the reference's own instance tree
+GOLDEN_CASES = RIGID_GOLDEN_CASES + ["nonrigid31", "gltf23s"]
 
 
 def pytest_configure(config):

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import _emu
-from conftest import GOLDEN_CASES, id_match, ldr_stats, load_golden
+from conftest import GOLDEN_CASES, RIGID_GOLDEN_CASES, id_match, ldr_stats, load_golden
 
 pytestmark = pytest.mark.skipif(not _emu.available(), reason="tests/host_emu/libyrt_hostemu.so not built (make hostemu)")
 
@@ -139,7 +139,7 @@ def test_emulated_device_hit_ids_full_size(case):
 
 
 # ---- apex grids (csrc/yrt_pgrid.cuh): rays of the camera / towards a point light start at the root of their cell ----------
-@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("name", RIGID_GOLDEN_CASES)     # (scenes with non-rigid frames have no grids)
 def test_apex_grids_change_nothing(name):
     """Same hits (ids, distances, barycentrics, tie winners) and the same image, bit for bit, with and without the grids —
     i.e. every cell's candidate list holds all instances a ray of that cell can hit — and against the reference's goldens."""

@@ -1,7 +1,7 @@
 """Write a small glTF 2.0 scene (scene.gltf + scene.bin) that the reference's loader accepts (src/ext/yocto_scn.cpp:723-1083):
 meshes with POSITION / NORMAL / TEXCOORD_0 and uint32 indices, KHR_materials_pbrSpecularGlossiness materials (the loader
 maps diffuseFactor -> kd, specularFactor -> ks, glossinessFactor -> rs, emissiveFactor -> ke), point lights as POINTS
-primitives with an emissive material, nodes with translation + rotation quaternions (rigid), one perspective camera node.
+primitives with an emissive material, nodes with translation + rotation quaternions (rigid; optionally node scales), one perspective camera node.
 Used by the tests and tools/make_golden.py to cover the SURVEY 8f.4 input path."""
 import json
 import os
@@ -85,8 +85,10 @@ class Builder:
         self.meshes.append({"name": name, "primitives": [prim]})
         return len(self.meshes) - 1
 
-    def node(self, name, mesh=None, camera=None, translation=(0, 0, 0), rotation=(0, 0, 0, 1), children=None):
+    def node(self, name, mesh=None, camera=None, translation=(0, 0, 0), rotation=(0, 0, 0, 1), children=None, scale=None):
         n = {"name": name, "translation": [float(x) for x in translation], "rotation": [float(x) for x in rotation]}
+        if scale is not None:     # a node scale makes the instance frame non-rigid (the reference keeps it in the frame's axes)
+            n["scale"] = [float(x) for x in scale]
         if mesh is not None:
             n["mesh"] = mesh
         if camera is not None:
@@ -109,8 +111,10 @@ class Builder:
         return p
 
 
-def gltf_scene(directory, seed=7, n_objects=10, name="gltf7"):
-    """Floor + rotated round cubes / spheres (a child-node hierarchy included) + two point lights + a look-at camera."""
+def gltf_scene(directory, seed=7, n_objects=10, name="gltf7", scales=False):
+    """Floor + rotated round cubes / spheres (a child-node hierarchy included) + two point lights + a look-at camera.
+    scales: every third object node also carries a non-uniform scale (children inherit it) — the usual case in glTF files,
+    and one the reference's ray transform does not invert (non-rigid instance frames)."""
     rng = np.random.default_rng(seed)
     b = Builder()
     m_floor = b.material("floor", kd=(0.6, 0.6, 0.55))
@@ -130,7 +134,8 @@ def gltf_scene(directory, seed=7, n_objects=10, name="gltf7"):
         child = None
         if k % 4 == 0:   # a satellite in the parent's frame: exercises the node hierarchy (xform = parent * local)
             child = [b.node(f"sat{k}", mesh=ball if k % 8 else cube, translation=(1.6, 0.4, 0.0), rotation=quat_from_axis_angle((0, 0, 1), 0.5))]
-        roots.append(b.node(f"obj{k}", mesh=cube if k % 2 else ball, translation=o, rotation=q, children=child))
+        sc = (rng.uniform(0.6, 1.7), rng.uniform(0.6, 1.7), rng.uniform(0.6, 1.7)) if scales and k % 3 == 0 else None
+        roots.append(b.node(f"obj{k}", mesh=cube if k % 2 else ball, translation=o, rotation=q, children=child, scale=sc))
     roots.append(b.node("light_a", mesh=light, translation=(-3, 6, 5)))
     roots.append(b.node("light_b", mesh=light2, translation=(4, 5, 3)))
     b.cameras.append({"type": "perspective", "perspective": {"yfov": 0.6, "aspectRatio": 16.0 / 9.0, "znear": 0.1, "zfar": 100.0}})

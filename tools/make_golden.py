@@ -52,18 +52,28 @@ def one(name, obj, res, smp, ids_res):
 
 
 def main():
+    """python tools/make_golden.py [case ...]   (no arguments: every case)"""
+    only = set(sys.argv[1:])
+    want = lambda name: not only or name in only
     os.makedirs(OUT, exist_ok=True)
     for name, (obj, res, smp, ids_res) in CASES.items():
-        one(name, obj, res, smp, ids_res)
+        if want(name):
+            one(name, obj, res, smp, ids_res)
     # synthetic scenes written in the reference's OBJ dialect and rendered by the reference
+    # (nonrigid31: scaled + sheared `i` lines — the reference's result depends on its own instance tree there, DESIGN.md section 1)
     with tempfile.TemporaryDirectory() as td:
-        for sc, res, smp, ids_res in ((synth.hair_scene(1024), 90, 2, 180), (synth.mixed_scene(7), 90, 2, 180)):
-            obj = sc.write_obj(os.path.join(td, sc.name))
-            one(sc.name, obj, res, smp, ids_res)
+        for sc, res, smp, ids_res in ((synth.hair_scene(1024), 90, 2, 180), (synth.mixed_scene(7), 90, 2, 180), (synth.nonrigid_scene(31, 5, 3), 90, 2, 180)):
+            if want(sc.name):
+                obj = sc.write_obj(os.path.join(td, sc.name))
+                one(sc.name, obj, res, smp, ids_res)
         # glTF input (SURVEY 8f.4): node hierarchy with translation + rotation quaternions, KHR_materials_pbrSpecularGlossiness
         # materials, POINTS primitives as lights, a camera node — loaded by the reference's own glTF loader
         import make_gltf
-        one("gltf7", make_gltf.gltf_scene(os.path.join(td, "gltf7")), 90, 2, 180)
+        if want("gltf7"):
+            one("gltf7", make_gltf.gltf_scene(os.path.join(td, "gltf7")), 90, 2, 180)
+        # ... and the same with node scales on every third object (children inherit them): non-rigid instance frames
+        if want("gltf23s"):
+            one("gltf23s", make_gltf.gltf_scene(os.path.join(td, "gltf23s"), seed=23, n_objects=14, name="gltf23s", scales=True), 90, 2, 180)
 
 
 if __name__ == "__main__":
