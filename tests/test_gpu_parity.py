@@ -309,7 +309,8 @@ def test_drop_in_cli_matches_reference_cli(gpu, tmp_path):
     ours, ref = os.path.join(ROOT, "bin", "raytrace"), os.path.join(ROOT, "oracle", "_ref", "raytrace_ref")
     if not (os.path.exists(ours) and os.path.exists(ref)):
         pytest.skip("bin/raytrace / oracle/_ref/raytrace_ref not built (need the reference sources at build time)")
-    for sc, res, smp in ((synth.instance_grid_scene(20, seed=9), 180, 2), (synth.mixed_scene(7), 120, 2), (synth.hair_scene(256), 120, 2)):
+    # (nonrigid31: scaled + sheared `i` lines — neither binary refuses it, and the PNGs agree like any other scene's)
+    for sc, res, smp in ((synth.instance_grid_scene(20, seed=9), 180, 2), (synth.mixed_scene(7), 120, 2), (synth.nonrigid_scene(31, 5, 3), 120, 2), (synth.hair_scene(256), 120, 2)):
         obj = sc.write_obj(str(tmp_path / sc.name))
         cwd = os.path.dirname(obj)
         a, b = os.path.join(cwd, "ours.png"), os.path.join(cwd, "ref.png")
