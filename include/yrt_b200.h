@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define YRT_ABI_VERSION 2
+#define YRT_ABI_VERSION 3   /* 3: + yrt_frame_truncated_paths; scenes with non-rigid instance frames are rendered (ABI 2 refused them unless opted in) */
 
 typedef enum yrt_status {
     YRT_OK = 0,
@@ -157,7 +157,7 @@ int yrt_scene_prepare(yrt_scene* scn, int width, int height, int samples);
  * Pure host function, needs no GPU. */
 int yrt_desc_nonrigid_instances(const yrt_scene_desc* desc);
 /* process-wide options; unknown names return YRT_ERR_INVALID.
- *   "allow_nonrigid"  accepted and ignored (ABI 1 refused scenes with non-rigid instance frames unless this was set).
+ *   "allow_nonrigid"  accepted and ignored (ABI 2 refused scenes with non-rigid instance frames unless this was set).
  *   "pin_host_frames" (0/1, default 0): yrt_render / yrt_render_ldr page-lock the caller's output buffer the first time they
  *                     see it and keep it registered while the same buffer keeps coming back (device->host copies into
  *                     pageable memory are staged by the driver).  The registration outlives the call: only for callers

@@ -24,7 +24,7 @@ def test_header_symbols_all_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/yrt_b200.h but not exported"
         assert n in _lib.SYMBOLS, f"{n} has no ctypes prototype"
-    assert lib.yrt_abi_version() == 2
+    assert lib.yrt_abi_version() == 3
 
 
 def test_struct_layouts_match_header():

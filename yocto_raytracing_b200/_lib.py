@@ -126,7 +126,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.yrt_abi_version() != 2:
+    if lib.yrt_abi_version() != 3:
         raise RuntimeError("libyrt_b200.so ABI version mismatch")
     _lib = lib
     return lib
