@@ -6,11 +6,11 @@
 //     4-wide: 128 B = pair(children 0,1) | pair(children 2,3) | 4 child refs | child count
 //     binary:  64 B = pair(children 0,1) | 2 child refs            (both arrays are built; see YRT_WIDE_CLOSEST / YRT_WIDE_ANY)
 //   prim record (48 B, in BLAS leaf order, all shapes concatenated):
-//     triangle: q0 = v0.xyz | ei     q1 = v1.xyz | -      q2 = v2.xyz | -
+//     triangle: q0 = v0.xyz | ei     q1 = e1.xyz | -      q2 = e2.xyz | -     (e1 = v1 - v0, e2 = v2 - v0: scene.cpp:236-237, subtracted once at build time)
 //     line:     q0 = v0.xyz | ei     q1 = v1.xyz | r0     q2 = r1, -, -, -
 //     point:    q0 = p.xyz  | ei     q1 = r, -, -, -
-//   prim attribute record (64 B, same order; pre-gathered shape::norm / shape::texcoord):
-//     q0 = n0.xyz | uv0.x   q1 = n1.xyz | uv0.y   q2 = n2.xyz | uv1.x   q3 = uv1.y, uv2.x, uv2.y, -
+//   prim attribute record (YRT_ATTR_STRIDE quads, same order; pre-gathered shape::norm / shape::texcoord, and a triangle's v1, v2 for eval_pos):
+//     q0 = n0.xyz | uv0.x   q1 = n1.xyz | uv0.y   q2 = n2.xyz | uv1.x   q3 = uv1.y, uv2.x, uv2.y, -   q4 = v1.xyz   q5 = v2.xyz
 //   instance record (64 B, in TLAS leaf order):
 //     q0 = frame.x | blas root ref   q1 = frame.y | instance index (scn->instances order)
 //     q2 = frame.z | material index  q3 = frame.o | shape index | kind << 28
