@@ -228,6 +228,20 @@ def test_edge_cases(gpu, oracle_mod):
         img, st = scn.render(64, 36, 2, 0.2)
     assert np.array_equal(img.view(np.uint32), ref.view(np.uint32)) and st.shadow_rays == 0
     assert img[18, 32, 0] == np.float32(0.2) * np.float32(0.5)
+    # instances of a shape without elements (the reference keeps them in its instance tree with an infinite / NaN box and never
+    # hits them), in a rigid scene (LBVH: dropped) and in a non-rigid one (copy of the reference's tree: kept)
+    for sc in (synth.mixed_scene(31, reflective_floor=False), synth.nonrigid_scene(31, 5, 3)):
+        F = np.float32
+        sc.shapes.append(synth.Shape("void", 0, np.zeros((3, 3), F), np.tile(np.array([0, 0, 1], F), (3, 1)), np.zeros((0, 3), np.int32), "matte", np.zeros((3, 2), F)))
+        sc.instances.append(("void", len(sc.shapes) - 1, synth.translation_frame((0.5, 1.0, 0.5))))
+        sc.instances.insert(3, ("void2", len(sc.shapes) - 1, synth.translation_frame((-1.5, 0.3, 2.5))))
+        flat = sc.flat()
+        rids, rdist, _ = oracle_mod.OracleScene(flat).trace_primary(128, 72, 1)
+        with gpu.Scene(flat) as scn:
+            ids, dist, _ = scn.trace_primary(128, 72, 1)
+        assert id_match(ids, rids) >= ID_BAR
+        same = (ids == rids).all(axis=1)
+        assert np.array_equal(dist[same], rdist[same])
 
 
 def test_truncated_paths_are_reported_without_statistics(gpu, monkeypatch):

@@ -303,3 +303,27 @@ def test_nonrigid_frames_walk_the_reference_instance_tree(oracle_mod, monkeypatc
     ids2, _, _, _ = _emu.EmuScene(flat).trace_primary(w, h, 1)
     assert not np.array_equal(ids2, rids)
 
+
+@pytest.mark.parametrize("nonrigid", [False, True])
+def test_instances_of_an_empty_shape(oracle_mod, nonrigid):
+    """An instance whose shape has no elements: the reference keeps it in its instance tree with the world box of an invalid
+    bbox (src/scene.cpp:558-562, bbox_to_world of +-FLT_MAX corners: infinities and NaNs in the partition and in the node
+    boxes) and can never hit it.  Same frames with and without it on the device path — through the LBVH (which drops such
+    instances) and through the copy of the reference's tree (which keeps them, like the reference)."""
+    from yocto_raytracing_b200 import synth
+    sc = synth.nonrigid_scene(31, 5, 3) if nonrigid else synth.mixed_scene(31, reflective_floor=False)
+    F = np.float32
+    sc.shapes.append(synth.Shape("void", 0, np.zeros((3, 3), F), np.tile(np.array([0, 0, 1], F), (3, 1)), np.zeros((0, 3), np.int32), "matte", np.zeros((3, 2), F)))
+    sc.instances.append(("void", len(sc.shapes) - 1, synth.translation_frame((0.5, 1.0, 0.5))))
+    sc.instances.insert(3, ("void2", len(sc.shapes) - 1, synth.translation_frame((-1.5, 0.3, 2.5))))
+    flat = sc.flat()
+    assert (flat.nonrigid_instances() > 0) == nonrigid
+    w, h = 128, 72
+    o, e = oracle_mod.OracleScene(flat), _emu.EmuScene(flat)
+    rids, rdist, _ = o.trace_primary(w, h, 1)
+    ids, dist, _, _ = e.trace_primary(w, h, 1)
+    assert np.array_equal(ids, rids) and np.array_equal(dist, rdist)
+    rimg, _ = o.render(w, h, 2, 0.1, threads=4)
+    img, _ = e.render(w, h, 2, 0.1, max_depth=10 ** 6)
+    assert np.array_equal(img.view(np.uint32), rimg.view(np.uint32))
+
