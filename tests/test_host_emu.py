@@ -327,3 +327,28 @@ def test_instances_of_an_empty_shape(oracle_mod, nonrigid):
     img, _ = e.render(w, h, 2, 0.1, max_depth=10 ** 6)
     assert np.array_equal(img.view(np.uint32), rimg.view(np.uint32))
 
+
+def test_nonrigid_frames_in_a_large_instance_tree(oracle_mod):
+    """The instance10000-shaped scene with every seventh instance scaled and sheared (1 429 of 10 004 frames): the copy of the
+    reference's instance tree is 13 levels deep there and leaves hold up to four instances; every primary ray and every pixel
+    must still equal the oracle's."""
+    from yocto_raytracing_b200 import synth
+    sc = synth.instance_grid_scene(100)
+    rng = np.random.default_rng(3)
+    for k, (iname, si, fr) in enumerate(list(sc.instances)):
+        if k % 7 == 0 and k > 0 and not iname.startswith("light") and not iname.startswith("floor"):
+            f = np.array(fr, np.float32).reshape(4, 3).copy()
+            f[0] *= rng.uniform(0.6, 1.6); f[1] *= rng.uniform(0.6, 1.6); f[2] *= rng.uniform(0.6, 1.6)
+            f[0] += 0.2 * f[2]
+            sc.instances[k] = (iname, si, f.reshape(-1))
+    flat = sc.flat()
+    assert flat.nonrigid_instances() > 1000
+    w, h = 160, 90
+    o, e = oracle_mod.OracleScene(flat), _emu.EmuScene(flat)
+    rids, rdist, _ = o.trace_primary(w, h, 1)
+    ids, dist, _, ctr = e.trace_primary(w, h, 1)
+    assert np.array_equal(ids, rids) and np.array_equal(dist, rdist) and ctr[4] == 0
+    rimg, rc = o.render(w // 2, h // 2, 2, 0.1, threads=4)
+    img, rays = e.render(w // 2, h // 2, 2, 0.1, max_depth=10 ** 6)
+    assert np.array_equal(img.view(np.uint32), rimg.view(np.uint32)) and rays[2] == rc["shadow_rays"]
+
