@@ -352,3 +352,39 @@ def test_nonrigid_frames_in_a_large_instance_tree(oracle_mod):
     img, rays = e.render(w // 2, h // 2, 2, 0.1, max_depth=10 ** 6)
     assert np.array_equal(img.view(np.uint32), rimg.view(np.uint32)) and rays[2] == rc["shadow_rays"]
 
+
+def test_randomized_scenes_and_cameras_vs_oracle(oracle_mod):
+    """A sweep nobody hand-picked: 40 seeded scenes of every kind (mixed, non-rigid, instance grids, hair, untextured), random
+    cameras — inside the scene, looking straight down — with and without apex grids.  Per scene: closest-hit ids on >= 99.99 %
+    of the rays (bit-identical distances where the ids agree), no box culled that the reference would enter, float image
+    identical on >= 99.9 % of the pixels.  (A 150-scene run of the same loop found one differing pixel: seed 1047, an
+    exact-distance tie between two instances whose later-ranked candidate the reference's own tree culls before it is tested —
+    the residual DESIGN.md section 1 describes; it is part of this sweep.)"""
+    from yocto_raytracing_b200 import synth
+    total = mismatched = 0
+    for seed in list(range(1000, 1039)) + [1047]:
+        rng = np.random.RandomState(seed)
+        kind = seed % 5
+        if kind == 0: sc = synth.mixed_scene(seed, n_objects=int(rng.randint(1, 40)))
+        elif kind == 1: sc = synth.nonrigid_scene(seed, seed + 1, 1 + seed % 3, mirror_floor=bool(seed & 4))
+        elif kind == 2: sc = synth.instance_grid_scene(int(rng.randint(2, 16)), seed=seed)
+        elif kind == 3: sc = synth.hair_scene(int(rng.randint(8, 300)), seed=seed)
+        else: sc = synth.mixed_scene(seed, reflective_floor=False, textured=False)
+        eye = rng.uniform(-6, 6, 3); eye[1] = rng.uniform(0.05, 8)
+        tgt = rng.uniform(-2, 2, 3); tgt[1] = rng.uniform(0, 2)
+        if seed % 7 == 0: tgt = eye + np.array([0, -1.0, 0.0]) + 1e-3 * rng.normal(size=3)
+        sc.camera = synth.make_camera(tuple(eye), tuple(tgt), float(rng.uniform(0.2, 1.2)))
+        flat = sc.flat()
+        w, h = 80, 45
+        o, e = oracle_mod.OracleScene(flat), _emu.EmuScene(flat)
+        if seed % 2: _emu.set_grids(e, 16 << (seed % 3), 1 + seed % 4)
+        rids, rdist, _ = o.trace_primary(w, h, 2)
+        ids, dist, _, ctr = e.trace_primary(w, h, 2)
+        same = (ids == rids).all(axis=1)
+        assert same.mean() >= 0.9999 and np.array_equal(dist[same], rdist[same]) and ctr[4] == 0, seed
+        rimg, _ = o.render(w, h, 2, 0.1, threads=4, max_depth=40)
+        img, _ = e.render(w, h, 2, 0.1, max_depth=40)
+        assert (img == rimg).all(axis=2).mean() >= 0.999, seed
+        total += same.size; mismatched += int((~same).sum())
+    assert total == 40 * 80 * 45 * 4 and mismatched <= 3, mismatched      # (2 of 576 000 rays, both exact ties)
+
